@@ -1,0 +1,342 @@
+"""Pins the CPU oracle against every known-answer vector the reference's own tests hold for this
+path. Vectors are cited by reference file:line. Runs on CPU (`-m "not gpu"`)."""
+import numpy as np
+import pytest
+
+P = 0xFFFFFFFF00000001
+
+
+def naive_eval(p, x):
+    acc = 0
+    for c in reversed([int(v) for v in p]):
+        acc = (acc * x + c) % P
+    return acc
+
+
+# ---- field: math/src/field/f64/tests.rs ----
+def test_field_basics(oracle):
+    o = oracle
+    assert o.mul(P - 1, P - 1) == 1                      # tests.rs:54-74 (m-1)^2 = 1
+    assert o.mul(o.inv(2), 2) == 1
+    assert o.add(P - 1, 1) == 0 and o.sub(0, 1) == P - 1
+    assert o.inv(0) == 0
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        a, b = (int(v) % P for v in rng.integers(0, 2**64, size=2, dtype=np.uint64))
+        assert o.mul(a, b) == a * b % P
+        assert o.add(a, b) == (a + b) % P
+        assert o.sub(a, b) == (a - b) % P
+    assert o.exp(7, P - 1) == 1
+    # root of unity order (tests.rs get_root_of_unity): g^(2^32) = 1, g^(2^31) != 1
+    g = o.root_of_unity(32)
+    assert g == 7277203076849721926
+    assert o.exp(g, 1 << 32) == 1 and o.exp(g, 1 << 31) == P - 1
+    for k in range(1, 7):  # small roots are powers of two (used by the device kernels)
+        assert o.root_of_unity(k) == pow(2, 192 >> k, P) if k <= 6 else True
+
+
+def test_montgomery_view(oracle):
+    # f64/tests.rs:173-189: elements_as_bytes exposes Montgomery words x * 2^64 mod p
+    for x in (0, 1, 2, 7, P - 1, 123456789123456789):
+        m = oracle.to_mont(x)
+        assert m == (x << 64) % P
+        assert oracle.from_mont(m) == x
+
+
+def test_quad_mul_kats(oracle):
+    # f64/tests.rs:220-246
+    m = P
+    cases = [((3, 1), (4, 2), (8, 12)),
+             ((3, m - 1), (m - 3, 5), (1, 13)),
+             ((3, m - 1), (10, m - 2), (26, 18446744069414584307))]
+    for a, b, e in cases:
+        assert list(oracle.ext_mul(a, b)) == list(e)
+
+
+def test_cube_mul_kats(oracle):
+    # f64/tests.rs:288-345
+    cases = [((3, 5, 2), (320, 68, 3), (1111, 1961, 995)),
+             ((18446744069414584267, 18446744069414584309, 9223372034707292160),
+              (18446744069414584101, 420, 18446744069414584121),
+              (14070, 18446744069414566571, 5970)),
+             ((18446744069414584266, 18446744069412558094, 5268562),
+              (18446744069414583589, 1226, 5346),
+              (18446744065041672051, 25275910656, 21824696736))]
+    for a, b, e in cases:
+        assert list(oracle.ext_mul(a, b)) == list(e)
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_ext_inv(oracle, d):
+    a = oracle.rand_elems(d, 5)
+    one = np.zeros(d, dtype=np.uint64); one[0] = 1
+    assert list(oracle.ext_mul(a, oracle.ext_inv(a))) == list(one)
+    assert list(oracle.ext_inv(np.zeros(d, dtype=np.uint64))) == [0] * d
+
+
+# ---- fft: math/src/fft/tests.rs ----
+def test_twiddles(oracle):
+    # tests.rs:63-73: twiddles == bit-reversed power series of the n-th root
+    n = 32
+    g = oracle.root_of_unity(5)
+    tw = oracle.get_twiddles(n)
+    for i in range(n // 2):
+        j = int(format(i, "04b")[::-1], 2)
+        assert int(tw[j]) == pow(g, i, P)
+    itw = oracle.get_inv_twiddles(n)
+    for i in range(n // 2):
+        assert oracle.mul(int(tw[i]), int(itw[i])) == 1
+
+
+@pytest.mark.parametrize("n", [4, 8, 16, 1024])
+def test_fft_vs_naive(oracle, n):
+    # tests.rs:20-61: evaluate_poly == polynom::eval_many over the n-th roots; interpolate inverts it
+    p = oracle.rand_elems(n, n)
+    ev = oracle.evaluate_poly(p)
+    g = oracle.root_of_unity(n.bit_length() - 1)
+    pts = range(n) if n <= 16 else [0, 1, 5, n // 2, n - 1]
+    for i in pts:
+        assert int(ev[i]) == naive_eval(p, pow(g, i, P))
+    assert (oracle.interpolate_poly(ev) == p).all()
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+def test_fft_with_offset(oracle, d):
+    # fft/mod.rs doc-tests :144-167, :328-350
+    n, b = 16, 4
+    p = oracle.rand_elems(n * d, 3)
+    ev = oracle.evaluate_poly_with_offset(p, 7, b, d)
+    g = oracle.root_of_unity(6)
+    for comp in range(d):
+        pc = p[comp::d]
+        for i in (0, 1, 17, 63):
+            assert int(ev[i * d + comp]) == naive_eval(pc, 7 * pow(g, i, P) % P)
+    # interpolate_with_offset inverts evaluation over the shifted size-n domain
+    ev1 = oracle.evaluate_poly_with_offset(p, 7, 1, d)
+    assert (oracle.interpolate_poly_with_offset(ev1, 7, d) == p).all()
+
+
+def test_lde_matrix_vs_naive(oracle):
+    # prover/src/matrix/tests.rs:15-42: f64, 64 columns, n=256, blowup 8, row-major == naive eval
+    n, c, b = 256, 64, 8
+    polys = oracle.rand_elems((c, n), 42)
+    lde = oracle.lde_rows(polys, b)
+    assert lde.shape == (n * b, c)
+    g = oracle.root_of_unity(11)
+    for row in (0, 1, 7, 8, 1000, n * b - 1):
+        x = 7 * pow(g, row, P) % P
+        for col in (0, 1, 7, 8, 33, 63):
+            assert int(lde[row, col]) == naive_eval(polys[col], x)
+    # every column equals evaluate_poly_with_offset of that column
+    for col in (0, 13, 63):
+        assert (lde[:, col] == oracle.evaluate_poly_with_offset(polys[col], 7, b)).all()
+
+
+def test_trace_lde_reinterpolates(oracle):
+    # prover/src/trace/trace_lde/default/tests.rs:22-72: interpolate trace -> polys evaluate to the
+    # Fibonacci trace; LDE of the polys re-interpolates to the same polys
+    n, b = 64, 8
+    tr = np.zeros((2, n), dtype=np.uint64)
+    a0, a1 = 1, 1
+    for i in range(n):
+        tr[0, i], tr[1, i] = a0, a1
+        a0 = (a0 + a1) % P
+        a1 = (a1 + a0) % P
+    polys = oracle.interpolate_columns(tr)
+    g = oracle.root_of_unity(6)
+    for i in (0, 1, 2, 63):
+        assert naive_eval(polys[0], pow(g, i, P)) == int(tr[0, i])
+        assert naive_eval(polys[1], pow(g, i, P)) == int(tr[1, i])
+    lde = oracle.lde_rows(polys, b)
+    for col in range(2):
+        back = oracle.interpolate_poly_with_offset(np.ascontiguousarray(lde[:, col]), 7)
+        assert (back[:n] == polys[col]).all() and not back[n:].any()
+    # commitment == MerkleTree(hash_elements(rows)) (tests.rs:74-106)
+    dg = oracle.hash_rows(oracle.BLAKE3, lde)
+    assert dg[5].tobytes() == oracle.hash_elements(oracle.BLAKE3, lde[5])
+
+
+# ---- hashers ----
+def test_blake3_vs_spec(oracle):
+    import blake3 as b3
+    rng = np.random.default_rng(7)
+    for ln in (0, 1, 31, 32, 40, 63, 64, 65, 127, 128, 512, 1023, 1024, 1025, 2048, 2049, 3072, 4097, 8192 + 17):
+        data = rng.integers(0, 256, size=ln, dtype=np.uint8).tobytes()
+        assert oracle.blake3(data) == b3.blake3(data).digest(), ln
+
+
+def test_blake3_hasher_semantics(oracle):
+    import blake3 as b3
+    e = oracle.rand_elems(9, 11)
+    # blake/mod.rs:52-65: canonical LE bytes, no length prefix
+    assert oracle.hash_elements(oracle.BLAKE3, e) == b3.blake3(e.astype("<u8").tobytes()).digest()
+    a, b = bytes(range(32)), bytes(range(32, 64))
+    assert oracle.merge(oracle.BLAKE3, a, b) == b3.blake3(a + b).digest()          # :33
+    assert oracle.merge_with_int(oracle.BLAKE3, a, 2**63 + 5) == b3.blake3(a + (2**63 + 5).to_bytes(8, "little")).digest()  # :41
+
+
+def test_rp64_permutation_kat(oracle):
+    # crypto/src/hash/rescue/rp64_256/tests.rs:69-105 (Sage reference vector)
+    expected = [11084501481526603421, 6291559951628160880, 13626645864671311919, 18397438323058963117,
+                7443014167353970324, 17930833023906771425, 4275355080008025761, 7676681476902901785,
+                3460534574143792217, 11912731278641497187, 8104899243369883110, 674509706691634438]
+    assert [int(v) for v in oracle.rp64_permute(np.arange(12, dtype=np.uint64))] == expected
+
+
+def test_rp64_consistency(oracle):
+    # rp64_256/tests.rs:107-159
+    R = oracle.RP64
+    e = oracle.rand_elems(8, 21)
+    m = oracle.merge(R, e[:4].tobytes(), e[4:].tobytes())
+    assert m == oracle.hash_elements(R, e)
+    assert m == oracle.merge_many(R, e.tobytes())
+    seed = oracle.rand_elems(4, 22)
+    v = int(oracle.rand_elems(1, 23)[0])
+    assert oracle.merge_with_int(R, seed.tobytes(), v) == oracle.hash_elements(R, np.array([int(x) for x in seed] + [v], dtype=np.uint64))
+    v = P + 2
+    assert oracle.merge_with_int(R, seed.tobytes(), v) == oracle.hash_elements(R, np.array([int(x) for x in seed] + [v % P, 1], dtype=np.uint64))
+
+
+# ---- Merkle: crypto/src/merkle/tests.rs:14-84 ----
+LEAVES4 = [
+    [166, 168, 47, 140, 153, 86, 156, 86, 226, 229, 149, 76, 70, 132, 209, 109, 166, 193, 113, 197, 42, 116, 170, 144, 74, 104, 29, 110, 220, 49, 224, 123],
+    [243, 57, 40, 140, 185, 79, 188, 229, 232, 117, 143, 118, 235, 229, 73, 251, 163, 246, 151, 170, 14, 243, 255, 127, 175, 230, 94, 227, 214, 5, 89, 105],
+    [11, 33, 220, 93, 26, 67, 166, 154, 93, 7, 115, 130, 70, 13, 166, 45, 120, 233, 175, 86, 144, 110, 253, 250, 67, 108, 214, 115, 24, 132, 45, 234],
+    [47, 173, 224, 232, 30, 46, 197, 186, 215, 15, 134, 211, 73, 14, 34, 216, 6, 11, 217, 150, 90, 242, 8, 31, 73, 85, 150, 254, 229, 244, 23, 231],
+]
+LEAVES8 = [
+    [115, 29, 176, 48, 97, 18, 34, 142, 51, 18, 164, 235, 236, 96, 113, 132, 189, 26, 70, 93, 101, 143, 142, 52, 252, 33, 80, 157, 194, 52, 209, 129],
+    [52, 46, 37, 214, 24, 248, 121, 199, 229, 25, 171, 67, 65, 37, 98, 142, 182, 72, 202, 42, 223, 160, 136, 60, 38, 255, 222, 82, 26, 27, 130, 203],
+    [130, 43, 231, 0, 59, 228, 152, 140, 18, 33, 87, 27, 49, 190, 44, 82, 188, 155, 163, 108, 166, 198, 106, 143, 83, 167, 201, 152, 106, 176, 242, 119],
+    [207, 158, 56, 143, 28, 146, 238, 47, 169, 32, 166, 97, 163, 238, 171, 243, 33, 209, 120, 219, 17, 182, 96, 136, 13, 90, 6, 27, 247, 242, 49, 111],
+    [179, 64, 123, 119, 226, 139, 161, 127, 36, 251, 218, 88, 20, 217, 212, 85, 112, 85, 185, 193, 230, 181, 4, 22, 54, 219, 135, 98, 235, 180, 182, 7],
+    [101, 240, 19, 44, 43, 213, 31, 138, 39, 26, 82, 147, 255, 96, 234, 51, 105, 6, 233, 144, 255, 187, 242, 3, 157, 246, 55, 175, 98, 121, 92, 175],
+    [25, 96, 149, 179, 94, 8, 170, 214, 169, 135, 12, 212, 224, 157, 182, 127, 233, 93, 151, 214, 36, 183, 156, 212, 233, 152, 125, 244, 146, 161, 75, 128],
+    [247, 43, 130, 141, 234, 172, 61, 187, 109, 31, 56, 30, 14, 232, 92, 158, 48, 161, 108, 234, 170, 180, 233, 77, 200, 248, 45, 152, 125, 11, 1, 171],
+]
+
+
+def _h2(a, b):
+    import blake3 as b3
+    return b3.blake3(a + b).digest()
+
+
+def test_merkle_fixtures(oracle):
+    l4 = np.array(LEAVES4, dtype=np.uint8)
+    n4 = oracle.merkle_nodes(oracle.BLAKE3, l4)
+    L = [bytes(r) for r in l4]
+    assert n4[1].tobytes() == _h2(_h2(L[0], L[1]), _h2(L[2], L[3]))
+    assert not n4[0].any()
+    l8 = np.array(LEAVES8, dtype=np.uint8)
+    n8 = oracle.merkle_nodes(oracle.BLAKE3, l8)
+    L = [bytes(r) for r in l8]
+    root = _h2(_h2(_h2(L[0], L[1]), _h2(L[2], L[3])), _h2(_h2(L[4], L[5]), _h2(L[6], L[7])))
+    assert n8[1].tobytes() == root
+    assert n8[4].tobytes() == _h2(L[0], L[1]) and n8[7].tobytes() == _h2(L[6], L[7])
+
+
+def _parse_batch_proof(buf):
+    depth, nvec = buf[0], buf[1] >> 1   # small vint64 values: one byte, (v<<1)|1
+    pos, vecs = 2, []
+    for _ in range(nvec):
+        ln = buf[pos] >> 1; pos += 1
+        vecs.append([buf[pos + 32 * i: pos + 32 * i + 32] for i in range(ln)]); pos += 32 * ln
+    assert pos == len(buf)
+    return depth, vecs
+
+
+def test_merkle_prove_batch_fixtures(oracle):
+    # merkle/tests.rs:140-186
+    l8 = np.array(LEAVES8, dtype=np.uint8)
+    n8 = oracle.merkle_nodes(oracle.BLAKE3, l8)
+    L = [bytes(r) for r in l8]
+    lv, pr = oracle.merkle_prove_batch(l8, n8, [1])
+    depth, vecs = _parse_batch_proof(pr)
+    assert depth == 3 and lv[0].tobytes() == L[1]
+    assert vecs == [[L[0], _h2(L[2], L[3]), _h2(_h2(L[4], L[5]), _h2(L[6], L[7]))]]
+    lv, pr = oracle.merkle_prove_batch(l8, n8, [1, 2])
+    depth, vecs = _parse_batch_proof(pr)
+    assert [x.tobytes() for x in lv] == [L[1], L[2]]
+    assert vecs == [[L[0], _h2(_h2(L[4], L[5]), _h2(L[6], L[7]))], [L[3]]]
+    lv, pr = oracle.merkle_prove_batch(l8, n8, [1, 6])
+    depth, vecs = _parse_batch_proof(pr)
+    assert vecs == [[L[0], _h2(L[2], L[3])], [L[7], _h2(L[4], L[5])]]
+    lv, pr = oracle.merkle_prove_batch(l8, n8, list(range(8)))
+    depth, vecs = _parse_batch_proof(pr)
+    assert vecs == [[], [], [], []] and [x.tobytes() for x in lv] == L
+    with pytest.raises(ValueError):
+        oracle.merkle_prove_batch(l8, n8, [1, 1])
+
+
+# ---- FRI ----
+def test_transpose_and_fold_positions(oracle):
+    # utils/core/src/lib.rs:158-165; fri/src/folding/mod.rs:129-136
+    assert list(oracle.transpose_slice(np.arange(8), 2)) == [0, 4, 1, 5, 2, 6, 3, 7]
+    assert list(oracle.fold_positions([1, 9, 12, 20], 32, 4)) == [1, 4]
+
+
+@pytest.mark.parametrize("nf", [2, 4, 8])
+@pytest.mark.parametrize("d", [1, 3])
+def test_drp_equals_coefficient_folding(oracle, nf, d):
+    # fri/src/folding/mod.rs:46-85 (doc-test for N=2; same identity for any N: folded poly has
+    # coefficients sum_k alpha^k * poly[N*i + k], evaluated over the domain offset^N * w_{n/N}^i)
+    n = 64
+    poly = oracle.rand_elems(n // 8 * d, 31)
+    poly_full = np.concatenate([poly, np.zeros((n - n // 8) * d, dtype=np.uint64)])
+    ev = oracle.evaluate_poly_with_offset(poly_full, 7, 1, d)
+    alpha = oracle.rand_elems(d, 32)
+    got = oracle.apply_drp(oracle.transpose_slice(ev, nf, d), nf, 7, alpha, d)
+    # coefficient-form folding
+    m = n // nf
+    folded = np.zeros(m * d, dtype=np.uint64)
+    for i in range(m):
+        acc = np.zeros(d, dtype=np.uint64)
+        ak = np.zeros(d, dtype=np.uint64); ak[0] = 1
+        for k in range(nf):
+            c = poly_full[(nf * i + k) * d:(nf * i + k + 1) * d]
+            cd = np.zeros(d, dtype=np.uint64); cd[:] = c
+            t = oracle.ext_mul(ak, cd) if d > 1 else np.array([oracle.mul(int(ak[0]), int(cd[0]))], dtype=np.uint64)
+            acc = np.array([oracle.add(int(x), int(y)) for x, y in zip(acc, t)], dtype=np.uint64)
+            ak = oracle.ext_mul(ak, alpha) if d > 1 else np.array([oracle.mul(int(ak[0]), int(alpha[0]))], dtype=np.uint64)
+        folded[i * d:(i + 1) * d] = acc
+    want = oracle.evaluate_poly_with_offset(folded, pow(7, nf, P), 1, d)
+    assert (got == want).all()
+
+
+def test_fri_layers_shape(oracle):
+    # fri/src/options.rs:85-93 + prover/mod.rs:179-239
+    assert oracle.fri_num_layers(2**19, 8, 31, 8) == 4      # cfg1: 2^19 -> 2^16 -> 2^13 -> 2^10 -> 2^7
+    n, b = 2**10, 8
+    poly = np.concatenate([oracle.rand_elems(n // b, 5), np.zeros(n - n // b, dtype=np.uint64)])
+    ev = oracle.evaluate_poly_with_offset(poly, 7, 1)
+    roots, rem, alphas = oracle.fri_build_layers(oracle.BLAKE3, ev, 4, 7, b)
+    assert roots.shape[0] == 3 and rem.size == 8 and alphas.size == 2   # 1024 -> 256 -> 64 (= 8*8)
+    # the remainder is a degree < 8 polynomial: re-evaluating it over the last domain reproduces
+    # the twice-folded codeword
+    t = ev
+    for a in alphas:
+        t = oracle.apply_drp(oracle.transpose_slice(t, 4), 4, 7, [a])
+    back = oracle.interpolate_poly_with_offset(t, 7)
+    assert (back[:8][::-1] == rem).all() and not back[8:].any()
+
+
+def test_random_coin(oracle):
+    import blake3 as b3
+    c = oracle.RandomCoin(oracle.BLAKE3, [1, 2, 3])
+    seed = b3.blake3(np.array([1, 2, 3], dtype="<u8").tobytes()).digest()
+    assert c.seed == seed
+    # draw: merge_with_int(seed, ++counter), first 8 bytes LE, rejected if >= p (default.rs:156-170)
+    cnt, want = 0, None
+    while want is None:
+        cnt += 1
+        v = int.from_bytes(b3.blake3(seed + cnt.to_bytes(8, "little")).digest()[:8], "little")
+        if v < P:
+            want = v
+    assert int(c.draw(1)[0]) == want
+    c.reseed(bytes(32))
+    assert c.seed == b3.blake3(seed + bytes(32)).digest()
+    lz = c.leading_zeros(5)
+    head = int.from_bytes(b3.blake3(c.seed + (5).to_bytes(8, "little")).digest()[:8], "little")
+    assert lz == (head & -head).bit_length() - 1
+    ints = c.draw_integers(20, 1024, 77)
+    assert len(ints) == 20 and all(int(v) < 1024 for v in ints)
