@@ -1,0 +1,156 @@
+/* winterfell_b200.h — C ABI of the B200-native STARK proving hot path.
+ *
+ * Drop-in boundary for facebook/winterfell v0.13.1 (reference paths relative to /root/reference):
+ * the library sits behind the four plug-in traits the reference's `Prover` selects through
+ * associated types (prover/src/lib.rs:125-158): `TraceLde` (prover/src/trace/trace_lde/mod.rs:26-76),
+ * `ConstraintEvaluator` (prover/src/constraints/evaluator/mod.rs:28-42), `ConstraintCommitment`
+ * (prover/src/constraints/commitment/mod.rs:24-37) and `VectorCommitment`
+ * (crypto/src/commitment.rs:28-86), plus the concrete FriProver (fri/src/prover/mod.rs:100-300)
+ * that a GPU prover replaces by overriding `Prover::generate_proof` (prover/src/lib.rs:282).
+ * INTEGRATION.md shows the Rust shim (`impl TraceLde for GpuTraceLde` ...) binding every entry
+ * point below.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns WF_OK (0) or a negative error code and
+ *    records a message retrievable with wf_last_error(). The Rust traits are infallible
+ *    (they panic on misuse, e.g. trace_lde/default/mod.rs:150-158): the shim turns non-zero into panic!.
+ *  - field elements are 64-bit words. `mont` flags say whether a HOST buffer holds the reference's
+ *    in-memory Montgomery words (x * 2^64 mod p — what a Rust `&[BaseElement]` reinterpreted as
+ *    `*const u64` exposes, math/src/field/f64/mod.rs:57-64,212-217) or canonical values in [0, p).
+ *    Device buffers are always canonical. Digests are 32 bytes (Blake3_256 bytes, or the four
+ *    canonical LE words of an Rp64_256 digest, rescue/rp64_256/digest.rs:36-45).
+ *  - one wf_ctx per prover object / per GPU; calls on one ctx are issued on its CUDA stream in
+ *    program order and are not re-entrant (the reference calls the factories sequentially from
+ *    the proving thread, prover/src/lib.rs:282-492).
+ *  - there is NO CPU fallback: every entry point fails with WF_ERR_CUDA when no sm_100 device is
+ *    usable.
+ */
+#ifndef WINTERFELL_B200_H
+#define WINTERFELL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WF_OK 0
+#define WF_ERR_CUDA (-1)
+#define WF_ERR_INVALID (-2)
+#define WF_ERR_UNSUPPORTED (-3)
+#define WF_ERR_STATE (-4)
+
+#define WF_HASH_BLAKE3_256 0 /* crypto/src/hash/blake/mod.rs:21 */
+#define WF_HASH_RP64_256 1   /* crypto/src/hash/rescue/rp64_256/mod.rs:118 */
+
+typedef struct wf_ctx wf_ctx;
+typedef struct wf_mat wf_mat;   /* device matrix of base-field columns (segment layout) */
+typedef struct wf_tree wf_tree; /* device Merkle tree: leaves + nodes (crypto/src/merkle/mod.rs:86-98) */
+typedef struct wf_fri wf_fri;   /* FRI prover state (fri/src/prover/mod.rs:100-116) */
+
+/* ---- context ---------------------------------------------------------------------------------- */
+/* `stream` is a cudaStream_t (NULL = legacy default stream). */
+int wf_ctx_create(wf_ctx** out, int device, void* stream);
+void wf_ctx_destroy(wf_ctx* ctx);
+const char* wf_last_error(const wf_ctx* ctx);
+int wf_ctx_sync(wf_ctx* ctx);
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
+uint64_t wf_ctx_launch_count(const wf_ctx* ctx);
+const char* wf_version(void);
+
+/* ---- matrices --------------------------------------------------------------------------------- */
+/* ColMatrix<E> (prover/src/matrix/col_matrix.rs:33): `ncols` host columns of `nrows` elements of
+ * extension degree `ext_degree`; becomes ncols*ext_degree base columns on the device. */
+int wf_mat_from_host_columns(wf_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, size_t nrows,
+                             int ext_degree, int mont, wf_mat** out);
+/* same, from a DEVICE buffer laid out column-major [ncols][nrows] (base columns, canonical) */
+int wf_mat_from_device_columns(wf_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, size_t nrows, wf_mat** out);
+int wf_mat_free(wf_ctx* ctx, wf_mat* m);
+size_t wf_mat_rows(const wf_mat* m);
+uint32_t wf_mat_cols(const wf_mat* m);
+/* copy out as column-major [cols][rows] or row-major [rows][cols]; dst is host (to_host=1) or device */
+int wf_mat_to_columns(wf_ctx* ctx, const wf_mat* m, uint64_t* dst, int to_host, int mont);
+int wf_mat_to_rows(wf_ctx* ctx, const wf_mat* m, uint64_t* dst, int to_host, int mont);
+/* rows at `positions` (k x cols words, canonical unless mont) -> host; TraceLde::query values
+ * (trace_lde/default/mod.rs:199-230, build_segment_queries :284-297) */
+int wf_mat_read_rows(wf_ctx* ctx, const wf_mat* m, const uint64_t* positions, size_t k, uint64_t* dst, int mont);
+
+/* ColMatrix::interpolate_columns (col_matrix.rs:192-202): evaluations over the size-n subgroup
+ * -> coefficients. n = rows must be a power of two >= 2. */
+int wf_mat_interpolate(wf_ctx* ctx, const wf_mat* evals, wf_mat** polys);
+/* fft::evaluate_poly per column (math/src/fft/mod.rs:85): coefficients -> evaluations, natural order */
+int wf_mat_evaluate(wf_ctx* ctx, const wf_mat* polys, wf_mat** evals);
+/* RowMatrix::evaluate_polys_over::<8> (row_matrix.rs:84-100): LDE over the coset 7 * <w_N>,
+ * N = n << log_blowup, row i <-> point 7 * w_N^i (natural order). */
+int wf_mat_lde(wf_ctx* ctx, const wf_mat* polys, uint32_t log_blowup, wf_mat** lde);
+/* fft::interpolate_poly_with_offset per column (math/src/fft/mod.rs:351) */
+int wf_mat_interpolate_with_offset(wf_ctx* ctx, const wf_mat* evals, uint64_t domain_offset, wf_mat** polys);
+
+/* ---- commitments ------------------------------------------------------------------------------ */
+/* RowMatrix::commit_to_rows (row_matrix.rs:184-228) with partition_size == num_cols, then
+ * MerkleTree::new (crypto/src/merkle/mod.rs:116-135). */
+int wf_commit_rows(wf_ctx* ctx, int hash_id, const wf_mat* m, wf_tree** out);
+/* MerkleTree::new from host/device leaf digests (VectorCommitment::new, crypto/src/commitment.rs:41) */
+int wf_tree_from_leaves(wf_ctx* ctx, int hash_id, const uint8_t* leaves, size_t nleaves, int leaves_on_device,
+                        wf_tree** out);
+int wf_tree_free(wf_ctx* ctx, wf_tree* t);
+int wf_tree_root(wf_ctx* ctx, const wf_tree* t, uint8_t root[32]); /* VectorCommitment::commitment */
+size_t wf_tree_num_leaves(const wf_tree* t);
+/* copies leaves (nleaves*32 B) and nodes (nleaves*32 B) to host: MerkleTree::from_raw_parts inputs
+ * (crypto/src/merkle/mod.rs:148) */
+int wf_tree_to_host(wf_ctx* ctx, const wf_tree* t, uint8_t* leaves, uint8_t* nodes);
+/* VectorCommitment::open_many = MerkleTree::prove_batch (merkle/mod.rs:217-272): writes the k leaf
+ * digests (in the order of `positions`) and the serialized BatchMerkleProof (proofs.rs:390-401).
+ * *proof_len: in = capacity, out = bytes written. */
+int wf_tree_open_many(wf_ctx* ctx, const wf_tree* t, const uint64_t* positions, size_t k, uint8_t* leaves_out,
+                      uint8_t* proof, size_t* proof_len);
+
+/* ---- FRI (fri/src/prover/mod.rs) --------------------------------------------------------------- */
+/* FriProver::new + build_layers (:179-239) over `len` evaluations of extension degree d held in
+ * device matrix `evals` (d base columns, len rows), domain offset 7.
+ * The transcript is the caller's: after each layer the library calls `commit(user, root32)` and
+ * then `draw_alpha(user, alpha_out[d])` (ProverChannel::commit_fri_layer / draw_fri_alpha,
+ * fri/src/prover/channel.rs:20-27); after the remainder it calls commit(user, remainder_hash). */
+typedef void (*wf_fri_commit_fn)(void* user, const uint8_t root[32]);
+typedef void (*wf_fri_draw_fn)(void* user, uint64_t* alpha_out);
+int wf_fri_build_layers(wf_ctx* ctx, int hash_id, const wf_mat* evals, int ext_degree, uint32_t folding_factor,
+                        uint32_t remainder_max_degree, uint32_t blowup, wf_fri_commit_fn commit,
+                        wf_fri_draw_fn draw_alpha, void* user, wf_fri** out);
+/* same, with the library's own DefaultProverChannel-style coin seeded with hash_elements([])
+ * (fri/src/prover/channel.rs:60-72); roots_out receives (num_layers + 1) x 32 bytes. */
+int wf_fri_build_layers_default_channel(wf_ctx* ctx, int hash_id, const wf_mat* evals, int ext_degree,
+                                        uint32_t folding_factor, uint32_t remainder_max_degree, uint32_t blowup,
+                                        uint8_t* roots_out, size_t roots_cap, wf_fri** out);
+uint32_t wf_fri_num_layers(const wf_fri* f);
+/* remainder polynomial, reversed coefficients (fri/src/prover/mod.rs:230-239); returns element count */
+size_t wf_fri_remainder(const wf_fri* f, uint64_t* coeffs, size_t cap_words);
+/* FriProver::build_proof (:254-296) serialized as FriProof (fri/src/proof.rs): *len in=cap, out=bytes */
+int wf_fri_build_proof(wf_ctx* ctx, wf_fri* f, const uint64_t* positions, size_t k, uint8_t* out, size_t* len);
+int wf_fri_free(wf_ctx* ctx, wf_fri* f);
+
+/* ---- plain kernels on caller-owned DEVICE buffers (unit parity + bench legs) ------------------- */
+/* in-place NTT (inverse=0) / iNTT (inverse=1) of `cols` columns, column-major [cols][n], n = 1 << log_n */
+int wf_ntt_dev(wf_ctx* ctx, uint64_t* d_data, uint32_t log_n, uint32_t cols, int inverse);
+/* leaf digests of a row-major [nrows][cols] device matrix */
+int wf_hash_rows_dev(wf_ctx* ctx, int hash_id, const uint64_t* d_rows, size_t nrows, uint32_t cols, uint8_t* d_digests);
+/* Merkle nodes (nleaves x 32 B, nodes[0] = 0, nodes[1] = root) from device leaf digests */
+int wf_merkle_dev(wf_ctx* ctx, int hash_id, const uint8_t* d_leaves, size_t nleaves, uint8_t* d_nodes);
+/* one FRI fold: d_evals [len][d] -> d_next [len/folding][d]; alpha = d host words */
+int wf_fri_fold_dev(wf_ctx* ctx, const uint64_t* d_evals, size_t len, int ext_degree, uint32_t folding_factor,
+                    const uint64_t* alpha, uint64_t* d_next);
+
+/* ---- host-side helpers of the product (transcript arithmetic; no GPU needed) ------------------- */
+/* H::hash_elements / merge / merge_with_int on the host (crypto/src/hash/mod.rs:31-64) */
+int wf_host_hash_elements(int hash_id, const uint64_t* elems, size_t n, uint8_t out[32]);
+int wf_host_merge(int hash_id, const uint8_t two[64], uint8_t out[32]);
+int wf_host_merge_with_int(int hash_id, const uint8_t seed[32], uint64_t value, uint8_t out[32]);
+uint64_t wf_host_mul(uint64_t a, uint64_t b);           /* canonical Goldilocks product */
+uint64_t wf_host_mul_2exp(uint64_t x, uint32_t k);      /* x * 2^k mod p, k <= 96 (kernel twiddle path) */
+uint64_t wf_host_mont_to_canonical(uint64_t m);
+uint64_t wf_host_canonical_to_mont(uint64_t x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WINTERFELL_B200_H */

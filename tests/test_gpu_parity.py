@@ -1,0 +1,191 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs — bit-exact (integer arithmetic mod p, bytes of digests)."""
+import numpy as np
+import pytest
+
+import winterfell_b200 as wf
+
+pytestmark = pytest.mark.gpu
+P = wf.P
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = wf.Context(0)
+    yield c
+    c.close()
+
+
+def naive_eval(p, x):
+    acc = 0
+    for c in reversed([int(v) for v in p]):
+        acc = (acc * x + c) % P
+    return acc
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 5, 8, 10, 11, 12, 13, 16])
+@pytest.mark.parametrize("cols", [1, 2, 3, 8, 11])
+def test_ntt_intt_vs_oracle(ctx, oracle, log_n, cols):
+    n = 1 << log_n
+    x = oracle.rand_elems((cols, n), 1000 * log_n + cols)
+    m = ctx.mat_from_host_columns(x)
+    assert (m.to_columns() == x).all() and (m.to_rows() == x.T).all()
+    ev = m.evaluate()
+    got = ev.to_columns()
+    for c in range(cols):
+        assert (got[c] == oracle.evaluate_poly(x[c])).all(), (log_n, c)
+    back = ev.interpolate()
+    assert (back.to_columns() == x).all()
+    it = m.interpolate().to_columns()
+    assert (it[0] == oracle.interpolate_poly(x[0])).all()
+    for h in (m, ev, back):
+        h.free()
+
+
+def test_ntt_small_vs_naive(ctx, oracle):
+    # math/src/fft/tests.rs:20-61 on the device path
+    for n in (4, 8, 16):
+        p = oracle.rand_elems((1, n), n)
+        ev = ctx.mat_from_host_columns(p).evaluate().to_columns()[0]
+        g = oracle.root_of_unity(n.bit_length() - 1)
+        for i in range(n):
+            assert int(ev[i]) == naive_eval(p[0], pow(g, i, P))
+
+
+def test_montgomery_abi(ctx, oracle):
+    # host buffers in the reference's in-memory form (f64/mod.rs:57-64): x * 2^64 mod p
+    x = oracle.rand_elems((3, 64), 9)
+    xm = np.array([[oracle.to_mont(int(v)) for v in row] for row in x], dtype=np.uint64)
+    m = ctx.mat_from_host_columns(xm, mont=True)
+    assert (m.to_columns() == x).all()
+    assert (m.to_columns(mont=True) == xm).all()
+    assert (m.read_rows([5, 0, 63], mont=True) == xm.T[[5, 0, 63]]).all()
+
+
+@pytest.mark.parametrize("log_n,cols,log_b", [(3, 2, 3), (8, 64, 3), (10, 8, 3), (11, 5, 2), (12, 8, 3), (13, 3, 1), (14, 16, 3), (16, 2, 3)])
+def test_lde_vs_oracle(ctx, oracle, log_n, cols, log_b):
+    # prover/src/matrix/tests.rs:15-42 (64 cols, n=256, blowup 8) and other shapes
+    n = 1 << log_n
+    polys = oracle.rand_elems((cols, n), 77 + log_n)
+    want = oracle.lde_rows(polys, 1 << log_b)
+    m = ctx.mat_from_host_columns(polys)
+    lde = m.lde(log_b)
+    assert (lde.to_rows() == want).all()
+    pos = [0, 1, (n << log_b) - 1, 12345 % (n << log_b)]
+    assert (lde.read_rows(pos) == want[pos]).all()
+    m.free(); lde.free()
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_lde_extension_columns(ctx, oracle, d):
+    # ColMatrix<E> with E = quadratic / cubic extension: d base columns per column
+    n, c, b = 256, 3, 8
+    polys = oracle.rand_elems((c, n * d), 5 + d)
+    want = oracle.lde_rows(polys, b, d)
+    m = ctx.mat_from_host_columns(polys, ext_degree=d)
+    assert m.cols == c * d
+    assert (m.lde(3).to_rows() == want).all()
+
+
+def test_interpolate_with_offset(ctx, oracle):
+    n = 1 << 12
+    ev = oracle.rand_elems((2, n), 4)
+    got = ctx.mat_from_host_columns(ev).interpolate_with_offset(7).to_columns()
+    for c in range(2):
+        assert (got[c] == oracle.interpolate_poly_with_offset(ev[c], 7)).all()
+
+
+@pytest.mark.parametrize("h", [wf.HASH_BLAKE3_256, wf.HASH_RP64_256])
+@pytest.mark.parametrize("cols", [1, 2, 3, 4, 7, 8, 9, 16, 24, 64, 130])
+def test_row_hash_and_merkle_vs_oracle(ctx, oracle, h, cols):
+    rows = 256 if h == wf.HASH_RP64_256 else 1024
+    x = oracle.rand_elems((cols, rows), 31 * cols + h)
+    m = ctx.mat_from_host_columns(x)
+    t = ctx.commit_rows(h, m)
+    lv, nd = t.to_host()
+    want_lv = oracle.hash_rows(h, np.ascontiguousarray(x.T))
+    assert (lv == want_lv).all()
+    want_nd = oracle.merkle_nodes(h, want_lv)
+    assert (nd == want_nd).all()
+    assert t.root() == want_nd[1].tobytes()
+    # batch openings (crypto/src/merkle/mod.rs:217-272)
+    for pos in ([1], [1, 2], [1, 6], [3, 4, 5], [0, 7, 100, 101, rows - 1], list(range(8))):
+        glv, gpr = t.open_many(pos)
+        wlv, wpr = oracle.merkle_prove_batch(want_lv, want_nd, pos)
+        assert (glv == wlv).all() and gpr == wpr
+    m.free(); t.free()
+
+
+@pytest.mark.parametrize("nleaves", [2, 4, 8, 256, 512, 1024, 4096])
+def test_merkle_small_trees(ctx, oracle, nleaves):
+    rng = np.random.default_rng(nleaves)
+    leaves = rng.integers(0, 256, size=(nleaves, 32), dtype=np.uint8)
+    t = ctx.tree_from_leaves(wf.HASH_BLAKE3_256, leaves)
+    lv, nd = t.to_host()
+    assert (nd == oracle.merkle_nodes(oracle.BLAKE3, leaves)).all()
+
+
+def test_merkle_reference_fixture(ctx):
+    # crypto/src/merkle/tests.rs:14-84 (LEAVES8): root == nested hash_2x1
+    import blake3 as b3
+    from test_oracle_kats import LEAVES8
+    l8 = np.array(LEAVES8, dtype=np.uint8)
+    L = [bytes(r) for r in l8]
+    h2 = lambda a, b: b3.blake3(a + b).digest()
+    root = h2(h2(h2(L[0], L[1]), h2(L[2], L[3])), h2(h2(L[4], L[5]), h2(L[6], L[7])))
+    assert ctx.tree_from_leaves(wf.HASH_BLAKE3_256, l8).root() == root
+
+
+@pytest.mark.parametrize("h", [wf.HASH_BLAKE3_256, wf.HASH_RP64_256])
+@pytest.mark.parametrize("d,nf,log_len", [(1, 4, 12), (1, 2, 10), (1, 8, 12), (1, 16, 12), (2, 4, 10), (3, 4, 12), (3, 8, 9)])
+def test_fri_layers_vs_oracle(ctx, oracle, h, d, nf, log_len):
+    # fri/src/prover/tests.rs round trip shape: commit phase roots and remainder
+    L, b = 1 << log_len, 8
+    poly = np.concatenate([oracle.rand_elems(L // b * d, 3 + d), np.zeros((L - L // b) * d, dtype=np.uint64)])
+    ev = oracle.evaluate_poly_with_offset(poly, 7, 1, d)
+    want_roots, want_rem, alphas = oracle.fri_build_layers(h, ev, nf, 7, b, d)
+    cols = np.ascontiguousarray(ev.reshape(L, d).T)     # d base columns
+    m = ctx.mat_from_host_columns(cols)
+    f, roots = ctx.fri_build_layers_default(h, m, d, nf, 7, b)
+    assert (roots == want_roots).all()
+    assert (f.remainder() == want_rem).all()
+    f.free(); m.free()
+
+
+def test_fri_fold_dev_vs_oracle(ctx, oracle):
+    import torch
+    for d, nf in ((1, 4), (3, 4), (1, 8), (2, 2)):
+        L = 1 << 12
+        ev = oracle.rand_elems(L * d, 11 * d + nf)
+        alpha = oracle.rand_elems(d, 5)
+        want = oracle.apply_drp(oracle.transpose_slice(ev, nf, d), nf, 7, alpha, d)
+        t_in = torch.from_numpy(ev.view(np.int64)).cuda()
+        t_out = torch.empty(L // nf * d, dtype=torch.int64, device="cuda")
+        ctx.fri_fold_dev(t_in.data_ptr(), L, d, nf, alpha, t_out.data_ptr())
+        ctx.sync()
+        assert (t_out.cpu().numpy().view(np.uint64) == want).all()
+
+
+def test_plain_dev_kernels(ctx, oracle):
+    import torch
+    n, c = 1 << 13, 5
+    x = oracle.rand_elems((c, n), 8)
+    t = torch.from_numpy(x.view(np.int64)).cuda()
+    ctx.ntt_dev(t.data_ptr(), 13, c, False)
+    ctx.sync()
+    got = t.cpu().numpy().view(np.uint64)
+    for j in range(c):
+        assert (got[j] == oracle.evaluate_poly(x[j])).all()
+    ctx.ntt_dev(t.data_ptr(), 13, c, True)
+    ctx.sync()
+    assert (t.cpu().numpy().view(np.uint64) == x).all()
+    rows = np.ascontiguousarray(x.T)
+    tr = torch.from_numpy(rows.view(np.int64)).cuda()
+    dg = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    nd = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    ctx.hash_rows_dev(wf.HASH_BLAKE3_256, tr.data_ptr(), n, c, dg.data_ptr())
+    ctx.merkle_dev(wf.HASH_BLAKE3_256, dg.data_ptr(), n, nd.data_ptr())
+    ctx.sync()
+    want = oracle.hash_rows(oracle.BLAKE3, rows)
+    assert (dg.cpu().numpy().reshape(n, 32) == want).all()
+    assert (nd.cpu().numpy().reshape(n, 32) == oracle.merkle_nodes(oracle.BLAKE3, want)).all()

@@ -1,0 +1,333 @@
+"""winterfell_b200 — ctypes binding of the B200-native STARK proving hot path.
+
+The product is the C-ABI shared library `libwinterfell_b200.so` (include/winterfell_b200.h) built
+from winterfell_b200/csrc/*.cu for sm_100a. This module only loads it and wraps the entry points
+for the tests and bench.py; it contains no arithmetic and no CPU fallback: if the library is not
+built, or no CUDA device is present, creating a Context raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwinterfell_b200.so")
+
+P = 0xFFFFFFFF00000001
+HASH_BLAKE3_256 = 0
+HASH_RP64_256 = 1
+
+WF_OK = 0
+
+u64p = C.POINTER(C.c_uint64)
+u8p = C.POINTER(C.c_uint8)
+vp = C.c_void_p
+
+FRI_COMMIT_FN = C.CFUNCTYPE(None, C.c_void_p, u8p)
+FRI_DRAW_FN = C.CFUNCTYPE(None, C.c_void_p, u64p)
+
+_lib = None
+
+# every symbol include/winterfell_b200.h declares: (name, restype, argtypes)
+_SIGS = [
+    ("wf_ctx_create", C.c_int, [C.POINTER(vp), C.c_int, vp]),
+    ("wf_ctx_destroy", None, [vp]),
+    ("wf_last_error", C.c_char_p, [vp]),
+    ("wf_ctx_sync", C.c_int, [vp]),
+    ("wf_ctx_launch_count", C.c_uint64, [vp]),
+    ("wf_version", C.c_char_p, []),
+    ("wf_mat_from_host_columns", C.c_int, [vp, C.POINTER(u64p), C.c_uint32, C.c_size_t, C.c_int, C.c_int, C.POINTER(vp)]),
+    ("wf_mat_from_device_columns", C.c_int, [vp, vp, C.c_uint32, C.c_size_t, C.POINTER(vp)]),
+    ("wf_mat_free", C.c_int, [vp, vp]),
+    ("wf_mat_rows", C.c_size_t, [vp]),
+    ("wf_mat_cols", C.c_uint32, [vp]),
+    ("wf_mat_to_columns", C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
+    ("wf_mat_to_rows", C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
+    ("wf_mat_read_rows", C.c_int, [vp, vp, u64p, C.c_size_t, u64p, C.c_int]),
+    ("wf_mat_interpolate", C.c_int, [vp, vp, C.POINTER(vp)]),
+    ("wf_mat_evaluate", C.c_int, [vp, vp, C.POINTER(vp)]),
+    ("wf_mat_lde", C.c_int, [vp, vp, C.c_uint32, C.POINTER(vp)]),
+    ("wf_mat_interpolate_with_offset", C.c_int, [vp, vp, C.c_uint64, C.POINTER(vp)]),
+    ("wf_commit_rows", C.c_int, [vp, C.c_int, vp, C.POINTER(vp)]),
+    ("wf_tree_from_leaves", C.c_int, [vp, C.c_int, vp, C.c_size_t, C.c_int, C.POINTER(vp)]),
+    ("wf_tree_free", C.c_int, [vp, vp]),
+    ("wf_tree_root", C.c_int, [vp, vp, u8p]),
+    ("wf_tree_num_leaves", C.c_size_t, [vp]),
+    ("wf_tree_to_host", C.c_int, [vp, vp, u8p, u8p]),
+    ("wf_tree_open_many", C.c_int, [vp, vp, u64p, C.c_size_t, u8p, u8p, C.POINTER(C.c_size_t)]),
+    ("wf_fri_build_layers", C.c_int, [vp, C.c_int, vp, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, FRI_COMMIT_FN, FRI_DRAW_FN, vp, C.POINTER(vp)]),
+    ("wf_fri_build_layers_default_channel", C.c_int, [vp, C.c_int, vp, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, u8p, C.c_size_t, C.POINTER(vp)]),
+    ("wf_fri_num_layers", C.c_uint32, [vp]),
+    ("wf_fri_remainder", C.c_size_t, [vp, u64p, C.c_size_t]),
+    ("wf_fri_build_proof", C.c_int, [vp, vp, u64p, C.c_size_t, u8p, C.POINTER(C.c_size_t)]),
+    ("wf_fri_free", C.c_int, [vp, vp]),
+    ("wf_ntt_dev", C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_int]),
+    ("wf_hash_rows_dev", C.c_int, [vp, C.c_int, vp, C.c_size_t, C.c_uint32, vp]),
+    ("wf_merkle_dev", C.c_int, [vp, C.c_int, vp, C.c_size_t, vp]),
+    ("wf_fri_fold_dev", C.c_int, [vp, vp, C.c_size_t, C.c_int, C.c_uint32, u64p, vp]),
+    ("wf_host_hash_elements", C.c_int, [C.c_int, u64p, C.c_size_t, u8p]),
+    ("wf_host_merge", C.c_int, [C.c_int, u8p, u8p]),
+    ("wf_host_merge_with_int", C.c_int, [C.c_int, u8p, C.c_uint64, u8p]),
+    ("wf_host_mul", C.c_uint64, [C.c_uint64, C.c_uint64]),
+    ("wf_host_mul_2exp", C.c_uint64, [C.c_uint64, C.c_uint32]),
+    ("wf_host_mont_to_canonical", C.c_uint64, [C.c_uint64]),
+    ("wf_host_canonical_to_mont", C.c_uint64, [C.c_uint64]),
+]
+
+
+def declared_symbols():
+    return [s[0] for s in _SIGS]
+
+
+def lib():
+    """Load the C-ABI library. Fails loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with winterfell_b200/build.sh "
+                "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in _SIGS:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class WfError(RuntimeError):
+    pass
+
+
+def _u64(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a, a.ctypes.data_as(u64p)
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a, a.ctypes.data_as(u8p)
+
+
+class Context:
+    """One prover context per GPU (wf_ctx). `stream` is a raw cudaStream_t integer (0 = default)."""
+
+    def __init__(self, device=0, stream=0):
+        self.L = lib()
+        h = vp()
+        r = self.L.wf_ctx_create(C.byref(h), device, vp(stream))
+        if r != WF_OK:
+            raise WfError(f"wf_ctx_create failed ({r}): no usable CUDA device — this library has no CPU path")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.wf_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, r):
+        if r != WF_OK:
+            raise WfError(f"error {r}: {self.L.wf_last_error(self.h).decode()}")
+
+    def sync(self):
+        self.check(self.L.wf_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return self.L.wf_ctx_launch_count(self.h)
+
+    # ---- matrices ----
+    def mat_from_host_columns(self, cols, ext_degree=1, mont=False):
+        """cols: [c, n*d] uint64 array (ColMatrix<E>: c columns of n elements of degree d)."""
+        a = np.ascontiguousarray(cols, dtype=np.uint64)
+        c = a.shape[0]
+        n = a.shape[1] // ext_degree
+        ptrs = (u64p * c)(*[a[j].ctypes.data_as(u64p) for j in range(c)])
+        h = vp()
+        self.check(self.L.wf_mat_from_host_columns(self.h, ptrs, c, n, ext_degree, int(mont), C.byref(h)))
+        return Mat(self, h)
+
+    def mat_from_device_columns(self, dptr, ncols, nrows):
+        h = vp()
+        self.check(self.L.wf_mat_from_device_columns(self.h, vp(dptr), ncols, nrows, C.byref(h)))
+        return Mat(self, h)
+
+    def commit_rows(self, hash_id, mat):
+        h = vp()
+        self.check(self.L.wf_commit_rows(self.h, hash_id, mat.h, C.byref(h)))
+        return Tree(self, h)
+
+    def tree_from_leaves(self, hash_id, leaves):
+        l_, lp = _u8(leaves)
+        h = vp()
+        self.check(self.L.wf_tree_from_leaves(self.h, hash_id, C.cast(lp, vp), l_.size // 32, 0, C.byref(h)))
+        return Tree(self, h)
+
+    def fri_build_layers_default(self, hash_id, mat, ext_degree, folding, rem_max_deg, blowup):
+        roots = np.zeros((64, 32), dtype=np.uint8)
+        h = vp()
+        self.check(self.L.wf_fri_build_layers_default_channel(self.h, hash_id, mat.h, ext_degree, folding, rem_max_deg,
+                                                              blowup, roots.ctypes.data_as(u8p), roots.size, C.byref(h)))
+        f = Fri(self, h, ext_degree)
+        return f, roots[: f.num_layers + 1].copy()
+
+    # ---- plain device kernels (raw device pointers as integers) ----
+    def ntt_dev(self, dptr, log_n, cols, inverse=False):
+        self.check(self.L.wf_ntt_dev(self.h, vp(dptr), log_n, cols, int(inverse)))
+
+    def hash_rows_dev(self, hash_id, d_rows, nrows, cols, d_digests):
+        self.check(self.L.wf_hash_rows_dev(self.h, hash_id, vp(d_rows), nrows, cols, vp(d_digests)))
+
+    def merkle_dev(self, hash_id, d_leaves, nleaves, d_nodes):
+        self.check(self.L.wf_merkle_dev(self.h, hash_id, vp(d_leaves), nleaves, vp(d_nodes)))
+
+    def fri_fold_dev(self, d_evals, length, ext_degree, folding, alpha, d_next):
+        a_, ap = _u64(alpha)
+        self.check(self.L.wf_fri_fold_dev(self.h, vp(d_evals), length, ext_degree, folding, ap, vp(d_next)))
+
+
+class Mat:
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def free(self):
+        if self.h:
+            self.ctx.L.wf_mat_free(self.ctx.h, self.h)
+            self.h = None
+
+    @property
+    def rows(self):
+        return self.ctx.L.wf_mat_rows(self.h)
+
+    @property
+    def cols(self):
+        return self.ctx.L.wf_mat_cols(self.h)
+
+    def to_columns(self, mont=False):
+        o = np.zeros((self.cols, self.rows), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.wf_mat_to_columns(self.ctx.h, self.h, vp(o.ctypes.data), 1, int(mont)))
+        return o
+
+    def to_rows(self, mont=False):
+        o = np.zeros((self.rows, self.cols), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.wf_mat_to_rows(self.ctx.h, self.h, vp(o.ctypes.data), 1, int(mont)))
+        return o
+
+    def to_device_rows(self, dptr):
+        self.ctx.check(self.ctx.L.wf_mat_to_rows(self.ctx.h, self.h, vp(dptr), 0, 0))
+
+    def read_rows(self, positions, mont=False):
+        p_, pp = _u64(positions)
+        o = np.zeros((p_.size, self.cols), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.wf_mat_read_rows(self.ctx.h, self.h, pp, p_.size, o.ctypes.data_as(u64p), int(mont)))
+        return o
+
+    def _unary(self, fn, *extra):
+        h = vp()
+        self.ctx.check(fn(self.ctx.h, self.h, *extra, C.byref(h)))
+        return Mat(self.ctx, h)
+
+    def interpolate(self):
+        return self._unary(self.ctx.L.wf_mat_interpolate)
+
+    def evaluate(self):
+        return self._unary(self.ctx.L.wf_mat_evaluate)
+
+    def lde(self, log_blowup):
+        return self._unary(self.ctx.L.wf_mat_lde, log_blowup)
+
+    def interpolate_with_offset(self, offset):
+        return self._unary(self.ctx.L.wf_mat_interpolate_with_offset, offset)
+
+
+class Tree:
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def free(self):
+        if self.h:
+            self.ctx.L.wf_tree_free(self.ctx.h, self.h)
+            self.h = None
+
+    @property
+    def num_leaves(self):
+        return self.ctx.L.wf_tree_num_leaves(self.h)
+
+    def root(self):
+        o = np.zeros(32, dtype=np.uint8)
+        self.ctx.check(self.ctx.L.wf_tree_root(self.ctx.h, self.h, o.ctypes.data_as(u8p)))
+        return o.tobytes()
+
+    def to_host(self):
+        n = self.num_leaves
+        lv = np.zeros((n, 32), dtype=np.uint8)
+        nd = np.zeros((n, 32), dtype=np.uint8)
+        self.ctx.check(self.ctx.L.wf_tree_to_host(self.ctx.h, self.h, lv.ctypes.data_as(u8p), nd.ctypes.data_as(u8p)))
+        return lv, nd
+
+    def open_many(self, positions):
+        p_, pp = _u64(positions)
+        k = p_.size
+        lv = np.zeros((k, 32), dtype=np.uint8)
+        cap = 64 + k * 40 * 33
+        buf = np.zeros(cap, dtype=np.uint8)
+        ln = C.c_size_t(cap)
+        self.ctx.check(self.ctx.L.wf_tree_open_many(self.ctx.h, self.h, pp, k, lv.ctypes.data_as(u8p),
+                                                    buf.ctypes.data_as(u8p), C.byref(ln)))
+        return lv, buf[: ln.value].tobytes()
+
+
+class Fri:
+    def __init__(self, ctx, h, d):
+        self.ctx, self.h, self.d = ctx, h, d
+
+    def free(self):
+        if self.h:
+            self.ctx.L.wf_fri_free(self.ctx.h, self.h)
+            self.h = None
+
+    @property
+    def num_layers(self):
+        return self.ctx.L.wf_fri_num_layers(self.h)
+
+    def remainder(self):
+        buf = np.zeros(4096, dtype=np.uint64)
+        n = self.ctx.L.wf_fri_remainder(self.h, buf.ctypes.data_as(u64p), buf.size)
+        return buf[: n * self.d].copy()
+
+    def build_proof(self, positions):
+        p_, pp = _u64(positions)
+        cap = 1 << 22
+        buf = np.zeros(cap, dtype=np.uint8)
+        ln = C.c_size_t(cap)
+        self.ctx.check(self.ctx.L.wf_fri_build_proof(self.ctx.h, self.h, pp, p_.size, buf.ctypes.data_as(u8p), C.byref(ln)))
+        return buf[: ln.value].tobytes()
+
+
+# ---- host helpers (usable without a GPU) ----
+def host_hash_elements(hash_id, elems):
+    e_, ep = _u64(np.asarray(elems, dtype=np.uint64).reshape(-1))
+    o = np.zeros(32, dtype=np.uint8)
+    lib().wf_host_hash_elements(hash_id, ep, e_.size, o.ctypes.data_as(u8p))
+    return o.tobytes()
+
+
+def host_merge(hash_id, a, b):
+    t_, tp = _u8(np.frombuffer(a + b, dtype=np.uint8))
+    o = np.zeros(32, dtype=np.uint8)
+    lib().wf_host_merge(hash_id, tp, o.ctypes.data_as(u8p))
+    return o.tobytes()
+
+
+def host_merge_with_int(hash_id, seed, value):
+    t_, tp = _u8(np.frombuffer(seed, dtype=np.uint8))
+    o = np.zeros(32, dtype=np.uint8)
+    lib().wf_host_merge_with_int(hash_id, tp, value, o.ctypes.data_as(u8p))
+    return o.tobytes()

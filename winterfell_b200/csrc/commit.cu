@@ -1,0 +1,229 @@
+// commit.cu — row hashing and Merkle tree construction on device (K3 / K4 in SURVEY.md §2.1).
+//
+// Replaces RowMatrix::commit_to_rows (prover/src/matrix/row_matrix.rs:184-228): digest_i =
+// H::hash_elements(row_i) over the first `cols` base elements of row i, as canonical LE bytes for
+// Blake3_256 (crypto/src/hash/blake/mod.rs:52-65) or as a sponge for Rp64_256
+// (crypto/src/hash/rescue/rp64_256/mod.rs:224-257); and MerkleTree::new / build_merkle_nodes
+// (crypto/src/merkle/mod.rs:116-135, :344-368): nodes[n/2 + i] = merge(leaf 2i, leaf 2i+1),
+// nodes[i] = merge(nodes[2i], nodes[2i+1]), nodes[1] = root, nodes[0] = zeros.
+//
+// One hash per thread: BLAKE3's 7 rounds run entirely in registers (blake3.cuh); a warp of 32 rows
+// reads 32 consecutive 64-byte segment rows = 2 KB contiguous per segment.
+#include "commit.cuh"
+
+#include "blake3.cuh"
+#include "rp64.cuh"
+
+// ---- row access in segment layout -----------------------------------------------------------
+struct RowSrc {
+    const u64* base;
+    size_t seg_stride;
+    int W, logW;
+    u32 cols;
+};
+__device__ __forceinline__ u64 row_elem(const RowSrc& m, size_t row, u32 e) {
+    return m.base[(size_t)(e >> m.logW) * m.seg_stride + row * m.W + (e & (m.W - 1))];
+}
+
+// BLAKE3 of `cols` elements (cols*8 bytes) of one row. Handles any length: chunks of 1024 bytes
+// (128 elements) merged through a small chaining-value stack.
+__device__ void blake3_row(const RowSrc& m, size_t row, u32 out[8]) {
+    const u32 cols = m.cols;
+    const u32 nchunks = cols <= 128 ? 1 : (cols + 127) / 128;
+    u32 stack[5][8];
+    int sp = 0;
+    u32 cv[8];
+    for (u32 c = 0; c < nchunks; c++) {
+        u32 e0 = c * 128, e1 = min(cols, e0 + 128);
+        u32 nblk = e1 == e0 ? 1 : (e1 - e0 + 7) / 8;
+        b3_iv(cv);
+        for (u32 b = 0; b < nblk; b++) {
+            u32 msg[16];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                u32 e = e0 + b * 8 + k;
+                u64 v = e < e1 ? row_elem(m, row, e) : 0;
+                msg[2 * k] = (u32)v;
+                msg[2 * k + 1] = (u32)(v >> 32);
+            }
+            u32 bl = min(64u, (e1 - e0 - b * 8) * 8);
+            u32 fl = (b == 0 ? B3_CHUNK_START : 0) |
+                     (b == nblk - 1 ? (B3_CHUNK_END | (nchunks == 1 ? B3_ROOT : 0)) : 0);
+            b3_compress(cv, msg, c, bl, fl);
+        }
+        if (c == nchunks - 1) break;
+        u32 total = c + 1;
+        while ((total & 1) == 0) {
+            u32 msg[16];
+            --sp;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { msg[k] = stack[sp][k]; msg[8 + k] = cv[k]; }
+            b3_iv(cv);
+            b3_compress(cv, msg, 0, 64, B3_PARENT);
+            total >>= 1;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) stack[sp][k] = cv[k];
+        sp++;
+    }
+    while (sp > 0) {
+        u32 msg[16];
+        --sp;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { msg[k] = stack[sp][k]; msg[8 + k] = cv[k]; }
+        b3_iv(cv);
+        b3_compress(cv, msg, 0, 64, B3_PARENT | (sp == 0 ? B3_ROOT : 0));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) out[k] = cv[k];
+}
+
+// fast path: one 8-column segment row == exactly one 64-byte BLAKE3 block
+__global__ void __launch_bounds__(256) hash_rows_blake3_w8c8_kernel(const u64* __restrict__ base, size_t nrows,
+                                                                    uint4* __restrict__ digests) {
+    size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    const uint4* src = reinterpret_cast<const uint4*>(base + row * 8);
+    u32 msg[16];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint4 v = __ldg(src + k);
+        msg[4 * k] = v.x; msg[4 * k + 1] = v.y; msg[4 * k + 2] = v.z; msg[4 * k + 3] = v.w;
+    }
+    u32 cv[8];
+    b3_hash64(msg, cv);
+    digests[2 * row] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    digests[2 * row + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+
+__global__ void __launch_bounds__(256) hash_rows_blake3_kernel(RowSrc m, size_t nrows, uint4* __restrict__ digests) {
+    size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    u32 cv[8];
+    blake3_row(m, row, cv);
+    digests[2 * row] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    digests[2 * row + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+
+__global__ void __launch_bounds__(128) hash_rows_rp64_kernel(RowSrc m, size_t nrows, u64* __restrict__ digests) {
+    size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    s[0] = m.cols;
+    u32 i = 0;
+    for (u32 e = 0; e < m.cols; e++) {  // rp64_256/mod.rs:237-246
+        s[4 + i] = gl_add(s[4 + i], row_elem(m, row, e));
+        if (++i == 8) { rp64_permute(s); i = 0; }
+    }
+    if (i > 0) rp64_permute(s);
+#pragma unroll
+    for (int k = 0; k < 4; k++) digests[row * 4 + k] = s[4 + k];
+}
+
+// ---- Merkle levels ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) merkle_level_blake3_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+                                                                  size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    u32 msg[16];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint4 v = __ldg(in + 4 * i + k);
+        msg[4 * k] = v.x; msg[4 * k + 1] = v.y; msg[4 * k + 2] = v.z; msg[4 * k + 3] = v.w;
+    }
+    u32 cv[8];
+    b3_hash64(msg, cv);
+    out[2 * i] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    out[2 * i + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+__global__ void __launch_bounds__(128) merkle_level_rp64_kernel(const u64* __restrict__ in, u64* __restrict__ out,
+                                                                size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    u64 v[8], o[4];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = in[8 * i + k];
+    rp64_merge(v, o);
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[4 * i + k] = o[k];
+}
+
+// the last levels (count <= 256 parents) in one block: nodes[count..2count) -> ... -> nodes[1]
+__global__ void __launch_bounds__(256) merkle_top_kernel(int hash_id, u64* nodes, u32 count) {
+    // `count` = number of nodes on the level to compute first; its children are already in place at
+    // nodes[2*count .. 4*count)
+    for (u32 m = count; m >= 1; m >>= 1) {
+        u32 i = threadIdx.x;
+        if (i < m) {
+            if (hash_id == WF_HASH_BLAKE3_256) {
+                const u32* src = reinterpret_cast<const u32*>(nodes + (size_t)(2 * (m + i)) * 4);
+                u32 msg[16], cv[8];
+#pragma unroll
+                for (int k = 0; k < 16; k++) msg[k] = src[k];
+                b3_hash64(msg, cv);
+                u32* dst = reinterpret_cast<u32*>(nodes + (size_t)(m + i) * 4);
+#pragma unroll
+                for (int k = 0; k < 8; k++) dst[k] = cv[k];
+            } else {
+                u64 v[8], o[4];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = nodes[(size_t)(2 * (m + i)) * 4 + k];
+                rp64_merge(v, o);
+#pragma unroll
+                for (int k = 0; k < 4; k++) nodes[(size_t)(m + i) * 4 + k] = o[k];
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) nodes[threadIdx.x] = 0;  // nodes[0] = default digest (merkle/mod.rs:349)
+}
+
+cudaError_t commit_hash_rows(int hash_id, const SegMatrix& m, u64* digests, cudaStream_t st) {
+    if (m.rows == 0) return cudaSuccess;
+    RowSrc src;
+    src.base = m.base; src.seg_stride = m.seg_stride; src.W = m.W; src.cols = m.cols;
+    src.logW = m.W == 8 ? 3 : m.W == 4 ? 2 : m.W == 2 ? 1 : 0;
+    if (hash_id == WF_HASH_BLAKE3_256) {
+        unsigned blocks = (unsigned)((m.rows + 255) / 256);
+        if (m.W == 8 && m.cols == 8)
+            hash_rows_blake3_w8c8_kernel<<<blocks, 256, 0, st>>>(m.base, m.rows, reinterpret_cast<uint4*>(digests));
+        else
+            hash_rows_blake3_kernel<<<blocks, 256, 0, st>>>(src, m.rows, reinterpret_cast<uint4*>(digests));
+    } else {
+        unsigned blocks = (unsigned)((m.rows + 127) / 128);
+        hash_rows_rp64_kernel<<<blocks, 128, 0, st>>>(src, m.rows, digests);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t commit_merkle_nodes(int hash_id, const u64* leaves, size_t nleaves, u64* nodes, cudaStream_t st) {
+    // nodes: nleaves digests (4 words each)
+    if (nleaves < 2) return cudaErrorInvalidValue;
+    size_t m = nleaves / 2;         // parents of leaf pairs live at nodes[m .. 2m)
+    const u64* src = leaves;
+    while (m > 256) {
+        u64* dst = nodes + m * 4;
+        if (hash_id == WF_HASH_BLAKE3_256) {
+            merkle_level_blake3_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(
+                reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), m);
+        } else {
+            merkle_level_rp64_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(src, dst, m);
+        }
+        src = dst;
+        m >>= 1;
+    }
+    // remaining levels in one block. If the leaf level itself is small, compute its parents first.
+    if (src == leaves) {
+        u64* dst = nodes + m * 4;
+        if (hash_id == WF_HASH_BLAKE3_256)
+            merkle_level_blake3_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const uint4*>(src),
+                                                          reinterpret_cast<uint4*>(dst), m);
+        else
+            merkle_level_rp64_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(src, dst, m);
+        m >>= 1;
+    }
+    merkle_top_kernel<<<1, 256, 0, st>>>(hash_id, nodes, (u32)m);
+    return cudaGetLastError();
+}

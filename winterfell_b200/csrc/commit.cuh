@@ -1,0 +1,27 @@
+// commit.cuh — segment-layout matrix descriptor + row hashing / Merkle entry points (commit.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "gl64.cuh"
+
+#define WF_HASH_BLAKE3_256 0
+#define WF_HASH_RP64_256 1
+
+// rows x cols base-field matrix in segment layout (see ntt.cuh):
+// elem(row, col) = base[(col / W) * seg_stride + row * W + col % W]
+struct SegMatrix {
+    u64* base;
+    size_t rows;
+    u32 cols;
+    int W;
+    size_t seg_stride;  // words; >= rows * W
+    u32 nseg() const { return (cols + W - 1) / W; }
+    size_t words() const { return (size_t)nseg() * seg_stride; }
+};
+
+static inline int seg_width_for(u32 cols) { return cols >= 8 ? 8 : cols > 2 ? 4 : cols == 2 ? 2 : 1; }
+
+// digests: rows x 4 words (32 bytes each)
+cudaError_t commit_hash_rows(int hash_id, const SegMatrix& m, u64* digests, cudaStream_t st);
+// nodes: nleaves x 4 words; nodes[0] = 0, nodes[1] = root
+cudaError_t commit_merkle_nodes(int hash_id, const u64* leaves, size_t nleaves, u64* nodes, cudaStream_t st);

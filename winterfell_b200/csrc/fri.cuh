@@ -1,0 +1,17 @@
+// fri.cuh — FRI layer leaf hashing and degree-respecting projection on device (fri.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "gl64.cuh"
+
+// Layer evaluations: `len` extension elements of degree d in natural order, element i at
+// evals[i * ld + 0..d) (ld >= d words per element).
+// Leaf i (i < len/nf) = hash_elements([v[i], v[i + m], ..., v[i + (nf-1) m]]), m = len / nf
+// (utils/core/src/lib.rs:166-185 transpose_slice + fri/src/prover/mod.rs:321-336).
+cudaError_t fri_hash_layer(int hash_id, const u64* evals, size_t len, int d, int ld, int nf, u64* digests,
+                           cudaStream_t st);
+// next[i] = apply_drp(row i) (fri/src/folding/mod.rs:86-118) with domain offset 7:
+// size-nf inverse DFT of the row, coefficient k scaled by (7 w_len^i)^-k / nf, evaluated at alpha.
+// inv_master: w_len^i for i < len/2 (forward root; negative powers are taken through the index).
+cudaError_t fri_fold_layer(const u64* evals, size_t len, int d, int ld, int nf, const u64* alpha,
+                           const u64* master, u64* next, int next_ld, cudaStream_t st);

@@ -1,0 +1,201 @@
+// gl64.cuh — Goldilocks field p = 2^64 - 2^32 + 1 and its quadratic / cubic extensions, for
+// sm_100a device code and for the host-side transcript code of the product.
+//
+// Semantics follow winter-math (reference math/src/field/f64/mod.rs): add :319, sub :339, mul :357,
+// inv :157, GENERATOR = 7 :251, TWO_ADIC_ROOT_OF_UNITY :267, ext2 (x^2 - x + 2) :401-435,
+// ext3 (x^3 - x - 1) :443-499. The reference stores Montgomery words (x * 2^64 mod p); the device
+// works on CANONICAL words in [0, p) because the Goldilocks reduction 2^64 = 2^32 - 1, 2^96 = -1
+// needs no Montgomery factor and every hash input must be canonical anyway (blake/mod.rs:52-65).
+// Conversion helpers for Montgomery-form buffers crossing the C ABI are gl_from_mont / gl_to_mont.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define GL_HD __host__ __device__ __forceinline__
+#else
+#define GL_HD inline
+#endif
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef uint8_t u8;
+
+#define GL_P 0xffffffff00000001ULL
+#define GL_EPS 0xffffffffULL
+#define GL_GENERATOR 7ULL
+#define GL_TWO_ADIC_ROOT 7277203076849721926ULL
+
+GL_HD u64 gl_add(u64 a, u64 b) {
+    u64 r = a + b;
+    // a, b < p: a + b < 2p; wrapped (carry) or >= p  =>  subtract p (== add 2^32 - 1 mod 2^64)
+    if (r < a || r >= GL_P) r += GL_EPS;
+    return r;
+}
+GL_HD u64 gl_sub(u64 a, u64 b) {
+    u64 r = a - b;
+    if (a < b) r -= GL_EPS;  // + p == - (2^32 - 1) mod 2^64
+    return r;
+}
+GL_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }
+GL_HD u64 gl_dbl(u64 a) { return gl_add(a, a); }
+
+// lo + 2^64 * hi  mod p, canonical result
+GL_HD u64 gl_reduce128(u64 lo, u64 hi) {
+    u64 hh = hi >> 32, hl = hi & GL_EPS;
+    u64 t = lo - hh;
+    if (lo < hh) t -= GL_EPS;
+    u64 m = (hl << 32) - hl;  // hl * (2^32 - 1)
+    u64 r = t + m;
+    if (r < m) r += GL_EPS;
+    if (r >= GL_P) r -= GL_P;
+    return r;
+}
+GL_HD u64 gl_mul(u64 a, u64 b) {
+#ifdef __CUDA_ARCH__
+    return gl_reduce128(a * b, __umul64hi(a, b));
+#else
+    unsigned __int128 x = (unsigned __int128)a * b;
+    return gl_reduce128((u64)x, (u64)(x >> 64));
+#endif
+}
+GL_HD u64 gl_sqr(u64 a) { return gl_mul(a, a); }
+
+// x * 2^k mod p for a compile-time k in [0, 96]: the twiddles of DFTs of size <= 64 are powers
+// of two (w_64 = 8, w_32 = 64, w_16 = 2^12, w_8 = 2^24, w_4 = 2^48, w_2 = 2^96 = -1), so the inner
+// butterflies of the radix-8/16 NTT rounds need no 64x64 multiplier.
+template <int K>
+GL_HD u64 gl_mul_2exp(u64 x) {
+    if (K == 0) return x;
+    if (K < 64) return gl_reduce128(x << (K & 63), x >> ((64 - K) & 63));
+    if (K == 96) return gl_neg(x);
+    // 64 <= K < 96: x * 2^K = (x << (K - 64)) * 2^64; let y = x << (K-64) = yl + 2^64 yh (yh < 2^32)
+    // => yl * 2^64 + yh * 2^128, and 2^128 = -2^32 (mod p).
+    u64 yl = x << ((K - 64) & 63), yh = (K == 64) ? 0 : (x >> ((128 - K) & 63));
+    u64 r = gl_reduce128(0, yl);
+    return gl_sub(r, gl_reduce128(yh << 32, 0));
+}
+
+GL_HD u64 gl_pow(u64 a, u64 e) {
+    u64 r = 1;
+    while (e) {
+        if (e & 1) r = gl_mul(r, a);
+        a = gl_mul(a, a);
+        e >>= 1;
+    }
+    return r;
+}
+GL_HD u64 gl_inv(u64 a) { return a ? gl_pow(a, GL_P - 2) : 0; }  // inv(0) = 0 as in f64/mod.rs:157
+GL_HD u64 gl_root_of_unity(u32 log_n) { return gl_pow(GL_TWO_ADIC_ROOT, 1ULL << (32 - log_n)); }
+// Montgomery words (x * 2^64 mod p, f64/mod.rs:57-83) <-> canonical: (2^64)^-1 = 18446744065119617025,
+// 2^64 = 2^32 - 1 (mod p).
+GL_HD u64 gl_from_mont(u64 m) { return gl_mul(m, 18446744065119617025ULL); }
+GL_HD u64 gl_to_mont(u64 x) { return gl_mul(x, GL_EPS); }
+
+// ---------------------------------------------------------------------------------------------
+// Extension elements: D consecutive base elements (extensions/cubic.rs:117-121).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct GlExt {
+    u64 v[D];
+};
+
+template <int D>
+GL_HD GlExt<D> ext_zero() {
+    GlExt<D> r;
+#pragma unroll
+    for (int i = 0; i < D; i++) r.v[i] = 0;
+    return r;
+}
+template <int D>
+GL_HD GlExt<D> ext_from_base(u64 b) {
+    GlExt<D> r = ext_zero<D>();
+    r.v[0] = b;
+    return r;
+}
+template <int D>
+GL_HD GlExt<D> ext_add(const GlExt<D>& a, const GlExt<D>& b) {
+    GlExt<D> r;
+#pragma unroll
+    for (int i = 0; i < D; i++) r.v[i] = gl_add(a.v[i], b.v[i]);
+    return r;
+}
+template <int D>
+GL_HD GlExt<D> ext_sub(const GlExt<D>& a, const GlExt<D>& b) {
+    GlExt<D> r;
+#pragma unroll
+    for (int i = 0; i < D; i++) r.v[i] = gl_sub(a.v[i], b.v[i]);
+    return r;
+}
+template <int D>
+GL_HD GlExt<D> ext_mul_base(const GlExt<D>& a, u64 b) {
+    GlExt<D> r;
+#pragma unroll
+    for (int i = 0; i < D; i++) r.v[i] = gl_mul(a.v[i], b);
+    return r;
+}
+GL_HD GlExt<1> ext_mul(const GlExt<1>& a, const GlExt<1>& b) {
+    GlExt<1> r;
+    r.v[0] = gl_mul(a.v[0], b.v[0]);
+    return r;
+}
+GL_HD GlExt<2> ext_mul(const GlExt<2>& a, const GlExt<2>& b) {  // f64/mod.rs:403-409
+    GlExt<2> r;
+    u64 a0b0 = gl_mul(a.v[0], b.v[0]);
+    r.v[0] = gl_sub(a0b0, gl_dbl(gl_mul(a.v[1], b.v[1])));
+    r.v[1] = gl_sub(gl_mul(gl_add(a.v[0], a.v[1]), gl_add(b.v[0], b.v[1])), a0b0);
+    return r;
+}
+GL_HD GlExt<3> ext_mul(const GlExt<3>& a, const GlExt<3>& b) {  // f64/mod.rs:445-466
+    GlExt<3> r;
+    u64 a0b0 = gl_mul(a.v[0], b.v[0]), a1b1 = gl_mul(a.v[1], b.v[1]), a2b2 = gl_mul(a.v[2], b.v[2]);
+    u64 s01 = gl_mul(gl_add(a.v[0], a.v[1]), gl_add(b.v[0], b.v[1]));
+    u64 s02 = gl_mul(gl_add(a.v[0], a.v[2]), gl_add(b.v[0], b.v[2]));
+    u64 s12 = gl_mul(gl_add(a.v[1], a.v[2]), gl_add(b.v[1], b.v[2]));
+    u64 m = gl_sub(a0b0, a1b1);
+    r.v[0] = gl_sub(gl_add(s12, m), a2b2);
+    r.v[1] = gl_sub(gl_sub(gl_add(s01, s12), gl_dbl(a1b1)), a0b0);
+    r.v[2] = gl_sub(s02, m);
+    return r;
+}
+GL_HD GlExt<2> ext_frobenius(const GlExt<2>& x) {  // f64/mod.rs:431
+    GlExt<2> r;
+    r.v[0] = gl_add(x.v[0], x.v[1]);
+    r.v[1] = gl_neg(x.v[1]);
+    return r;
+}
+GL_HD GlExt<3> ext_frobenius(const GlExt<3>& x) {  // f64/mod.rs:490-498
+    GlExt<3> r;
+    r.v[0] = gl_add(x.v[0], gl_add(gl_mul(10615703402128488253ULL, x.v[1]), gl_mul(6700183068485440220ULL, x.v[2])));
+    r.v[1] = gl_add(gl_mul(10050274602728160328ULL, x.v[1]), gl_mul(14531223735771536287ULL, x.v[2]));
+    r.v[2] = gl_add(gl_mul(11746561000929144102ULL, x.v[1]), gl_mul(8396469466686423992ULL, x.v[2]));
+    return r;
+}
+GL_HD GlExt<1> ext_inv(const GlExt<1>& a) {
+    GlExt<1> r;
+    r.v[0] = gl_inv(a.v[0]);
+    return r;
+}
+GL_HD GlExt<2> ext_inv(const GlExt<2>& a) {  // extensions/quadratic.rs:81-94
+    if ((a.v[0] | a.v[1]) == 0) return a;
+    GlExt<2> num = ext_frobenius(a);
+    GlExt<2> norm = ext_mul(a, num);
+    return ext_mul_base(num, gl_inv(norm.v[0]));
+}
+GL_HD GlExt<3> ext_inv(const GlExt<3>& a) {  // extensions/cubic.rs:81-97
+    if ((a.v[0] | a.v[1] | a.v[2]) == 0) return a;
+    GlExt<3> c1 = ext_frobenius(a);
+    GlExt<3> c2 = ext_frobenius(c1);
+    GlExt<3> num = ext_mul(c1, c2);
+    GlExt<3> norm = ext_mul(a, num);
+    return ext_mul_base(num, gl_inv(norm.v[0]));
+}
+template <int D>
+GL_HD GlExt<D> ext_pow(GlExt<D> a, u64 e) {
+    GlExt<D> r = ext_from_base<D>(1);
+    while (e) {
+        if (e & 1) r = ext_mul(r, a);
+        a = ext_mul(a, a);
+        e >>= 1;
+    }
+    return r;
+}

@@ -1,0 +1,99 @@
+// layout.cu — see layout.cuh.
+#include "layout.cuh"
+
+__global__ void __launch_bounds__(256) cols_to_seg_kernel(const u64* __restrict__ src, size_t nrows, int d, int mont,
+                                                          SegMatrix dst) {
+    // thread = (row, segment); reads W columns at `row` (coalesced per column across the warp),
+    // writes one W*8-byte segment row
+    size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 g = blockIdx.y;
+    if (row >= nrows) return;
+    u64* o = dst.base + (size_t)g * dst.seg_stride + row * dst.W;
+    for (int q = 0; q < dst.W; q++) {
+        u32 col = g * dst.W + q;
+        u64 v = 0;
+        if (col < dst.cols) {
+            v = src[(size_t)(col / d) * nrows * d + row * d + (col % d)];
+            if (mont) v = gl_from_mont(v);
+        }
+        o[q] = v;
+    }
+}
+__global__ void __launch_bounds__(256) rows_to_seg_kernel(const u64* __restrict__ src, SegMatrix dst) {
+    size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 g = blockIdx.y;
+    if (row >= dst.rows) return;
+    u64* o = dst.base + (size_t)g * dst.seg_stride + row * dst.W;
+    for (int q = 0; q < dst.W; q++) {
+        u32 col = g * dst.W + q;
+        o[q] = col < dst.cols ? src[row * dst.cols + col] : 0;
+    }
+}
+__global__ void __launch_bounds__(256) seg_to_flat_kernel(SegMatrix src, u64* __restrict__ dst, int row_major, int mont) {
+    size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 g = blockIdx.y;
+    if (row >= src.rows) return;
+    const u64* in = src.base + (size_t)g * src.seg_stride + row * src.W;
+    for (int q = 0; q < src.W; q++) {
+        u32 col = g * src.W + q;
+        if (col >= src.cols) break;
+        u64 v = in[q];
+        if (mont) v = gl_to_mont(v);
+        if (row_major) dst[row * src.cols + col] = v;
+        else dst[(size_t)col * src.rows + row] = v;
+    }
+}
+__global__ void gather_rows_kernel(SegMatrix src, const u64* __restrict__ pos, size_t k, u64* __restrict__ dst, int mont) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= k * src.cols) return;
+    size_t i = idx / src.cols;
+    u32 col = (u32)(idx % src.cols);
+    size_t row = pos[i];
+    u64 v = src.base[(size_t)(col / src.W) * src.seg_stride + row * src.W + (col % src.W)];
+    dst[idx] = mont ? gl_to_mont(v) : v;
+}
+__global__ void gather_digests_kernel(const u64* __restrict__ nodes, const u64* __restrict__ leaves, size_t n,
+                                      const u64* __restrict__ want, size_t k, u64* __restrict__ dst) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= k * 4) return;
+    size_t i = idx >> 2, w = idx & 3;
+    u64 e = want[i];
+    dst[idx] = e < n ? nodes[e * 4 + w] : leaves[(e - n) * 4 + w];
+}
+__global__ void __launch_bounds__(256) scale_rows_kernel(SegMatrix m, u64 base) {
+    size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 g = blockIdx.y;
+    if (row >= m.rows) return;
+    u64 f = gl_pow(base, row);
+    u64* p = m.base + (size_t)g * m.seg_stride + row * m.W;
+    for (int q = 0; q < m.W; q++) p[q] = gl_mul(p[q], f);
+}
+
+static dim3 row_grid(size_t rows, u32 nseg) { return dim3((unsigned)((rows + 255) / 256), nseg); }
+
+cudaError_t layout_cols_to_seg(const u64* src, size_t nrows, int d, int mont, const SegMatrix& dst, cudaStream_t st) {
+    cols_to_seg_kernel<<<row_grid(nrows, dst.nseg()), 256, 0, st>>>(src, nrows, d, mont, dst);
+    return cudaGetLastError();
+}
+cudaError_t layout_rows_to_seg(const u64* src, const SegMatrix& dst, cudaStream_t st) {
+    rows_to_seg_kernel<<<row_grid(dst.rows, dst.nseg()), 256, 0, st>>>(src, dst);
+    return cudaGetLastError();
+}
+cudaError_t layout_seg_to_flat(const SegMatrix& src, u64* dst, int row_major, int mont, cudaStream_t st) {
+    seg_to_flat_kernel<<<row_grid(src.rows, src.nseg()), 256, 0, st>>>(src, dst, row_major, mont);
+    return cudaGetLastError();
+}
+cudaError_t layout_gather_rows(const SegMatrix& src, const u64* pos, size_t k, u64* dst, int mont, cudaStream_t st) {
+    size_t total = k * src.cols;
+    gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, pos, k, dst, mont);
+    return cudaGetLastError();
+}
+cudaError_t layout_gather_digests(const u64* nodes, const u64* leaves, size_t n, const u64* want, size_t k, u64* dst,
+                                  cudaStream_t st) {
+    gather_digests_kernel<<<(unsigned)((k * 4 + 255) / 256), 256, 0, st>>>(nodes, leaves, n, want, k, dst);
+    return cudaGetLastError();
+}
+cudaError_t layout_scale_rows_by_powers(const SegMatrix& m, u64 base, cudaStream_t st) {
+    scale_rows_kernel<<<row_grid(m.rows, m.nseg()), 256, 0, st>>>(m, base);
+    return cudaGetLastError();
+}

@@ -1,0 +1,189 @@
+// ntt.cu — see ntt.cuh for the layout and schedule.
+#include "ntt.cuh"
+
+#include "minidft.cuh"
+
+// One radix-2^R round at DIF stage `stage` on the S x 8 tile `s` (row-major, 8 lanes per row).
+template <int R>
+__device__ __forceinline__ void dif_round(u64* s, const u64* stw, int logS, int stage, int tid) {
+    const int logspan = logS - stage - R;
+    const u32 span = 1u << logspan;
+    const u32 nbf = (1u << logS) >> R;
+    const u32 half = (1u << logS) >> 1;
+    const int lane = tid & (NTT_LANES - 1);
+    for (u32 bf = tid >> 3; bf < nbf; bf += NTT_THREADS / NTT_LANES) {
+        u32 lo = bf & (span - 1);
+        u32 base = ((bf >> logspan) << (logspan + R)) + lo;
+        u64 x[1 << R];
+#pragma unroll
+        for (int q = 0; q < (1 << R); q++) x[q] = s[((base + ((u32)q << logspan)) << 3) + lane];
+        mini_dft<R>(x);
+        if (logspan > 0) {
+#pragma unroll
+            for (int qo = 1; qo < (1 << R); qo++) {
+                // position qo holds frequency bitrev(qo) of the mini-DFT: twiddle w_G^(lo * freq)
+                u32 e = (lo * brev(qo, R)) << stage;
+                x[qo] = gl_mul(x[qo], tw_lookup(stw, e, half));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < (1 << R); q++) s[((base + ((u32)q << logspan)) << 3) + lane] = x[q];
+    }
+}
+
+__device__ __forceinline__ void tile_dft(u64* s, const u64* stw, int logS, int tid) {
+    int stage = 0;
+    while (logS - stage >= 3) {
+        dif_round<3>(s, stw, logS, stage, tid);
+        stage += 3;
+        __syncthreads();
+    }
+    if (logS - stage == 2) {
+        dif_round<2>(s, stw, logS, stage, tid);
+        __syncthreads();
+    } else if (logS - stage == 1) {
+        dif_round<1>(s, stw, logS, stage, tid);
+        __syncthreads();
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// TMA bulk copy of the sub-transform twiddle table into shared memory.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gsrc, u32 bytes, u64* mbar, int tid) {
+    u32 mb = (u32)__cvta_generic_to_shared(mbar);
+    u32 dst = (u32)__cvta_generic_to_shared(smem_dst);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+            "l"(gsrc), "r"(bytes), "r"(mb)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_bulk_wait(u64* mbar) {
+    u32 mb = (u32)__cvta_generic_to_shared(mbar);
+    u32 done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(mb)
+            : "memory");
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// The pass kernel. grid = (tiles, segments, batch), block = NTT_THREADS.
+// Shared memory: tile [S][8] | sub twiddles [S/2] | post twiddles [S][T] (if has_post) | mbarrier
+// -------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const NttPassParams p) {
+    extern __shared__ __align__(16) u64 smem[];
+    const int tid = threadIdx.x;
+    const int logS = p.logS;
+    const u32 S = 1u << logS;
+    const int W = p.W;
+    const int logW = 31 - __clz(W);
+    const int T = NTT_LANES >> logW;
+    u64* s = smem;
+    u64* stw = s + (size_t)S * NTT_LANES;
+    u64* ctw = stw + (S >> 1 ? S >> 1 : 1);
+    u64* mbar = ctw + (p.has_post ? (size_t)S * T : 0);
+
+    const u32 tile = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+    const u32 R = 1u << p.logR, C = 1u << p.logC;
+    const int lane = tid & 7;
+    const int t = lane >> logW;        // tile column of this lane
+    const int q = lane & (W - 1);      // segment column of this lane
+    const u32 col = tile * T + t;      // STRIDED: m2; CONTIG: j1
+    const bool col_ok = (MODE == NTT_STRIDED) ? (col < C) : (col < R);
+
+    // stage the twiddle table with one bulk copy (needs >= 16 bytes, 16-byte aligned)
+    const u32 tw_bytes = (S >> 1) * 8;
+    const bool use_tma = tw_bytes >= 16;
+    if (use_tma) tma_bulk_load(stw, p.sub_tw, tw_bytes, mbar, tid);
+    else if (tid < (int)(S >> 1)) stw[tid] = p.sub_tw[tid];
+
+    // post twiddles for this tile: ctw[j][t]
+    if (p.has_post) {
+        const u32 M = 1u << p.logM, Mh = M >> 1;
+        for (u32 idx = tid; idx < S * (u32)T; idx += NTT_THREADS) {
+            u32 j = idx / T, tt = idx % T;
+            u32 c = tile * T + tt;
+            u64 e64 = ((u64)j * p.a_mul + (u64)(p.batch0 + b) * p.b_mul) * c;
+            u32 e = (u32)(e64 & (M - 1));
+            if (p.inverse && e) e = M - e;
+            u64 w = tw_lookup(p.master, e, Mh);
+            if (p.ctab) w = gl_mul(w, p.ctab[c < (MODE == NTT_STRIDED ? C : R) ? c : 0]);
+            if (p.cconst != 1) w = gl_mul(w, p.cconst);
+            ctw[idx] = w;
+        }
+    }
+
+    // load the tile
+    const u64* in = p.in + (size_t)g * p.in_seg_stride + (size_t)b * p.in_batch_stride;
+    const u64* pre = p.pre_tab ? p.pre_tab + (size_t)b * p.pre_batch_stride : nullptr;
+    for (u32 i = tid >> 3; i < S; i += NTT_THREADS / NTT_LANES) {
+        u64 v = 0;
+        if (col_ok) {
+            size_t a;
+            if (MODE == NTT_STRIDED) a = (((size_t)i << p.logC) + col) * W + q;   // row C*m1 + m2
+            else a = (((size_t)col << p.logC) + i) * W + q;                       // row j1*C + m2
+            v = in[a];
+            if (pre) v = gl_mul(v, pre[i]);
+        }
+        s[(i << 3) + lane] = v;
+    }
+    if (use_tma) tma_bulk_wait(mbar);
+    __syncthreads();
+
+    tile_dft(s, stw, logS, tid);
+
+    // write back: smem position pos holds forward X[bitrev(pos)]
+    u64* out = p.out + (size_t)g * p.out_seg_stride + (size_t)b * p.out_batch_stride;
+    for (u32 j = tid >> 3; j < S; j += NTT_THREADS / NTT_LANES) {
+        if (!col_ok) continue;
+        u32 jf = p.inverse ? ((S - j) & (S - 1)) : j;
+        u64 v = s[(brev(jf, logS) << 3) + lane];
+        if (p.has_post) v = gl_mul(v, ctw[j * T + t]);
+        size_t a;
+        if (MODE == NTT_STRIDED) {
+            a = (((size_t)j << p.logC) + col) * W + q;                            // Y[j1][m2]
+        } else {
+            size_t row = (size_t)col + ((size_t)j << p.logR);                     // X[j1 + R*j2]
+            a = (row * p.out_row_mul + (size_t)b * p.out_row_add) * W + q;
+        }
+        out[a] = v;
+    }
+}
+
+size_t ntt_pass_smem_bytes(const NttPassParams& p) {
+    size_t S = (size_t)1 << p.logS;
+    size_t T = NTT_LANES / p.W;
+    size_t words = S * NTT_LANES + (S / 2 ? S / 2 : 1) + (p.has_post ? S * T : 0) + 2;
+    return words * 8;
+}
+
+cudaError_t ntt_launch_pass(int mode, const NttPassParams& p, u32 n_segments, u32 n_batch, cudaStream_t st) {
+    size_t smem = ntt_pass_smem_bytes(p);
+    u32 T = NTT_LANES / p.W;
+    u32 ncols = mode == NTT_STRIDED ? (1u << p.logC) : (1u << p.logR);
+    dim3 grid((ncols + T - 1) / T, n_segments, n_batch);
+    cudaError_t e;
+    if (mode == NTT_STRIDED) {
+        e = cudaFuncSetAttribute(ntt_pass_kernel<NTT_STRIDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        ntt_pass_kernel<NTT_STRIDED><<<grid, NTT_THREADS, smem, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(ntt_pass_kernel<NTT_CONTIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        ntt_pass_kernel<NTT_CONTIG><<<grid, NTT_THREADS, smem, st>>>(p);
+    }
+    return cudaGetLastError();
+}
