@@ -66,6 +66,8 @@ int wf_mat_from_host_columns(wf_ctx* ctx, const uint64_t* const* cols, uint32_t 
                              int ext_degree, int mont, wf_mat** out);
 /* same, from a DEVICE buffer laid out column-major [ncols][nrows] (base columns, canonical) */
 int wf_mat_from_device_columns(wf_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, size_t nrows, wf_mat** out);
+/* new matrix holding base columns [first, first + count) of m */
+int wf_mat_select_columns(wf_ctx* ctx, const wf_mat* m, uint32_t first, uint32_t count, wf_mat** out);
 int wf_mat_free(wf_ctx* ctx, wf_mat* m);
 size_t wf_mat_rows(const wf_mat* m);
 uint32_t wf_mat_cols(const wf_mat* m);

@@ -38,6 +38,7 @@ _SIGS = [
     ("wf_version", C.c_char_p, []),
     ("wf_mat_from_host_columns", C.c_int, [vp, C.POINTER(u64p), C.c_uint32, C.c_size_t, C.c_int, C.c_int, C.POINTER(vp)]),
     ("wf_mat_from_device_columns", C.c_int, [vp, vp, C.c_uint32, C.c_size_t, C.POINTER(vp)]),
+    ("wf_mat_select_columns", C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
     ("wf_mat_free", C.c_int, [vp, vp]),
     ("wf_mat_rows", C.c_size_t, [vp]),
     ("wf_mat_cols", C.c_uint32, [vp]),
@@ -233,6 +234,9 @@ class Mat:
         h = vp()
         self.ctx.check(fn(self.ctx.h, self.h, *extra, C.byref(h)))
         return Mat(self.ctx, h)
+
+    def select_columns(self, first, count):
+        return self._unary(self.ctx.L.wf_mat_select_columns, first, count)
 
     def interpolate(self):
         return self._unary(self.ctx.L.wf_mat_interpolate)

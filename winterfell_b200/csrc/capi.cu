@@ -146,17 +146,23 @@ static int get_twiddles(wf_ctx* ctx, u32 log_n, const u64** out) {
 }
 
 // n = R * C split for the two-pass schedule
-static void split_log(u32 log_n, u32* logR, u32* logC) {
-    if (log_n <= NTT_MAX_LOGS) { *logR = 0; *logC = log_n; }
-    else { *logR = (log_n + 1) / 2; *logC = log_n - *logR; }
+// The strided pass also holds S*T post twiddles in shared memory (T = 8/W tile columns), so for
+// single-column segments (W = 1) its sub-transform is capped at 2^10 to stay under 227 KB.
+static void split_log(u32 log_n, int W, u32* logR, u32* logC) {
+    if (log_n <= NTT_MAX_LOGS) { *logR = 0; *logC = log_n; return; }
+    u32 max_r = W == 1 ? NTT_MAX_LOGS - 1 : NTT_MAX_LOGS;
+    u32 r = (log_n + 1) / 2;
+    if (r > max_r) r = max_r;
+    *logR = r;
+    *logC = log_n - r;
 }
 
-static int get_lde_tables(wf_ctx* ctx, u32 log_n, u32 log_b, LdeTables* out) {
-    auto key = std::make_pair(log_n, log_b);
+static int get_lde_tables(wf_ctx* ctx, u32 log_n, u32 log_b, int W, LdeTables* out) {
+    auto key = std::make_pair(log_n | (W == 1 ? 0x100u : 0u), log_b);
     auto it = ctx->lde_tabs.find(key);
     if (it != ctx->lde_tabs.end()) { *out = it->second; return WF_OK; }
     u32 logR, logC;
-    split_log(log_n, &logR, &logC);
+    split_log(log_n, W, &logR, &logC);
     size_t b = (size_t)1 << log_b, R = (size_t)1 << logR, C = (size_t)1 << logC;
     u64 g = gl_root_of_unity(log_n + log_b);
     // s_k = 7 * w_N^k (coset k of the LDE domain; natural row i = b*j + k)
@@ -208,17 +214,15 @@ static void pass_defaults(NttPassParams& p, const SegMatrix& in, const SegMatrix
 // shape) is needed when log_n > NTT_MAX_LOGS. in == out is allowed.
 static int run_ntt(wf_ctx* ctx, const SegMatrix& in, SegMatrix& out, const SegMatrix* tmp, u32 log_n, int inverse) {
     u32 logR, logC;
-    split_log(log_n, &logR, &logC);
-    if (logR > NTT_MAX_LOGS) return fail(ctx, WF_ERR_UNSUPPORTED, "NTT size 2^%u exceeds the two-pass limit 2^%d", log_n, 2 * NTT_MAX_LOGS);
+    split_log(log_n, in.W, &logR, &logC);
+    if (logC > NTT_MAX_LOGS) return fail(ctx, WF_ERR_UNSUPPORTED, "NTT size 2^%u exceeds the two-pass limit 2^%d", log_n, 2 * NTT_MAX_LOGS);
     u64 inv_n = gl_inv(((u64)1 << log_n) % GL_P);
     NttPassParams p;
     if (logR == 0) {
         pass_defaults(p, in, out);
         p.logS = (int)logC; p.logR = 0; p.logC = logC; p.inverse = inverse;
         CKI(get_twiddles(ctx, std::max(log_n, 1u), &p.sub_tw));
-        if (inverse) {
-            p.has_post = 1; p.master = p.sub_tw; p.logM = std::max(log_n, 1u); p.a_mul = 0; p.b_mul = 0; p.cconst = inv_n;
-        }
+        if (inverse) p.cconst = inv_n;
         CK(ntt_launch_pass(NTT_CONTIG, p, in.nseg(), 1, ctx->st));
         ctx->launches++;
         return WF_OK;
@@ -245,11 +249,11 @@ static int run_ntt(wf_ctx* ctx, const SegMatrix& in, SegMatrix& out, const SegMa
 // LDE of coefficient columns over 7 * <w_N>: out has n << log_b rows, row b*j + k = P(7 w_N^k w_n^j).
 static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_n, u32 log_b) {
     u32 logR, logC;
-    split_log(log_n, &logR, &logC);
-    if (logR > NTT_MAX_LOGS) return fail(ctx, WF_ERR_UNSUPPORTED, "LDE of 2^%u rows exceeds the two-pass limit", log_n);
+    split_log(log_n, polys.W, &logR, &logC);
+    if (logC > NTT_MAX_LOGS) return fail(ctx, WF_ERR_UNSUPPORTED, "LDE of 2^%u rows exceeds the two-pass limit", log_n);
     u32 b = 1u << log_b;
     LdeTables tabs;
-    CKI(get_lde_tables(ctx, log_n, log_b, &tabs));
+    CKI(get_lde_tables(ctx, log_n, log_b, polys.W, &tabs));
     NttPassParams p;
     if (logR == 0) {
         pass_defaults(p, polys, out);
@@ -365,6 +369,15 @@ int wf_mat_from_host_columns(wf_ctx* ctx, const uint64_t* const* cols, uint32_t 
     ctx->launches++;
     dev_free(ctx, stage);
     *out = m;
+    return WF_OK;
+}
+int wf_mat_select_columns(wf_ctx* ctx, const wf_mat* m, uint32_t first, uint32_t count, wf_mat** out) {
+    if (!ctx || !m || !out || count == 0 || first + count > m->m.cols) return fail(ctx, WF_ERR_INVALID, "bad column range");
+    wf_mat* o;
+    CKI(mat_alloc(ctx, m->m.rows, count, &o));
+    CK(layout_select_cols(m->m, first, o->m, ctx->st));
+    ctx->launches++;
+    *out = o;
     return WF_OK;
 }
 int wf_mat_free(wf_ctx* ctx, wf_mat* m) {

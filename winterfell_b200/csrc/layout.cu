@@ -69,6 +69,22 @@ __global__ void __launch_bounds__(256) scale_rows_kernel(SegMatrix m, u64 base) 
     for (int q = 0; q < m.W; q++) p[q] = gl_mul(p[q], f);
 }
 
+__global__ void __launch_bounds__(256) select_cols_kernel(SegMatrix src, u32 first, SegMatrix dst) {
+    size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 g = blockIdx.y;
+    if (row >= dst.rows) return;
+    u64* o = dst.base + (size_t)g * dst.seg_stride + row * dst.W;
+    for (int q = 0; q < dst.W; q++) {
+        u32 col = g * dst.W + q;
+        u64 v = 0;
+        if (col < dst.cols) {
+            u32 sc = first + col;
+            v = src.base[(size_t)(sc / src.W) * src.seg_stride + row * src.W + (sc % src.W)];
+        }
+        o[q] = v;
+    }
+}
+
 static dim3 row_grid(size_t rows, u32 nseg) { return dim3((unsigned)((rows + 255) / 256), nseg); }
 
 cudaError_t layout_cols_to_seg(const u64* src, size_t nrows, int d, int mont, const SegMatrix& dst, cudaStream_t st) {
@@ -95,5 +111,9 @@ cudaError_t layout_gather_digests(const u64* nodes, const u64* leaves, size_t n,
 }
 cudaError_t layout_scale_rows_by_powers(const SegMatrix& m, u64 base, cudaStream_t st) {
     scale_rows_kernel<<<row_grid(m.rows, m.nseg()), 256, 0, st>>>(m, base);
+    return cudaGetLastError();
+}
+cudaError_t layout_select_cols(const SegMatrix& src, u32 first, const SegMatrix& dst, cudaStream_t st) {
+    select_cols_kernel<<<row_grid(dst.rows, dst.nseg()), 256, 0, st>>>(src, first, dst);
     return cudaGetLastError();
 }

@@ -19,3 +19,5 @@ cudaError_t layout_gather_digests(const u64* nodes, const u64* leaves, size_t n,
                                   cudaStream_t st);
 // row i of every column *= base^i
 cudaError_t layout_scale_rows_by_powers(const SegMatrix& m, u64 base, cudaStream_t st);
+// dst(row, j) = src(row, first + j) for j < dst.cols
+cudaError_t layout_select_cols(const SegMatrix& src, u32 first, const SegMatrix& dst, cudaStream_t st);

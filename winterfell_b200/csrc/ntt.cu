@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const NttPassPara
         u32 jf = p.inverse ? ((S - j) & (S - 1)) : j;
         u64 v = s[(brev(jf, logS) << 3) + lane];
         if (p.has_post) v = gl_mul(v, ctw[j * T + t]);
+        else if (p.cconst != 1) v = gl_mul(v, p.cconst);
         size_t a;
         if (MODE == NTT_STRIDED) {
             a = (((size_t)j << p.logC) + col) * W + q;                            // Y[j1][m2]

@@ -55,7 +55,8 @@ struct NttPassParams {
     u32 a_mul, b_mul;
     u32 batch0;                                // added to the batch index in the twiddle exponent
     const u64* ctab;                           // optional per-column constant table
-    u64 cconst;                                // constant factor (e.g. 1/n), 1 if unused
+    u64 cconst;                                // constant factor (e.g. 1/n) folded into the post twiddle, or applied
+                                               // alone at write-back when has_post == 0; 1 if unused
 };
 
 enum { NTT_STRIDED = 0, NTT_CONTIG = 1 };
