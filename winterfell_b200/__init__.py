@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwinterfell_b200.so")
+LIB_PATH = os.environ.get("WF_LIB_PATH") or os.path.join(_HERE, "libwinterfell_b200.so")  # WF_LIB_PATH: kernel experiments
 
 P = 0xFFFFFFFF00000001
 HASH_BLAKE3_256 = 0

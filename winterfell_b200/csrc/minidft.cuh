@@ -6,11 +6,7 @@
 // Register mini-DFTs (decimation in frequency, in place, bit-reversed output). All internal
 // twiddles are powers of two: w_8 = 2^24, w_4 = 2^48, w_2 = -1 (gl64.cuh gl_mul_2exp).
 // -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bf2(u64& a, u64& b) {
-    u64 s = gl_add(a, b);
-    b = gl_sub(a, b);
-    a = s;
-}
+__device__ __forceinline__ void bf2(u64& a, u64& b) { gl_butterfly(a, b); }
 template <int R>
 __device__ __forceinline__ void mini_dft(u64* x);
 template <>

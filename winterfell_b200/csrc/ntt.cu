@@ -33,6 +33,13 @@ __device__ __forceinline__ void dif_round(u64* s, const u64* stw, int logS, int 
 
 __device__ __forceinline__ void tile_dft(u64* s, const u64* stw, int logS, int tid) {
     int stage = 0;
+#ifdef NTT_RADIX16
+    while (logS - stage >= 4) {
+        dif_round<4>(s, stw, logS, stage, tid);
+        stage += 4;
+        __syncthreads();
+    }
+#endif
     while (logS - stage >= 3) {
         dif_round<3>(s, stw, logS, stage, tid);
         stage += 3;
@@ -83,7 +90,7 @@ __device__ __forceinline__ void tma_bulk_wait(u64* mbar) {
 // Shared memory: tile [S][8] | sub twiddles [S/2] | post twiddles [S][T] (if has_post) | mbarrier
 // -------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const NttPassParams p) {
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_pass_kernel(const NttPassParams p) {
     extern __shared__ __align__(16) u64 smem[];
     const int tid = threadIdx.x;
     const int logS = p.logS;
@@ -110,35 +117,67 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const NttPassPara
     if (use_tma) tma_bulk_load(stw, p.sub_tw, tw_bytes, mbar, tid);
     else if (tid < (int)(S >> 1)) stw[tid] = p.sub_tw[tid];
 
-    // post twiddles for this tile: ctw[j][t]
+    // post twiddles for this tile: ctw[j][t] (gathers batched the same way)
     if (p.has_post) {
         const u32 M = 1u << p.logM, Mh = M >> 1;
-        for (u32 idx = tid; idx < S * (u32)T; idx += NTT_THREADS) {
-            u32 j = idx / T, tt = idx % T;
-            u32 c = tile * T + tt;
-            u64 e64 = ((u64)j * p.a_mul + (u64)(p.batch0 + b) * p.b_mul) * c;
-            u32 e = (u32)(e64 & (M - 1));
-            if (p.inverse && e) e = M - e;
-            u64 w = tw_lookup(p.master, e, Mh);
-            if (p.ctab) w = gl_mul(w, p.ctab[c < (MODE == NTT_STRIDED ? C : R) ? c : 0]);
-            if (p.cconst != 1) w = gl_mul(w, p.cconst);
-            ctw[idx] = w;
+        const u32 total = S * (u32)T;
+        const int logT = 3 - logW;
+        for (u32 idx0 = tid; idx0 < total; idx0 += NTT_THREADS * 4) {
+            u64 w[4], cc[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                u32 idx = idx0 + k * NTT_THREADS;
+                w[k] = 1;
+                cc[k] = 1;
+                if (idx < total) {
+                    u32 j = idx >> logT, tt = idx & (T - 1);
+                    u32 c = tile * T + tt;
+                    u64 e64 = ((u64)j * p.a_mul + (u64)(p.batch0 + b) * p.b_mul) * c;
+                    u32 e = (u32)(e64 & (M - 1));
+                    if (p.inverse && e) e = M - e;
+                    w[k] = tw_lookup(p.master, e, Mh);
+                    if (p.ctab) cc[k] = p.ctab[c < (MODE == NTT_STRIDED ? C : R) ? c : 0];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                u32 idx = idx0 + k * NTT_THREADS;
+                if (idx < total) {
+                    u64 x = w[k];
+                    if (p.ctab) x = gl_mul(x, cc[k]);
+                    if (p.cconst != 1) x = gl_mul(x, p.cconst);
+                    ctw[idx] = x;
+                }
+            }
         }
     }
 
-    // load the tile
+    // load the tile: batches of NTT_LD_BATCH independent loads per thread are issued before any is
+    // consumed (the first profile showed long-scoreboard stalls of 2.7 cycles per issued instruction
+    // from one-at-a-time LDG -> STS chains)
     const u64* in = p.in + (size_t)g * p.in_seg_stride + (size_t)b * p.in_batch_stride;
     const u64* pre = p.pre_tab ? p.pre_tab + (size_t)b * p.pre_batch_stride : nullptr;
-    for (u32 i = tid >> 3; i < S; i += NTT_THREADS / NTT_LANES) {
-        u64 v = 0;
-        if (col_ok) {
-            size_t a;
-            if (MODE == NTT_STRIDED) a = (((size_t)i << p.logC) + col) * W + q;   // row C*m1 + m2
-            else a = (((size_t)col << p.logC) + i) * W + q;                       // row j1*C + m2
-            v = in[a];
-            if (pre) v = gl_mul(v, pre[i]);
+    constexpr u32 ROWS_PER_IT = NTT_THREADS / NTT_LANES;
+    for (u32 i0 = tid >> 3; i0 < S; i0 += ROWS_PER_IT * NTT_LD_BATCH) {
+        u64 v[NTT_LD_BATCH], f[NTT_LD_BATCH];
+#pragma unroll
+        for (int k = 0; k < NTT_LD_BATCH; k++) {
+            u32 i = i0 + k * ROWS_PER_IT;
+            v[k] = 0;
+            f[k] = 1;
+            if (col_ok && i < S) {
+                size_t a;
+                if (MODE == NTT_STRIDED) a = (((size_t)i << p.logC) + col) * W + q;   // row C*m1 + m2
+                else a = (((size_t)col << p.logC) + i) * W + q;                       // row j1*C + m2
+                v[k] = in[a];
+                if (pre) f[k] = pre[i];
+            }
         }
-        s[(i << 3) + lane] = v;
+#pragma unroll
+        for (int k = 0; k < NTT_LD_BATCH; k++) {
+            u32 i = i0 + k * ROWS_PER_IT;
+            if (i < S) s[(i << 3) + lane] = pre ? gl_mul(v[k], f[k]) : v[k];
+        }
     }
     if (use_tma) tma_bulk_wait(mbar);
     __syncthreads();

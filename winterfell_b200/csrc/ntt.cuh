@@ -31,7 +31,15 @@
 #include "gl64.cuh"
 
 #define NTT_LANES 8
-#define NTT_THREADS 256
+#ifndef NTT_THREADS
+#define NTT_THREADS 512
+#endif
+#ifndef NTT_LD_BATCH
+#define NTT_LD_BATCH 8
+#endif
+#ifndef NTT_MIN_BLOCKS
+#define NTT_MIN_BLOCKS 2
+#endif
 #define NTT_MAX_LOGS 11
 
 struct NttPassParams {
