@@ -320,6 +320,39 @@ class RandomCoin:
         return o
 
 
+# ---- full prover / verifier restatement (oracle/wf_prover.cpp) ----
+def make_opts(num_queries=28, blowup=8, grinding=0, ext=1, folding=4, rem_max_deg=7, batch_c=0, batch_d=0, hash_id=BLAKE3):
+    return np.array([num_queries, blowup, grinding, ext, folding, rem_max_deg, batch_c, batch_d, hash_id], dtype=np.uint32)
+
+
+def build_fib_trace(k, n):
+    tr = np.zeros((2 * k, n), dtype=np.uint64)
+    res = np.zeros(k, dtype=np.uint64)
+    lib().wfo_build_fib_trace(C.c_size_t(k), C.c_size_t(n), tr.ctypes.data_as(u64p), res.ctypes.data_as(u64p))
+    return tr, res
+
+
+def prove_fib(trace, results, opts):
+    t_, tp = _u64(trace)
+    r_, rp = _u64(results)
+    k, n = t_.shape[0] // 2, t_.shape[1]
+    cap = 1 << 23
+    out = np.zeros(cap, dtype=np.uint8)
+    L = lib()
+    L.wfo_prove_fib.restype = C.c_long
+    ln = L.wfo_prove_fib(tp, C.c_size_t(k), C.c_size_t(n), rp, opts.ctypes.data_as(C.POINTER(C.c_uint32)),
+                         out.ctypes.data_as(u8p), C.c_size_t(cap))
+    if ln < 0:
+        raise RuntimeError("prove_fib failed")
+    return out[:ln].tobytes()
+
+
+def verify_fib(proof: bytes, k, results, hash_id=BLAKE3):
+    p_, pp = _u8(np.frombuffer(proof, dtype=np.uint8))
+    r_, rp = _u64(results)
+    return lib().wfo_verify_fib(pp, C.c_size_t(len(proof)), C.c_size_t(k), rp, C.c_int(hash_id))
+
+
 def rand_elems(shape, seed):
     """Uniform field elements in [0, p) from a seeded PRNG (rejection sampling)."""
     rng = np.random.default_rng(seed)
