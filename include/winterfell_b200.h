@@ -131,6 +131,17 @@ size_t wf_fri_remainder(const wf_fri* f, uint64_t* coeffs, size_t cap_words);
 int wf_fri_build_proof(wf_ctx* ctx, wf_fri* f, const uint64_t* positions, size_t k, uint8_t* out, size_t* len);
 int wf_fri_free(wf_ctx* ctx, wf_fri* f);
 
+/* ---- full proof (Prover::prove / generate_proof, prover/src/lib.rs:250-492) --------------------- */
+/* Proves the built-in AIR family "FibSmall x k" (k copies of examples/src/fibonacci/fib_small/air.rs
+ * side by side, trace width 2k; k = 1 is the reference's fib_small example) and writes the
+ * serialized Proof (air/src/proof/mod.rs:189-200). trace_cols: 2k host columns of 2^log_n words;
+ * results: the k public inputs (last value of column 2j+1).
+ * opts[9] = { num_queries, blowup, grinding, field_extension (1|2|3), fri_folding, fri_remainder_max_degree,
+ *             constraint batching (0 Linear | 1 Algebraic | 2 Horner), DEEP batching, hash_id }
+ * (ProofOptions::new, air/src/options.rs:132). *proof_len: in = capacity, out = bytes written. */
+int wf_prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, uint32_t k, uint32_t log_n,
+                 const uint64_t* results, const uint32_t* opts, uint8_t* proof, size_t* proof_len);
+
 /* ---- plain kernels on caller-owned DEVICE buffers (unit parity + bench legs) ------------------- */
 /* in-place NTT (inverse=0) / iNTT (inverse=1) of `cols` columns, column-major [cols][n], n = 1 << log_n */
 int wf_ntt_dev(wf_ctx* ctx, uint64_t* d_data, uint32_t log_n, uint32_t cols, int inverse);

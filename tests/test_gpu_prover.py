@@ -1,0 +1,60 @@
+"""GPU proof generation vs the oracle: the serialized Proof produced by the device pipeline
+(wf_prove_fib) must be byte-identical to the CPU restatement of Prover::generate_proof, and the
+restated verifier (verifier/src/lib.rs) must accept it. Mirrors examples/src/fibonacci/fib_small/tests.rs:8-24
+(n = 128, Rp64_256, base and quadratic extension, 28 queries, blowup 8, folding 4, remainder 7) and
+examples/src/tests.rs:8-17 (wrong public input is rejected)."""
+import numpy as np
+import pytest
+
+import winterfell_b200 as wf
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = wf.Context(0)
+    yield c
+    c.close()
+
+
+CASES = [
+    # k, log_n, ext, hash, folding, rem_max_deg, batching, grinding, blowup, queries
+    (1, 7, 1, wf.HASH_RP64_256, 4, 7, 0, 0, 8, 28),      # the reference's own fib_small test
+    (1, 7, 2, wf.HASH_RP64_256, 4, 7, 0, 0, 8, 28),      # ... with the quadratic extension
+    (1, 10, 1, wf.HASH_BLAKE3_256, 8, 31, 0, 8, 8, 28),  # configs[0] shape (fib_small CLI defaults), small n
+    (1, 8, 3, wf.HASH_BLAKE3_256, 4, 7, 0, 4, 8, 28),
+    (4, 10, 1, wf.HASH_BLAKE3_256, 4, 31, 0, 8, 8, 32),  # configs[1] AIR (8 columns), small n
+    (4, 12, 3, wf.HASH_BLAKE3_256, 4, 31, 1, 4, 8, 32),  # two-pass NTT sizes, cubic, algebraic batching
+    (32, 9, 3, wf.HASH_BLAKE3_256, 4, 31, 2, 0, 8, 32),  # configs[2] AIR (64 columns, cubic), Horner batching
+    (2, 8, 2, wf.HASH_BLAKE3_256, 2, 7, 0, 0, 4, 20),
+    (3, 9, 1, wf.HASH_RP64_256, 16, 7, 2, 0, 16, 12),
+]
+
+
+@pytest.mark.parametrize("k,log_n,ext,h,fold,rem,batch,grind,blowup,nq", CASES)
+def test_proof_bytes_match_oracle_and_verify(ctx, oracle, k, log_n, ext, h, fold, rem, batch, grind, blowup, nq):
+    n = 1 << log_n
+    trace, results = oracle.build_fib_trace(k, n)
+    opts = oracle.make_opts(num_queries=nq, blowup=blowup, grinding=grind, ext=ext, folding=fold, rem_max_deg=rem,
+                            batch_c=batch, batch_d=batch, hash_id=h)
+    want = oracle.prove_fib(trace, results, opts)
+    got = ctx.prove_fib(trace, results, opts)
+    assert len(got) == len(want)
+    assert got == want, next(i for i in range(len(got)) if got[i] != want[i])
+    assert oracle.verify_fib(got, k, results, h) == 0
+    # negative tests: wrong public input (examples/src/tests.rs:8-17) and a flipped byte
+    bad = results.copy()
+    bad[0] += np.uint64(1)
+    assert oracle.verify_fib(got, k, bad, h) != 0
+    t = bytearray(got)
+    t[len(t) // 3] ^= 0x40
+    assert oracle.verify_fib(bytes(t), k, results, h) != 0
+
+
+def test_montgomery_trace_input(ctx, oracle):
+    # the Rust shim passes &[BaseElement] reinterpreted as u64: Montgomery words
+    trace, results = oracle.build_fib_trace(1, 256)
+    tm = np.array([[oracle.to_mont(int(v)) for v in row] for row in trace], dtype=np.uint64)
+    opts = oracle.make_opts(folding=8, rem_max_deg=31, grinding=2)
+    assert ctx.prove_fib(tm, results, opts, mont=True) == oracle.prove_fib(trace, results, opts)

@@ -62,6 +62,7 @@ _SIGS = [
     ("wf_fri_remainder", C.c_size_t, [vp, u64p, C.c_size_t]),
     ("wf_fri_build_proof", C.c_int, [vp, vp, u64p, C.c_size_t, u8p, C.POINTER(C.c_size_t)]),
     ("wf_fri_free", C.c_int, [vp, vp]),
+    ("wf_prove_fib", C.c_int, [vp, C.POINTER(u64p), C.c_int, C.c_uint32, C.c_uint32, u64p, C.POINTER(C.c_uint32), u8p, C.POINTER(C.c_size_t)]),
     ("wf_ntt_dev", C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_int]),
     ("wf_hash_rows_dev", C.c_int, [vp, C.c_int, vp, C.c_size_t, C.c_uint32, vp]),
     ("wf_merkle_dev", C.c_int, [vp, C.c_int, vp, C.c_size_t, vp]),
@@ -178,6 +179,20 @@ class Context:
                                                               blowup, roots.ctypes.data_as(u8p), roots.size, C.byref(h)))
         f = Fri(self, h, ext_degree)
         return f, roots[: f.num_layers + 1].copy()
+
+    def prove_fib(self, trace, results, opts, mont=False):
+        """trace: [2k, n] uint64; results: [k]; opts: uint32[9] (see wf_prove_fib). Returns proof bytes."""
+        a = np.ascontiguousarray(trace, dtype=np.uint64)
+        c, n = a.shape
+        ptrs = (u64p * c)(*[a[j].ctypes.data_as(u64p) for j in range(c)])
+        r_, rp = _u64(results)
+        o_ = np.ascontiguousarray(opts, dtype=np.uint32)
+        cap = 1 << 23
+        buf = np.zeros(cap, dtype=np.uint8)
+        ln = C.c_size_t(cap)
+        self.check(self.L.wf_prove_fib(self.h, ptrs, int(mont), c // 2, int(n).bit_length() - 1, rp,
+                                       o_.ctypes.data_as(C.POINTER(C.c_uint32)), buf.ctypes.data_as(u8p), C.byref(ln)))
+        return buf[: ln.value].tobytes()
 
     # ---- plain device kernels (raw device pointers as integers) ----
     def ntt_dev(self, dptr, log_n, cols, inverse=False):

@@ -11,35 +11,9 @@
 #include <string>
 #include <vector>
 
-#include "../../include/winterfell_b200.h"
-#include "commit.cuh"
-#include "fri.cuh"
-#include "host_transcript.hpp"
-#include "layout.cuh"
-#include "ntt.cuh"
+#include "internal.hpp"
 
-// =================================================================================================
-// context
-// =================================================================================================
-struct LdeTables {
-    u64* pre;    // two-pass: [blowup][R] (s_k^C)^m1 ; single pass: [blowup][n] s_k^m
-    u64* pow7;   // two-pass: [C] 7^m2 ; single pass: null
-};
-
-struct wf_ctx {
-    int device;
-    cudaStream_t st;
-    std::string err;
-    uint64_t launches;
-    std::multimap<size_t, void*> pool;       // free device buffers by size
-    std::map<void*, size_t> live;            // allocated device buffers
-    std::map<u32, u64*> tw;                  // log_n -> w_n^i, i < n/2
-    std::map<std::pair<u32, u32>, LdeTables> lde_tabs;  // (log_n, log_blowup)
-    void* pinned;                            // staging buffer (pinned host)
-    size_t pinned_bytes;
-};
-
-static int fail(wf_ctx* ctx, int code, const char* fmt, ...) {
+int wf_fail(wf_ctx* ctx, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -48,19 +22,7 @@ static int fail(wf_ctx* ctx, int code, const char* fmt, ...) {
     if (ctx) ctx->err = buf;
     return code;
 }
-#define CK(call)                                                                                       \
-    do {                                                                                               \
-        cudaError_t _e = (call);                                                                       \
-        if (_e != cudaSuccess)                                                                         \
-            return fail(ctx, WF_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
-    } while (0)
-#define CKI(call)                 \
-    do {                          \
-        int _r = (call);          \
-        if (_r != WF_OK) return _r; \
-    } while (0)
-
-static int dev_alloc(wf_ctx* ctx, size_t bytes, void** out) {
+int wf_dev_alloc(wf_ctx* ctx, size_t bytes, void** out) {
     bytes = (bytes + 255) & ~(size_t)255;
     if (bytes == 0) bytes = 256;
     auto it = ctx->pool.find(bytes);
@@ -77,7 +39,7 @@ static int dev_alloc(wf_ctx* ctx, size_t bytes, void** out) {
         for (auto& kv : ctx->pool) cudaFree(kv.second);
         ctx->pool.clear();
         e = cudaMalloc(&p, bytes);
-        if (e != cudaSuccess) return fail(ctx, WF_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+        if (e != cudaSuccess) return wf_fail(ctx, WF_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
     }
     ctx->live[p] = bytes;
     *out = p;
@@ -85,31 +47,21 @@ static int dev_alloc(wf_ctx* ctx, size_t bytes, void** out) {
 }
 // Buffers return to the pool in stream order: all work is issued on ctx->st, so a later user of the
 // same buffer is ordered after the earlier kernels that touched it.
-static void dev_free(wf_ctx* ctx, void* p) {
+void wf_dev_free(wf_ctx* ctx, void* p) {
     if (!p) return;
     auto it = ctx->live.find(p);
     if (it == ctx->live.end()) return;
     ctx->pool.insert({it->second, p});
     ctx->live.erase(it);
 }
-struct wf_mat {
-    SegMatrix m;
-};
-struct wf_tree {
-    int hash_id;
-    size_t nleaves;
-    u64* leaves;  // nleaves x 4 words
-    u64* nodes;   // nleaves x 4 words
-};
-
-static int mat_alloc(wf_ctx* ctx, size_t rows, u32 cols, wf_mat** out) {
+int wf_mat_alloc(wf_ctx* ctx, size_t rows, u32 cols, wf_mat** out) {
     wf_mat* m = new wf_mat();
     m->m.rows = rows;
     m->m.cols = cols;
     m->m.W = seg_width_for(cols);
     m->m.seg_stride = rows * m->m.W;
     void* p;
-    int r = dev_alloc(ctx, m->m.words() * 8, &p);
+    int r = wf_dev_alloc(ctx, m->m.words() * 8, &p);
     if (r != WF_OK) { delete m; return r; }
     m->m.base = (u64*)p;
     *out = m;
@@ -128,15 +80,15 @@ __global__ void pow_table2_kernel(u64* out, const u64* bases, size_t count, size
     if (i < count * nbases) out[i] = gl_pow(bases[i / count], i % count);
 }
 
-static int get_twiddles(wf_ctx* ctx, u32 log_n, const u64** out) {
+int wf_get_twiddles(wf_ctx* ctx, u32 log_n, const u64** out) {
     auto it = ctx->tw.find(log_n);
     if (it != ctx->tw.end()) { *out = it->second; return WF_OK; }
-    if (log_n < 1 || log_n > 32) return fail(ctx, WF_ERR_INVALID, "no 2^%u-th root of unity", log_n);
+    if (log_n < 1 || log_n > 32) return wf_fail(ctx, WF_ERR_INVALID, "no 2^%u-th root of unity", log_n);
     size_t half = log_n >= 1 ? ((size_t)1 << (log_n - 1)) : 1;
     void* p;
     // never returned to the pool: cudaMalloc directly
     cudaError_t e = cudaMalloc(&p, std::max(half * 8, (size_t)16));
-    if (e != cudaSuccess) return fail(ctx, WF_ERR_CUDA, "cudaMalloc twiddles: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return wf_fail(ctx, WF_ERR_CUDA, "cudaMalloc twiddles: %s", cudaGetErrorString(e));
     pow_table_kernel<<<(unsigned)((half + 255) / 256), 256, 0, ctx->st>>>((u64*)p, gl_root_of_unity(log_n), 1, half);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -215,32 +167,32 @@ static void pass_defaults(NttPassParams& p, const SegMatrix& in, const SegMatrix
 static int run_ntt(wf_ctx* ctx, const SegMatrix& in, SegMatrix& out, const SegMatrix* tmp, u32 log_n, int inverse) {
     u32 logR, logC;
     split_log(log_n, in.W, &logR, &logC);
-    if (logC > NTT_MAX_LOGS) return fail(ctx, WF_ERR_UNSUPPORTED, "NTT size 2^%u exceeds the two-pass limit 2^%d", log_n, 2 * NTT_MAX_LOGS);
+    if (logC > NTT_MAX_LOGS) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "NTT size 2^%u exceeds the two-pass limit 2^%d", log_n, 2 * NTT_MAX_LOGS);
     u64 inv_n = gl_inv(((u64)1 << log_n) % GL_P);
     NttPassParams p;
     if (logR == 0) {
         pass_defaults(p, in, out);
         p.logS = (int)logC; p.logR = 0; p.logC = logC; p.inverse = inverse;
-        CKI(get_twiddles(ctx, std::max(log_n, 1u), &p.sub_tw));
+        CKI(wf_get_twiddles(ctx, std::max(log_n, 1u), &p.sub_tw));
         if (inverse) p.cconst = inv_n;
         CK(ntt_launch_pass(NTT_CONTIG, p, in.nseg(), 1, ctx->st));
         ctx->launches++;
         return WF_OK;
     }
-    if (!tmp) return fail(ctx, WF_ERR_STATE, "run_ntt: scratch matrix required");
+    if (!tmp) return wf_fail(ctx, WF_ERR_STATE, "run_ntt: scratch matrix required");
     // pass 1: strided size-R transforms + twiddle w_n^(+-j1*m2) (and 1/n for the inverse)
     pass_defaults(p, in, *tmp);
     p.logS = (int)logR; p.logR = logR; p.logC = logC; p.inverse = inverse;
-    CKI(get_twiddles(ctx, logR, &p.sub_tw));
+    CKI(wf_get_twiddles(ctx, logR, &p.sub_tw));
     p.has_post = 1;
-    CKI(get_twiddles(ctx, log_n, &p.master));
+    CKI(wf_get_twiddles(ctx, log_n, &p.master));
     p.logM = log_n; p.a_mul = 1; p.b_mul = 0; p.cconst = inverse ? inv_n : 1;
     CK(ntt_launch_pass(NTT_STRIDED, p, in.nseg(), 1, ctx->st));
     ctx->launches++;
     // pass 2: contiguous size-C transforms, transposed write-back
     pass_defaults(p, *tmp, out);
     p.logS = (int)logC; p.logR = logR; p.logC = logC; p.inverse = inverse;
-    CKI(get_twiddles(ctx, logC, &p.sub_tw));
+    CKI(wf_get_twiddles(ctx, logC, &p.sub_tw));
     CK(ntt_launch_pass(NTT_CONTIG, p, in.nseg(), 1, ctx->st));
     ctx->launches++;
     return WF_OK;
@@ -250,7 +202,7 @@ static int run_ntt(wf_ctx* ctx, const SegMatrix& in, SegMatrix& out, const SegMa
 static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_n, u32 log_b) {
     u32 logR, logC;
     split_log(log_n, polys.W, &logR, &logC);
-    if (logC > NTT_MAX_LOGS) return fail(ctx, WF_ERR_UNSUPPORTED, "LDE of 2^%u rows exceeds the two-pass limit", log_n);
+    if (logC > NTT_MAX_LOGS) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "LDE of 2^%u rows exceeds the two-pass limit", log_n);
     u32 b = 1u << log_b;
     LdeTables tabs;
     CKI(get_lde_tables(ctx, log_n, log_b, polys.W, &tabs));
@@ -258,7 +210,7 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
     if (logR == 0) {
         pass_defaults(p, polys, out);
         p.logS = (int)logC; p.logR = 0; p.logC = logC;
-        CKI(get_twiddles(ctx, std::max(log_n, 1u), &p.sub_tw));
+        CKI(wf_get_twiddles(ctx, std::max(log_n, 1u), &p.sub_tw));
         p.pre_tab = tabs.pre; p.pre_batch_stride = (size_t)1 << log_n;
         p.out_row_mul = b; p.out_row_add = 1;
         CK(ntt_launch_pass(NTT_CONTIG, p, polys.nseg(), b, ctx->st));
@@ -268,12 +220,12 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
     // scratch Y for one coset
     SegMatrix y = polys;
     void* yp;
-    CKI(dev_alloc(ctx, polys.words() * 8, &yp));
+    CKI(wf_dev_alloc(ctx, polys.words() * 8, &yp));
     y.base = (u64*)yp;
     const u64 *twR, *twC, *twN;
-    CKI(get_twiddles(ctx, logR, &twR));
-    CKI(get_twiddles(ctx, logC, &twC));
-    CKI(get_twiddles(ctx, log_n + log_b, &twN));
+    CKI(wf_get_twiddles(ctx, logR, &twR));
+    CKI(wf_get_twiddles(ctx, logC, &twC));
+    CKI(wf_get_twiddles(ctx, log_n + log_b, &twN));
     for (u32 k = 0; k < b; k++) {
         // pass 1: Y_k[j1][m2] = 7^m2 w_N^((b j1 + k) m2) sum_m1 a[C m1 + m2] (s_k^C)^m1 w_R^(j1 m1)
         pass_defaults(p, polys, y);
@@ -294,7 +246,7 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
         CK(ntt_launch_pass(NTT_CONTIG, p, polys.nseg(), 1, ctx->st));
         ctx->launches++;
     }
-    dev_free(ctx, yp);
+    wf_dev_free(ctx, yp);
     return WF_OK;
 }
 
@@ -342,9 +294,9 @@ uint64_t wf_ctx_launch_count(const wf_ctx* ctx) { return ctx->launches; }
 
 // ---- matrices -----------------------------------------------------------------------------------
 int wf_mat_from_device_columns(wf_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, size_t nrows, wf_mat** out) {
-    if (!ctx || !d_cols || !out || ncols == 0 || nrows == 0) return fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (!ctx || !d_cols || !out || ncols == 0 || nrows == 0) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     wf_mat* m;
-    CKI(mat_alloc(ctx, nrows, ncols, &m));
+    CKI(wf_mat_alloc(ctx, nrows, ncols, &m));
     CK(layout_cols_to_seg(d_cols, nrows, 1, 0, m->m, ctx->st));
     ctx->launches++;
     *out = m;
@@ -354,27 +306,27 @@ int wf_mat_from_device_columns(wf_ctx* ctx, const uint64_t* d_cols, uint32_t nco
 int wf_mat_from_host_columns(wf_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, size_t nrows, int ext_degree,
                              int mont, wf_mat** out) {
     if (!ctx || !cols || !out || ncols == 0 || nrows == 0 || ext_degree < 1 || ext_degree > 3)
-        return fail(ctx, WF_ERR_INVALID, "bad arguments");
+        return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     // stage: host column j (nrows * d words, elements interleaved) -> device [ncols][nrows*d]
     size_t col_words = nrows * ext_degree;
     void* stage;
-    CKI(dev_alloc(ctx, (size_t)ncols * col_words * 8, &stage));
+    CKI(wf_dev_alloc(ctx, (size_t)ncols * col_words * 8, &stage));
     for (uint32_t j = 0; j < ncols; j++)
         CK(cudaMemcpyAsync((u64*)stage + (size_t)j * col_words, cols[j], col_words * 8, cudaMemcpyHostToDevice, ctx->st));
     wf_mat* m;
-    int r = mat_alloc(ctx, nrows, ncols * ext_degree, &m);
-    if (r != WF_OK) { dev_free(ctx, stage); return r; }
+    int r = wf_mat_alloc(ctx, nrows, ncols * ext_degree, &m);
+    if (r != WF_OK) { wf_dev_free(ctx, stage); return r; }
     // base column q = component (q % d) of column (q / d): element (row, q) at stage[(q/d)*col_words + row*d + q%d]
     CK(layout_cols_to_seg((u64*)stage, nrows, ext_degree, mont, m->m, ctx->st));
     ctx->launches++;
-    dev_free(ctx, stage);
+    wf_dev_free(ctx, stage);
     *out = m;
     return WF_OK;
 }
 int wf_mat_select_columns(wf_ctx* ctx, const wf_mat* m, uint32_t first, uint32_t count, wf_mat** out) {
-    if (!ctx || !m || !out || count == 0 || first + count > m->m.cols) return fail(ctx, WF_ERR_INVALID, "bad column range");
+    if (!ctx || !m || !out || count == 0 || first + count > m->m.cols) return wf_fail(ctx, WF_ERR_INVALID, "bad column range");
     wf_mat* o;
-    CKI(mat_alloc(ctx, m->m.rows, count, &o));
+    CKI(wf_mat_alloc(ctx, m->m.rows, count, &o));
     CK(layout_select_cols(m->m, first, o->m, ctx->st));
     ctx->launches++;
     *out = o;
@@ -382,7 +334,7 @@ int wf_mat_select_columns(wf_ctx* ctx, const wf_mat* m, uint32_t first, uint32_t
 }
 int wf_mat_free(wf_ctx* ctx, wf_mat* m) {
     if (!m) return WF_OK;
-    dev_free(ctx, m->m.base);
+    wf_dev_free(ctx, m->m.base);
     delete m;
     return WF_OK;
 }
@@ -390,17 +342,17 @@ size_t wf_mat_rows(const wf_mat* m) { return m->m.rows; }
 uint32_t wf_mat_cols(const wf_mat* m) { return m->m.cols; }
 
 static int mat_export(wf_ctx* ctx, const wf_mat* m, uint64_t* dst, int to_host, int mont, int row_major) {
-    if (!ctx || !m || !dst) return fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (!ctx || !m || !dst) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     size_t words = m->m.rows * m->m.cols;
     u64* d = dst;
     void* tmp = nullptr;
-    if (to_host) { CKI(dev_alloc(ctx, words * 8, &tmp)); d = (u64*)tmp; }
+    if (to_host) { CKI(wf_dev_alloc(ctx, words * 8, &tmp)); d = (u64*)tmp; }
     CK(layout_seg_to_flat(m->m, d, row_major, mont, ctx->st));
     ctx->launches++;
     if (to_host) {
         CK(cudaMemcpyAsync(dst, d, words * 8, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
-        dev_free(ctx, tmp);
+        wf_dev_free(ctx, tmp);
     }
     return WF_OK;
 }
@@ -408,20 +360,20 @@ int wf_mat_to_columns(wf_ctx* ctx, const wf_mat* m, uint64_t* dst, int to_host, 
 int wf_mat_to_rows(wf_ctx* ctx, const wf_mat* m, uint64_t* dst, int to_host, int mont) { return mat_export(ctx, m, dst, to_host, mont, 1); }
 
 int wf_mat_read_rows(wf_ctx* ctx, const wf_mat* m, const uint64_t* positions, size_t k, uint64_t* dst, int mont) {
-    if (!ctx || !m || !positions || !dst) return fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (!ctx || !m || !positions || !dst) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     if (k == 0) return WF_OK;
     for (size_t i = 0; i < k; i++)
-        if (positions[i] >= m->m.rows) return fail(ctx, WF_ERR_INVALID, "row %llu out of range", (unsigned long long)positions[i]);
+        if (positions[i] >= m->m.rows) return wf_fail(ctx, WF_ERR_INVALID, "row %llu out of range", (unsigned long long)positions[i]);
     void *dpos, *dout;
-    CKI(dev_alloc(ctx, k * 8, &dpos));
-    CKI(dev_alloc(ctx, k * m->m.cols * 8, &dout));
+    CKI(wf_dev_alloc(ctx, k * 8, &dpos));
+    CKI(wf_dev_alloc(ctx, k * m->m.cols * 8, &dout));
     CK(cudaMemcpyAsync(dpos, positions, k * 8, cudaMemcpyHostToDevice, ctx->st));
     CK(layout_gather_rows(m->m, (const u64*)dpos, k, (u64*)dout, mont, ctx->st));
     ctx->launches++;
     CK(cudaMemcpyAsync(dst, dout, k * m->m.cols * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    dev_free(ctx, dpos);
-    dev_free(ctx, dout);
+    wf_dev_free(ctx, dpos);
+    wf_dev_free(ctx, dout);
     return WF_OK;
 }
 
@@ -434,20 +386,20 @@ static int log2_exact(size_t n, u32* out) {
 }
 
 static int mat_transform(wf_ctx* ctx, const wf_mat* in, int inverse, wf_mat** out) {
-    if (!ctx || !in || !out) return fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (!ctx || !in || !out) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     u32 log_n;
-    if (log2_exact(in->m.rows, &log_n) || log_n < 1) return fail(ctx, WF_ERR_INVALID, "rows must be a power of two >= 2");
+    if (log2_exact(in->m.rows, &log_n) || log_n < 1) return wf_fail(ctx, WF_ERR_INVALID, "rows must be a power of two >= 2");
     wf_mat* o;
-    CKI(mat_alloc(ctx, in->m.rows, in->m.cols, &o));
+    CKI(wf_mat_alloc(ctx, in->m.rows, in->m.cols, &o));
     SegMatrix tmp = in->m;
     void* tp = nullptr;
     if (log_n > NTT_MAX_LOGS) {
-        int r = dev_alloc(ctx, in->m.words() * 8, &tp);
+        int r = wf_dev_alloc(ctx, in->m.words() * 8, &tp);
         if (r != WF_OK) { wf_mat_free(ctx, o); return r; }
         tmp.base = (u64*)tp;
     }
     int r = run_ntt(ctx, in->m, o->m, tp ? &tmp : nullptr, log_n, inverse);
-    dev_free(ctx, tp);
+    wf_dev_free(ctx, tp);
     if (r != WF_OK) { wf_mat_free(ctx, o); return r; }
     *out = o;
     return WF_OK;
@@ -456,12 +408,12 @@ int wf_mat_interpolate(wf_ctx* ctx, const wf_mat* evals, wf_mat** polys) { retur
 int wf_mat_evaluate(wf_ctx* ctx, const wf_mat* polys, wf_mat** evals) { return mat_transform(ctx, polys, 0, evals); }
 
 int wf_mat_lde(wf_ctx* ctx, const wf_mat* polys, uint32_t log_blowup, wf_mat** lde) {
-    if (!ctx || !polys || !lde) return fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (!ctx || !polys || !lde) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     u32 log_n;
-    if (log2_exact(polys->m.rows, &log_n) || log_n < 1) return fail(ctx, WF_ERR_INVALID, "rows must be a power of two >= 2");
-    if (log_blowup > 7 || log_n + log_blowup > 32) return fail(ctx, WF_ERR_INVALID, "bad blowup");
+    if (log2_exact(polys->m.rows, &log_n) || log_n < 1) return wf_fail(ctx, WF_ERR_INVALID, "rows must be a power of two >= 2");
+    if (log_blowup > 7 || log_n + log_blowup > 32) return wf_fail(ctx, WF_ERR_INVALID, "bad blowup");
     wf_mat* o;
-    CKI(mat_alloc(ctx, polys->m.rows << log_blowup, polys->m.cols, &o));
+    CKI(wf_mat_alloc(ctx, polys->m.rows << log_blowup, polys->m.cols, &o));
     int r = run_lde(ctx, polys->m, o->m, log_n, log_blowup);
     if (r != WF_OK) { wf_mat_free(ctx, o); return r; }
     *lde = o;
@@ -470,7 +422,7 @@ int wf_mat_lde(wf_ctx* ctx, const wf_mat* polys, uint32_t log_blowup, wf_mat** l
 
 int wf_mat_interpolate_with_offset(wf_ctx* ctx, const wf_mat* evals, uint64_t domain_offset, wf_mat** polys) {
     // fft/serial.rs:84-101: iNTT, then coefficient i *= offset^-i (the 1/n is already in the iNTT)
-    if (domain_offset == 0 || domain_offset >= GL_P) return fail(ctx, WF_ERR_INVALID, "bad domain offset");
+    if (domain_offset == 0 || domain_offset >= GL_P) return wf_fail(ctx, WF_ERR_INVALID, "bad domain offset");
     wf_mat* p;
     CKI(mat_transform(ctx, evals, 1, &p));
     CK(layout_scale_rows_by_powers(p->m, gl_inv(domain_offset), ctx->st));
@@ -481,15 +433,15 @@ int wf_mat_interpolate_with_offset(wf_ctx* ctx, const wf_mat* evals, uint64_t do
 
 // ---- commitments --------------------------------------------------------------------------------
 static int tree_alloc(wf_ctx* ctx, int hash_id, size_t nleaves, wf_tree** out) {
-    if (nleaves < 2 || (nleaves & (nleaves - 1))) return fail(ctx, WF_ERR_INVALID, "number of leaves must be a power of two >= 2");
+    if (nleaves < 2 || (nleaves & (nleaves - 1))) return wf_fail(ctx, WF_ERR_INVALID, "number of leaves must be a power of two >= 2");
     wf_tree* t = new wf_tree();
     t->hash_id = hash_id;
     t->nleaves = nleaves;
     void *a, *b;
-    int r = dev_alloc(ctx, nleaves * 32, &a);
+    int r = wf_dev_alloc(ctx, nleaves * 32, &a);
     if (r != WF_OK) { delete t; return r; }
-    r = dev_alloc(ctx, nleaves * 32, &b);
-    if (r != WF_OK) { dev_free(ctx, a); delete t; return r; }
+    r = wf_dev_alloc(ctx, nleaves * 32, &b);
+    if (r != WF_OK) { wf_dev_free(ctx, a); delete t; return r; }
     t->leaves = (u64*)a;
     t->nodes = (u64*)b;
     *out = t;
@@ -504,8 +456,8 @@ static u32 merkle_launches(size_t nleaves) {
     return l;
 }
 int wf_commit_rows(wf_ctx* ctx, int hash_id, const wf_mat* m, wf_tree** out) {
-    if (!ctx || !m || !out) return fail(ctx, WF_ERR_INVALID, "bad arguments");
-    if (hash_id != WF_HASH_BLAKE3_256 && hash_id != WF_HASH_RP64_256) return fail(ctx, WF_ERR_UNSUPPORTED, "unknown hash %d", hash_id);
+    if (!ctx || !m || !out) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (hash_id != WF_HASH_BLAKE3_256 && hash_id != WF_HASH_RP64_256) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "unknown hash %d", hash_id);
     wf_tree* t;
     CKI(tree_alloc(ctx, hash_id, m->m.rows, &t));
     CK(commit_hash_rows(hash_id, m->m, t->leaves, ctx->st));
@@ -515,7 +467,7 @@ int wf_commit_rows(wf_ctx* ctx, int hash_id, const wf_mat* m, wf_tree** out) {
     return WF_OK;
 }
 int wf_tree_from_leaves(wf_ctx* ctx, int hash_id, const uint8_t* leaves, size_t nleaves, int on_device, wf_tree** out) {
-    if (!ctx || !leaves || !out) return fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (!ctx || !leaves || !out) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     wf_tree* t;
     CKI(tree_alloc(ctx, hash_id, nleaves, &t));
     CK(cudaMemcpyAsync(t->leaves, leaves, nleaves * 32, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->st));
@@ -527,20 +479,20 @@ int wf_tree_from_leaves(wf_ctx* ctx, int hash_id, const uint8_t* leaves, size_t 
 }
 int wf_tree_free(wf_ctx* ctx, wf_tree* t) {
     if (!t) return WF_OK;
-    dev_free(ctx, t->leaves);
-    dev_free(ctx, t->nodes);
+    wf_dev_free(ctx, t->leaves);
+    wf_dev_free(ctx, t->nodes);
     delete t;
     return WF_OK;
 }
 size_t wf_tree_num_leaves(const wf_tree* t) { return t->nleaves; }
 int wf_tree_root(wf_ctx* ctx, const wf_tree* t, uint8_t root[32]) {
-    if (!ctx || !t || !root) return fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (!ctx || !t || !root) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     CK(cudaMemcpyAsync(root, t->nodes + 4, 32, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     return WF_OK;
 }
 int wf_tree_to_host(wf_ctx* ctx, const wf_tree* t, uint8_t* leaves, uint8_t* nodes) {
-    if (!ctx || !t) return fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (!ctx || !t) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     if (leaves) CK(cudaMemcpyAsync(leaves, t->leaves, t->nleaves * 32, cudaMemcpyDeviceToHost, ctx->st));
     if (nodes) CK(cudaMemcpyAsync(nodes, t->nodes, t->nleaves * 32, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
@@ -549,18 +501,19 @@ int wf_tree_to_host(wf_ctx* ctx, const wf_tree* t, uint8_t* leaves, uint8_t* nod
 
 // MerkleTree::prove_batch (crypto/src/merkle/mod.rs:217-272) on a device tree: the walk decides
 // which digests are needed (host, indices only), one gather kernel fetches them.
-static int tree_open_many(wf_ctx* ctx, const wf_tree* t, const uint64_t* positions, size_t k, uint8_t* leaves_out,
+}  // extern "C"
+int wf_tree_open_many_bytes(wf_ctx* ctx, const wf_tree* t, const uint64_t* positions, size_t k, uint8_t* leaves_out,
                           ByteVec& proof) {
     size_t n = t->nleaves;
     u32 depth = 0;
     while (((size_t)1 << depth) < n) depth++;
-    if (k == 0) return fail(ctx, WF_ERR_INVALID, "no positions");
+    if (k == 0) return wf_fail(ctx, WF_ERR_INVALID, "no positions");
     std::map<size_t, size_t> index_map;
     for (size_t i = 0; i < k; i++) {
-        if (positions[i] >= n) return fail(ctx, WF_ERR_INVALID, "leaf index out of bounds");
+        if (positions[i] >= n) return wf_fail(ctx, WF_ERR_INVALID, "leaf index out of bounds");
         index_map[positions[i]] = i;
     }
-    if (index_map.size() != k) return fail(ctx, WF_ERR_INVALID, "duplicate leaf index");
+    if (index_map.size() != k) return wf_fail(ctx, WF_ERR_INVALID, "duplicate leaf index");
     std::set<size_t> norm;
     for (size_t i = 0; i < k; i++) norm.insert(positions[i] & ~(size_t)1);
     // gather list: entries < n address nodes[], entries >= n address leaves[entry - n]
@@ -592,16 +545,16 @@ static int tree_open_many(wf_ctx* ctx, const wf_tree* t, const uint64_t* positio
         }
     }
     void *dw, *dg;
-    CKI(dev_alloc(ctx, want.size() * 8, &dw));
-    CKI(dev_alloc(ctx, want.size() * 32, &dg));
+    CKI(wf_dev_alloc(ctx, want.size() * 8, &dw));
+    CKI(wf_dev_alloc(ctx, want.size() * 32, &dg));
     CK(cudaMemcpyAsync(dw, want.data(), want.size() * 8, cudaMemcpyHostToDevice, ctx->st));
     CK(layout_gather_digests(t->nodes, t->leaves, n, (const u64*)dw, want.size(), (u64*)dg, ctx->st));
     ctx->launches++;
     std::vector<u8> got(want.size() * 32);
     CK(cudaMemcpyAsync(got.data(), dg, got.size(), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    dev_free(ctx, dw);
-    dev_free(ctx, dg);
+    wf_dev_free(ctx, dw);
+    wf_dev_free(ctx, dg);
     for (size_t i = 0; i < k; i++) memcpy(leaves_out + i * 32, got.data() + leaf_slot[i] * 32, 32);
     // BatchMerkleProof::write_into (proofs.rs:390-401)
     proof.u8_((u8)depth);
@@ -612,12 +565,13 @@ static int tree_open_many(wf_ctx* ctx, const wf_tree* t, const uint64_t* positio
     }
     return WF_OK;
 }
+extern "C" {
 int wf_tree_open_many(wf_ctx* ctx, const wf_tree* t, const uint64_t* positions, size_t k, uint8_t* leaves_out,
                       uint8_t* proof, size_t* proof_len) {
-    if (!ctx || !t || !positions || !leaves_out || !proof || !proof_len) return fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (!ctx || !t || !positions || !leaves_out || !proof || !proof_len) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     ByteVec bv;
-    CKI(tree_open_many(ctx, t, positions, k, leaves_out, bv));
-    if (bv.v.size() > *proof_len) return fail(ctx, WF_ERR_INVALID, "proof buffer too small (%zu needed)", bv.v.size());
+    CKI(wf_tree_open_many_bytes(ctx, t, positions, k, leaves_out, bv));
+    if (bv.v.size() > *proof_len) return wf_fail(ctx, WF_ERR_INVALID, "proof buffer too small (%zu needed)", bv.v.size());
     memcpy(proof, bv.v.data(), bv.v.size());
     *proof_len = bv.v.size();
     return WF_OK;
@@ -673,33 +627,33 @@ static void host_interpolate_with_offset(std::vector<u64>& v, size_t n, int d, u
 
 int wf_fri_free(wf_ctx* ctx, wf_fri* f) {
     if (!f) return WF_OK;
-    for (auto& l : f->layers) { dev_free(ctx, l.evals); wf_tree_free(ctx, l.tree); }
+    for (auto& l : f->layers) { wf_dev_free(ctx, l.evals); wf_tree_free(ctx, l.tree); }
     delete f;
     return WF_OK;
 }
 
 int wf_fri_build_layers(wf_ctx* ctx, int hash_id, const wf_mat* evals, int d, uint32_t folding, uint32_t rem_max_deg,
                         uint32_t blowup, wf_fri_commit_fn commit, wf_fri_draw_fn draw_alpha, void* user, wf_fri** out) {
-    if (!ctx || !evals || !commit || !draw_alpha || !out) return fail(ctx, WF_ERR_INVALID, "bad arguments");
-    if (d < 1 || d > 3 || (int)evals->m.cols != d) return fail(ctx, WF_ERR_INVALID, "evaluations must have ext_degree base columns");
-    if (folding != 2 && folding != 4 && folding != 8 && folding != 16) return fail(ctx, WF_ERR_UNSUPPORTED, "folding factor %u", folding);
+    if (!ctx || !evals || !commit || !draw_alpha || !out) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (d < 1 || d > 3 || (int)evals->m.cols != d) return wf_fail(ctx, WF_ERR_INVALID, "evaluations must have ext_degree base columns");
+    if (folding != 2 && folding != 4 && folding != 8 && folding != 16) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "folding factor %u", folding);
     size_t len = evals->m.rows;
     u32 logL;
-    if (log2_exact(len, &logL)) return fail(ctx, WF_ERR_INVALID, "domain size must be a power of two");
+    if (log2_exact(len, &logL)) return wf_fail(ctx, WF_ERR_INVALID, "domain size must be a power of two");
     wf_fri* f = new wf_fri();
     f->hash_id = hash_id; f->d = d; f->folding = folding; f->blowup = blowup;
     f->ld = evals->m.W;  // d base columns live in one segment of width W >= d
     const int ld = f->ld;
     // layer 0 evaluations: copy of the segment (the prover keeps its own copy, fri/src/prover/mod.rs:217-221)
     void* cur;
-    CKI(dev_alloc(ctx, len * ld * 8, &cur));
+    CKI(wf_dev_alloc(ctx, len * ld * 8, &cur));
     CK(cudaMemcpyAsync(cur, evals->m.base, len * ld * 8, cudaMemcpyDeviceToDevice, ctx->st));
     size_t max_rem = (size_t)(rem_max_deg + 1) * blowup;  // fri/src/options.rs:85-93
     while (len > max_rem) {
         size_t m = len / folding;
         wf_tree* t;
         int r = tree_alloc(ctx, hash_id, m, &t);
-        if (r != WF_OK) { dev_free(ctx, cur); wf_fri_free(ctx, f); return r; }
+        if (r != WF_OK) { wf_dev_free(ctx, cur); wf_fri_free(ctx, f); return r; }
         CK(fri_hash_layer(hash_id, (u64*)cur, len, d, ld, (int)folding, t->leaves, ctx->st));
         CK(commit_merkle_nodes(hash_id, t->leaves, m, t->nodes, ctx->st));
         ctx->launches += 1 + merkle_launches(m);
@@ -712,9 +666,9 @@ int wf_fri_build_layers(wf_ctx* ctx, int hash_id, const wf_mat* evals, int d, ui
         const u64* master;
         u32 ll = 0;
         while (((size_t)1 << ll) < len) ll++;
-        CKI(get_twiddles(ctx, ll, &master));
+        CKI(wf_get_twiddles(ctx, ll, &master));
         void* nxt;
-        CKI(dev_alloc(ctx, m * ld * 8, &nxt));
+        CKI(wf_dev_alloc(ctx, m * ld * 8, &nxt));
         if (ld > d) CK(cudaMemsetAsync(nxt, 0, m * ld * 8, ctx->st));
         CK(fri_fold_layer((u64*)cur, len, d, ld, (int)folding, alpha, master, (u64*)nxt, ld, ctx->st));
         ctx->launches++;
@@ -726,7 +680,7 @@ int wf_fri_build_layers(wf_ctx* ctx, int hash_id, const wf_mat* evals, int d, ui
     std::vector<u64> raw(len * ld), v(len * d);
     CK(cudaMemcpyAsync(raw.data(), cur, len * ld * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    dev_free(ctx, cur);
+    wf_dev_free(ctx, cur);
     for (size_t i = 0; i < len; i++)
         for (int c = 0; c < d; c++) v[i * d + c] = raw[i * ld + c];
     host_interpolate_with_offset(v, len, d, GL_GENERATOR);
@@ -762,7 +716,7 @@ int wf_fri_build_layers_default_channel(wf_ctx* ctx, int hash_id, const wf_mat* 
     DefaultChannel ch{PublicCoin(hash_id, nullptr, 0), d, {}};
     CKI(wf_fri_build_layers(ctx, hash_id, evals, d, folding, rem_max_deg, blowup, dc_commit, dc_draw, &ch, out));
     if (roots_out) {
-        if (roots_cap < ch.commitments.size() * 32) return fail(ctx, WF_ERR_INVALID, "roots buffer too small");
+        if (roots_cap < ch.commitments.size() * 32) return wf_fail(ctx, WF_ERR_INVALID, "roots buffer too small");
         for (size_t i = 0; i < ch.commitments.size(); i++) memcpy(roots_out + 32 * i, ch.commitments[i].b, 32);
     }
     return WF_OK;
@@ -775,7 +729,7 @@ size_t wf_fri_remainder(const wf_fri* f, uint64_t* coeffs, size_t cap_words) {
 
 int wf_fri_build_proof(wf_ctx* ctx, wf_fri* f, const uint64_t* positions, size_t k, uint8_t* out, size_t* len) {
     // fri/src/prover/mod.rs:254-319 + fri/src/proof.rs:149-163,275-285
-    if (!ctx || !f || !positions || !out || !len) return fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (!ctx || !f || !positions || !out || !len) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     ByteVec bv;
     bv.u8_((u8)f->layers.size());
     std::vector<u64> pos(positions, positions + k);
@@ -800,7 +754,7 @@ int wf_fri_build_proof(wf_ctx* ctx, wf_fri* f, const uint64_t* positions, size_t
         CKI(wf_mat_read_rows(ctx, &tmpm, gpos.data(), gpos.size(), vals.data(), 0));
         std::vector<u8> leaves(nq * 32);
         ByteVec paths;
-        CKI(tree_open_many(ctx, L.tree, pos.data(), nq, leaves.data(), paths));
+        CKI(wf_tree_open_many_bytes(ctx, L.tree, pos.data(), nq, leaves.data(), paths));
         bv.u32_((u32)(vals.size() * 8));
         bv.bytes(vals.data(), vals.size() * 8);
         bv.u32_((u32)paths.v.size());
@@ -809,7 +763,7 @@ int wf_fri_build_proof(wf_ctx* ctx, wf_fri* f, const uint64_t* positions, size_t
     bv.u16_((uint16_t)(f->remainder.size() * 8));
     bv.bytes(f->remainder.data(), f->remainder.size() * 8);
     bv.u8_(0);  // log2(num_partitions = 1)
-    if (bv.v.size() > *len) return fail(ctx, WF_ERR_INVALID, "proof buffer too small (%zu needed)", bv.v.size());
+    if (bv.v.size() > *len) return wf_fail(ctx, WF_ERR_INVALID, "proof buffer too small (%zu needed)", bv.v.size());
     memcpy(out, bv.v.data(), bv.v.size());
     *len = bv.v.size();
     return WF_OK;
@@ -817,7 +771,7 @@ int wf_fri_build_proof(wf_ctx* ctx, wf_fri* f, const uint64_t* positions, size_t
 
 // ---- plain kernels on caller-owned device buffers -------------------------------------------------
 int wf_ntt_dev(wf_ctx* ctx, uint64_t* d_data, uint32_t log_n, uint32_t cols, int inverse) {
-    if (!ctx || !d_data || cols == 0 || log_n < 1) return fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (!ctx || !d_data || cols == 0 || log_n < 1) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     wf_mat *m, *o;
     CKI(wf_mat_from_device_columns(ctx, d_data, cols, (size_t)1 << log_n, &m));
     int r = mat_transform(ctx, m, inverse, &o);
@@ -828,11 +782,11 @@ int wf_ntt_dev(wf_ctx* ctx, uint64_t* d_data, uint32_t log_n, uint32_t cols, int
     return r;
 }
 int wf_hash_rows_dev(wf_ctx* ctx, int hash_id, const uint64_t* d_rows, size_t nrows, uint32_t cols, uint8_t* d_digests) {
-    if (!ctx || !d_rows || !d_digests || cols == 0) return fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (!ctx || !d_rows || !d_digests || cols == 0) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     // a row-major matrix is a single segment of width `cols`; reuse the generic kernel through a
     // one-segment view when cols is a supported width, else convert
     wf_mat* m;
-    CKI(mat_alloc(ctx, nrows, cols, &m));
+    CKI(wf_mat_alloc(ctx, nrows, cols, &m));
     CK(layout_rows_to_seg(d_rows, m->m, ctx->st));
     CK(commit_hash_rows(hash_id, m->m, (u64*)d_digests, ctx->st));
     ctx->launches += 2;
@@ -840,19 +794,19 @@ int wf_hash_rows_dev(wf_ctx* ctx, int hash_id, const uint64_t* d_rows, size_t nr
     return WF_OK;
 }
 int wf_merkle_dev(wf_ctx* ctx, int hash_id, const uint8_t* d_leaves, size_t nleaves, uint8_t* d_nodes) {
-    if (!ctx || !d_leaves || !d_nodes) return fail(ctx, WF_ERR_INVALID, "bad arguments");
-    if (nleaves < 2 || (nleaves & (nleaves - 1))) return fail(ctx, WF_ERR_INVALID, "number of leaves must be a power of two >= 2");
+    if (!ctx || !d_leaves || !d_nodes) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (nleaves < 2 || (nleaves & (nleaves - 1))) return wf_fail(ctx, WF_ERR_INVALID, "number of leaves must be a power of two >= 2");
     CK(commit_merkle_nodes(hash_id, (const u64*)d_leaves, nleaves, (u64*)d_nodes, ctx->st));
     ctx->launches += merkle_launches(nleaves);
     return WF_OK;
 }
 int wf_fri_fold_dev(wf_ctx* ctx, const uint64_t* d_evals, size_t len, int d, uint32_t folding, const uint64_t* alpha,
                     uint64_t* d_next) {
-    if (!ctx || !d_evals || !alpha || !d_next || d < 1 || d > 3) return fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (!ctx || !d_evals || !alpha || !d_next || d < 1 || d > 3) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     u32 ll;
-    if (log2_exact(len, &ll) || len < folding) return fail(ctx, WF_ERR_INVALID, "bad length");
+    if (log2_exact(len, &ll) || len < folding) return wf_fail(ctx, WF_ERR_INVALID, "bad length");
     const u64* master;
-    CKI(get_twiddles(ctx, std::max(ll, 1u), &master));
+    CKI(wf_get_twiddles(ctx, std::max(ll, 1u), &master));
     CK(fri_fold_layer(d_evals, len, d, d, (int)folding, alpha, master, d_next, d, ctx->st));
     ctx->launches++;
     return WF_OK;

@@ -1,0 +1,65 @@
+// internal.hpp — shared host-side definitions of the C-ABI implementation (capi.cu, prover.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/winterfell_b200.h"
+#include "commit.cuh"
+#include "fri.cuh"
+#include "host_transcript.hpp"
+#include "layout.cuh"
+#include "ntt.cuh"
+
+// =================================================================================================
+// context
+// =================================================================================================
+struct LdeTables {
+    u64* pre;    // two-pass: [blowup][R] (s_k^C)^m1 ; single pass: [blowup][n] s_k^m
+    u64* pow7;   // two-pass: [C] 7^m2 ; single pass: null
+};
+
+struct wf_ctx {
+    int device;
+    cudaStream_t st;
+    std::string err;
+    uint64_t launches;
+    std::multimap<size_t, void*> pool;       // free device buffers by size
+    std::map<void*, size_t> live;            // allocated device buffers
+    std::map<u32, u64*> tw;                  // log_n -> w_n^i, i < n/2
+    std::map<std::pair<u32, u32>, LdeTables> lde_tabs;  // (log_n, log_blowup)
+    void* pinned;                            // staging buffer (pinned host)
+    size_t pinned_bytes;
+};
+
+struct wf_mat {
+    SegMatrix m;
+};
+struct wf_tree {
+    int hash_id;
+    size_t nleaves;
+    u64* leaves;  // nleaves x 4 words
+    u64* nodes;   // nleaves x 4 words
+};
+
+int wf_fail(wf_ctx* ctx, int code, const char* fmt, ...);
+int wf_dev_alloc(wf_ctx* ctx, size_t bytes, void** out);
+void wf_dev_free(wf_ctx* ctx, void* p);
+int wf_mat_alloc(wf_ctx* ctx, size_t rows, u32 cols, wf_mat** out);
+int wf_get_twiddles(wf_ctx* ctx, u32 log_n, const u64** out);
+int wf_tree_open_many_bytes(wf_ctx* ctx, const wf_tree* t, const uint64_t* positions, size_t k, uint8_t* leaves_out,
+                            ByteVec& proof);
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t _e = (call);                                                                          \
+        if (_e != cudaSuccess)                                                                            \
+            return wf_fail(ctx, WF_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+    } while (0)
+#define CKI(call)                   \
+    do {                            \
+        int _r = (call);            \
+        if (_r != WF_OK) return _r; \
+    } while (0)

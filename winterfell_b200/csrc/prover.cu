@@ -1,0 +1,514 @@
+// prover.cu — the full proving pipeline on device behind one C-ABI call (wf_prove_fib), i.e. the body
+// of winterfell's Prover::generate_proof (prover/src/lib.rs:282-492) with every hot loop on the GPU:
+//   K1-K4  trace commitment          (ntt.cu, commit.cu)         DefaultTraceLde::new
+//   K5     constraint evaluation     (fib_constraints_kernel)     DefaultConstraintEvaluator::evaluate
+//   K6/K7  composition poly + commit (ntt.cu, commit.cu)         DefaultConstraintCommitment::new
+//   K8     out-of-domain frames      (ood_partial_kernel)         TracePolyTable/CompositionPoly::get_ood_frame
+//   K9/K10 DEEP composition          (deep_eval_kernel)           DeepCompositionPoly::{add_trace_polys, evaluate}
+//   K11    FRI commit phase          (fri.cu)                     FriProver::build_layers
+//   K13    proof-of-work grinding    (host, serial semantics: smallest nonce)
+// The Fiat-Shamir transcript (ProverChannel, prover/src/channel.rs) and the proof wire format
+// (air/src/proof/*.rs) are host code here, bit-exact with the reference.
+//
+// The DEEP composition is computed in EVALUATION form over the LDE domain,
+//   D(x) = (S(x) - S(z)) / (x - z) + (S(x) - S(zg)) / (x - zg),  S = sum_j cc_j T_j + sum_j cc'_j H_j,
+// which is the same polynomial the reference builds in coefficient form by synthetic division
+// (composer/mod.rs:67-210) and evaluates by LDE (:171): exact field arithmetic, identical values
+// (SURVEY.md A.4), but row-parallel and without the extra LDE.
+//
+// Constraint evaluation needs a device functor per AIR (Air::evaluate_transition is user Rust code,
+// air/src/air/mod.rs:210). Built in: the "FibSmall x k" family = k copies of
+// examples/src/fibonacci/fib_small/air.rs:16-69 side by side (k = 1 is the reference example).
+#include <algorithm>
+
+#include "internal.hpp"
+
+// =================================================================================================
+// kernels
+// =================================================================================================
+template <int D>
+__device__ __forceinline__ GlExt<D> ld_ext(const u64* p) {
+    GlExt<D> r;
+#pragma unroll
+    for (int i = 0; i < D; i++) r.v[i] = p[i];
+    return r;
+}
+__device__ __forceinline__ u64 seg_at(const SegMatrix& m, size_t row, u32 col) {
+    return m.base[(size_t)(col / m.W) * m.seg_stride + row * m.W + (col % m.W)];
+}
+
+struct FibEvalParams {
+    SegMatrix lde;      // N x 2k trace LDE
+    SegMatrix out;      // ce x D combined constraint evaluations
+    u32 k, log_n, log_blowup, log_ce_blowup;
+    const u64* tcoef;   // [2k][D] transition coefficients
+    const u64* bcoef0;  // [2k][D] boundary coefficients, group (step 0): column q = value q/2 + 1
+    const u64* bcoef1;  // [k][D]  boundary coefficients, group (step n-1): column 2j+1 = results[j]
+    const u64* results; // [k]
+    const u64* tw_ce;   // w_ce^i, i < ce/2
+    u64 zt[8];          // 1 / (x^n - 1) at CE step i mod ce_blowup
+    u64 last;           // g_trace^(n-1): transition exemption point and divisor offset of group 1
+};
+
+// One CE-domain row per thread (evaluator/default.rs:165-214 evaluate_fragment_main +
+// evaluation_table.rs:317-367 acc_column, fused).
+template <int D>
+__global__ void __launch_bounds__(256) fib_constraints_kernel(FibEvalParams p) {
+    const size_t ce = (size_t)1 << (p.log_n + p.log_ce_blowup);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ce) return;
+    const size_t N = (size_t)1 << (p.log_n + p.log_blowup);
+    const u32 lde_shift = p.log_blowup - p.log_ce_blowup;
+    const size_t ls = i << lde_shift;
+    const size_t nx = (ls + ((size_t)1 << p.log_blowup)) & (N - 1);  // trace_lde/default/mod.rs:169-180
+    GlExt<D> T = ext_zero<D>(), B0 = ext_zero<D>(), B1 = ext_zero<D>();
+    for (u32 j = 0; j < p.k; j++) {
+        u64 c0 = seg_at(p.lde, ls, 2 * j), c1 = seg_at(p.lde, ls, 2 * j + 1);
+        u64 n0 = seg_at(p.lde, nx, 2 * j), n1 = seg_at(p.lde, nx, 2 * j + 1);
+        u64 t0 = gl_sub(n0, gl_add(c0, c1));  // fib_small/air.rs:58
+        u64 t1 = gl_sub(n1, gl_add(c1, n0));  // :59
+        T = ext_add(T, ext_mul_base(ld_ext<D>(p.tcoef + (size_t)(2 * j) * D), t0));
+        T = ext_add(T, ext_mul_base(ld_ext<D>(p.tcoef + (size_t)(2 * j + 1) * D), t1));
+        u64 v = j + 1;
+        B0 = ext_add(B0, ext_mul_base(ld_ext<D>(p.bcoef0 + (size_t)(2 * j) * D), gl_sub(c0, v)));
+        B0 = ext_add(B0, ext_mul_base(ld_ext<D>(p.bcoef0 + (size_t)(2 * j + 1) * D), gl_sub(c1, v)));
+        B1 = ext_add(B1, ext_mul_base(ld_ext<D>(p.bcoef1 + (size_t)j * D), gl_sub(c1, p.results[j])));
+    }
+    const u32 half = (u32)(ce >> 1);
+    u64 w = p.tw_ce[i & (half - 1)];
+    if (i & half) w = gl_neg(w);
+    u64 x = gl_mul(w, GL_GENERATOR);  // domain.rs:123 get_ce_x_at
+    u64 d0 = gl_sub(x, 1), d1 = gl_sub(x, p.last);
+    u64 inv01 = gl_inv(gl_mul(d0, d1));
+    u64 z0 = gl_mul(inv01, d1), z1 = gl_mul(inv01, d0);                      // 1/(x - 1), 1/(x - g^(n-1))
+    u64 zt = gl_mul(p.zt[i & (((size_t)1 << p.log_ce_blowup) - 1)], d1);     // e(x) / (x^n - 1)
+    GlExt<D> acc = ext_add(ext_add(ext_mul_base(T, zt), ext_mul_base(B0, z0)), ext_mul_base(B1, z1));
+    u64* o = p.out.base + i * p.out.W;
+#pragma unroll
+    for (int q = 0; q < D; q++) o[q] = acc.v[q];
+}
+
+// composition_poly.rs:128-140 segment(): column j = coefficients [j*n, (j+1)*n) of the interpolated
+// CE-domain polynomial; each is an extension column of D base columns.
+__global__ void comp_split_kernel(SegMatrix coefs, size_t n, u32 kc, int D, SegMatrix out) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = n * kc * D;
+    if (idx >= total) return;
+    size_t i = idx / (kc * D);
+    u32 col = (u32)(idx % (kc * D));
+    u32 j = col / D, comp = col % D;
+    u64 v = coefs.base[(j * n + i) * coefs.W + comp];
+    out.base[(size_t)(col / out.W) * out.seg_stride + i * out.W + (col % out.W)] = v;
+}
+
+// Horner evaluation of every base-coefficient column at an extension point, as per-chunk partial
+// sums (polynom::eval, math/src/polynom/mod.rs:55-62; ColMatrix::evaluate_columns_at :245).
+// Block = 256 threads x OOD_PER_THREAD coefficients of one segment; partial[seg col][chunk] =
+// z^(chunk start) * sum_{m in chunk} a_m z^(m - start).
+#define OOD_PER_THREAD 16
+template <int D>
+__global__ void __launch_bounds__(256) ood_partial_kernel(SegMatrix polys, GlExt<D> z, u64* partial /*[cols][chunks][D]*/,
+                                                          u32 chunks) {
+    const u32 g = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
+    const int W = polys.W;
+    const size_t n = polys.rows;
+    const size_t start = ((size_t)chunk * 256 + t) * OOD_PER_THREAD;
+    GlExt<D> acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) acc[q] = ext_zero<D>();
+    const u64* base = polys.base + (size_t)g * polys.seg_stride;
+    for (int r = OOD_PER_THREAD - 1; r >= 0; r--) {
+        size_t row = start + r;
+        if (row >= n) continue;
+        for (int q = 0; q < W; q++) {
+            acc[q] = ext_mul(acc[q], z);
+            acc[q].v[0] = gl_add(acc[q].v[0], base[row * W + q]);
+        }
+    }
+    GlExt<D> zp = ext_pow(z, start);  // z^(first row of this thread)
+    __shared__ u64 red[8][8][D];
+    for (int q = 0; q < W; q++) {
+        GlExt<D> v = ext_mul(acc[q], zp);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int c = 0; c < D; c++) v.v[c] = gl_add(v.v[c], __shfl_down_sync(0xffffffffu, v.v[c], off));
+        }
+        if ((t & 31) == 0) {
+#pragma unroll
+            for (int c = 0; c < D; c++) red[t >> 5][q][c] = v.v[c];
+        }
+    }
+    __syncthreads();
+    if (t < (u32)W) {
+        u32 col = g * W + t;
+        if (col < polys.cols) {
+            GlExt<D> s = ext_zero<D>();
+            for (int wp = 0; wp < 8; wp++) s = ext_add(s, ld_ext<D>(&red[wp][t][0]));
+            u64* o = partial + ((size_t)col * chunks + chunk) * D;
+#pragma unroll
+            for (int c = 0; c < D; c++) o[c] = s.v[c];
+        }
+    }
+}
+template <int D>
+__global__ void ood_reduce_kernel(const u64* partial, u32 cols, u32 chunks, u64* out /*[cols][D]*/) {
+    u32 col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= cols) return;
+    GlExt<D> s = ext_zero<D>();
+    for (u32 c = 0; c < chunks; c++) s = ext_add(s, ld_ext<D>(partial + ((size_t)col * chunks + c) * D));
+    for (int c = 0; c < D; c++) out[(size_t)col * D + c] = s.v[c];
+}
+
+struct DeepParams {
+    SegMatrix trace;   // N x c
+    SegMatrix cons;    // N x kc*D
+    SegMatrix out;     // N x D
+    u32 c, kc, log_N;
+    const u64* tcc;    // [c][D]  DEEP coefficients for trace columns
+    const u64* ccc;    // [kc][D] DEEP coefficients for composition columns
+    const u64* tw_N;   // w_N^i, i < N/2
+};
+#define DEEP_ROWS 4
+// DeepCompositionPoly in evaluation form; DEEP_ROWS rows per thread share one batch inversion.
+template <int D>
+__global__ void __launch_bounds__(256) deep_eval_kernel(DeepParams p, GlExt<D> z, GlExt<D> zg, GlExt<D> Sz, GlExt<D> Szg) {
+    const size_t N = (size_t)1 << p.log_N;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    GlExt<D> S[DEEP_ROWS], den[2 * DEEP_ROWS];
+    const u32 half = (u32)(N >> 1);
+#pragma unroll
+    for (int r = 0; r < DEEP_ROWS; r++) {
+        size_t row = tid + r * stride;
+        S[r] = ext_zero<D>();
+        den[2 * r] = ext_from_base<D>(1);
+        den[2 * r + 1] = ext_from_base<D>(1);
+        if (row >= N) continue;
+        for (u32 j = 0; j < p.c; j++) S[r] = ext_add(S[r], ext_mul_base(ld_ext<D>(p.tcc + (size_t)j * D), seg_at(p.trace, row, j)));
+        for (u32 j = 0; j < p.kc; j++) {
+            GlExt<D> hv;
+#pragma unroll
+            for (int q = 0; q < D; q++) hv.v[q] = seg_at(p.cons, row, j * D + q);
+            S[r] = ext_add(S[r], ext_mul(ld_ext<D>(p.ccc + (size_t)j * D), hv));
+        }
+        u64 w = p.tw_N[row & (half - 1)];
+        if (row & half) w = gl_neg(w);
+        GlExt<D> x = ext_from_base<D>(gl_mul(w, GL_GENERATOR));
+        den[2 * r] = ext_sub(x, z);
+        den[2 * r + 1] = ext_sub(x, zg);
+    }
+    // batch inversion (math/src/utils/mod.rs:169 Montgomery trick); denominators are never zero
+    // (z is outside the base-field LDE domain with overwhelming probability; a zero would also
+    // break the reference's synthetic division)
+    GlExt<D> pre[2 * DEEP_ROWS];
+    GlExt<D> run = ext_from_base<D>(1);
+#pragma unroll
+    for (int q = 0; q < 2 * DEEP_ROWS; q++) { pre[q] = run; run = ext_mul(run, den[q]); }
+    run = ext_inv(run);
+#pragma unroll
+    for (int q = 2 * DEEP_ROWS - 1; q >= 0; q--) { GlExt<D> inv = ext_mul(run, pre[q]); run = ext_mul(run, den[q]); den[q] = inv; }
+#pragma unroll
+    for (int r = 0; r < DEEP_ROWS; r++) {
+        size_t row = tid + r * stride;
+        if (row >= N) continue;
+        GlExt<D> v = ext_add(ext_mul(ext_sub(S[r], Sz), den[2 * r]), ext_mul(ext_sub(S[r], Szg), den[2 * r + 1]));
+        u64* o = p.out.base + row * p.out.W;
+#pragma unroll
+        for (int q = 0; q < D; q++) o[q] = v.v[q];
+    }
+}
+
+// =================================================================================================
+// host orchestration
+// =================================================================================================
+namespace {
+
+struct Options {
+    u32 num_queries, blowup, grinding, ext, folding, rem_max_deg, batch_c, batch_d, num_partitions, hash_rate;
+    int hash_id;
+};
+
+template <int D>
+struct Channel {  // ProverChannel (prover/src/channel.rs)
+    PublicCoin coin;
+    ByteVec commitments;
+    Channel(int h, const std::vector<u64>& seed) : coin(h, seed.data(), seed.size()) {}
+    void commit(const u8 root[32]) {  // commit_trace / commit_constraints / commit_fri_layer
+        commitments.bytes(root, 32);
+        Digest d;
+        memcpy(d.b, root, 32);
+        coin.reseed(d);
+    }
+    GlExt<D> draw() {
+        GlExt<D> r = ext_zero<D>();
+        coin.draw(D, r.v);
+        return r;
+    }
+    // air/src/air/coefficients.rs:201-218: Linear / Algebraic / Horner batching
+    std::vector<GlExt<D>> draw_coeffs(u32 method, size_t n) {
+        std::vector<GlExt<D>> r;
+        if (method == 0) { for (size_t i = 0; i < n; i++) r.push_back(draw()); return r; }
+        GlExt<D> a = draw(), x = ext_from_base<D>(1);
+        for (size_t i = 0; i < n; i++) { r.push_back(x); x = ext_mul(x, a); }
+        if (method == 2) std::reverse(r.begin(), r.end());
+        return r;
+    }
+};
+template <int D>
+void fri_commit_cb(void* u, const uint8_t root[32]) { ((Channel<D>*)u)->commit(root); }
+template <int D>
+void fri_draw_cb(void* u, uint64_t* alpha) { GlExt<D> a = ((Channel<D>*)u)->draw(); for (int i = 0; i < D; i++) alpha[i] = a.v[i]; }
+
+template <int D>
+int upload_ext(wf_ctx* ctx, const std::vector<GlExt<D>>& v, size_t first, size_t count, u64** out) {
+    void* p;
+    CKI(wf_dev_alloc(ctx, std::max(count, (size_t)1) * D * 8, &p));
+    std::vector<u64> flat(count * D);
+    for (size_t i = 0; i < count; i++) for (int q = 0; q < D; q++) flat[i * D + q] = v[first + i].v[q];
+    CK(cudaMemcpyAsync(p, flat.data(), flat.size() * 8, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));  // `flat` is a stack object
+    *out = (u64*)p;
+    return WF_OK;
+}
+
+// evaluate all columns of a coefficient matrix at extension point z -> host vector [cols][D]
+template <int D>
+int ood_eval(wf_ctx* ctx, const wf_mat* polys, const GlExt<D>& z, std::vector<GlExt<D>>& out) {
+    const size_t n = polys->m.rows;
+    const u32 chunks = (u32)((n + 256 * OOD_PER_THREAD - 1) / (256 * OOD_PER_THREAD));
+    const u32 cols = polys->m.cols;
+    void *part, *res;
+    CKI(wf_dev_alloc(ctx, (size_t)cols * chunks * D * 8, &part));
+    CKI(wf_dev_alloc(ctx, (size_t)cols * D * 8, &res));
+    ood_partial_kernel<D><<<dim3(chunks, polys->m.nseg()), 256, 0, ctx->st>>>(polys->m, z, (u64*)part, chunks);
+    ood_reduce_kernel<D><<<(cols + 63) / 64, 64, 0, ctx->st>>>((const u64*)part, cols, chunks, (u64*)res);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    std::vector<u64> host((size_t)cols * D);
+    CK(cudaMemcpyAsync(host.data(), res, host.size() * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    wf_dev_free(ctx, part);
+    wf_dev_free(ctx, res);
+    out.resize(cols);
+    for (u32 j = 0; j < cols; j++) for (int q = 0; q < D; q++) out[j].v[q] = host[(size_t)j * D + q];
+    return WF_OK;
+}
+
+template <int D>
+void write_elems(ByteVec& w, const std::vector<GlExt<D>>& v) {
+    for (auto& e : v) for (int q = 0; q < D; q++) w.u64_(e.v[q]);
+}
+
+// Queries::new (air/src/proof/queries.rs:51-78) + Serializable (:138-146)
+int write_queries(wf_ctx* ctx, const wf_mat* m, const wf_tree* t, const std::vector<u64>& pos, ByteVec& w) {
+    std::vector<u64> rows(pos.size() * m->m.cols);
+    CKI(wf_mat_read_rows(ctx, m, pos.data(), pos.size(), rows.data(), 0));
+    std::vector<u8> leaves(pos.size() * 32);
+    ByteVec proof;
+    CKI(wf_tree_open_many_bytes(ctx, t, pos.data(), pos.size(), leaves.data(), proof));
+    w.usize(rows.size() * 8);
+    w.bytes(rows.data(), rows.size() * 8);
+    w.usize(proof.v.size());
+    w.bytes(proof.v.data(), proof.v.size());
+    return WF_OK;
+}
+
+template <int D>
+int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, u32 k, u32 log_n, const u64* results, const Options& o,
+              std::vector<u8>& proof_out) {
+    const int h = o.hash_id;
+    const size_t n = (size_t)1 << log_n;
+    u32 log_b = 0;
+    while ((1u << log_b) < o.blowup) log_b++;
+    const size_t N = n << log_b;
+    const u32 c = 2 * k, kc = 1, log_ceb = 1;  // degree-1 constraints: ce_blowup 2, one composition column
+    const u32 n_tr = 2 * k, n_as = 3 * k;
+    // ---- channel seed: Context::to_elements || pub inputs (channel.rs:57-82, context.rs:119-136) ----
+    std::vector<u64> seed = {((u64)c << 8), (u64)n, 1, 0xFFFFFFFFULL, (u64)(n_tr + n_as),
+                             ((u64)o.ext << 24) | ((u64)o.folding << 16) | ((u64)o.rem_max_deg << 8) | o.blowup,
+                             o.grinding, o.num_queries};
+    for (u32 j = 0; j < k; j++) seed.push_back(results[j]);
+    Channel<D> ch(h, seed);
+
+    // ---- 1. trace commitment (lib.rs:497-522) ----
+    wf_mat *trace = nullptr, *polys = nullptr, *lde = nullptr;
+    wf_tree* ttree = nullptr;
+    CKI(wf_mat_from_host_columns(ctx, trace_cols, c, n, 1, mont, &trace));
+    CKI(wf_mat_interpolate(ctx, trace, &polys));
+    wf_mat_free(ctx, trace);
+    CKI(wf_mat_lde(ctx, polys, log_b, &lde));
+    CKI(wf_commit_rows(ctx, h, lde, &ttree));
+    u8 root[32];
+    CKI(wf_tree_root(ctx, ttree, root));
+    ch.commit(root);
+
+    // ---- 2. constraint evaluation (lib.rs:373-378) ----
+    std::vector<GlExt<D>> cc = ch.draw_coeffs(o.batch_c, n_tr + n_as);
+    // boundary coefficients follow the assertions sorted by (stride, first_step, column)
+    // (air/src/air/assertions/mod.rs:301-315): 2k assertions at step 0, then k at step n-1
+    u64 *d_tc, *d_b0, *d_b1, *d_res;
+    CKI(upload_ext<D>(ctx, cc, 0, n_tr, &d_tc));
+    CKI(upload_ext<D>(ctx, cc, n_tr, 2 * k, &d_b0));
+    CKI(upload_ext<D>(ctx, cc, n_tr + 2 * k, k, &d_b1));
+    {
+        void* p;
+        CKI(wf_dev_alloc(ctx, k * 8, &p));
+        CK(cudaMemcpyAsync(p, results, k * 8, cudaMemcpyHostToDevice, ctx->st));
+        d_res = (u64*)p;
+    }
+    const size_t ce = n << log_ceb;
+    wf_mat* comp;
+    CKI(wf_mat_alloc(ctx, ce, D, &comp));
+    if (comp->m.W > D) CK(cudaMemsetAsync(comp->m.base, 0, comp->m.words() * 8, ctx->st));
+    {
+        FibEvalParams p;
+        p.lde = lde->m; p.out = comp->m; p.k = k; p.log_n = log_n; p.log_blowup = log_b; p.log_ce_blowup = log_ceb;
+        p.tcoef = d_tc; p.bcoef0 = d_b0; p.bcoef1 = d_b1; p.results = d_res;
+        CKI(wf_get_twiddles(ctx, log_n + log_ceb, &p.tw_ce));
+        u64 g_tr = gl_root_of_unity(log_n);
+        p.last = gl_pow(g_tr, n - 1);
+        // x^n over the CE domain takes ce_blowup values: (7 w_ce^i)^n = 7^n * w_ceb^i
+        u64 o_n = gl_pow(GL_GENERATOR, n), w_ceb = gl_root_of_unity(log_ceb);
+        for (u32 i = 0; i < (1u << log_ceb); i++) p.zt[i] = gl_inv(gl_sub(gl_mul(o_n, gl_pow(w_ceb, i)), 1));
+        fib_constraints_kernel<D><<<(unsigned)((ce + 255) / 256), 256, 0, ctx->st>>>(p);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    // ---- 3. composition polynomial + commitment (lib.rs:527-552) ----
+    wf_mat *ccoefs, *cpolys, *clde;
+    wf_tree* ctree;
+    CKI(wf_mat_interpolate_with_offset(ctx, comp, GL_GENERATOR, &ccoefs));
+    wf_mat_free(ctx, comp);
+    CKI(wf_mat_alloc(ctx, n, kc * D, &cpolys));
+    if (cpolys->m.W > (int)(kc * D)) CK(cudaMemsetAsync(cpolys->m.base, 0, cpolys->m.words() * 8, ctx->st));
+    comp_split_kernel<<<(unsigned)((n * kc * D + 255) / 256), 256, 0, ctx->st>>>(ccoefs->m, n, kc, D, cpolys->m);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    wf_mat_free(ctx, ccoefs);
+    CKI(wf_mat_lde(ctx, cpolys, log_b, &clde));
+    CKI(wf_commit_rows(ctx, h, clde, &ctree));
+    CKI(wf_tree_root(ctx, ctree, root));
+    ch.commit(root);
+
+    // ---- 4. out-of-domain frames (lib.rs:392-401) ----
+    GlExt<D> z = ch.draw();
+    GlExt<D> zg = ext_mul_base(z, gl_root_of_unity(log_n));
+    std::vector<GlExt<D>> t_cur, t_nxt, qb_cur, qb_nxt;
+    CKI(ood_eval<D>(ctx, polys, z, t_cur));
+    CKI(ood_eval<D>(ctx, polys, zg, t_nxt));
+    CKI(ood_eval<D>(ctx, cpolys, z, qb_cur));   // per base component column
+    CKI(ood_eval<D>(ctx, cpolys, zg, qb_nxt));
+    // H_j(z) = sum_comp phi^comp * (component column evaluated at z)
+    auto combine = [&](const std::vector<GlExt<D>>& comp_evals) {
+        std::vector<GlExt<D>> r(kc);
+        for (u32 j = 0; j < kc; j++) {
+            GlExt<D> acc = ext_zero<D>();
+            for (int q = 0; q < D; q++) {
+                GlExt<D> basis = ext_zero<D>();
+                basis.v[q] = 1;
+                acc = ext_add(acc, ext_mul(basis, comp_evals[j * D + q]));
+            }
+            r[j] = acc;
+        }
+        return r;
+    };
+    std::vector<GlExt<D>> q_cur = combine(qb_cur), q_nxt = combine(qb_nxt);
+    ByteVec ood_t, ood_q;  // OodFrame (air/src/proof/ood_frame.rs:59-72, :95-108)
+    ood_t.u8_(2); write_elems<D>(ood_t, t_cur); write_elems<D>(ood_t, t_nxt);
+    ood_q.u8_(2); write_elems<D>(ood_q, q_cur); write_elems<D>(ood_q, q_nxt);
+    {
+        ByteVec m;  // merge_ood_evaluations (:335-349): cur(trace, quotient), next(trace, quotient)
+        write_elems<D>(m, t_cur); write_elems<D>(m, q_cur); write_elems<D>(m, t_nxt); write_elems<D>(m, q_nxt);
+        Digest dg = hh_hash_elements(h, (const u64*)m.v.data(), m.v.size() / 8);
+        ch.coin.reseed(dg);  // channel.rs:109-112 (not added to the commitments)
+    }
+    // ---- 5. DEEP composition (lib.rs:403-440), evaluation form ----
+    std::vector<GlExt<D>> dc = ch.draw_coeffs(o.batch_d, c + kc);
+    GlExt<D> Sz = ext_zero<D>(), Szg = ext_zero<D>();
+    for (u32 j = 0; j < c; j++) { Sz = ext_add(Sz, ext_mul(dc[j], t_cur[j])); Szg = ext_add(Szg, ext_mul(dc[j], t_nxt[j])); }
+    for (u32 j = 0; j < kc; j++) { Sz = ext_add(Sz, ext_mul(dc[c + j], q_cur[j])); Szg = ext_add(Szg, ext_mul(dc[c + j], q_nxt[j])); }
+    u64 *d_dt, *d_dq;
+    CKI(upload_ext<D>(ctx, dc, 0, c, &d_dt));
+    CKI(upload_ext<D>(ctx, dc, c, kc, &d_dq));
+    wf_mat* deep;
+    CKI(wf_mat_alloc(ctx, N, D, &deep));
+    if (deep->m.W > D) CK(cudaMemsetAsync(deep->m.base, 0, deep->m.words() * 8, ctx->st));
+    {
+        DeepParams p;
+        p.trace = lde->m; p.cons = clde->m; p.out = deep->m; p.c = c; p.kc = kc; p.log_N = log_n + log_b;
+        p.tcc = d_dt; p.ccc = d_dq;
+        CKI(wf_get_twiddles(ctx, log_n + log_b, &p.tw_N));
+        size_t threads = (N + DEEP_ROWS - 1) / DEEP_ROWS;
+        deep_eval_kernel<D><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->st>>>(p, z, zg, Sz, Szg);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    // ---- 6. FRI (lib.rs:442-448) ----
+    wf_fri* fri;
+    CKI(wf_fri_build_layers(ctx, h, deep, D, o.folding, o.rem_max_deg, o.blowup, fri_commit_cb<D>, fri_draw_cb<D>, &ch, &fri));
+    wf_mat_free(ctx, deep);
+    // ---- 7. grinding + query positions (channel.rs:151-184; serial semantics: smallest nonce) ----
+    u64 nonce = 1;
+    while (ch.coin.check_leading_zeros(nonce) < o.grinding) nonce++;
+    std::vector<u64> pos;
+    if (!ch.coin.draw_integers(o.num_queries, N, nonce, pos)) return wf_fail(ctx, WF_ERR_STATE, "failed to draw query positions");
+    std::sort(pos.begin(), pos.end());
+    pos.erase(std::unique(pos.begin(), pos.end()), pos.end());
+    // ---- 8. proof object (lib.rs:464-489; air/src/proof/mod.rs:189-200) ----
+    ByteVec w;
+    // Context (context.rs:142-151): TraceInfo, modulus, ProofOptions, num_constraints
+    w.u8_((u8)c); w.u8_(0); w.u8_(0); w.u8_((u8)log_n); w.u16_(0);
+    w.u8_(8); w.u64_(GL_P);
+    w.u8_((u8)o.num_queries); w.u8_((u8)o.blowup); w.u8_((u8)o.grinding); w.u8_((u8)o.ext); w.u8_((u8)o.folding);
+    w.u8_((u8)o.rem_max_deg); w.u8_((u8)o.batch_c); w.u8_((u8)o.batch_d); w.u8_((u8)o.num_partitions); w.u8_((u8)o.hash_rate);
+    w.usize(n_tr + n_as);
+    w.u8_((u8)pos.size());
+    w.u16_((uint16_t)ch.commitments.v.size());
+    w.bytes(ch.commitments.v.data(), ch.commitments.v.size());
+    CKI(write_queries(ctx, lde, ttree, pos, w));
+    CKI(write_queries(ctx, clde, ctree, pos, w));
+    w.u16_((uint16_t)ood_t.v.size()); w.bytes(ood_t.v.data(), ood_t.v.size());
+    w.u16_((uint16_t)ood_q.v.size()); w.bytes(ood_q.v.data(), ood_q.v.size());
+    {
+        std::vector<u8> fp(1 << 22);
+        size_t fl = fp.size();
+        CKI(wf_fri_build_proof(ctx, fri, pos.data(), pos.size(), fp.data(), &fl));
+        w.bytes(fp.data(), fl);
+    }
+    w.u64_(nonce);
+    proof_out.swap(w.v);
+    wf_fri_free(ctx, fri);
+    for (wf_mat* m : {polys, lde, cpolys, clde}) wf_mat_free(ctx, m);
+    wf_tree_free(ctx, ttree);
+    wf_tree_free(ctx, ctree);
+    for (u64* p : {d_tc, d_b0, d_b1, d_res, d_dt, d_dq}) wf_dev_free(ctx, p);
+    return WF_OK;
+}
+
+}  // namespace
+
+extern "C" int wf_prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, uint32_t k, uint32_t log_n,
+                            const uint64_t* results, const uint32_t* opts, uint8_t* proof, size_t* proof_len) {
+    if (!ctx || !trace_cols || !results || !opts || !proof || !proof_len || k == 0 || 2 * k > 255 || log_n < 3)
+        return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    Options o;
+    o.num_queries = opts[0]; o.blowup = opts[1]; o.grinding = opts[2]; o.ext = opts[3]; o.folding = opts[4];
+    o.rem_max_deg = opts[5]; o.batch_c = opts[6]; o.batch_d = opts[7]; o.hash_id = (int)opts[8];
+    o.num_partitions = 1; o.hash_rate = 1;
+    if (o.blowup < 2 || (o.blowup & (o.blowup - 1)) || o.num_queries == 0 || o.num_queries > 255 || o.batch_c > 2 || o.batch_d > 2)
+        return wf_fail(ctx, WF_ERR_INVALID, "bad proof options");
+    std::vector<u8> out;
+    int r;
+    switch (o.ext) {
+        case 1: r = prove_fib<1>(ctx, trace_cols, mont, k, log_n, results, o, out); break;
+        case 2: r = prove_fib<2>(ctx, trace_cols, mont, k, log_n, results, o, out); break;
+        case 3: r = prove_fib<3>(ctx, trace_cols, mont, k, log_n, results, o, out); break;
+        default: return wf_fail(ctx, WF_ERR_UNSUPPORTED, "field extension %u", o.ext);
+    }
+    if (r != WF_OK) return r;
+    if (out.size() > *proof_len) return wf_fail(ctx, WF_ERR_INVALID, "proof buffer too small (%zu needed)", out.size());
+    memcpy(proof, out.data(), out.size());
+    *proof_len = out.size();
+    return WF_OK;
+}
