@@ -58,6 +58,11 @@ int wf_ctx_sync(wf_ctx* ctx);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 uint64_t wf_ctx_launch_count(const wf_ctx* ctx);
 const char* wf_version(void);
+/* stage tracing (the reference's `tracing` spans, prover/src/lib.rs:312-466): when on, the proving
+ * entry points record a CUDA event at every stage boundary; wf_ctx_stage_times returns the stage
+ * names (comma separated) and their durations in ms since the previous boundary, and resets. */
+int wf_ctx_set_profiling(wf_ctx* ctx, int on);
+int wf_ctx_stage_times(wf_ctx* ctx, char* names, size_t names_cap, float* ms, size_t* count);
 
 /* ---- matrices --------------------------------------------------------------------------------- */
 /* ColMatrix<E> (prover/src/matrix/col_matrix.rs:33): `ncols` host columns of `nrows` elements of
@@ -141,6 +146,14 @@ int wf_fri_free(wf_ctx* ctx, wf_fri* f);
  * (ProofOptions::new, air/src/options.rs:132). *proof_len: in = capacity, out = bytes written. */
 int wf_prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, uint32_t k, uint32_t log_n,
                  const uint64_t* results, const uint32_t* opts, uint8_t* proof, size_t* proof_len);
+
+/* same, trace already on the device: column-major [2k][2^log_n], canonical words */
+int wf_prove_fib_dev(wf_ctx* ctx, const uint64_t* d_trace, uint32_t k, uint32_t log_n, const uint64_t* results,
+                     const uint32_t* opts, uint8_t* proof, size_t* proof_len);
+
+/* ProverChannel::grind_query_seed (prover/src/channel.rs:169-184), serial semantics: the SMALLEST
+ * nonce >= 1 with trailing_zeros(first 8 LE bytes of H::merge_with_int(seed, nonce)) >= grinding. */
+int wf_grind(wf_ctx* ctx, int hash_id, const uint8_t seed[32], uint32_t grinding, uint64_t* nonce);
 
 /* ---- plain kernels on caller-owned DEVICE buffers (unit parity + bench legs) ------------------- */
 /* in-place NTT (inverse=0) / iNTT (inverse=1) of `cols` columns, column-major [cols][n], n = 1 << log_n */

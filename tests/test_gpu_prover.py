@@ -58,3 +58,13 @@ def test_montgomery_trace_input(ctx, oracle):
     tm = np.array([[oracle.to_mont(int(v)) for v in row] for row in trace], dtype=np.uint64)
     opts = oracle.make_opts(folding=8, rem_max_deg=31, grinding=2)
     assert ctx.prove_fib(tm, results, opts, mont=True) == oracle.prove_fib(trace, results, opts)
+
+
+@pytest.mark.parametrize("h,g", [(wf.HASH_BLAKE3_256, 16), (wf.HASH_BLAKE3_256, 21), (wf.HASH_RP64_256, 10)])
+def test_grinding_smallest_nonce(ctx, oracle, h, g):
+    # prover/src/channel.rs:173-175 (serial branch): smallest nonce
+    coin = oracle.RandomCoin(h, [1, 2, 3, g])
+    want = 1
+    while coin.leading_zeros(want) < g:
+        want += 1
+    assert ctx.grind(h, coin.seed, g) == want

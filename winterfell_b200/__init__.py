@@ -36,6 +36,8 @@ _SIGS = [
     ("wf_ctx_sync", C.c_int, [vp]),
     ("wf_ctx_launch_count", C.c_uint64, [vp]),
     ("wf_version", C.c_char_p, []),
+    ("wf_ctx_set_profiling", C.c_int, [vp, C.c_int]),
+    ("wf_ctx_stage_times", C.c_int, [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_size_t)]),
     ("wf_mat_from_host_columns", C.c_int, [vp, C.POINTER(u64p), C.c_uint32, C.c_size_t, C.c_int, C.c_int, C.POINTER(vp)]),
     ("wf_mat_from_device_columns", C.c_int, [vp, vp, C.c_uint32, C.c_size_t, C.POINTER(vp)]),
     ("wf_mat_select_columns", C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
@@ -63,6 +65,8 @@ _SIGS = [
     ("wf_fri_build_proof", C.c_int, [vp, vp, u64p, C.c_size_t, u8p, C.POINTER(C.c_size_t)]),
     ("wf_fri_free", C.c_int, [vp, vp]),
     ("wf_prove_fib", C.c_int, [vp, C.POINTER(u64p), C.c_int, C.c_uint32, C.c_uint32, u64p, C.POINTER(C.c_uint32), u8p, C.POINTER(C.c_size_t)]),
+    ("wf_prove_fib_dev", C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u64p, C.POINTER(C.c_uint32), u8p, C.POINTER(C.c_size_t)]),
+    ("wf_grind", C.c_int, [vp, C.c_int, u8p, C.c_uint32, C.POINTER(C.c_uint64)]),
     ("wf_ntt_dev", C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_int]),
     ("wf_hash_rows_dev", C.c_int, [vp, C.c_int, vp, C.c_size_t, C.c_uint32, vp]),
     ("wf_merkle_dev", C.c_int, [vp, C.c_int, vp, C.c_size_t, vp]),
@@ -193,6 +197,33 @@ class Context:
         self.check(self.L.wf_prove_fib(self.h, ptrs, int(mont), c // 2, int(n).bit_length() - 1, rp,
                                        o_.ctypes.data_as(C.POINTER(C.c_uint32)), buf.ctypes.data_as(u8p), C.byref(ln)))
         return buf[: ln.value].tobytes()
+
+    def prove_fib_dev(self, d_trace, k, log_n, results, opts, out_buf=None):
+        """trace resident on the device: column-major [2k][n] at raw pointer d_trace."""
+        r_, rp = _u64(results)
+        o_ = np.ascontiguousarray(opts, dtype=np.uint32)
+        buf = out_buf if out_buf is not None else np.zeros(1 << 23, dtype=np.uint8)
+        ln = C.c_size_t(buf.size)
+        self.check(self.L.wf_prove_fib_dev(self.h, vp(d_trace), k, log_n, rp, o_.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                           buf.ctypes.data_as(u8p), C.byref(ln)))
+        return buf[: ln.value].tobytes()
+
+    def set_profiling(self, on):
+        self.check(self.L.wf_ctx_set_profiling(self.h, int(on)))
+
+    def stage_times(self):
+        names = C.create_string_buffer(4096)
+        ms = (C.c_float * 64)()
+        cnt = C.c_size_t(64)
+        self.check(self.L.wf_ctx_stage_times(self.h, names, 4096, ms, C.byref(cnt)))
+        nm = [x for x in names.value.decode().split(",") if x]
+        return [(nm[i], float(ms[i])) for i in range(cnt.value)]
+
+    def grind(self, hash_id, seed: bytes, grinding):
+        t_, tp = _u8(np.frombuffer(seed, dtype=np.uint8))
+        nonce = C.c_uint64(0)
+        self.check(self.L.wf_grind(self.h, hash_id, tp, grinding, C.byref(nonce)))
+        return nonce.value
 
     # ---- plain device kernels (raw device pointers as integers) ----
     def ntt_dev(self, dptr, log_n, cols, inverse=False):

@@ -13,6 +13,13 @@
 
 #include "internal.hpp"
 
+void wf_mark(wf_ctx* ctx, const char* name) {
+    if (!ctx->profiling) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, ctx->st);
+    ctx->marks.push_back({name, e});
+}
 int wf_fail(wf_ctx* ctx, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -274,6 +281,7 @@ int wf_ctx_create(wf_ctx** out, int device, void* stream) {
     ctx->launches = 0;
     ctx->pinned = nullptr;
     ctx->pinned_bytes = 0;
+    ctx->profiling = false;
     *out = ctx;
     return WF_OK;
 }
@@ -287,6 +295,29 @@ void wf_ctx_destroy(wf_ctx* ctx) {
     for (auto& kv : ctx->lde_tabs) { cudaFree(kv.second.pre); if (kv.second.pow7) cudaFree(kv.second.pow7); }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     delete ctx;
+}
+int wf_ctx_set_profiling(wf_ctx* ctx, int on) {
+    if (!ctx) return WF_ERR_INVALID;
+    ctx->profiling = on != 0;
+    for (auto& m : ctx->marks) cudaEventDestroy(m.second);
+    ctx->marks.clear();
+    return WF_OK;
+}
+int wf_ctx_stage_times(wf_ctx* ctx, char* names, size_t names_cap, float* ms, size_t* count) {
+    if (!ctx || !names || !ms || !count) return WF_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->st));
+    size_t n = ctx->marks.size() > 0 ? ctx->marks.size() - 1 : 0, used = 0;
+    if (n > *count) n = *count;
+    names[0] = 0;
+    for (size_t i = 0; i < n; i++) {
+        CK(cudaEventElapsedTime(&ms[i], ctx->marks[i].second, ctx->marks[i + 1].second));
+        const std::string& nm = ctx->marks[i + 1].first;
+        if (used + nm.size() + 2 < names_cap) { memcpy(names + used, nm.c_str(), nm.size()); used += nm.size(); names[used++] = ','; names[used] = 0; }
+    }
+    *count = n;
+    for (auto& m : ctx->marks) cudaEventDestroy(m.second);
+    ctx->marks.clear();
+    return WF_OK;
 }
 const char* wf_last_error(const wf_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (is a CUDA device present?)"; }
 int wf_ctx_sync(wf_ctx* ctx) { CK(cudaStreamSynchronize(ctx->st)); return WF_OK; }

@@ -32,7 +32,11 @@ struct wf_ctx {
     std::map<std::pair<u32, u32>, LdeTables> lde_tabs;  // (log_n, log_blowup)
     void* pinned;                            // staging buffer (pinned host)
     size_t pinned_bytes;
+    bool profiling;                          // record a CUDA event at every pipeline stage boundary
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
 };
+// stage marker (tracing spans of the reference: prover/src/lib.rs:312-466 info_span!/instrument)
+void wf_mark(wf_ctx* ctx, const char* name);
 
 struct wf_mat {
     SegMatrix m;

@@ -22,6 +22,8 @@
 #include <algorithm>
 
 #include "internal.hpp"
+#include "blake3.cuh"
+#include "rp64.cuh"
 
 // =================================================================================================
 // kernels
@@ -219,9 +221,69 @@ __global__ void __launch_bounds__(256) deep_eval_kernel(DeepParams p, GlExt<D> z
     }
 }
 
+// Proof-of-work grinding (K13; prover/src/channel.rs:169-184, crypto/src/random/default.rs:141-146):
+// thread idx tests nonce = start + idx: trailing_zeros(LE u64 of merge_with_int(seed, nonce)[..8]) >=
+// grinding. atomicMin keeps the SMALLEST qualifying nonce of the batch, and batches are scanned in
+// increasing order, so the result is the serial-semantics nonce (the reference's `concurrent`
+// find_any is nondeterministic; byte-identity is defined against the serial branch).
+__global__ void __launch_bounds__(256) grind_kernel(int hash_id, const u64* seed /*4 words*/, u64 start, u64 count, u32 grinding,
+                                                    unsigned long long* result) {
+    u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    u64 nonce = start + idx;
+    u64 head;
+    if (hash_id == WF_HASH_BLAKE3_256) {
+        u32 m[16], cv[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { m[2 * i] = (u32)seed[i]; m[2 * i + 1] = (u32)(seed[i] >> 32); }
+        m[8] = (u32)nonce; m[9] = (u32)(nonce >> 32);
+#pragma unroll
+        for (int i = 10; i < 16; i++) m[i] = 0;
+        b3_iv(cv);
+        b3_compress(cv, m, 0, 40, B3_CHUNK_START | B3_CHUNK_END | B3_ROOT);  // blake/mod.rs:41-46
+        head = (u64)cv[0] | ((u64)cv[1] << 32);
+    } else {
+        u64 s[12];  // rp64_256/mod.rs:198-218
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) s[4 + i] = seed[i];
+        if (nonce < GL_P) { s[8] = nonce; s[0] = 5; }
+        else { s[8] = nonce - GL_P; s[9] = 1; s[0] = 6; }
+        rp64_permute(s);
+        head = s[4];
+    }
+    u64 mask = grinding >= 64 ? ~0ULL : ((1ULL << grinding) - 1);
+    if ((head & mask) == 0) atomicMin(result, (unsigned long long)nonce);
+}
+
 // =================================================================================================
 // host orchestration
 // =================================================================================================
+static int grind_on_device(wf_ctx* ctx, int hash_id, const Digest& seed, u32 grinding, u64* nonce_out) {
+    if (grinding == 0) { *nonce_out = 1; return WF_OK; }
+    void *d_seed, *d_res;
+    CKI(wf_dev_alloc(ctx, 32, &d_seed));
+    CKI(wf_dev_alloc(ctx, 8, &d_res));
+    CK(cudaMemcpyAsync(d_seed, seed.b, 32, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(d_res, 0xff, 8, ctx->st));
+    const u64 batch = hash_id == WF_HASH_BLAKE3_256 ? (1ULL << 20) : (1ULL << 16);
+    u64 start = 1, found = ~0ULL;
+    while (found == ~0ULL) {
+        grind_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, ctx->st>>>(hash_id, (const u64*)d_seed, start, batch, grinding,
+                                                                         (unsigned long long*)d_res);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&found, d_res, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        start += batch;
+    }
+    wf_dev_free(ctx, d_seed);
+    wf_dev_free(ctx, d_res);
+    *nonce_out = found;
+    return WF_OK;
+}
+
 namespace {
 
 struct Options {
@@ -315,8 +377,8 @@ int write_queries(wf_ctx* ctx, const wf_mat* m, const wf_tree* t, const std::vec
 }
 
 template <int D>
-int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, u32 k, u32 log_n, const u64* results, const Options& o,
-              std::vector<u8>& proof_out) {
+int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont, u32 k, u32 log_n,
+              const u64* results, const Options& o, std::vector<u8>& proof_out) {
     const int h = o.hash_id;
     const size_t n = (size_t)1 << log_n;
     u32 log_b = 0;
@@ -334,13 +396,19 @@ int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, u32 k, u
     // ---- 1. trace commitment (lib.rs:497-522) ----
     wf_mat *trace = nullptr, *polys = nullptr, *lde = nullptr;
     wf_tree* ttree = nullptr;
-    CKI(wf_mat_from_host_columns(ctx, trace_cols, c, n, 1, mont, &trace));
+    wf_mark(ctx, "start");
+    if (d_trace) CKI(wf_mat_from_device_columns(ctx, d_trace, c, n, &trace));
+    else CKI(wf_mat_from_host_columns(ctx, trace_cols, c, n, 1, mont, &trace));
+    wf_mark(ctx, "trace_upload_layout");
     CKI(wf_mat_interpolate(ctx, trace, &polys));
     wf_mat_free(ctx, trace);
+    wf_mark(ctx, "trace_interpolate");
     CKI(wf_mat_lde(ctx, polys, log_b, &lde));
+    wf_mark(ctx, "trace_lde");
     CKI(wf_commit_rows(ctx, h, lde, &ttree));
     u8 root[32];
     CKI(wf_tree_root(ctx, ttree, root));
+    wf_mark(ctx, "trace_commit");
     ch.commit(root);
 
     // ---- 2. constraint evaluation (lib.rs:373-378) ----
@@ -375,6 +443,7 @@ int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, u32 k, u
         ctx->launches++;
         CK(cudaGetLastError());
     }
+    wf_mark(ctx, "constraint_eval");
     // ---- 3. composition polynomial + commitment (lib.rs:527-552) ----
     wf_mat *ccoefs, *cpolys, *clde;
     wf_tree* ctree;
@@ -386,9 +455,12 @@ int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, u32 k, u
     ctx->launches++;
     CK(cudaGetLastError());
     wf_mat_free(ctx, ccoefs);
+    wf_mark(ctx, "composition_interpolate");
     CKI(wf_mat_lde(ctx, cpolys, log_b, &clde));
+    wf_mark(ctx, "composition_lde");
     CKI(wf_commit_rows(ctx, h, clde, &ctree));
     CKI(wf_tree_root(ctx, ctree, root));
+    wf_mark(ctx, "composition_commit");
     ch.commit(root);
 
     // ---- 4. out-of-domain frames (lib.rs:392-401) ----
@@ -423,6 +495,7 @@ int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, u32 k, u
         Digest dg = hh_hash_elements(h, (const u64*)m.v.data(), m.v.size() / 8);
         ch.coin.reseed(dg);  // channel.rs:109-112 (not added to the commitments)
     }
+    wf_mark(ctx, "ood_frames");
     // ---- 5. DEEP composition (lib.rs:403-440), evaluation form ----
     std::vector<GlExt<D>> dc = ch.draw_coeffs(o.batch_d, c + kc);
     GlExt<D> Sz = ext_zero<D>(), Szg = ext_zero<D>();
@@ -444,17 +517,21 @@ int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, u32 k, u
         ctx->launches++;
         CK(cudaGetLastError());
     }
+    wf_mark(ctx, "deep_composition");
     // ---- 6. FRI (lib.rs:442-448) ----
     wf_fri* fri;
     CKI(wf_fri_build_layers(ctx, h, deep, D, o.folding, o.rem_max_deg, o.blowup, fri_commit_cb<D>, fri_draw_cb<D>, &ch, &fri));
     wf_mat_free(ctx, deep);
+    wf_mark(ctx, "fri_layers");
     // ---- 7. grinding + query positions (channel.rs:151-184; serial semantics: smallest nonce) ----
-    u64 nonce = 1;
-    while (ch.coin.check_leading_zeros(nonce) < o.grinding) nonce++;
+    u64 nonce;
+    CKI(grind_on_device(ctx, h, ch.coin.seed, o.grinding, &nonce));
+    if (ch.coin.check_leading_zeros(nonce) < o.grinding) return wf_fail(ctx, WF_ERR_STATE, "grinding self-check failed");
     std::vector<u64> pos;
     if (!ch.coin.draw_integers(o.num_queries, N, nonce, pos)) return wf_fail(ctx, WF_ERR_STATE, "failed to draw query positions");
     std::sort(pos.begin(), pos.end());
     pos.erase(std::unique(pos.begin(), pos.end()), pos.end());
+    wf_mark(ctx, "grinding");
     // ---- 8. proof object (lib.rs:464-489; air/src/proof/mod.rs:189-200) ----
     ByteVec w;
     // Context (context.rs:142-151): TraceInfo, modulus, ProofOptions, num_constraints
@@ -477,6 +554,7 @@ int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, u32 k, u
         w.bytes(fp.data(), fl);
     }
     w.u64_(nonce);
+    wf_mark(ctx, "queries_and_proof");
     proof_out.swap(w.v);
     wf_fri_free(ctx, fri);
     for (wf_mat* m : {polys, lde, cpolys, clde}) wf_mat_free(ctx, m);
@@ -488,9 +566,16 @@ int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, u32 k, u
 
 }  // namespace
 
-extern "C" int wf_prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, uint32_t k, uint32_t log_n,
-                            const uint64_t* results, const uint32_t* opts, uint8_t* proof, size_t* proof_len) {
-    if (!ctx || !trace_cols || !results || !opts || !proof || !proof_len || k == 0 || 2 * k > 255 || log_n < 3)
+extern "C" int wf_grind(wf_ctx* ctx, int hash_id, const uint8_t seed[32], uint32_t grinding, uint64_t* nonce) {
+    if (!ctx || !seed || !nonce || grinding > 40) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    Digest d;
+    memcpy(d.b, seed, 32);
+    return grind_on_device(ctx, hash_id, d, grinding, nonce);
+}
+
+static int prove_fib_entry(wf_ctx* ctx, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont, uint32_t k,
+                           uint32_t log_n, const uint64_t* results, const uint32_t* opts, uint8_t* proof, size_t* proof_len) {
+    if (!ctx || (!trace_cols && !d_trace) || !results || !opts || !proof || !proof_len || k == 0 || 2 * k > 255 || log_n < 3)
         return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     Options o;
     o.num_queries = opts[0]; o.blowup = opts[1]; o.grinding = opts[2]; o.ext = opts[3]; o.folding = opts[4];
@@ -501,9 +586,9 @@ extern "C" int wf_prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int 
     std::vector<u8> out;
     int r;
     switch (o.ext) {
-        case 1: r = prove_fib<1>(ctx, trace_cols, mont, k, log_n, results, o, out); break;
-        case 2: r = prove_fib<2>(ctx, trace_cols, mont, k, log_n, results, o, out); break;
-        case 3: r = prove_fib<3>(ctx, trace_cols, mont, k, log_n, results, o, out); break;
+        case 1: r = prove_fib<1>(ctx, trace_cols, d_trace, mont, k, log_n, results, o, out); break;
+        case 2: r = prove_fib<2>(ctx, trace_cols, d_trace, mont, k, log_n, results, o, out); break;
+        case 3: r = prove_fib<3>(ctx, trace_cols, d_trace, mont, k, log_n, results, o, out); break;
         default: return wf_fail(ctx, WF_ERR_UNSUPPORTED, "field extension %u", o.ext);
     }
     if (r != WF_OK) return r;
@@ -511,4 +596,13 @@ extern "C" int wf_prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int 
     memcpy(proof, out.data(), out.size());
     *proof_len = out.size();
     return WF_OK;
+}
+
+extern "C" int wf_prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, uint32_t k, uint32_t log_n,
+                            const uint64_t* results, const uint32_t* opts, uint8_t* proof, size_t* proof_len) {
+    return prove_fib_entry(ctx, trace_cols, nullptr, mont, k, log_n, results, opts, proof, proof_len);
+}
+extern "C" int wf_prove_fib_dev(wf_ctx* ctx, const uint64_t* d_trace, uint32_t k, uint32_t log_n, const uint64_t* results,
+                                const uint32_t* opts, uint8_t* proof, size_t* proof_len) {
+    return prove_fib_entry(ctx, nullptr, d_trace, 0, k, log_n, results, opts, proof, proof_len);
 }
