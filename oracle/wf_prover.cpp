@@ -11,6 +11,8 @@
 // (SURVEY.md §8d). Pair j starts at (j+1, j+1); public inputs = the k results (for k = 1 exactly
 // fib_small's single BaseElement).
 #include <array>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "wf_oracle.cpp"
 
@@ -174,7 +176,14 @@ static void queries_for(const Field& F, int h, const u64* rows_mat, size_t row_w
     w.usize((u64)pl); w.bytes(pr.data(), (size_t)pl);
 }
 
+struct StageTimer {
+    bool on; double t0;
+    StageTimer() : on(getenv("WFO_TIMING") != nullptr), t0(omp_get_wtime()) {}
+    void mark(const char* name) { if (!on) return; double t = omp_get_wtime(); fprintf(stderr, "[oracle] %-26s %9.3f ms\n", name, (t - t0) * 1e3); t0 = t; }
+};
+
 static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/) {
+    StageTimer tm;
     const Opts& o = air.o;
     const int h = o.hash_id;
     Field F{(int)o.ext};
@@ -197,6 +206,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
     commitments.bytes(t_nodes.data() + 32, 32);
     coin.reseed(t_nodes.data() + 32);
 
+    tm.mark("trace_commit");
     // 2. constraint evaluation (evaluator/default.rs:60-118, evaluation_table.rs:163-407)
     std::vector<EE> ccoef = coin.draw_coeffs(F, (int)o.batch_c, air.num_transition() + air.num_assertions());
     std::vector<EE> tcoef(ccoef.begin(), ccoef.begin() + air.num_transition());
@@ -231,6 +241,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
             comp[i] = acc;
         }
     }
+    tm.mark("constraint_eval");
     // 3. composition polynomial + commitment (composition_poly.rs:58-78, commitment/default.rs:109-150)
     std::vector<u64> cp(ce * d);
     for (size_t i = 0; i < ce; i++) for (int k = 0; k < d; k++) cp[i * d + k] = comp[i].v[k];
@@ -246,6 +257,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
     commitments.bytes(c_nodes.data() + 32, 32);
     coin.reseed(c_nodes.data() + 32);
 
+    tm.mark("composition_commit");
     // 4. OOD frame (lib.rs:392-401, poly_table.rs:68-76, composition_poly.rs:101-108, channel.rs:102-113)
     EE z = coin.draw(F);
     EE zg = F.mul_base(z, g_tr);
@@ -267,6 +279,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
         hash_elements(h, m.data(), m.size(), dg);
         coin.reseed(dg);
     }
+    tm.mark("ood_frames");
     // 5. DEEP composition polynomial, coefficient form (composer/mod.rs:67-210)
     std::vector<EE> dcoef = coin.draw_coeffs(F, (int)o.batch_d, c + kc);
     std::vector<EE> comp_z(n, F.zero()), comp_gz(n, F.zero());
@@ -297,6 +310,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
     std::vector<u64> deep_ev(N * d);
     { auto tw = get_twiddles(n); evaluate_poly_with_offset(deep.data(), n, d, tw.data(), GENERATOR, b, deep_ev.data()); }
 
+    tm.mark("deep_composition");
     // 6. FRI commit phase with the prover channel (fri/src/prover/mod.rs:179-239, channel.rs:215-234)
     struct Layer { std::vector<u64> tv; std::vector<u8> leaves, nodes; size_t rows; };
     std::vector<Layer> layers;
@@ -332,6 +346,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
         commitments.bytes(dg, 32);
         coin.reseed(dg);
     }
+    tm.mark("fri_layers");
     // 7. grinding + query positions (channel.rs:151-184; serial branch: smallest nonce)
     u64 nonce = 1;
     while (wfo_coin_leading_zeros(&coin.c, nonce) < o.grinding) nonce++;
@@ -340,6 +355,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
     std::sort(pos.begin(), pos.end());
     pos.erase(std::unique(pos.begin(), pos.end()), pos.end());
 
+    tm.mark("grinding");
     // 8. proof object (lib.rs:464-489; air/src/proof/mod.rs:189-200)
     Writer w;
     write_context(w, air);
@@ -372,6 +388,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
     w.u16_((uint16_t)(remainder.size() * 8)); w.bytes(remainder.data(), remainder.size() * 8);
     w.u8_(0);
     w.u64_(nonce);
+    tm.mark("queries_and_proof");
     return w.b;
 }
 
