@@ -533,11 +533,15 @@ int wf_tree_to_host(wf_ctx* ctx, const wf_tree* t, uint8_t* leaves, uint8_t* nod
 // MerkleTree::prove_batch (crypto/src/merkle/mod.rs:217-272) on a device tree: the walk decides
 // which digests are needed (host, indices only), one gather kernel fetches them.
 }  // extern "C"
-int wf_tree_open_many_bytes(wf_ctx* ctx, const wf_tree* t, const uint64_t* positions, size_t k, uint8_t* leaves_out,
-                          ByteVec& proof) {
-    size_t n = t->nleaves;
-    u32 depth = 0;
-    while (((size_t)1 << depth) < n) depth++;
+
+// ---- batched openings ------------------------------------------------------------------------------
+// MerkleTree::prove_batch (crypto/src/merkle/mod.rs:217-272) split into a host-only PLAN (which
+// digests are needed: pure index arithmetic) and a FINISH step (serialisation, proofs.rs:390-401), so
+// that all the gathers of a proof (trace rows, constraint rows, every FRI layer) share ONE index
+// upload, ONE result download and ONE stream synchronisation (GatherBatch).
+int wf_open_plan(wf_ctx* ctx, size_t n, const uint64_t* positions, size_t k, OpenPlan& pl) {
+    pl.depth = 0;
+    while (((size_t)1 << pl.depth) < n) pl.depth++;
     if (k == 0) return wf_fail(ctx, WF_ERR_INVALID, "no positions");
     std::map<size_t, size_t> index_map;
     for (size_t i = 0; i < k; i++) {
@@ -548,52 +552,106 @@ int wf_tree_open_many_bytes(wf_ctx* ctx, const wf_tree* t, const uint64_t* posit
     std::set<size_t> norm;
     for (size_t i = 0; i < k; i++) norm.insert(positions[i] & ~(size_t)1);
     // gather list: entries < n address nodes[], entries >= n address leaves[entry - n]
-    std::vector<u64> want;
-    std::vector<std::vector<size_t>> vec_slots;  // per proof vector: indices into `want`
-    std::vector<size_t> leaf_slot(k);
+    pl.want.clear();
+    pl.vec_slots.clear();
+    pl.leaf_slot.assign(k, 0);
     std::vector<size_t> next;
     for (size_t index : norm) {
         std::vector<size_t> slots;
         for (size_t i = index; i < index + 2; i++) {
             auto it = index_map.find(i);
-            want.push_back(n + i);
-            if (it != index_map.end()) leaf_slot[it->second] = want.size() - 1;
-            else slots.push_back(want.size() - 1);
+            pl.want.push_back(n + i);
+            if (it != index_map.end()) pl.leaf_slot[it->second] = pl.want.size() - 1;
+            else slots.push_back(pl.want.size() - 1);
         }
-        vec_slots.push_back(slots);
+        pl.vec_slots.push_back(slots);
         next.push_back((index + n) >> 1);
     }
-    for (u32 lvl = 1; lvl < depth; lvl++) {
+    for (u32 lvl = 1; lvl < pl.depth; lvl++) {
         std::vector<size_t> idx = next;
         next.clear();
         size_t i = 0;
         while (i < idx.size()) {
             size_t sib = idx[i] ^ 1;
             if (i + 1 < idx.size() && idx[i + 1] == sib) i += 1;
-            else { want.push_back(sib); vec_slots[i].push_back(want.size() - 1); }
+            else { pl.want.push_back(sib); pl.vec_slots[i].push_back(pl.want.size() - 1); }
             next.push_back(sib >> 1);
             i += 1;
         }
     }
-    void *dw, *dg;
-    CKI(wf_dev_alloc(ctx, want.size() * 8, &dw));
-    CKI(wf_dev_alloc(ctx, want.size() * 32, &dg));
-    CK(cudaMemcpyAsync(dw, want.data(), want.size() * 8, cudaMemcpyHostToDevice, ctx->st));
-    CK(layout_gather_digests(t->nodes, t->leaves, n, (const u64*)dw, want.size(), (u64*)dg, ctx->st));
-    ctx->launches++;
-    std::vector<u8> got(want.size() * 32);
-    CK(cudaMemcpyAsync(got.data(), dg, got.size(), cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
-    wf_dev_free(ctx, dw);
-    wf_dev_free(ctx, dg);
-    for (size_t i = 0; i < k; i++) memcpy(leaves_out + i * 32, got.data() + leaf_slot[i] * 32, 32);
-    // BatchMerkleProof::write_into (proofs.rs:390-401)
-    proof.u8_((u8)depth);
-    proof.usize(vec_slots.size());
-    for (auto& v : vec_slots) {
+    return WF_OK;
+}
+void wf_open_finish(const OpenPlan& pl, const uint8_t* got, uint8_t* leaves_out, ByteVec& proof) {
+    if (leaves_out)
+        for (size_t i = 0; i < pl.leaf_slot.size(); i++) memcpy(leaves_out + i * 32, got + pl.leaf_slot[i] * 32, 32);
+    proof.u8_((u8)pl.depth);  // BatchMerkleProof::write_into (proofs.rs:390-401)
+    proof.usize(pl.vec_slots.size());
+    for (auto& v : pl.vec_slots) {
         proof.usize(v.size());
-        for (size_t s : v) proof.bytes(got.data() + s * 32, 32);
+        for (size_t s : v) proof.bytes(got + s * 32, 32);
     }
+}
+
+static int pinned_reserve(wf_ctx* ctx, size_t bytes) {
+    if (ctx->pinned_bytes >= bytes) return WF_OK;
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 0;
+    bytes = std::max(bytes * 2, (size_t)1 << 20);
+    CK(cudaMallocHost(&ctx->pinned, bytes));
+    ctx->pinned_bytes = bytes;
+    return WF_OK;
+}
+
+size_t GatherBatch::add_rows(const SegMatrix& m, const std::vector<u64>& pos) {
+    rows.push_back({m, pos, 0, 0});
+    return rows.size() - 1;
+}
+int GatherBatch::add_opening(wf_ctx* ctx, const wf_tree* t, const std::vector<u64>& pos, size_t* id) {
+    digs.emplace_back();
+    digs.back().t = t;
+    CKI(wf_open_plan(ctx, t->nleaves, pos.data(), pos.size(), digs.back().plan));
+    *id = digs.size() - 1;
+    return WF_OK;
+}
+int GatherBatch::run(wf_ctx* ctx) {
+    size_t idx_words = 0, out_words = 0;
+    for (auto& j : rows) { j.idx_off = idx_words; j.out_off = out_words; idx_words += j.pos.size(); out_words += j.pos.size() * j.m.cols; }
+    for (auto& j : digs) { j.idx_off = idx_words; j.out_off = out_words; idx_words += j.plan.want.size(); out_words += j.plan.want.size() * 4; }
+    if (idx_words == 0) return WF_OK;
+    CKI(pinned_reserve(ctx, (idx_words + out_words) * 8));
+    u64* h_idx = (u64*)ctx->pinned;
+    u64* h_out = h_idx + idx_words;
+    for (auto& j : rows) memcpy(h_idx + j.idx_off, j.pos.data(), j.pos.size() * 8);
+    for (auto& j : digs) memcpy(h_idx + j.idx_off, j.plan.want.data(), j.plan.want.size() * 8);
+    void *d_idx, *d_out;
+    CKI(wf_dev_alloc(ctx, idx_words * 8, &d_idx));
+    CKI(wf_dev_alloc(ctx, out_words * 8, &d_out));
+    CK(cudaMemcpyAsync(d_idx, h_idx, idx_words * 8, cudaMemcpyHostToDevice, ctx->st));
+    for (auto& j : rows) {
+        CK(layout_gather_rows(j.m, (const u64*)d_idx + j.idx_off, j.pos.size(), (u64*)d_out + j.out_off, 0, ctx->st));
+        ctx->launches++;
+    }
+    for (auto& j : digs) {
+        CK(layout_gather_digests(j.t->nodes, j.t->leaves, j.t->nleaves, (const u64*)d_idx + j.idx_off, j.plan.want.size(),
+                                 (u64*)d_out + j.out_off, ctx->st));
+        ctx->launches++;
+    }
+    CK(cudaMemcpyAsync(h_out, d_out, out_words * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    wf_dev_free(ctx, d_idx);
+    wf_dev_free(ctx, d_out);
+    result = h_out;
+    return WF_OK;
+}
+
+int wf_tree_open_many_bytes(wf_ctx* ctx, const wf_tree* t, const uint64_t* positions, size_t k, uint8_t* leaves_out,
+                            ByteVec& proof) {
+    GatherBatch gb;
+    size_t id;
+    CKI(gb.add_opening(ctx, t, std::vector<u64>(positions, positions + k), &id));
+    CKI(gb.run(ctx));
+    wf_open_finish(gb.digs[id].plan, gb.digest_result(id), leaves_out, proof);
     return WF_OK;
 }
 extern "C" {
@@ -609,18 +667,6 @@ int wf_tree_open_many(wf_ctx* ctx, const wf_tree* t, const uint64_t* positions, 
 }
 
 // ---- FRI ----------------------------------------------------------------------------------------
-struct FriLayer {
-    u64* evals;   // len x ld words (natural order)
-    size_t len;
-    wf_tree* tree;
-};
-struct wf_fri {
-    int hash_id, d, ld;
-    u32 folding, blowup;
-    std::vector<FriLayer> layers;
-    std::vector<u64> remainder;  // reversed coefficients, d words each
-};
-
 // host iNTT with offset for the remainder (<= a few hundred elements; fri/src/prover/mod.rs:230-239,
 // fft/serial.rs:84-101). Plain O(n log n) radix-2 on the host copy.
 static void host_interpolate_with_offset(std::vector<u64>& v, size_t n, int d, u64 offset) {
@@ -758,42 +804,57 @@ size_t wf_fri_remainder(const wf_fri* f, uint64_t* coeffs, size_t cap_words) {
     return f->remainder.size() / f->d;
 }
 
-int wf_fri_build_proof(wf_ctx* ctx, wf_fri* f, const uint64_t* positions, size_t k, uint8_t* out, size_t* len) {
-    // fri/src/prover/mod.rs:254-319 + fri/src/proof.rs:149-163,275-285
-    if (!ctx || !f || !positions || !out || !len) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
-    ByteVec bv;
-    bv.u8_((u8)f->layers.size());
-    std::vector<u64> pos(positions, positions + k);
+}  // extern "C"
+int wf_fri_queue_proof(wf_ctx* ctx, wf_fri* f, const std::vector<u64>& positions, GatherBatch& gb, FriProofPlan& plan) {
+    // fri/src/prover/mod.rs:254-319: per layer fold the positions, queue the row values and the opening
+    std::vector<u64> pos = positions;
     for (auto& L : f->layers) {
-        // fold_positions (fri/src/folding/mod.rs:159-176)
         size_t m = L.len / f->folding;
-        std::vector<u64> fp;
+        std::vector<u64> fp;  // fold_positions (fri/src/folding/mod.rs:159-176)
         for (u64 p : pos) {
             u64 q = p % m;
             if (std::find(fp.begin(), fp.end(), q) == fp.end()) fp.push_back(q);
         }
         pos = fp;
         // queried values: row `position` of the transposed layer = v[pos + j*m], j < folding
-        size_t nq = pos.size(), ne = (size_t)f->folding * f->d;
-        std::vector<u64> gpos(nq * f->folding);
-        for (size_t i = 0; i < nq; i++)
+        std::vector<u64> gpos(pos.size() * f->folding);
+        for (size_t i = 0; i < pos.size(); i++)
             for (u32 j = 0; j < f->folding; j++) gpos[i * f->folding + j] = pos[i] + (u64)j * m;
         SegMatrix lm;
         lm.base = L.evals; lm.rows = L.len; lm.cols = (u32)f->d; lm.W = f->ld; lm.seg_stride = L.len * f->ld;
-        wf_mat tmpm{lm};
-        std::vector<u64> vals(nq * ne);
-        CKI(wf_mat_read_rows(ctx, &tmpm, gpos.data(), gpos.size(), vals.data(), 0));
-        std::vector<u8> leaves(nq * 32);
+        plan.row_ids.push_back(gb.add_rows(lm, gpos));
+        size_t id;
+        CKI(gb.add_opening(ctx, L.tree, pos, &id));
+        plan.dig_ids.push_back(id);
+        plan.nq.push_back(pos.size());
+    }
+    return WF_OK;
+}
+void wf_fri_finish_proof(const wf_fri* f, const GatherBatch& gb, const FriProofPlan& plan, ByteVec& bv) {
+    // FriProof / FriProofLayer wire format (fri/src/proof.rs:149-163, 275-285)
+    bv.u8_((u8)f->layers.size());
+    for (size_t l = 0; l < f->layers.size(); l++) {
+        size_t nvals = plan.nq[l] * f->folding * f->d;
         ByteVec paths;
-        CKI(wf_tree_open_many_bytes(ctx, L.tree, pos.data(), nq, leaves.data(), paths));
-        bv.u32_((u32)(vals.size() * 8));
-        bv.bytes(vals.data(), vals.size() * 8);
+        wf_open_finish(gb.digs[plan.dig_ids[l]].plan, gb.digest_result(plan.dig_ids[l]), nullptr, paths);
+        bv.u32_((u32)(nvals * 8));
+        bv.bytes(gb.row_result(plan.row_ids[l]), nvals * 8);
         bv.u32_((u32)paths.v.size());
         bv.bytes(paths.v.data(), paths.v.size());
     }
     bv.u16_((uint16_t)(f->remainder.size() * 8));
     bv.bytes(f->remainder.data(), f->remainder.size() * 8);
     bv.u8_(0);  // log2(num_partitions = 1)
+}
+extern "C" {
+int wf_fri_build_proof(wf_ctx* ctx, wf_fri* f, const uint64_t* positions, size_t k, uint8_t* out, size_t* len) {
+    if (!ctx || !f || !positions || !out || !len) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    GatherBatch gb;
+    FriProofPlan plan;
+    CKI(wf_fri_queue_proof(ctx, f, std::vector<u64>(positions, positions + k), gb, plan));
+    CKI(gb.run(ctx));
+    ByteVec bv;
+    wf_fri_finish_proof(f, gb, plan, bv);
     if (bv.v.size() > *len) return wf_fail(ctx, WF_ERR_INVALID, "proof buffer too small (%zu needed)", bv.v.size());
     memcpy(out, bv.v.data(), bv.v.size());
     *len = bv.v.size();

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -53,6 +54,43 @@ int wf_dev_alloc(wf_ctx* ctx, size_t bytes, void** out);
 void wf_dev_free(wf_ctx* ctx, void* p);
 int wf_mat_alloc(wf_ctx* ctx, size_t rows, u32 cols, wf_mat** out);
 int wf_get_twiddles(wf_ctx* ctx, u32 log_n, const u64** out);
+struct OpenPlan {
+    u32 depth;
+    std::vector<u64> want;                       // < n: nodes[want]; >= n: leaves[want - n]
+    std::vector<std::vector<size_t>> vec_slots;  // per proof vector: slots into `want`
+    std::vector<size_t> leaf_slot;               // per queried position: slot of its leaf digest
+};
+int wf_open_plan(wf_ctx* ctx, size_t n, const uint64_t* positions, size_t k, OpenPlan& pl);
+void wf_open_finish(const OpenPlan& pl, const uint8_t* got, uint8_t* leaves_out, ByteVec& proof);
+// all row / digest gathers of one proof: one upload, one download, one synchronisation
+struct GatherBatch {
+    struct RowJob { SegMatrix m; std::vector<u64> pos; size_t idx_off, out_off; };
+    struct DigJob { const wf_tree* t; OpenPlan plan; size_t idx_off, out_off; };
+    std::vector<RowJob> rows;
+    std::vector<DigJob> digs;
+    const u64* result = nullptr;  // pinned host buffer, valid until the next run()
+    size_t add_rows(const SegMatrix& m, const std::vector<u64>& pos);
+    int add_opening(wf_ctx* ctx, const wf_tree* t, const std::vector<u64>& pos, size_t* id);
+    int run(wf_ctx* ctx);
+    const u64* row_result(size_t id) const { return result + rows[id].out_off; }
+    const u8* digest_result(size_t id) const { return (const u8*)(result + digs[id].out_off); }
+};
+struct FriLayer {
+    u64* evals;   // len x ld words (natural order)
+    size_t len;
+    wf_tree* tree;
+};
+struct wf_fri {
+    int hash_id, d, ld;
+    u32 folding, blowup;
+    std::vector<FriLayer> layers;
+    std::vector<u64> remainder;  // reversed coefficients, d words each
+};
+
+// FriProver::build_proof split the same way: queue the gathers, then serialise
+struct FriProofPlan { std::vector<size_t> row_ids, dig_ids; std::vector<size_t> nq; };
+int wf_fri_queue_proof(wf_ctx* ctx, wf_fri* f, const std::vector<u64>& positions, GatherBatch& gb, FriProofPlan& plan);
+void wf_fri_finish_proof(const wf_fri* f, const GatherBatch& gb, const FriProofPlan& plan, ByteVec& out);
 int wf_tree_open_many_bytes(wf_ctx* ctx, const wf_tree* t, const uint64_t* positions, size_t k, uint8_t* leaves_out,
                             ByteVec& proof);
 

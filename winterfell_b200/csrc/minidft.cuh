@@ -53,6 +53,29 @@ __device__ __forceinline__ void mini_dft<4>(u64* x) {
     mini_dft<3>(x);
     mini_dft<3>(x + 8);
 }
+template <>
+__device__ __forceinline__ void mini_dft<5>(u64* x) {
+#pragma unroll
+    for (int q = 0; q < 16; q++) bf2(x[q], x[q + 16]);
+    // w_32 = 2^6: x[16 + q] *= 2^(6q)
+    x[17] = gl_mul_2exp<6>(x[17]);
+    x[18] = gl_mul_2exp<12>(x[18]);
+    x[19] = gl_mul_2exp<18>(x[19]);
+    x[20] = gl_mul_2exp<24>(x[20]);
+    x[21] = gl_mul_2exp<30>(x[21]);
+    x[22] = gl_mul_2exp<36>(x[22]);
+    x[23] = gl_mul_2exp<42>(x[23]);
+    x[24] = gl_mul_2exp<48>(x[24]);
+    x[25] = gl_mul_2exp<54>(x[25]);
+    x[26] = gl_mul_2exp<60>(x[26]);
+    x[27] = gl_mul_2exp<66>(x[27]);
+    x[28] = gl_mul_2exp<72>(x[28]);
+    x[29] = gl_mul_2exp<78>(x[29]);
+    x[30] = gl_mul_2exp<84>(x[30]);
+    x[31] = gl_mul_2exp<90>(x[31]);
+    mini_dft<4>(x);
+    mini_dft<4>(x + 16);
+}
 __device__ __forceinline__ u32 brev(u32 v, int bits) { return __brev(v) >> (32 - bits); }
 
 // w_S^e for e in [0, S) from the half table (w^(e + S/2) = -w^e)

@@ -33,6 +33,13 @@ __device__ __forceinline__ void dif_round(u64* s, const u64* stw, int logS, int 
 
 __device__ __forceinline__ void tile_dft(u64* s, const u64* stw, int logS, int tid) {
     int stage = 0;
+#ifdef NTT_RADIX32
+    while (logS - stage >= 5) {
+        dif_round<5>(s, stw, logS, stage, tid);
+        stage += 5;
+        __syncthreads();
+    }
+#endif
 #ifdef NTT_RADIX16
     while (logS - stage >= 4) {
         dif_round<4>(s, stw, logS, stage, tid);

@@ -52,42 +52,63 @@ struct FibEvalParams {
     u64 last;           // g_trace^(n-1): transition exemption point and divisor offset of group 1
 };
 
-// One CE-domain row per thread (evaluator/default.rs:165-214 evaluate_fragment_main +
-// evaluation_table.rs:317-367 acc_column, fused).
+// CE-domain rows, FIB_ROWS per thread sharing one field inversion (evaluator/default.rs:165-214
+// evaluate_fragment_main + evaluation_table.rs:317-367 acc_column, fused).
+#define FIB_ROWS 4
 template <int D>
 __global__ void __launch_bounds__(256) fib_constraints_kernel(FibEvalParams p) {
     const size_t ce = (size_t)1 << (p.log_n + p.log_ce_blowup);
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ce) return;
     const size_t N = (size_t)1 << (p.log_n + p.log_blowup);
     const u32 lde_shift = p.log_blowup - p.log_ce_blowup;
-    const size_t ls = i << lde_shift;
-    const size_t nx = (ls + ((size_t)1 << p.log_blowup)) & (N - 1);  // trace_lde/default/mod.rs:169-180
-    GlExt<D> T = ext_zero<D>(), B0 = ext_zero<D>(), B1 = ext_zero<D>();
-    for (u32 j = 0; j < p.k; j++) {
-        u64 c0 = seg_at(p.lde, ls, 2 * j), c1 = seg_at(p.lde, ls, 2 * j + 1);
-        u64 n0 = seg_at(p.lde, nx, 2 * j), n1 = seg_at(p.lde, nx, 2 * j + 1);
-        u64 t0 = gl_sub(n0, gl_add(c0, c1));  // fib_small/air.rs:58
-        u64 t1 = gl_sub(n1, gl_add(c1, n0));  // :59
-        T = ext_add(T, ext_mul_base(ld_ext<D>(p.tcoef + (size_t)(2 * j) * D), t0));
-        T = ext_add(T, ext_mul_base(ld_ext<D>(p.tcoef + (size_t)(2 * j + 1) * D), t1));
-        u64 v = j + 1;
-        B0 = ext_add(B0, ext_mul_base(ld_ext<D>(p.bcoef0 + (size_t)(2 * j) * D), gl_sub(c0, v)));
-        B0 = ext_add(B0, ext_mul_base(ld_ext<D>(p.bcoef0 + (size_t)(2 * j + 1) * D), gl_sub(c1, v)));
-        B1 = ext_add(B1, ext_mul_base(ld_ext<D>(p.bcoef1 + (size_t)j * D), gl_sub(c1, p.results[j])));
-    }
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const u32 half = (u32)(ce >> 1);
-    u64 w = p.tw_ce[i & (half - 1)];
-    if (i & half) w = gl_neg(w);
-    u64 x = gl_mul(w, GL_GENERATOR);  // domain.rs:123 get_ce_x_at
-    u64 d0 = gl_sub(x, 1), d1 = gl_sub(x, p.last);
-    u64 inv01 = gl_inv(gl_mul(d0, d1));
-    u64 z0 = gl_mul(inv01, d1), z1 = gl_mul(inv01, d0);                      // 1/(x - 1), 1/(x - g^(n-1))
-    u64 zt = gl_mul(p.zt[i & (((size_t)1 << p.log_ce_blowup) - 1)], d1);     // e(x) / (x^n - 1)
-    GlExt<D> acc = ext_add(ext_add(ext_mul_base(T, zt), ext_mul_base(B0, z0)), ext_mul_base(B1, z1));
-    u64* o = p.out.base + i * p.out.W;
+    GlExt<D> T[FIB_ROWS], B0[FIB_ROWS], B1[FIB_ROWS];
+    u64 d0[FIB_ROWS], d1[FIB_ROWS];
 #pragma unroll
-    for (int q = 0; q < D; q++) o[q] = acc.v[q];
+    for (int r = 0; r < FIB_ROWS; r++) {
+        const size_t i = tid + r * stride;
+        T[r] = ext_zero<D>(); B0[r] = ext_zero<D>(); B1[r] = ext_zero<D>();
+        d0[r] = 1; d1[r] = 1;
+        if (i >= ce) continue;
+        const size_t ls = i << lde_shift;
+        const size_t nx = (ls + ((size_t)1 << p.log_blowup)) & (N - 1);  // trace_lde/default/mod.rs:169-180
+        for (u32 j = 0; j < p.k; j++) {
+            u64 c0 = seg_at(p.lde, ls, 2 * j), c1 = seg_at(p.lde, ls, 2 * j + 1);
+            u64 n0 = seg_at(p.lde, nx, 2 * j), n1 = seg_at(p.lde, nx, 2 * j + 1);
+            u64 t0 = gl_sub(n0, gl_add(c0, c1));  // fib_small/air.rs:58
+            u64 t1 = gl_sub(n1, gl_add(c1, n0));  // :59
+            T[r] = ext_add(T[r], ext_mul_base(ld_ext<D>(p.tcoef + (size_t)(2 * j) * D), t0));
+            T[r] = ext_add(T[r], ext_mul_base(ld_ext<D>(p.tcoef + (size_t)(2 * j + 1) * D), t1));
+            u64 v = j + 1;
+            B0[r] = ext_add(B0[r], ext_mul_base(ld_ext<D>(p.bcoef0 + (size_t)(2 * j) * D), gl_sub(c0, v)));
+            B0[r] = ext_add(B0[r], ext_mul_base(ld_ext<D>(p.bcoef0 + (size_t)(2 * j + 1) * D), gl_sub(c1, v)));
+            B1[r] = ext_add(B1[r], ext_mul_base(ld_ext<D>(p.bcoef1 + (size_t)j * D), gl_sub(c1, p.results[j])));
+        }
+        u64 w = p.tw_ce[i & (half - 1)];
+        if (i & half) w = gl_neg(w);
+        u64 x = gl_mul(w, GL_GENERATOR);  // domain.rs:123 get_ce_x_at
+        d0[r] = gl_sub(x, 1);             // boundary divisor of the step-0 group
+        d1[r] = gl_sub(x, p.last);        // boundary divisor of the last-step group = transition exemption
+    }
+    // batch inversion of the products d0*d1 (never zero: x lies on the coset 7<w>, 1 and g^(n-1) do not)
+    u64 prod[FIB_ROWS], pre[FIB_ROWS], run = 1;
+#pragma unroll
+    for (int r = 0; r < FIB_ROWS; r++) { prod[r] = gl_mul(d0[r], d1[r]); pre[r] = run; run = gl_mul(run, prod[r]); }
+    run = gl_inv(run);
+#pragma unroll
+    for (int r = FIB_ROWS - 1; r >= 0; r--) { u64 inv = gl_mul(run, pre[r]); run = gl_mul(run, prod[r]); prod[r] = inv; }
+#pragma unroll
+    for (int r = 0; r < FIB_ROWS; r++) {
+        const size_t i = tid + r * stride;
+        if (i >= ce) continue;
+        u64 z0 = gl_mul(prod[r], d1[r]), z1 = gl_mul(prod[r], d0[r]);                   // 1/(x - 1), 1/(x - g^(n-1))
+        u64 zt = gl_mul(p.zt[i & (((size_t)1 << p.log_ce_blowup) - 1)], d1[r]);         // e(x) / (x^n - 1)
+        GlExt<D> acc = ext_add(ext_add(ext_mul_base(T[r], zt), ext_mul_base(B0[r], z0)), ext_mul_base(B1[r], z1));
+        u64* o = p.out.base + i * p.out.W;
+#pragma unroll
+        for (int q = 0; q < D; q++) o[q] = acc.v[q];
+    }
 }
 
 // composition_poly.rs:128-140 segment(): column j = coefficients [j*n, (j+1)*n) of the interpolated
@@ -103,63 +124,69 @@ __global__ void comp_split_kernel(SegMatrix coefs, size_t n, u32 kc, int D, SegM
     out.base[(size_t)(col / out.W) * out.seg_stride + i * out.W + (col % out.W)] = v;
 }
 
-// Horner evaluation of every base-coefficient column at an extension point, as per-chunk partial
-// sums (polynom::eval, math/src/polynom/mod.rs:55-62; ColMatrix::evaluate_columns_at :245).
-// Block = 256 threads x OOD_PER_THREAD coefficients of one segment; partial[seg col][chunk] =
-// z^(chunk start) * sum_{m in chunk} a_m z^(m - start).
+// Horner evaluation of every base-coefficient column at TWO extension points (z and z*g), as
+// per-chunk partial sums (polynom::eval, math/src/polynom/mod.rs:55-62; ColMatrix::evaluate_columns_at
+// :245; TracePolyTable::get_ood_frame poly_table.rs:68-76). Block = 256 threads x OOD_PER_THREAD
+// coefficients of one segment; partial[col][chunk][point] = sum_{m in chunk} a_m z^m.
 #define OOD_PER_THREAD 16
 template <int D>
-__global__ void __launch_bounds__(256) ood_partial_kernel(SegMatrix polys, GlExt<D> z, u64* partial /*[cols][chunks][D]*/,
-                                                          u32 chunks) {
+__global__ void __launch_bounds__(256) ood_partial_kernel(SegMatrix polys, GlExt<D> z0, GlExt<D> z1,
+                                                          u64* partial /*[cols][chunks][2][D]*/, u32 chunks) {
     const u32 g = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
     const int W = polys.W;
     const size_t n = polys.rows;
     const size_t start = ((size_t)chunk * 256 + t) * OOD_PER_THREAD;
-    GlExt<D> acc[8];
-#pragma unroll
-    for (int q = 0; q < 8; q++) acc[q] = ext_zero<D>();
     const u64* base = polys.base + (size_t)g * polys.seg_stride;
-    for (int r = OOD_PER_THREAD - 1; r >= 0; r--) {
-        size_t row = start + r;
-        if (row >= n) continue;
+    __shared__ u64 red[2][8][8][D];
+#pragma unroll
+    for (int pt = 0; pt < 2; pt++) {
+        const GlExt<D> z = pt == 0 ? z0 : z1;
+        GlExt<D> acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q] = ext_zero<D>();
+        for (int r = OOD_PER_THREAD - 1; r >= 0; r--) {
+            size_t row = start + r;
+            if (row >= n) continue;
+            for (int q = 0; q < W; q++) {
+                acc[q] = ext_mul(acc[q], z);
+                acc[q].v[0] = gl_add(acc[q].v[0], base[row * W + q]);
+            }
+        }
+        GlExt<D> zp = ext_pow(z, start);  // z^(first row of this thread)
         for (int q = 0; q < W; q++) {
-            acc[q] = ext_mul(acc[q], z);
-            acc[q].v[0] = gl_add(acc[q].v[0], base[row * W + q]);
-        }
-    }
-    GlExt<D> zp = ext_pow(z, start);  // z^(first row of this thread)
-    __shared__ u64 red[8][8][D];
-    for (int q = 0; q < W; q++) {
-        GlExt<D> v = ext_mul(acc[q], zp);
+            GlExt<D> v = ext_mul(acc[q], zp);
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
+            for (int off = 16; off > 0; off >>= 1) {
 #pragma unroll
-            for (int c = 0; c < D; c++) v.v[c] = gl_add(v.v[c], __shfl_down_sync(0xffffffffu, v.v[c], off));
-        }
-        if ((t & 31) == 0) {
+                for (int c = 0; c < D; c++) v.v[c] = gl_add(v.v[c], __shfl_down_sync(0xffffffffu, v.v[c], off));
+            }
+            if ((t & 31) == 0) {
 #pragma unroll
-            for (int c = 0; c < D; c++) red[t >> 5][q][c] = v.v[c];
+                for (int c = 0; c < D; c++) red[pt][t >> 5][q][c] = v.v[c];
+            }
         }
     }
     __syncthreads();
-    if (t < (u32)W) {
-        u32 col = g * W + t;
+    if (t < (u32)(2 * W)) {
+        const u32 pt = t / W, q = t % W;
+        u32 col = g * W + q;
         if (col < polys.cols) {
             GlExt<D> s = ext_zero<D>();
-            for (int wp = 0; wp < 8; wp++) s = ext_add(s, ld_ext<D>(&red[wp][t][0]));
-            u64* o = partial + ((size_t)col * chunks + chunk) * D;
+            for (int wp = 0; wp < 8; wp++) s = ext_add(s, ld_ext<D>(&red[pt][wp][q][0]));
+            u64* o = partial + (((size_t)col * chunks + chunk) * 2 + pt) * D;
 #pragma unroll
             for (int c = 0; c < D; c++) o[c] = s.v[c];
         }
     }
 }
 template <int D>
-__global__ void ood_reduce_kernel(const u64* partial, u32 cols, u32 chunks, u64* out /*[cols][D]*/) {
-    u32 col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= cols) return;
+__global__ void ood_reduce_kernel(const u64* partial, u32 cols, u32 chunks, u64* out /*[cols][2][D]*/) {
+    u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cols * 2) return;
+    u32 col = idx >> 1, pt = idx & 1;
     GlExt<D> s = ext_zero<D>();
-    for (u32 c = 0; c < chunks; c++) s = ext_add(s, ld_ext<D>(partial + ((size_t)col * chunks + c) * D));
-    for (int c = 0; c < D; c++) out[(size_t)col * D + c] = s.v[c];
+    for (u32 c = 0; c < chunks; c++) s = ext_add(s, ld_ext<D>(partial + (((size_t)col * chunks + c) * 2 + pt) * D));
+    for (int c = 0; c < D; c++) out[(size_t)idx * D + c] = s.v[c];
 }
 
 struct DeepParams {
@@ -334,26 +361,44 @@ int upload_ext(wf_ctx* ctx, const std::vector<GlExt<D>>& v, size_t first, size_t
     return WF_OK;
 }
 
-// evaluate all columns of a coefficient matrix at extension point z -> host vector [cols][D]
+// evaluate all columns of two coefficient matrices at z0 and z1 -> host vectors [cols][D]; one
+// synchronisation for both matrices
 template <int D>
-int ood_eval(wf_ctx* ctx, const wf_mat* polys, const GlExt<D>& z, std::vector<GlExt<D>>& out) {
-    const size_t n = polys->m.rows;
-    const u32 chunks = (u32)((n + 256 * OOD_PER_THREAD - 1) / (256 * OOD_PER_THREAD));
-    const u32 cols = polys->m.cols;
-    void *part, *res;
-    CKI(wf_dev_alloc(ctx, (size_t)cols * chunks * D * 8, &part));
-    CKI(wf_dev_alloc(ctx, (size_t)cols * D * 8, &res));
-    ood_partial_kernel<D><<<dim3(chunks, polys->m.nseg()), 256, 0, ctx->st>>>(polys->m, z, (u64*)part, chunks);
-    ood_reduce_kernel<D><<<(cols + 63) / 64, 64, 0, ctx->st>>>((const u64*)part, cols, chunks, (u64*)res);
-    ctx->launches += 2;
-    CK(cudaGetLastError());
-    std::vector<u64> host((size_t)cols * D);
+int ood_eval(wf_ctx* ctx, const wf_mat* a, const wf_mat* b, const GlExt<D>& z0, const GlExt<D>& z1,
+             std::vector<GlExt<D>> out[4] /* a@z0, a@z1, b@z0, b@z1 */) {
+    const wf_mat* mats[2] = {a, b};
+    void* part[2];
+    void* res;
+    const size_t total_cols = (size_t)a->m.cols + b->m.cols;
+    CKI(wf_dev_alloc(ctx, total_cols * 2 * D * 8, &res));
+    size_t off = 0;
+    for (int m = 0; m < 2; m++) {
+        const size_t n = mats[m]->m.rows;
+        const u32 chunks = (u32)((n + 256 * OOD_PER_THREAD - 1) / (256 * OOD_PER_THREAD));
+        const u32 cols = mats[m]->m.cols;
+        CKI(wf_dev_alloc(ctx, (size_t)cols * chunks * 2 * D * 8, &part[m]));
+        ood_partial_kernel<D><<<dim3(chunks, mats[m]->m.nseg()), 256, 0, ctx->st>>>(mats[m]->m, z0, z1, (u64*)part[m], chunks);
+        ood_reduce_kernel<D><<<(2 * cols + 63) / 64, 64, 0, ctx->st>>>((const u64*)part[m], cols, chunks, (u64*)res + off);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+        off += (size_t)cols * 2 * D;
+    }
+    std::vector<u64> host(total_cols * 2 * D);
     CK(cudaMemcpyAsync(host.data(), res, host.size() * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    wf_dev_free(ctx, part);
+    wf_dev_free(ctx, part[0]);
+    wf_dev_free(ctx, part[1]);
     wf_dev_free(ctx, res);
-    out.resize(cols);
-    for (u32 j = 0; j < cols; j++) for (int q = 0; q < D; q++) out[j].v[q] = host[(size_t)j * D + q];
+    off = 0;
+    for (int m = 0; m < 2; m++) {
+        const u32 cols = mats[m]->m.cols;
+        out[2 * m].resize(cols);
+        out[2 * m + 1].resize(cols);
+        for (u32 j = 0; j < cols; j++)
+            for (int pt = 0; pt < 2; pt++)
+                for (int q = 0; q < D; q++) out[2 * m + pt][j].v[q] = host[off + ((size_t)j * 2 + pt) * D + q];
+        off += (size_t)cols * 2 * D;
+    }
     return WF_OK;
 }
 
@@ -362,18 +407,14 @@ void write_elems(ByteVec& w, const std::vector<GlExt<D>>& v) {
     for (auto& e : v) for (int q = 0; q < D; q++) w.u64_(e.v[q]);
 }
 
-// Queries::new (air/src/proof/queries.rs:51-78) + Serializable (:138-146)
-int write_queries(wf_ctx* ctx, const wf_mat* m, const wf_tree* t, const std::vector<u64>& pos, ByteVec& w) {
-    std::vector<u64> rows(pos.size() * m->m.cols);
-    CKI(wf_mat_read_rows(ctx, m, pos.data(), pos.size(), rows.data(), 0));
-    std::vector<u8> leaves(pos.size() * 32);
+// Queries::new (air/src/proof/queries.rs:51-78) + Serializable (:138-146), from batched gathers
+void write_queries(const GatherBatch& gb, size_t row_id, size_t dig_id, size_t nvals, ByteVec& w) {
     ByteVec proof;
-    CKI(wf_tree_open_many_bytes(ctx, t, pos.data(), pos.size(), leaves.data(), proof));
-    w.usize(rows.size() * 8);
-    w.bytes(rows.data(), rows.size() * 8);
+    wf_open_finish(gb.digs[dig_id].plan, gb.digest_result(dig_id), nullptr, proof);
+    w.usize(nvals * 8);
+    w.bytes(gb.row_result(row_id), nvals * 8);
     w.usize(proof.v.size());
     w.bytes(proof.v.data(), proof.v.size());
-    return WF_OK;
 }
 
 template <int D>
@@ -439,7 +480,8 @@ int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, const uint64_t* d_
         // x^n over the CE domain takes ce_blowup values: (7 w_ce^i)^n = 7^n * w_ceb^i
         u64 o_n = gl_pow(GL_GENERATOR, n), w_ceb = gl_root_of_unity(log_ceb);
         for (u32 i = 0; i < (1u << log_ceb); i++) p.zt[i] = gl_inv(gl_sub(gl_mul(o_n, gl_pow(w_ceb, i)), 1));
-        fib_constraints_kernel<D><<<(unsigned)((ce + 255) / 256), 256, 0, ctx->st>>>(p);
+        size_t threads = (ce + FIB_ROWS - 1) / FIB_ROWS;
+        fib_constraints_kernel<D><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->st>>>(p);
         ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -466,11 +508,9 @@ int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, const uint64_t* d_
     // ---- 4. out-of-domain frames (lib.rs:392-401) ----
     GlExt<D> z = ch.draw();
     GlExt<D> zg = ext_mul_base(z, gl_root_of_unity(log_n));
-    std::vector<GlExt<D>> t_cur, t_nxt, qb_cur, qb_nxt;
-    CKI(ood_eval<D>(ctx, polys, z, t_cur));
-    CKI(ood_eval<D>(ctx, polys, zg, t_nxt));
-    CKI(ood_eval<D>(ctx, cpolys, z, qb_cur));   // per base component column
-    CKI(ood_eval<D>(ctx, cpolys, zg, qb_nxt));
+    std::vector<GlExt<D>> ood[4];
+    CKI(ood_eval<D>(ctx, polys, cpolys, z, zg, ood));
+    std::vector<GlExt<D>>&t_cur = ood[0], &t_nxt = ood[1], &qb_cur = ood[2], &qb_nxt = ood[3];  // qb_*: per base component column
     // H_j(z) = sum_comp phi^comp * (component column evaluated at z)
     auto combine = [&](const std::vector<GlExt<D>>& comp_evals) {
         std::vector<GlExt<D>> r(kc);
@@ -543,16 +583,20 @@ int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, const uint64_t* d_
     w.u8_((u8)pos.size());
     w.u16_((uint16_t)ch.commitments.v.size());
     w.bytes(ch.commitments.v.data(), ch.commitments.v.size());
-    CKI(write_queries(ctx, lde, ttree, pos, w));
-    CKI(write_queries(ctx, clde, ctree, pos, w));
+    // every gather of the proof (trace rows, constraint rows, all FRI layers + their Merkle paths)
+    // goes through one batch: one index upload, one download, one synchronisation
+    GatherBatch gb;
+    FriProofPlan fplan;
+    size_t tr_rows = gb.add_rows(lde->m, pos), cr_rows = gb.add_rows(clde->m, pos), tr_dig, cr_dig;
+    CKI(gb.add_opening(ctx, ttree, pos, &tr_dig));
+    CKI(gb.add_opening(ctx, ctree, pos, &cr_dig));
+    CKI(wf_fri_queue_proof(ctx, fri, pos, gb, fplan));
+    CKI(gb.run(ctx));
+    write_queries(gb, tr_rows, tr_dig, pos.size() * c, w);
+    write_queries(gb, cr_rows, cr_dig, pos.size() * kc * D, w);
     w.u16_((uint16_t)ood_t.v.size()); w.bytes(ood_t.v.data(), ood_t.v.size());
     w.u16_((uint16_t)ood_q.v.size()); w.bytes(ood_q.v.data(), ood_q.v.size());
-    {
-        std::vector<u8> fp(1 << 22);
-        size_t fl = fp.size();
-        CKI(wf_fri_build_proof(ctx, fri, pos.data(), pos.size(), fp.data(), &fl));
-        w.bytes(fp.data(), fl);
-    }
+    wf_fri_finish_proof(fri, gb, fplan, w);
     w.u64_(nonce);
     wf_mark(ctx, "queries_and_proof");
     proof_out.swap(w.v);
