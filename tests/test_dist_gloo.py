@@ -1,0 +1,79 @@
+"""world_size-2 `gloo` test of the multi-GPU host logic (winterfell_b200/dist.py) on CPU: the sharding
+plan, the all-to-all row re-sharding, the subtree-root all-gather and the top-of-tree merge. Local
+compute is done by a CPU test backend built on the oracle; the result must equal the single-device
+commitment of the whole trace."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleBackend:
+    def lde_rows(self, cols, ncols, n, log_blowup):
+        from oracle import oracle as o
+        polys = o.interpolate_columns(cols.numpy().view(np.uint64))
+        return torch.from_numpy(o.lde_rows(polys, 1 << log_blowup).view(np.int64))
+
+    def subtree_root(self, hash_id, rows):
+        from oracle import oracle as o
+        lv = o.hash_rows(hash_id, rows.numpy().view(np.uint64))
+        nd = o.merkle_nodes(hash_id, lv)
+        return nd[1].tobytes(), torch.from_numpy(lv), torch.from_numpy(nd)
+
+
+def _worker(rank, world, port, hash_id, log_n, cols, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as o
+    from winterfell_b200 import dist as wd
+    n = 1 << log_n
+    trace = o.rand_elems((cols, n), 99)            # same seed on every rank: the whole trace
+    lo, hi = wd.column_range(cols, world, rank)
+    local = torch.from_numpy(trace[lo:hi].copy().view(np.int64))
+    root, rows, digests, nodes = wd.sharded_trace_commit(OracleBackend(), hash_id, local, cols, log_n, 3)
+    # single-device reference: commitment of the full trace
+    lde = o.lde_rows(o.interpolate_columns(trace), 8)
+    want_nodes = o.merkle_nodes(hash_id, o.hash_rows(hash_id, lde))
+    N = n * 8
+    ok = root == want_nodes[1].tobytes()
+    ok = ok and (rows.numpy().view(np.uint64) == lde[rank * N // world:(rank + 1) * N // world]).all()
+    # my subtree is the heap node world + rank of the full tree
+    ok = ok and nodes.numpy()[1].tobytes() == want_nodes[world + rank].tobytes()
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("hash_id,log_n,cols", [(0, 6, 4), (1, 5, 2)])
+def test_sharded_trace_commit_world2(hash_id, log_n, cols):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, hash_id, log_n, cols, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_column_ranges_and_top_levels(oracle):
+    from winterfell_b200 import dist as wd
+    assert [wd.column_range(64, 8, r) for r in (0, 7)] == [(0, 8), (56, 64)]
+    assert [wd.column_range(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    leaves = np.random.default_rng(1).integers(0, 256, (8, 32), dtype=np.uint8)
+    nodes = oracle.merkle_nodes(0, leaves)
+    # the four depth-2 nodes (heap 4..7) merge to the root
+    assert wd.top_levels(0, [nodes[4 + i].tobytes() for i in range(4)]) == nodes[1].tobytes()

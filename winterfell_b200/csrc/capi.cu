@@ -479,11 +479,15 @@ static int tree_alloc(wf_ctx* ctx, int hash_id, size_t nleaves, wf_tree** out) {
     return WF_OK;
 }
 static u32 merkle_launches(size_t nleaves) {
-    u32 l = 1;
+    u32 l = 0;
     size_t m = nleaves / 2;
-    bool any = false;
-    while (m > 256) { l++; m >>= 1; any = true; }
-    if (!any) l++;
+    while (m > (1u << 13)) { l++; m >>= 1; }
+    for (;;) {
+        l++;
+        if (m <= 256) break;
+        m = (m >> 8) >> 1;
+        if (m == 0) break;
+    }
     return l;
 }
 int wf_commit_rows(wf_ctx* ctx, int hash_id, const wf_mat* m, wf_tree** out) {

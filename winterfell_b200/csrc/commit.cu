@@ -150,34 +150,58 @@ __global__ void __launch_bounds__(128) merkle_level_rp64_kernel(const u64* __res
     for (int k = 0; k < 4; k++) out[4 * i + k] = o[k];
 }
 
-// the last levels (count <= 256 parents) in one block: nodes[count..2count) -> ... -> nodes[1]
-__global__ void __launch_bounds__(256) merkle_top_kernel(int hash_id, u64* nodes, u32 count) {
-    // `count` = number of nodes on the level to compute first; its children are already in place at
-    // nodes[2*count .. 4*count)
-    for (u32 m = count; m >= 1; m >>= 1) {
-        u32 i = threadIdx.x;
-        if (i < m) {
-            if (hash_id == WF_HASH_BLAKE3_256) {
-                const u32* src = reinterpret_cast<const u32*>(nodes + (size_t)(2 * (m + i)) * 4);
-                u32 msg[16], cv[8];
+// Up to 9 tree levels per launch: block b turns 512 consecutive child digests into their 256 parents
+// and keeps reducing in shared memory down to the single ancestor of the block; every level is written
+// to its heap position (nodes[m + ...], crypto/src/merkle/mod.rs:344-368). `m` = number of nodes on
+// the first level computed (children = `src`, 2m digests); levels stop at `m_stop` (inclusive).
+template <int HASH>
+__device__ __forceinline__ void merge_digests(const u64* a /*8 words: two digests*/, u64* out /*4 words*/) {
+    if (HASH == WF_HASH_BLAKE3_256) {
+        u32 msg[16], cv[8];
 #pragma unroll
-                for (int k = 0; k < 16; k++) msg[k] = src[k];
-                b3_hash64(msg, cv);
-                u32* dst = reinterpret_cast<u32*>(nodes + (size_t)(m + i) * 4);
+        for (int k = 0; k < 8; k++) { msg[2 * k] = (u32)a[k]; msg[2 * k + 1] = (u32)(a[k] >> 32); }
+        b3_hash64(msg, cv);
 #pragma unroll
-                for (int k = 0; k < 8; k++) dst[k] = cv[k];
-            } else {
-                u64 v[8], o[4];
+        for (int k = 0; k < 4; k++) out[k] = (u64)cv[2 * k] | ((u64)cv[2 * k + 1] << 32);
+    } else {
+        rp64_merge(a, out);
+    }
+}
+template <int HASH>
+__global__ void __launch_bounds__(256) merkle_subtree_kernel(const u64* __restrict__ src, u64* __restrict__ nodes, size_t m) {
+    __shared__ u64 lvl[256][4];
+    const u32 t = threadIdx.x;
+    const size_t b = blockIdx.x;
+    size_t i = b * 256 + t;  // parent index within the level
+    if (i < m) {
+        u64 in[8], o[4];
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(src + i * 8);
 #pragma unroll
-                for (int k = 0; k < 8; k++) v[k] = nodes[(size_t)(2 * (m + i)) * 4 + k];
-                rp64_merge(v, o);
+        for (int k = 0; k < 4; k++) { ulonglong2 v = __ldg(p + k); in[2 * k] = v.x; in[2 * k + 1] = v.y; }
+        merge_digests<HASH>(in, o);
 #pragma unroll
-                for (int k = 0; k < 4; k++) nodes[(size_t)(m + i) * 4 + k] = o[k];
-            }
+        for (int k = 0; k < 4; k++) { lvl[t][k] = o[k]; nodes[(m + i) * 4 + k] = o[k]; }
+    }
+    // further levels inside the block: level size (per block) 128, 64, ..., 1
+    size_t level_m = m;
+    for (u32 width = 128; width >= 1; width >>= 1) {
+        level_m >>= 1;
+        if (level_m == 0) break;
+        __syncthreads();
+        u64 in[8], o[4];
+        const bool active = t < width && (b * width + t) < level_m;
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) { in[k] = lvl[2 * t][k]; in[4 + k] = lvl[2 * t + 1][k]; }
+            merge_digests<HASH>(in, o);
         }
         __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) { lvl[t][k] = o[k]; nodes[(level_m + b * width + t) * 4 + k] = o[k]; }
+        }
     }
-    if (threadIdx.x < 4) nodes[threadIdx.x] = 0;  // nodes[0] = default digest (merkle/mod.rs:349)
+    if (m <= 256 && b == 0 && t < 4) nodes[t] = 0;  // nodes[0] = default digest (merkle/mod.rs:349); set by the last launch
 }
 
 cudaError_t commit_hash_rows(int hash_id, const SegMatrix& m, u64* digests, cudaStream_t st) {
@@ -199,31 +223,32 @@ cudaError_t commit_hash_rows(int hash_id, const SegMatrix& m, u64* digests, cuda
 }
 
 cudaError_t commit_merkle_nodes(int hash_id, const u64* leaves, size_t nleaves, u64* nodes, cudaStream_t st) {
-    // nodes: nleaves digests (4 words each)
+    // nodes: nleaves digests (4 words each). Each launch covers up to 9 levels.
     if (nleaves < 2) return cudaErrorInvalidValue;
-    size_t m = nleaves / 2;         // parents of leaf pairs live at nodes[m .. 2m)
+    size_t m = nleaves / 2;  // parents of leaf pairs live at nodes[m .. 2m)
     const u64* src = leaves;
-    while (m > 256) {
+    // wide levels: one full-occupancy launch per level (the in-block tail of the fused kernel would
+    // idle 7/8 of every block); narrow levels (launch-latency-bound): fused, 9 levels per launch
+    while (m > (1u << 13)) {
         u64* dst = nodes + m * 4;
-        if (hash_id == WF_HASH_BLAKE3_256) {
-            merkle_level_blake3_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(
-                reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), m);
-        } else {
+        if (hash_id == WF_HASH_BLAKE3_256)
+            merkle_level_blake3_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src),
+                                                                                   reinterpret_cast<uint4*>(dst), m);
+        else
             merkle_level_rp64_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(src, dst, m);
-        }
         src = dst;
         m >>= 1;
     }
-    // remaining levels in one block. If the leaf level itself is small, compute its parents first.
-    if (src == leaves) {
-        u64* dst = nodes + m * 4;
-        if (hash_id == WF_HASH_BLAKE3_256)
-            merkle_level_blake3_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const uint4*>(src),
-                                                          reinterpret_cast<uint4*>(dst), m);
-        else
-            merkle_level_rp64_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(src, dst, m);
-        m >>= 1;
+    for (;;) {
+        unsigned blocks = (unsigned)((m + 255) / 256);
+        if (hash_id == WF_HASH_BLAKE3_256) merkle_subtree_kernel<WF_HASH_BLAKE3_256><<<blocks, 256, 0, st>>>(src, nodes, m);
+        else merkle_subtree_kernel<WF_HASH_RP64_256><<<blocks, 256, 0, st>>>(src, nodes, m);
+        if (m <= 256) break;           // this launch reached the root
+        // the launch produced levels m, m/2, ..., m/256 (one node per block); continue above them
+        size_t top = m >> 8;
+        src = nodes + 2 * (top >> 1) * 4;  // children of the next level = nodes[top .. 2*top)
+        m = top >> 1;
+        if (m == 0) break;
     }
-    merkle_top_kernel<<<1, 256, 0, st>>>(hash_id, nodes, (u32)m);
     return cudaGetLastError();
 }

@@ -198,17 +198,19 @@ struct DeepParams {
     const u64* ccc;    // [kc][D] DEEP coefficients for composition columns
     const u64* tw_N;   // w_N^i, i < N/2
 };
-#define DEEP_ROWS 4
+// rows per thread sharing one batch inversion: 8 in the base field, 4 for extensions (registers)
+#define DEEP_ROWS (D == 1 ? 8 : 4)
 // DeepCompositionPoly in evaluation form; DEEP_ROWS rows per thread share one batch inversion.
 template <int D>
 __global__ void __launch_bounds__(256) deep_eval_kernel(DeepParams p, GlExt<D> z, GlExt<D> zg, GlExt<D> Sz, GlExt<D> Szg) {
     const size_t N = (size_t)1 << p.log_N;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    GlExt<D> S[DEEP_ROWS], den[2 * DEEP_ROWS];
+    constexpr int ROWS = (D == 1 ? 8 : 4);
+    GlExt<D> S[ROWS], den[2 * ROWS];
     const u32 half = (u32)(N >> 1);
 #pragma unroll
-    for (int r = 0; r < DEEP_ROWS; r++) {
+    for (int r = 0; r < ROWS; r++) {
         size_t row = tid + r * stride;
         S[r] = ext_zero<D>();
         den[2 * r] = ext_from_base<D>(1);
@@ -230,15 +232,15 @@ __global__ void __launch_bounds__(256) deep_eval_kernel(DeepParams p, GlExt<D> z
     // batch inversion (math/src/utils/mod.rs:169 Montgomery trick); denominators are never zero
     // (z is outside the base-field LDE domain with overwhelming probability; a zero would also
     // break the reference's synthetic division)
-    GlExt<D> pre[2 * DEEP_ROWS];
+    GlExt<D> pre[2 * ROWS];
     GlExt<D> run = ext_from_base<D>(1);
 #pragma unroll
-    for (int q = 0; q < 2 * DEEP_ROWS; q++) { pre[q] = run; run = ext_mul(run, den[q]); }
+    for (int q = 0; q < 2 * ROWS; q++) { pre[q] = run; run = ext_mul(run, den[q]); }
     run = ext_inv(run);
 #pragma unroll
-    for (int q = 2 * DEEP_ROWS - 1; q >= 0; q--) { GlExt<D> inv = ext_mul(run, pre[q]); run = ext_mul(run, den[q]); den[q] = inv; }
+    for (int q = 2 * ROWS - 1; q >= 0; q--) { GlExt<D> inv = ext_mul(run, pre[q]); run = ext_mul(run, den[q]); den[q] = inv; }
 #pragma unroll
-    for (int r = 0; r < DEEP_ROWS; r++) {
+    for (int r = 0; r < ROWS; r++) {
         size_t row = tid + r * stride;
         if (row >= N) continue;
         GlExt<D> v = ext_add(ext_mul(ext_sub(S[r], Sz), den[2 * r]), ext_mul(ext_sub(S[r], Szg), den[2 * r + 1]));
@@ -552,7 +554,8 @@ int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, const uint64_t* d_
         p.trace = lde->m; p.cons = clde->m; p.out = deep->m; p.c = c; p.kc = kc; p.log_N = log_n + log_b;
         p.tcc = d_dt; p.ccc = d_dq;
         CKI(wf_get_twiddles(ctx, log_n + log_b, &p.tw_N));
-        size_t threads = (N + DEEP_ROWS - 1) / DEEP_ROWS;
+        const size_t rows_per_thread = (D == 1 ? 8 : 4);
+        size_t threads = (N + rows_per_thread - 1) / rows_per_thread;
         deep_eval_kernel<D><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->st>>>(p, z, zg, Sz, Szg);
         ctx->launches++;
         CK(cudaGetLastError());
