@@ -174,9 +174,41 @@ static void pass_defaults(NttPassParams& p, const SegMatrix& in, const SegMatrix
 static int run_ntt(wf_ctx* ctx, const SegMatrix& in, SegMatrix& out, const SegMatrix* tmp, u32 log_n, int inverse) {
     u32 logR, logC;
     split_log(log_n, in.W, &logR, &logC);
-    if (logC > NTT_MAX_LOGS) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "NTT size 2^%u exceeds the two-pass limit 2^%d", log_n, 2 * NTT_MAX_LOGS);
     u64 inv_n = gl_inv(((u64)1 << log_n) % GL_P);
     NttPassParams p;
+    if (logC > NTT_MAX_LOGS) {
+        // THREE passes (n > 2^22): n = R * C with C itself two-pass. Pass A is the strided size-R step
+        // of the four-step scheme over the whole array; the contiguous size-C step is then a batch of R
+        // independent two-pass transforms (batch index = j1) whose last pass writes X[j1 + R * j].
+        if (!tmp) return wf_fail(ctx, WF_ERR_STATE, "run_ntt: scratch matrix required");
+        u32 lr = (log_n + 2) / 3, lc = log_n - lr, lr2, lc2;
+        split_log(lc, in.W, &lr2, &lc2);
+        if (lr2 == 0 || lc2 > NTT_MAX_LOGS || lr > NTT_MAX_LOGS - (in.W == 1 ? 1 : 0))
+            return wf_fail(ctx, WF_ERR_UNSUPPORTED, "NTT size 2^%u exceeds the three-pass limit", log_n);
+        pass_defaults(p, in, *tmp);  // pass A
+        p.logS = (int)lr; p.logR = lr; p.logC = lc; p.inverse = inverse;
+        CKI(wf_get_twiddles(ctx, lr, &p.sub_tw));
+        p.has_post = 1;
+        CKI(wf_get_twiddles(ctx, log_n, &p.master));
+        p.logM = log_n; p.a_mul = 1; p.b_mul = 0; p.cconst = inverse ? inv_n : 1;
+        CK(ntt_launch_pass(NTT_STRIDED, p, in.nseg(), 1, ctx->st));
+        pass_defaults(p, *tmp, *tmp);  // pass B: in place, batch = row j1 of the R x C matrix
+        p.in_batch_stride = p.out_batch_stride = ((size_t)1 << lc) * in.W;
+        p.logS = (int)lr2; p.logR = lr2; p.logC = lc2; p.inverse = inverse;
+        CKI(wf_get_twiddles(ctx, lr2, &p.sub_tw));
+        p.has_post = 1;
+        CKI(wf_get_twiddles(ctx, lc, &p.master));
+        p.logM = lc; p.a_mul = 1; p.b_mul = 0;
+        CK(ntt_launch_pass(NTT_STRIDED, p, in.nseg(), 1u << lr, ctx->st));
+        pass_defaults(p, *tmp, out);  // pass C: X[j1 + R * (inner index)]
+        p.in_batch_stride = ((size_t)1 << lc) * in.W;
+        p.logS = (int)lc2; p.logR = lr2; p.logC = lc2; p.inverse = inverse;
+        p.out_row_mul = 1u << lr; p.out_row_add = 1;
+        CKI(wf_get_twiddles(ctx, lc2, &p.sub_tw));
+        CK(ntt_launch_pass(NTT_CONTIG, p, in.nseg(), 1u << lr, ctx->st));
+        ctx->launches += 3;
+        return WF_OK;
+    }
     if (logR == 0) {
         pass_defaults(p, in, out);
         p.logS = (int)logC; p.logR = 0; p.logC = logC; p.inverse = inverse;

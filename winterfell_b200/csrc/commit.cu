@@ -49,7 +49,7 @@ __device__ void blake3_row(const RowSrc& m, size_t row, u32 out[8]) {
             u32 bl = min(64u, (e1 - e0 - b * 8) * 8);
             u32 fl = (b == 0 ? B3_CHUNK_START : 0) |
                      (b == nblk - 1 ? (B3_CHUNK_END | (nchunks == 1 ? B3_ROOT : 0)) : 0);
-            b3_compress(cv, msg, c, bl, fl);
+            b3_compress(cv, msg, c, bl, fl, b3_runtime_one());
         }
         if (c == nchunks - 1) break;
         u32 total = c + 1;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) hash_rows_blake3_w8c8_kernel(const u64* _
         msg[4 * k] = v.x; msg[4 * k + 1] = v.y; msg[4 * k + 2] = v.z; msg[4 * k + 3] = v.w;
     }
     u32 cv[8];
-    b3_hash64(msg, cv);
+    b3_hash64(msg, cv, b3_runtime_one());
     digests[2 * row] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
     digests[2 * row + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) merkle_level_blake3_kernel(const uint4* _
         msg[4 * k] = v.x; msg[4 * k + 1] = v.y; msg[4 * k + 2] = v.z; msg[4 * k + 3] = v.w;
     }
     u32 cv[8];
-    b3_hash64(msg, cv);
+    b3_hash64(msg, cv, b3_runtime_one());
     out[2 * i] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
     out[2 * i + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
@@ -160,7 +160,7 @@ __device__ __forceinline__ void merge_digests(const u64* a /*8 words: two digest
         u32 msg[16], cv[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) { msg[2 * k] = (u32)a[k]; msg[2 * k + 1] = (u32)(a[k] >> 32); }
-        b3_hash64(msg, cv);
+        b3_hash64(msg, cv, b3_runtime_one());
 #pragma unroll
         for (int k = 0; k < 4; k++) out[k] = (u64)cv[2 * k] | ((u64)cv[2 * k + 1] << 32);
     } else {

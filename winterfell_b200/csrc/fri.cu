@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) fri_hash_blake3_kernel(const u64* __restr
         }
         u32 bl = min(64u, (ne - b * 8) * 8);
         u32 fl = (b == 0 ? B3_CHUNK_START : 0) | (b == nblk - 1 ? (B3_CHUNK_END | B3_ROOT) : 0);
-        b3_compress(cv, msg, 0, bl, fl);
+        b3_compress(cv, msg, 0, bl, fl, b3_runtime_one());
     }
     digests[2 * i] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
     digests[2 * i + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);

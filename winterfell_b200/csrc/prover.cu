@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) grind_kernel(int hash_id, const u64* seed
 #pragma unroll
         for (int i = 10; i < 16; i++) m[i] = 0;
         b3_iv(cv);
-        b3_compress(cv, m, 0, 40, B3_CHUNK_START | B3_CHUNK_END | B3_ROOT);  // blake/mod.rs:41-46
+        b3_compress(cv, m, 0, 40, B3_CHUNK_START | B3_CHUNK_END | B3_ROOT, b3_runtime_one());  // blake/mod.rs:41-46
         head = (u64)cv[0] | ((u64)cv[1] << 32);
     } else {
         u64 s[12];  // rp64_256/mod.rs:198-218
