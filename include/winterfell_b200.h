@@ -98,6 +98,10 @@ int wf_mat_interpolate_with_offset(wf_ctx* ctx, const wf_mat* evals, uint64_t do
 /* RowMatrix::commit_to_rows (row_matrix.rs:184-228) with partition_size == num_cols, then
  * MerkleTree::new (crypto/src/merkle/mod.rs:116-135). */
 int wf_commit_rows(wf_ctx* ctx, int hash_id, const wf_mat* m, wf_tree** out);
+/* same with column partitions (row_matrix.rs:204-223): the row digest is H::merge_many of the digests of
+ * chunks of `partition_size` BASE columns — partition_size = PartitionOptions::partition_size::<E>(cols)
+ * * E::EXTENSION_DEGREE (air/src/options.rs:428-444); at most 16 partitions. 0 = whole rows. */
+int wf_commit_rows_partitioned(wf_ctx* ctx, int hash_id, const wf_mat* m, uint32_t partition_size, wf_tree** out);
 /* MerkleTree::new from host/device leaf digests (VectorCommitment::new, crypto/src/commitment.rs:41) */
 int wf_tree_from_leaves(wf_ctx* ctx, int hash_id, const uint8_t* leaves, size_t nleaves, int leaves_on_device,
                         wf_tree** out);

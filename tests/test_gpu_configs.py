@@ -72,7 +72,7 @@ def test_config3_rp64_2p18(ctx, oracle):
     _check(ctx, oracle, 1, 18, opts, compare_bytes=False)
 
 
-@pytest.mark.parametrize("log_len,d", [(20, 1), (22, 1), (20, 3)])
+@pytest.mark.parametrize("log_len,d", [(20, 1), (22, 1), (20, 3), (26, 1)])
 def test_config4_fri_only(ctx, oracle, log_len, d):
     # FRI-only: codeword = LDE (blowup 8) of a random polynomial, folding 4, remainder max degree 31;
     # layer roots and remainder vs the oracle's FriProver (fri/benches/prover.rs:22-43 shape)
@@ -86,8 +86,21 @@ def test_config4_fri_only(ctx, oracle, log_len, d):
     want_roots, want_rem, _ = oracle.fri_build_layers(oracle.BLAKE3, ev, 4, 31, b, d)
     f, roots = ctx.fri_build_layers_default(wf.HASH_BLAKE3_256, cw, d, 4, 31, b)
     assert (roots == want_roots).all() and (f.remainder() == want_rem).all()
-    # the remainder has degree < len/blowup: the codeword really was low degree
-    assert f.remainder().size == 256 // 8 * d * (1 if log_len % 2 == 0 else 2) or True
+    if os.environ.get("WF_REPORT"):
+        import json
+        f.free()
+        f2, _ = ctx.fri_build_layers_default(wf.HASH_BLAKE3_256, cw, d, 4, 31, b)      # warm pool
+        f2.free()
+        ctx.sync()
+        import time
+        t0 = time.perf_counter()
+        f3, _ = ctx.fri_build_layers_default(wf.HASH_BLAKE3_256, cw, d, 4, 31, b)
+        ctx.sync()
+        ms = (time.perf_counter() - t0) * 1e3
+        alg = (8 * d * L * 1.25 + 32 * L) * 4 / 3     # e*L*1.25 + 32*L per layer, x4/3 over layers
+        with open(os.environ["WF_REPORT"], "a") as fh:
+            fh.write(json.dumps({"fri_only": True, "log_len": log_len, "ext_degree": d, "ms_commit_phase": round(ms, 3),
+                                 "algorithmic_GB": round(alg / 1e9, 3), "achieved_GBps": round(alg / 1e9 / (ms * 1e-3), 1)}) + "\n")
 
 
 @pytest.mark.parametrize("log_n,cols", [(23, 1), (23, 3), (24, 8)])

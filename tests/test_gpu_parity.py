@@ -189,3 +189,17 @@ def test_plain_dev_kernels(ctx, oracle):
     want = oracle.hash_rows(oracle.BLAKE3, rows)
     assert (dg.cpu().numpy().reshape(n, 32) == want).all()
     assert (nd.cpu().numpy().reshape(n, 32) == oracle.merkle_nodes(oracle.BLAKE3, want)).all()
+
+
+@pytest.mark.parametrize("h", [wf.HASH_BLAKE3_256, wf.HASH_RP64_256])
+@pytest.mark.parametrize("cols,psize", [(64, 8), (64, 16), (20, 8), (9, 4), (130, 9), (16, 1)])
+def test_partitioned_row_hash_vs_oracle(ctx, oracle, h, cols, psize):
+    # RowMatrix::commit_to_rows with PartitionOptions (row_matrix.rs:204-223): merge_many of chunk digests
+    rows = 128
+    x = oracle.rand_elems((cols, rows), cols * 7 + psize)
+    m = ctx.mat_from_host_columns(x)
+    t = ctx.commit_rows(h, m, partition_size=psize)
+    lv, nd = t.to_host()
+    want = oracle.hash_rows(h, np.ascontiguousarray(x.T), partition_size=psize)
+    assert (lv == want).all()
+    assert (nd == oracle.merkle_nodes(h, want)).all()

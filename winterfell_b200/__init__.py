@@ -52,6 +52,7 @@ _SIGS = [
     ("wf_mat_lde", C.c_int, [vp, vp, C.c_uint32, C.POINTER(vp)]),
     ("wf_mat_interpolate_with_offset", C.c_int, [vp, vp, C.c_uint64, C.POINTER(vp)]),
     ("wf_commit_rows", C.c_int, [vp, C.c_int, vp, C.POINTER(vp)]),
+    ("wf_commit_rows_partitioned", C.c_int, [vp, C.c_int, vp, C.c_uint32, C.POINTER(vp)]),
     ("wf_tree_from_leaves", C.c_int, [vp, C.c_int, vp, C.c_size_t, C.c_int, C.POINTER(vp)]),
     ("wf_tree_free", C.c_int, [vp, vp]),
     ("wf_tree_root", C.c_int, [vp, vp, u8p]),
@@ -165,9 +166,12 @@ class Context:
         self.check(self.L.wf_mat_from_device_columns(self.h, vp(dptr), ncols, nrows, C.byref(h)))
         return Mat(self, h)
 
-    def commit_rows(self, hash_id, mat):
+    def commit_rows(self, hash_id, mat, partition_size=0):
         h = vp()
-        self.check(self.L.wf_commit_rows(self.h, hash_id, mat.h, C.byref(h)))
+        if partition_size:
+            self.check(self.L.wf_commit_rows_partitioned(self.h, hash_id, mat.h, partition_size, C.byref(h)))
+        else:
+            self.check(self.L.wf_commit_rows(self.h, hash_id, mat.h, C.byref(h)))
         return Tree(self, h)
 
     def tree_from_leaves(self, hash_id, leaves):

@@ -116,12 +116,12 @@ static void split_log(u32 log_n, int W, u32* logR, u32* logC) {
     *logC = log_n - r;
 }
 
-static int get_lde_tables(wf_ctx* ctx, u32 log_n, u32 log_b, int W, LdeTables* out) {
-    auto key = std::make_pair(log_n | (W == 1 ? 0x100u : 0u), log_b);
+// tables for the first LDE pass of an n = R * C split (logR = 0: single pass over n = C points)
+static int get_lde_tables(wf_ctx* ctx, u32 log_n, u32 log_b, u32 logR, LdeTables* out) {
+    auto key = std::make_pair(log_n | (logR << 8), log_b);
     auto it = ctx->lde_tabs.find(key);
     if (it != ctx->lde_tabs.end()) { *out = it->second; return WF_OK; }
-    u32 logR, logC;
-    split_log(log_n, W, &logR, &logC);
+    const u32 logC = log_n - logR;
     size_t b = (size_t)1 << log_b, R = (size_t)1 << logR, C = (size_t)1 << logC;
     u64 g = gl_root_of_unity(log_n + log_b);
     // s_k = 7 * w_N^k (coset k of the LDE domain; natural row i = b*j + k)
@@ -241,11 +241,52 @@ static int run_ntt(wf_ctx* ctx, const SegMatrix& in, SegMatrix& out, const SegMa
 static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_n, u32 log_b) {
     u32 logR, logC;
     split_log(log_n, polys.W, &logR, &logC);
-    if (logC > NTT_MAX_LOGS) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "LDE of 2^%u rows exceeds the two-pass limit", log_n);
     u32 b = 1u << log_b;
     LdeTables tabs;
-    CKI(get_lde_tables(ctx, log_n, log_b, polys.W, &tabs));
     NttPassParams p;
+    if (logC > NTT_MAX_LOGS) {
+        // THREE passes per coset (n > 2^22), same structure as run_ntt: pass A carries the coset scaling
+        // and the four-step twiddle, the contiguous size-C step is a batch of R two-pass transforms whose
+        // last pass writes row b*(j1 + R*j) + k.
+        u32 lr = (log_n + 2) / 3, lc = log_n - lr, lr2, lc2;
+        split_log(lc, polys.W, &lr2, &lc2);
+        if (lr2 == 0 || lc2 > NTT_MAX_LOGS || lr > NTT_MAX_LOGS - (polys.W == 1 ? 1 : 0))
+            return wf_fail(ctx, WF_ERR_UNSUPPORTED, "LDE of 2^%u rows exceeds the three-pass limit", log_n);
+        CKI(get_lde_tables(ctx, log_n, log_b, lr, &tabs));
+        SegMatrix y = polys;
+        void* yp;
+        CKI(wf_dev_alloc(ctx, polys.words() * 8, &yp));
+        y.base = (u64*)yp;
+        const u64 *twA, *twB, *twC2, *twN, *twInner;
+        CKI(wf_get_twiddles(ctx, lr, &twA));
+        CKI(wf_get_twiddles(ctx, lr2, &twB));
+        CKI(wf_get_twiddles(ctx, lc2, &twC2));
+        CKI(wf_get_twiddles(ctx, log_n + log_b, &twN));
+        CKI(wf_get_twiddles(ctx, lc, &twInner));
+        for (u32 k = 0; k < b; k++) {
+            pass_defaults(p, polys, y);  // pass A
+            p.logS = (int)lr; p.logR = lr; p.logC = lc; p.sub_tw = twA;
+            p.pre_tab = tabs.pre + ((size_t)k << lr); p.pre_batch_stride = 0;
+            p.has_post = 1; p.master = twN; p.logM = log_n + log_b; p.a_mul = b; p.b_mul = 1; p.batch0 = k;
+            p.ctab = tabs.pow7;
+            CK(ntt_launch_pass(NTT_STRIDED, p, polys.nseg(), 1, ctx->st));
+            pass_defaults(p, y, y);  // pass B (in place), batch = j1
+            p.in_batch_stride = p.out_batch_stride = ((size_t)1 << lc) * polys.W;
+            p.logS = (int)lr2; p.logR = lr2; p.logC = lc2; p.sub_tw = twB;
+            p.has_post = 1; p.master = twInner; p.logM = lc; p.a_mul = 1; p.b_mul = 0;
+            CK(ntt_launch_pass(NTT_STRIDED, p, polys.nseg(), 1u << lr, ctx->st));
+            pass_defaults(p, y, out);  // pass C: row b*(j1 + R*j) + k
+            p.in_batch_stride = ((size_t)1 << lc) * polys.W;
+            p.logS = (int)lc2; p.logR = lr2; p.logC = lc2; p.sub_tw = twC2;
+            p.out_row_mul = b << lr; p.out_row_add = b;
+            p.out = out.base + (size_t)k * out.W;
+            CK(ntt_launch_pass(NTT_CONTIG, p, polys.nseg(), 1u << lr, ctx->st));
+            ctx->launches += 3;
+        }
+        wf_dev_free(ctx, yp);
+        return WF_OK;
+    }
+    CKI(get_lde_tables(ctx, log_n, log_b, logR, &tabs));
     if (logR == 0) {
         pass_defaults(p, polys, out);
         p.logS = (int)logC; p.logR = 0; p.logC = logC;
@@ -521,6 +562,19 @@ static u32 merkle_launches(size_t nleaves) {
         if (m == 0) break;
     }
     return l;
+}
+int wf_commit_rows_partitioned(wf_ctx* ctx, int hash_id, const wf_mat* m, uint32_t partition_size, wf_tree** out) {
+    if (!ctx || !m || !out) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (hash_id != WF_HASH_BLAKE3_256 && hash_id != WF_HASH_RP64_256) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "unknown hash %d", hash_id);
+    if (partition_size != 0 && partition_size < m->m.cols && (m->m.cols + partition_size - 1) / partition_size > 16)
+        return wf_fail(ctx, WF_ERR_INVALID, "more than 16 partitions");
+    wf_tree* t;
+    CKI(tree_alloc(ctx, hash_id, m->m.rows, &t));
+    CK(commit_hash_rows(hash_id, m->m, t->leaves, ctx->st, partition_size));
+    CK(commit_merkle_nodes(hash_id, t->leaves, t->nleaves, t->nodes, ctx->st));
+    ctx->launches += 1 + merkle_launches(t->nleaves);
+    *out = t;
+    return WF_OK;
 }
 int wf_commit_rows(wf_ctx* ctx, int hash_id, const wf_mat* m, wf_tree** out) {
     if (!ctx || !m || !out) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");

@@ -27,8 +27,8 @@ __device__ __forceinline__ u64 row_elem(const RowSrc& m, size_t row, u32 e) {
 
 // BLAKE3 of `cols` elements (cols*8 bytes) of one row. Handles any length: chunks of 1024 bytes
 // (128 elements) merged through a small chaining-value stack.
-__device__ void blake3_row(const RowSrc& m, size_t row, u32 out[8]) {
-    const u32 cols = m.cols;
+__device__ void blake3_row(const RowSrc& m, size_t row, u32 out[8], u32 first = 0, u32 count = 0xffffffffu) {
+    const u32 cols = min(count, m.cols - first);
     const u32 nchunks = cols <= 128 ? 1 : (cols + 127) / 128;
     u32 stack[5][8];
     int sp = 0;
@@ -42,7 +42,7 @@ __device__ void blake3_row(const RowSrc& m, size_t row, u32 out[8]) {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 u32 e = e0 + b * 8 + k;
-                u64 v = e < e1 ? row_elem(m, row, e) : 0;
+                u64 v = e < e1 ? row_elem(m, row, first + e) : 0;
                 msg[2 * k] = (u32)v;
                 msg[2 * k + 1] = (u32)(v >> 32);
             }
@@ -120,6 +120,64 @@ __global__ void __launch_bounds__(128) hash_rows_rp64_kernel(RowSrc m, size_t nr
     if (i > 0) rp64_permute(s);
 #pragma unroll
     for (int k = 0; k < 4; k++) digests[row * 4 + k] = s[4 + k];
+}
+
+// Partitioned row hashing (row_matrix.rs:204-223, PartitionOptions air/src/options.rs:405-445):
+// digest = merge_many(hash_elements(chunk_0), hash_elements(chunk_1), ...), chunks of `psize` base
+// columns. merge_many = BLAKE3 of the concatenated digests (blake/mod.rs:37) or the Rp64 sponge over
+// their elements (rp64_256/mod.rs:194).
+__global__ void __launch_bounds__(128) hash_rows_partitioned_kernel(int hash_id, RowSrc m, size_t nrows, u32 psize,
+                                                                    u64* __restrict__ digests) {
+    size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    const u32 np = (m.cols + psize - 1) / psize;  // <= 16
+    if (hash_id == WF_HASH_BLAKE3_256) {
+        u32 parts[16][8];
+        for (u32 j = 0; j < np; j++) blake3_row(m, row, parts[j], j * psize, psize);
+        // BLAKE3 of np*32 bytes (<= 512: one chunk)
+        u32 cv[8];
+        b3_iv(cv);
+        const u32 nblk = (np + 1) / 2;
+        for (u32 b = 0; b < nblk; b++) {
+            u32 msg[16];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                msg[k] = parts[2 * b][k];
+                msg[8 + k] = (2 * b + 1 < np) ? parts[2 * b + 1][k] : 0;
+            }
+            u32 bl = (2 * b + 1 < np) ? 64 : 32;
+            u32 fl = (b == 0 ? B3_CHUNK_START : 0) | (b == nblk - 1 ? (B3_CHUNK_END | B3_ROOT) : 0);
+            b3_compress(cv, msg, 0, bl, fl, b3_runtime_one());
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) digests[row * 4 + k] = (u64)cv[2 * k] | ((u64)cv[2 * k + 1] << 32);
+    } else {
+        u64 acc[12];  // outer sponge over the np*4 digest elements
+#pragma unroll
+        for (int i = 0; i < 12; i++) acc[i] = 0;
+        acc[0] = np * 4;
+        u32 fill = 0;
+        for (u32 j = 0; j < np; j++) {
+            u64 s[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = 0;
+            u32 e0 = j * psize, e1 = min(m.cols, e0 + psize);
+            s[0] = e1 - e0;
+            u32 i = 0;
+            for (u32 e = e0; e < e1; e++) {
+                s[4 + i] = gl_add(s[4 + i], row_elem(m, row, e));
+                if (++i == 8) { rp64_permute(s); i = 0; }
+            }
+            if (i > 0) rp64_permute(s);
+            for (int k = 0; k < 4; k++) {
+                acc[4 + fill] = gl_add(acc[4 + fill], s[4 + k]);
+                if (++fill == 8) { rp64_permute(acc); fill = 0; }
+            }
+        }
+        if (fill > 0) rp64_permute(acc);
+#pragma unroll
+        for (int k = 0; k < 4; k++) digests[row * 4 + k] = acc[4 + k];
+    }
 }
 
 // ---- Merkle levels ----------------------------------------------------------------------------
@@ -204,11 +262,16 @@ __global__ void __launch_bounds__(256) merkle_subtree_kernel(const u64* __restri
     if (m <= 256 && b == 0 && t < 4) nodes[t] = 0;  // nodes[0] = default digest (merkle/mod.rs:349); set by the last launch
 }
 
-cudaError_t commit_hash_rows(int hash_id, const SegMatrix& m, u64* digests, cudaStream_t st) {
+cudaError_t commit_hash_rows(int hash_id, const SegMatrix& m, u64* digests, cudaStream_t st, u32 partition_size) {
     if (m.rows == 0) return cudaSuccess;
     RowSrc src;
     src.base = m.base; src.seg_stride = m.seg_stride; src.W = m.W; src.cols = m.cols;
     src.logW = m.W == 8 ? 3 : m.W == 4 ? 2 : m.W == 2 ? 1 : 0;
+    if (partition_size != 0 && partition_size < m.cols) {
+        if ((m.cols + partition_size - 1) / partition_size > 16) return cudaErrorInvalidValue;
+        hash_rows_partitioned_kernel<<<(unsigned)((m.rows + 127) / 128), 128, 0, st>>>(hash_id, src, m.rows, partition_size, digests);
+        return cudaGetLastError();
+    }
     if (hash_id == WF_HASH_BLAKE3_256) {
         unsigned blocks = (unsigned)((m.rows + 255) / 256);
         if (m.W == 8 && m.cols == 8)

@@ -22,6 +22,7 @@ struct SegMatrix {
 static inline int seg_width_for(u32 cols) { return cols >= 8 ? 8 : cols > 2 ? 4 : cols == 2 ? 2 : 1; }
 
 // digests: rows x 4 words (32 bytes each)
-cudaError_t commit_hash_rows(int hash_id, const SegMatrix& m, u64* digests, cudaStream_t st);
+// partition_size (base columns) = 0 or >= cols: whole-row hashing; else row digest = merge_many of chunk digests
+cudaError_t commit_hash_rows(int hash_id, const SegMatrix& m, u64* digests, cudaStream_t st, u32 partition_size = 0);
 // nodes: nleaves x 4 words; nodes[0] = 0, nodes[1] = root
 cudaError_t commit_merkle_nodes(int hash_id, const u64* leaves, size_t nleaves, u64* nodes, cudaStream_t st);
