@@ -297,33 +297,39 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
         ctx->launches++;
         return WF_OK;
     }
-    // scratch Y for one coset
+    // Cosets per launch: a narrow matrix (few segments) gives fewer tiles than SMs, so all its cosets go
+    // into ONE launch (grid.z = coset) with a b-times larger scratch; wide matrices run coset by coset so
+    // that the scratch Y stays n*c words and is re-read from L2.
+    const size_t tiles = (((size_t)1 << logC) * polys.W / NTT_LANES) * polys.nseg();
+    const u32 kb = tiles < 4 * 148 ? b : 1;
     SegMatrix y = polys;
     void* yp;
-    CKI(wf_dev_alloc(ctx, polys.words() * 8, &yp));
+    CKI(wf_dev_alloc(ctx, polys.words() * 8 * kb, &yp));
     y.base = (u64*)yp;
     const u64 *twR, *twC, *twN;
     CKI(wf_get_twiddles(ctx, logR, &twR));
     CKI(wf_get_twiddles(ctx, logC, &twC));
     CKI(wf_get_twiddles(ctx, log_n + log_b, &twN));
-    for (u32 k = 0; k < b; k++) {
+    for (u32 k = 0; k < b; k += kb) {
         // pass 1: Y_k[j1][m2] = 7^m2 w_N^((b j1 + k) m2) sum_m1 a[C m1 + m2] (s_k^C)^m1 w_R^(j1 m1)
         pass_defaults(p, polys, y);
         p.logS = (int)logR; p.logR = logR; p.logC = logC;
         p.sub_tw = twR;
-        p.pre_tab = tabs.pre + ((size_t)k << logR); p.pre_batch_stride = 0;
-        // exponent (b*j1 + k)*m2 = (j1*a_mul + batch0*b_mul)*m2
+        p.pre_tab = tabs.pre + ((size_t)k << logR); p.pre_batch_stride = (size_t)1 << logR;
+        p.out_batch_stride = polys.words();
+        // exponent (b*j1 + k)*m2 = (j1*a_mul + (batch0 + z)*b_mul)*m2
         p.has_post = 1; p.master = twN; p.logM = log_n + log_b; p.a_mul = b; p.b_mul = 1; p.batch0 = k;
         p.ctab = tabs.pow7;
-        CK(ntt_launch_pass(NTT_STRIDED, p, polys.nseg(), 1, ctx->st));
+        CK(ntt_launch_pass(NTT_STRIDED, p, polys.nseg(), kb, ctx->st));
         ctx->launches++;
         // pass 2: X_k[j1 + R j2] = sum_m2 Y_k[j1][m2] w_C^(j2 m2)  -> row b*(j1 + R j2) + k
         pass_defaults(p, y, out);
         p.logS = (int)logC; p.logR = logR; p.logC = logC;
         p.sub_tw = twC;
-        p.out_row_mul = b; p.out_row_add = 0;
-        p.out = out.base + (size_t)k * out.W;  // + k rows
-        CK(ntt_launch_pass(NTT_CONTIG, p, polys.nseg(), 1, ctx->st));
+        p.in_batch_stride = polys.words();
+        p.out_row_mul = b; p.out_row_add = 1;
+        p.out = out.base + (size_t)k * out.W;  // + k rows; the launch's coset z adds z rows
+        CK(ntt_launch_pass(NTT_CONTIG, p, polys.nseg(), kb, ctx->st));
         ctx->launches++;
     }
     wf_dev_free(ctx, yp);

@@ -141,7 +141,9 @@ __device__ __forceinline__ u64 gl_reduce128(u64 lo, u64 hi) {
         "}"
         : "=l"(r)
         : "l"(lo), "l"(hi));
-    if (r >= GL_P) r -= GL_P;
+    // r is in [0, 2^64); r >= p has probability 2^-32 for uniform r: a predicated branch that is
+    // (almost) never taken is cheaper than the compare/select pair of a branch-free form
+    if (__builtin_expect(r >= GL_P, 0)) r -= GL_P;
     return r;
 }
 __device__ __forceinline__ u64 gl_mul(u64 a, u64 b) {

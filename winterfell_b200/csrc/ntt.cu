@@ -9,7 +9,6 @@ __device__ __forceinline__ void dif_round(u64* s, const u64* stw, int logS, int 
     const int logspan = logS - stage - R;
     const u32 span = 1u << logspan;
     const u32 nbf = (1u << logS) >> R;
-    const u32 half = (1u << logS) >> 1;
     const int lane = tid & (NTT_LANES - 1);
     for (u32 bf = tid >> 3; bf < nbf; bf += NTT_THREADS / NTT_LANES) {
         u32 lo = bf & (span - 1);
@@ -22,8 +21,8 @@ __device__ __forceinline__ void dif_round(u64* s, const u64* stw, int logS, int 
 #pragma unroll
             for (int qo = 1; qo < (1 << R); qo++) {
                 // position qo holds frequency bitrev(qo) of the mini-DFT: twiddle w_G^(lo * freq)
-                u32 e = (lo * brev(qo, R)) << stage;
-                x[qo] = gl_mul(x[qo], tw_lookup(stw, e, half));
+                u32 e = (lo * brev(qo, R)) << stage;   // < S: the table holds w_S^e for all e in [0, S)
+                x[qo] = gl_mul(x[qo], stw[e]);
             }
         }
 #pragma unroll
@@ -106,8 +105,8 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_pass_kernel(c
     const int logW = 31 - __clz(W);
     const int T = NTT_LANES >> logW;
     u64* s = smem;
-    u64* stw = s + (size_t)S * NTT_LANES;
-    u64* ctw = stw + (S >> 1 ? S >> 1 : 1);
+    u64* stw = s + (size_t)S * NTT_LANES;   // S entries: w_S^e, e < S (second half = negated first half)
+    u64* ctw = stw + S;
     u64* mbar = ctw + (p.has_post ? (size_t)S * T : 0);
 
     const u32 tile = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
@@ -165,6 +164,37 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_pass_kernel(c
     const u64* in = p.in + (size_t)g * p.in_seg_stride + (size_t)b * p.in_batch_stride;
     const u64* pre = p.pre_tab ? p.pre_tab + (size_t)b * p.pre_batch_stride : nullptr;
     constexpr u32 ROWS_PER_IT = NTT_THREADS / NTT_LANES;
+    if (MODE == NTT_CONTIG && W < NTT_LANES) {
+        // narrow segments: lane = (tile column t, segment column q) and every tile column is its own
+        // contiguous run of C*W words, so map threads along the run (index-fastest) instead of along the
+        // lanes: a warp then reads 256 contiguous bytes instead of 8-byte pieces of 8 different rows
+        const u32 run = S << logW;  // words per tile column
+        for (u32 e0 = tid; e0 < run * (u32)T; e0 += NTT_THREADS * NTT_LD_BATCH) {
+            u64 v[NTT_LD_BATCH], f[NTT_LD_BATCH];
+#pragma unroll
+            for (int k = 0; k < NTT_LD_BATCH; k++) {
+                u32 e = e0 + k * NTT_THREADS;
+                v[k] = 0;
+                f[k] = 1;
+                if (e < run * (u32)T) {
+                    u32 tt = e / run, r = e % run, i = r >> logW;
+                    u32 c = tile * T + tt;
+                    if (c < R) {
+                        v[k] = in[(((size_t)c << p.logC) << logW) + r];
+                        if (pre) f[k] = pre[i];
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NTT_LD_BATCH; k++) {
+                u32 e = e0 + k * NTT_THREADS;
+                if (e < run * (u32)T) {
+                    u32 tt = e / run, r = e % run, i = r >> logW, qq = r & (W - 1);
+                    s[(i << 3) + (tt << logW) + qq] = pre ? gl_mul(v[k], f[k]) : v[k];
+                }
+            }
+        }
+    } else
     for (u32 i0 = tid >> 3; i0 < S; i0 += ROWS_PER_IT * NTT_LD_BATCH) {
         u64 v[NTT_LD_BATCH], f[NTT_LD_BATCH];
 #pragma unroll
@@ -187,6 +217,8 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_pass_kernel(c
         }
     }
     if (use_tma) tma_bulk_wait(mbar);
+    __syncthreads();
+    for (u32 e = tid; e < (S >> 1); e += NTT_THREADS) stw[(S >> 1) + e] = gl_neg(stw[e]);  // w^(e + S/2) = -w^e
     __syncthreads();
 
     tile_dft(s, stw, logS, tid);
@@ -213,7 +245,7 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_pass_kernel(c
 size_t ntt_pass_smem_bytes(const NttPassParams& p) {
     size_t S = (size_t)1 << p.logS;
     size_t T = NTT_LANES / p.W;
-    size_t words = S * NTT_LANES + (S / 2 ? S / 2 : 1) + (p.has_post ? S * T : 0) + 2;
+    size_t words = S * NTT_LANES + S + (p.has_post ? S * T : 0) + 2;
     return words * 8;
 }
 

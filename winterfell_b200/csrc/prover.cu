@@ -216,7 +216,22 @@ __global__ void __launch_bounds__(256) deep_eval_kernel(DeepParams p, GlExt<D> z
         den[2 * r] = ext_from_base<D>(1);
         den[2 * r + 1] = ext_from_base<D>(1);
         if (row >= N) continue;
-        for (u32 j = 0; j < p.c; j++) S[r] = ext_add(S[r], ext_mul_base(ld_ext<D>(p.tcc + (size_t)j * D), seg_at(p.trace, row, j)));
+        if (p.trace.W == 8) {
+            // one 64-byte segment row = four 16-byte loads
+            for (u32 g = 0; g * 8 < p.c; g++) {
+                const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(p.trace.base + (size_t)g * p.trace.seg_stride + row * 8);
+                u64 v[8];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { ulonglong2 t2 = __ldg(rp + k); v[2 * k] = t2.x; v[2 * k + 1] = t2.y; }
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    u32 j = g * 8 + q;
+                    if (j < p.c) S[r] = ext_add(S[r], ext_mul_base(ld_ext<D>(p.tcc + (size_t)j * D), v[q]));
+                }
+            }
+        } else {
+            for (u32 j = 0; j < p.c; j++) S[r] = ext_add(S[r], ext_mul_base(ld_ext<D>(p.tcc + (size_t)j * D), seg_at(p.trace, row, j)));
+        }
         for (u32 j = 0; j < p.kc; j++) {
             GlExt<D> hv;
 #pragma unroll
