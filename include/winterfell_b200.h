@@ -151,6 +151,21 @@ int wf_fri_free(wf_ctx* ctx, wf_fri* f);
 int wf_prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, uint32_t k, uint32_t log_n,
                  const uint64_t* results, const uint32_t* opts, uint8_t* proof, size_t* proof_len);
 
+/* Generic single-segment AIR: Air::evaluate_transition (air/src/air/mod.rs:210) described as a
+ * straight-line program, so that user AIRs beyond the built-in family run on the device evaluator.
+ * air_desc (u64 words):
+ *   [width, nT, {base_degree, ncycles, cycle...} x nT        TransitionConstraintDegree (transition/degree.rs)
+ *    nP, {len, values...} x nP                               get_periodic_column_values (air/mod.rs:300)
+ *    nC, constants...,  num_regs,  nI, {op, dst, a, b} x nI   registers: [0,w) current row, [w,2w) next row,
+ *                                                             [2w,2w+nP) periodic values, then temporaries;
+ *                                                             op 0 ADD, 1 SUB, 2 MUL (dst = r[a] op r[b]),
+ *                                                             3 CONST (dst = constants[a]), 4 OUT (result[dst] = r[a])
+ *    nA, {column, first_step, stride, value} x nA            Assertion::single (stride 0) / ::periodic
+ *    nPub, public input elements...,  num_transition_exemptions]
+ * Not supported yet: auxiliary trace segments, sequence assertions. */
+int wf_prove_air(wf_ctx* ctx, const uint64_t* air_desc, size_t air_desc_len, const uint64_t* const* trace_cols, int mont,
+                 uint32_t log_n, const uint32_t* opts, uint8_t* proof, size_t* proof_len);
+
 /* same, trace already on the device: column-major [2k][2^log_n], canonical words */
 int wf_prove_fib_dev(wf_ctx* ctx, const uint64_t* d_trace, uint32_t k, uint32_t log_n, const uint64_t* results,
                      const uint32_t* opts, uint8_t* proof, size_t* proof_len);

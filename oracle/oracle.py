@@ -353,6 +353,26 @@ def verify_fib(proof: bytes, k, results, hash_id=BLAKE3):
     return lib().wfo_verify_fib(pp, C.c_size_t(len(proof)), C.c_size_t(k), rp, C.c_int(hash_id))
 
 
+def prove_air(desc, trace, opts):
+    d_, dp = _u64(desc)
+    t_, tp = _u64(trace)
+    cap = 1 << 23
+    out = np.zeros(cap, dtype=np.uint8)
+    L = lib()
+    L.wfo_prove_air.restype = C.c_long
+    ln = L.wfo_prove_air(dp, C.c_size_t(d_.size), tp, C.c_size_t(t_.shape[1]), opts.ctypes.data_as(C.POINTER(C.c_uint32)),
+                         out.ctypes.data_as(u8p), C.c_size_t(cap))
+    if ln < 0:
+        raise RuntimeError(f"prove_air failed ({ln})")
+    return out[:ln].tobytes()
+
+
+def verify_air(desc, proof: bytes, hash_id=BLAKE3):
+    d_, dp = _u64(desc)
+    p_, pp = _u8(np.frombuffer(proof, dtype=np.uint8))
+    return lib().wfo_verify_air(dp, C.c_size_t(d_.size), pp, C.c_size_t(len(proof)), C.c_int(hash_id))
+
+
 def rand_elems(shape, seed):
     """Uniform field elements in [0, p) from a seeded PRNG (rejection sampling)."""
     rng = np.random.default_rng(seed)

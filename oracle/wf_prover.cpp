@@ -55,35 +55,148 @@ struct Writer {
     void elems(const Field& F, const EE* e, size_t n) { for (size_t i = 0; i < n; i++) for (int k = 0; k < F.d; k++) u64_(e[i].v[k]); }
 };
 
-// ---- AIR: FibSmall x k ---------------------------------------------------------------------------
-struct FibAir {
-    size_t k, n;
-    std::vector<u64> results;
+// ---- AIR description -------------------------------------------------------------------------------
+// A generic single-segment AIR (air/src/air/mod.rs:174 `Air`): transition constraints as a small
+// straight-line program over the evaluation frame, so that the same description drives the oracle,
+// the device evaluator and the verifier. FibSmall x k is one instance (fib_air()).
+struct Assertion { size_t column, first_step, stride; u64 value; };  // stride 0: single; else periodic single-value
+struct Instr { u32 op, dst, a, b; };  // ADD/SUB/MUL dst = r[a] op r[b]; CONST dst = consts[a]; OUT result[dst] = r[a]
+enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_CONST = 3, OP_OUT = 4 };
+struct Air {
+    size_t w = 0, n = 0;
     Opts o;
-    size_t width() const { return 2 * k; }
-    size_t num_transition() const { return 2 * k; }
-    size_t num_assertions() const { return 3 * k; }
-    size_t ce_blowup() const { return 2; }      // degree-1 constraints: transition/degree.rs min_blowup_factor
-    size_t num_comp_cols() const { return 1; }  // air/src/air/context.rs:265-285
+    std::vector<u64> pub_inputs;                                 // PublicInputs::to_elements
+    std::vector<std::pair<u32, std::vector<u32>>> degrees;       // TransitionConstraintDegree: base, cycles
+    std::vector<std::vector<u64>> periodic;                      // get_periodic_column_values
+    std::vector<u64> consts;
+    std::vector<Instr> prog;
+    u32 num_regs = 0;                                            // r[0..w) current, r[w..2w) next, r[2w..2w+np) periodic, temps
+    std::vector<Assertion> asserts;
+    u32 exemptions = 1;                                          // AirContext::num_transition_exemptions
+    size_t width() const { return w; }
+    size_t num_transition() const { return degrees.size(); }
+    size_t num_assertions() const { return asserts.size(); }
     size_t lde_size() const { return n * o.blowup; }
-    // examples/src/fibonacci/fib_small/air.rs:43-60 per pair
-    template <class T, class Sub, class Add>
-    void eval_transition(const T* cur, const T* nxt, T* res, Sub sub, Add add) const {
-        for (size_t j = 0; j < k; j++) {
-            res[2 * j] = sub(nxt[2 * j], add(cur[2 * j], cur[2 * j + 1]));
-            res[2 * j + 1] = sub(nxt[2 * j + 1], add(cur[2 * j + 1], nxt[2 * j]));
+    size_t ce_blowup() const {  // air/src/air/context.rs:87-100 + transition/degree.rs min_blowup_factor
+        size_t r = 0;
+        for (auto& dg : degrees) {
+            size_t bound = dg.first + dg.second.size() - 1, p2 = 1;
+            while (p2 < bound) p2 <<= 1;
+            r = std::max(r, std::max(p2, (size_t)2));
+        }
+        return r;
+    }
+    size_t num_comp_cols() const {  // context.rs:265-285
+        size_t hi = 0;
+        for (auto& dg : degrees) {
+            size_t e = dg.first * (n - 1);  // degree.rs get_evaluation_degree
+            for (u32 cyc : dg.second) e += (n / cyc) * (cyc - 1);
+            hi = std::max(hi, e);
+        }
+        size_t div = n - exemptions;
+        return std::max((hi - div + n - 1) / n, (size_t)1);
+    }
+    // Air::evaluate_transition through the program, over any field type T
+    template <class T, class Sub, class Add, class Mul, class FromBase>
+    void eval_transition(const T* cur, const T* nxt, const T* per, T* res, Sub sub, Add add, Mul mul, FromBase fb) const {
+        std::vector<T> r(num_regs);
+        for (size_t i = 0; i < w; i++) { r[i] = cur[i]; r[w + i] = nxt[i]; }
+        for (size_t i = 0; i < periodic.size(); i++) r[2 * w + i] = per[i];
+        for (const Instr& in : prog) {
+            switch (in.op) {
+                case OP_ADD: r[in.dst] = add(r[in.a], r[in.b]); break;
+                case OP_SUB: r[in.dst] = sub(r[in.a], r[in.b]); break;
+                case OP_MUL: r[in.dst] = mul(r[in.a], r[in.b]); break;
+                case OP_CONST: r[in.dst] = fb(consts[in.a]); break;
+                case OP_OUT: res[in.dst] = r[in.a]; break;
+            }
         }
     }
     // assertions in the reference's sorted order (stride, first_step, column):
     // air/src/air/assertions/mod.rs:301-315, boundary/mod.rs prepare_assertions
-    struct Assertion { size_t column, step; u64 value; };
     std::vector<Assertion> assertions() const {
-        std::vector<Assertion> a;
-        for (size_t c = 0; c < 2 * k; c++) a.push_back({c, 0, (u64)(c / 2 + 1)});
-        for (size_t j = 0; j < k; j++) a.push_back({2 * j + 1, n - 1, results[j]});
+        std::vector<Assertion> a = asserts;
+        std::stable_sort(a.begin(), a.end(), [](const Assertion& x, const Assertion& y) {
+            if (x.stride != y.stride) return x.stride < y.stride;
+            if (x.first_step != y.first_step) return x.first_step < y.first_step;
+            return x.column < y.column;
+        });
         return a;
     }
+    // periodic column polynomials (air/src/air/mod.rs:325-360): interpolation over the cycle
+    std::vector<std::vector<u64>> periodic_polys() const {
+        std::vector<std::vector<u64>> r;
+        for (auto& col : periodic) {
+            std::vector<u64> p = col;
+            auto itw = get_inv_twiddles(p.size());
+            interpolate_poly(p.data(), p.size(), 1, itw.data());
+            r.push_back(p);
+        }
+        return r;
+    }
 };
+typedef Air FibAir;  // the FibSmall x k entry points build an Air through fib_air()
+
+// examples/src/fibonacci/fib_small/air.rs:16-69, k copies side by side: pair j starts at (j+1, j+1)
+static Air fib_air(size_t k, size_t n, const u64* results, const Opts& o) {
+    Air a;
+    a.w = 2 * k; a.n = n; a.o = o;
+    a.pub_inputs.assign(results, results + k);
+    const u32 w = (u32)a.w;
+    u32 t = 2 * w;  // first temp register
+    for (u32 j = 0; j < k; j++) {
+        a.degrees.push_back({1, {}});
+        a.degrees.push_back({1, {}});
+        // result[2j] = next[2j] - (cur[2j] + cur[2j+1]); result[2j+1] = next[2j+1] - (cur[2j+1] + next[2j])
+        a.prog.push_back({OP_ADD, t, 2 * j, 2 * j + 1});
+        a.prog.push_back({OP_SUB, t + 1, w + 2 * j, t});
+        a.prog.push_back({OP_OUT, 2 * j, t + 1, 0});
+        a.prog.push_back({OP_ADD, t, 2 * j + 1, w + 2 * j});
+        a.prog.push_back({OP_SUB, t + 1, w + 2 * j + 1, t});
+        a.prog.push_back({OP_OUT, 2 * j + 1, t + 1, 0});
+        a.asserts.push_back({2 * j, 0, 0, (u64)(j + 1)});
+        a.asserts.push_back({2 * j + 1, 0, 0, (u64)(j + 1)});
+        a.asserts.push_back({2 * j + 1, n - 1, 0, results ? results[j] : 0});
+    }
+    a.num_regs = t + 2;
+    return a;
+}
+
+// flat u64 description shared with the product's C ABI (include/winterfell_b200.h wf_prove_air):
+// [w, nT, {base, ncyc, cyc...}*, nP, {len, values...}*, nC, consts..., num_regs, nI, {op,dst,a,b}*,
+//  nA, {column, first_step, stride, value}*, nPub, pub..., exemptions]
+static bool parse_air(const u64* d, size_t len, Air& a) {
+    size_t p = 0;
+    auto rd = [&](u64& v) { if (p >= len) return false; v = d[p++]; return true; };
+    u64 v, cnt;
+    if (!rd(v)) return false;
+    a.w = v;
+    if (!rd(cnt)) return false;
+    for (u64 i = 0; i < cnt; i++) {
+        u64 base, nc; if (!rd(base) || !rd(nc)) return false;
+        std::vector<u32> cyc; for (u64 j = 0; j < nc; j++) { if (!rd(v)) return false; cyc.push_back((u32)v); }
+        a.degrees.push_back({(u32)base, cyc});
+    }
+    if (!rd(cnt)) return false;
+    for (u64 i = 0; i < cnt; i++) {
+        u64 ln; if (!rd(ln)) return false;
+        std::vector<u64> col; for (u64 j = 0; j < ln; j++) { if (!rd(v)) return false; col.push_back(v); }
+        a.periodic.push_back(col);
+    }
+    if (!rd(cnt)) return false;
+    for (u64 i = 0; i < cnt; i++) { if (!rd(v)) return false; a.consts.push_back(v); }
+    if (!rd(v)) return false;
+    a.num_regs = (u32)v;
+    if (!rd(cnt)) return false;
+    for (u64 i = 0; i < cnt; i++) { u64 op, ds, x, y; if (!rd(op) || !rd(ds) || !rd(x) || !rd(y)) return false; a.prog.push_back({(u32)op, (u32)ds, (u32)x, (u32)y}); }
+    if (!rd(cnt)) return false;
+    for (u64 i = 0; i < cnt; i++) { u64 c, fs, st, val; if (!rd(c) || !rd(fs) || !rd(st) || !rd(val)) return false; a.asserts.push_back({(size_t)c, (size_t)fs, (size_t)st, val}); }
+    if (!rd(cnt)) return false;
+    for (u64 i = 0; i < cnt; i++) { if (!rd(v)) return false; a.pub_inputs.push_back(v); }
+    if (!rd(v)) return false;
+    a.exemptions = (u32)v;
+    return p == len;
+}
 
 static std::vector<u64> context_elements(const FibAir& air) {
     // air/src/proof/context.rs:119-136; air/src/air/trace_info.rs:209-238; air/src/options.rs:294-305
@@ -140,21 +253,35 @@ static EE horner_ext(const Field& F, const EE* p, size_t n, const EE& x) {
     return acc;
 }
 
-// ---- constraint evaluation at one point (shared by prover rows and the verifier's OOD check) -------
-struct BoundaryGroup { u64 divisor_offset; std::vector<size_t> cols; std::vector<u64> values; std::vector<EE> cc; };
-static std::vector<BoundaryGroup> boundary_groups(const FibAir& air, const std::vector<EE>& bcoef) {
-    // air/src/air/boundary/mod.rs:154 group_constraints: BTreeMap keyed by (stride, first_step);
-    // single assertions: divisor (x - g^step) (divisor.rs from_assertion)
+// ---- boundary constraint groups (air/src/air/boundary/mod.rs:154 group_constraints) -----------------
+// BTreeMap keyed by (stride, first_step); divisor x^a - b with a = number of asserted steps and
+// b = g^(a * first_step) (air/src/air/divisor.rs:44-56 from_assertion); single-value constraints only.
+struct BoundaryGroup { u64 a, b; std::vector<size_t> cols; std::vector<u64> values; std::vector<EE> cc; };
+static std::vector<BoundaryGroup> boundary_groups(const Air& air, const std::vector<EE>& bcoef) {
     u64 g = root_of_unity((u32)__builtin_ctzll(air.n));
-    std::vector<BoundaryGroup> gs(2);
-    gs[0].divisor_offset = 1;
-    gs[1].divisor_offset = f_exp(g, air.n - 1);
+    std::map<std::pair<size_t, size_t>, BoundaryGroup> m;
     auto as = air.assertions();
     for (size_t i = 0; i < as.size(); i++) {
-        BoundaryGroup& G = as[i].step == 0 ? gs[0] : gs[1];
-        G.cols.push_back(as[i].column); G.values.push_back(as[i].value); G.cc.push_back(bcoef[i]);
+        auto key = std::make_pair(as[i].stride, as[i].first_step);
+        auto it = m.find(key);
+        if (it == m.end()) {
+            BoundaryGroup G;
+            G.a = as[i].stride == 0 ? 1 : air.n / as[i].stride;  // assertions/mod.rs:284-295 get_num_steps
+            G.b = as[i].first_step == 0 ? 1 : f_exp(g, G.a * as[i].first_step);
+            it = m.insert({key, G}).first;
+        }
+        it->second.cols.push_back(as[i].column); it->second.values.push_back(as[i].value); it->second.cc.push_back(bcoef[i]);
     }
-    return gs;
+    std::vector<BoundaryGroup> r;
+    for (auto& kv : m) r.push_back(kv.second);
+    return r;
+}
+// transition divisor exemption points g^(n-1), ..., g^(n-k) (divisor.rs:31-41 from_transition)
+static std::vector<u64> exemption_points(const Air& air) {
+    u64 g = root_of_unity((u32)__builtin_ctzll(air.n));
+    std::vector<u64> r;
+    for (size_t st = air.n - air.exemptions; st < air.n; st++) r.push_back(f_exp(g, st));
+    return r;
 }
 
 // ---- the proof -----------------------------------------------------------------------------------
@@ -191,7 +318,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
     const size_t n = air.n, N = air.lde_size(), c = air.width(), b = o.blowup;
     // channel (prover/src/channel.rs:57-82)
     std::vector<u64> seed = context_elements(air);
-    for (u64 r : air.results) seed.push_back(r);
+    for (u64 r : air.pub_inputs) seed.push_back(r);
     Coin coin(h, seed);
     Writer commitments;
 
@@ -216,32 +343,48 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
     const size_t lde_shift = (size_t)__builtin_ctzll(b / air.ce_blowup());
     const u64 g_ce = root_of_unity((u32)__builtin_ctzll(ce));
     const u64 g_tr = root_of_unity((u32)__builtin_ctzll(n));
-    const u64 exempt = f_exp(g_tr, n - 1);  // divisor.rs from_transition: last step exempted
+    const std::vector<u64> exempt = exemption_points(air);
+    // periodic value table (evaluator/periodic_table.rs:24-76): column j evaluated over the coset
+    // offset^(n/L) <w_(L*ceb)>, row i of the CE domain reads entry i mod (L*ceb)
+    std::vector<std::vector<u64>> ptab;
+    {
+        auto pp = air.periodic_polys();
+        for (auto& poly : pp) {
+            size_t L = poly.size();
+            std::vector<u64> ev(L * air.ce_blowup());
+            auto tw = get_twiddles(L);
+            evaluate_poly_with_offset(poly.data(), L, 1, tw.data(), f_exp(GENERATOR, n / L), air.ce_blowup(), ev.data());
+            ptab.push_back(ev);
+        }
+    }
     std::vector<EE> comp(ce);
 #pragma omp parallel
     {
-        std::vector<u64> tev(air.num_transition());
+        std::vector<u64> tev(air.num_transition()), per(ptab.size());
 #pragma omp for schedule(static)
         for (size_t i = 0; i < ce; i++) {
             size_t ls = i << lde_shift;
             const u64* cur = &lde[ls * c];
             const u64* nxt = &lde[((ls + b) % N) * c];  // trace_lde/default/mod.rs:169-180
-            air.eval_transition(cur, nxt, tev.data(), f_sub, f_add);
+            for (size_t j = 0; j < ptab.size(); j++) per[j] = ptab[j][i % ptab[j].size()];
+            std::fill(tev.begin(), tev.end(), 0);
+            air.eval_transition(cur, nxt, per.data(), tev.data(), f_sub, f_add, f_mul, [](u64 v) { return v; });
             EE t = F.zero();
             for (size_t j = 0; j < tev.size(); j++) t = F.add(t, F.mul_base(tcoef[j], tev[j]));
             u64 x = f_mul(f_exp(g_ce, i), GENERATOR);                  // domain.rs get_ce_x_at
             u64 zt = f_inv(f_sub(f_exp(x, n), 1));                     // 1 / (x^n - 1)
-            EE acc = F.mul_base(t, f_mul(zt, f_sub(x, exempt)));       // evaluation_table.rs:343-366
+            u64 ex = 1;
+            for (u64 e : exempt) ex = f_mul(ex, f_sub(x, e));          // divisor.rs evaluate_exemptions_at
+            EE acc = F.mul_base(t, f_mul(zt, ex));                     // evaluation_table.rs:343-366
             for (auto& G : groups) {
                 EE bsum = F.zero();
                 for (size_t q = 0; q < G.cols.size(); q++)             // evaluator/boundary.rs SingleValueConstraint
                     bsum = F.add(bsum, F.mul_base(G.cc[q], f_sub(cur[G.cols[q]], G.values[q])));
-                acc = F.add(acc, F.mul_base(bsum, f_inv(f_sub(x, G.divisor_offset))));  // :329-340
+                acc = F.add(acc, F.mul_base(bsum, f_inv(f_sub(f_exp(x, G.a), G.b))));  // :329-340
             }
             comp[i] = acc;
         }
     }
-    tm.mark("constraint_eval");
     // 3. composition polynomial + commitment (composition_poly.rs:58-78, commitment/default.rs:109-150)
     std::vector<u64> cp(ce * d);
     for (size_t i = 0; i < ce; i++) for (int k = 0; k < d; k++) cp[i * d + k] = comp[i].v[k];
@@ -515,6 +658,10 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
     if (!r.ok) return V_MALFORMED;
     air.o = o;
     air.n = (size_t)1 << logn;
+    if (air.asserts.empty() && air.w > 0) {  // FibSmall x k entry point: assertions reference step n - 1
+        std::vector<u64> res = air.pub_inputs;
+        air = fib_air(air.w / 2, air.n, res.data(), o);
+    }
     if (mw != air.width() || ncons != air.num_assertions() + air.num_transition() || o.ext < 1 || o.ext > 3) return V_CONTEXT;
     const int h = o.hash_id;
     Field F{(int)o.ext};
@@ -558,7 +705,7 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
 
     // transcript (lib.rs:149-260)
     std::vector<u64> seed = context_elements(air);
-    for (u64 x : air.results) seed.push_back(x);
+    for (u64 x : air.pub_inputs) seed.push_back(x);
     Coin coin(h, seed);
     coin.reseed(trace_root);
     std::vector<EE> ccoef = coin.draw_coeffs(F, (int)o.batch_c, air.num_transition() + air.num_assertions());
@@ -568,21 +715,25 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
     {
         std::vector<EE> tcoef(ccoef.begin(), ccoef.begin() + air.num_transition());
         std::vector<EE> bcoef(ccoef.begin() + air.num_transition(), ccoef.end());
-        std::vector<EE> tev(air.num_transition());
-        air.eval_transition(t_cur.data(), t_nxt.data(), tev.data(),
-                            [&](const EE& a, const EE& b) { return F.sub(a, b); }, [&](const EE& a, const EE& b) { return F.add(a, b); });
+        std::vector<EE> tev(air.num_transition(), F.zero());
+        // periodic values at z: poly_j(z^(n/L_j)) (verifier/src/evaluator.rs:27-35)
+        std::vector<EE> per;
+        for (auto& poly : air.periodic_polys()) per.push_back(horner_base(F, poly.data(), poly.size(), F.exp(z, n / poly.size())));
+        air.eval_transition(t_cur.data(), t_nxt.data(), per.data(), tev.data(),
+                            [&](const EE& a, const EE& b) { return F.sub(a, b); }, [&](const EE& a, const EE& b) { return F.add(a, b); },
+                            [&](const EE& a, const EE& b) { return F.mul(a, b); }, [&](u64 v) { return F.from_base(v); });
         EE t = F.zero();
         for (size_t j = 0; j < tev.size(); j++) t = F.add(t, F.mul(tcoef[j], tev[j]));
-        u64 g_tr = root_of_unity((u32)__builtin_ctzll(n));
-        // transition divisor (x^n - 1) / (x - g^(n-1)) at z (transition/mod.rs:153-174, divisor.rs:79-100)
+        // transition divisor (x^n - 1) / prod (x - exemption) at z (transition/mod.rs:153-174, divisor.rs:79-100)
         EE num = F.sub(F.exp(z, n), F.one());
-        EE den = F.sub(z, F.from_base(f_exp(g_tr, n - 1)));
+        EE den = F.one();
+        for (u64 e : exemption_points(air)) den = F.mul(den, F.sub(z, F.from_base(e)));
         EE res = F.mul(t, F.mul(den, F.inv(num)));
         for (auto& G : boundary_groups(air, bcoef)) {
             EE bs = F.zero();
             for (size_t q = 0; q < G.cols.size(); q++)
                 bs = F.add(bs, F.mul(F.sub(t_cur[G.cols[q]], F.from_base(G.values[q])), G.cc[q]));
-            res = F.add(res, F.mul(bs, F.inv(F.sub(z, F.from_base(G.divisor_offset)))));
+            res = F.add(res, F.mul(bs, F.inv(F.sub(F.exp(z, G.a), F.from_base(G.b)))));
         }
         EE res2 = F.zero();
         for (size_t i = 0; i < kc; i++) res2 = F.add(res2, F.mul(F.exp(z, i * n), q_cur[i]));
@@ -722,8 +873,7 @@ static Opts make_opts(const uint32_t* v) {
 // trace: [2k][n] canonical words; results: k words. Returns proof length (bytes written to out), or -1.
 long wfo_prove_fib(const uint64_t* trace, size_t k, size_t n, const uint64_t* results, const uint32_t* opts, uint8_t* out,
                    size_t cap) {
-    FibAir air;
-    air.k = k; air.n = n; air.results.assign(results, results + k); air.o = make_opts(opts);
+    Air air = fib_air(k, n, results, make_opts(opts));
     std::vector<u8> p = prove_fib(air, trace);
     if (p.size() > cap) return -1;
     memcpy(out, p.data(), p.size());
@@ -731,8 +881,28 @@ long wfo_prove_fib(const uint64_t* trace, size_t k, size_t n, const uint64_t* re
 }
 // 0 = accepted; otherwise the failed check (V_* above)
 int wfo_verify_fib(const uint8_t* proof, size_t len, size_t k, const uint64_t* results, int hash_id) {
-    FibAir air;
-    air.k = k; air.n = 0; air.results.assign(results, results + k);
+    Opts o;
+    memset(&o, 0, sizeof(o));
+    o.hash_id = hash_id;
+    Air air = fib_air(k, 0, results, o);
+    air.asserts.clear();  // rebuilt once n is known from the proof
+    int r = verify_fib(proof, len, air);
+    return r;
+}
+// generic AIR (flat description, see parse_air): trace [w][n]
+long wfo_prove_air(const uint64_t* desc, size_t desc_len, const uint64_t* trace, size_t n, const uint32_t* opts, uint8_t* out,
+                   size_t cap) {
+    Air air;
+    if (!parse_air(desc, desc_len, air)) return -2;
+    air.n = n; air.o = make_opts(opts);
+    std::vector<u8> p = prove_fib(air, trace);
+    if (p.size() > cap) return -1;
+    memcpy(out, p.data(), p.size());
+    return (long)p.size();
+}
+int wfo_verify_air(const uint64_t* desc, size_t desc_len, const uint8_t* proof, size_t len, int hash_id) {
+    Air air;
+    if (!parse_air(desc, desc_len, air)) return -2;
     memset(&air.o, 0, sizeof(air.o));
     air.o.hash_id = hash_id;
     return verify_fib(proof, len, air);

@@ -1,0 +1,142 @@
+"""AIR descriptions for the generic prover (flat u64 format shared by oracle/wf_prover.cpp parse_air and
+the product's wf_prove_air) and matching trace builders. Each AIR restates a reference example over
+the f64 field, or exercises a feature (periodic columns, periodic assertions, degree > 1)."""
+import numpy as np
+
+P = 0xFFFFFFFF00000001
+ADD, SUB, MUL, CONST, OUT = 0, 1, 2, 3, 4
+
+
+class AirBuilder:
+    def __init__(self, width):
+        self.w = width
+        self.degrees, self.periodic, self.consts, self.prog, self.asserts, self.pub = [], [], [], [], [], []
+        self.exemptions = 1
+        self.next_reg = None
+
+    def cur(self, c): return c
+    def nxt(self, c): return self.w + c
+    def per(self, j): return 2 * self.w + j
+
+    def _tmp(self):
+        if self.next_reg is None:
+            self.next_reg = 2 * self.w + len(self.periodic)
+        r = self.next_reg
+        self.next_reg += 1
+        return r
+
+    def op(self, code, a, b):
+        d = self._tmp()
+        self.prog.append((code, d, a, b))
+        return d
+
+    def add(self, a, b): return self.op(ADD, a, b)
+    def sub(self, a, b): return self.op(SUB, a, b)
+    def mul(self, a, b): return self.op(MUL, a, b)
+
+    def const(self, v):
+        self.consts.append(v % P)
+        d = self._tmp()
+        self.prog.append((CONST, d, len(self.consts) - 1, 0))
+        return d
+
+    def constraint(self, reg, base_degree, cycles=()):
+        self.prog.append((OUT, len(self.degrees), reg, 0))
+        self.degrees.append((base_degree, list(cycles)))
+
+    def assert_single(self, column, step, value): self.asserts.append((column, step, 0, int(value) % P))
+    def assert_periodic(self, column, first_step, stride, value): self.asserts.append((column, first_step, stride, int(value) % P))
+
+    def build(self):
+        if self.next_reg is None:
+            self.next_reg = 2 * self.w + len(self.periodic)
+        d = [self.w, len(self.degrees)]
+        for base, cyc in self.degrees:
+            d += [base, len(cyc)] + list(cyc)
+        d.append(len(self.periodic))
+        for col in self.periodic:
+            d += [len(col)] + [int(v) % P for v in col]
+        d += [len(self.consts)] + self.consts
+        d += [self.next_reg, len(self.prog)]
+        for ins in self.prog:
+            d += list(ins)
+        d.append(len(self.asserts))
+        for a in self.asserts:
+            d += list(a)
+        d += [len(self.pub)] + [int(v) % P for v in self.pub]
+        d.append(self.exemptions)
+        return np.array(d, dtype=np.uint64)
+
+
+def fib_small_x(k, n):
+    """k copies of examples/src/fibonacci/fib_small (pair j starts at (j+1, j+1)); must produce exactly
+    the proofs of the specialised wf_prove_fib / wfo_prove_fib path."""
+    tr = np.zeros((2 * k, n), dtype=np.uint64)
+    res = []
+    for j in range(k):
+        a = b = j + 1
+        for i in range(n):
+            tr[2 * j, i], tr[2 * j + 1, i] = a, b
+            a = (a + b) % P
+            b = (b + a) % P
+        res.append(int(tr[2 * j + 1, n - 1]))
+    A = AirBuilder(2 * k)
+    A.pub = res
+    for j in range(k):
+        A.constraint(A.sub(A.nxt(2 * j), A.add(A.cur(2 * j), A.cur(2 * j + 1))), 1)
+        A.constraint(A.sub(A.nxt(2 * j + 1), A.add(A.cur(2 * j + 1), A.nxt(2 * j))), 1)
+        A.assert_single(2 * j, 0, j + 1)
+        A.assert_single(2 * j + 1, 0, j + 1)
+        A.assert_single(2 * j + 1, n - 1, res[j])
+    return A.build(), tr
+
+
+def mulfib2(n):
+    """examples/src/fibonacci/mulfib2/air.rs over f64: s0' = s0*s1, s1' = s1*s0' (degree 2), start (1, 2)."""
+    tr = np.zeros((2, n), dtype=np.uint64)
+    a, b = 1, 2
+    for i in range(n):
+        tr[0, i], tr[1, i] = a, b
+        a = a * b % P
+        b = b * a % P
+    A = AirBuilder(2)
+    A.pub = [int(tr[0, n - 1])]
+    A.constraint(A.sub(A.nxt(0), A.mul(A.cur(0), A.cur(1))), 2)
+    A.constraint(A.sub(A.nxt(1), A.mul(A.cur(1), A.nxt(0))), 2)
+    A.assert_single(0, 0, 1)
+    A.assert_single(1, 0, 2)
+    A.assert_single(0, n - 1, int(tr[0, n - 1]))
+    return A.build(), tr
+
+
+def periodic_mix(n, cycle=8):
+    """Periodic columns + a periodic assertion + degree 3 + two transition exemptions:
+         s0' = s0 * k0 + k1          (k0, k1 periodic with cycle `cycle` and 4: degree 1 + 1 cycle)
+         s1' = s1^3 + s0 + k1        (degree 3, one cycle)
+       column 2 is a flag column equal to 1 on every `cycle`-th step (periodic assertion) with the
+       constraint flag * (flag - 1) = 0 (degree 2)."""
+    k0 = [(3 * i + 1) % P for i in range(cycle)]
+    k1 = [5, 7, 11, 13]
+    tr = np.zeros((3, n), dtype=np.uint64)
+    a, b = 3, 4
+    for i in range(n):
+        tr[0, i], tr[1, i], tr[2, i] = a, b, 1 if i % cycle == 0 else 0
+        a2 = (a * k0[i % cycle] + k1[i % 4]) % P
+        b = (pow(b, 3, P) + a + k1[i % 4]) % P
+        a = a2
+    A = AirBuilder(3)
+    A.periodic = [k0, k1]
+    A.exemptions = 2
+    A.pub = [int(tr[0, n - 1]), int(tr[1, n - 1])]
+    A.constraint(A.sub(A.nxt(0), A.add(A.mul(A.cur(0), A.per(0)), A.per(1))), 1, [cycle])
+    b3 = A.mul(A.mul(A.cur(1), A.cur(1)), A.cur(1))
+    A.constraint(A.sub(A.nxt(1), A.add(A.add(b3, A.cur(0)), A.per(1))), 3, [4])
+    one = A.const(1)
+    A.constraint(A.mul(A.cur(2), A.sub(A.cur(2), one)), 2)
+    A.assert_single(0, 0, 3)
+    A.assert_single(1, 0, 4)
+    A.assert_periodic(2, 0, cycle, 1)
+    # with two exemptions the last TWO transitions are not enforced; the final values are still asserted
+    A.assert_single(0, n - 1, int(tr[0, n - 1]))
+    A.assert_single(1, n - 1, int(tr[1, n - 1]))
+    return A.build(), tr

@@ -68,3 +68,31 @@ def test_grinding_smallest_nonce(ctx, oracle, h, g):
     while coin.leading_zeros(want) < g:
         want += 1
     assert ctx.grind(h, coin.seed, g) == want
+
+
+# ---- generic AIR front end (wf_prove_air): same description drives oracle prover, oracle verifier, device ----
+import airs  # noqa: E402  (tests/airs.py)
+
+
+@pytest.mark.parametrize("k,log_n,ext", [(1, 7, 1), (4, 9, 3)])
+def test_generic_air_reproduces_fib_path(ctx, oracle, k, log_n, ext):
+    # the FibSmall x k AIR written as a program must give exactly the specialised kernel's proof
+    desc, trace = airs.fib_small_x(k, 1 << log_n)
+    _, results = oracle.build_fib_trace(k, 1 << log_n)
+    opts = oracle.make_opts(ext=ext, grinding=3, folding=4, rem_max_deg=7)
+    assert ctx.prove_air(desc, trace, opts) == ctx.prove_fib(trace, results, opts)
+
+
+@pytest.mark.parametrize("name,log_n", [("mulfib2", 8), ("periodic_mix", 9), ("periodic_mix", 12)])
+@pytest.mark.parametrize("ext,h,batch", [(1, wf.HASH_BLAKE3_256, 0), (3, wf.HASH_BLAKE3_256, 1), (2, wf.HASH_RP64_256, 2)])
+def test_generic_air_vs_oracle(ctx, oracle, name, log_n, ext, h, batch):
+    # mulfib2 = examples/src/fibonacci/mulfib2/air.rs over f64 (degree 2); periodic_mix exercises periodic
+    # columns, a periodic assertion, degree 3 (ce_blowup 4, three composition columns) and two exemptions
+    desc, trace = getattr(airs, name)(1 << log_n)
+    opts = oracle.make_opts(num_queries=24, blowup=8, grinding=2, ext=ext, folding=4, rem_max_deg=15, batch_c=batch, batch_d=batch, hash_id=h)
+    got = ctx.prove_air(desc, trace, opts)
+    assert got == oracle.prove_air(desc, trace, opts)
+    assert oracle.verify_air(desc, got, h) == 0
+    bad = desc.copy()
+    bad[-2] ^= np.uint64(1)  # last public input
+    assert oracle.verify_air(bad, got, h) != 0

@@ -66,6 +66,7 @@ _SIGS = [
     ("wf_fri_build_proof", C.c_int, [vp, vp, u64p, C.c_size_t, u8p, C.POINTER(C.c_size_t)]),
     ("wf_fri_free", C.c_int, [vp, vp]),
     ("wf_prove_fib", C.c_int, [vp, C.POINTER(u64p), C.c_int, C.c_uint32, C.c_uint32, u64p, C.POINTER(C.c_uint32), u8p, C.POINTER(C.c_size_t)]),
+    ("wf_prove_air", C.c_int, [vp, u64p, C.c_size_t, C.POINTER(u64p), C.c_int, C.c_uint32, C.POINTER(C.c_uint32), u8p, C.POINTER(C.c_size_t)]),
     ("wf_prove_fib_dev", C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u64p, C.POINTER(C.c_uint32), u8p, C.POINTER(C.c_size_t)]),
     ("wf_grind", C.c_int, [vp, C.c_int, u8p, C.c_uint32, C.POINTER(C.c_uint64)]),
     ("wf_ntt_dev", C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_int]),
@@ -199,6 +200,20 @@ class Context:
         buf = np.zeros(cap, dtype=np.uint8)
         ln = C.c_size_t(cap)
         self.check(self.L.wf_prove_fib(self.h, ptrs, int(mont), c // 2, int(n).bit_length() - 1, rp,
+                                       o_.ctypes.data_as(C.POINTER(C.c_uint32)), buf.ctypes.data_as(u8p), C.byref(ln)))
+        return buf[: ln.value].tobytes()
+
+    def prove_air(self, desc, trace, opts, mont=False):
+        """desc: flat AIR description (see wf_prove_air); trace: [width, n] uint64. Returns proof bytes."""
+        d_, dp = _u64(desc)
+        a = np.ascontiguousarray(trace, dtype=np.uint64)
+        c, n = a.shape
+        ptrs = (u64p * c)(*[a[j].ctypes.data_as(u64p) for j in range(c)])
+        o_ = np.ascontiguousarray(opts, dtype=np.uint32)
+        cap = 1 << 23
+        buf = np.zeros(cap, dtype=np.uint8)
+        ln = C.c_size_t(cap)
+        self.check(self.L.wf_prove_air(self.h, dp, d_.size, ptrs, int(mont), int(n).bit_length() - 1,
                                        o_.ctypes.data_as(C.POINTER(C.c_uint32)), buf.ctypes.data_as(u8p), C.byref(ln)))
         return buf[: ln.value].tobytes()
 

@@ -763,41 +763,6 @@ int wf_tree_open_many(wf_ctx* ctx, const wf_tree* t, const uint64_t* positions, 
 }
 
 // ---- FRI ----------------------------------------------------------------------------------------
-// host iNTT with offset for the remainder (<= a few hundred elements; fri/src/prover/mod.rs:230-239,
-// fft/serial.rs:84-101). Plain O(n log n) radix-2 on the host copy.
-static void host_interpolate_with_offset(std::vector<u64>& v, size_t n, int d, u64 offset) {
-    u32 log_n = 0;
-    while (((size_t)1 << log_n) < n) log_n++;
-    // inverse DFT: a[j] = (1/n) sum_i v[i] w^(-ij)
-    u64 w_inv = gl_inv(gl_root_of_unity(std::max(log_n, 1u)));
-    if (n == 1) w_inv = 1;
-    // bit-reverse, then DIT butterflies
-    for (size_t i = 0; i < n; i++) {
-        size_t j = 0;
-        for (u32 b = 0; b < log_n; b++) j |= ((i >> b) & 1) << (log_n - 1 - b);
-        if (j > i) for (int c = 0; c < d; c++) std::swap(v[i * d + c], v[j * d + c]);
-    }
-    for (size_t len = 2; len <= n; len <<= 1) {
-        u64 wl = gl_pow(w_inv, n / len);
-        for (size_t s = 0; s < n; s += len) {
-            u64 w = 1;
-            for (size_t i = 0; i < len / 2; i++) {
-                for (int c = 0; c < d; c++) {
-                    u64 a = v[(s + i) * d + c], b = gl_mul(v[(s + i + len / 2) * d + c], w);
-                    v[(s + i) * d + c] = gl_add(a, b);
-                    v[(s + i + len / 2) * d + c] = gl_sub(a, b);
-                }
-                w = gl_mul(w, wl);
-            }
-        }
-    }
-    u64 scale = gl_inv((u64)n % GL_P), oinv = gl_inv(offset);
-    for (size_t i = 0; i < n; i++) {
-        for (int c = 0; c < d; c++) v[i * d + c] = gl_mul(v[i * d + c], scale);
-        scale = gl_mul(scale, oinv);
-    }
-}
-
 int wf_fri_free(wf_ctx* ctx, wf_fri* f) {
     if (!f) return WF_OK;
     for (auto& l : f->layers) { wf_dev_free(ctx, l.evals); wf_tree_free(ctx, l.tree); }
@@ -856,7 +821,7 @@ int wf_fri_build_layers(wf_ctx* ctx, int hash_id, const wf_mat* evals, int d, ui
     wf_dev_free(ctx, cur);
     for (size_t i = 0; i < len; i++)
         for (int c = 0; c < d; c++) v[i * d + c] = raw[i * ld + c];
-    host_interpolate_with_offset(v, len, d, GL_GENERATOR);
+    wf_host_dft(v, len, d, true, GL_GENERATOR);
     size_t rsize = len / blowup;
     f->remainder.resize(rsize * d);
     for (size_t i = 0; i < rsize; i++)

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <map>
 #include <set>
 #include <string>
@@ -48,6 +49,47 @@ struct wf_tree {
     u64* leaves;  // nleaves x 4 words
     u64* nodes;   // nleaves x 4 words
 };
+
+// Small host-side transforms for transcript-sized data (FRI remainder, periodic column tables):
+// plain radix-2 on `n` elements of `d` interleaved components. inverse: a_j = (1/n) sum v_i w^(-ij),
+// then coefficient j scaled by offset^-j (fft/serial.rs:84-101 interpolate_poly_with_offset);
+// forward: coefficient j scaled by offset^j first, then v_i = sum a_j w^(ij) (evaluation over offset*<w>).
+static inline void wf_host_dft(std::vector<u64>& v, size_t n, int d, bool inverse, u64 offset) {
+    u32 log_n = 0;
+    while (((size_t)1 << log_n) < n) log_n++;
+    u64 w0 = n > 1 ? gl_root_of_unity(log_n) : 1;
+    if (inverse) w0 = gl_inv(w0);
+    if (!inverse && offset != 1) {
+        u64 f = 1;
+        for (size_t i = 0; i < n; i++) { for (int c = 0; c < d; c++) v[i * d + c] = gl_mul(v[i * d + c], f); f = gl_mul(f, offset); }
+    }
+    for (size_t i = 0; i < n; i++) {  // bit-reverse, then DIT butterflies
+        size_t j = 0;
+        for (u32 b = 0; b < log_n; b++) j |= ((i >> b) & 1) << (log_n - 1 - b);
+        if (j > i) for (int c = 0; c < d; c++) std::swap(v[i * d + c], v[j * d + c]);
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        u64 wl = gl_pow(w0, n / len);
+        for (size_t s = 0; s < n; s += len) {
+            u64 w = 1;
+            for (size_t i = 0; i < len / 2; i++) {
+                for (int c = 0; c < d; c++) {
+                    u64 a = v[(s + i) * d + c], b = gl_mul(v[(s + i + len / 2) * d + c], w);
+                    v[(s + i) * d + c] = gl_add(a, b);
+                    v[(s + i + len / 2) * d + c] = gl_sub(a, b);
+                }
+                w = gl_mul(w, wl);
+            }
+        }
+    }
+    if (inverse) {
+        u64 scale = gl_inv((u64)n % GL_P), oinv = gl_inv(offset);
+        for (size_t i = 0; i < n; i++) {
+            for (int c = 0; c < d; c++) v[i * d + c] = gl_mul(v[i * d + c], scale);
+            scale = gl_mul(scale, oinv);
+        }
+    }
+}
 
 int wf_fail(wf_ctx* ctx, int code, const char* fmt, ...);
 int wf_dev_alloc(wf_ctx* ctx, size_t bytes, void** out);

@@ -111,6 +111,80 @@ __global__ void __launch_bounds__(256) fib_constraints_kernel(FibEvalParams p) {
     }
 }
 
+// Generic constraint evaluator: Air::evaluate_transition given as a straight-line program over the
+// frame registers (r[0..w) current row, r[w..2w) next row, then periodic values, then temporaries),
+// any number of single-value boundary groups and transition exemptions. One CE row
+// per thread; registers live in local memory.
+#define GEN_MAX_REGS 160
+struct GenEvalParams {
+    SegMatrix lde, out;
+    u32 w, log_n, log_blowup, log_ce_blowup;
+    const u32* prog;       // [prog_len][4]: op, dst, a, b
+    u32 prog_len, num_regs, num_periodic, num_tc;
+    const u64* consts;
+    const u64* ptab;       // periodic tables, concatenated
+    const u32* ptab_off;   // [num_periodic]
+    const u32* ptab_len;   // [num_periodic]  (L_j * ce_blowup, a power of two)
+    const u64* tcoef;      // [num_tc][D]
+    u32 num_groups;
+    const u32* g_off;      // [num_groups + 1] offsets into the entry arrays
+    const u64* g_a;        // x^a - b divisor exponent (a divides n)
+    const u64* g_b;
+    const u64* g_oa;       // 7^a
+    const u32* e_col;
+    const u64* e_val;
+    const u64* e_cc;       // [entries][D]
+    const u64* tw_ce;      // w_ce^i, i < ce/2
+    u64 zt[8];             // 1 / (x^n - 1) at CE step i mod ce_blowup
+    u64 exempt[8];
+    u32 num_exempt;
+};
+template <int D>
+__global__ void __launch_bounds__(128) generic_constraints_kernel(GenEvalParams p) {
+    const size_t ce = (size_t)1 << (p.log_n + p.log_ce_blowup);
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ce) return;
+    const size_t N = (size_t)1 << (p.log_n + p.log_blowup);
+    const size_t ls = i << (p.log_blowup - p.log_ce_blowup);
+    const size_t nx = (ls + ((size_t)1 << p.log_blowup)) & (N - 1);
+    u64 r[GEN_MAX_REGS];
+    for (u32 c = 0; c < p.w; c++) { r[c] = seg_at(p.lde, ls, c); r[p.w + c] = seg_at(p.lde, nx, c); }
+    for (u32 j = 0; j < p.num_periodic; j++) r[2 * p.w + j] = p.ptab[p.ptab_off[j] + (u32)(i & (p.ptab_len[j] - 1))];
+    GlExt<D> T = ext_zero<D>();
+    for (u32 k = 0; k < p.prog_len; k++) {
+        const u32 op = p.prog[4 * k], dst = p.prog[4 * k + 1], a = p.prog[4 * k + 2], b = p.prog[4 * k + 3];
+        switch (op) {
+            case 0: r[dst] = gl_add(r[a], r[b]); break;
+            case 1: r[dst] = gl_sub(r[a], r[b]); break;
+            case 2: r[dst] = gl_mul(r[a], r[b]); break;
+            case 3: r[dst] = p.consts[a]; break;
+            default: T = ext_add(T, ext_mul_base(ld_ext<D>(p.tcoef + (size_t)dst * D), r[a])); break;  // OUT
+        }
+    }
+    const u32 half = (u32)(ce >> 1);
+    const u32 cemask = (u32)(ce - 1);
+    u64 w = p.tw_ce[i & (half - 1)];
+    if (i & half) w = gl_neg(w);
+    const u64 x = gl_mul(w, GL_GENERATOR);
+    u64 ex = 1;
+    for (u32 k = 0; k < p.num_exempt; k++) ex = gl_mul(ex, gl_sub(x, p.exempt[k]));
+    GlExt<D> acc = ext_mul_base(T, gl_mul(p.zt[i & (((size_t)1 << p.log_ce_blowup) - 1)], ex));
+    for (u32 g = 0; g < p.num_groups; g++) {
+        GlExt<D> B = ext_zero<D>();
+        for (u32 e = p.g_off[g]; e < p.g_off[g + 1]; e++)
+            B = ext_add(B, ext_mul_base(ld_ext<D>(p.e_cc + (size_t)e * D), gl_sub(r[p.e_col[e]], p.e_val[e])));
+        // x^a = 7^a * w_ce^(i*a mod ce)
+        u32 ia = (u32)(((u64)i * p.g_a[g]) & cemask);
+        u64 wa = p.tw_ce[ia & (half - 1)];
+        if (ia & half) wa = gl_neg(wa);
+        u64 den = gl_sub(gl_mul(wa, p.g_oa[g]), p.g_b[g]);
+        acc = ext_add(acc, ext_mul_base(B, gl_inv(den)));
+    }
+    u64* o = p.out.base + i * p.out.W;
+#pragma unroll
+    for (int q = 0; q < D; q++) o[q] = acc.v[q];
+}
+
 // composition_poly.rs:128-140 segment(): column j = coefficients [j*n, (j+1)*n) of the interpolated
 // CE-domain polynomial; each is an extension column of D base columns.
 __global__ void comp_split_kernel(SegMatrix coefs, size_t n, u32 kc, int D, SegMatrix out) {
@@ -335,6 +409,113 @@ struct Options {
     int hash_id;
 };
 
+// Host-side AIR description (mirrors oracle/wf_prover.cpp `Air`; flat format documented at
+// wf_prove_air in include/winterfell_b200.h)
+struct AirAssertion { u64 column, first_step, stride, value; };
+struct AirHost {
+    u32 w = 0;
+    std::vector<u64> pub_inputs;
+    std::vector<std::pair<u32, std::vector<u32>>> degrees;
+    std::vector<std::vector<u64>> periodic;
+    std::vector<u64> consts;
+    std::vector<u32> prog;  // 4 words per instruction
+    u32 num_regs = 0;
+    std::vector<AirAssertion> asserts;
+    u32 exemptions = 1;
+    bool is_fib = false;  // FibSmall x k: use the specialised kernel
+    u32 fib_k = 0;
+    std::vector<u64> fib_results;
+    u32 log_ce_blowup() const {  // air/src/air/context.rs:87-100, transition/degree.rs min_blowup_factor
+        u32 r = 1;
+        for (auto& dg : degrees) {
+            u32 bound = dg.first + (u32)dg.second.size() - 1, l = 0;
+            while ((1u << l) < bound) l++;
+            r = std::max(r, std::max(l, 1u));
+        }
+        return r;
+    }
+    u32 num_comp_cols(size_t n) const {  // context.rs:265-285
+        size_t hi = 0;
+        for (auto& dg : degrees) {
+            size_t e = (size_t)dg.first * (n - 1);
+            for (u32 cyc : dg.second) e += (n / cyc) * (cyc - 1);
+            hi = std::max(hi, e);
+        }
+        size_t div = n - exemptions;
+        return (u32)std::max((hi - div + n - 1) / n, (size_t)1);
+    }
+    std::vector<AirAssertion> sorted_assertions() const {  // assertions/mod.rs:301-315
+        std::vector<AirAssertion> a = asserts;
+        std::stable_sort(a.begin(), a.end(), [](const AirAssertion& x, const AirAssertion& y) {
+            if (x.stride != y.stride) return x.stride < y.stride;
+            if (x.first_step != y.first_step) return x.first_step < y.first_step;
+            return x.column < y.column;
+        });
+        return a;
+    }
+};
+static AirHost fib_air_host(u32 k, size_t n, const u64* results) {
+    AirHost a;
+    a.w = 2 * k;
+    a.pub_inputs.assign(results, results + k);
+    a.is_fib = true; a.fib_k = k; a.fib_results.assign(results, results + k);
+    for (u32 j = 0; j < k; j++) {
+        a.degrees.push_back({1, {}});
+        a.degrees.push_back({1, {}});
+        a.asserts.push_back({2 * j, 0, 0, (u64)(j + 1)});
+        a.asserts.push_back({2 * j + 1, 0, 0, (u64)(j + 1)});
+        a.asserts.push_back({2 * j + 1, n - 1, 0, results[j]});
+    }
+    return a;
+}
+static bool parse_air_host(const u64* d, size_t len, AirHost& a) {
+    size_t p = 0;
+    auto rd = [&](u64& v) { if (p >= len) return false; v = d[p++]; return true; };
+    u64 v, cnt;
+    if (!rd(v) || v == 0 || v > 255) return false;
+    a.w = (u32)v;
+    if (!rd(cnt) || cnt == 0 || cnt > 4096) return false;
+    for (u64 i = 0; i < cnt; i++) {
+        u64 base, nc;
+        if (!rd(base) || !rd(nc) || base == 0 || nc > 16) return false;
+        std::vector<u32> cyc;
+        for (u64 j = 0; j < nc; j++) { if (!rd(v)) return false; cyc.push_back((u32)v); }
+        a.degrees.push_back({(u32)base, cyc});
+    }
+    if (!rd(cnt) || cnt > 64) return false;
+    for (u64 i = 0; i < cnt; i++) {
+        u64 ln;
+        if (!rd(ln) || ln < 2 || (ln & (ln - 1))) return false;
+        std::vector<u64> col;
+        for (u64 j = 0; j < ln; j++) { if (!rd(v) || v >= GL_P) return false; col.push_back(v); }
+        a.periodic.push_back(col);
+    }
+    if (!rd(cnt)) return false;
+    for (u64 i = 0; i < cnt; i++) { if (!rd(v) || v >= GL_P) return false; a.consts.push_back(v); }
+    if (!rd(v) || v > GEN_MAX_REGS || v < 2 * a.w + a.periodic.size()) return false;
+    a.num_regs = (u32)v;
+    if (!rd(cnt) || cnt > (1u << 20)) return false;
+    for (u64 i = 0; i < cnt; i++) {
+        u64 op, ds, x, y;
+        if (!rd(op) || !rd(ds) || !rd(x) || !rd(y) || op > 4) return false;
+        if (op == 4) { if (ds >= a.degrees.size() || x >= a.num_regs) return false; }
+        else if (op == 3) { if (ds >= a.num_regs || x >= a.consts.size()) return false; }
+        else if (ds >= a.num_regs || x >= a.num_regs || y >= a.num_regs) return false;
+        a.prog.insert(a.prog.end(), {(u32)op, (u32)ds, (u32)x, (u32)y});
+    }
+    if (!rd(cnt) || cnt == 0) return false;
+    for (u64 i = 0; i < cnt; i++) {
+        AirAssertion as;
+        if (!rd(as.column) || !rd(as.first_step) || !rd(as.stride) || !rd(as.value) || as.column >= a.w || as.value >= GL_P) return false;
+        a.asserts.push_back(as);
+    }
+    if (!rd(cnt)) return false;
+    for (u64 i = 0; i < cnt; i++) { if (!rd(v) || v >= GL_P) return false; a.pub_inputs.push_back(v); }
+    if (!rd(v) || v == 0 || v > 8) return false;
+    a.exemptions = (u32)v;
+    return p == len;
+}
+
 template <int D>
 struct Channel {  // ProverChannel (prover/src/channel.rs)
     PublicCoin coin;
@@ -435,20 +616,25 @@ void write_queries(const GatherBatch& gb, size_t row_id, size_t dig_id, size_t n
 }
 
 template <int D>
-int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont, u32 k, u32 log_n,
-              const u64* results, const Options& o, std::vector<u8>& proof_out) {
+int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont, u32 log_n,
+              const Options& o, std::vector<u8>& proof_out) {
     const int h = o.hash_id;
     const size_t n = (size_t)1 << log_n;
     u32 log_b = 0;
     while ((1u << log_b) < o.blowup) log_b++;
     const size_t N = n << log_b;
-    const u32 c = 2 * k, kc = 1, log_ceb = 1;  // degree-1 constraints: ce_blowup 2, one composition column
-    const u32 n_tr = 2 * k, n_as = 3 * k;
+    const u32 c = air.w, kc = air.num_comp_cols(n), log_ceb = air.log_ce_blowup();
+    const u32 n_tr = (u32)air.degrees.size(), n_as = (u32)air.asserts.size();
+    if (log_ceb > log_b) return wf_fail(ctx, WF_ERR_INVALID, "blowup factor too small for the constraint degrees");
+    for (auto& col : air.periodic) if (col.size() > n) return wf_fail(ctx, WF_ERR_INVALID, "periodic column longer than the trace");
+    for (auto& as : air.asserts)
+        if (as.first_step >= n || (as.stride != 0 && (as.stride < 2 || (as.stride & (as.stride - 1)) || as.stride > n || as.first_step >= as.stride)))
+            return wf_fail(ctx, WF_ERR_INVALID, "invalid assertion");
     // ---- channel seed: Context::to_elements || pub inputs (channel.rs:57-82, context.rs:119-136) ----
     std::vector<u64> seed = {((u64)c << 8), (u64)n, 1, 0xFFFFFFFFULL, (u64)(n_tr + n_as),
                              ((u64)o.ext << 24) | ((u64)o.folding << 16) | ((u64)o.rem_max_deg << 8) | o.blowup,
                              o.grinding, o.num_queries};
-    for (u32 j = 0; j < k; j++) seed.push_back(results[j]);
+    for (u64 v : air.pub_inputs) seed.push_back(v);
     Channel<D> ch(h, seed);
 
     // ---- 1. trace commitment (lib.rs:497-522) ----
@@ -471,37 +657,112 @@ int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, const uint64_t* d_
 
     // ---- 2. constraint evaluation (lib.rs:373-378) ----
     std::vector<GlExt<D>> cc = ch.draw_coeffs(o.batch_c, n_tr + n_as);
-    // boundary coefficients follow the assertions sorted by (stride, first_step, column)
-    // (air/src/air/assertions/mod.rs:301-315): 2k assertions at step 0, then k at step n-1
-    u64 *d_tc, *d_b0, *d_b1, *d_res;
-    CKI(upload_ext<D>(ctx, cc, 0, n_tr, &d_tc));
-    CKI(upload_ext<D>(ctx, cc, n_tr, 2 * k, &d_b0));
-    CKI(upload_ext<D>(ctx, cc, n_tr + 2 * k, k, &d_b1));
-    {
-        void* p;
-        CKI(wf_dev_alloc(ctx, k * 8, &p));
-        CK(cudaMemcpyAsync(p, results, k * 8, cudaMemcpyHostToDevice, ctx->st));
-        d_res = (u64*)p;
-    }
     const size_t ce = n << log_ceb;
     wf_mat* comp;
     CKI(wf_mat_alloc(ctx, ce, D, &comp));
     if (comp->m.W > D) CK(cudaMemsetAsync(comp->m.base, 0, comp->m.words() * 8, ctx->st));
-    {
+    const u64 g_tr = gl_root_of_unity(log_n);
+    u64 zt[8];
+    {   // x^n over the CE domain takes ce_blowup values: (7 w_ce^i)^n = 7^n * w_ceb^i
+        u64 o_n = gl_pow(GL_GENERATOR, n), w_ceb = gl_root_of_unity(log_ceb);
+        for (u32 i = 0; i < (1u << log_ceb); i++) zt[i] = gl_inv(gl_sub(gl_mul(o_n, gl_pow(w_ceb, i)), 1));
+    }
+    std::vector<void*> scratch;  // device buffers of this stage
+    auto upload = [&](const void* src, size_t bytes, void** out) -> int {
+        void* p;
+        CKI(wf_dev_alloc(ctx, std::max(bytes, (size_t)8), &p));
+        // stream-ordered copy; the (pageable) source vectors stay alive until the synchronisation below
+        if (bytes) CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->st));
+        scratch.push_back(p);
+        *out = p;
+        return WF_OK;
+    };
+    auto flat = [&](size_t first, size_t count) {
+        std::vector<u64> f(count * D);
+        for (size_t i = 0; i < count; i++) for (int q = 0; q < D; q++) f[i * D + q] = cc[first + i].v[q];
+        return f;
+    };
+    if (air.is_fib) {
+        // boundary coefficients follow the assertions sorted by (stride, first_step, column)
+        // (air/src/air/assertions/mod.rs:301-315): 2k assertions at step 0, then k at step n-1
+        const u32 k = air.fib_k;
+        void *d_tc, *d_b0, *d_b1, *d_res;
+        auto f0 = flat(0, n_tr), f1 = flat(n_tr, 2 * k), f2 = flat(n_tr + 2 * k, k);
+        CKI(upload(f0.data(), f0.size() * 8, &d_tc));
+        CKI(upload(f1.data(), f1.size() * 8, &d_b0));
+        CKI(upload(f2.data(), f2.size() * 8, &d_b1));
+        CKI(upload(air.fib_results.data(), k * 8, &d_res));
         FibEvalParams p;
         p.lde = lde->m; p.out = comp->m; p.k = k; p.log_n = log_n; p.log_blowup = log_b; p.log_ce_blowup = log_ceb;
-        p.tcoef = d_tc; p.bcoef0 = d_b0; p.bcoef1 = d_b1; p.results = d_res;
+        p.tcoef = (u64*)d_tc; p.bcoef0 = (u64*)d_b0; p.bcoef1 = (u64*)d_b1; p.results = (u64*)d_res;
         CKI(wf_get_twiddles(ctx, log_n + log_ceb, &p.tw_ce));
-        u64 g_tr = gl_root_of_unity(log_n);
         p.last = gl_pow(g_tr, n - 1);
-        // x^n over the CE domain takes ce_blowup values: (7 w_ce^i)^n = 7^n * w_ceb^i
-        u64 o_n = gl_pow(GL_GENERATOR, n), w_ceb = gl_root_of_unity(log_ceb);
-        for (u32 i = 0; i < (1u << log_ceb); i++) p.zt[i] = gl_inv(gl_sub(gl_mul(o_n, gl_pow(w_ceb, i)), 1));
+        for (u32 i = 0; i < (1u << log_ceb); i++) p.zt[i] = zt[i];
         size_t threads = (ce + FIB_ROWS - 1) / FIB_ROWS;
         fib_constraints_kernel<D><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->st>>>(p);
         ctx->launches++;
         CK(cudaGetLastError());
+    } else {
+        GenEvalParams p;
+        memset(&p, 0, sizeof(p));
+        p.lde = lde->m; p.out = comp->m; p.w = c; p.log_n = log_n; p.log_blowup = log_b; p.log_ce_blowup = log_ceb;
+        p.prog_len = (u32)(air.prog.size() / 4); p.num_regs = air.num_regs; p.num_periodic = (u32)air.periodic.size(); p.num_tc = n_tr;
+        void* dp;
+        CKI(upload(air.prog.data(), air.prog.size() * 4, &dp)); p.prog = (u32*)dp;
+        CKI(upload(air.consts.data(), air.consts.size() * 8, &dp)); p.consts = (u64*)dp;
+        // periodic value tables (evaluator/periodic_table.rs:24-76): poly_j over offset^(n/L) <w_(L*ceb)>
+        std::vector<u64> ptab;
+        std::vector<u32> poff, plen;
+        for (auto& col : air.periodic) {
+            const size_t L = col.size(), M = L << log_ceb;
+            std::vector<u64> v = col;
+            wf_host_dft(v, L, 1, true, 1);              // get_periodic_column_polys (air/mod.rs:325-360)
+            v.resize(M, 0);
+            wf_host_dft(v, M, 1, false, gl_pow(GL_GENERATOR, n / L));
+            poff.push_back((u32)ptab.size()); plen.push_back((u32)M);
+            ptab.insert(ptab.end(), v.begin(), v.end());
+        }
+        CKI(upload(ptab.data(), ptab.size() * 8, &dp)); p.ptab = (u64*)dp;
+        CKI(upload(poff.data(), poff.size() * 4, &dp)); p.ptab_off = (u32*)dp;
+        CKI(upload(plen.data(), plen.size() * 4, &dp)); p.ptab_len = (u32*)dp;
+        auto f0 = flat(0, n_tr);
+        CKI(upload(f0.data(), f0.size() * 8, &dp)); p.tcoef = (u64*)dp;
+        // boundary groups: BTreeMap keyed by (stride, first_step) (air/src/air/boundary/mod.rs:154),
+        // coefficients assigned in sorted-assertion order; divisor x^a - g^(a*first_step) (divisor.rs:44-56)
+        auto as = air.sorted_assertions();
+        std::map<std::pair<u64, u64>, std::vector<size_t>> groups;
+        for (size_t i = 0; i < as.size(); i++) groups[{as[i].stride, as[i].first_step}].push_back(i);
+        std::vector<u32> goff = {0}, ecol;
+        std::vector<u64> ga, gb, goa, eval, ecc;
+        for (auto& kv : groups) {
+            u64 a = kv.first.first == 0 ? 1 : n / kv.first.first;
+            ga.push_back(a);
+            gb.push_back(kv.first.second == 0 ? 1 : gl_pow(g_tr, a * kv.first.second));
+            goa.push_back(gl_pow(GL_GENERATOR, a));
+            for (size_t i : kv.second) {
+                ecol.push_back((u32)as[i].column); eval.push_back(as[i].value);
+                for (int q = 0; q < D; q++) ecc.push_back(cc[n_tr + i].v[q]);
+            }
+            goff.push_back((u32)ecol.size());
+        }
+        p.num_groups = (u32)ga.size();
+        CKI(upload(goff.data(), goff.size() * 4, &dp)); p.g_off = (u32*)dp;
+        CKI(upload(ga.data(), ga.size() * 8, &dp)); p.g_a = (u64*)dp;
+        CKI(upload(gb.data(), gb.size() * 8, &dp)); p.g_b = (u64*)dp;
+        CKI(upload(goa.data(), goa.size() * 8, &dp)); p.g_oa = (u64*)dp;
+        CKI(upload(ecol.data(), ecol.size() * 4, &dp)); p.e_col = (u32*)dp;
+        CKI(upload(eval.data(), eval.size() * 8, &dp)); p.e_val = (u64*)dp;
+        CKI(upload(ecc.data(), ecc.size() * 8, &dp)); p.e_cc = (u64*)dp;
+        CKI(wf_get_twiddles(ctx, log_n + log_ceb, &p.tw_ce));
+        for (u32 i = 0; i < (1u << log_ceb); i++) p.zt[i] = zt[i];
+        p.num_exempt = air.exemptions;
+        for (u32 e = 0; e < air.exemptions; e++) p.exempt[e] = gl_pow(g_tr, n - air.exemptions + e);  // divisor.rs:31-41
+        generic_constraints_kernel<D><<<(unsigned)((ce + 127) / 128), 128, 0, ctx->st>>>(p);
+        ctx->launches++;
+        CK(cudaGetLastError());
     }
+    CK(cudaStreamSynchronize(ctx->st));
+    for (void* sp : scratch) wf_dev_free(ctx, sp);
     wf_mark(ctx, "constraint_eval");
     // ---- 3. composition polynomial + commitment (lib.rs:527-552) ----
     wf_mat *ccoefs, *cpolys, *clde;
@@ -622,7 +883,7 @@ int prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, const uint64_t* d_
     for (wf_mat* m : {polys, lde, cpolys, clde}) wf_mat_free(ctx, m);
     wf_tree_free(ctx, ttree);
     wf_tree_free(ctx, ctree);
-    for (u64* p : {d_tc, d_b0, d_b1, d_res, d_dt, d_dq}) wf_dev_free(ctx, p);
+    for (u64* p : {d_dt, d_dq}) wf_dev_free(ctx, p);
     return WF_OK;
 }
 
@@ -635,22 +896,24 @@ extern "C" int wf_grind(wf_ctx* ctx, int hash_id, const uint8_t seed[32], uint32
     return grind_on_device(ctx, hash_id, d, grinding, nonce);
 }
 
-static int prove_fib_entry(wf_ctx* ctx, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont, uint32_t k,
-                           uint32_t log_n, const uint64_t* results, const uint32_t* opts, uint8_t* proof, size_t* proof_len) {
-    if (!ctx || (!trace_cols && !d_trace) || !results || !opts || !proof || !proof_len || k == 0 || 2 * k > 255 || log_n < 3)
-        return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
-    Options o;
+static int parse_options(wf_ctx* ctx, const uint32_t* opts, Options& o) {
     o.num_queries = opts[0]; o.blowup = opts[1]; o.grinding = opts[2]; o.ext = opts[3]; o.folding = opts[4];
     o.rem_max_deg = opts[5]; o.batch_c = opts[6]; o.batch_d = opts[7]; o.hash_id = (int)opts[8];
     o.num_partitions = 1; o.hash_rate = 1;
-    if (o.blowup < 2 || (o.blowup & (o.blowup - 1)) || o.num_queries == 0 || o.num_queries > 255 || o.batch_c > 2 || o.batch_d > 2)
+    if (o.blowup < 2 || o.blowup > 128 || (o.blowup & (o.blowup - 1)) || o.num_queries == 0 || o.num_queries > 255 || o.batch_c > 2 ||
+        o.batch_d > 2 || o.grinding > 32 || o.rem_max_deg > 255)
         return wf_fail(ctx, WF_ERR_INVALID, "bad proof options");
+    if (o.hash_id != WF_HASH_BLAKE3_256 && o.hash_id != WF_HASH_RP64_256) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "unknown hash %d", o.hash_id);
+    return WF_OK;
+}
+static int prove_dispatch(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont,
+                          uint32_t log_n, const Options& o, uint8_t* proof, size_t* proof_len) {
     std::vector<u8> out;
     int r;
     switch (o.ext) {
-        case 1: r = prove_fib<1>(ctx, trace_cols, d_trace, mont, k, log_n, results, o, out); break;
-        case 2: r = prove_fib<2>(ctx, trace_cols, d_trace, mont, k, log_n, results, o, out); break;
-        case 3: r = prove_fib<3>(ctx, trace_cols, d_trace, mont, k, log_n, results, o, out); break;
+        case 1: r = prove_air<1>(ctx, air, trace_cols, d_trace, mont, log_n, o, out); break;
+        case 2: r = prove_air<2>(ctx, air, trace_cols, d_trace, mont, log_n, o, out); break;
+        case 3: r = prove_air<3>(ctx, air, trace_cols, d_trace, mont, log_n, o, out); break;
         default: return wf_fail(ctx, WF_ERR_UNSUPPORTED, "field extension %u", o.ext);
     }
     if (r != WF_OK) return r;
@@ -658,6 +921,25 @@ static int prove_fib_entry(wf_ctx* ctx, const uint64_t* const* trace_cols, const
     memcpy(proof, out.data(), out.size());
     *proof_len = out.size();
     return WF_OK;
+}
+static int prove_fib_entry(wf_ctx* ctx, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont, uint32_t k,
+                           uint32_t log_n, const uint64_t* results, const uint32_t* opts, uint8_t* proof, size_t* proof_len) {
+    if (!ctx || (!trace_cols && !d_trace) || !results || !opts || !proof || !proof_len || k == 0 || 2 * k > 255 || log_n < 3)
+        return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    Options o;
+    CKI(parse_options(ctx, opts, o));
+    AirHost air = fib_air_host(k, (size_t)1 << log_n, results);
+    return prove_dispatch(ctx, air, trace_cols, d_trace, mont, log_n, o, proof, proof_len);
+}
+extern "C" int wf_prove_air(wf_ctx* ctx, const uint64_t* air_desc, size_t air_desc_len, const uint64_t* const* trace_cols, int mont,
+                            uint32_t log_n, const uint32_t* opts, uint8_t* proof, size_t* proof_len) {
+    if (!ctx || !air_desc || !trace_cols || !opts || !proof || !proof_len || log_n < 3)
+        return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    Options o;
+    CKI(parse_options(ctx, opts, o));
+    AirHost air;
+    if (!parse_air_host(air_desc, air_desc_len, air)) return wf_fail(ctx, WF_ERR_INVALID, "malformed AIR description");
+    return prove_dispatch(ctx, air, trace_cols, nullptr, mont, log_n, o, proof, proof_len);
 }
 
 extern "C" int wf_prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, uint32_t k, uint32_t log_n,
