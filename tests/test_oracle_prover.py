@@ -1,0 +1,62 @@
+"""CPU tests of the oracle's generate_proof / verify restatement (oracle/wf_prover.cpp): round trips,
+negative tests, and the reference's own end-to-end test configuration
+(examples/src/fibonacci/fib_small/tests.rs:8-24, examples/src/tests.rs:8-17)."""
+import numpy as np
+import pytest
+
+import airs
+
+
+@pytest.mark.parametrize("ext", [1, 2])
+def test_reference_fib_small_test_config(oracle, ext):
+    # FibSmall, sequence length 128 => 64 rows? the reference example proves `sequence_length / 2` rows:
+    # fib_small::get_example(&options, 128) builds a 64-row trace; options: 28 queries, blowup 8,
+    # grinding 0, folding 4, remainder max degree 7, Rp64_256 (fibonacci/utils.rs:33-42, fib_small/tests.rs)
+    for n in (64, 128):
+        trace, res = oracle.build_fib_trace(1, n)
+        opts = oracle.make_opts(num_queries=28, blowup=8, grinding=0, ext=ext, folding=4, rem_max_deg=7, hash_id=oracle.RP64)
+        proof = oracle.prove_fib(trace, res, opts)
+        assert oracle.verify_fib(proof, 1, res, oracle.RP64) == 0
+        # wrong public input must be rejected (examples/src/tests.rs:8-17)
+        assert oracle.verify_fib(proof, 1, res + np.uint64(1), oracle.RP64) != 0
+
+
+@pytest.mark.parametrize("k,n,ext,h,fold,batch", [(1, 256, 1, 0, 8, 0), (4, 256, 3, 0, 4, 1), (2, 64, 3, 0, 2, 2), (3, 128, 2, 1, 16, 0)])
+def test_fib_round_trip_and_tamper(oracle, k, n, ext, h, fold, batch):
+    trace, res = oracle.build_fib_trace(k, n)
+    opts = oracle.make_opts(ext=ext, hash_id=h, folding=fold, batch_c=batch, batch_d=batch, grinding=4)
+    proof = oracle.prove_fib(trace, res, opts)
+    assert oracle.verify_fib(proof, k, res, h) == 0
+    rng = np.random.default_rng(k * n)
+    for _ in range(12):                                    # any flipped bit must be caught
+        t = bytearray(proof)
+        i = int(rng.integers(0, len(t)))
+        t[i] ^= 1 << int(rng.integers(0, 8))
+        assert oracle.verify_fib(bytes(t), k, res, h) != 0, i
+    assert oracle.verify_fib(proof[:-1], k, res, h) != 0   # truncated
+    assert oracle.verify_fib(proof + b"\0", k, res, h) != 0  # trailing byte
+
+
+def test_generic_air_equals_specialised_fib(oracle):
+    for k, n, ext in [(1, 64, 1), (4, 128, 3)]:
+        desc, trace = airs.fib_small_x(k, n)
+        tr2, res = oracle.build_fib_trace(k, n)
+        assert (trace == tr2).all()
+        opts = oracle.make_opts(ext=ext, grinding=2)
+        assert oracle.prove_air(desc, trace, opts) == oracle.prove_fib(tr2, res, opts)
+
+
+@pytest.mark.parametrize("name", ["mulfib2", "periodic_mix"])
+@pytest.mark.parametrize("ext", [1, 2, 3])
+def test_generic_airs_round_trip(oracle, name, ext):
+    desc, trace = getattr(airs, name)(256)
+    opts = oracle.make_opts(ext=ext, grinding=2, blowup=8, folding=4, rem_max_deg=7)
+    proof = oracle.prove_air(desc, trace, opts)
+    assert oracle.verify_air(desc, proof) == 0
+    bad = desc.copy()
+    bad[-2] ^= np.uint64(1)
+    assert oracle.verify_air(bad, proof) != 0
+    # an invalid trace (one flipped cell) must not verify: the constraint quotient stops being low degree
+    t2 = trace.copy()
+    t2[0, 17] ^= np.uint64(1)
+    assert oracle.verify_air(desc, oracle.prove_air(desc, t2, opts)) != 0
