@@ -162,9 +162,29 @@ int wf_prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, uint3
  *                                                             3 CONST (dst = constants[a]), 4 OUT (result[dst] = r[a])
  *    nA, {column, first_step, stride, value} x nA            Assertion::single (stride 0) / ::periodic
  *    nPub, public input elements...,  num_transition_exemptions]
- * Not supported yet: auxiliary trace segments, sequence assertions. */
+ * Not supported yet: sequence assertions. Multi-segment descriptions go through wf_prove_air_aux. */
 int wf_prove_air(wf_ctx* ctx, const uint64_t* air_desc, size_t air_desc_len, const uint64_t* const* trace_cols, int mont,
                  uint32_t log_n, const uint32_t* opts, uint8_t* proof, size_t* proof_len);
+
+/* Multi-segment AIR (one auxiliary segment, as in the reference: air/src/air/trace_info.rs:24-40).
+ * The description above is followed by the aux section
+ *   [aux_width, num_rand_elements,
+ *    nTa, {base_degree, ncycles, cycle...} x nTa            aux_transition_constraint_degrees (context.rs:93)
+ *    aux_num_regs, nIa, {op, dst, a, b} x nIa                Air::evaluate_aux_transition (air/mod.rs:248-260):
+ *                                                            registers over E: [0,w) main current, [w,2w) main next,
+ *                                                            [2w,2w+aw) aux current, [2w+aw,2w+2aw) aux next, then
+ *                                                            nP periodic values, then the random elements, then
+ *                                                            temporaries; same opcodes
+ *    nAa, {column, first_step, stride, v0, v1, v2} x nAa]    Air::get_aux_assertions (:279), value in E
+ * After the main commitment the prover draws num_rand_elements E elements from the public coin
+ * (Air::get_aux_rand_elements, air/mod.rs:292-306) and calls `aux_builder` (Prover::build_aux_trace,
+ * prover/src/lib.rs:236-247) on the HOST: rand_elements = [num_rand][d] words, aux_out = [aux_width][n][d]
+ * words (one Vec<E> per column, as ColMatrix<E>), both in the representation selected by `mont`.
+ * The builder returns 0 on success. d = opts.field_extension. */
+typedef int (*wf_aux_builder_fn)(void* user, const uint64_t* rand_elements, uint64_t* aux_out);
+int wf_prove_air_aux(wf_ctx* ctx, const uint64_t* air_desc, size_t air_desc_len, const uint64_t* const* trace_cols, int mont,
+                     uint32_t log_n, const uint32_t* opts, wf_aux_builder_fn aux_builder, void* aux_user, uint8_t* proof,
+                     size_t* proof_len);
 
 /* same, trace already on the device: column-major [2k][2^log_n], canonical words */
 int wf_prove_fib_dev(wf_ctx* ctx, const uint64_t* d_trace, uint32_t k, uint32_t log_n, const uint64_t* results,

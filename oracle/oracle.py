@@ -367,6 +367,40 @@ def prove_air(desc, trace, opts):
     return out[:ln].tobytes()
 
 
+AUX_BUILDER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
+
+
+def aux_callback(builder, aw, nr, n, d):
+    """Wraps `builder(rand [nr, d] uint64) -> aux columns [aw, n, d] uint64` as the C callback both
+    provers take (prover/src/lib.rs:236-247 build_aux_trace)."""
+    def cb(_user, rand_p, out_p):
+        try:
+            rand = np.ctypeslib.as_array(rand_p, shape=(nr, d)).copy() if nr else np.zeros((0, d), dtype=np.uint64)
+            aux = np.ascontiguousarray(builder(rand), dtype=np.uint64).reshape(aw, n, d)
+            np.ctypeslib.as_array(out_p, shape=(aw, n, d))[:] = aux
+            return 0
+        except Exception:  # an exception must not unwind through the C caller
+            import traceback
+            traceback.print_exc()
+            return 1
+    return AUX_BUILDER(cb)
+
+
+def prove_air_aux(desc, trace, opts, builder, aw, nr):
+    d_, dp = _u64(desc)
+    t_, tp = _u64(trace)
+    cap = 1 << 23
+    out = np.zeros(cap, dtype=np.uint8)
+    L = lib()
+    L.wfo_prove_air_aux.restype = C.c_long
+    cb = aux_callback(builder, aw, nr, t_.shape[1], int(opts[3]))
+    ln = L.wfo_prove_air_aux(dp, C.c_size_t(d_.size), tp, C.c_size_t(t_.shape[1]), opts.ctypes.data_as(C.POINTER(C.c_uint32)),
+                             cb, None, out.ctypes.data_as(u8p), C.c_size_t(cap))
+    if ln < 0:
+        raise RuntimeError(f"prove_air_aux failed ({ln})")
+    return out[:ln].tobytes()
+
+
 def verify_air(desc, proof: bytes, hash_id=BLAKE3):
     d_, dp = _u64(desc)
     p_, pp = _u8(np.frombuffer(proof, dtype=np.uint8))

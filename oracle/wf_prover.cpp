@@ -60,6 +60,7 @@ struct Writer {
 // straight-line program over the evaluation frame, so that the same description drives the oracle,
 // the device evaluator and the verifier. FibSmall x k is one instance (fib_air()).
 struct Assertion { size_t column, first_step, stride; u64 value; };  // stride 0: single; else periodic single-value
+struct AuxAssertion { size_t column, first_step, stride; u64 value[3]; };  // value in E (first d words used)
 struct Instr { u32 op, dst, a, b; };  // ADD/SUB/MUL dst = r[a] op r[b]; CONST dst = consts[a]; OUT result[dst] = r[a]
 enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_CONST = 3, OP_OUT = 4 };
 struct Air {
@@ -73,13 +74,26 @@ struct Air {
     u32 num_regs = 0;                                            // r[0..w) current, r[w..2w) next, r[2w..2w+np) periodic, temps
     std::vector<Assertion> asserts;
     u32 exemptions = 1;                                          // AirContext::num_transition_exemptions
+    // auxiliary trace segment (air/src/air/trace_info.rs:24-40; at most one, as in the reference):
+    // aw columns over E built from nr random elements drawn after the main commitment. The aux
+    // program's registers: [0,w) main cur, [w,2w) main next, [2w,2w+aw) aux cur, [2w+aw,2w+2aw) aux
+    // next, then periodic values, then the nr random elements, then temporaries — all of type E.
+    size_t aw = 0, nr = 0;
+    std::vector<std::pair<u32, std::vector<u32>>> aux_degrees;
+    std::vector<Instr> aux_prog;
+    u32 aux_num_regs = 0;
+    std::vector<AuxAssertion> aux_asserts;
     size_t width() const { return w; }
-    size_t num_transition() const { return degrees.size(); }
-    size_t num_assertions() const { return asserts.size(); }
+    size_t num_main_transition() const { return degrees.size(); }
+    size_t num_transition() const { return degrees.size() + aux_degrees.size(); }  // context.rs:205-207
+    size_t num_assertions() const { return asserts.size() + aux_asserts.size(); }  // context.rs:223-225
+    std::vector<std::pair<u32, std::vector<u32>>> all_degrees() const {            // context.rs:268-271
+        auto r = degrees; r.insert(r.end(), aux_degrees.begin(), aux_degrees.end()); return r;
+    }
     size_t lde_size() const { return n * o.blowup; }
     size_t ce_blowup() const {  // air/src/air/context.rs:87-100 + transition/degree.rs min_blowup_factor
         size_t r = 0;
-        for (auto& dg : degrees) {
+        for (auto& dg : all_degrees()) {
             size_t bound = dg.first + dg.second.size() - 1, p2 = 1;
             while (p2 < bound) p2 <<= 1;
             r = std::max(r, std::max(p2, (size_t)2));
@@ -88,7 +102,7 @@ struct Air {
     }
     size_t num_comp_cols() const {  // context.rs:265-285
         size_t hi = 0;
-        for (auto& dg : degrees) {
+        for (auto& dg : all_degrees()) {
             size_t e = dg.first * (n - 1);  // degree.rs get_evaluation_degree
             for (u32 cyc : dg.second) e += (n / cyc) * (cyc - 1);
             hi = std::max(hi, e);
@@ -111,6 +125,35 @@ struct Air {
                 case OP_OUT: res[in.dst] = r[in.a]; break;
             }
         }
+    }
+    // Air::evaluate_aux_transition (air/src/air/mod.rs:248-260) through the aux program, over E
+    template <class T, class Sub, class Add, class Mul, class FromBase>
+    void eval_aux_transition(const T* mcur, const T* mnxt, const T* acur, const T* anxt, const T* per, const T* rnd, T* res,
+                             Sub sub, Add add, Mul mul, FromBase fb) const {
+        std::vector<T> r(aux_num_regs);
+        for (size_t i = 0; i < w; i++) { r[i] = mcur[i]; r[w + i] = mnxt[i]; }
+        for (size_t i = 0; i < aw; i++) { r[2 * w + i] = acur[i]; r[2 * w + aw + i] = anxt[i]; }
+        const size_t pb = 2 * w + 2 * aw;
+        for (size_t i = 0; i < periodic.size(); i++) r[pb + i] = per[i];
+        for (size_t i = 0; i < nr; i++) r[pb + periodic.size() + i] = rnd[i];
+        for (const Instr& in : aux_prog) {
+            switch (in.op) {
+                case OP_ADD: r[in.dst] = add(r[in.a], r[in.b]); break;
+                case OP_SUB: r[in.dst] = sub(r[in.a], r[in.b]); break;
+                case OP_MUL: r[in.dst] = mul(r[in.a], r[in.b]); break;
+                case OP_CONST: r[in.dst] = fb(consts[in.a]); break;
+                case OP_OUT: res[in.dst] = r[in.a]; break;
+            }
+        }
+    }
+    std::vector<AuxAssertion> aux_assertions() const {
+        std::vector<AuxAssertion> a = aux_asserts;
+        std::stable_sort(a.begin(), a.end(), [](const AuxAssertion& x, const AuxAssertion& y) {
+            if (x.stride != y.stride) return x.stride < y.stride;
+            if (x.first_step != y.first_step) return x.first_step < y.first_step;
+            return x.column < y.column;
+        });
+        return a;
     }
     // assertions in the reference's sorted order (stride, first_step, column):
     // air/src/air/assertions/mod.rs:301-315, boundary/mod.rs prepare_assertions
@@ -195,13 +238,36 @@ static bool parse_air(const u64* d, size_t len, Air& a) {
     for (u64 i = 0; i < cnt; i++) { if (!rd(v)) return false; a.pub_inputs.push_back(v); }
     if (!rd(v)) return false;
     a.exemptions = (u32)v;
-    return p == len;
+    if (p == len) return true;  // single-segment description
+    // optional aux section: [aw, nr, nTa, {base, ncyc, cyc...}*, aux_num_regs, nIa, {op,dst,a,b}*,
+    //                        nAa, {column, first_step, stride, v0, v1, v2}*]
+    if (!rd(v)) return false;
+    a.aw = v;
+    if (!rd(v)) return false;
+    a.nr = v;
+    if (!rd(cnt)) return false;
+    for (u64 i = 0; i < cnt; i++) {
+        u64 base, nc; if (!rd(base) || !rd(nc)) return false;
+        std::vector<u32> cyc; for (u64 j = 0; j < nc; j++) { if (!rd(v)) return false; cyc.push_back((u32)v); }
+        a.aux_degrees.push_back({(u32)base, cyc});
+    }
+    if (!rd(v)) return false;
+    a.aux_num_regs = (u32)v;
+    if (!rd(cnt)) return false;
+    for (u64 i = 0; i < cnt; i++) { u64 op, ds, x, y; if (!rd(op) || !rd(ds) || !rd(x) || !rd(y)) return false; a.aux_prog.push_back({(u32)op, (u32)ds, (u32)x, (u32)y}); }
+    if (!rd(cnt)) return false;
+    for (u64 i = 0; i < cnt; i++) {
+        u64 c, fs, st, v0, v1, v2; if (!rd(c) || !rd(fs) || !rd(st) || !rd(v0) || !rd(v1) || !rd(v2)) return false;
+        a.aux_asserts.push_back({(size_t)c, (size_t)fs, (size_t)st, {v0, v1, v2}});
+    }
+    return p == len && a.aw > 0 && !a.aux_degrees.empty() && !a.aux_asserts.empty();  // context.rs:104-113
 }
 
 static std::vector<u64> context_elements(const FibAir& air) {
     // air/src/proof/context.rs:119-136; air/src/air/trace_info.rs:209-238; air/src/options.rs:294-305
     std::vector<u64> e;
-    e.push_back(((u64)air.width() << 8) | 0);  // main width, 0 aux segments
+    if (air.aw == 0) e.push_back(((u64)air.width() << 8) | 0);  // main width, 0 aux segments
+    else e.push_back((((((u64)air.width() << 8) | 1) << 8 | air.aw) << 8) | air.nr);
     e.push_back((u64)air.n);
     e.push_back(1);                            // low half of the modulus bytes
     e.push_back(0xFFFFFFFFULL);                // high half
@@ -214,7 +280,7 @@ static std::vector<u64> context_elements(const FibAir& air) {
 }
 static void write_context(Writer& w, const FibAir& air) {
     // context.rs:142-151; trace_info.rs:240-264; options.rs:307-320
-    w.u8_((u8)air.width()); w.u8_(0); w.u8_(0);
+    w.u8_((u8)air.width()); w.u8_((u8)air.aw); w.u8_((u8)air.nr);
     w.u8_((u8)__builtin_ctzll(air.n));
     w.u16_(0);  // no trace meta
     w.u8_(8);
@@ -276,6 +342,33 @@ static std::vector<BoundaryGroup> boundary_groups(const Air& air, const std::vec
     for (auto& kv : m) r.push_back(kv.second);
     return r;
 }
+// constraints against the auxiliary segment (boundary/mod.rs:121-128): same grouping, values in E
+struct AuxBoundaryGroup { u64 a, b; std::vector<size_t> cols; std::vector<EE> values; std::vector<EE> cc; };
+static std::vector<AuxBoundaryGroup> aux_boundary_groups(const Air& air, const EE* bcoef) {
+    u64 g = root_of_unity((u32)__builtin_ctzll(air.n));
+    std::map<std::pair<size_t, size_t>, AuxBoundaryGroup> m;
+    auto as = air.aux_assertions();
+    for (size_t i = 0; i < as.size(); i++) {
+        auto key = std::make_pair(as[i].stride, as[i].first_step);
+        auto it = m.find(key);
+        if (it == m.end()) {
+            AuxBoundaryGroup G;
+            G.a = as[i].stride == 0 ? 1 : air.n / as[i].stride;
+            G.b = as[i].first_step == 0 ? 1 : f_exp(g, G.a * as[i].first_step);
+            it = m.insert({key, G}).first;
+        }
+        EE v{{as[i].value[0], as[i].value[1], as[i].value[2]}};
+        for (int k = (int)air.o.ext; k < 3; k++) v.v[k] = 0;
+        it->second.cols.push_back(as[i].column); it->second.values.push_back(v); it->second.cc.push_back(bcoef[i]);
+    }
+    std::vector<AuxBoundaryGroup> r;
+    for (auto& kv : m) r.push_back(kv.second);
+    return r;
+}
+// builds the auxiliary segment (Prover::build_aux_trace, prover/src/lib.rs:236-247): rand [nr][d] words,
+// out [aw][n][d] words
+typedef int (*AuxBuilder)(void* user, const u64* rand_elements, u64* aux_out);
+
 // transition divisor exemption points g^(n-1), ..., g^(n-k) (divisor.rs:31-41 from_transition)
 static std::vector<u64> exemption_points(const Air& air) {
     u64 g = root_of_unity((u32)__builtin_ctzll(air.n));
@@ -309,13 +402,14 @@ struct StageTimer {
     void mark(const char* name) { if (!on) return; double t = omp_get_wtime(); fprintf(stderr, "[oracle] %-26s %9.3f ms\n", name, (t - t0) * 1e3); t0 = t; }
 };
 
-static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/) {
+static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[w][n]*/, AuxBuilder aux_builder = nullptr,
+                                  void* aux_user = nullptr) {
     StageTimer tm;
     const Opts& o = air.o;
     const int h = o.hash_id;
     Field F{(int)o.ext};
     const int d = F.d;
-    const size_t n = air.n, N = air.lde_size(), c = air.width(), b = o.blowup;
+    const size_t n = air.n, N = air.lde_size(), c = air.width(), b = o.blowup, aw = air.aw;
     // channel (prover/src/channel.rs:57-82)
     std::vector<u64> seed = context_elements(air);
     for (u64 r : air.pub_inputs) seed.push_back(r);
@@ -333,12 +427,39 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
     commitments.bytes(t_nodes.data() + 32, 32);
     coin.reseed(t_nodes.data() + 32);
 
+    // 1b. auxiliary segment (lib.rs:309-349, air/src/air/mod.rs:292-306, trace_lde/default/mod.rs:140-166)
+    std::vector<EE> rnd;
+    std::vector<u64> apolys, alde;
+    std::vector<u8> a_leaves, a_nodes;
+    if (aw) {
+        for (size_t i = 0; i < air.nr; i++) rnd.push_back(coin.draw(F));
+        std::vector<u64> rw(air.nr * d);
+        for (size_t i = 0; i < air.nr; i++) for (int k = 0; k < d; k++) rw[i * d + k] = rnd[i].v[k];
+        apolys.assign(aw * n * d, 0);
+        if (!aux_builder || aux_builder(aux_user, rw.data(), apolys.data())) abort();
+        interpolate_columns(apolys.data(), aw, n, d);
+        alde.resize(N * aw * d);
+        lde_rows(apolys.data(), aw, n, d, b, alde.data());
+        a_leaves.resize(N * 32); a_nodes.resize(N * 32);
+        hash_rows(h, alde.data(), N, aw * d, aw * d, a_leaves.data());
+        merkle_nodes(h, a_leaves.data(), N, a_nodes.data());
+        commitments.bytes(a_nodes.data() + 32, 32);
+        coin.reseed(a_nodes.data() + 32);
+    }
+
     tm.mark("trace_commit");
     // 2. constraint evaluation (evaluator/default.rs:60-118, evaluation_table.rs:163-407)
     std::vector<EE> ccoef = coin.draw_coeffs(F, (int)o.batch_c, air.num_transition() + air.num_assertions());
-    std::vector<EE> tcoef(ccoef.begin(), ccoef.begin() + air.num_transition());
-    std::vector<EE> bcoef(ccoef.begin() + air.num_transition(), ccoef.end());
+    const size_t nTm = air.num_main_transition(), nT = air.num_transition();
+    std::vector<EE> tcoef(ccoef.begin(), ccoef.begin() + nTm);          // transition/mod.rs:63-72 split
+    std::vector<EE> tcoef_aux(ccoef.begin() + nTm, ccoef.begin() + nT);
+    std::vector<EE> bcoef(ccoef.begin() + nT, ccoef.begin() + nT + air.asserts.size());  // boundary/mod.rs:108-110
     auto groups = boundary_groups(air, bcoef);
+    auto aux_groups = aux_boundary_groups(air, ccoef.data() + nT + air.asserts.size());
+    auto e_sub = [&](const EE& x, const EE& y) { return F.sub(x, y); };
+    auto e_add = [&](const EE& x, const EE& y) { return F.add(x, y); };
+    auto e_mul = [&](const EE& x, const EE& y) { return F.mul(x, y); };
+    auto e_fb = [&](u64 v) { return F.from_base(v); };
     const size_t ce = n * air.ce_blowup();
     const size_t lde_shift = (size_t)__builtin_ctzll(b / air.ce_blowup());
     const u64 g_ce = root_of_unity((u32)__builtin_ctzll(ce));
@@ -360,7 +481,8 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
     std::vector<EE> comp(ce);
 #pragma omp parallel
     {
-        std::vector<u64> tev(air.num_transition()), per(ptab.size());
+        std::vector<u64> tev(nTm), per(ptab.size());
+        std::vector<EE> mc(c), mn(c), ac(aw), an(aw), pe(ptab.size()), aev(tcoef_aux.size());
 #pragma omp for schedule(static)
         for (size_t i = 0; i < ce; i++) {
             size_t ls = i << lde_shift;
@@ -371,6 +493,20 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
             air.eval_transition(cur, nxt, per.data(), tev.data(), f_sub, f_add, f_mul, [](u64 v) { return v; });
             EE t = F.zero();
             for (size_t j = 0; j < tev.size(); j++) t = F.add(t, F.mul_base(tcoef[j], tev[j]));
+            if (aw) {  // evaluator/default.rs:306-341 evaluate_aux_transition
+                const u64* ar = &alde[ls * aw * d];
+                const u64* arn = &alde[((ls + b) % N) * aw * d];
+                for (size_t j = 0; j < c; j++) { mc[j] = F.from_base(cur[j]); mn[j] = F.from_base(nxt[j]); }
+                for (size_t j = 0; j < aw; j++) {
+                    ac[j] = F.zero(); an[j] = F.zero();
+                    for (int k = 0; k < d; k++) { ac[j].v[k] = ar[j * d + k]; an[j].v[k] = arn[j * d + k]; }
+                }
+                for (size_t j = 0; j < per.size(); j++) pe[j] = F.from_base(per[j]);
+                std::fill(aev.begin(), aev.end(), F.zero());
+                air.eval_aux_transition(mc.data(), mn.data(), ac.data(), an.data(), pe.data(), rnd.data(), aev.data(), e_sub, e_add,
+                                        e_mul, e_fb);
+                for (size_t j = 0; j < aev.size(); j++) t = F.add(t, F.mul(aev[j], tcoef_aux[j]));
+            }
             u64 x = f_mul(f_exp(g_ce, i), GENERATOR);                  // domain.rs get_ce_x_at
             u64 zt = f_inv(f_sub(f_exp(x, n), 1));                     // 1 / (x^n - 1)
             u64 ex = 1;
@@ -381,6 +517,11 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
                 for (size_t q = 0; q < G.cols.size(); q++)             // evaluator/boundary.rs SingleValueConstraint
                     bsum = F.add(bsum, F.mul_base(G.cc[q], f_sub(cur[G.cols[q]], G.values[q])));
                 acc = F.add(acc, F.mul_base(bsum, f_inv(f_sub(f_exp(x, G.a), G.b))));  // :329-340
+            }
+            for (auto& G : aux_groups) {  // evaluator/boundary.rs:228-260 aux_single_value
+                EE bsum = F.zero();
+                for (size_t q = 0; q < G.cols.size(); q++) bsum = F.add(bsum, F.mul(F.sub(ac[G.cols[q]], G.values[q]), G.cc[q]));
+                acc = F.add(acc, F.mul_base(bsum, f_inv(f_sub(f_exp(x, G.a), G.b))));
             }
             comp[i] = acc;
         }
@@ -404,15 +545,21 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
     // 4. OOD frame (lib.rs:392-401, poly_table.rs:68-76, composition_poly.rs:101-108, channel.rs:102-113)
     EE z = coin.draw(F);
     EE zg = F.mul_base(z, g_tr);
-    std::vector<EE> t_cur(c), t_nxt(c), q_cur(kc), q_nxt(kc);
+    const size_t ct = c + aw;  // main columns then aux columns (ood_frame.rs:40-72)
+    std::vector<EE> t_cur(ct), t_nxt(ct), q_cur(kc), q_nxt(kc);
     for (size_t j = 0; j < c; j++) { t_cur[j] = horner_base(F, &polys[j * n], n, z); t_nxt[j] = horner_base(F, &polys[j * n], n, zg); }
+    for (size_t j = 0; j < aw; j++) {
+        std::vector<EE> pe(n);
+        for (size_t i = 0; i < n; i++) { pe[i] = F.zero(); for (int k = 0; k < d; k++) pe[i].v[k] = apolys[(j * n + i) * d + k]; }
+        t_cur[c + j] = horner_ext(F, pe.data(), n, z); t_nxt[c + j] = horner_ext(F, pe.data(), n, zg);
+    }
     for (size_t j = 0; j < kc; j++) {
         std::vector<EE> pe(n);
         for (size_t i = 0; i < n; i++) { pe[i] = F.zero(); for (int k = 0; k < d; k++) pe[i].v[k] = cpolys[(j * n + i) * d + k]; }
         q_cur[j] = horner_ext(F, pe.data(), n, z); q_nxt[j] = horner_ext(F, pe.data(), n, zg);
     }
     Writer ood_t, ood_q;
-    ood_t.u8_(2); ood_t.elems(F, t_cur.data(), c); ood_t.elems(F, t_nxt.data(), c);   // ood_frame.rs:59-72
+    ood_t.u8_(2); ood_t.elems(F, t_cur.data(), ct); ood_t.elems(F, t_nxt.data(), ct); // ood_frame.rs:59-72
     ood_q.u8_(2); ood_q.elems(F, q_cur.data(), kc); ood_q.elems(F, q_nxt.data(), kc); // :95-108
     {
         std::vector<u64> m;  // merge_ood_evaluations ood_frame.rs:335-349
@@ -424,7 +571,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
     }
     tm.mark("ood_frames");
     // 5. DEEP composition polynomial, coefficient form (composer/mod.rs:67-210)
-    std::vector<EE> dcoef = coin.draw_coeffs(F, (int)o.batch_d, c + kc);
+    std::vector<EE> dcoef = coin.draw_coeffs(F, (int)o.batch_d, ct + kc);
     std::vector<EE> comp_z(n, F.zero()), comp_gz(n, F.zero());
     for (size_t j = 0; j < c; j++) {  // acc_trace_poly: mul_acc + constant term
         for (size_t i = 0; i < n; i++) {
@@ -434,14 +581,23 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
         comp_z[0] = F.sub(comp_z[0], F.mul(t_cur[j], dcoef[j]));
         comp_gz[0] = F.sub(comp_gz[0], F.mul(t_nxt[j], dcoef[j]));
     }
-    for (size_t j = 0; j < kc; j++) {
+    for (size_t j = 0; j < aw; j++) {  // composer/mod.rs:100-125 aux trace polys, acc_trace_poly::<E, E>
         for (size_t i = 0; i < n; i++) {
-            EE pe = F.zero(); for (int k = 0; k < d; k++) pe.v[k] = cpolys[(j * n + i) * d + k];
+            EE pe = F.zero(); for (int k = 0; k < d; k++) pe.v[k] = apolys[(j * n + i) * d + k];
             EE t = F.mul(pe, dcoef[c + j]);
             comp_z[i] = F.add(comp_z[i], t); comp_gz[i] = F.add(comp_gz[i], t);
         }
-        comp_z[0] = F.sub(comp_z[0], F.mul(q_cur[j], dcoef[c + j]));
-        comp_gz[0] = F.sub(comp_gz[0], F.mul(q_nxt[j], dcoef[c + j]));
+        comp_z[0] = F.sub(comp_z[0], F.mul(t_cur[c + j], dcoef[c + j]));
+        comp_gz[0] = F.sub(comp_gz[0], F.mul(t_nxt[c + j], dcoef[c + j]));
+    }
+    for (size_t j = 0; j < kc; j++) {
+        for (size_t i = 0; i < n; i++) {
+            EE pe = F.zero(); for (int k = 0; k < d; k++) pe.v[k] = cpolys[(j * n + i) * d + k];
+            EE t = F.mul(pe, dcoef[ct + j]);
+            comp_z[i] = F.add(comp_z[i], t); comp_gz[i] = F.add(comp_gz[i], t);
+        }
+        comp_z[0] = F.sub(comp_z[0], F.mul(q_cur[j], dcoef[ct + j]));
+        comp_gz[0] = F.sub(comp_gz[0], F.mul(q_nxt[j], dcoef[ct + j]));
     }
     auto syn_div = [&](std::vector<EE>& p, const EE& bb) {  // polynom/mod.rs:498-505 (a == 1)
         EE cc = F.zero();
@@ -504,7 +660,8 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[2k][n]*/
     write_context(w, air);
     w.u8_((u8)pos.size());
     w.u16_((uint16_t)commitments.b.size()); w.bytes(commitments.b.data(), commitments.b.size());
-    queries_for(F, h, lde.data(), c, t_leaves, t_nodes, N, pos, w);          // trace queries (1 segment)
+    queries_for(F, h, lde.data(), c, t_leaves, t_nodes, N, pos, w);          // trace queries: main segment
+    if (aw) queries_for(F, h, alde.data(), aw * d, a_leaves, a_nodes, N, pos, w);  // aux segment (trace_lde/default/mod.rs:199-218)
     queries_for(F, h, clde.data(), kc * d, c_leaves, c_nodes, N, pos, w);    // constraint queries
     w.u16_((uint16_t)ood_t.b.size()); w.bytes(ood_t.b.data(), ood_t.b.size());
     w.u16_((uint16_t)ood_q.b.size()); w.bytes(ood_q.b.data(), ood_q.b.size());
@@ -650,7 +807,7 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
     r.take(meta);
     u8 ml = r.u8_();
     const u8* mod = r.take(ml);
-    if (!r.ok || ml != 8 || memcmp(mod, &P, 8) || aw || ar) return V_CONTEXT;
+    if (!r.ok || ml != 8 || memcmp(mod, &P, 8) || aw != air.aw || ar != air.nr) return V_CONTEXT;
     Opts o = air.o;
     o.num_queries = r.u8_(); o.blowup = r.u8_(); o.grinding = r.u8_(); o.ext = r.u8_(); o.folding = r.u8_();
     o.rem_max_deg = r.u8_(); o.batch_c = r.u8_(); o.batch_d = r.u8_(); o.num_partitions = r.u8_(); o.hash_rate = r.u8_();
@@ -666,29 +823,31 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
     const int h = o.hash_id;
     Field F{(int)o.ext};
     const int d = F.d;
-    const size_t n = air.n, N = air.lde_size(), c = air.width(), kc = air.num_comp_cols(), nf = o.folding;
+    const size_t n = air.n, N = air.lde_size(), c = air.width(), kc = air.num_comp_cols(), nf = o.folding, ct = c + air.aw;
+    const size_t nseg = air.aw ? 2 : 1;
     u8 nuq = r.u8_();
     u64 clen = r.le(2);
     const u8* cm = r.take(clen);
     if (!r.ok) return V_MALFORMED;
     size_t nlayers = 0;
     { size_t dom = N, max_rem = (size_t)(o.rem_max_deg + 1) * o.blowup; while (dom > max_rem) { dom /= nf; nlayers++; } }
-    if (clen != 32 * (2 + nlayers + 1)) return V_MALFORMED;
-    const u8* trace_root = cm; const u8* cons_root = cm + 32; const u8* fri_roots = cm + 64;
+    if (clen != 32 * (nseg + 1 + nlayers + 1)) return V_MALFORMED;
+    const u8* trace_root = cm; const u8* aux_root = cm + 32;  // air/src/proof/commitments.rs:66-100
+    const u8* cons_root = cm + 32 * nseg; const u8* fri_roots = cm + 32 * (nseg + 1);
     // queries
     auto read_q = [&](std::vector<u8>& vals, std::vector<u8>& pr) {
         u64 vl = r.usize(); const u8* v = r.take(vl); if (!r.ok) return false; vals.assign(v, v + vl);
         u64 pl = r.usize(); const u8* p2 = r.take(pl); if (!r.ok) return false; pr.assign(p2, p2 + pl);
         return true;
     };
-    std::vector<u8> tq_vals, tq_pr, cq_vals, cq_pr;
-    if (!read_q(tq_vals, tq_pr) || !read_q(cq_vals, cq_pr)) return V_MALFORMED;
+    std::vector<u8> tq_vals, tq_pr, aq_vals, aq_pr, cq_vals, cq_pr;
+    if (!read_q(tq_vals, tq_pr) || (air.aw && !read_q(aq_vals, aq_pr)) || !read_q(cq_vals, cq_pr)) return V_MALFORMED;
     u64 otl = r.le(2); const u8* ot = r.take(otl);
     u64 oql = r.le(2); const u8* oq = r.take(oql);
-    if (!r.ok || otl != 1 + 2 * c * d * 8 || oql != 1 + 2 * kc * d * 8 || ot[0] != 2 || oq[0] != 2) return V_MALFORMED;
+    if (!r.ok || otl != 1 + 2 * ct * d * 8 || oql != 1 + 2 * kc * d * 8 || ot[0] != 2 || oq[0] != 2) return V_MALFORMED;
     auto rd = [&](const u8* p, size_t idx) { EE e = F.zero(); memcpy(e.v, p + idx * d * 8, d * 8); return e; };
-    std::vector<EE> t_cur(c), t_nxt(c), q_cur(kc), q_nxt(kc);
-    for (size_t j = 0; j < c; j++) { t_cur[j] = rd(ot + 1, j); t_nxt[j] = rd(ot + 1, c + j); }
+    std::vector<EE> t_cur(ct), t_nxt(ct), q_cur(kc), q_nxt(kc);
+    for (size_t j = 0; j < ct; j++) { t_cur[j] = rd(ot + 1, j); t_nxt[j] = rd(ot + 1, ct + j); }
     for (size_t j = 0; j < kc; j++) { q_cur[j] = rd(oq + 1, j); q_nxt[j] = rd(oq + 1, kc + j); }
     // FRI proof
     u8 fl = r.u8_();
@@ -708,20 +867,31 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
     for (u64 x : air.pub_inputs) seed.push_back(x);
     Coin coin(h, seed);
     coin.reseed(trace_root);
+    std::vector<EE> rnd;
+    if (air.aw) {  // verifier/src/lib.rs:170-184
+        for (size_t i = 0; i < air.nr; i++) rnd.push_back(coin.draw(F));
+        coin.reseed(aux_root);
+    }
     std::vector<EE> ccoef = coin.draw_coeffs(F, (int)o.batch_c, air.num_transition() + air.num_assertions());
     coin.reseed(cons_root);
     EE z = coin.draw(F);
     // OOD consistency (verifier/src/evaluator.rs:15-80)
     {
-        std::vector<EE> tcoef(ccoef.begin(), ccoef.begin() + air.num_transition());
-        std::vector<EE> bcoef(ccoef.begin() + air.num_transition(), ccoef.end());
-        std::vector<EE> tev(air.num_transition(), F.zero());
+        const size_t nTm = air.num_main_transition(), nT = air.num_transition();
+        std::vector<EE> tcoef(ccoef.begin(), ccoef.begin() + nT);
+        std::vector<EE> bcoef(ccoef.begin() + nT, ccoef.begin() + nT + air.asserts.size());
+        std::vector<EE> tev(nT, F.zero());
         // periodic values at z: poly_j(z^(n/L_j)) (verifier/src/evaluator.rs:27-35)
         std::vector<EE> per;
         for (auto& poly : air.periodic_polys()) per.push_back(horner_base(F, poly.data(), poly.size(), F.exp(z, n / poly.size())));
         air.eval_transition(t_cur.data(), t_nxt.data(), per.data(), tev.data(),
                             [&](const EE& a, const EE& b) { return F.sub(a, b); }, [&](const EE& a, const EE& b) { return F.add(a, b); },
                             [&](const EE& a, const EE& b) { return F.mul(a, b); }, [&](u64 v) { return F.from_base(v); });
+        if (air.aw)  // verifier/src/evaluator.rs:43-57
+            air.eval_aux_transition(t_cur.data(), t_nxt.data(), t_cur.data() + c, t_nxt.data() + c, per.data(), rnd.data(),
+                                    tev.data() + nTm, [&](const EE& a, const EE& b) { return F.sub(a, b); },
+                                    [&](const EE& a, const EE& b) { return F.add(a, b); },
+                                    [&](const EE& a, const EE& b) { return F.mul(a, b); }, [&](u64 v) { return F.from_base(v); });
         EE t = F.zero();
         for (size_t j = 0; j < tev.size(); j++) t = F.add(t, F.mul(tcoef[j], tev[j]));
         // transition divisor (x^n - 1) / prod (x - exemption) at z (transition/mod.rs:153-174, divisor.rs:79-100)
@@ -733,6 +903,11 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
             EE bs = F.zero();
             for (size_t q = 0; q < G.cols.size(); q++)
                 bs = F.add(bs, F.mul(F.sub(t_cur[G.cols[q]], F.from_base(G.values[q])), G.cc[q]));
+            res = F.add(res, F.mul(bs, F.inv(F.sub(F.exp(z, G.a), F.from_base(G.b)))));
+        }
+        for (auto& G : aux_boundary_groups(air, ccoef.data() + nT + air.asserts.size())) {  // evaluator.rs:76-83
+            EE bs = F.zero();
+            for (size_t q = 0; q < G.cols.size(); q++) bs = F.add(bs, F.mul(F.sub(t_cur[c + G.cols[q]], G.values[q]), G.cc[q]));
             res = F.add(res, F.mul(bs, F.inv(F.sub(F.exp(z, G.a), F.from_base(G.b)))));
         }
         EE res2 = F.zero();
@@ -747,7 +922,7 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
         hash_elements(h, m.data(), m.size(), dg);
         coin.reseed(dg);
     }
-    std::vector<EE> dcoef = coin.draw_coeffs(F, (int)o.batch_d, c + kc);
+    std::vector<EE> dcoef = coin.draw_coeffs(F, (int)o.batch_d, ct + kc);
     // FriVerifier::new (fri/src/verifier/mod.rs:48-90): reseed + draw for every commitment incl. remainder
     std::vector<EE> alphas;
     for (size_t i = 0; i <= nlayers; i++) { coin.reseed(fri_roots + 32 * i); alphas.push_back(coin.draw(F)); }
@@ -769,6 +944,7 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
         return batch_root(h, bp, pos, lv, got) && !memcmp(got, root, 32);
     };
     if (!check_q(tq_vals, tq_pr, c, trace_root)) return V_TRACE_QUERY;
+    if (air.aw && !check_q(aq_vals, aq_pr, air.aw * d, aux_root)) return V_TRACE_QUERY;  // channel.rs:206-240
     if (!check_q(cq_vals, cq_pr, kc * d, cons_root)) return V_CONSTRAINT_QUERY;
     // DEEP composition at the query positions (verifier/src/composer.rs)
     u64 g_lde = root_of_unity((u32)__builtin_ctzll(N)), g_tr = root_of_unity((u32)__builtin_ctzll(n));
@@ -784,10 +960,15 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
             t1 = F.add(t1, F.mul(F.sub(v, t_cur[j]), dcoef[j]));
             t2 = F.add(t2, F.mul(F.sub(v, t_nxt[j]), dcoef[j]));
         }
+        for (size_t j = 0; j < air.aw; j++) {  // composer.rs:103-130
+            EE v = F.zero(); memcpy(v.v, aq_vals.data() + (qi * air.aw + j) * d * 8, d * 8);
+            t1 = F.add(t1, F.mul(F.sub(v, t_cur[c + j]), dcoef[c + j]));
+            t2 = F.add(t2, F.mul(F.sub(v, t_nxt[c + j]), dcoef[c + j]));
+        }
         for (size_t j = 0; j < kc; j++) {
             EE v = F.zero(); memcpy(v.v, crow + j * d, d * 8);
-            t1 = F.add(t1, F.mul(F.sub(v, q_cur[j]), dcoef[c + j]));
-            t2 = F.add(t2, F.mul(F.sub(v, q_nxt[j]), dcoef[c + j]));
+            t1 = F.add(t1, F.mul(F.sub(v, q_cur[j]), dcoef[ct + j]));
+            t2 = F.add(t2, F.mul(F.sub(v, q_nxt[j]), dcoef[ct + j]));
         }
         EE d1 = F.sub(x, z), d2 = F.sub(x, zg);
         evals[qi] = F.mul(F.add(F.mul(t1, d2), F.mul(t2, d1)), F.inv(F.mul(d1, d2)));
@@ -895,7 +1076,19 @@ long wfo_prove_air(const uint64_t* desc, size_t desc_len, const uint64_t* trace,
     Air air;
     if (!parse_air(desc, desc_len, air)) return -2;
     air.n = n; air.o = make_opts(opts);
+    if (air.aw) return -3;  // multi-segment AIRs go through wfo_prove_air_aux
     std::vector<u8> p = prove_fib(air, trace);
+    if (p.size() > cap) return -1;
+    memcpy(out, p.data(), p.size());
+    return (long)p.size();
+}
+// multi-segment AIR: `builder` fills the aux columns [aw][n][d] from the drawn random elements [nr][d]
+long wfo_prove_air_aux(const uint64_t* desc, size_t desc_len, const uint64_t* trace, size_t n, const uint32_t* opts,
+                       int (*builder)(void*, const uint64_t*, uint64_t*), void* user, uint8_t* out, size_t cap) {
+    Air air;
+    if (!parse_air(desc, desc_len, air)) return -2;
+    air.n = n; air.o = make_opts(opts);
+    std::vector<u8> p = prove_fib(air, trace, builder, user);
     if (p.size() > cap) return -1;
     memcpy(out, p.data(), p.size());
     return (long)p.size();

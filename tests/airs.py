@@ -47,7 +47,19 @@ class AirBuilder:
     def assert_single(self, column, step, value): self.asserts.append((column, step, 0, int(value) % P))
     def assert_periodic(self, column, first_step, stride, value): self.asserts.append((column, first_step, stride, int(value) % P))
 
+    def aux(self, aux_width, num_rands):
+        """Declares the auxiliary segment; returns the builder for its constraint program."""
+        self.aux_seg = AuxSegment(self, aux_width, num_rands)
+        return self.aux_seg
+
     def build(self):
+        d = self._build_main()
+        seg = getattr(self, "aux_seg", None)
+        if seg is not None:
+            d = np.concatenate([d, seg.build()])
+        return d
+
+    def _build_main(self):
         if self.next_reg is None:
             self.next_reg = 2 * self.w + len(self.periodic)
         d = [self.w, len(self.degrees)]
@@ -65,6 +77,56 @@ class AirBuilder:
             d += list(a)
         d += [len(self.pub)] + [int(v) % P for v in self.pub]
         d.append(self.exemptions)
+        return np.array(d, dtype=np.uint64)
+
+
+class AuxSegment:
+    """Aux-segment constraint program (Air::evaluate_aux_transition, air/src/air/mod.rs:248-260).
+    Registers: main cur/next, aux cur/next, periodic values, random elements, temporaries — all in E."""
+
+    def __init__(self, air, aw, nr):
+        self.air, self.aw, self.nr = air, aw, nr
+        self.degrees, self.prog, self.asserts = [], [], []
+        self.next_reg = 2 * air.w + 2 * aw + len(air.periodic) + nr
+
+    def cur(self, c): return c
+    def nxt(self, c): return self.air.w + c
+    def acur(self, c): return 2 * self.air.w + c
+    def anxt(self, c): return 2 * self.air.w + self.aw + c
+    def per(self, j): return 2 * self.air.w + 2 * self.aw + j
+    def rnd(self, j): return 2 * self.air.w + 2 * self.aw + len(self.air.periodic) + j
+
+    def op(self, code, a, b):
+        d = self.next_reg
+        self.next_reg += 1
+        self.prog.append((code, d, a, b))
+        return d
+
+    def add(self, a, b): return self.op(ADD, a, b)
+    def sub(self, a, b): return self.op(SUB, a, b)
+    def mul(self, a, b): return self.op(MUL, a, b)
+
+    def const(self, v):
+        self.air.consts.append(v % P)
+        return self.op(CONST, len(self.air.consts) - 1, 0)
+
+    def constraint(self, reg, base_degree, cycles=()):
+        self.prog.append((OUT, len(self.degrees), reg, 0))
+        self.degrees.append((base_degree, list(cycles)))
+
+    def assert_single(self, column, step, value=(0, 0, 0)):
+        self.asserts.append((column, step, 0) + tuple(int(v) % P for v in value))
+
+    def build(self):
+        d = [self.aw, self.nr, len(self.degrees)]
+        for base, cyc in self.degrees:
+            d += [base, len(cyc)] + list(cyc)
+        d += [self.next_reg, len(self.prog)]
+        for ins in self.prog:
+            d += list(ins)
+        d.append(len(self.asserts))
+        for a in self.asserts:
+            d += list(a)
         return np.array(d, dtype=np.uint64)
 
 
@@ -140,3 +202,58 @@ def periodic_mix(n, cycle=8):
     A.assert_single(0, n - 1, int(tr[0, n - 1]))
     A.assert_single(1, n - 1, int(tr[1, n - 1]))
     return A.build(), tr
+
+
+def perm_rap(n, seed=5):
+    """Two-segment AIR in the style of examples/src/rescue_raps (a randomised AIR with preprocessing):
+    main columns x0, x1 (the FibSmall pair) and b = a permutation of x0's first n-1 values; the aux
+    segment proves the permutation with a running product and carries a running sum that mixes main
+    columns, a periodic column and both random elements:
+        p' * (b + gamma) = p * (x0 + gamma),   p[0] = p[n-1] = 1
+        q' = q + alpha * k * x1 * p,           q[0] = 0
+    Returns (description, main trace, aux builder(rand [2, d]) -> [2, n, d])."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(seed)
+    tr = np.zeros((3, n), dtype=np.uint64)
+    a = b = 1
+    for i in range(n):
+        tr[0, i], tr[1, i] = a, b
+        a = (a + b) % P
+        b = (b + a) % P
+    perm = rng.permutation(n - 1)
+    tr[2, : n - 1] = tr[0, perm]
+    tr[2, n - 1] = 12345
+    k = [1, 2, 3, 4]
+    A = AirBuilder(3)
+    A.periodic = [k]
+    A.pub = [int(tr[1, n - 1])]
+    A.constraint(A.sub(A.nxt(0), A.add(A.cur(0), A.cur(1))), 1)
+    A.constraint(A.sub(A.nxt(1), A.add(A.cur(1), A.nxt(0))), 1)
+    A.assert_single(0, 0, 1)
+    A.assert_single(1, 0, 1)
+    A.assert_single(1, n - 1, int(tr[1, n - 1]))
+    X = A.aux(2, 2)
+    gamma, alpha = X.rnd(0), X.rnd(1)
+    lhs = X.mul(X.anxt(0), X.add(X.cur(2), gamma))
+    rhs = X.mul(X.acur(0), X.add(X.cur(0), gamma))
+    X.constraint(X.sub(lhs, rhs), 2)
+    term = X.mul(X.mul(alpha, X.per(0)), X.mul(X.cur(1), X.acur(0)))
+    X.constraint(X.sub(X.anxt(1), X.add(X.acur(1), term)), 2, [4])
+    X.assert_single(0, 0, (1, 0, 0))
+    X.assert_single(0, n - 1, (1, 0, 0))
+    X.assert_single(1, 0, (0, 0, 0))
+
+    def builder(rand):
+        d = rand.shape[1]
+        g, al = rand[0], rand[1]
+        emb = lambda v: np.array([int(v)] + [0] * (d - 1), dtype=np.uint64)
+        eadd = lambda x, y: np.array([(int(x[i]) + int(y[i])) % P for i in range(d)], dtype=np.uint64)
+        aux = np.zeros((2, n, d), dtype=np.uint64)
+        p, q = emb(1), emb(0)
+        for i in range(n):
+            aux[0, i], aux[1, i] = p, q
+            q = eadd(q, O.ext_mul(O.ext_mul(al, emb(k[i % 4] * int(tr[1, i]) % P)), p))
+            p = O.ext_mul(O.ext_mul(p, eadd(emb(tr[0, i]), g)), O.ext_inv(eadd(emb(tr[2, i]), g)))
+        return aux
+
+    return A.build(), tr, builder

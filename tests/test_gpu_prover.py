@@ -96,3 +96,38 @@ def test_generic_air_vs_oracle(ctx, oracle, name, log_n, ext, h, batch):
     bad = desc.copy()
     bad[-2] ^= np.uint64(1)  # last public input
     assert oracle.verify_air(bad, got, h) != 0
+
+
+# ---- auxiliary trace segment (wf_prove_air_aux): RAP-style two-segment AIR ----
+@pytest.mark.parametrize("log_n", [6, 10])
+@pytest.mark.parametrize("ext,h,batch", [(1, wf.HASH_BLAKE3_256, 0), (2, wf.HASH_BLAKE3_256, 1), (3, wf.HASH_RP64_256, 2)])
+def test_aux_segment_vs_oracle(ctx, oracle, log_n, ext, h, batch):
+    # the flow of examples/src/rescue_raps (prover/src/lib.rs:309-349): main commit -> draw random elements ->
+    # host builds the aux columns over E -> aux commit -> constraints over both segments
+    desc, trace, builder = airs.perm_rap(1 << log_n)
+    opts = oracle.make_opts(num_queries=24, blowup=8, grinding=2, ext=ext, folding=4, rem_max_deg=7, batch_c=batch, batch_d=batch, hash_id=h)
+    got = ctx.prove_air_aux(desc, trace, opts, builder, 2, 2)
+    assert got == oracle.prove_air_aux(desc, trace, opts, builder, 2, 2)
+    assert oracle.verify_air(desc, got, h) == 0
+    # single-segment entry point refuses a multi-segment description
+    with pytest.raises(wf.WfError):
+        ctx.prove_air(desc, trace, opts)
+
+
+def test_aux_segment_montgomery_io(ctx, oracle):
+    # mont=1: trace, random elements and aux columns all cross the ABI as the reference's Montgomery words
+    desc, trace, builder = airs.perm_rap(64)
+    opts = oracle.make_opts(num_queries=16, blowup=8, ext=2, folding=4, rem_max_deg=7)
+    to_m = np.vectorize(lambda v: oracle.to_mont(int(v)), otypes=[np.uint64])
+    from_m = np.vectorize(lambda v: oracle.from_mont(int(v)), otypes=[np.uint64])
+    got = ctx.prove_air_aux(desc, to_m(trace), opts, lambda r: to_m(builder(from_m(r))), 2, 2, mont=True)
+    assert got == oracle.prove_air_aux(desc, trace, opts, builder, 2, 2)
+
+
+def test_aux_segment_inconsistent_trace_is_rejected(ctx, oracle):
+    desc, trace, builder = airs.perm_rap(128)
+    bad = trace.copy()
+    bad[2, 7] = (int(bad[2, 7]) + 1) % airs.P  # b is no longer a permutation of x0
+    opts = oracle.make_opts(num_queries=16, blowup=8, ext=2, folding=4, rem_max_deg=7)
+    proof = ctx.prove_air_aux(desc, bad, opts, builder, 2, 2)
+    assert oracle.verify_air(desc, proof) != 0

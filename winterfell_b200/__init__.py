@@ -25,6 +25,7 @@ vp = C.c_void_p
 
 FRI_COMMIT_FN = C.CFUNCTYPE(None, C.c_void_p, u8p)
 FRI_DRAW_FN = C.CFUNCTYPE(None, C.c_void_p, u64p)
+AUX_BUILDER = C.CFUNCTYPE(C.c_int, C.c_void_p, u64p, u64p)
 
 _lib = None
 
@@ -67,6 +68,8 @@ _SIGS = [
     ("wf_fri_free", C.c_int, [vp, vp]),
     ("wf_prove_fib", C.c_int, [vp, C.POINTER(u64p), C.c_int, C.c_uint32, C.c_uint32, u64p, C.POINTER(C.c_uint32), u8p, C.POINTER(C.c_size_t)]),
     ("wf_prove_air", C.c_int, [vp, u64p, C.c_size_t, C.POINTER(u64p), C.c_int, C.c_uint32, C.POINTER(C.c_uint32), u8p, C.POINTER(C.c_size_t)]),
+    ("wf_prove_air_aux", C.c_int, [vp, u64p, C.c_size_t, C.POINTER(u64p), C.c_int, C.c_uint32, C.POINTER(C.c_uint32), AUX_BUILDER, vp,
+                                   u8p, C.POINTER(C.c_size_t)]),
     ("wf_prove_fib_dev", C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u64p, C.POINTER(C.c_uint32), u8p, C.POINTER(C.c_size_t)]),
     ("wf_grind", C.c_int, [vp, C.c_int, u8p, C.c_uint32, C.POINTER(C.c_uint64)]),
     ("wf_ntt_dev", C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_int]),
@@ -215,6 +218,37 @@ class Context:
         ln = C.c_size_t(cap)
         self.check(self.L.wf_prove_air(self.h, dp, d_.size, ptrs, int(mont), int(n).bit_length() - 1,
                                        o_.ctypes.data_as(C.POINTER(C.c_uint32)), buf.ctypes.data_as(u8p), C.byref(ln)))
+        return buf[: ln.value].tobytes()
+
+    def prove_air_aux(self, desc, trace, opts, builder, aux_width, num_rands, mont=False):
+        """Multi-segment AIR (wf_prove_air_aux). builder(rand [num_rands, d] uint64) -> aux columns
+        [aux_width, n, d] uint64, called on the host after the main commitment."""
+        d_, dp = _u64(desc)
+        a = np.ascontiguousarray(trace, dtype=np.uint64)
+        c, n = a.shape
+        ptrs = (u64p * c)(*[a[j].ctypes.data_as(u64p) for j in range(c)])
+        o_ = np.ascontiguousarray(opts, dtype=np.uint32)
+        d = int(o_[3])
+
+        def cb(_user, rand_p, out_p):
+            try:
+                rand = (np.ctypeslib.as_array(rand_p, shape=(num_rands, d)).copy() if num_rands
+                        else np.zeros((0, d), dtype=np.uint64))
+                aux = np.ascontiguousarray(builder(rand), dtype=np.uint64).reshape(aux_width, n, d)
+                np.ctypeslib.as_array(out_p, shape=(aux_width, n, d))[:] = aux
+                return 0
+            except Exception:  # must not unwind through the C caller
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        cfn = AUX_BUILDER(cb)
+        cap = 1 << 23
+        buf = np.zeros(cap, dtype=np.uint8)
+        ln = C.c_size_t(cap)
+        self.check(self.L.wf_prove_air_aux(self.h, dp, d_.size, ptrs, int(mont), int(n).bit_length() - 1,
+                                           o_.ctypes.data_as(C.POINTER(C.c_uint32)), cfn, None, buf.ctypes.data_as(u8p),
+                                           C.byref(ln)))
         return buf[: ln.value].tobytes()
 
     def prove_fib_dev(self, d_trace, k, log_n, results, opts, out_buf=None):

@@ -138,8 +138,23 @@ struct GenEvalParams {
     u64 zt[8];             // 1 / (x^n - 1) at CE step i mod ce_blowup
     u64 exempt[8];
     u32 num_exempt;
+    // auxiliary segment (Air::evaluate_aux_transition, air/src/air/mod.rs:248-260): program over E
+    // registers [main cur | main next | aux cur | aux next | periodic | random elements | temporaries]
+    SegMatrix alde;        // N x aw*D
+    u32 aw, nr, aprog_len, num_agroups;
+    const u32* aprog;
+    const u64* rnd;        // [nr][D]
+    const u64* atcoef;     // [aux constraints][D]
+    const u32* ag_off;     // aux boundary groups (air/src/air/boundary/mod.rs:121-128)
+    const u64* ag_a;
+    const u64* ag_b;
+    const u64* ag_oa;
+    const u32* ae_col;
+    const u64* ae_val;     // [entries][D]
+    const u64* ae_cc;      // [entries][D]
 };
-template <int D>
+#define AUX_MAX_REGS 96
+template <int D, bool AUX>
 __global__ void __launch_bounds__(128) generic_constraints_kernel(GenEvalParams p) {
     const size_t ce = (size_t)1 << (p.log_n + p.log_ce_blowup);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,6 +176,30 @@ __global__ void __launch_bounds__(128) generic_constraints_kernel(GenEvalParams 
             default: T = ext_add(T, ext_mul_base(ld_ext<D>(p.tcoef + (size_t)dst * D), r[a])); break;  // OUT
         }
     }
+    GlExt<D> ra[AUX ? AUX_MAX_REGS : 1];
+    if constexpr (AUX) {  // evaluator/default.rs:306-341 evaluate_aux_transition
+        for (u32 c = 0; c < 2 * p.w; c++) ra[c] = ext_from_base<D>(r[c]);
+        for (u32 j = 0; j < p.aw; j++) {
+#pragma unroll
+            for (int q = 0; q < D; q++) {
+                ra[2 * p.w + j].v[q] = seg_at(p.alde, ls, j * D + q);
+                ra[2 * p.w + p.aw + j].v[q] = seg_at(p.alde, nx, j * D + q);
+            }
+        }
+        const u32 pb = 2 * p.w + 2 * p.aw;
+        for (u32 j = 0; j < p.num_periodic; j++) ra[pb + j] = ext_from_base<D>(r[2 * p.w + j]);
+        for (u32 j = 0; j < p.nr; j++) ra[pb + p.num_periodic + j] = ld_ext<D>(p.rnd + (size_t)j * D);
+        for (u32 k = 0; k < p.aprog_len; k++) {
+            const u32 op = p.aprog[4 * k], dst = p.aprog[4 * k + 1], a = p.aprog[4 * k + 2], b = p.aprog[4 * k + 3];
+            switch (op) {
+                case 0: ra[dst] = ext_add(ra[a], ra[b]); break;
+                case 1: ra[dst] = ext_sub(ra[a], ra[b]); break;
+                case 2: ra[dst] = ext_mul(ra[a], ra[b]); break;
+                case 3: ra[dst] = ext_from_base<D>(p.consts[a]); break;
+                default: T = ext_add(T, ext_mul(ra[a], ld_ext<D>(p.atcoef + (size_t)dst * D))); break;  // OUT
+            }
+        }
+    }
     const u32 half = (u32)(ce >> 1);
     const u32 cemask = (u32)(ce - 1);
     u64 w = p.tw_ce[i & (half - 1)];
@@ -179,6 +218,18 @@ __global__ void __launch_bounds__(128) generic_constraints_kernel(GenEvalParams 
         if (ia & half) wa = gl_neg(wa);
         u64 den = gl_sub(gl_mul(wa, p.g_oa[g]), p.g_b[g]);
         acc = ext_add(acc, ext_mul_base(B, gl_inv(den)));
+    }
+    if constexpr (AUX) {  // evaluator/boundary.rs: aux_single_value constraints, values and columns in E
+        for (u32 g = 0; g < p.num_agroups; g++) {
+            GlExt<D> B = ext_zero<D>();
+            for (u32 e = p.ag_off[g]; e < p.ag_off[g + 1]; e++)
+                B = ext_add(B, ext_mul(ext_sub(ra[2 * p.w + p.ae_col[e]], ld_ext<D>(p.ae_val + (size_t)e * D)), ld_ext<D>(p.ae_cc + (size_t)e * D)));
+            u32 ia = (u32)(((u64)i * p.ag_a[g]) & cemask);
+            u64 wa = p.tw_ce[ia & (half - 1)];
+            if (ia & half) wa = gl_neg(wa);
+            u64 den = gl_sub(gl_mul(wa, p.ag_oa[g]), p.ag_b[g]);
+            acc = ext_add(acc, ext_mul_base(B, gl_inv(den)));
+        }
     }
     u64* o = p.out.base + i * p.out.W;
 #pragma unroll
@@ -267,7 +318,9 @@ struct DeepParams {
     SegMatrix trace;   // N x c
     SegMatrix cons;    // N x kc*D
     SegMatrix out;     // N x D
-    u32 c, kc, log_N;
+    SegMatrix aux;     // N x aw*D (aux segment LDE; aw == 0 when single-segment)
+    u32 c, kc, log_N, aw;
+    const u64* acc;    // [aw][D] DEEP coefficients for aux columns (composer/mod.rs:100-125)
     const u64* tcc;    // [c][D]  DEEP coefficients for trace columns
     const u64* ccc;    // [kc][D] DEEP coefficients for composition columns
     const u64* tw_N;   // w_N^i, i < N/2
@@ -305,6 +358,12 @@ __global__ void __launch_bounds__(256) deep_eval_kernel(DeepParams p, GlExt<D> z
             }
         } else {
             for (u32 j = 0; j < p.c; j++) S[r] = ext_add(S[r], ext_mul_base(ld_ext<D>(p.tcc + (size_t)j * D), seg_at(p.trace, row, j)));
+        }
+        for (u32 j = 0; j < p.aw; j++) {
+            GlExt<D> av;
+#pragma unroll
+            for (int q = 0; q < D; q++) av.v[q] = seg_at(p.aux, row, j * D + q);
+            S[r] = ext_add(S[r], ext_mul(ld_ext<D>(p.acc + (size_t)j * D), av));
         }
         for (u32 j = 0; j < p.kc; j++) {
             GlExt<D> hv;
@@ -412,8 +471,17 @@ struct Options {
 // Host-side AIR description (mirrors oracle/wf_prover.cpp `Air`; flat format documented at
 // wf_prove_air in include/winterfell_b200.h)
 struct AirAssertion { u64 column, first_step, stride, value; };
+struct AuxAssertion { u64 column, first_step, stride, value[3]; };
 struct AirHost {
     u32 w = 0;
+    // auxiliary segment (air/src/air/trace_info.rs:24-40): aw columns over E, nr random elements
+    u32 aw = 0, nr = 0, aux_num_regs = 0;
+    std::vector<std::pair<u32, std::vector<u32>>> aux_degrees;
+    std::vector<u32> aux_prog;
+    std::vector<AuxAssertion> aux_asserts;
+    std::vector<std::pair<u32, std::vector<u32>>> all_degrees() const {  // context.rs:268-271
+        auto r = degrees; r.insert(r.end(), aux_degrees.begin(), aux_degrees.end()); return r;
+    }
     std::vector<u64> pub_inputs;
     std::vector<std::pair<u32, std::vector<u32>>> degrees;
     std::vector<std::vector<u64>> periodic;
@@ -427,7 +495,7 @@ struct AirHost {
     std::vector<u64> fib_results;
     u32 log_ce_blowup() const {  // air/src/air/context.rs:87-100, transition/degree.rs min_blowup_factor
         u32 r = 1;
-        for (auto& dg : degrees) {
+        for (auto& dg : all_degrees()) {
             u32 bound = dg.first + (u32)dg.second.size() - 1, l = 0;
             while ((1u << l) < bound) l++;
             r = std::max(r, std::max(l, 1u));
@@ -436,13 +504,22 @@ struct AirHost {
     }
     u32 num_comp_cols(size_t n) const {  // context.rs:265-285
         size_t hi = 0;
-        for (auto& dg : degrees) {
+        for (auto& dg : all_degrees()) {
             size_t e = (size_t)dg.first * (n - 1);
             for (u32 cyc : dg.second) e += (n / cyc) * (cyc - 1);
             hi = std::max(hi, e);
         }
         size_t div = n - exemptions;
         return (u32)std::max((hi - div + n - 1) / n, (size_t)1);
+    }
+    std::vector<AuxAssertion> sorted_aux_assertions() const {
+        std::vector<AuxAssertion> a = aux_asserts;
+        std::stable_sort(a.begin(), a.end(), [](const AuxAssertion& x, const AuxAssertion& y) {
+            if (x.stride != y.stride) return x.stride < y.stride;
+            if (x.first_step != y.first_step) return x.first_step < y.first_step;
+            return x.column < y.column;
+        });
+        return a;
     }
     std::vector<AirAssertion> sorted_assertions() const {  // assertions/mod.rs:301-315
         std::vector<AirAssertion> a = asserts;
@@ -498,9 +575,10 @@ static bool parse_air_host(const u64* d, size_t len, AirHost& a) {
     for (u64 i = 0; i < cnt; i++) {
         u64 op, ds, x, y;
         if (!rd(op) || !rd(ds) || !rd(x) || !rd(y) || op > 4) return false;
+        const u64 first_tmp = 2 * a.w + a.periodic.size();  // inputs are read-only: boundary terms re-read them
         if (op == 4) { if (ds >= a.degrees.size() || x >= a.num_regs) return false; }
-        else if (op == 3) { if (ds >= a.num_regs || x >= a.consts.size()) return false; }
-        else if (ds >= a.num_regs || x >= a.num_regs || y >= a.num_regs) return false;
+        else if (op == 3) { if (ds >= a.num_regs || ds < first_tmp || x >= a.consts.size()) return false; }
+        else if (ds >= a.num_regs || ds < first_tmp || x >= a.num_regs || y >= a.num_regs) return false;
         a.prog.insert(a.prog.end(), {(u32)op, (u32)ds, (u32)x, (u32)y});
     }
     if (!rd(cnt) || cnt == 0) return false;
@@ -513,6 +591,41 @@ static bool parse_air_host(const u64* d, size_t len, AirHost& a) {
     for (u64 i = 0; i < cnt; i++) { if (!rd(v) || v >= GL_P) return false; a.pub_inputs.push_back(v); }
     if (!rd(v) || v == 0 || v > 8) return false;
     a.exemptions = (u32)v;
+    if (p == len) return true;
+    // optional aux section: [aw, nr, nTa, {base, ncyc, cyc...}*, aux_num_regs, nIa, {op,dst,a,b}*,
+    //                        nAa, {column, first_step, stride, v0, v1, v2}*]
+    if (!rd(v) || v == 0 || v > 255) return false;
+    a.aw = (u32)v;
+    if (!rd(v) || v > 255) return false;
+    a.nr = (u32)v;
+    if (!rd(cnt) || cnt == 0 || cnt > 4096) return false;   // context.rs:104-113
+    for (u64 i = 0; i < cnt; i++) {
+        u64 base, nc;
+        if (!rd(base) || !rd(nc) || base == 0 || nc > 16) return false;
+        std::vector<u32> cyc;
+        for (u64 j = 0; j < nc; j++) { if (!rd(v)) return false; cyc.push_back((u32)v); }
+        a.aux_degrees.push_back({(u32)base, cyc});
+    }
+    const u64 first_tmp = 2 * a.w + 2 * a.aw + a.periodic.size() + a.nr;
+    if (!rd(v) || v > AUX_MAX_REGS || v < first_tmp) return false;
+    a.aux_num_regs = (u32)v;
+    if (!rd(cnt) || cnt > (1u << 20)) return false;
+    for (u64 i = 0; i < cnt; i++) {
+        u64 op, ds, x, y;
+        if (!rd(op) || !rd(ds) || !rd(x) || !rd(y) || op > 4) return false;
+        if (op == 4) { if (ds >= a.aux_degrees.size() || x >= a.aux_num_regs) return false; }
+        else if (op == 3) { if (ds >= a.aux_num_regs || ds < first_tmp || x >= a.consts.size()) return false; }
+        else if (ds >= a.aux_num_regs || ds < first_tmp || x >= a.aux_num_regs || y >= a.aux_num_regs) return false;
+        a.aux_prog.insert(a.aux_prog.end(), {(u32)op, (u32)ds, (u32)x, (u32)y});
+    }
+    if (!rd(cnt) || cnt == 0) return false;
+    for (u64 i = 0; i < cnt; i++) {
+        AuxAssertion as;
+        if (!rd(as.column) || !rd(as.first_step) || !rd(as.stride) || !rd(as.value[0]) || !rd(as.value[1]) || !rd(as.value[2]) ||
+            as.column >= a.aw || as.value[0] >= GL_P || as.value[1] >= GL_P || as.value[2] >= GL_P)
+            return false;
+        a.aux_asserts.push_back(as);
+    }
     return p == len;
 }
 
@@ -559,18 +672,20 @@ int upload_ext(wf_ctx* ctx, const std::vector<GlExt<D>>& v, size_t first, size_t
     return WF_OK;
 }
 
-// evaluate all columns of two coefficient matrices at z0 and z1 -> host vectors [cols][D]; one
-// synchronisation for both matrices
+// evaluate all columns of the coefficient matrices at z0 and z1 -> host vectors [cols][D]
+// (out[2m] = mats[m] @ z0, out[2m+1] = mats[m] @ z1); one synchronisation for all matrices
 template <int D>
-int ood_eval(wf_ctx* ctx, const wf_mat* a, const wf_mat* b, const GlExt<D>& z0, const GlExt<D>& z1,
-             std::vector<GlExt<D>> out[4] /* a@z0, a@z1, b@z0, b@z1 */) {
-    const wf_mat* mats[2] = {a, b};
-    void* part[2];
+int ood_eval(wf_ctx* ctx, const std::vector<const wf_mat*>& mats, const GlExt<D>& z0, const GlExt<D>& z1,
+             std::vector<std::vector<GlExt<D>>>& out) {
+    const int nm = (int)mats.size();
+    std::vector<void*> part(nm);
     void* res;
-    const size_t total_cols = (size_t)a->m.cols + b->m.cols;
+    size_t total_cols = 0;
+    for (auto* m : mats) total_cols += m->m.cols;
+    out.assign(2 * nm, {});
     CKI(wf_dev_alloc(ctx, total_cols * 2 * D * 8, &res));
     size_t off = 0;
-    for (int m = 0; m < 2; m++) {
+    for (int m = 0; m < nm; m++) {
         const size_t n = mats[m]->m.rows;
         const u32 chunks = (u32)((n + 256 * OOD_PER_THREAD - 1) / (256 * OOD_PER_THREAD));
         const u32 cols = mats[m]->m.cols;
@@ -584,11 +699,10 @@ int ood_eval(wf_ctx* ctx, const wf_mat* a, const wf_mat* b, const GlExt<D>& z0, 
     std::vector<u64> host(total_cols * 2 * D);
     CK(cudaMemcpyAsync(host.data(), res, host.size() * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    wf_dev_free(ctx, part[0]);
-    wf_dev_free(ctx, part[1]);
+    for (void* pp : part) wf_dev_free(ctx, pp);
     wf_dev_free(ctx, res);
     off = 0;
-    for (int m = 0; m < 2; m++) {
+    for (int m = 0; m < nm; m++) {
         const u32 cols = mats[m]->m.cols;
         out[2 * m].resize(cols);
         out[2 * m + 1].resize(cols);
@@ -617,21 +731,29 @@ void write_queries(const GatherBatch& gb, size_t row_id, size_t dig_id, size_t n
 
 template <int D>
 int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont, u32 log_n,
-              const Options& o, std::vector<u8>& proof_out) {
+              const Options& o, wf_aux_builder_fn aux_builder, void* aux_user, std::vector<u8>& proof_out) {
     const int h = o.hash_id;
     const size_t n = (size_t)1 << log_n;
     u32 log_b = 0;
     while ((1u << log_b) < o.blowup) log_b++;
     const size_t N = n << log_b;
     const u32 c = air.w, kc = air.num_comp_cols(n), log_ceb = air.log_ce_blowup();
-    const u32 n_tr = (u32)air.degrees.size(), n_as = (u32)air.asserts.size();
+    const u32 aw = air.aw, n_atr = (u32)air.aux_degrees.size(), n_aas = (u32)air.aux_asserts.size();
+    const u32 n_mtr = (u32)air.degrees.size(), n_mas = (u32)air.asserts.size();
+    const u32 n_tr = n_mtr + n_atr, n_as = n_mas + n_aas;  // context.rs:205-207, :223-225
+    if (aw && !aux_builder) return wf_fail(ctx, WF_ERR_INVALID, "multi-segment AIR needs an aux trace builder");
     if (log_ceb > log_b) return wf_fail(ctx, WF_ERR_INVALID, "blowup factor too small for the constraint degrees");
     for (auto& col : air.periodic) if (col.size() > n) return wf_fail(ctx, WF_ERR_INVALID, "periodic column longer than the trace");
+    for (auto& as : air.aux_asserts)
+        if (as.first_step >= n || (as.stride != 0 && (as.stride < 2 || (as.stride & (as.stride - 1)) || as.stride > n || as.first_step >= as.stride)))
+            return wf_fail(ctx, WF_ERR_INVALID, "invalid aux assertion");
     for (auto& as : air.asserts)
         if (as.first_step >= n || (as.stride != 0 && (as.stride < 2 || (as.stride & (as.stride - 1)) || as.stride > n || as.first_step >= as.stride)))
             return wf_fail(ctx, WF_ERR_INVALID, "invalid assertion");
     // ---- channel seed: Context::to_elements || pub inputs (channel.rs:57-82, context.rs:119-136) ----
-    std::vector<u64> seed = {((u64)c << 8), (u64)n, 1, 0xFFFFFFFFULL, (u64)(n_tr + n_as),
+    // TraceInfo::to_elements (air/src/air/trace_info.rs:209-238)
+    const u64 ti0 = aw ? ((((((u64)c << 8) | 1) << 8) | aw) << 8) | air.nr : ((u64)c << 8);
+    std::vector<u64> seed = {ti0, (u64)n, 1, 0xFFFFFFFFULL, (u64)(n_tr + n_as),
                              ((u64)o.ext << 24) | ((u64)o.folding << 16) | ((u64)o.rem_max_deg << 8) | o.blowup,
                              o.grinding, o.num_queries};
     for (u64 v : air.pub_inputs) seed.push_back(v);
@@ -655,7 +777,41 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     wf_mark(ctx, "trace_commit");
     ch.commit(root);
 
+    // ---- 1b. auxiliary segment (lib.rs:309-349; Air::get_aux_rand_elements air/src/air/mod.rs:292-306;
+    //          DefaultTraceLde::set_aux_trace trace_lde/default/mod.rs:140-166) ----
+    wf_mat *apolys = nullptr, *alde = nullptr;
+    wf_tree* atree = nullptr;
+    std::vector<u64> rnd_flat;  // [nr][D], canonical
+    if (aw) {
+        for (u32 i = 0; i < air.nr; i++) { GlExt<D> e = ch.draw(); for (int q = 0; q < D; q++) rnd_flat.push_back(e.v[q]); }
+        std::vector<u64> rnd_user = rnd_flat;
+        if (mont) for (u64& v : rnd_user) v = gl_mul(v, 0xFFFFFFFFULL);  // x * R, R = 2^64 mod p
+        std::vector<u64> aux_host((size_t)aw * n * D);  // [aw][n][D]: ColMatrix<E>, one Vec<E> per column
+        if (aux_builder(aux_user, rnd_user.data(), aux_host.data()) != 0) return wf_fail(ctx, WF_ERR_INVALID, "aux trace builder failed");
+        // E column j -> D base columns j*D + q (rows of the LDE then serialise exactly like [E] rows)
+        std::vector<u64> comp((size_t)aw * D * n);
+        std::vector<const u64*> cols(aw * D);
+        for (u32 j = 0; j < aw; j++)
+            for (int q = 0; q < D; q++) {
+                u64* dst = &comp[((size_t)j * D + q) * n];
+                const u64* src = &aux_host[(size_t)j * n * D + q];
+                for (size_t i = 0; i < n; i++) dst[i] = src[i * D];
+                cols[j * D + q] = dst;
+            }
+        wf_mat* atrace;
+        CKI(wf_mat_from_host_columns(ctx, cols.data(), aw * D, n, 1, mont, &atrace));
+        CKI(wf_mat_interpolate(ctx, atrace, &apolys));
+        wf_mat_free(ctx, atrace);
+        CKI(wf_mat_lde(ctx, apolys, log_b, &alde));
+        CKI(wf_commit_rows(ctx, h, alde, &atree));
+        CKI(wf_tree_root(ctx, atree, root));
+        wf_mark(ctx, "aux_commit");
+        ch.commit(root);
+    }
+
     // ---- 2. constraint evaluation (lib.rs:373-378) ----
+    // coefficient order: main transition, aux transition (transition/mod.rs:63-72), main assertions,
+    // aux assertions (boundary/mod.rs:108-110)
     std::vector<GlExt<D>> cc = ch.draw_coeffs(o.batch_c, n_tr + n_as);
     const size_t ce = n << log_ceb;
     wf_mat* comp;
@@ -706,7 +862,7 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
         GenEvalParams p;
         memset(&p, 0, sizeof(p));
         p.lde = lde->m; p.out = comp->m; p.w = c; p.log_n = log_n; p.log_blowup = log_b; p.log_ce_blowup = log_ceb;
-        p.prog_len = (u32)(air.prog.size() / 4); p.num_regs = air.num_regs; p.num_periodic = (u32)air.periodic.size(); p.num_tc = n_tr;
+        p.prog_len = (u32)(air.prog.size() / 4); p.num_regs = air.num_regs; p.num_periodic = (u32)air.periodic.size(); p.num_tc = n_mtr;
         void* dp;
         CKI(upload(air.prog.data(), air.prog.size() * 4, &dp)); p.prog = (u32*)dp;
         CKI(upload(air.consts.data(), air.consts.size() * 8, &dp)); p.consts = (u64*)dp;
@@ -725,7 +881,7 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
         CKI(upload(ptab.data(), ptab.size() * 8, &dp)); p.ptab = (u64*)dp;
         CKI(upload(poff.data(), poff.size() * 4, &dp)); p.ptab_off = (u32*)dp;
         CKI(upload(plen.data(), plen.size() * 4, &dp)); p.ptab_len = (u32*)dp;
-        auto f0 = flat(0, n_tr);
+        auto f0 = flat(0, n_mtr);
         CKI(upload(f0.data(), f0.size() * 8, &dp)); p.tcoef = (u64*)dp;
         // boundary groups: BTreeMap keyed by (stride, first_step) (air/src/air/boundary/mod.rs:154),
         // coefficients assigned in sorted-assertion order; divisor x^a - g^(a*first_step) (divisor.rs:44-56)
@@ -757,7 +913,40 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
         for (u32 i = 0; i < (1u << log_ceb); i++) p.zt[i] = zt[i];
         p.num_exempt = air.exemptions;
         for (u32 e = 0; e < air.exemptions; e++) p.exempt[e] = gl_pow(g_tr, n - air.exemptions + e);  // divisor.rs:31-41
-        generic_constraints_kernel<D><<<(unsigned)((ce + 127) / 128), 128, 0, ctx->st>>>(p);
+        std::vector<u32> agoff = {0}, aecol;
+        std::vector<u64> aga, agb, agoa, aeval, aecc, fa;
+        if (aw) {
+            p.alde = alde->m; p.aw = aw; p.nr = air.nr; p.aprog_len = (u32)(air.aux_prog.size() / 4);
+            CKI(upload(air.aux_prog.data(), air.aux_prog.size() * 4, &dp)); p.aprog = (u32*)dp;
+            CKI(upload(rnd_flat.data(), rnd_flat.size() * 8, &dp)); p.rnd = (u64*)dp;
+            fa = flat(n_mtr, n_atr);
+            CKI(upload(fa.data(), fa.size() * 8, &dp)); p.atcoef = (u64*)dp;
+            auto aas = air.sorted_aux_assertions();
+            std::map<std::pair<u64, u64>, std::vector<size_t>> agroups;
+            for (size_t i = 0; i < aas.size(); i++) agroups[{aas[i].stride, aas[i].first_step}].push_back(i);
+            for (auto& kv : agroups) {
+                u64 a = kv.first.first == 0 ? 1 : n / kv.first.first;
+                aga.push_back(a);
+                agb.push_back(kv.first.second == 0 ? 1 : gl_pow(g_tr, a * kv.first.second));
+                agoa.push_back(gl_pow(GL_GENERATOR, a));
+                for (size_t i : kv.second) {
+                    aecol.push_back((u32)aas[i].column);
+                    for (int q = 0; q < D; q++) { aeval.push_back(aas[i].value[q]); aecc.push_back(cc[n_tr + n_mas + i].v[q]); }
+                }
+                agoff.push_back((u32)aecol.size());
+            }
+            p.num_agroups = (u32)aga.size();
+            CKI(upload(agoff.data(), agoff.size() * 4, &dp)); p.ag_off = (u32*)dp;
+            CKI(upload(aga.data(), aga.size() * 8, &dp)); p.ag_a = (u64*)dp;
+            CKI(upload(agb.data(), agb.size() * 8, &dp)); p.ag_b = (u64*)dp;
+            CKI(upload(agoa.data(), agoa.size() * 8, &dp)); p.ag_oa = (u64*)dp;
+            CKI(upload(aecol.data(), aecol.size() * 4, &dp)); p.ae_col = (u32*)dp;
+            CKI(upload(aeval.data(), aeval.size() * 8, &dp)); p.ae_val = (u64*)dp;
+            CKI(upload(aecc.data(), aecc.size() * 8, &dp)); p.ae_cc = (u64*)dp;
+            generic_constraints_kernel<D, true><<<(unsigned)((ce + 127) / 128), 128, 0, ctx->st>>>(p);
+        } else {
+            generic_constraints_kernel<D, false><<<(unsigned)((ce + 127) / 128), 128, 0, ctx->st>>>(p);
+        }
         ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -786,13 +975,17 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     // ---- 4. out-of-domain frames (lib.rs:392-401) ----
     GlExt<D> z = ch.draw();
     GlExt<D> zg = ext_mul_base(z, gl_root_of_unity(log_n));
-    std::vector<GlExt<D>> ood[4];
-    CKI(ood_eval<D>(ctx, polys, cpolys, z, zg, ood));
+    std::vector<std::vector<GlExt<D>>> ood;
+    {
+        std::vector<const wf_mat*> mats = {polys, cpolys};
+        if (aw) mats.push_back(apolys);
+        CKI(ood_eval<D>(ctx, mats, z, zg, ood));
+    }
     std::vector<GlExt<D>>&t_cur = ood[0], &t_nxt = ood[1], &qb_cur = ood[2], &qb_nxt = ood[3];  // qb_*: per base component column
     // H_j(z) = sum_comp phi^comp * (component column evaluated at z)
     auto combine = [&](const std::vector<GlExt<D>>& comp_evals) {
-        std::vector<GlExt<D>> r(kc);
-        for (u32 j = 0; j < kc; j++) {
+        std::vector<GlExt<D>> r(comp_evals.size() / D);
+        for (u32 j = 0; j < r.size(); j++) {
             GlExt<D> acc = ext_zero<D>();
             for (int q = 0; q < D; q++) {
                 GlExt<D> basis = ext_zero<D>();
@@ -804,6 +997,12 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
         return r;
     };
     std::vector<GlExt<D>> q_cur = combine(qb_cur), q_nxt = combine(qb_nxt);
+    if (aw) {  // trace frame rows = main columns then aux columns (ood_frame.rs:40-72)
+        auto a_cur = combine(ood[4]), a_nxt = combine(ood[5]);
+        t_cur.insert(t_cur.end(), a_cur.begin(), a_cur.end());
+        t_nxt.insert(t_nxt.end(), a_nxt.begin(), a_nxt.end());
+    }
+    const u32 ct = c + aw;
     ByteVec ood_t, ood_q;  // OodFrame (air/src/proof/ood_frame.rs:59-72, :95-108)
     ood_t.u8_(2); write_elems<D>(ood_t, t_cur); write_elems<D>(ood_t, t_nxt);
     ood_q.u8_(2); write_elems<D>(ood_q, q_cur); write_elems<D>(ood_q, q_nxt);
@@ -815,20 +1014,22 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     }
     wf_mark(ctx, "ood_frames");
     // ---- 5. DEEP composition (lib.rs:403-440), evaluation form ----
-    std::vector<GlExt<D>> dc = ch.draw_coeffs(o.batch_d, c + kc);
+    std::vector<GlExt<D>> dc = ch.draw_coeffs(o.batch_d, ct + kc);
     GlExt<D> Sz = ext_zero<D>(), Szg = ext_zero<D>();
-    for (u32 j = 0; j < c; j++) { Sz = ext_add(Sz, ext_mul(dc[j], t_cur[j])); Szg = ext_add(Szg, ext_mul(dc[j], t_nxt[j])); }
-    for (u32 j = 0; j < kc; j++) { Sz = ext_add(Sz, ext_mul(dc[c + j], q_cur[j])); Szg = ext_add(Szg, ext_mul(dc[c + j], q_nxt[j])); }
-    u64 *d_dt, *d_dq;
+    for (u32 j = 0; j < ct; j++) { Sz = ext_add(Sz, ext_mul(dc[j], t_cur[j])); Szg = ext_add(Szg, ext_mul(dc[j], t_nxt[j])); }
+    for (u32 j = 0; j < kc; j++) { Sz = ext_add(Sz, ext_mul(dc[ct + j], q_cur[j])); Szg = ext_add(Szg, ext_mul(dc[ct + j], q_nxt[j])); }
+    u64 *d_dt, *d_dq, *d_da;
     CKI(upload_ext<D>(ctx, dc, 0, c, &d_dt));
-    CKI(upload_ext<D>(ctx, dc, c, kc, &d_dq));
+    CKI(upload_ext<D>(ctx, dc, c, aw, &d_da));
+    CKI(upload_ext<D>(ctx, dc, ct, kc, &d_dq));
     wf_mat* deep;
     CKI(wf_mat_alloc(ctx, N, D, &deep));
     if (deep->m.W > D) CK(cudaMemsetAsync(deep->m.base, 0, deep->m.words() * 8, ctx->st));
     {
         DeepParams p;
         p.trace = lde->m; p.cons = clde->m; p.out = deep->m; p.c = c; p.kc = kc; p.log_N = log_n + log_b;
-        p.tcc = d_dt; p.ccc = d_dq;
+        p.tcc = d_dt; p.ccc = d_dq; p.acc = d_da; p.aw = aw;
+        if (aw) p.aux = alde->m; else p.aux = lde->m;
         CKI(wf_get_twiddles(ctx, log_n + log_b, &p.tw_N));
         const size_t rows_per_thread = (D == 1 ? 8 : 4);
         size_t threads = (N + rows_per_thread - 1) / rows_per_thread;
@@ -854,7 +1055,7 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     // ---- 8. proof object (lib.rs:464-489; air/src/proof/mod.rs:189-200) ----
     ByteVec w;
     // Context (context.rs:142-151): TraceInfo, modulus, ProofOptions, num_constraints
-    w.u8_((u8)c); w.u8_(0); w.u8_(0); w.u8_((u8)log_n); w.u16_(0);
+    w.u8_((u8)c); w.u8_((u8)aw); w.u8_((u8)air.nr); w.u8_((u8)log_n); w.u16_(0);
     w.u8_(8); w.u64_(GL_P);
     w.u8_((u8)o.num_queries); w.u8_((u8)o.blowup); w.u8_((u8)o.grinding); w.u8_((u8)o.ext); w.u8_((u8)o.folding);
     w.u8_((u8)o.rem_max_deg); w.u8_((u8)o.batch_c); w.u8_((u8)o.batch_d); w.u8_((u8)o.num_partitions); w.u8_((u8)o.hash_rate);
@@ -867,11 +1068,15 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     GatherBatch gb;
     FriProofPlan fplan;
     size_t tr_rows = gb.add_rows(lde->m, pos), cr_rows = gb.add_rows(clde->m, pos), tr_dig, cr_dig;
+    size_t ar_rows = 0, ar_dig = 0;
+    if (aw) ar_rows = gb.add_rows(alde->m, pos);
     CKI(gb.add_opening(ctx, ttree, pos, &tr_dig));
     CKI(gb.add_opening(ctx, ctree, pos, &cr_dig));
+    if (aw) CKI(gb.add_opening(ctx, atree, pos, &ar_dig));
     CKI(wf_fri_queue_proof(ctx, fri, pos, gb, fplan));
     CKI(gb.run(ctx));
     write_queries(gb, tr_rows, tr_dig, pos.size() * c, w);
+    if (aw) write_queries(gb, ar_rows, ar_dig, pos.size() * aw * D, w);  // trace_lde/default/mod.rs:199-218
     write_queries(gb, cr_rows, cr_dig, pos.size() * kc * D, w);
     w.u16_((uint16_t)ood_t.v.size()); w.bytes(ood_t.v.data(), ood_t.v.size());
     w.u16_((uint16_t)ood_q.v.size()); w.bytes(ood_q.v.data(), ood_q.v.size());
@@ -881,9 +1086,10 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     proof_out.swap(w.v);
     wf_fri_free(ctx, fri);
     for (wf_mat* m : {polys, lde, cpolys, clde}) wf_mat_free(ctx, m);
+    if (aw) { wf_mat_free(ctx, apolys); wf_mat_free(ctx, alde); wf_tree_free(ctx, atree); }
     wf_tree_free(ctx, ttree);
     wf_tree_free(ctx, ctree);
-    for (u64* p : {d_dt, d_dq}) wf_dev_free(ctx, p);
+    for (u64* p : {d_dt, d_dq, d_da}) wf_dev_free(ctx, p);
     return WF_OK;
 }
 
@@ -907,13 +1113,14 @@ static int parse_options(wf_ctx* ctx, const uint32_t* opts, Options& o) {
     return WF_OK;
 }
 static int prove_dispatch(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont,
-                          uint32_t log_n, const Options& o, uint8_t* proof, size_t* proof_len) {
+                          uint32_t log_n, const Options& o, uint8_t* proof, size_t* proof_len, wf_aux_builder_fn aux_builder = nullptr,
+                          void* aux_user = nullptr) {
     std::vector<u8> out;
     int r;
     switch (o.ext) {
-        case 1: r = prove_air<1>(ctx, air, trace_cols, d_trace, mont, log_n, o, out); break;
-        case 2: r = prove_air<2>(ctx, air, trace_cols, d_trace, mont, log_n, o, out); break;
-        case 3: r = prove_air<3>(ctx, air, trace_cols, d_trace, mont, log_n, o, out); break;
+        case 1: r = prove_air<1>(ctx, air, trace_cols, d_trace, mont, log_n, o, aux_builder, aux_user, out); break;
+        case 2: r = prove_air<2>(ctx, air, trace_cols, d_trace, mont, log_n, o, aux_builder, aux_user, out); break;
+        case 3: r = prove_air<3>(ctx, air, trace_cols, d_trace, mont, log_n, o, aux_builder, aux_user, out); break;
         default: return wf_fail(ctx, WF_ERR_UNSUPPORTED, "field extension %u", o.ext);
     }
     if (r != WF_OK) return r;
@@ -939,7 +1146,19 @@ extern "C" int wf_prove_air(wf_ctx* ctx, const uint64_t* air_desc, size_t air_de
     CKI(parse_options(ctx, opts, o));
     AirHost air;
     if (!parse_air_host(air_desc, air_desc_len, air)) return wf_fail(ctx, WF_ERR_INVALID, "malformed AIR description");
+    if (air.aw) return wf_fail(ctx, WF_ERR_INVALID, "multi-segment AIR: use wf_prove_air_aux");
     return prove_dispatch(ctx, air, trace_cols, nullptr, mont, log_n, o, proof, proof_len);
+}
+extern "C" int wf_prove_air_aux(wf_ctx* ctx, const uint64_t* air_desc, size_t air_desc_len, const uint64_t* const* trace_cols, int mont,
+                                uint32_t log_n, const uint32_t* opts, wf_aux_builder_fn aux_builder, void* aux_user, uint8_t* proof,
+                                size_t* proof_len) {
+    if (!ctx || !air_desc || !trace_cols || !opts || !proof || !proof_len || log_n < 3)
+        return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    Options o;
+    CKI(parse_options(ctx, opts, o));
+    AirHost air;
+    if (!parse_air_host(air_desc, air_desc_len, air)) return wf_fail(ctx, WF_ERR_INVALID, "malformed AIR description");
+    return prove_dispatch(ctx, air, trace_cols, nullptr, mont, log_n, o, proof, proof_len, aux_builder, aux_user);
 }
 
 extern "C" int wf_prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, uint32_t k, uint32_t log_n,
