@@ -190,6 +190,34 @@ int wf_prove_air_aux(wf_ctx* ctx, const uint64_t* air_desc, size_t air_desc_len,
 int wf_prove_fib_dev(wf_ctx* ctx, const uint64_t* d_trace, uint32_t k, uint32_t log_n, const uint64_t* results,
                      const uint32_t* opts, uint8_t* proof, size_t* proof_len);
 
+/* ---- the same pipeline as separate steps, for a host that owns the transcript (the Rust shim of
+ *      impl ConstraintEvaluator / ConstraintCommitment, prover/src/lib.rs:195-223) ---- */
+/* ConstraintEvaluator::evaluate (prover/src/constraints/evaluator/mod.rs:28-42, default.rs:60-118) +
+ * ConstraintEvaluationTable::combine (evaluation_table.rs:163): CompositionPolyTrace over the CE domain
+ * as a (n * ce_blowup) x ext matrix. air_desc as for wf_prove_air[_aux]; main_lde N x width, aux_lde
+ * N x aux_width*ext (NULL for single-segment AIRs). coeffs: ConstraintCompositionCoefficients
+ * (air/src/air/coefficients.rs:72) flattened [transition: main, aux | boundary: main, aux][ext] with
+ * boundary coefficients in the sorted-assertion order; aux_rand [num_rand][ext]. Canonical words. */
+int wf_eval_constraints(wf_ctx* ctx, const uint64_t* air_desc, size_t air_desc_len, uint32_t log_n, uint32_t blowup, uint32_t ext,
+                        const wf_mat* main_lde, const wf_mat* aux_lde, const uint64_t* coeffs, const uint64_t* aux_rand,
+                        wf_mat** out);
+/* Prover::build_constraint_commitment (prover/src/lib.rs:215-223; DefaultConstraintCommitment::new,
+ * constraints/commitment/default.rs:44-150): composition trace -> num_cols column polynomials of
+ * degree < n (CompositionPoly, n x num_cols*ext), their LDE (N x num_cols*ext) and its row commitment */
+int wf_composition_commit(wf_ctx* ctx, int hash_id, const wf_mat* comp_trace, uint32_t log_n, uint32_t blowup, uint32_t ext,
+                          uint32_t num_cols, wf_mat** polys, wf_mat** lde, wf_tree** tree);
+/* ColMatrix::evaluate_columns_at (prover/src/matrix/col_matrix.rs:245) at two points of E (z and z*g for
+ * TracePolyTable::get_ood_frame, trace/poly_table.rs:68-76; CompositionPoly::get_ood_frame,
+ * composition_poly.rs:101-108). col_ext = 1: base columns; col_ext = ext: the matrix holds columns of E
+ * (ext consecutive base columns each). out0/out1: [cols / col_ext][ext] host words. */
+int wf_mat_evaluate_at(wf_ctx* ctx, const wf_mat* polys, uint32_t ext, uint32_t col_ext, const uint64_t* z0, const uint64_t* z1,
+                       uint64_t* out0, uint64_t* out1);
+/* DeepCompositionPoly::{add_trace_polys, add_composition_poly, evaluate} (prover/src/composer/mod.rs:67-210):
+ * DEEP composition evaluated over the LDE domain, N x ext. coeffs / ood_cur / ood_next: [width + aux_width +
+ * composition columns][ext] in that order (DeepCompositionCoefficients, TraceOodFrame + QuotientOodFrame rows). */
+int wf_deep_compose(wf_ctx* ctx, uint32_t ext, const wf_mat* main_lde, const wf_mat* aux_lde, const wf_mat* cons_lde, uint32_t log_n,
+                    const uint64_t* z, const uint64_t* coeffs, const uint64_t* ood_cur, const uint64_t* ood_next, wf_mat** out);
+
 /* ProverChannel::grind_query_seed (prover/src/channel.rs:169-184), serial semantics: the SMALLEST
  * nonce >= 1 with trailing_zeros(first 8 LE bytes of H::merge_with_int(seed, nonce)) >= grinding. */
 int wf_grind(wf_ctx* ctx, int hash_id, const uint8_t seed[32], uint32_t grinding, uint64_t* nonce);

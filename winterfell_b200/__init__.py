@@ -70,6 +70,10 @@ _SIGS = [
     ("wf_prove_air", C.c_int, [vp, u64p, C.c_size_t, C.POINTER(u64p), C.c_int, C.c_uint32, C.POINTER(C.c_uint32), u8p, C.POINTER(C.c_size_t)]),
     ("wf_prove_air_aux", C.c_int, [vp, u64p, C.c_size_t, C.POINTER(u64p), C.c_int, C.c_uint32, C.POINTER(C.c_uint32), AUX_BUILDER, vp,
                                    u8p, C.POINTER(C.c_size_t)]),
+    ("wf_eval_constraints", C.c_int, [vp, u64p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, u64p, u64p, C.POINTER(vp)]),
+    ("wf_composition_commit", C.c_int, [vp, C.c_int, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    ("wf_mat_evaluate_at", C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u64p, u64p, u64p, u64p]),
+    ("wf_deep_compose", C.c_int, [vp, C.c_uint32, vp, vp, vp, C.c_uint32, u64p, u64p, u64p, u64p, C.POINTER(vp)]),
     ("wf_prove_fib_dev", C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u64p, C.POINTER(C.c_uint32), u8p, C.POINTER(C.c_size_t)]),
     ("wf_grind", C.c_int, [vp, C.c_int, u8p, C.c_uint32, C.POINTER(C.c_uint64)]),
     ("wf_ntt_dev", C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_int]),
@@ -191,6 +195,43 @@ class Context:
                                                               blowup, roots.ctypes.data_as(u8p), roots.size, C.byref(h)))
         f = Fri(self, h, ext_degree)
         return f, roots[: f.num_layers + 1].copy()
+
+    # ---- stepwise pipeline (the seams of prover/src/lib.rs:195-223 and the steps between them) ----
+    def eval_constraints(self, desc, log_n, blowup, ext, main_lde, aux_lde, coeffs, aux_rand=None):
+        d_, dp = _u64(desc)
+        c_, cp = _u64(coeffs)
+        rp = None
+        if aux_rand is not None:
+            r_, rp = _u64(aux_rand)
+        h = vp()
+        self.check(self.L.wf_eval_constraints(self.h, dp, d_.size, log_n, blowup, ext, main_lde.h, aux_lde.h if aux_lde else None,
+                                              cp, rp, C.byref(h)))
+        return Mat(self, h)
+
+    def composition_commit(self, hash_id, comp_trace, log_n, blowup, ext, num_cols):
+        a, b, t = vp(), vp(), vp()
+        self.check(self.L.wf_composition_commit(self.h, hash_id, comp_trace.h, log_n, blowup, ext, num_cols,
+                                                C.byref(a), C.byref(b), C.byref(t)))
+        return Mat(self, a), Mat(self, b), Tree(self, t)
+
+    def evaluate_at(self, polys, ext, col_ext, z0, z1):
+        a_, ap = _u64(z0)
+        b_, bp = _u64(z1)
+        ncols = polys.cols // col_ext
+        o0 = np.zeros((ncols, ext), dtype=np.uint64)
+        o1 = np.zeros((ncols, ext), dtype=np.uint64)
+        self.check(self.L.wf_mat_evaluate_at(self.h, polys.h, ext, col_ext, ap, bp, o0.ctypes.data_as(u64p), o1.ctypes.data_as(u64p)))
+        return o0, o1
+
+    def deep_compose(self, ext, main_lde, aux_lde, cons_lde, log_n, z, coeffs, ood_cur, ood_next):
+        z_, zp = _u64(z)
+        c_, cp = _u64(coeffs)
+        a_, ap = _u64(ood_cur)
+        b_, bp = _u64(ood_next)
+        h = vp()
+        self.check(self.L.wf_deep_compose(self.h, ext, main_lde.h, aux_lde.h if aux_lde else None, cons_lde.h, log_n, zp, cp, ap, bp,
+                                          C.byref(h)))
+        return Mat(self, h)
 
     def prove_fib(self, trace, results, opts, mont=False):
         """trace: [2k, n] uint64; results: [k]; opts: uint32[9] (see wf_prove_fib). Returns proof bytes."""

@@ -15,3 +15,8 @@ done
 for p in "${pids[@]}"; do wait $p; done
 $NVCC -shared -o libwinterfell_b200.so _build/*.o -lcudart -ccbin /usr/bin/g++
 echo "built $(pwd)/libwinterfell_b200.so"
+# the C++ mirror of the reference's plugin interface (include/winterfell_b200.hpp) + its driver: plain
+# g++ over the C ABI, proving the header has no CUDA dependency
+/usr/bin/g++ -O2 -std=c++17 -Wall -Wextra -I../include ../tests/shim/generate_proof_main.cpp -o _build/generate_proof_main \
+  -L. -lwinterfell_b200 -Wl,-rpath,'$ORIGIN/..' -Wl,-rpath-link,/usr/local/cuda/lib64
+echo "built $(pwd)/_build/generate_proof_main"

@@ -729,90 +729,17 @@ void write_queries(const GatherBatch& gb, size_t row_id, size_t dig_id, size_t n
     w.bytes(proof.v.data(), proof.v.size());
 }
 
+// DefaultConstraintEvaluator::evaluate (prover/src/constraints/evaluator/default.rs:60-118) fused with
+// ConstraintEvaluationTable::combine (evaluation_table.rs:163-407): the combined, divisor-normalised
+// constraint evaluations over the CE domain = CompositionPolyTrace, as a (n * ce_blowup) x D matrix.
+// cc: main transition, aux transition, main assertions, aux assertions (sorted order).
 template <int D>
-int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont, u32 log_n,
-              const Options& o, wf_aux_builder_fn aux_builder, void* aux_user, std::vector<u8>& proof_out) {
-    const int h = o.hash_id;
+int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const wf_mat* alde, const std::vector<GlExt<D>>& cc,
+                     const std::vector<u64>& rnd_flat, u32 log_n, u32 log_b, wf_mat** out) {
     const size_t n = (size_t)1 << log_n;
-    u32 log_b = 0;
-    while ((1u << log_b) < o.blowup) log_b++;
-    const size_t N = n << log_b;
-    const u32 c = air.w, kc = air.num_comp_cols(n), log_ceb = air.log_ce_blowup();
-    const u32 aw = air.aw, n_atr = (u32)air.aux_degrees.size(), n_aas = (u32)air.aux_asserts.size();
-    const u32 n_mtr = (u32)air.degrees.size(), n_mas = (u32)air.asserts.size();
-    const u32 n_tr = n_mtr + n_atr, n_as = n_mas + n_aas;  // context.rs:205-207, :223-225
-    if (aw && !aux_builder) return wf_fail(ctx, WF_ERR_INVALID, "multi-segment AIR needs an aux trace builder");
-    if (log_ceb > log_b) return wf_fail(ctx, WF_ERR_INVALID, "blowup factor too small for the constraint degrees");
-    for (auto& col : air.periodic) if (col.size() > n) return wf_fail(ctx, WF_ERR_INVALID, "periodic column longer than the trace");
-    for (auto& as : air.aux_asserts)
-        if (as.first_step >= n || (as.stride != 0 && (as.stride < 2 || (as.stride & (as.stride - 1)) || as.stride > n || as.first_step >= as.stride)))
-            return wf_fail(ctx, WF_ERR_INVALID, "invalid aux assertion");
-    for (auto& as : air.asserts)
-        if (as.first_step >= n || (as.stride != 0 && (as.stride < 2 || (as.stride & (as.stride - 1)) || as.stride > n || as.first_step >= as.stride)))
-            return wf_fail(ctx, WF_ERR_INVALID, "invalid assertion");
-    // ---- channel seed: Context::to_elements || pub inputs (channel.rs:57-82, context.rs:119-136) ----
-    // TraceInfo::to_elements (air/src/air/trace_info.rs:209-238)
-    const u64 ti0 = aw ? ((((((u64)c << 8) | 1) << 8) | aw) << 8) | air.nr : ((u64)c << 8);
-    std::vector<u64> seed = {ti0, (u64)n, 1, 0xFFFFFFFFULL, (u64)(n_tr + n_as),
-                             ((u64)o.ext << 24) | ((u64)o.folding << 16) | ((u64)o.rem_max_deg << 8) | o.blowup,
-                             o.grinding, o.num_queries};
-    for (u64 v : air.pub_inputs) seed.push_back(v);
-    Channel<D> ch(h, seed);
-
-    // ---- 1. trace commitment (lib.rs:497-522) ----
-    wf_mat *trace = nullptr, *polys = nullptr, *lde = nullptr;
-    wf_tree* ttree = nullptr;
-    wf_mark(ctx, "start");
-    if (d_trace) CKI(wf_mat_from_device_columns(ctx, d_trace, c, n, &trace));
-    else CKI(wf_mat_from_host_columns(ctx, trace_cols, c, n, 1, mont, &trace));
-    wf_mark(ctx, "trace_upload_layout");
-    CKI(wf_mat_interpolate(ctx, trace, &polys));
-    wf_mat_free(ctx, trace);
-    wf_mark(ctx, "trace_interpolate");
-    CKI(wf_mat_lde(ctx, polys, log_b, &lde));
-    wf_mark(ctx, "trace_lde");
-    CKI(wf_commit_rows(ctx, h, lde, &ttree));
-    u8 root[32];
-    CKI(wf_tree_root(ctx, ttree, root));
-    wf_mark(ctx, "trace_commit");
-    ch.commit(root);
-
-    // ---- 1b. auxiliary segment (lib.rs:309-349; Air::get_aux_rand_elements air/src/air/mod.rs:292-306;
-    //          DefaultTraceLde::set_aux_trace trace_lde/default/mod.rs:140-166) ----
-    wf_mat *apolys = nullptr, *alde = nullptr;
-    wf_tree* atree = nullptr;
-    std::vector<u64> rnd_flat;  // [nr][D], canonical
-    if (aw) {
-        for (u32 i = 0; i < air.nr; i++) { GlExt<D> e = ch.draw(); for (int q = 0; q < D; q++) rnd_flat.push_back(e.v[q]); }
-        std::vector<u64> rnd_user = rnd_flat;
-        if (mont) for (u64& v : rnd_user) v = gl_mul(v, 0xFFFFFFFFULL);  // x * R, R = 2^64 mod p
-        std::vector<u64> aux_host((size_t)aw * n * D);  // [aw][n][D]: ColMatrix<E>, one Vec<E> per column
-        if (aux_builder(aux_user, rnd_user.data(), aux_host.data()) != 0) return wf_fail(ctx, WF_ERR_INVALID, "aux trace builder failed");
-        // E column j -> D base columns j*D + q (rows of the LDE then serialise exactly like [E] rows)
-        std::vector<u64> comp((size_t)aw * D * n);
-        std::vector<const u64*> cols(aw * D);
-        for (u32 j = 0; j < aw; j++)
-            for (int q = 0; q < D; q++) {
-                u64* dst = &comp[((size_t)j * D + q) * n];
-                const u64* src = &aux_host[(size_t)j * n * D + q];
-                for (size_t i = 0; i < n; i++) dst[i] = src[i * D];
-                cols[j * D + q] = dst;
-            }
-        wf_mat* atrace;
-        CKI(wf_mat_from_host_columns(ctx, cols.data(), aw * D, n, 1, mont, &atrace));
-        CKI(wf_mat_interpolate(ctx, atrace, &apolys));
-        wf_mat_free(ctx, atrace);
-        CKI(wf_mat_lde(ctx, apolys, log_b, &alde));
-        CKI(wf_commit_rows(ctx, h, alde, &atree));
-        CKI(wf_tree_root(ctx, atree, root));
-        wf_mark(ctx, "aux_commit");
-        ch.commit(root);
-    }
-
-    // ---- 2. constraint evaluation (lib.rs:373-378) ----
-    // coefficient order: main transition, aux transition (transition/mod.rs:63-72), main assertions,
-    // aux assertions (boundary/mod.rs:108-110)
-    std::vector<GlExt<D>> cc = ch.draw_coeffs(o.batch_c, n_tr + n_as);
+    const u32 c = air.w, aw = air.aw, log_ceb = air.log_ce_blowup();
+    const u32 n_atr = (u32)air.aux_degrees.size(), n_mtr = (u32)air.degrees.size(), n_mas = (u32)air.asserts.size();
+    const u32 n_tr = n_mtr + n_atr;
     const size_t ce = n << log_ceb;
     wf_mat* comp;
     CKI(wf_mat_alloc(ctx, ce, D, &comp));
@@ -952,12 +879,19 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     }
     CK(cudaStreamSynchronize(ctx->st));
     for (void* sp : scratch) wf_dev_free(ctx, sp);
-    wf_mark(ctx, "constraint_eval");
-    // ---- 3. composition polynomial + commitment (lib.rs:527-552) ----
+    *out = comp;
+    return WF_OK;
+}
+
+// DefaultConstraintCommitment::new (prover/src/constraints/commitment/default.rs:44-150): composition
+// trace (CE-domain evaluations, ce x D) -> CompositionPoly columns (n x kc*D coefficient matrix,
+// composition_poly.rs:58-78,128-140), their LDE (N x kc*D) and the row commitment.
+int composition_commit(wf_ctx* ctx, int h, const wf_mat* comp, u32 log_n, u32 log_b, int D, u32 kc, wf_mat** polys_out,
+                       wf_mat** lde_out, wf_tree** tree_out) {
+    const size_t n = (size_t)1 << log_n;
+    if (comp->m.rows < n * kc || (int)comp->m.cols != D) return wf_fail(ctx, WF_ERR_INVALID, "composition trace shape");
     wf_mat *ccoefs, *cpolys, *clde;
-    wf_tree* ctree;
     CKI(wf_mat_interpolate_with_offset(ctx, comp, GL_GENERATOR, &ccoefs));
-    wf_mat_free(ctx, comp);
     CKI(wf_mat_alloc(ctx, n, kc * D, &cpolys));
     if (cpolys->m.W > (int)(kc * D)) CK(cudaMemsetAsync(cpolys->m.base, 0, cpolys->m.words() * 8, ctx->st));
     comp_split_kernel<<<(unsigned)((n * kc * D + 255) / 256), 256, 0, ctx->st>>>(ccoefs->m, n, kc, D, cpolys->m);
@@ -967,7 +901,128 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     wf_mark(ctx, "composition_interpolate");
     CKI(wf_mat_lde(ctx, cpolys, log_b, &clde));
     wf_mark(ctx, "composition_lde");
-    CKI(wf_commit_rows(ctx, h, clde, &ctree));
+    CKI(wf_commit_rows(ctx, h, clde, tree_out));
+    *polys_out = cpolys;
+    *lde_out = clde;
+    return WF_OK;
+}
+
+// DeepCompositionPoly::{add_trace_polys, add_composition_poly, evaluate} (prover/src/composer/mod.rs:67-210)
+// in evaluation form over the LDE domain (see the header of this file). dc: c + aw + kc coefficients.
+template <int D>
+int deep_compose(wf_ctx* ctx, const wf_mat* lde, const wf_mat* alde, const wf_mat* clde, u32 kc, u32 log_N,
+                 const std::vector<GlExt<D>>& dc, const GlExt<D>& z, const GlExt<D>& zg, const GlExt<D>& Sz, const GlExt<D>& Szg,
+                 wf_mat** out) {
+    const u32 c = lde->m.cols, aw = alde ? alde->m.cols / D : 0, ct = c + aw;
+    const size_t N = (size_t)1 << log_N;
+    u64 *d_dt, *d_dq, *d_da;
+    CKI(upload_ext<D>(ctx, dc, 0, c, &d_dt));
+    CKI(upload_ext<D>(ctx, dc, c, aw, &d_da));
+    CKI(upload_ext<D>(ctx, dc, ct, kc, &d_dq));
+    wf_mat* deep;
+    CKI(wf_mat_alloc(ctx, N, D, &deep));
+    if (deep->m.W > D) CK(cudaMemsetAsync(deep->m.base, 0, deep->m.words() * 8, ctx->st));
+    DeepParams p;
+    p.trace = lde->m; p.cons = clde->m; p.out = deep->m; p.c = c; p.kc = kc; p.log_N = log_N;
+    p.tcc = d_dt; p.ccc = d_dq; p.acc = d_da; p.aw = aw;
+    p.aux = aw ? alde->m : lde->m;
+    CKI(wf_get_twiddles(ctx, log_N, &p.tw_N));
+    const size_t rows_per_thread = (D == 1 ? 8 : 4);
+    size_t threads = (N + rows_per_thread - 1) / rows_per_thread;
+    deep_eval_kernel<D><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->st>>>(p, z, zg, Sz, Szg);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    // the coefficient buffers are pool allocations on the same stream: safe to release after the launch
+    for (u64* q : {d_dt, d_dq, d_da}) wf_dev_free(ctx, q);
+    *out = deep;
+    return WF_OK;
+}
+
+template <int D>
+int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont, u32 log_n,
+              const Options& o, wf_aux_builder_fn aux_builder, void* aux_user, std::vector<u8>& proof_out) {
+    const int h = o.hash_id;
+    const size_t n = (size_t)1 << log_n;
+    u32 log_b = 0;
+    while ((1u << log_b) < o.blowup) log_b++;
+    const size_t N = n << log_b;
+    const u32 c = air.w, kc = air.num_comp_cols(n), log_ceb = air.log_ce_blowup();
+    const u32 aw = air.aw, n_atr = (u32)air.aux_degrees.size(), n_aas = (u32)air.aux_asserts.size();
+    const u32 n_mtr = (u32)air.degrees.size(), n_mas = (u32)air.asserts.size();
+    const u32 n_tr = n_mtr + n_atr, n_as = n_mas + n_aas;  // context.rs:205-207, :223-225
+    if (aw && !aux_builder) return wf_fail(ctx, WF_ERR_INVALID, "multi-segment AIR needs an aux trace builder");
+    if (log_ceb > log_b) return wf_fail(ctx, WF_ERR_INVALID, "blowup factor too small for the constraint degrees");
+    for (auto& col : air.periodic) if (col.size() > n) return wf_fail(ctx, WF_ERR_INVALID, "periodic column longer than the trace");
+    for (auto& as : air.aux_asserts)
+        if (as.first_step >= n || (as.stride != 0 && (as.stride < 2 || (as.stride & (as.stride - 1)) || as.stride > n || as.first_step >= as.stride)))
+            return wf_fail(ctx, WF_ERR_INVALID, "invalid aux assertion");
+    for (auto& as : air.asserts)
+        if (as.first_step >= n || (as.stride != 0 && (as.stride < 2 || (as.stride & (as.stride - 1)) || as.stride > n || as.first_step >= as.stride)))
+            return wf_fail(ctx, WF_ERR_INVALID, "invalid assertion");
+    // ---- channel seed: Context::to_elements || pub inputs (channel.rs:57-82, context.rs:119-136) ----
+    // TraceInfo::to_elements (air/src/air/trace_info.rs:209-238)
+    const u64 ti0 = aw ? ((((((u64)c << 8) | 1) << 8) | aw) << 8) | air.nr : ((u64)c << 8);
+    std::vector<u64> seed = {ti0, (u64)n, 1, 0xFFFFFFFFULL, (u64)(n_tr + n_as),
+                             ((u64)o.ext << 24) | ((u64)o.folding << 16) | ((u64)o.rem_max_deg << 8) | o.blowup,
+                             o.grinding, o.num_queries};
+    for (u64 v : air.pub_inputs) seed.push_back(v);
+    Channel<D> ch(h, seed);
+
+    // ---- 1. trace commitment (lib.rs:497-522) ----
+    wf_mat *trace = nullptr, *polys = nullptr, *lde = nullptr;
+    wf_tree* ttree = nullptr;
+    wf_mark(ctx, "start");
+    if (d_trace) CKI(wf_mat_from_device_columns(ctx, d_trace, c, n, &trace));
+    else CKI(wf_mat_from_host_columns(ctx, trace_cols, c, n, 1, mont, &trace));
+    wf_mark(ctx, "trace_upload_layout");
+    CKI(wf_mat_interpolate(ctx, trace, &polys));
+    wf_mat_free(ctx, trace);
+    wf_mark(ctx, "trace_interpolate");
+    CKI(wf_mat_lde(ctx, polys, log_b, &lde));
+    wf_mark(ctx, "trace_lde");
+    CKI(wf_commit_rows(ctx, h, lde, &ttree));
+    u8 root[32];
+    CKI(wf_tree_root(ctx, ttree, root));
+    wf_mark(ctx, "trace_commit");
+    ch.commit(root);
+
+    // ---- 1b. auxiliary segment (lib.rs:309-349; Air::get_aux_rand_elements air/src/air/mod.rs:292-306;
+    //          DefaultTraceLde::set_aux_trace trace_lde/default/mod.rs:140-166) ----
+    wf_mat *apolys = nullptr, *alde = nullptr;
+    wf_tree* atree = nullptr;
+    std::vector<u64> rnd_flat;  // [nr][D], canonical
+    if (aw) {
+        for (u32 i = 0; i < air.nr; i++) { GlExt<D> e = ch.draw(); for (int q = 0; q < D; q++) rnd_flat.push_back(e.v[q]); }
+        std::vector<u64> rnd_user = rnd_flat;
+        if (mont) for (u64& v : rnd_user) v = gl_mul(v, 0xFFFFFFFFULL);  // x * R, R = 2^64 mod p
+        std::vector<u64> aux_host((size_t)aw * n * D);  // [aw][n][D]: ColMatrix<E>, one Vec<E> per column
+        if (aux_builder(aux_user, rnd_user.data(), aux_host.data()) != 0) return wf_fail(ctx, WF_ERR_INVALID, "aux trace builder failed");
+        // E column j -> D base columns j*D + q (rows of the LDE then serialise exactly like [E] rows)
+        std::vector<const u64*> cols(aw);
+        for (u32 j = 0; j < aw; j++) cols[j] = &aux_host[(size_t)j * n * D];
+        wf_mat* atrace;
+        CKI(wf_mat_from_host_columns(ctx, cols.data(), aw, n, D, mont, &atrace));
+        CKI(wf_mat_interpolate(ctx, atrace, &apolys));
+        wf_mat_free(ctx, atrace);
+        CKI(wf_mat_lde(ctx, apolys, log_b, &alde));
+        CKI(wf_commit_rows(ctx, h, alde, &atree));
+        CKI(wf_tree_root(ctx, atree, root));
+        wf_mark(ctx, "aux_commit");
+        ch.commit(root);
+    }
+
+    // ---- 2. constraint evaluation (lib.rs:373-378) ----
+    // coefficient order: main transition, aux transition (transition/mod.rs:63-72), main assertions,
+    // aux assertions (boundary/mod.rs:108-110)
+    std::vector<GlExt<D>> cc = ch.draw_coeffs(o.batch_c, n_tr + n_as);
+    wf_mat* comp;
+    CKI(eval_constraints<D>(ctx, air, lde, alde, cc, rnd_flat, log_n, log_b, &comp));
+    wf_mark(ctx, "constraint_eval");
+    // ---- 3. composition polynomial + commitment (lib.rs:527-552) ----
+    wf_mat *cpolys, *clde;
+    wf_tree* ctree;
+    CKI(composition_commit(ctx, h, comp, log_n, log_b, D, kc, &cpolys, &clde, &ctree));
+    wf_mat_free(ctx, comp);
     CKI(wf_tree_root(ctx, ctree, root));
     wf_mark(ctx, "composition_commit");
     ch.commit(root);
@@ -1015,28 +1070,11 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     wf_mark(ctx, "ood_frames");
     // ---- 5. DEEP composition (lib.rs:403-440), evaluation form ----
     std::vector<GlExt<D>> dc = ch.draw_coeffs(o.batch_d, ct + kc);
-    GlExt<D> Sz = ext_zero<D>(), Szg = ext_zero<D>();
+    GlExt<D> Sz = ext_zero<D>(), Szg = ext_zero<D>();  // S(z), S(zg): the constant terms composer/mod.rs:202-210 subtracts
     for (u32 j = 0; j < ct; j++) { Sz = ext_add(Sz, ext_mul(dc[j], t_cur[j])); Szg = ext_add(Szg, ext_mul(dc[j], t_nxt[j])); }
     for (u32 j = 0; j < kc; j++) { Sz = ext_add(Sz, ext_mul(dc[ct + j], q_cur[j])); Szg = ext_add(Szg, ext_mul(dc[ct + j], q_nxt[j])); }
-    u64 *d_dt, *d_dq, *d_da;
-    CKI(upload_ext<D>(ctx, dc, 0, c, &d_dt));
-    CKI(upload_ext<D>(ctx, dc, c, aw, &d_da));
-    CKI(upload_ext<D>(ctx, dc, ct, kc, &d_dq));
     wf_mat* deep;
-    CKI(wf_mat_alloc(ctx, N, D, &deep));
-    if (deep->m.W > D) CK(cudaMemsetAsync(deep->m.base, 0, deep->m.words() * 8, ctx->st));
-    {
-        DeepParams p;
-        p.trace = lde->m; p.cons = clde->m; p.out = deep->m; p.c = c; p.kc = kc; p.log_N = log_n + log_b;
-        p.tcc = d_dt; p.ccc = d_dq; p.acc = d_da; p.aw = aw;
-        if (aw) p.aux = alde->m; else p.aux = lde->m;
-        CKI(wf_get_twiddles(ctx, log_n + log_b, &p.tw_N));
-        const size_t rows_per_thread = (D == 1 ? 8 : 4);
-        size_t threads = (N + rows_per_thread - 1) / rows_per_thread;
-        deep_eval_kernel<D><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->st>>>(p, z, zg, Sz, Szg);
-        ctx->launches++;
-        CK(cudaGetLastError());
-    }
+    CKI(deep_compose<D>(ctx, lde, alde, clde, kc, log_n + log_b, dc, z, zg, Sz, Szg, &deep));
     wf_mark(ctx, "deep_composition");
     // ---- 6. FRI (lib.rs:442-448) ----
     wf_fri* fri;
@@ -1089,7 +1127,6 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     if (aw) { wf_mat_free(ctx, apolys); wf_mat_free(ctx, alde); wf_tree_free(ctx, atree); }
     wf_tree_free(ctx, ttree);
     wf_tree_free(ctx, ctree);
-    for (u64* p : {d_dt, d_dq, d_da}) wf_dev_free(ctx, p);
     return WF_OK;
 }
 
@@ -1159,6 +1196,116 @@ extern "C" int wf_prove_air_aux(wf_ctx* ctx, const uint64_t* air_desc, size_t ai
     AirHost air;
     if (!parse_air_host(air_desc, air_desc_len, air)) return wf_fail(ctx, WF_ERR_INVALID, "malformed AIR description");
     return prove_dispatch(ctx, air, trace_cols, nullptr, mont, log_n, o, proof, proof_len, aux_builder, aux_user);
+}
+
+// ---- stepwise exports: the seams of prover/src/lib.rs:125-223 (ConstraintEvaluator, ConstraintCommitment)
+//      and the concrete steps between them, for a host that keeps the transcript itself ----------------
+template <int D>
+static int eval_constraints_entry(wf_ctx* ctx, const AirHost& air, u32 log_n, u32 log_b, const wf_mat* lde, const wf_mat* alde,
+                                  const uint64_t* coeffs, const uint64_t* aux_rand, wf_mat** out) {
+    const size_t ncc = air.degrees.size() + air.aux_degrees.size() + air.asserts.size() + air.aux_asserts.size();
+    std::vector<GlExt<D>> cc(ncc);
+    for (size_t i = 0; i < ncc; i++) for (int q = 0; q < D; q++) cc[i].v[q] = coeffs[i * D + q];
+    std::vector<u64> rnd;
+    if (air.aw) rnd.assign(aux_rand, aux_rand + (size_t)air.nr * D);
+    return eval_constraints<D>(ctx, air, lde, alde, cc, rnd, log_n, log_b, out);
+}
+extern "C" int wf_eval_constraints(wf_ctx* ctx, const uint64_t* air_desc, size_t air_desc_len, uint32_t log_n, uint32_t blowup,
+                                   uint32_t ext, const wf_mat* main_lde, const wf_mat* aux_lde, const uint64_t* coeffs,
+                                   const uint64_t* aux_rand, wf_mat** out) {
+    if (!ctx || !air_desc || !main_lde || !coeffs || !out || log_n < 3 || blowup < 2 || (blowup & (blowup - 1)))
+        return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    AirHost air;
+    if (!parse_air_host(air_desc, air_desc_len, air)) return wf_fail(ctx, WF_ERR_INVALID, "malformed AIR description");
+    u32 log_b = 0;
+    while ((1u << log_b) < blowup) log_b++;
+    const size_t N = (size_t)1 << (log_n + log_b);
+    if (air.log_ce_blowup() > log_b) return wf_fail(ctx, WF_ERR_INVALID, "blowup factor too small for the constraint degrees");
+    if (main_lde->m.rows != N || main_lde->m.cols != air.w) return wf_fail(ctx, WF_ERR_INVALID, "main LDE shape does not match the AIR");
+    if (air.aw && (!aux_lde || !aux_rand || aux_lde->m.rows != N || aux_lde->m.cols != air.aw * ext))
+        return wf_fail(ctx, WF_ERR_INVALID, "aux LDE / random elements missing or of the wrong shape");
+    for (auto& col : air.periodic) if (col.size() > ((size_t)1 << log_n)) return wf_fail(ctx, WF_ERR_INVALID, "periodic column longer than the trace");
+    const wf_mat* al = air.aw ? aux_lde : nullptr;
+    switch (ext) {
+        case 1: return eval_constraints_entry<1>(ctx, air, log_n, log_b, main_lde, al, coeffs, aux_rand, out);
+        case 2: return eval_constraints_entry<2>(ctx, air, log_n, log_b, main_lde, al, coeffs, aux_rand, out);
+        case 3: return eval_constraints_entry<3>(ctx, air, log_n, log_b, main_lde, al, coeffs, aux_rand, out);
+    }
+    return wf_fail(ctx, WF_ERR_UNSUPPORTED, "field extension %u", ext);
+}
+
+extern "C" int wf_composition_commit(wf_ctx* ctx, int hash_id, const wf_mat* comp_trace, uint32_t log_n, uint32_t blowup, uint32_t ext,
+                                     uint32_t num_cols, wf_mat** polys, wf_mat** lde, wf_tree** tree) {
+    if (!ctx || !comp_trace || !polys || !lde || !tree || ext < 1 || ext > 3 || num_cols == 0 || blowup < 2 || (blowup & (blowup - 1)))
+        return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    u32 log_b = 0;
+    while ((1u << log_b) < blowup) log_b++;
+    return composition_commit(ctx, hash_id, comp_trace, log_n, log_b, (int)ext, num_cols, polys, lde, tree);
+}
+
+template <int D>
+static int evaluate_at_entry(wf_ctx* ctx, const wf_mat* polys, u32 col_ext, const uint64_t* z0, const uint64_t* z1, uint64_t* o0,
+                             uint64_t* o1) {
+    GlExt<D> a = ext_zero<D>(), b = ext_zero<D>();
+    for (int q = 0; q < D; q++) { a.v[q] = z0[q]; b.v[q] = z1[q]; }
+    std::vector<std::vector<GlExt<D>>> ev;
+    CKI(ood_eval<D>(ctx, {polys}, a, b, ev));
+    for (int pt = 0; pt < 2; pt++) {
+        uint64_t* o = pt ? o1 : o0;
+        const size_t cols = ev[pt].size() / col_ext;
+        for (size_t j = 0; j < cols; j++) {
+            GlExt<D> acc = ext_zero<D>();
+            for (u32 q = 0; q < col_ext; q++) {  // column of E = sum_q phi^q * (component column q)
+                GlExt<D> basis = ext_zero<D>();
+                basis.v[q] = 1;
+                acc = ext_add(acc, ext_mul(basis, ev[pt][j * col_ext + q]));
+            }
+            for (int q = 0; q < D; q++) o[j * D + q] = acc.v[q];
+        }
+    }
+    return WF_OK;
+}
+extern "C" int wf_mat_evaluate_at(wf_ctx* ctx, const wf_mat* polys, uint32_t ext, uint32_t col_ext, const uint64_t* z0, const uint64_t* z1,
+                                  uint64_t* out0, uint64_t* out1) {
+    if (!ctx || !polys || !z0 || !z1 || !out0 || !out1 || (col_ext != 1 && col_ext != ext) || polys->m.cols % col_ext)
+        return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    switch (ext) {
+        case 1: return evaluate_at_entry<1>(ctx, polys, col_ext, z0, z1, out0, out1);
+        case 2: return evaluate_at_entry<2>(ctx, polys, col_ext, z0, z1, out0, out1);
+        case 3: return evaluate_at_entry<3>(ctx, polys, col_ext, z0, z1, out0, out1);
+    }
+    return wf_fail(ctx, WF_ERR_UNSUPPORTED, "field extension %u", ext);
+}
+
+template <int D>
+static int deep_entry(wf_ctx* ctx, const wf_mat* lde, const wf_mat* alde, const wf_mat* clde, u32 log_n, const uint64_t* zw,
+                      const uint64_t* coeffs, const uint64_t* ood_cur, const uint64_t* ood_next, wf_mat** out) {
+    const u32 c = lde->m.cols, aw = alde ? alde->m.cols / D : 0, kc = clde->m.cols / D, tot = c + aw + kc;
+    u32 log_N = 0;
+    while (((size_t)1 << log_N) < lde->m.rows) log_N++;
+    std::vector<GlExt<D>> dc(tot);
+    GlExt<D> z = ext_zero<D>(), Sz = ext_zero<D>(), Szg = ext_zero<D>();
+    for (int q = 0; q < D; q++) z.v[q] = zw[q];
+    for (u32 i = 0; i < tot; i++) {
+        GlExt<D> a = ext_zero<D>(), b = ext_zero<D>();
+        for (int q = 0; q < D; q++) { dc[i].v[q] = coeffs[i * D + q]; a.v[q] = ood_cur[i * D + q]; b.v[q] = ood_next[i * D + q]; }
+        Sz = ext_add(Sz, ext_mul(dc[i], a));
+        Szg = ext_add(Szg, ext_mul(dc[i], b));
+    }
+    GlExt<D> zg = ext_mul_base(z, gl_root_of_unity(log_n));
+    return deep_compose<D>(ctx, lde, alde, clde, kc, log_N, dc, z, zg, Sz, Szg, out);
+}
+extern "C" int wf_deep_compose(wf_ctx* ctx, uint32_t ext, const wf_mat* main_lde, const wf_mat* aux_lde, const wf_mat* cons_lde,
+                               uint32_t log_n, const uint64_t* z, const uint64_t* coeffs, const uint64_t* ood_cur,
+                               const uint64_t* ood_next, wf_mat** out) {
+    if (!ctx || !main_lde || !cons_lde || !z || !coeffs || !ood_cur || !ood_next || !out || ext < 1 || ext > 3 ||
+        cons_lde->m.cols % ext || cons_lde->m.rows != main_lde->m.rows || (aux_lde && (aux_lde->m.cols % ext || aux_lde->m.rows != main_lde->m.rows)))
+        return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    switch (ext) {
+        case 1: return deep_entry<1>(ctx, main_lde, aux_lde, cons_lde, log_n, z, coeffs, ood_cur, ood_next, out);
+        case 2: return deep_entry<2>(ctx, main_lde, aux_lde, cons_lde, log_n, z, coeffs, ood_cur, ood_next, out);
+        default: return deep_entry<3>(ctx, main_lde, aux_lde, cons_lde, log_n, z, coeffs, ood_cur, ood_next, out);
+    }
 }
 
 extern "C" int wf_prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, uint32_t k, uint32_t log_n,
