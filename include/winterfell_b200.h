@@ -233,6 +233,13 @@ int wf_merkle_dev(wf_ctx* ctx, int hash_id, const uint8_t* d_leaves, size_t nlea
 int wf_fri_fold_dev(wf_ctx* ctx, const uint64_t* d_evals, size_t len, int ext_degree, uint32_t folding_factor,
                     const uint64_t* alpha, uint64_t* d_next);
 
+/* field arithmetic of the device code on caller-chosen operands (a, b: n canonical words each, device):
+ * d_out[0..n) = a*b (math/src/field/f64/mod.rs:357), [n..2n) = a+b (:319), [2n..3n) = a-b (:339),
+ * [3n..4n) = 1/a (:157; 0 for a = 0), then 18 blocks a * 2^s for s in WF_FIELD_TEST_SHIFTS.
+ * d_out holds 22 n words. */
+#define WF_FIELD_TEST_SHIFTS {1, 3, 6, 12, 24, 31, 32, 33, 48, 63, 64, 65, 72, 80, 84, 90, 95, 96}
+int wf_field_ops_dev(wf_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, size_t n, uint64_t* d_out);
+
 /* ---- host-side helpers of the product (transcript arithmetic; no GPU needed) ------------------- */
 /* H::hash_elements / merge / merge_with_int on the host (crypto/src/hash/mod.rs:31-64) */
 int wf_host_hash_elements(int hash_id, const uint64_t* elems, size_t n, uint8_t out[32]);

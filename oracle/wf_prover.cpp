@@ -59,8 +59,12 @@ struct Writer {
 // A generic single-segment AIR (air/src/air/mod.rs:174 `Air`): transition constraints as a small
 // straight-line program over the evaluation frame, so that the same description drives the oracle,
 // the device evaluator and the verifier. FibSmall x k is one instance (fib_air()).
-struct Assertion { size_t column, first_step, stride; u64 value; };  // stride 0: single; else periodic single-value
-struct AuxAssertion { size_t column, first_step, stride; u64 value[3]; };  // value in E (first d words used)
+// air/src/air/assertions/mod.rs:41-50. stride 0: Assertion::single; stride > 0 with one value: ::periodic;
+// stride > 0 with n / stride values: ::sequence. Main-segment values are base elements (v[0] only),
+// aux-segment values are elements of E.
+struct Assertion { size_t column, first_step, stride; std::vector<EE> values; };
+typedef Assertion AuxAssertion;
+static Assertion single_assertion(size_t column, size_t step, u64 value) { return Assertion{column, step, 0, {EE{{value, 0, 0}}}}; }
 struct Instr { u32 op, dst, a, b; };  // ADD/SUB/MUL dst = r[a] op r[b]; CONST dst = consts[a]; OUT result[dst] = r[a]
 enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_CONST = 3, OP_OUT = 4 };
 struct Air {
@@ -197,9 +201,9 @@ static Air fib_air(size_t k, size_t n, const u64* results, const Opts& o) {
         a.prog.push_back({OP_ADD, t, 2 * j + 1, w + 2 * j});
         a.prog.push_back({OP_SUB, t + 1, w + 2 * j + 1, t});
         a.prog.push_back({OP_OUT, 2 * j + 1, t + 1, 0});
-        a.asserts.push_back({2 * j, 0, 0, (u64)(j + 1)});
-        a.asserts.push_back({2 * j + 1, 0, 0, (u64)(j + 1)});
-        a.asserts.push_back({2 * j + 1, n - 1, 0, results ? results[j] : 0});
+        a.asserts.push_back(single_assertion(2 * j, 0, (u64)(j + 1)));
+        a.asserts.push_back(single_assertion(2 * j + 1, 0, (u64)(j + 1)));
+        a.asserts.push_back(single_assertion(2 * j + 1, n - 1, results ? results[j] : 0));
     }
     a.num_regs = t + 2;
     return a;
@@ -207,7 +211,7 @@ static Air fib_air(size_t k, size_t n, const u64* results, const Opts& o) {
 
 // flat u64 description shared with the product's C ABI (include/winterfell_b200.h wf_prove_air):
 // [w, nT, {base, ncyc, cyc...}*, nP, {len, values...}*, nC, consts..., num_regs, nI, {op,dst,a,b}*,
-//  nA, {column, first_step, stride, value}*, nPub, pub..., exemptions]
+//  nA, {column, first_step, stride, nvals, values...}*, nPub, pub..., exemptions]
 static bool parse_air(const u64* d, size_t len, Air& a) {
     size_t p = 0;
     auto rd = [&](u64& v) { if (p >= len) return false; v = d[p++]; return true; };
@@ -233,14 +237,19 @@ static bool parse_air(const u64* d, size_t len, Air& a) {
     if (!rd(cnt)) return false;
     for (u64 i = 0; i < cnt; i++) { u64 op, ds, x, y; if (!rd(op) || !rd(ds) || !rd(x) || !rd(y)) return false; a.prog.push_back({(u32)op, (u32)ds, (u32)x, (u32)y}); }
     if (!rd(cnt)) return false;
-    for (u64 i = 0; i < cnt; i++) { u64 c, fs, st, val; if (!rd(c) || !rd(fs) || !rd(st) || !rd(val)) return false; a.asserts.push_back({(size_t)c, (size_t)fs, (size_t)st, val}); }
+    for (u64 i = 0; i < cnt; i++) {
+        u64 c, fs, st, nv; if (!rd(c) || !rd(fs) || !rd(st) || !rd(nv) || nv == 0 || nv > len) return false;
+        Assertion as{(size_t)c, (size_t)fs, (size_t)st, {}};
+        for (u64 j = 0; j < nv; j++) { if (!rd(v)) return false; as.values.push_back(EE{{v, 0, 0}}); }
+        a.asserts.push_back(as);
+    }
     if (!rd(cnt)) return false;
     for (u64 i = 0; i < cnt; i++) { if (!rd(v)) return false; a.pub_inputs.push_back(v); }
     if (!rd(v)) return false;
     a.exemptions = (u32)v;
     if (p == len) return true;  // single-segment description
     // optional aux section: [aw, nr, nTa, {base, ncyc, cyc...}*, aux_num_regs, nIa, {op,dst,a,b}*,
-    //                        nAa, {column, first_step, stride, v0, v1, v2}*]
+    //                        nAa, {column, first_step, stride, nvals, {v0, v1, v2} x nvals}*]
     if (!rd(v)) return false;
     a.aw = v;
     if (!rd(v)) return false;
@@ -257,8 +266,10 @@ static bool parse_air(const u64* d, size_t len, Air& a) {
     for (u64 i = 0; i < cnt; i++) { u64 op, ds, x, y; if (!rd(op) || !rd(ds) || !rd(x) || !rd(y)) return false; a.aux_prog.push_back({(u32)op, (u32)ds, (u32)x, (u32)y}); }
     if (!rd(cnt)) return false;
     for (u64 i = 0; i < cnt; i++) {
-        u64 c, fs, st, v0, v1, v2; if (!rd(c) || !rd(fs) || !rd(st) || !rd(v0) || !rd(v1) || !rd(v2)) return false;
-        a.aux_asserts.push_back({(size_t)c, (size_t)fs, (size_t)st, {v0, v1, v2}});
+        u64 c, fs, st, nv, v0, v1, v2; if (!rd(c) || !rd(fs) || !rd(st) || !rd(nv) || nv == 0 || nv > len) return false;
+        Assertion as{(size_t)c, (size_t)fs, (size_t)st, {}};
+        for (u64 j = 0; j < nv; j++) { if (!rd(v0) || !rd(v1) || !rd(v2)) return false; as.values.push_back(EE{{v0, v1, v2}}); }
+        a.aux_asserts.push_back(as);
     }
     return p == len && a.aw > 0 && !a.aux_degrees.empty() && !a.aux_asserts.empty();  // context.rs:104-113
 }
@@ -321,12 +332,15 @@ static EE horner_ext(const Field& F, const EE* p, size_t n, const EE& x) {
 
 // ---- boundary constraint groups (air/src/air/boundary/mod.rs:154 group_constraints) -----------------
 // BTreeMap keyed by (stride, first_step); divisor x^a - b with a = number of asserted steps and
-// b = g^(a * first_step) (air/src/air/divisor.rs:44-56 from_assertion); single-value constraints only.
-struct BoundaryGroup { u64 a, b; std::vector<size_t> cols; std::vector<u64> values; std::vector<EE> cc; };
-static std::vector<BoundaryGroup> boundary_groups(const Air& air, const std::vector<EE>& bcoef) {
+// b = g^(a * first_step) (air/src/air/divisor.rs:44-56 from_assertion). A constraint's value polynomial
+// (boundary/constraint.rs:47-75): one coefficient for single / periodic assertions; for sequence
+// assertions the interpolant of the values over the size-a subgroup, evaluated at x * g^(-first_step).
+struct BoundaryEntry { size_t col; std::vector<EE> poly; u64 x_offset; size_t first_step; EE cc; };
+struct BoundaryGroup { u64 a, b; std::vector<BoundaryEntry> e; };
+typedef BoundaryGroup AuxBoundaryGroup;
+static std::vector<BoundaryGroup> group_constraints(const Air& air, const std::vector<Assertion>& as, const EE* bcoef, int d) {
     u64 g = root_of_unity((u32)__builtin_ctzll(air.n));
     std::map<std::pair<size_t, size_t>, BoundaryGroup> m;
-    auto as = air.assertions();
     for (size_t i = 0; i < as.size(); i++) {
         auto key = std::make_pair(as[i].stride, as[i].first_step);
         auto it = m.find(key);
@@ -336,34 +350,42 @@ static std::vector<BoundaryGroup> boundary_groups(const Air& air, const std::vec
             G.b = as[i].first_step == 0 ? 1 : f_exp(g, G.a * as[i].first_step);
             it = m.insert({key, G}).first;
         }
-        it->second.cols.push_back(as[i].column); it->second.values.push_back(as[i].value); it->second.cc.push_back(bcoef[i]);
+        BoundaryEntry e{as[i].column, as[i].values, 1, as[i].first_step, bcoef[i]};
+        for (auto& v : e.poly) for (int k = d; k < 3; k++) v.v[k] = 0;
+        if (e.poly.size() > 1) {  // boundary/constraint.rs:58-68
+            const size_t L = e.poly.size();
+            std::vector<u64> flat(L * d);
+            for (size_t j = 0; j < L; j++) for (int k = 0; k < d; k++) flat[j * d + k] = e.poly[j].v[k];
+            auto itw = get_inv_twiddles(L);
+            interpolate_poly(flat.data(), L, d, itw.data());
+            for (size_t j = 0; j < L; j++) for (int k = 0; k < d; k++) e.poly[j].v[k] = flat[j * d + k];
+            if (as[i].first_step != 0) e.x_offset = f_exp(f_inv(g), as[i].first_step);
+        }
+        it->second.e.push_back(e);
     }
     std::vector<BoundaryGroup> r;
     for (auto& kv : m) r.push_back(kv.second);
     return r;
 }
+static std::vector<BoundaryGroup> boundary_groups(const Air& air, const std::vector<EE>& bcoef) {
+    return group_constraints(air, air.assertions(), bcoef.data(), 1);
+}
 // constraints against the auxiliary segment (boundary/mod.rs:121-128): same grouping, values in E
-struct AuxBoundaryGroup { u64 a, b; std::vector<size_t> cols; std::vector<EE> values; std::vector<EE> cc; };
-static std::vector<AuxBoundaryGroup> aux_boundary_groups(const Air& air, const EE* bcoef) {
-    u64 g = root_of_unity((u32)__builtin_ctzll(air.n));
-    std::map<std::pair<size_t, size_t>, AuxBoundaryGroup> m;
-    auto as = air.aux_assertions();
-    for (size_t i = 0; i < as.size(); i++) {
-        auto key = std::make_pair(as[i].stride, as[i].first_step);
-        auto it = m.find(key);
-        if (it == m.end()) {
-            AuxBoundaryGroup G;
-            G.a = as[i].stride == 0 ? 1 : air.n / as[i].stride;
-            G.b = as[i].first_step == 0 ? 1 : f_exp(g, G.a * as[i].first_step);
-            it = m.insert({key, G}).first;
-        }
-        EE v{{as[i].value[0], as[i].value[1], as[i].value[2]}};
-        for (int k = (int)air.o.ext; k < 3; k++) v.v[k] = 0;
-        it->second.cols.push_back(as[i].column); it->second.values.push_back(v); it->second.cc.push_back(bcoef[i]);
-    }
-    std::vector<AuxBoundaryGroup> r;
-    for (auto& kv : m) r.push_back(kv.second);
-    return r;
+static std::vector<BoundaryGroup> aux_boundary_groups(const Air& air, const EE* bcoef) {
+    return group_constraints(air, air.aux_assertions(), bcoef, (int)air.o.ext);
+}
+// LargePolyConstraint::new (prover/src/constraints/evaluator/boundary.rs:400-425): the value polynomial
+// evaluated over the whole CE domain (offset 7); row i of the CE domain reads entry (i - first_step *
+// ce_blowup) mod ce (:428-445). SmallPolyConstraint (:340-375, Horner at x * x_offset) computes the same
+// values, so one table serves both. Returned flat [ce][d]; empty for single-value constraints.
+static std::vector<u64> sequence_table(const BoundaryEntry& e, int d, size_t ce) {
+    const size_t L = e.poly.size();
+    if (L <= 1) return {};
+    std::vector<u64> flat(L * d), out(ce * d);
+    for (size_t j = 0; j < L; j++) for (int k = 0; k < d; k++) flat[j * d + k] = e.poly[j].v[k];
+    auto tw = get_twiddles(L);
+    evaluate_poly_with_offset(flat.data(), L, d, tw.data(), GENERATOR, ce / L, out.data());
+    return out;
 }
 // builds the auxiliary segment (Prover::build_aux_trace, prover/src/lib.rs:236-247): rand [nr][d] words,
 // out [aw][n][d] words
@@ -478,6 +500,9 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[w][n]*/,
             ptab.push_back(ev);
         }
     }
+    std::vector<std::vector<std::vector<u64>>> gtab(groups.size()), agtab(aux_groups.size());
+    for (size_t gi = 0; gi < groups.size(); gi++) for (auto& e : groups[gi].e) gtab[gi].push_back(sequence_table(e, 1, ce));
+    for (size_t gi = 0; gi < aux_groups.size(); gi++) for (auto& e : aux_groups[gi].e) agtab[gi].push_back(sequence_table(e, d, ce));
     std::vector<EE> comp(ce);
 #pragma omp parallel
     {
@@ -512,15 +537,29 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[w][n]*/,
             u64 ex = 1;
             for (u64 e : exempt) ex = f_mul(ex, f_sub(x, e));          // divisor.rs evaluate_exemptions_at
             EE acc = F.mul_base(t, f_mul(zt, ex));                     // evaluation_table.rs:343-366
-            for (auto& G : groups) {
+            for (size_t gi = 0; gi < groups.size(); gi++) {
+                auto& G = groups[gi];
                 EE bsum = F.zero();
-                for (size_t q = 0; q < G.cols.size(); q++)             // evaluator/boundary.rs SingleValueConstraint
-                    bsum = F.add(bsum, F.mul_base(G.cc[q], f_sub(cur[G.cols[q]], G.values[q])));
+                for (size_t q = 0; q < G.e.size(); q++) {              // evaluator/boundary.rs Single / Small / LargePoly
+                    const BoundaryEntry& e = G.e[q];
+                    u64 val = e.poly.size() == 1 ? e.poly[0].v[0] : gtab[gi][q][(i + ce - (e.first_step * air.ce_blowup()) % ce) % ce];
+                    bsum = F.add(bsum, F.mul_base(e.cc, f_sub(cur[e.col], val)));
+                }
                 acc = F.add(acc, F.mul_base(bsum, f_inv(f_sub(f_exp(x, G.a), G.b))));  // :329-340
             }
-            for (auto& G : aux_groups) {  // evaluator/boundary.rs:228-260 aux_single_value
+            for (size_t gi = 0; gi < aux_groups.size(); gi++) {  // evaluator/boundary.rs:228-260 aux constraints
+                auto& G = aux_groups[gi];
                 EE bsum = F.zero();
-                for (size_t q = 0; q < G.cols.size(); q++) bsum = F.add(bsum, F.mul(F.sub(ac[G.cols[q]], G.values[q]), G.cc[q]));
+                for (size_t q = 0; q < G.e.size(); q++) {
+                    const BoundaryEntry& e = G.e[q];
+                    EE val = e.poly[0];
+                    if (e.poly.size() > 1) {
+                        size_t idx = (i + ce - (e.first_step * air.ce_blowup()) % ce) % ce;
+                        val = F.zero();
+                        for (int k = 0; k < d; k++) val.v[k] = agtab[gi][q][idx * d + k];
+                    }
+                    bsum = F.add(bsum, F.mul(F.sub(ac[e.col], val), e.cc));
+                }
                 acc = F.add(acc, F.mul_base(bsum, f_inv(f_sub(f_exp(x, G.a), G.b))));
             }
             comp[i] = acc;
@@ -901,13 +940,14 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
         EE res = F.mul(t, F.mul(den, F.inv(num)));
         for (auto& G : boundary_groups(air, bcoef)) {
             EE bs = F.zero();
-            for (size_t q = 0; q < G.cols.size(); q++)
-                bs = F.add(bs, F.mul(F.sub(t_cur[G.cols[q]], F.from_base(G.values[q])), G.cc[q]));
+            for (auto& e : G.e)  // BoundaryConstraint::evaluate_at (air/src/air/boundary/constraint.rs:128-147)
+                bs = F.add(bs, F.mul(F.sub(t_cur[e.col], horner_ext(F, e.poly.data(), e.poly.size(), F.mul_base(z, e.x_offset))), e.cc));
             res = F.add(res, F.mul(bs, F.inv(F.sub(F.exp(z, G.a), F.from_base(G.b)))));
         }
         for (auto& G : aux_boundary_groups(air, ccoef.data() + nT + air.asserts.size())) {  // evaluator.rs:76-83
             EE bs = F.zero();
-            for (size_t q = 0; q < G.cols.size(); q++) bs = F.add(bs, F.mul(F.sub(t_cur[c + G.cols[q]], G.values[q]), G.cc[q]));
+            for (auto& e : G.e)
+                bs = F.add(bs, F.mul(F.sub(t_cur[c + e.col], horner_ext(F, e.poly.data(), e.poly.size(), F.mul_base(z, e.x_offset))), e.cc));
             res = F.add(res, F.mul(bs, F.inv(F.sub(F.exp(z, G.a), F.from_base(G.b)))));
         }
         EE res2 = F.zero();

@@ -44,8 +44,12 @@ class AirBuilder:
         self.prog.append((OUT, len(self.degrees), reg, 0))
         self.degrees.append((base_degree, list(cycles)))
 
-    def assert_single(self, column, step, value): self.asserts.append((column, step, 0, int(value) % P))
-    def assert_periodic(self, column, first_step, stride, value): self.asserts.append((column, first_step, stride, int(value) % P))
+    # Assertion::single / ::periodic / ::sequence (air/src/air/assertions/mod.rs:62-120)
+    def assert_single(self, column, step, value): self.asserts.append((column, step, 0, 1, int(value) % P))
+    def assert_periodic(self, column, first_step, stride, value): self.asserts.append((column, first_step, stride, 1, int(value) % P))
+
+    def assert_sequence(self, column, first_step, stride, values):
+        self.asserts.append((column, first_step, stride, len(values)) + tuple(int(v) % P for v in values))
 
     def aux(self, aux_width, num_rands):
         """Declares the auxiliary segment; returns the builder for its constraint program."""
@@ -115,7 +119,12 @@ class AuxSegment:
         self.degrees.append((base_degree, list(cycles)))
 
     def assert_single(self, column, step, value=(0, 0, 0)):
-        self.asserts.append((column, step, 0) + tuple(int(v) % P for v in value))
+        self.asserts.append((column, step, 0, 1) + tuple(int(v) % P for v in value))
+
+    def assert_sequence(self, column, first_step, stride, values):
+        """values: list of (v0, v1, v2) elements of E, one per asserted step."""
+        flat = tuple(int(x) % P for v in values for x in v)
+        self.asserts.append((column, first_step, stride, len(values)) + flat)
 
     def build(self):
         d = [self.aw, self.nr, len(self.degrees)]
@@ -257,3 +266,27 @@ def perm_rap(n, seed=5):
         return aux
 
     return A.build(), tr, builder
+
+
+def sequence_mix(n, stride=4):
+    """Sequence assertions (Assertion::sequence): every `stride`-th value of x0 starting at step 1 is asserted
+    (n / stride values: a LargePoly constraint for n / stride >= 63, a SmallPoly one below,
+    prover/src/constraints/evaluator/boundary.rs:340,389), next to single and periodic assertions that
+    share and do not share its divisor."""
+    tr = np.zeros((3, n), dtype=np.uint64)
+    a, b = 2, 3
+    for i in range(n):
+        tr[0, i], tr[1, i], tr[2, i] = a, b, 7 if i % stride == 1 else (i % 5)
+        a = (a * a + b) % P
+        b = (b + a) % P
+    A = AirBuilder(3)
+    A.pub = [int(tr[1, n - 1])]
+    A.constraint(A.sub(A.nxt(0), A.add(A.mul(A.cur(0), A.cur(0)), A.cur(1))), 2)
+    A.constraint(A.sub(A.nxt(1), A.add(A.cur(1), A.nxt(0))), 1)
+    A.assert_single(0, 0, 2)
+    A.assert_single(1, 0, 3)
+    A.assert_single(1, n - 1, int(tr[1, n - 1]))
+    A.assert_sequence(0, 1, stride, [int(v) for v in tr[0, 1::stride]])   # first_step != 0: x offset g^-1
+    A.assert_periodic(2, 1, stride, 7)                                    # same divisor as the sequence
+    A.assert_sequence(1, 0, n // 2, [int(tr[1, 0]), int(tr[1, n // 2])])  # two values, first_step 0
+    return A.build(), tr

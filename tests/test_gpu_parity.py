@@ -203,3 +203,46 @@ def test_partitioned_row_hash_vs_oracle(ctx, oracle, h, cols, psize):
     want = oracle.hash_rows(h, np.ascontiguousarray(x.T), partition_size=psize)
     assert (lv == want).all()
     assert (nd == oracle.merkle_nodes(h, want)).all()
+
+
+def test_field_ops_edge_cases(ctx):
+    """Device field arithmetic (gl64.cuh) on operands chosen to reach every reduction path. Uniform random
+    data takes the canonicalisation step (result in [p, 2^64) before the final subtraction) with
+    probability 2^-32 per operation, so the NTT / proof parity tests never see it: products that land in
+    [0, 2^32) and operands next to 0, 2^32, p are generated here and checked against Python integers."""
+    import torch
+    P = wf.P
+    rng = np.random.default_rng(99)
+    edge = [0, 1, 2, 3, P - 1, P - 2, P - 3, 2**32 - 2, 2**32 - 1, 2**32, 2**32 + 1, 2**33 - 1, 2**63, 2**63 - 1,
+            P - 2**32, P - 2**32 + 1, P - 2**32 - 1, 0xFFFFFFFF00000000, 0xFFFFFFFE00000001, 0x00000001FFFFFFFF, 2**48, 2**24]
+    a, b = [], []
+    for x in edge:
+        for y in edge:
+            a.append(x); b.append(y)
+    small = [0, 1, 2, 5, 2**16, 2**31, 2**32 - 3, 2**32 - 2, 2**32 - 1, 2**32, 2**32 + 1, P - 1, P - 2, P - 2**32, P - 2**32 + 5]
+    for _ in range(6000):  # a * b = c with c in the ranges where the pre-canonical result exceeds p
+        x = int(rng.integers(1, 2**63)) * 2 % P or 1
+        c = small[int(rng.integers(0, len(small)))] if rng.random() < 0.5 else int(rng.integers(0, 2**32))
+        a.append(x); b.append(c * pow(x, P - 2, P) % P)
+    for _ in range(4000):
+        a.append(int(rng.integers(0, 2**63)) * 2 % P); b.append(int(rng.integers(0, 2**63)) * 2 % P)
+    for _ in range(2000):  # sums / differences around the wrap points
+        x = int(rng.integers(0, 2**63)) * 2 % P
+        d = int(rng.integers(0, 4)) - 2
+        a.append(x); b.append((P - x + d) % P)
+    n = len(a)
+    ta = torch.from_numpy(np.array(a, dtype=np.uint64).view(np.int64)).cuda()
+    tb = torch.from_numpy(np.array(b, dtype=np.uint64).view(np.int64)).cuda()
+    out = torch.empty(22 * n, dtype=torch.int64, device="cuda")
+    ctx.field_ops_dev(ta.data_ptr(), tb.data_ptr(), n, out.data_ptr())
+    ctx.sync()
+    got = out.cpu().numpy().view(np.uint64).reshape(22, n)
+    shifts = [1, 3, 6, 12, 24, 31, 32, 33, 48, 63, 64, 65, 72, 80, 84, 90, 95, 96]
+    for i in range(n):
+        x, y = a[i], b[i]
+        assert int(got[0, i]) == x * y % P, ("mul", hex(x), hex(y))
+        assert int(got[1, i]) == (x + y) % P, ("add/butterfly", hex(x), hex(y))
+        assert int(got[2, i]) == (x - y) % P, ("sub", hex(x), hex(y))
+        assert int(got[3, i]) == (pow(x, P - 2, P) if x else 0), ("inv", hex(x))
+        for k, sh in enumerate(shifts):
+            assert int(got[4 + k, i]) == (x << sh) % P, ("shift", sh, hex(x))

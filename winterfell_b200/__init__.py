@@ -80,6 +80,7 @@ _SIGS = [
     ("wf_hash_rows_dev", C.c_int, [vp, C.c_int, vp, C.c_size_t, C.c_uint32, vp]),
     ("wf_merkle_dev", C.c_int, [vp, C.c_int, vp, C.c_size_t, vp]),
     ("wf_fri_fold_dev", C.c_int, [vp, vp, C.c_size_t, C.c_int, C.c_uint32, u64p, vp]),
+    ("wf_field_ops_dev", C.c_int, [vp, vp, vp, C.c_size_t, vp]),
     ("wf_host_hash_elements", C.c_int, [C.c_int, u64p, C.c_size_t, u8p]),
     ("wf_host_merge", C.c_int, [C.c_int, u8p, u8p]),
     ("wf_host_merge_with_int", C.c_int, [C.c_int, u8p, C.c_uint64, u8p]),
@@ -328,6 +329,9 @@ class Context:
 
     def merkle_dev(self, hash_id, d_leaves, nleaves, d_nodes):
         self.check(self.L.wf_merkle_dev(self.h, hash_id, vp(d_leaves), nleaves, vp(d_nodes)))
+
+    def field_ops_dev(self, d_a, d_b, n, d_out):
+        self.check(self.L.wf_field_ops_dev(self.h, vp(d_a), vp(d_b), n, vp(d_out)))
 
     def fri_fold_dev(self, d_evals, length, ext_degree, folding, alpha, d_next):
         a_, ap = _u64(alpha)

@@ -340,6 +340,27 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
 // C ABI
 // =================================================================================================
 template <int K>
+__device__ __forceinline__ void field_shift_store(u64 a, u64* out, size_t n, size_t i, int slot) { out[(4 + slot) * n + i] = gl_mul_2exp<K>(a); }
+__global__ void field_ops_kernel(const u64* a, const u64* b, size_t n, u64* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 x = a[i], y = b[i];
+    out[i] = gl_mul(x, y);
+    out[n + i] = gl_add(x, y);
+    out[2 * n + i] = gl_sub(x, y);
+    out[3 * n + i] = x ? gl_inv(x) : 0;
+    u64 s = x, d = y;
+    gl_butterfly(s, d);
+    if (s != out[n + i] || d != out[2 * n + i]) out[n + i] = ~0ULL;  // butterfly must agree with add / sub
+    field_shift_store<1>(x, out, n, i, 0);   field_shift_store<3>(x, out, n, i, 1);   field_shift_store<6>(x, out, n, i, 2);
+    field_shift_store<12>(x, out, n, i, 3);  field_shift_store<24>(x, out, n, i, 4);  field_shift_store<31>(x, out, n, i, 5);
+    field_shift_store<32>(x, out, n, i, 6);  field_shift_store<33>(x, out, n, i, 7);  field_shift_store<48>(x, out, n, i, 8);
+    field_shift_store<63>(x, out, n, i, 9);  field_shift_store<64>(x, out, n, i, 10); field_shift_store<65>(x, out, n, i, 11);
+    field_shift_store<72>(x, out, n, i, 12); field_shift_store<80>(x, out, n, i, 13); field_shift_store<84>(x, out, n, i, 14);
+    field_shift_store<90>(x, out, n, i, 15); field_shift_store<95>(x, out, n, i, 16); field_shift_store<96>(x, out, n, i, 17);
+}
+
+template <int K>
 static u64 m2e(u64 x) { return gl_mul_2exp<K>(x); }
 
 extern "C" {
@@ -951,6 +972,17 @@ int wf_merkle_dev(wf_ctx* ctx, int hash_id, const uint8_t* d_leaves, size_t nlea
     if (nleaves < 2 || (nleaves & (nleaves - 1))) return wf_fail(ctx, WF_ERR_INVALID, "number of leaves must be a power of two >= 2");
     CK(commit_merkle_nodes(hash_id, (const u64*)d_leaves, nleaves, (u64*)d_nodes, ctx->st));
     ctx->launches += merkle_launches(nleaves);
+    return WF_OK;
+}
+// field-arithmetic self-test hook: out[0..n) = a*b, out[n..2n) = a+b, out[2n..3n) = a-b,
+// out[3n..4n) = 1/a (0 for a = 0), then out[(4+k) n ..) = a * 2^shift[k] for the 18 compile-time shifts
+// the mini-DFTs use. Inputs canonical. Exists because uniform random data reaches the reduction's
+// canonicalisation branch with probability 2^-32 per operation: tests feed crafted operands.
+int wf_field_ops_dev(wf_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, size_t n, uint64_t* d_out) {
+    if (!ctx || !d_a || !d_b || !d_out || n == 0) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    field_ops_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->st>>>(d_a, d_b, n, d_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
     return WF_OK;
 }
 int wf_fri_fold_dev(wf_ctx* ctx, const uint64_t* d_evals, size_t len, int d, uint32_t folding, const uint64_t* alpha,

@@ -117,44 +117,96 @@ __device__ __forceinline__ void gl_butterfly(u64& a, u64& b) {
     a = s;
     b = d;
 }
-// lo + 2^64 hi mod p, canonical: x0 + 2^32 x1 + (2^32 - 1) x2 - x3.  2 FMA-pipe + ~12 ALU.
+// r in [0, 2^64) -> [0, p): r >= p exactly when hi = 2^32 - 1 and lo >= 1, i.e. when r + (2^32 - 1)
+// carries out of 64 bits; then r - p = (lo - 1, 0) = (lo - carry, hi + carry). Two carry-only adds, the
+// carry bit (IMAD.X) and two 32-bit adds. (One add chain only: PTX's CC.CF after add.cc must not be fed
+// to subc — ptxas implements sub chains with the inverted flag.) The compare/branch form of this step
+// was if-converted by ptxas into 6-7 ALU instructions and was 20 % of all instructions the NTT issued
+// (ncu source view, profiles/r1_ntt_pass_v2_summary.txt).
+__device__ __forceinline__ u64 gl_canon(u64 r) {
+    u64 o;
+    asm("{\n\t"
+        ".reg .u32 r0, r1, t0, t1, k;\n\t"
+        "mov.b64 {r0, r1}, %1;\n\t"
+        "add.cc.u32 t0, r0, 0xffffffff;\n\t"
+        "addc.cc.u32 t1, r1, 0;\n\t"
+        "addc.u32 k, 0, 0;\n\t"
+        "sub.u32 r0, r0, k;\n\t"
+        "add.u32 r1, r1, k;\n\t"
+        "mov.b64 %0, {r0, r1};\n\t"
+        "}"
+        : "=l"(o)
+        : "l"(r));
+    return o;
+}
+// lo + 2^64 hi mod p, canonical: V = x0 + 2^32 x1 + (2^32 - 1) x2 - x3 as W + adj * 2^64 with
+// adj = carry - borrow in {-1, 0, 1}; then W + adj * (2^32 - 1), which cannot wrap: adj = 1 means
+// V < 2^65 - 2^33 + 1 so W < 2^64 - 2^33 + 1; adj = -1 means V > -2^32 so W > 2^64 - 2^32.
+// The mad.lo.cc / madc.hi.cc pair compiles to IMAD.WIDE.U32 with carry predicates (FMA pipe).
 __device__ __forceinline__ u64 gl_reduce128(u64 lo, u64 hi) {
     u64 r;
     asm("{\n\t"
-        ".reg .u32 x0, x1, x2, x3, m, c;\n\t"
+        ".reg .u32 c0, c1, c2, c3, k, m;\n\t"
+        ".reg .s32 adj;\n\t"
         ".reg .u64 t;\n\t"
-        "mov.b64 {x0, x1}, %1;\n\t"
-        "mov.b64 {x2, x3}, %2;\n\t"
-        "sub.cc.u32 x0, x0, x3;\n\t"            // lo - x3, borrow -> -(2^32 - 1)
-        "subc.cc.u32 x1, x1, 0;\n\t"
+        "mov.b64 {c0, c1}, %1;\n\t"
+        "mov.b64 {c2, c3}, %2;\n\t"
+        "mad.lo.cc.u32 c0, c2, 0xffffffff, c0;\n\t"
+        "madc.hi.cc.u32 c1, c2, 0xffffffff, c1;\n\t"
+        "addc.u32 k, 0, 0;\n\t"
+        "sub.cc.u32 c0, c0, c3;\n\t"
+        "subc.cc.u32 c1, c1, 0;\n\t"
         "subc.u32 m, 0, 0;\n\t"
-        "sub.cc.u32 x0, x0, m;\n\t"
-        "subc.u32 x1, x1, 0;\n\t"
-        "mul.wide.u32 t, x2, 0xffffffff;\n\t"   // x2 * (2^32 - 1)
-        "mov.b64 {x2, x3}, t;\n\t"
-        "add.cc.u32 x0, x0, x2;\n\t"
-        "addc.cc.u32 x1, x1, x3;\n\t"
-        "addc.u32 c, 0, 0;\n\t"
-        "mov.b64 t, {x0, x1};\n\t"
-        "mad.wide.u32 t, c, 0xffffffff, t;\n\t" // carry: + (2^32 - 1); cannot wrap again
-        "mov.b64 %0, t;\n\t"
+        "add.s32 adj, k, m;\n\t"
+        "mov.b64 t, {c0, c1};\n\t"
+        "mad.wide.s32 t, adj, -1, t;\n\t"
+        "mov.b64 {c0, c1}, t;\n\t"
+        "add.u32 c1, c1, adj;\n\t"
+        "mov.b64 %0, {c0, c1};\n\t"
         "}"
         : "=l"(r)
         : "l"(lo), "l"(hi));
-    // r is in [0, 2^64); r >= p has probability 2^-32 for uniform r: a predicated branch that is
-    // (almost) never taken is cheaper than the compare/select pair of a branch-free form
-    if (__builtin_expect(r >= GL_P, 0)) r -= GL_P;
-    return r;
+    return gl_canon(r);
 }
+// 64 x 64 -> 128 as even columns (a0 b0 | a1 b1) plus the odd column a0 b1 + a1 b0 shifted by 32,
+// carries chained through the multiply-adds (IMAD.WIDE.U32 with carry in / out), fused with the
+// reduction above.
 __device__ __forceinline__ u64 gl_mul(u64 a, u64 b) {
-    // 4 IMAD.WIDE for the 128-bit product (FMA pipe), then the reduction above
-    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
-    u64 p00 = (u64)a0 * b0;
-    u64 mid = (u64)a0 * b1 + (p00 >> 32);
-    u64 mid2 = (u64)a1 * b0 + (u32)mid;
-    u64 hi = (u64)a1 * b1 + (mid >> 32) + (mid2 >> 32);
-    u64 lo = (mid2 << 32) | (u32)p00;
-    return gl_reduce128(lo, hi);
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 a0, a1, b0, b1, c0, c1, c2, c3, o0, o1, o2, k, m;\n\t"
+        ".reg .s32 adj;\n\t"
+        ".reg .u64 t;\n\t"
+        "mov.b64 {a0, a1}, %1;\n\t"
+        "mov.b64 {b0, b1}, %2;\n\t"
+        "mul.lo.u32 c0, a0, b0;\n\t"
+        "mul.hi.u32 c1, a0, b0;\n\t"
+        "mul.lo.u32 c2, a1, b1;\n\t"
+        "mul.hi.u32 c3, a1, b1;\n\t"
+        "mul.lo.u32 o0, a0, b1;\n\t"
+        "mul.hi.u32 o1, a0, b1;\n\t"
+        "mad.lo.cc.u32 o0, a1, b0, o0;\n\t"
+        "madc.hi.cc.u32 o1, a1, b0, o1;\n\t"
+        "addc.u32 o2, 0, 0;\n\t"
+        "add.cc.u32 c1, c1, o0;\n\t"
+        "addc.cc.u32 c2, c2, o1;\n\t"
+        "addc.u32 c3, c3, o2;\n\t"
+        "mad.lo.cc.u32 c0, c2, 0xffffffff, c0;\n\t"
+        "madc.hi.cc.u32 c1, c2, 0xffffffff, c1;\n\t"
+        "addc.u32 k, 0, 0;\n\t"
+        "sub.cc.u32 c0, c0, c3;\n\t"
+        "subc.cc.u32 c1, c1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "add.s32 adj, k, m;\n\t"
+        "mov.b64 t, {c0, c1};\n\t"
+        "mad.wide.s32 t, adj, -1, t;\n\t"
+        "mov.b64 {c0, c1}, t;\n\t"
+        "add.u32 c1, c1, adj;\n\t"
+        "mov.b64 %0, {c0, c1};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(a), "l"(b));
+    return gl_canon(r);
 }
 #else
 GL_HD u64 gl_add(u64 a, u64 b) { return gl_add_host(a, b); }
