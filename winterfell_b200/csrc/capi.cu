@@ -297,11 +297,12 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
         ctx->launches++;
         return WF_OK;
     }
-    // Cosets per launch: a narrow matrix (few segments) gives fewer tiles than SMs, so all its cosets go
-    // into ONE launch (grid.z = coset) with a b-times larger scratch; wide matrices run coset by coset so
-    // that the scratch Y stays n*c words and is re-read from L2.
-    const size_t tiles = (((size_t)1 << logC) * polys.W / NTT_LANES) * polys.nseg();
-    const u32 kb = tiles < 4 * 148 ? b : 1;
+    // Cosets per launch (grid.z = coset): as many as keep the scratch Y within 1 GiB. The passes are
+    // ALU-bound (DRAM ~10 %), so a scratch that no longer fits L2 costs nothing, while one launch per
+    // coset leaves a partial last wave every time (1024 tiles on 296 resident blocks: measured 6 % on
+    // the cfg2 trace LDE, 35 % on its one-column composition LDE).
+    u32 kb = b;
+    while (kb > 1 && polys.words() * 8 * kb > ((size_t)1 << 30)) kb >>= 1;
     SegMatrix y = polys;
     void* yp;
     CKI(wf_dev_alloc(ctx, polys.words() * 8 * kb, &yp));
