@@ -160,9 +160,11 @@ int wf_prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, uint3
  *                                                             [2w,2w+nP) periodic values, then temporaries;
  *                                                             op 0 ADD, 1 SUB, 2 MUL (dst = r[a] op r[b]),
  *                                                             3 CONST (dst = constants[a]), 4 OUT (result[dst] = r[a])
- *    nA, {column, first_step, stride, value} x nA            Assertion::single (stride 0) / ::periodic
+ *    nA, {column, first_step, stride, nvals, values...} x nA  Assertion::single (stride 0, 1 value) / ::periodic
+ *                                                             (stride > 0, 1 value) / ::sequence (stride > 0,
+ *                                                             nvals = n / stride values) (assertions/mod.rs:62-120)
  *    nPub, public input elements...,  num_transition_exemptions]
- * Not supported yet: sequence assertions. Multi-segment descriptions go through wf_prove_air_aux. */
+ * Multi-segment descriptions go through wf_prove_air_aux. */
 int wf_prove_air(wf_ctx* ctx, const uint64_t* air_desc, size_t air_desc_len, const uint64_t* const* trace_cols, int mont,
                  uint32_t log_n, const uint32_t* opts, uint8_t* proof, size_t* proof_len);
 
@@ -175,7 +177,8 @@ int wf_prove_air(wf_ctx* ctx, const uint64_t* air_desc, size_t air_desc_len, con
  *                                                            [2w,2w+aw) aux current, [2w+aw,2w+2aw) aux next, then
  *                                                            nP periodic values, then the random elements, then
  *                                                            temporaries; same opcodes
- *    nAa, {column, first_step, stride, v0, v1, v2} x nAa]    Air::get_aux_assertions (:279), value in E
+ *    nAa, {column, first_step, stride, nvals, {v0, v1, v2} x nvals} x nAa]   Air::get_aux_assertions (:279),
+ *                                                            values in E (first ext words used)
  * After the main commitment the prover draws num_rand_elements E elements from the public coin
  * (Air::get_aux_rand_elements, air/mod.rs:292-306) and calls `aux_builder` (Prover::build_aux_trace,
  * prover/src/lib.rs:236-247) on the HOST: rand_elements = [num_rand][d] words, aux_out = [aux_width][n][d]

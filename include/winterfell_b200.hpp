@@ -112,7 +112,7 @@ struct Air {
         rd();  // num_regs
         { u64 ni = rd(); p += 4 * ni; }
         num_assertions = rd();
-        p += 4 * num_assertions;
+        for (size_t i = 0; i < num_assertions; i++) { p += 3; u64 nv = rd(); p += nv; }  // column, first_step, stride, nvals, values
         { u64 np = rd(); for (u64 i = 0; i < np; i++) pub_inputs.push_back(rd()); }
         num_exemptions = (u32)rd();
         if (p == desc.size()) return;
@@ -122,7 +122,7 @@ struct Air {
         rd();
         { u64 ni = rd(); p += 4 * ni; }
         num_aux_assertions = rd();
-        p += 6 * num_aux_assertions;
+        for (size_t i = 0; i < num_aux_assertions; i++) { p += 3; u64 nv = rd(); p += 3 * nv; }
         if (p != desc.size()) throw Error(WF_ERR_INVALID, "malformed AIR description");
     }
     size_t num_transition_constraints() const { return degrees.size() + aux_degrees.size(); }  // context.rs:205

@@ -213,6 +213,9 @@ def periodic_mix(n, cycle=8):
     return A.build(), tr
 
 
+PERM_RAP_AUX_WIDTH = 3
+
+
 def perm_rap(n, seed=5):
     """Two-segment AIR in the style of examples/src/rescue_raps (a randomised AIR with preprocessing):
     main columns x0, x1 (the FibSmall pair) and b = a permutation of x0's first n-1 values; the aux
@@ -220,6 +223,7 @@ def perm_rap(n, seed=5):
     columns, a periodic column and both random elements:
         p' * (b + gamma) = p * (x0 + gamma),   p[0] = p[n-1] = 1
         q' = q + alpha * k * x1 * p,           q[0] = 0
+        c' = c + 1,                            c[1 + i n/4] asserted as a SEQUENCE (values in E)
     Returns (description, main trace, aux builder(rand [2, d]) -> [2, n, d])."""
     from oracle import oracle as O
     rng = np.random.default_rng(seed)
@@ -241,7 +245,7 @@ def perm_rap(n, seed=5):
     A.assert_single(0, 0, 1)
     A.assert_single(1, 0, 1)
     A.assert_single(1, n - 1, int(tr[1, n - 1]))
-    X = A.aux(2, 2)
+    X = A.aux(PERM_RAP_AUX_WIDTH, 2)
     gamma, alpha = X.rnd(0), X.rnd(1)
     lhs = X.mul(X.anxt(0), X.add(X.cur(2), gamma))
     rhs = X.mul(X.acur(0), X.add(X.cur(0), gamma))
@@ -251,16 +255,19 @@ def perm_rap(n, seed=5):
     X.assert_single(0, 0, (1, 0, 0))
     X.assert_single(0, n - 1, (1, 0, 0))
     X.assert_single(1, 0, (0, 0, 0))
+    one = X.const(1)
+    X.constraint(X.sub(X.anxt(2), X.add(X.acur(2), one)), 1)
+    X.assert_sequence(2, 1, n // 4, [(5 + 1 + k * (n // 4), 0, 0) for k in range(4)])
 
     def builder(rand):
         d = rand.shape[1]
         g, al = rand[0], rand[1]
         emb = lambda v: np.array([int(v)] + [0] * (d - 1), dtype=np.uint64)
         eadd = lambda x, y: np.array([(int(x[i]) + int(y[i])) % P for i in range(d)], dtype=np.uint64)
-        aux = np.zeros((2, n, d), dtype=np.uint64)
+        aux = np.zeros((PERM_RAP_AUX_WIDTH, n, d), dtype=np.uint64)
         p, q = emb(1), emb(0)
         for i in range(n):
-            aux[0, i], aux[1, i] = p, q
+            aux[0, i], aux[1, i], aux[2, i] = p, q, emb(5 + i)
             q = eadd(q, O.ext_mul(O.ext_mul(al, emb(k[i % 4] * int(tr[1, i]) % P)), p))
             p = O.ext_mul(O.ext_mul(p, eadd(emb(tr[0, i]), g)), O.ext_inv(eadd(emb(tr[2, i]), g)))
         return aux

@@ -106,8 +106,8 @@ def test_aux_segment_vs_oracle(ctx, oracle, log_n, ext, h, batch):
     # host builds the aux columns over E -> aux commit -> constraints over both segments
     desc, trace, builder = airs.perm_rap(1 << log_n)
     opts = oracle.make_opts(num_queries=24, blowup=8, grinding=2, ext=ext, folding=4, rem_max_deg=7, batch_c=batch, batch_d=batch, hash_id=h)
-    got = ctx.prove_air_aux(desc, trace, opts, builder, 2, 2)
-    assert got == oracle.prove_air_aux(desc, trace, opts, builder, 2, 2)
+    got = ctx.prove_air_aux(desc, trace, opts, builder, airs.PERM_RAP_AUX_WIDTH, 2)
+    assert got == oracle.prove_air_aux(desc, trace, opts, builder, airs.PERM_RAP_AUX_WIDTH, 2)
     assert oracle.verify_air(desc, got, h) == 0
     # single-segment entry point refuses a multi-segment description
     with pytest.raises(wf.WfError):
@@ -120,8 +120,8 @@ def test_aux_segment_montgomery_io(ctx, oracle):
     opts = oracle.make_opts(num_queries=16, blowup=8, ext=2, folding=4, rem_max_deg=7)
     to_m = np.vectorize(lambda v: oracle.to_mont(int(v)), otypes=[np.uint64])
     from_m = np.vectorize(lambda v: oracle.from_mont(int(v)), otypes=[np.uint64])
-    got = ctx.prove_air_aux(desc, to_m(trace), opts, lambda r: to_m(builder(from_m(r))), 2, 2, mont=True)
-    assert got == oracle.prove_air_aux(desc, trace, opts, builder, 2, 2)
+    got = ctx.prove_air_aux(desc, to_m(trace), opts, lambda r: to_m(builder(from_m(r))), airs.PERM_RAP_AUX_WIDTH, 2, mont=True)
+    assert got == oracle.prove_air_aux(desc, trace, opts, builder, airs.PERM_RAP_AUX_WIDTH, 2)
 
 
 def test_aux_segment_inconsistent_trace_is_rejected(ctx, oracle):
@@ -129,5 +129,31 @@ def test_aux_segment_inconsistent_trace_is_rejected(ctx, oracle):
     bad = trace.copy()
     bad[2, 7] = (int(bad[2, 7]) + 1) % airs.P  # b is no longer a permutation of x0
     opts = oracle.make_opts(num_queries=16, blowup=8, ext=2, folding=4, rem_max_deg=7)
-    proof = ctx.prove_air_aux(desc, bad, opts, builder, 2, 2)
+    proof = ctx.prove_air_aux(desc, bad, opts, builder, airs.PERM_RAP_AUX_WIDTH, 2)
     assert oracle.verify_air(desc, proof) != 0
+
+
+# ---- sequence assertions (SmallPoly / LargePoly boundary constraints) ----
+@pytest.mark.parametrize("log_n", [6, 11])
+@pytest.mark.parametrize("ext,h,batch", [(1, wf.HASH_BLAKE3_256, 0), (3, wf.HASH_BLAKE3_256, 2)])
+def test_sequence_assertions_vs_oracle(ctx, oracle, log_n, ext, h, batch):
+    # n / 4 asserted values (16: the reference's Horner path; 512: its pre-evaluated table path,
+    # prover/src/constraints/evaluator/boundary.rs:340,389) with first_step = 1, sharing a divisor with a
+    # periodic assertion, plus a two-value sequence at first_step 0
+    desc, trace = airs.sequence_mix(1 << log_n)
+    opts = oracle.make_opts(num_queries=20, blowup=8, grinding=1, ext=ext, folding=4, rem_max_deg=7, batch_c=batch, batch_d=batch, hash_id=h)
+    got = ctx.prove_air(desc, trace, opts)
+    assert got == oracle.prove_air(desc, trace, opts)
+    assert oracle.verify_air(desc, got, h) == 0
+    # a description asserting a different sequence value does not verify this proof
+    bad = desc.copy()
+    i = int(np.nonzero(bad == np.uint64(trace[0, 5]))[0][0])  # trace[0, 5] is the second value of the sequence
+    bad[i] ^= np.uint64(1)
+    assert oracle.verify_air(bad, got, h) != 0
+
+
+def test_invalid_sequence_is_refused(ctx, oracle):
+    desc, trace = airs.sequence_mix(64)
+    opts = oracle.make_opts(num_queries=8, blowup=8)
+    with pytest.raises(wf.WfError):
+        ctx.prove_air(desc, trace[:, :32].copy(), opts)  # n / stride no longer equals the number of values

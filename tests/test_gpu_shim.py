@@ -52,6 +52,7 @@ def ctx():
     ("mulfib2", 9, 3, wf.HASH_BLAKE3_256, 2),
     ("periodic_mix", 11, 1, wf.HASH_BLAKE3_256, 0),
     ("periodic_mix", 8, 3, wf.HASH_RP64_256, 1),
+    ("sequence_mix", 9, 2, wf.HASH_BLAKE3_256, 0),
 ])
 def test_cpp_generate_proof_double(ctx, oracle, tmp_path, name, log_n, ext, h, batch):
     n = 1 << log_n
@@ -82,7 +83,7 @@ def test_cpp_double_aux_segment(ctx, oracle, tmp_path, ext):
         seen["cols"] = builder(rand)
         return seen["cols"]
 
-    want = oracle.prove_air_aux(desc, trace, opts, recording, 2, 2)
+    want = oracle.prove_air_aux(desc, trace, opts, recording, airs.PERM_RAP_AUX_WIDTH, 2)
     got = run_double(tmp_path, desc, trace, opts, aux=(seen["rand"], seen["cols"]))
     assert got == want
     assert oracle.verify_air(desc, got) == 0

@@ -67,17 +67,34 @@ def test_generic_airs_round_trip(oracle, name, ext):
 def test_aux_segment_roundtrip_and_tamper(oracle, ext):
     desc, trace, builder = airs.perm_rap(64)
     opts = oracle.make_opts(num_queries=16, blowup=8, grinding=2, ext=ext, folding=4, rem_max_deg=7)
-    proof = oracle.prove_air_aux(desc, trace, opts, builder, 2, 2)
+    proof = oracle.prove_air_aux(desc, trace, opts, builder, airs.PERM_RAP_AUX_WIDTH, 2)
     assert oracle.verify_air(desc, proof) == 0
     # Context carries (main width, aux width, aux rands): air/src/air/trace_info.rs:240-264
-    assert proof[0] == 3 and proof[1] == 2 and proof[2] == 2
+    assert proof[0] == 3 and proof[1] == airs.PERM_RAP_AUX_WIDTH and proof[2] == 2
     b = bytearray(proof)
     b[len(b) // 2] ^= 1
     assert oracle.verify_air(desc, bytes(b)) != 0
     # main trace inconsistent with the aux columns: the permutation argument fails at the OOD check
     bad = trace.copy()
     bad[2, 3] = (int(bad[2, 3]) + 1) % airs.P
-    assert oracle.verify_air(desc, oracle.prove_air_aux(desc, bad, opts, builder, 2, 2)) != 0
+    assert oracle.verify_air(desc, oracle.prove_air_aux(desc, bad, opts, builder, airs.PERM_RAP_AUX_WIDTH, 2)) != 0
     # a single-segment verifier description does not accept a two-segment proof
     single, _ = airs.fib_small_x(1, 64)
     assert oracle.verify_air(single, proof) != 0
+
+
+# ---- sequence assertions ----
+@pytest.mark.parametrize("n", [32, 256])
+def test_sequence_assertions_roundtrip(oracle, n):
+    desc, trace = airs.sequence_mix(n)
+    opts = oracle.make_opts(num_queries=16, blowup=8, ext=2, folding=4, rem_max_deg=7)
+    proof = oracle.prove_air(desc, trace, opts)
+    assert oracle.verify_air(desc, proof) == 0
+    bad = desc.copy()
+    i = int(np.nonzero(bad == np.uint64(trace[0, 5]))[0][0])
+    bad[i] ^= np.uint64(1)
+    assert oracle.verify_air(bad, proof) != 0
+    # the prover run on a trace that violates an asserted sequence value yields a rejected proof
+    t2 = trace.copy()
+    t2[2, 1] = 8  # periodic assertion (column 2, first step 1) expects 7; column 2 has no transition constraint
+    assert oracle.verify_air(desc, oracle.prove_air(desc, t2, opts)) != 0

@@ -134,6 +134,11 @@ struct GenEvalParams {
     const u32* e_col;
     const u64* e_val;
     const u64* e_cc;       // [entries][D]
+    // sequence assertions (Assertion::sequence): per entry the value polynomial evaluated over the CE
+    // domain (LargePolyConstraint, evaluator/boundary.rs:389-445); nullptr for single-value entries
+    const u64* const* e_tab;
+    const u32* e_tstride;  // words per table row
+    const u32* e_shift;    // (first_step * ce_blowup) mod ce
     const u64* tw_ce;      // w_ce^i, i < ce/2
     u64 zt[8];             // 1 / (x^n - 1) at CE step i mod ce_blowup
     u64 exempt[8];
@@ -152,6 +157,9 @@ struct GenEvalParams {
     const u32* ae_col;
     const u64* ae_val;     // [entries][D]
     const u64* ae_cc;      // [entries][D]
+    const u64* const* ae_tab;
+    const u32* ae_tstride;
+    const u32* ae_shift;
 };
 #define AUX_MAX_REGS 96
 template <int D, bool AUX>
@@ -210,8 +218,11 @@ __global__ void __launch_bounds__(128) generic_constraints_kernel(GenEvalParams 
     GlExt<D> acc = ext_mul_base(T, gl_mul(p.zt[i & (((size_t)1 << p.log_ce_blowup) - 1)], ex));
     for (u32 g = 0; g < p.num_groups; g++) {
         GlExt<D> B = ext_zero<D>();
-        for (u32 e = p.g_off[g]; e < p.g_off[g + 1]; e++)
-            B = ext_add(B, ext_mul_base(ld_ext<D>(p.e_cc + (size_t)e * D), gl_sub(r[p.e_col[e]], p.e_val[e])));
+        for (u32 e = p.g_off[g]; e < p.g_off[g + 1]; e++) {
+            u64 val = p.e_val[e];
+            if (const u64* tab = p.e_tab[e]) val = tab[(size_t)((u32)(i - p.e_shift[e]) & cemask) * p.e_tstride[e]];
+            B = ext_add(B, ext_mul_base(ld_ext<D>(p.e_cc + (size_t)e * D), gl_sub(r[p.e_col[e]], val)));
+        }
         // x^a = 7^a * w_ce^(i*a mod ce)
         u32 ia = (u32)(((u64)i * p.g_a[g]) & cemask);
         u64 wa = p.tw_ce[ia & (half - 1)];
@@ -222,8 +233,11 @@ __global__ void __launch_bounds__(128) generic_constraints_kernel(GenEvalParams 
     if constexpr (AUX) {  // evaluator/boundary.rs: aux_single_value constraints, values and columns in E
         for (u32 g = 0; g < p.num_agroups; g++) {
             GlExt<D> B = ext_zero<D>();
-            for (u32 e = p.ag_off[g]; e < p.ag_off[g + 1]; e++)
-                B = ext_add(B, ext_mul(ext_sub(ra[2 * p.w + p.ae_col[e]], ld_ext<D>(p.ae_val + (size_t)e * D)), ld_ext<D>(p.ae_cc + (size_t)e * D)));
+            for (u32 e = p.ag_off[g]; e < p.ag_off[g + 1]; e++) {
+                GlExt<D> val = ld_ext<D>(p.ae_val + (size_t)e * D);
+                if (const u64* tab = p.ae_tab[e]) val = ld_ext<D>(tab + (size_t)((u32)(i - p.ae_shift[e]) & cemask) * p.ae_tstride[e]);
+                B = ext_add(B, ext_mul(ext_sub(ra[2 * p.w + p.ae_col[e]], val), ld_ext<D>(p.ae_cc + (size_t)e * D)));
+            }
             u32 ia = (u32)(((u64)i * p.ag_a[g]) & cemask);
             u64 wa = p.tw_ce[ia & (half - 1)];
             if (ia & half) wa = gl_neg(wa);
@@ -470,8 +484,10 @@ struct Options {
 
 // Host-side AIR description (mirrors oracle/wf_prover.cpp `Air`; flat format documented at
 // wf_prove_air in include/winterfell_b200.h)
-struct AirAssertion { u64 column, first_step, stride, value; };
-struct AuxAssertion { u64 column, first_step, stride, value[3]; };
+// stride 0: Assertion::single; one value + stride: ::periodic; n / stride values: ::sequence
+// (air/src/air/assertions/mod.rs:62-120). Main values: one word each; aux values: three words each.
+struct AirAssertion { u64 column, first_step, stride; std::vector<u64> values; };
+typedef AirAssertion AuxAssertion;
 struct AirHost {
     u32 w = 0;
     // auxiliary segment (air/src/air/trace_info.rs:24-40): aw columns over E, nr random elements
@@ -539,9 +555,9 @@ static AirHost fib_air_host(u32 k, size_t n, const u64* results) {
     for (u32 j = 0; j < k; j++) {
         a.degrees.push_back({1, {}});
         a.degrees.push_back({1, {}});
-        a.asserts.push_back({2 * j, 0, 0, (u64)(j + 1)});
-        a.asserts.push_back({2 * j + 1, 0, 0, (u64)(j + 1)});
-        a.asserts.push_back({2 * j + 1, n - 1, 0, results[j]});
+        a.asserts.push_back({2 * j, 0, 0, {(u64)(j + 1)}});
+        a.asserts.push_back({2 * j + 1, 0, 0, {(u64)(j + 1)}});
+        a.asserts.push_back({2 * j + 1, n - 1, 0, {results[j]}});
     }
     return a;
 }
@@ -584,7 +600,9 @@ static bool parse_air_host(const u64* d, size_t len, AirHost& a) {
     if (!rd(cnt) || cnt == 0) return false;
     for (u64 i = 0; i < cnt; i++) {
         AirAssertion as;
-        if (!rd(as.column) || !rd(as.first_step) || !rd(as.stride) || !rd(as.value) || as.column >= a.w || as.value >= GL_P) return false;
+        u64 nv;
+        if (!rd(as.column) || !rd(as.first_step) || !rd(as.stride) || !rd(nv) || as.column >= a.w || nv == 0 || nv > len) return false;
+        for (u64 j = 0; j < nv; j++) { if (!rd(v) || v >= GL_P) return false; as.values.push_back(v); }
         a.asserts.push_back(as);
     }
     if (!rd(cnt)) return false;
@@ -593,7 +611,7 @@ static bool parse_air_host(const u64* d, size_t len, AirHost& a) {
     a.exemptions = (u32)v;
     if (p == len) return true;
     // optional aux section: [aw, nr, nTa, {base, ncyc, cyc...}*, aux_num_regs, nIa, {op,dst,a,b}*,
-    //                        nAa, {column, first_step, stride, v0, v1, v2}*]
+    //                        nAa, {column, first_step, stride, nvals, {v0, v1, v2} x nvals}*]
     if (!rd(v) || v == 0 || v > 255) return false;
     a.aw = (u32)v;
     if (!rd(v) || v > 255) return false;
@@ -621,9 +639,9 @@ static bool parse_air_host(const u64* d, size_t len, AirHost& a) {
     if (!rd(cnt) || cnt == 0) return false;
     for (u64 i = 0; i < cnt; i++) {
         AuxAssertion as;
-        if (!rd(as.column) || !rd(as.first_step) || !rd(as.stride) || !rd(as.value[0]) || !rd(as.value[1]) || !rd(as.value[2]) ||
-            as.column >= a.aw || as.value[0] >= GL_P || as.value[1] >= GL_P || as.value[2] >= GL_P)
-            return false;
+        u64 nv;
+        if (!rd(as.column) || !rd(as.first_step) || !rd(as.stride) || !rd(nv) || as.column >= a.aw || nv == 0 || nv > len) return false;
+        for (u64 j = 0; j < 3 * nv; j++) { if (!rd(v) || v >= GL_P) return false; as.values.push_back(v); }
         a.aux_asserts.push_back(as);
     }
     return p == len;
@@ -729,6 +747,47 @@ void write_queries(const GatherBatch& gb, size_t row_id, size_t dig_id, size_t n
     w.bytes(proof.v.data(), proof.v.size());
 }
 
+// Assertion validity (air/src/air/assertions/mod.rs:62-120, :166-230 validate_*)
+static int validate_assertions(wf_ctx* ctx, const std::vector<AirAssertion>& as, size_t n, size_t words_per_value, const char* what) {
+    for (auto& a : as) {
+        const size_t nv = a.values.size() / words_per_value;
+        bool ok = a.first_step < n && nv >= 1;
+        if (a.stride != 0) ok = ok && a.stride >= 2 && !(a.stride & (a.stride - 1)) && a.stride <= n && a.first_step < a.stride;
+        if (nv > 1) ok = ok && a.stride != 0 && !(nv & (nv - 1)) && nv * a.stride == n;   // sequence: one value per asserted step
+        if (!ok) return wf_fail(ctx, WF_ERR_INVALID, "invalid %s", what);
+    }
+    return WF_OK;
+}
+
+// Value table of a sequence assertion over the CE domain (LargePolyConstraint::new,
+// prover/src/constraints/evaluator/boundary.rs:400-425): interpolate the L values over the size-L
+// subgroup (air/src/air/boundary/constraint.rs:58-68), then evaluate that polynomial at 7 * w_ce^i for
+// all i (coefficient k scaled by 7^k, zero-padded, one plain NTT of size ce). The reference's
+// SmallPolyConstraint (Horner at x * g^(-first_step), :340-375) yields the same values, so one path
+// serves both; the x offset becomes the row shift (i - first_step * ce_blowup) mod ce (:428-445).
+static int sequence_table(wf_ctx* ctx, const u64* values, size_t L, u32 words_per_value, u32 dcols, size_t ce, wf_mat** out) {
+    std::vector<u64> cols((size_t)dcols * L);
+    std::vector<const u64*> ptr(dcols);
+    for (u32 q = 0; q < dcols; q++) {
+        for (size_t k = 0; k < L; k++) cols[q * L + k] = values[k * words_per_value + q];
+        ptr[q] = &cols[q * L];
+    }
+    wf_mat *vals, *poly, *padded;
+    CKI(wf_mat_from_host_columns(ctx, ptr.data(), dcols, L, 1, 0, &vals));  // synchronous w.r.t. `cols`
+    CKI(wf_mat_interpolate(ctx, vals, &poly));
+    wf_mat_free(ctx, vals);
+    CKI(wf_mat_alloc(ctx, ce, dcols, &padded));
+    CK(cudaMemsetAsync(padded->m.base, 0, padded->m.words() * 8, ctx->st));
+    // dcols <= 3 -> one segment: the first L rows of `padded` are the L rows of `poly`
+    CK(cudaMemcpyAsync(padded->m.base, poly->m.base, poly->m.words() * 8, cudaMemcpyDeviceToDevice, ctx->st));
+    wf_mat_free(ctx, poly);
+    CK(layout_scale_rows_by_powers(padded->m, GL_GENERATOR, ctx->st));
+    ctx->launches++;
+    int r = wf_mat_evaluate(ctx, padded, out);
+    wf_mat_free(ctx, padded);
+    return r;
+}
+
 // DefaultConstraintEvaluator::evaluate (prover/src/constraints/evaluator/default.rs:60-118) fused with
 // ConstraintEvaluationTable::combine (evaluation_table.rs:163-407): the combined, divisor-normalised
 // constraint evaluations over the CE domain = CompositionPolyTrace, as a (n * ce_blowup) x D matrix.
@@ -815,16 +874,25 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
         auto as = air.sorted_assertions();
         std::map<std::pair<u64, u64>, std::vector<size_t>> groups;
         for (size_t i = 0; i < as.size(); i++) groups[{as[i].stride, as[i].first_step}].push_back(i);
-        std::vector<u32> goff = {0}, ecol;
+        std::vector<u32> goff = {0}, ecol, etstride, eshift;
         std::vector<u64> ga, gb, goa, eval, ecc;
+        std::vector<const u64*> etab;
+        std::vector<wf_mat*> seq_tables;  // freed after the kernel
         for (auto& kv : groups) {
             u64 a = kv.first.first == 0 ? 1 : n / kv.first.first;
             ga.push_back(a);
             gb.push_back(kv.first.second == 0 ? 1 : gl_pow(g_tr, a * kv.first.second));
             goa.push_back(gl_pow(GL_GENERATOR, a));
             for (size_t i : kv.second) {
-                ecol.push_back((u32)as[i].column); eval.push_back(as[i].value);
+                ecol.push_back((u32)as[i].column); eval.push_back(as[i].values[0]);
                 for (int q = 0; q < D; q++) ecc.push_back(cc[n_tr + i].v[q]);
+                if (as[i].values.size() > 1) {
+                    wf_mat* t;
+                    CKI(sequence_table(ctx, as[i].values.data(), as[i].values.size(), 1, 1, ce, &t));
+                    seq_tables.push_back(t);
+                    etab.push_back(t->m.base); etstride.push_back((u32)t->m.W);
+                    eshift.push_back((u32)(((u64)as[i].first_step << log_ceb) & (ce - 1)));
+                } else { etab.push_back(nullptr); etstride.push_back(0); eshift.push_back(0); }
             }
             goff.push_back((u32)ecol.size());
         }
@@ -836,12 +904,16 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
         CKI(upload(ecol.data(), ecol.size() * 4, &dp)); p.e_col = (u32*)dp;
         CKI(upload(eval.data(), eval.size() * 8, &dp)); p.e_val = (u64*)dp;
         CKI(upload(ecc.data(), ecc.size() * 8, &dp)); p.e_cc = (u64*)dp;
+        CKI(upload(etab.data(), etab.size() * 8, &dp)); p.e_tab = (const u64* const*)dp;
+        CKI(upload(etstride.data(), etstride.size() * 4, &dp)); p.e_tstride = (u32*)dp;
+        CKI(upload(eshift.data(), eshift.size() * 4, &dp)); p.e_shift = (u32*)dp;
         CKI(wf_get_twiddles(ctx, log_n + log_ceb, &p.tw_ce));
         for (u32 i = 0; i < (1u << log_ceb); i++) p.zt[i] = zt[i];
         p.num_exempt = air.exemptions;
         for (u32 e = 0; e < air.exemptions; e++) p.exempt[e] = gl_pow(g_tr, n - air.exemptions + e);  // divisor.rs:31-41
-        std::vector<u32> agoff = {0}, aecol;
+        std::vector<u32> agoff = {0}, aecol, aetstride, aeshift;
         std::vector<u64> aga, agb, agoa, aeval, aecc, fa;
+        std::vector<const u64*> aetab;
         if (aw) {
             p.alde = alde->m; p.aw = aw; p.nr = air.nr; p.aprog_len = (u32)(air.aux_prog.size() / 4);
             CKI(upload(air.aux_prog.data(), air.aux_prog.size() * 4, &dp)); p.aprog = (u32*)dp;
@@ -858,7 +930,14 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
                 agoa.push_back(gl_pow(GL_GENERATOR, a));
                 for (size_t i : kv.second) {
                     aecol.push_back((u32)aas[i].column);
-                    for (int q = 0; q < D; q++) { aeval.push_back(aas[i].value[q]); aecc.push_back(cc[n_tr + n_mas + i].v[q]); }
+                    for (int q = 0; q < D; q++) { aeval.push_back(aas[i].values[q]); aecc.push_back(cc[n_tr + n_mas + i].v[q]); }
+                    if (aas[i].values.size() > 3) {
+                        wf_mat* t;
+                        CKI(sequence_table(ctx, aas[i].values.data(), aas[i].values.size() / 3, 3, D, ce, &t));
+                        seq_tables.push_back(t);
+                        aetab.push_back(t->m.base); aetstride.push_back((u32)t->m.W);
+                        aeshift.push_back((u32)(((u64)aas[i].first_step << log_ceb) & (ce - 1)));
+                    } else { aetab.push_back(nullptr); aetstride.push_back(0); aeshift.push_back(0); }
                 }
                 agoff.push_back((u32)aecol.size());
             }
@@ -870,12 +949,16 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
             CKI(upload(aecol.data(), aecol.size() * 4, &dp)); p.ae_col = (u32*)dp;
             CKI(upload(aeval.data(), aeval.size() * 8, &dp)); p.ae_val = (u64*)dp;
             CKI(upload(aecc.data(), aecc.size() * 8, &dp)); p.ae_cc = (u64*)dp;
+            CKI(upload(aetab.data(), aetab.size() * 8, &dp)); p.ae_tab = (const u64* const*)dp;
+            CKI(upload(aetstride.data(), aetstride.size() * 4, &dp)); p.ae_tstride = (u32*)dp;
+            CKI(upload(aeshift.data(), aeshift.size() * 4, &dp)); p.ae_shift = (u32*)dp;
             generic_constraints_kernel<D, true><<<(unsigned)((ce + 127) / 128), 128, 0, ctx->st>>>(p);
         } else {
             generic_constraints_kernel<D, false><<<(unsigned)((ce + 127) / 128), 128, 0, ctx->st>>>(p);
         }
         ctx->launches++;
         CK(cudaGetLastError());
+        for (wf_mat* t : seq_tables) wf_mat_free(ctx, t);  // stream-ordered pool: reuse is ordered after the kernel
     }
     CK(cudaStreamSynchronize(ctx->st));
     for (void* sp : scratch) wf_dev_free(ctx, sp);
@@ -953,12 +1036,8 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     if (aw && !aux_builder) return wf_fail(ctx, WF_ERR_INVALID, "multi-segment AIR needs an aux trace builder");
     if (log_ceb > log_b) return wf_fail(ctx, WF_ERR_INVALID, "blowup factor too small for the constraint degrees");
     for (auto& col : air.periodic) if (col.size() > n) return wf_fail(ctx, WF_ERR_INVALID, "periodic column longer than the trace");
-    for (auto& as : air.aux_asserts)
-        if (as.first_step >= n || (as.stride != 0 && (as.stride < 2 || (as.stride & (as.stride - 1)) || as.stride > n || as.first_step >= as.stride)))
-            return wf_fail(ctx, WF_ERR_INVALID, "invalid aux assertion");
-    for (auto& as : air.asserts)
-        if (as.first_step >= n || (as.stride != 0 && (as.stride < 2 || (as.stride & (as.stride - 1)) || as.stride > n || as.first_step >= as.stride)))
-            return wf_fail(ctx, WF_ERR_INVALID, "invalid assertion");
+    CKI(validate_assertions(ctx, air.aux_asserts, n, 3, "aux assertion"));
+    CKI(validate_assertions(ctx, air.asserts, n, 1, "assertion"));
     // ---- channel seed: Context::to_elements || pub inputs (channel.rs:57-82, context.rs:119-136) ----
     // TraceInfo::to_elements (air/src/air/trace_info.rs:209-238)
     const u64 ti0 = aw ? ((((((u64)c << 8) | 1) << 8) | aw) << 8) | air.nr : ((u64)c << 8);
@@ -1225,6 +1304,8 @@ extern "C" int wf_eval_constraints(wf_ctx* ctx, const uint64_t* air_desc, size_t
     if (air.aw && (!aux_lde || !aux_rand || aux_lde->m.rows != N || aux_lde->m.cols != air.aw * ext))
         return wf_fail(ctx, WF_ERR_INVALID, "aux LDE / random elements missing or of the wrong shape");
     for (auto& col : air.periodic) if (col.size() > ((size_t)1 << log_n)) return wf_fail(ctx, WF_ERR_INVALID, "periodic column longer than the trace");
+    CKI(validate_assertions(ctx, air.aux_asserts, (size_t)1 << log_n, 3, "aux assertion"));
+    CKI(validate_assertions(ctx, air.asserts, (size_t)1 << log_n, 1, "assertion"));
     const wf_mat* al = air.aw ? aux_lde : nullptr;
     switch (ext) {
         case 1: return eval_constraints_entry<1>(ctx, air, log_n, log_b, main_lde, al, coeffs, aux_rand, out);
