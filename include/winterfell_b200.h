@@ -91,6 +91,13 @@ int wf_mat_evaluate(wf_ctx* ctx, const wf_mat* polys, wf_mat** evals);
 /* RowMatrix::evaluate_polys_over::<8> (row_matrix.rs:84-100): LDE over the coset 7 * <w_N>,
  * N = n << log_blowup, row i <-> point 7 * w_N^i (natural order). */
 int wf_mat_lde(wf_ctx* ctx, const wf_mat* polys, uint32_t log_blowup, wf_mat** lde);
+/* DefaultTraceLde::new up to the commitment (prover/src/trace/trace_lde/default/mod.rs:63-100,
+ * build_trace_commitment :245-265) straight from HOST columns: equivalent to wf_mat_from_host_columns ->
+ * wf_mat_interpolate -> wf_mat_lde, but the upload of column chunk k+1 overlaps the layout / iNTT / LDE of
+ * chunk k (pass pinned host memory to get the overlap). Returns the coefficient matrix (TracePolyTable)
+ * and the LDE. */
+int wf_trace_lde_from_host(wf_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, size_t nrows, int mont, uint32_t log_blowup,
+                           wf_mat** polys, wf_mat** lde);
 /* fft::interpolate_poly_with_offset per column (math/src/fft/mod.rs:351) */
 int wf_mat_interpolate_with_offset(wf_ctx* ctx, const wf_mat* evals, uint64_t domain_offset, wf_mat** polys);
 

@@ -258,11 +258,7 @@ class TraceLde {
     // DefaultTraceLde::new (:63-100): interpolate, extend, commit the main segment
     TraceLde(wf_ctx* c, int h, const u64* const* main_trace_cols, u32 width, u32 log_n_, u32 blowup, u32 ext_, int mont)
         : ctx(c), hash_id(h), log_n(log_n_), blowup_factor(blowup), ext(ext_) {
-        wf_mat* trace;
-        check(ctx, wf_mat_from_host_columns(ctx, main_trace_cols, width, (size_t)1 << log_n, 1, mont, &trace));
-        check(ctx, wf_mat_interpolate(ctx, trace, &polys.main_polys));
-        wf_mat_free(ctx, trace);
-        check(ctx, wf_mat_lde(ctx, polys.main_polys, log2(blowup), &main_lde));
+        check(ctx, wf_trace_lde_from_host(ctx, main_trace_cols, width, (size_t)1 << log_n, mont, log2(blowup), &polys.main_polys, &main_lde));
         check(ctx, wf_commit_rows(ctx, hash_id, main_lde, &main_tree));
     }
     ~TraceLde() {

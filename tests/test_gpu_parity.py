@@ -246,3 +246,28 @@ def test_field_ops_edge_cases(ctx):
         assert int(got[3, i]) == (pow(x, P - 2, P) if x else 0), ("inv", hex(x))
         for k, sh in enumerate(shifts):
             assert int(got[4 + k, i]) == (x << sh) % P, ("shift", sh, hex(x))
+
+
+@pytest.mark.parametrize("ncols,log_n", [(8, 13), (16, 12), (12, 13), (3, 12), (5, 14), (8, 9), (24, 12)])
+def test_pipelined_trace_lde_equals_stepwise(ctx, oracle, ncols, log_n):
+    # wf_trace_lde_from_host cuts the columns into chunks (whole segments for >= 2 segments, halves of the
+    # one segment otherwise; small or narrow inputs take the plain path) and overlaps upload with compute:
+    # coefficients and LDE must equal from_host_columns -> interpolate -> lde, and the oracle
+    cols = oracle.rand_elems((ncols, 1 << log_n), 1000 + ncols)
+    polys, lde = ctx.trace_lde_from_host(cols, 3)
+    m = ctx.mat_from_host_columns(cols)
+    p2 = m.interpolate()
+    l2 = p2.lde(3)
+    assert (polys.to_columns() == p2.to_columns()).all()
+    assert (lde.to_rows() == l2.to_rows()).all()
+    if log_n <= 12:
+        assert (lde.to_rows() == oracle.lde_rows(oracle.interpolate_columns(cols), 8)).all()
+    to_m = np.vectorize(lambda v: oracle.to_mont(int(v)), otypes=[np.uint64])
+    if ncols == 3:
+        pm, lm = ctx.trace_lde_from_host(to_m(cols), 3, mont=True)
+        assert (lm.to_rows() == l2.to_rows()).all()
+        pm.free(); lm.free()
+    tree_a, tree_b = ctx.commit_rows(wf.HASH_BLAKE3_256, lde), ctx.commit_rows(wf.HASH_BLAKE3_256, l2)
+    assert tree_a.root() == tree_b.root()
+    for o in (polys, lde, m, p2, l2, tree_a, tree_b):
+        o.free()

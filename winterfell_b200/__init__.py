@@ -51,6 +51,7 @@ _SIGS = [
     ("wf_mat_interpolate", C.c_int, [vp, vp, C.POINTER(vp)]),
     ("wf_mat_evaluate", C.c_int, [vp, vp, C.POINTER(vp)]),
     ("wf_mat_lde", C.c_int, [vp, vp, C.c_uint32, C.POINTER(vp)]),
+    ("wf_trace_lde_from_host", C.c_int, [vp, C.POINTER(u64p), C.c_uint32, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(vp), C.POINTER(vp)]),
     ("wf_mat_interpolate_with_offset", C.c_int, [vp, vp, C.c_uint64, C.POINTER(vp)]),
     ("wf_commit_rows", C.c_int, [vp, C.c_int, vp, C.POINTER(vp)]),
     ("wf_commit_rows_partitioned", C.c_int, [vp, C.c_int, vp, C.c_uint32, C.POINTER(vp)]),
@@ -169,6 +170,16 @@ class Context:
         h = vp()
         self.check(self.L.wf_mat_from_host_columns(self.h, ptrs, c, n, ext_degree, int(mont), C.byref(h)))
         return Mat(self, h)
+
+    def trace_lde_from_host(self, cols, log_blowup, mont=False):
+        """cols: [ncols, n] uint64 host array (pinned for overlap). Returns (polys Mat, lde Mat)."""
+        a = np.ascontiguousarray(cols, dtype=np.uint64)
+        c, n = a.shape
+        ptrs = (u64p * c)(*[a[j].ctypes.data_as(u64p) for j in range(c)])
+        p, l = vp(), vp()
+        self.check(self.L.wf_trace_lde_from_host(self.h, ptrs, c, n, int(mont), log_blowup, C.byref(p), C.byref(l)))
+        self.sync()  # `a` may be a temporary: the asynchronous copies must finish before it is released
+        return Mat(self, p), Mat(self, l)
 
     def mat_from_device_columns(self, dptr, ncols, nrows):
         h = vp()

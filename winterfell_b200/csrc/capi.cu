@@ -61,11 +61,12 @@ void wf_dev_free(wf_ctx* ctx, void* p) {
     ctx->pool.insert({it->second, p});
     ctx->live.erase(it);
 }
-int wf_mat_alloc(wf_ctx* ctx, size_t rows, u32 cols, wf_mat** out) {
+int wf_mat_alloc(wf_ctx* ctx, size_t rows, u32 cols, wf_mat** out) { return wf_mat_alloc_w(ctx, rows, cols, seg_width_for(cols), out); }
+int wf_mat_alloc_w(wf_ctx* ctx, size_t rows, u32 cols, int W, wf_mat** out) {
     wf_mat* m = new wf_mat();
     m->m.rows = rows;
     m->m.cols = cols;
-    m->m.W = seg_width_for(cols);
+    m->m.W = W;
     m->m.seg_stride = rows * m->m.W;
     void* p;
     int r = wf_dev_alloc(ctx, m->m.words() * 8, &p);
@@ -165,6 +166,7 @@ static void pass_defaults(NttPassParams& p, const SegMatrix& in, const SegMatrix
     p.in_seg_stride = in.seg_stride;
     p.out_seg_stride = out.seg_stride;
     p.W = in.W;
+    p.out_W = (u32)out.W;
     p.out_row_mul = 1;
     p.cconst = 1;
 }
@@ -238,7 +240,9 @@ static int run_ntt(wf_ctx* ctx, const SegMatrix& in, SegMatrix& out, const SegMa
 }
 
 // LDE of coefficient columns over 7 * <w_N>: out has n << log_b rows, row b*j + k = P(7 w_N^k w_n^j).
-static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_n, u32 log_b) {
+// `out` may be a view of a wider matrix: segment width out.W >= polys.W, the polys' columns landing at
+// column offset out_col0 of each out row (column-chunked trace pipeline, wf_trace_lde_from_host).
+static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_n, u32 log_b, u32 out_col0 = 0) {
     u32 logR, logC;
     split_log(log_n, polys.W, &logR, &logC);
     u32 b = 1u << log_b;
@@ -278,7 +282,7 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
             pass_defaults(p, y, out);  // pass C: row b*(j1 + R*j) + k
             p.in_batch_stride = ((size_t)1 << lc) * polys.W;
             p.logS = (int)lc2; p.logR = lr2; p.logC = lc2; p.sub_tw = twC2;
-            p.out_row_mul = b << lr; p.out_row_add = b;
+            p.out_row_mul = b << lr; p.out_row_add = b; p.out_col0 = out_col0;
             p.out = out.base + (size_t)k * out.W;
             CK(ntt_launch_pass(NTT_CONTIG, p, polys.nseg(), 1u << lr, ctx->st));
             ctx->launches += 3;
@@ -292,7 +296,7 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
         p.logS = (int)logC; p.logR = 0; p.logC = logC;
         CKI(wf_get_twiddles(ctx, std::max(log_n, 1u), &p.sub_tw));
         p.pre_tab = tabs.pre; p.pre_batch_stride = (size_t)1 << log_n;
-        p.out_row_mul = b; p.out_row_add = 1;
+        p.out_row_mul = b; p.out_row_add = 1; p.out_col0 = out_col0;
         CK(ntt_launch_pass(NTT_CONTIG, p, polys.nseg(), b, ctx->st));
         ctx->launches++;
         return WF_OK;
@@ -328,7 +332,7 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
         p.logS = (int)logC; p.logR = logR; p.logC = logC;
         p.sub_tw = twC;
         p.in_batch_stride = polys.words();
-        p.out_row_mul = b; p.out_row_add = 1;
+        p.out_row_mul = b; p.out_row_add = 1; p.out_col0 = out_col0;
         p.out = out.base + (size_t)k * out.W;  // + k rows; the launch's coset z adds z rows
         CK(ntt_launch_pass(NTT_CONTIG, p, polys.nseg(), kb, ctx->st));
         ctx->launches++;
@@ -395,6 +399,12 @@ void wf_ctx_destroy(wf_ctx* ctx) {
     for (auto& kv : ctx->tw) cudaFree(kv.second);
     for (auto& kv : ctx->lde_tabs) { cudaFree(kv.second.pre); if (kv.second.pow7) cudaFree(kv.second.pow7); }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->copy_st) {
+        cudaStreamSynchronize(ctx->copy_st);
+        for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_up[i]); cudaEventDestroy(ctx->ev_used[i]); }
+        cudaEventDestroy(ctx->ev_start);
+        cudaStreamDestroy(ctx->copy_st);
+    }
     delete ctx;
 }
 int wf_ctx_set_profiling(wf_ctx* ctx, int on) {
@@ -549,6 +559,83 @@ int wf_mat_lde(wf_ctx* ctx, const wf_mat* polys, uint32_t log_blowup, wf_mat** l
     int r = run_lde(ctx, polys->m, o->m, log_n, log_blowup);
     if (r != WF_OK) { wf_mat_free(ctx, o); return r; }
     *lde = o;
+    return WF_OK;
+}
+
+// DefaultTraceLde::new up to the commitment (trace_lde/default/mod.rs:63-100, build_trace_commitment
+// :245-282) from HOST columns, with the upload pipelined against the transforms: the columns are cut
+// into chunks (whole 8-column segments when there are several, else the two halves of the one segment);
+// chunk k+1 crosses PCIe on a copy stream while chunk k is laid out, interpolated and extended on the
+// compute stream. Columns are independent, so the result equals from_host_columns -> interpolate -> lde.
+int wf_trace_lde_from_host(wf_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, size_t nrows, int mont, uint32_t log_blowup,
+                           wf_mat** polys_out, wf_mat** lde_out) {
+    if (!ctx || !cols || !polys_out || !lde_out || ncols == 0) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    u32 log_n;
+    if (log2_exact(nrows, &log_n) || log_n < 1) return wf_fail(ctx, WF_ERR_INVALID, "rows must be a power of two >= 2");
+    if (log_blowup > 7 || log_n + log_blowup > 32) return wf_fail(ctx, WF_ERR_INVALID, "bad blowup");
+    const int Wout = seg_width_for(ncols);
+    const u32 nseg_out = (ncols + Wout - 1) / Wout;
+    int Wc = nseg_out >= 2 ? Wout : (Wout >= 4 ? Wout / 2 : 0);
+    if (Wc == 0 || log_n < 12) {  // too narrow / too small to be worth a pipeline
+        wf_mat* tr;
+        CKI(wf_mat_from_host_columns(ctx, cols, ncols, nrows, 1, mont, &tr));
+        int r = wf_mat_interpolate(ctx, tr, polys_out);
+        wf_mat_free(ctx, tr);
+        if (r != WF_OK) return r;
+        return wf_mat_lde(ctx, *polys_out, log_blowup, lde_out);
+    }
+    if (!ctx->copy_st) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CK(cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_used[i], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+    }
+    const u32 nchunks = (ncols + Wc - 1) / Wc;
+    wf_mat *polys, *lde, *tr;
+    void* stage[2] = {nullptr, nullptr};
+    void* tmp = nullptr;
+    CKI(wf_mat_alloc_w(ctx, nrows, ncols, Wc, &polys));
+    CKI(wf_mat_alloc(ctx, nrows << log_blowup, ncols, &lde));
+    CKI(wf_mat_alloc_w(ctx, nrows, Wc, Wc, &tr));                       // one chunk of trace values (reused)
+    for (int i = 0; i < 2; i++) CKI(wf_dev_alloc(ctx, (size_t)Wc * nrows * 8, &stage[i]));
+    CKI(wf_dev_alloc(ctx, (size_t)Wc * nrows * 8, &tmp));               // two-pass scratch
+    if (lde->m.W > (int)ncols) CK(cudaMemsetAsync(lde->m.base, 0, lde->m.words() * 8, ctx->st));  // padding columns
+    // the copy stream must not write pool buffers before their previous users on the compute stream are done
+    CK(cudaEventRecord(ctx->ev_start, ctx->st));
+    CK(cudaStreamWaitEvent(ctx->copy_st, ctx->ev_start, 0));
+    for (u32 k = 0; k < nchunks; k++) {
+        const u32 c0 = k * Wc, cw = std::min<u32>(Wc, ncols - c0);
+        const int sb = k & 1;
+        if (k >= 2) CK(cudaStreamWaitEvent(ctx->copy_st, ctx->ev_used[sb], 0));
+        for (u32 j = 0; j < cw; j++)
+            CK(cudaMemcpyAsync((u64*)stage[sb] + (size_t)j * nrows, cols[c0 + j], nrows * 8, cudaMemcpyHostToDevice, ctx->copy_st));
+        CK(cudaEventRecord(ctx->ev_up[sb], ctx->copy_st));
+        CK(cudaStreamWaitEvent(ctx->st, ctx->ev_up[sb], 0));
+        SegMatrix trv = tr->m;
+        trv.cols = cw;
+        CK(layout_cols_to_seg((const u64*)stage[sb], nrows, 1, mont, trv, ctx->st));
+        CK(cudaEventRecord(ctx->ev_used[sb], ctx->st));
+        ctx->launches++;
+        SegMatrix pv = polys->m;                                          // segment k of the W = Wc polys matrix
+        pv.base = polys->m.base + (size_t)k * polys->m.seg_stride;
+        pv.cols = cw;
+        SegMatrix tv = trv;
+        tv.base = (u64*)tmp;
+        int r = run_ntt(ctx, trv, pv, &tv, log_n, 1);
+        if (r != WF_OK) return r;
+        SegMatrix ov = lde->m;                                            // out segment holding columns c0..
+        ov.base = lde->m.base + (size_t)(c0 / Wout) * lde->m.seg_stride;
+        ov.cols = cw;
+        r = run_lde(ctx, pv, ov, log_n, log_blowup, c0 % Wout);
+        if (r != WF_OK) return r;
+    }
+    wf_mat_free(ctx, tr);
+    for (int i = 0; i < 2; i++) wf_dev_free(ctx, stage[i]);
+    wf_dev_free(ctx, tmp);
+    *polys_out = polys;
+    *lde_out = lde;
     return WF_OK;
 }
 

@@ -34,6 +34,8 @@ struct wf_ctx {
     std::map<std::pair<u32, u32>, LdeTables> lde_tabs;  // (log_n, log_blowup)
     void* pinned;                            // staging buffer (pinned host)
     size_t pinned_bytes;
+    cudaStream_t copy_st = nullptr;          // H2D stream of the chunked trace pipeline (created on first use)
+    cudaEvent_t ev_up[2], ev_used[2], ev_start;
     bool profiling;                          // record a CUDA event at every pipeline stage boundary
     std::vector<std::pair<std::string, cudaEvent_t>> marks;
 };
@@ -95,6 +97,7 @@ int wf_fail(wf_ctx* ctx, int code, const char* fmt, ...);
 int wf_dev_alloc(wf_ctx* ctx, size_t bytes, void** out);
 void wf_dev_free(wf_ctx* ctx, void* p);
 int wf_mat_alloc(wf_ctx* ctx, size_t rows, u32 cols, wf_mat** out);
+int wf_mat_alloc_w(wf_ctx* ctx, size_t rows, u32 cols, int W, wf_mat** out);
 int wf_get_twiddles(wf_ctx* ctx, u32 log_n, const u64** out);
 struct OpenPlan {
     u32 depth;

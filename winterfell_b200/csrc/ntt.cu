@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_pass_kernel(c
             a = (((size_t)j << p.logC) + col) * W + q;                            // Y[j1][m2]
         } else {
             size_t row = (size_t)col + ((size_t)j << p.logR);                     // X[j1 + R*j2]
-            a = (row * p.out_row_mul + (size_t)b * p.out_row_add) * W + q;
+            a = (row * p.out_row_mul + (size_t)b * p.out_row_add) * p.out_W + p.out_col0 + q;
         }
         out[a] = v;
     }

@@ -53,6 +53,9 @@ struct NttPassParams {
     int inverse;                               // 1: inverse sub-transform (index-reversed output)
     // CONTIG output row mapping: out_row = row * out_row_mul + batch * out_row_add
     u32 out_row_mul, out_row_add;
+    // CONTIG output segment geometry: the output matrix may be wider than the input segment (a column
+    // chunk of W columns lands at column offset out_col0 of an out_W-wide segment row)
+    u32 out_W, out_col0;
     const u64* sub_tw;                         // w_S^i, i < S/2 (forward root)
     const u64* pre_tab;                        // optional [batch][S] input scale, indexed by sub-transform input index
     size_t pre_batch_stride;

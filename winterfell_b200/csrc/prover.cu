@@ -1051,13 +1051,17 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     wf_mat *trace = nullptr, *polys = nullptr, *lde = nullptr;
     wf_tree* ttree = nullptr;
     wf_mark(ctx, "start");
-    if (d_trace) CKI(wf_mat_from_device_columns(ctx, d_trace, c, n, &trace));
-    else CKI(wf_mat_from_host_columns(ctx, trace_cols, c, n, 1, mont, &trace));
-    wf_mark(ctx, "trace_upload_layout");
-    CKI(wf_mat_interpolate(ctx, trace, &polys));
-    wf_mat_free(ctx, trace);
-    wf_mark(ctx, "trace_interpolate");
-    CKI(wf_mat_lde(ctx, polys, log_b, &lde));
+    if (d_trace) {
+        CKI(wf_mat_from_device_columns(ctx, d_trace, c, n, &trace));
+        wf_mark(ctx, "trace_upload_layout");
+        CKI(wf_mat_interpolate(ctx, trace, &polys));
+        wf_mat_free(ctx, trace);
+        wf_mark(ctx, "trace_interpolate");
+        CKI(wf_mat_lde(ctx, polys, log_b, &lde));
+    } else {
+        // host trace: upload, layout, iNTT and LDE pipelined per column chunk (capi.cu)
+        CKI(wf_trace_lde_from_host(ctx, trace_cols, c, n, mont, log_b, &polys, &lde));
+    }
     wf_mark(ctx, "trace_lde");
     CKI(wf_commit_rows(ctx, h, lde, &ttree));
     u8 root[32];
