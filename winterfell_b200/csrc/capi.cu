@@ -576,6 +576,8 @@ int wf_trace_lde_from_host(wf_ctx* ctx, const uint64_t* const* cols, uint32_t nc
     const int Wout = seg_width_for(ncols);
     const u32 nseg_out = (ncols + Wout - 1) / Wout;
     int Wc = nseg_out >= 2 ? Wout : (Wout >= 4 ? Wout / 2 : 0);
+    // (measured on cfg2, 8 columns: halves 7.03 ms e2e, quarters 7.35 — W = 2 tiles cost more than the
+    // shorter upload head saves — no pipeline 7.36)
     if (Wc == 0 || log_n < 12) {  // too narrow / too small to be worth a pipeline
         wf_mat* tr;
         CKI(wf_mat_from_host_columns(ctx, cols, ncols, nrows, 1, mont, &tr));
