@@ -194,26 +194,29 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_pass_kernel(c
                 }
             }
         }
-    } else
-    for (u32 i0 = tid >> 3; i0 < S; i0 += ROWS_PER_IT * NTT_LD_BATCH) {
-        u64 v[NTT_LD_BATCH], f[NTT_LD_BATCH];
+    } else {
+        // the address is linear in the tile row i: one 64-bit base per thread, one multiply-add per load
+        // (STRIDED: row C*m1 + m2, i = m1; CONTIG: row j1*C + m2, i = m2)
+        const u64* in_thr = MODE == NTT_STRIDED ? in + (size_t)col * W + q : in + (((size_t)col << p.logC) * W + q);
+        const u64 istride = MODE == NTT_STRIDED ? ((u64)W << p.logC) : (u64)W;
+        u64* s_thr = s + lane;
+        for (u32 i0 = tid >> 3; i0 < S; i0 += ROWS_PER_IT * NTT_LD_BATCH) {
+            u64 v[NTT_LD_BATCH], f[NTT_LD_BATCH];
 #pragma unroll
-        for (int k = 0; k < NTT_LD_BATCH; k++) {
-            u32 i = i0 + k * ROWS_PER_IT;
-            v[k] = 0;
-            f[k] = 1;
-            if (col_ok && i < S) {
-                size_t a;
-                if (MODE == NTT_STRIDED) a = (((size_t)i << p.logC) + col) * W + q;   // row C*m1 + m2
-                else a = (((size_t)col << p.logC) + i) * W + q;                       // row j1*C + m2
-                v[k] = in[a];
-                if (pre) f[k] = pre[i];
+            for (int k = 0; k < NTT_LD_BATCH; k++) {
+                u32 i = i0 + k * ROWS_PER_IT;
+                v[k] = 0;
+                f[k] = 1;
+                if (col_ok && i < S) {
+                    v[k] = in_thr[(u64)i * istride];
+                    if (pre) f[k] = pre[i];
+                }
             }
-        }
 #pragma unroll
-        for (int k = 0; k < NTT_LD_BATCH; k++) {
-            u32 i = i0 + k * ROWS_PER_IT;
-            if (i < S) s[(i << 3) + lane] = pre ? gl_mul(v[k], f[k]) : v[k];
+            for (int k = 0; k < NTT_LD_BATCH; k++) {
+                u32 i = i0 + k * ROWS_PER_IT;
+                if (i < S) s_thr[i << 3] = pre ? gl_mul(v[k], f[k]) : v[k];
+            }
         }
     }
     if (use_tma) tma_bulk_wait(mbar);
@@ -225,20 +228,28 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_pass_kernel(c
 
     // write back: smem position pos holds forward X[bitrev(pos)]
     u64* out = p.out + (size_t)g * p.out_seg_stride + (size_t)b * p.out_batch_stride;
-    for (u32 j = tid >> 3; j < S; j += NTT_THREADS / NTT_LANES) {
-        if (!col_ok) continue;
-        u32 jf = p.inverse ? ((S - j) & (S - 1)) : j;
-        u64 v = s[(brev(jf, logS) << 3) + lane];
-        if (p.has_post) v = gl_mul(v, ctw[j * T + t]);
-        else if (p.cconst != 1) v = gl_mul(v, p.cconst);
-        size_t a;
+    if (col_ok) {
+        // linear in j: STRIDED Y[j][m2] = row j*C + col; CONTIG X[j1 + R*j] -> out row (col + R*j)*mul + b*add
+        u64* out_thr;
+        u64 jstride;
         if (MODE == NTT_STRIDED) {
-            a = (((size_t)j << p.logC) + col) * W + q;                            // Y[j1][m2]
+            out_thr = out + (size_t)col * W + q;
+            jstride = (u64)W << p.logC;
         } else {
-            size_t row = (size_t)col + ((size_t)j << p.logR);                     // X[j1 + R*j2]
-            a = (row * p.out_row_mul + (size_t)b * p.out_row_add) * p.out_W + p.out_col0 + q;
+            out_thr = out + ((size_t)col * p.out_row_mul + (size_t)b * p.out_row_add) * p.out_W + p.out_col0 + q;
+            jstride = ((u64)p.out_row_mul << p.logR) * p.out_W;
         }
-        out[a] = v;
+        const u64* s_thr = s + lane;
+        const u64* ctw_thr = ctw + t;
+        const bool post = p.has_post, scale = !p.has_post && p.cconst != 1;
+        const u32 inv_mask = p.inverse ? (S - 1) : 0;  // jf = inverse ? (S - j) mod S : j
+        for (u32 j = tid >> 3; j < S; j += NTT_THREADS / NTT_LANES) {
+            u32 jf = inv_mask ? ((S - j) & inv_mask) : j;
+            u64 v = s_thr[brev(jf, logS) << 3];
+            if (post) v = gl_mul(v, ctw_thr[j * T]);
+            else if (scale) v = gl_mul(v, p.cconst);
+            out_thr[(u64)j * jstride] = v;
+        }
     }
 }
 
