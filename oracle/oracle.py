@@ -401,6 +401,16 @@ def prove_air_aux(desc, trace, opts, builder, aw, nr):
     return out[:ln].tobytes()
 
 
+def perm_rap_aux(trace, rand):
+    """Aux columns [3, n, d] of tests/airs.py perm_rap for the drawn random elements rand [2, d]."""
+    t_, tp = _u64(trace)
+    r_, rp = _u64(rand)
+    n, d = t_.shape[1], r_.shape[1]
+    out = np.zeros((3, n, d), dtype=np.uint64)
+    lib().wfo_perm_rap_aux(tp, C.c_size_t(n), C.c_int(d), rp, out.ctypes.data_as(u64p))
+    return out
+
+
 def verify_air(desc, proof: bytes, hash_id=BLAKE3):
     d_, dp = _u64(desc)
     p_, pp = _u8(np.frombuffer(proof, dtype=np.uint8))

@@ -1140,6 +1140,29 @@ int wfo_verify_air(const uint64_t* desc, size_t desc_len, const uint8_t* proof, 
     air.o.hash_id = hash_id;
     return verify_fib(proof, len, air);
 }
+// Aux columns of the two-segment test AIR tests/airs.py perm_rap (the user's Prover::build_aux_trace for
+// that AIR; test helper so that 2^18-row cases do not loop in Python). trace [3][n] (x0, x1, b), rand =
+// [gamma, alpha] (d words each), out [3][n][d]:  p' = p (x0 + gamma) / (b + gamma), p[0] = 1;
+// q' = q + alpha k x1 p, q[0] = 0, k = 1,2,3,4 periodic;  c[i] = 5 + i.
+void wfo_perm_rap_aux(const uint64_t* trace, size_t n, int d, const uint64_t* rand, uint64_t* out) {
+    Field F{d};
+    EE g = F.zero(), al = F.zero();
+    for (int k = 0; k < d; k++) { g.v[k] = rand[k]; al.v[k] = rand[d + k]; }
+    EE p = F.one(), q = F.zero();
+    for (size_t i = 0; i < n; i++) {
+        for (int k = 0; k < d; k++) {
+            out[(0 * n + i) * d + k] = p.v[k];
+            out[(1 * n + i) * d + k] = q.v[k];
+            out[(2 * n + i) * d + k] = k == 0 ? (u64)(5 + i) : 0;
+        }
+        u64 kk = (u64)(i % 4) + 1;
+        q = F.add(q, F.mul(F.mul_base(al, f_mul(kk, trace[n + i])), p));
+        EE num = g, den = g;
+        num.v[0] = f_add(num.v[0], trace[i]);
+        den.v[0] = f_add(den.v[0], trace[2 * n + i]);
+        p = F.mul(F.mul(p, num), F.inv(den));
+    }
+}
 // builds the FibSmall x k trace: pair j starts at (j+1, j+1); results[j] = last value of column 2j+1
 void wfo_build_fib_trace(size_t k, size_t n, uint64_t* trace, uint64_t* results) {
     for (size_t j = 0; j < k; j++) {

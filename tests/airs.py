@@ -259,7 +259,7 @@ def perm_rap(n, seed=5):
     X.constraint(X.sub(X.anxt(2), X.add(X.acur(2), one)), 1)
     X.assert_sequence(2, 1, n // 4, [(5 + 1 + k * (n // 4), 0, 0) for k in range(4)])
 
-    def builder(rand):
+    def builder_py(rand):  # reference implementation of the aux columns, element by element
         d = rand.shape[1]
         g, al = rand[0], rand[1]
         emb = lambda v: np.array([int(v)] + [0] * (d - 1), dtype=np.uint64)
@@ -272,6 +272,10 @@ def perm_rap(n, seed=5):
             p = O.ext_mul(O.ext_mul(p, eadd(emb(tr[0, i]), g)), O.ext_inv(eadd(emb(tr[2, i]), g)))
         return aux
 
+    def builder(rand):  # the same columns from the C helper (oracle/wf_prover.cpp wfo_perm_rap_aux)
+        return O.perm_rap_aux(tr, rand)
+
+    builder.reference = builder_py
     return A.build(), tr, builder
 
 

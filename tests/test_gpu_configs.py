@@ -72,6 +72,36 @@ def test_config3_rp64_2p18(ctx, oracle):
     _check(ctx, oracle, 1, 18, opts, compare_bytes=False)
 
 
+def test_config3_raps_aux_rp64_2p18(ctx, oracle):
+    # BASELINE configs[3] substitute (ii): a randomised AIR with an auxiliary trace segment
+    # over f64 (examples/src/rescue_raps is f128-only) at 2^18 rows with the Rp64_256 hasher, quadratic
+    # extension and Horner batching as in examples/src/rescue_raps/tests.rs: exercises set_aux_trace, the
+    # aux constraint program, aux (sequence) assertions and the Rp64 leaf / Merkle kernels on two segments.
+    import time
+    import airs
+    n = 1 << 18
+    desc, trace, builder = airs.perm_rap(n)
+    opts = oracle.make_opts(num_queries=28, blowup=8, grinding=8, ext=2, folding=8, rem_max_deg=31, batch_c=2, batch_d=2, hash_id=1)
+    got = ctx.prove_air_aux(desc, trace, opts, builder, airs.PERM_RAP_AUX_WIDTH, 2)
+    assert oracle.verify_air(desc, got, 1) == 0
+    bad = desc.copy()
+    bad[-3] ^= np.uint64(1)  # last word of the last aux sequence value
+    assert oracle.verify_air(bad, got, 1) != 0
+    if os.environ.get("WF_REPORT"):
+        import json
+        ctx.set_profiling(True)
+        t0 = time.perf_counter()
+        ctx.prove_air_aux(desc, trace, opts, builder, airs.PERM_RAP_AUX_WIDTH, 2)
+        wall = (time.perf_counter() - t0) * 1e3
+        stages = {k2: round(v, 3) for k2, v in ctx.stage_times()}
+        ctx.set_profiling(False)
+        rec = {"air": "perm_rap (3 main + 3 aux columns, 2 random elements)", "log_n": 18, "opts": [int(x) for x in opts],
+               "proof_bytes": len(got), "e2e_wall_ms_incl_host_aux_builder": round(wall, 2),
+               "gpu_ms_sum": round(sum(stages.values()), 3), "stage_ms": stages}
+        with open(os.environ["WF_REPORT"], "a") as f:
+            f.write(json.dumps(rec) + "\n")
+
+
 @pytest.mark.parametrize("log_len,d", [(20, 1), (22, 1), (20, 3), (26, 1)])
 def test_config4_fri_only(ctx, oracle, log_len, d):
     # FRI-only: codeword = LDE (blowup 8) of a random polynomial, folding 4, remainder max degree 31;

@@ -29,7 +29,29 @@ e1.record(); torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1) / 3], device="cuda")
 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:
+    import json
     m = ctx.mat_from_host_columns(trace)
-    t = ctx.commit_rows(wf.HASH_BLAKE3_256, m.interpolate().lde(3))
-    print({"world": world, "log_n": log_n, "cols": cols, "root_matches_single_gpu": t.root() == root, "ms_max_over_ranks": round(float(ms[0]), 3)})
+    def single():
+        p_ = m.interpolate(); l_ = p_.lde(3); t_ = ctx.commit_rows(wf.HASH_BLAKE3_256, l_)
+        r_ = t_.root()
+        for o in (p_, l_, t_):
+            o.free()
+        return r_
+    ref_root = single()
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(3):
+        single()
+    s1.record(); torch.cuda.synchronize()
+    N = n << 3
+    rec = {"world": world, "log_n": log_n, "cols": cols, "blowup": 8, "hash": "blake3_256",
+           "root_matches_single_gpu": ref_root == root, "ms_sharded_max_over_ranks": round(float(ms[0]), 3),
+           "ms_single_gpu_same_box": round(s0.elapsed_time(s1) / 3, 3),
+           "lde_gelem_per_s_sharded": round(N * cols / (float(ms[0]) * 1e-3) / 1e9, 2),
+           "leaves_per_s_sharded": round(N / (float(ms[0]) * 1e-3), 1)}
+    print(json.dumps(rec))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/sharded_commit_r1.jsonl", "a") as f:
+        f.write(json.dumps(rec) + "\n")
 dist.destroy_process_group()

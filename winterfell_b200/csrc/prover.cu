@@ -342,6 +342,9 @@ struct DeepParams {
 // rows per thread sharing one batch inversion: 8 in the base field, 4 for extensions (registers)
 #define DEEP_ROWS (D == 1 ? 8 : 4)
 // DeepCompositionPoly in evaluation form; DEEP_ROWS rows per thread share one batch inversion.
+// (Tried and dropped: chains of rows i, i + b, ... that reuse 1 / (x_{i-b} - z) = g / (x_i - z g) to halve
+// the inversions with 16 rows per thread — 23 % fewer multiplications but 0.94 ms instead of 0.64 ms on
+// cfg2: the strided row pattern and the register pressure cost more than the arithmetic saved.)
 template <int D>
 __global__ void __launch_bounds__(256) deep_eval_kernel(DeepParams p, GlExt<D> z, GlExt<D> zg, GlExt<D> Sz, GlExt<D> Szg) {
     const size_t N = (size_t)1 << p.log_N;
@@ -1368,6 +1371,7 @@ static int deep_entry(wf_ctx* ctx, const wf_mat* lde, const wf_mat* alde, const 
     const u32 c = lde->m.cols, aw = alde ? alde->m.cols / D : 0, kc = clde->m.cols / D, tot = c + aw + kc;
     u32 log_N = 0;
     while (((size_t)1 << log_N) < lde->m.rows) log_N++;
+    if (log_n > log_N) return wf_fail(ctx, WF_ERR_INVALID, "trace length exceeds the LDE domain");
     std::vector<GlExt<D>> dc(tot);
     GlExt<D> z = ext_zero<D>(), Sz = ext_zero<D>(), Szg = ext_zero<D>();
     for (int q = 0; q < D; q++) z.v[q] = zw[q];
