@@ -28,6 +28,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 P = 0xFFFFFFFF00000001
+# dram__bytes_read.sum + dram__bytes_write.sum of the four ntt_pass_kernel launches of the cfg2 trace interpolate + LDE,
+# from the committed ncu --set full capture (profiles/r1_ntt_pass_v2_summary.txt, launches 0-3)
+NCU_TRAFFIC_BYTES = 2495322112
 METRIC = "prover_ms"
 FOLDING, REM_MAX_DEG, LOG_BLOWUP, NUM_QUERIES, GRINDING = 4, 31, 3, 32, 16
 
@@ -281,9 +284,15 @@ def main():
             "gpu_launches": launches // max(args.steps, 1),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel (trace interpolate + LDE launches)", "achieved": round(achieved, 1), "peak": hbm,
-                         "unit": "GB/s", "frac": round(achieved / hbm, 4), "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": round(achieved / hbm, 4),
+                         "traffic": NCU_TRAFFIC_BYTES if (log_n, cols) == (20, 8) else None, "peak_source": peak_src,
                          "algorithmic_bytes": int(alg_bytes), "kernel_ms": round(ntt_ms, 4),
-                         "note": "ALU-bound kernel (ncu: ALU pipe 51-66% busy, DRAM 7-9%); see DESIGN.md"},
+                         "launches": 4,
+                         "note": "achieved / traffic / algorithmic_bytes are sums over the 4 launches of the group (2 iNTT passes, "
+                                 "2 LDE passes with all 8 cosets in grid.z). traffic = dram__bytes_read.sum + dram__bytes_write.sum "
+                                 "of the same 4 launches in profiles/r1_ntt_pass_v2_summary.txt (ncu --set full): 3.7x the algorithmic "
+                                 "bytes because the two-pass schedule writes and re-reads the intermediate. The kernel is integer-ALU-"
+                                 "bound (ALU pipe 55-59 %, FMA 28-32 %, issue slots 66-68 %, DRAM 21 % of peak); see DESIGN.md 4"},
             "stage_ms": breakdown,
             "lde_commit_fri_ms": round(lcf, 4),
             "proof_bytes": len(p_e2e),

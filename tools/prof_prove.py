@@ -20,7 +20,8 @@ for j in range(pairs):
         vb = (vb + va) % P
     trace[2 * j], trace[2 * j + 1], res[j] = np.array(ca, dtype=np.uint64), np.array(cb, dtype=np.uint64), cb[n - 1]
 ctx = wf.Context(0)
-opts = np.array([32, 8, 16, 1, 4, 31, 0, 0, 0], dtype=np.uint32)
+ext = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+opts = np.array([32, 8, 16, ext, 4, 31, 0, 0, 0], dtype=np.uint32)
 if resident:
     import torch
     d_trace = torch.from_numpy(trace.view(np.int64)).cuda()

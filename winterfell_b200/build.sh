@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unknown-pragmas --use_fast_math -ccbin /usr/bin/g++"
+FLAGS="-Wno-deprecated-gpu-targets -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unknown-pragmas --use_fast_math -ccbin /usr/bin/g++"
 mkdir -p _build
 pids=()
 for f in ntt commit fri layout capi prover ${EXTRA_SRCS}; do
@@ -13,7 +13,7 @@ for f in ntt commit fri layout capi prover ${EXTRA_SRCS}; do
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o libwinterfell_b200.so _build/*.o -lcudart -ccbin /usr/bin/g++
+$NVCC -Wno-deprecated-gpu-targets -shared -o libwinterfell_b200.so _build/*.o -lcudart -ccbin /usr/bin/g++
 echo "built $(pwd)/libwinterfell_b200.so"
 # the C++ mirror of the reference's plugin interface (include/winterfell_b200.hpp) + its driver: plain
 # g++ over the C ABI, proving the header has no CUDA dependency

@@ -4,7 +4,7 @@
 //   K5     constraint evaluation     (fib_constraints_kernel)     DefaultConstraintEvaluator::evaluate
 //   K6/K7  composition poly + commit (ntt.cu, commit.cu)         DefaultConstraintCommitment::new
 //   K8     out-of-domain frames      (ood_partial_kernel)         TracePolyTable/CompositionPoly::get_ood_frame
-//   K9/K10 DEEP composition          (deep_eval_kernel)           DeepCompositionPoly::{add_trace_polys, evaluate}
+//   K9/K10 DEEP composition          (deep_sum/div_kernel)        DeepCompositionPoly::{add_trace_polys, evaluate}
 //   K11    FRI commit phase          (fri.cu)                     FriProver::build_layers
 //   K13    proof-of-work grinding    (host, serial semantics: smallest nonce)
 // The Fiat-Shamir transcript (ProverChannel, prover/src/channel.rs) and the proof wire format
@@ -277,23 +277,38 @@ __global__ void __launch_bounds__(256) ood_partial_kernel(SegMatrix polys, GlExt
     const size_t start = ((size_t)chunk * 256 + t) * OOD_PER_THREAD;
     const u64* base = polys.base + (size_t)g * polys.seg_stride;
     __shared__ u64 red[2][8][8][D];
+    // z^r, r < OOD_PER_THREAD, for both points: a coefficient then costs one base-by-extension product per
+    // point (D multiplications) instead of the D^2 of a Horner step, and is loaded once for both points
+    __shared__ u64 zpow[2][OOD_PER_THREAD][D];
+    if (t < 2 * OOD_PER_THREAD) {
+        GlExt<D> v = ext_pow(t < OOD_PER_THREAD ? z0 : z1, t % OOD_PER_THREAD);
 #pragma unroll
-    for (int pt = 0; pt < 2; pt++) {
-        const GlExt<D> z = pt == 0 ? z0 : z1;
-        GlExt<D> acc[8];
+        for (int c = 0; c < D; c++) zpow[t / OOD_PER_THREAD][t % OOD_PER_THREAD][c] = v.v[c];
+    }
+    __syncthreads();
+    GlExt<D> acc[2][8];
 #pragma unroll
-        for (int q = 0; q < 8; q++) acc[q] = ext_zero<D>();
-        for (int r = OOD_PER_THREAD - 1; r >= 0; r--) {
-            size_t row = start + r;
-            if (row >= n) continue;
-            for (int q = 0; q < W; q++) {
-                acc[q] = ext_mul(acc[q], z);
-                acc[q].v[0] = gl_add(acc[q].v[0], base[row * W + q]);
+    for (int q = 0; q < 8; q++) { acc[0][q] = ext_zero<D>(); acc[1][q] = ext_zero<D>(); }
+    for (int r = 0; r < OOD_PER_THREAD; r++) {
+        size_t row = start + r;
+        if (row >= n) break;
+        const GlExt<D> p0 = ld_ext<D>(&zpow[0][r][0]), p1 = ld_ext<D>(&zpow[1][r][0]);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {  // fully unrolled with a guard: acc[][] must stay in registers
+            if (q < W) {
+                const u64 cf = base[row * W + q];
+                acc[0][q] = ext_add(acc[0][q], ext_mul_base(p0, cf));
+                acc[1][q] = ext_add(acc[1][q], ext_mul_base(p1, cf));
             }
         }
-        GlExt<D> zp = ext_pow(z, start);  // z^(first row of this thread)
-        for (int q = 0; q < W; q++) {
-            GlExt<D> v = ext_mul(acc[q], zp);
+    }
+#pragma unroll
+    for (int pt = 0; pt < 2; pt++) {
+        GlExt<D> zp = ext_pow(pt == 0 ? z0 : z1, start);  // z^(first row of this thread)
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (q >= W) break;
+            GlExt<D> v = ext_mul(acc[pt][q], zp);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
 #pragma unroll
@@ -339,64 +354,86 @@ struct DeepParams {
     const u64* ccc;    // [kc][D] DEEP coefficients for composition columns
     const u64* tw_N;   // w_N^i, i < N/2
 };
-// rows per thread sharing one batch inversion: 8 in the base field, 4 for extensions (registers)
-#define DEEP_ROWS (D == 1 ? 8 : 4)
-// DeepCompositionPoly in evaluation form; DEEP_ROWS rows per thread share one batch inversion.
+// DeepCompositionPoly in evaluation form, two kernels:
+//   deep_sum_kernel: S(x) = sum_j cc_j T_j(x) + sum_j cc'_j A_j(x) + sum_j cc''_j H_j(x) for every LDE row — the
+//     pass that reads the whole LDE; one row per thread, coefficients in shared memory, ~40 registers, so
+//     the SMs stay full (the earlier single kernel needed 242 registers per thread with cubic elements:
+//     12 % occupancy, 28 % issue utilisation, 2.0 ms for 2^21 rows x 64 columns);
+//   deep_div_kernel: D(x) = (S(x) - S(z)) / (x - z) + (S(x) - S(zg)) / (x - zg) in place, DEEP_ROWS rows per
+//     thread sharing one batch inversion (math/src/utils/mod.rs:169).
 // (Tried and dropped: chains of rows i, i + b, ... that reuse 1 / (x_{i-b} - z) = g / (x_i - z g) to halve
-// the inversions with 16 rows per thread — 23 % fewer multiplications but 0.94 ms instead of 0.64 ms on
-// cfg2: the strided row pattern and the register pressure cost more than the arithmetic saved.)
+// the inversions — the strided row pattern cost more than the arithmetic saved.)
+#define DEEP_SUM_THREADS 256
 template <int D>
-__global__ void __launch_bounds__(256) deep_eval_kernel(DeepParams p, GlExt<D> z, GlExt<D> zg, GlExt<D> Sz, GlExt<D> Szg) {
+__global__ void __launch_bounds__(DEEP_SUM_THREADS) deep_sum_kernel(DeepParams p) {
+    extern __shared__ __align__(16) u64 dsm[];
+    u64* s_t = dsm;                                  // [c][D]
+    u64* s_a = s_t + (size_t)p.c * D;                // [aw][D]
+    u64* s_c = s_a + (size_t)p.aw * D;               // [kc][D]
+    for (u32 i = threadIdx.x; i < p.c * D; i += DEEP_SUM_THREADS) s_t[i] = p.tcc[i];
+    for (u32 i = threadIdx.x; i < p.aw * D; i += DEEP_SUM_THREADS) s_a[i] = p.acc[i];
+    for (u32 i = threadIdx.x; i < p.kc * D; i += DEEP_SUM_THREADS) s_c[i] = p.ccc[i];
+    __syncthreads();
+    const size_t N = (size_t)1 << p.log_N;
+    const size_t row = (size_t)blockIdx.x * DEEP_SUM_THREADS + threadIdx.x;
+    if (row >= N) return;
+    GlExt<D> S = ext_zero<D>();
+    if (p.trace.W == 8) {
+        for (u32 g = 0; g * 8 < p.c; g++) {  // one 64-byte segment row = four 16-byte loads
+            const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(p.trace.base + (size_t)g * p.trace.seg_stride + row * 8);
+            u64 v[8];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { ulonglong2 t2 = __ldg(rp + k); v[2 * k] = t2.x; v[2 * k + 1] = t2.y; }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                u32 j = g * 8 + q;
+                if (j < p.c) S = ext_add(S, ext_mul_base(ld_ext<D>(s_t + (size_t)j * D), v[q]));
+            }
+        }
+    } else {
+        for (u32 j = 0; j < p.c; j++) S = ext_add(S, ext_mul_base(ld_ext<D>(s_t + (size_t)j * D), seg_at(p.trace, row, j)));
+    }
+    for (u32 j = 0; j < p.aw; j++) {
+        GlExt<D> av;
+#pragma unroll
+        for (int q = 0; q < D; q++) av.v[q] = seg_at(p.aux, row, j * D + q);
+        S = ext_add(S, ext_mul(ld_ext<D>(s_a + (size_t)j * D), av));
+    }
+    for (u32 j = 0; j < p.kc; j++) {
+        GlExt<D> hv;
+#pragma unroll
+        for (int q = 0; q < D; q++) hv.v[q] = seg_at(p.cons, row, j * D + q);
+        S = ext_add(S, ext_mul(ld_ext<D>(s_c + (size_t)j * D), hv));
+    }
+    u64* o = p.out.base + row * p.out.W;
+#pragma unroll
+    for (int q = 0; q < D; q++) o[q] = S.v[q];
+}
+
+// rows per thread sharing one batch inversion
+#define DEEP_ROWS (D == 1 ? 16 : (D == 2 ? 8 : 4))
+template <int D>
+__global__ void __launch_bounds__(256) deep_div_kernel(DeepParams p, GlExt<D> z, GlExt<D> zg, GlExt<D> Sz, GlExt<D> Szg) {
     const size_t N = (size_t)1 << p.log_N;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    constexpr int ROWS = (D == 1 ? 8 : 4);
-    GlExt<D> S[ROWS], den[2 * ROWS];
+    constexpr int ROWS = DEEP_ROWS;
+    GlExt<D> den[2 * ROWS];
     const u32 half = (u32)(N >> 1);
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
         size_t row = tid + r * stride;
-        S[r] = ext_zero<D>();
         den[2 * r] = ext_from_base<D>(1);
         den[2 * r + 1] = ext_from_base<D>(1);
         if (row >= N) continue;
-        if (p.trace.W == 8) {
-            // one 64-byte segment row = four 16-byte loads
-            for (u32 g = 0; g * 8 < p.c; g++) {
-                const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(p.trace.base + (size_t)g * p.trace.seg_stride + row * 8);
-                u64 v[8];
-#pragma unroll
-                for (int k = 0; k < 4; k++) { ulonglong2 t2 = __ldg(rp + k); v[2 * k] = t2.x; v[2 * k + 1] = t2.y; }
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    u32 j = g * 8 + q;
-                    if (j < p.c) S[r] = ext_add(S[r], ext_mul_base(ld_ext<D>(p.tcc + (size_t)j * D), v[q]));
-                }
-            }
-        } else {
-            for (u32 j = 0; j < p.c; j++) S[r] = ext_add(S[r], ext_mul_base(ld_ext<D>(p.tcc + (size_t)j * D), seg_at(p.trace, row, j)));
-        }
-        for (u32 j = 0; j < p.aw; j++) {
-            GlExt<D> av;
-#pragma unroll
-            for (int q = 0; q < D; q++) av.v[q] = seg_at(p.aux, row, j * D + q);
-            S[r] = ext_add(S[r], ext_mul(ld_ext<D>(p.acc + (size_t)j * D), av));
-        }
-        for (u32 j = 0; j < p.kc; j++) {
-            GlExt<D> hv;
-#pragma unroll
-            for (int q = 0; q < D; q++) hv.v[q] = seg_at(p.cons, row, j * D + q);
-            S[r] = ext_add(S[r], ext_mul(ld_ext<D>(p.ccc + (size_t)j * D), hv));
-        }
         u64 w = p.tw_N[row & (half - 1)];
         if (row & half) w = gl_neg(w);
         GlExt<D> x = ext_from_base<D>(gl_mul(w, GL_GENERATOR));
         den[2 * r] = ext_sub(x, z);
         den[2 * r + 1] = ext_sub(x, zg);
     }
-    // batch inversion (math/src/utils/mod.rs:169 Montgomery trick); denominators are never zero
-    // (z is outside the base-field LDE domain with overwhelming probability; a zero would also
-    // break the reference's synthetic division)
+    // batch inversion; denominators are never zero (z is outside the base-field LDE domain with
+    // overwhelming probability; a zero would also break the reference's synthetic division)
     GlExt<D> pre[2 * ROWS];
     GlExt<D> run = ext_from_base<D>(1);
 #pragma unroll
@@ -408,8 +445,9 @@ __global__ void __launch_bounds__(256) deep_eval_kernel(DeepParams p, GlExt<D> z
     for (int r = 0; r < ROWS; r++) {
         size_t row = tid + r * stride;
         if (row >= N) continue;
-        GlExt<D> v = ext_add(ext_mul(ext_sub(S[r], Sz), den[2 * r]), ext_mul(ext_sub(S[r], Szg), den[2 * r + 1]));
         u64* o = p.out.base + row * p.out.W;
+        GlExt<D> S = ld_ext<D>(o);
+        GlExt<D> v = ext_add(ext_mul(ext_sub(S, Sz), den[2 * r]), ext_mul(ext_sub(S, Szg), den[2 * r + 1]));
 #pragma unroll
         for (int q = 0; q < D; q++) o[q] = v.v[q];
     }
@@ -831,7 +869,7 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
         // boundary coefficients follow the assertions sorted by (stride, first_step, column)
         // (air/src/air/assertions/mod.rs:301-315): 2k assertions at step 0, then k at step n-1
         const u32 k = air.fib_k;
-        void *d_tc, *d_b0, *d_b1, *d_res;
+        void *d_tc = nullptr, *d_b0 = nullptr, *d_b1 = nullptr, *d_res = nullptr;
         auto f0 = flat(0, n_tr), f1 = flat(n_tr, 2 * k), f2 = flat(n_tr + 2 * k, k);
         CKI(upload(f0.data(), f0.size() * 8, &d_tc));
         CKI(upload(f1.data(), f1.size() * 8, &d_b0));
@@ -852,7 +890,7 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
         memset(&p, 0, sizeof(p));
         p.lde = lde->m; p.out = comp->m; p.w = c; p.log_n = log_n; p.log_blowup = log_b; p.log_ce_blowup = log_ceb;
         p.prog_len = (u32)(air.prog.size() / 4); p.num_regs = air.num_regs; p.num_periodic = (u32)air.periodic.size(); p.num_tc = n_mtr;
-        void* dp;
+        void* dp = nullptr;
         CKI(upload(air.prog.data(), air.prog.size() * 4, &dp)); p.prog = (u32*)dp;
         CKI(upload(air.consts.data(), air.consts.size() * 8, &dp)); p.consts = (u64*)dp;
         // periodic value tables (evaluator/periodic_table.rs:24-76): poly_j over offset^(n/L) <w_(L*ceb)>
@@ -1013,10 +1051,12 @@ int deep_compose(wf_ctx* ctx, const wf_mat* lde, const wf_mat* alde, const wf_ma
     p.tcc = d_dt; p.ccc = d_dq; p.acc = d_da; p.aw = aw;
     p.aux = aw ? alde->m : lde->m;
     CKI(wf_get_twiddles(ctx, log_N, &p.tw_N));
-    const size_t rows_per_thread = (D == 1 ? 8 : 4);
+    const size_t coef_bytes = (size_t)(c + aw + kc) * D * 8;
+    deep_sum_kernel<D><<<(unsigned)((N + DEEP_SUM_THREADS - 1) / DEEP_SUM_THREADS), DEEP_SUM_THREADS, coef_bytes, ctx->st>>>(p);
+    const size_t rows_per_thread = DEEP_ROWS;
     size_t threads = (N + rows_per_thread - 1) / rows_per_thread;
-    deep_eval_kernel<D><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->st>>>(p, z, zg, Sz, Szg);
-    ctx->launches++;
+    deep_div_kernel<D><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->st>>>(p, z, zg, Sz, Szg);
+    ctx->launches += 2;
     CK(cudaGetLastError());
     // the coefficient buffers are pool allocations on the same stream: safe to release after the launch
     for (u64* q : {d_dt, d_dq, d_da}) wf_dev_free(ctx, q);
