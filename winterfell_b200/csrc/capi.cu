@@ -943,27 +943,103 @@ int wf_fri_build_layers(wf_ctx* ctx, int hash_id, const wf_mat* evals, int d, ui
     return WF_OK;
 }
 
+}  // extern "C"
+// FriProver::build_layers with the transcript replicated on the device: every layer's leaf hashing, tree,
+// coin step (fri_coin_step: reseed with the root, draw alpha) and fold are enqueued back to back, and the
+// host synchronises ONCE at the end, replays commit_fri_layer / draw_fri_alpha on its own coin and checks
+// that it draws the alphas the device used. (The callback form above pays a device-to-host round trip
+// per layer: ~20 us x 8 layers on the 2^23-point codeword of cfg2.)
+int wf_fri_build_layers_coin(wf_ctx* ctx, int hash_id, const wf_mat* evals, int d, uint32_t folding, uint32_t rem_max_deg,
+                             uint32_t blowup, PublicCoin& coin, std::vector<Digest>& commitments, wf_fri** out) {
+    if (!ctx || !evals || !out) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    if (d < 1 || d > 3 || (int)evals->m.cols != d) return wf_fail(ctx, WF_ERR_INVALID, "evaluations must have ext_degree base columns");
+    if (folding != 2 && folding != 4 && folding != 8 && folding != 16) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "folding factor %u", folding);
+    size_t len = evals->m.rows;
+    u32 logL;
+    if (log2_exact(len, &logL)) return wf_fail(ctx, WF_ERR_INVALID, "domain size must be a power of two");
+    wf_fri* f = new wf_fri();
+    f->hash_id = hash_id; f->d = d; f->folding = folding; f->blowup = blowup;
+    f->ld = evals->m.W;
+    const int ld = f->ld;
+    const size_t max_rem = (size_t)(rem_max_deg + 1) * blowup;  // fri/src/options.rs:85-93
+    size_t nlayers = 0;
+    for (size_t l = len; l > max_rem; l /= folding) nlayers++;
+    void *cur, *dstate, *dalpha, *dlog;
+    CKI(wf_dev_alloc(ctx, len * ld * 8, &cur));
+    CK(cudaMemcpyAsync(cur, evals->m.base, len * ld * 8, cudaMemcpyDeviceToDevice, ctx->st));
+    CKI(wf_dev_alloc(ctx, 8 * 8, &dstate));
+    CKI(wf_dev_alloc(ctx, 8 * 8, &dalpha));
+    CKI(wf_dev_alloc(ctx, std::max<size_t>(nlayers, 1) * 8 * 8, &dlog));
+    u64 seed_words[4];
+    memcpy(seed_words, coin.seed.b, 32);
+    CK(cudaMemcpyAsync(dstate, seed_words, 32, cudaMemcpyHostToDevice, ctx->st));
+    size_t layer = 0;
+    while (len > max_rem) {
+        size_t m = len / folding;
+        wf_tree* t;
+        int r = tree_alloc(ctx, hash_id, m, &t);
+        if (r != WF_OK) { wf_dev_free(ctx, cur); wf_fri_free(ctx, f); return r; }
+        CK(fri_hash_layer(hash_id, (u64*)cur, len, d, ld, (int)folding, t->leaves, ctx->st));
+        CK(commit_merkle_nodes(hash_id, t->leaves, m, t->nodes, ctx->st));
+        CK(fri_coin_step(hash_id, (u64*)dstate, t->nodes + 4, d, (u64*)dalpha, (u64*)dlog + 8 * layer, ctx->st));
+        ctx->launches += 2 + merkle_launches(m);
+        const u64* master;
+        u32 ll = 0;
+        while (((size_t)1 << ll) < len) ll++;
+        CKI(wf_get_twiddles(ctx, ll, &master));
+        void* nxt;
+        CKI(wf_dev_alloc(ctx, m * ld * 8, &nxt));
+        if (ld > d) CK(cudaMemsetAsync(nxt, 0, m * ld * 8, ctx->st));
+        CK(fri_fold_layer((u64*)cur, len, d, ld, (int)folding, nullptr, master, (u64*)nxt, ld, ctx->st, (const u64*)dalpha));
+        ctx->launches++;
+        f->layers.push_back(FriLayer{(u64*)cur, len, t});
+        cur = nxt;
+        len = m;
+        layer++;
+    }
+    std::vector<u64> raw(len * ld), v(len * d), log(std::max<size_t>(nlayers, 1) * 8);
+    CK(cudaMemcpyAsync(raw.data(), cur, len * ld * 8, cudaMemcpyDeviceToHost, ctx->st));
+    if (nlayers) CK(cudaMemcpyAsync(log.data(), dlog, nlayers * 8 * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    wf_dev_free(ctx, cur);
+    wf_dev_free(ctx, dstate); wf_dev_free(ctx, dalpha); wf_dev_free(ctx, dlog);
+    // replay on the host coin: commit_fri_layer, draw_fri_alpha (prover/src/channel.rs:215-234)
+    for (size_t l = 0; l < nlayers; l++) {
+        Digest root;
+        memcpy(root.b, &log[8 * l], 32);
+        commitments.push_back(root);
+        coin.reseed(root);
+        u64 alpha[3] = {0, 0, 0};
+        bool ok = coin.draw(d, alpha) && log[8 * l + 7] == 1;
+        for (int k = 0; k < d; k++) ok = ok && alpha[k] == log[8 * l + 4 + k];
+        if (!ok) { wf_fri_free(ctx, f); return wf_fail(ctx, WF_ERR_STATE, "device and host FRI transcripts diverged at layer %zu", l); }
+    }
+    // remainder (fri/src/prover/mod.rs:230-239)
+    for (size_t i = 0; i < len; i++)
+        for (int c = 0; c < d; c++) v[i * d + c] = raw[i * ld + c];
+    wf_host_dft(v, len, d, true, GL_GENERATOR);
+    size_t rsize = len / blowup;
+    f->remainder.resize(rsize * d);
+    for (size_t i = 0; i < rsize; i++)
+        for (int c = 0; c < d; c++) f->remainder[i * d + c] = v[(rsize - 1 - i) * d + c];
+    Digest rc = hh_hash_elements(hash_id, f->remainder.data(), f->remainder.size());
+    commitments.push_back(rc);
+    coin.reseed(rc);
+    *out = f;
+    return WF_OK;
+}
+extern "C" {
+
 struct DefaultChannel {
     PublicCoin coin;
     int d;
     std::vector<Digest> commitments;
 };
-static void dc_commit(void* u, const uint8_t root[32]) {
-    DefaultChannel* c = (DefaultChannel*)u;
-    Digest dg;
-    memcpy(dg.b, root, 32);
-    c->commitments.push_back(dg);
-    c->coin.reseed(dg);
-}
-static void dc_draw(void* u, uint64_t* alpha) {
-    DefaultChannel* c = (DefaultChannel*)u;
-    c->coin.draw(c->d, alpha);
-}
 int wf_fri_build_layers_default_channel(wf_ctx* ctx, int hash_id, const wf_mat* evals, int d, uint32_t folding,
                                         uint32_t rem_max_deg, uint32_t blowup, uint8_t* roots_out, size_t roots_cap,
                                         wf_fri** out) {
     DefaultChannel ch{PublicCoin(hash_id, nullptr, 0), d, {}};
-    CKI(wf_fri_build_layers(ctx, hash_id, evals, d, folding, rem_max_deg, blowup, dc_commit, dc_draw, &ch, out));
+    CKI(wf_fri_build_layers_coin(ctx, hash_id, evals, d, folding, rem_max_deg, blowup, ch.coin, ch.commitments, out));
     if (roots_out) {
         if (roots_cap < ch.commitments.size() * 32) return wf_fail(ctx, WF_ERR_INVALID, "roots buffer too small");
         for (size_t i = 0; i < ch.commitments.size(); i++) memcpy(roots_out + 32 * i, ch.commitments[i].b, 32);

@@ -64,11 +64,15 @@ __host__ __device__ constexpr u32 cbrev(u32 v, int bits) {
 
 template <int D, int LOGNF>
 __global__ void __launch_bounds__(256) fri_fold_kernel(const u64* __restrict__ ev, size_t m, int ld, GlExt<D> alpha,
-                                                       const u64* __restrict__ master, u32 logL, u64* __restrict__ next,
-                                                       int next_ld) {
+                                                       const u64* __restrict__ d_alpha, const u64* __restrict__ master,
+                                                       u32 logL, u64* __restrict__ next, int next_ld) {
     constexpr int NF = 1 << LOGNF;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
+    if (d_alpha) {  // alpha drawn by the device coin (fri_coin_kernel) instead of passed by the host
+#pragma unroll
+        for (int c = 0; c < D; c++) alpha.v[c] = d_alpha[c];
+    }
     u64 x[D][NF];
 #pragma unroll
     for (int k = 0; k < NF; k++)
@@ -114,30 +118,101 @@ cudaError_t fri_hash_layer(int hash_id, const u64* evals, size_t len, int d, int
 }
 
 template <int D>
-static cudaError_t fold_dispatch(const u64* evals, size_t len, int ld, int nf, const u64* alpha, const u64* master,
-                                 u64* next, int next_ld, cudaStream_t st) {
+static cudaError_t fold_dispatch(const u64* evals, size_t len, int ld, int nf, const u64* alpha, const u64* d_alpha,
+                                 const u64* master, u64* next, int next_ld, cudaStream_t st) {
     size_t m = len / nf;
     u32 logL = 0;
     while (((size_t)1 << logL) < len) logL++;
     GlExt<D> a;
-    for (int c = 0; c < D; c++) a.v[c] = alpha[c];
+    for (int c = 0; c < D; c++) a.v[c] = alpha ? alpha[c] : 0;
     unsigned blocks = (unsigned)((m + 255) / 256);
     switch (nf) {
-        case 2: fri_fold_kernel<D, 1><<<blocks, 256, 0, st>>>(evals, m, ld, a, master, logL, next, next_ld); break;
-        case 4: fri_fold_kernel<D, 2><<<blocks, 256, 0, st>>>(evals, m, ld, a, master, logL, next, next_ld); break;
-        case 8: fri_fold_kernel<D, 3><<<blocks, 256, 0, st>>>(evals, m, ld, a, master, logL, next, next_ld); break;
-        case 16: fri_fold_kernel<D, 4><<<blocks, 256, 0, st>>>(evals, m, ld, a, master, logL, next, next_ld); break;
+        case 2: fri_fold_kernel<D, 1><<<blocks, 256, 0, st>>>(evals, m, ld, a, d_alpha, master, logL, next, next_ld); break;
+        case 4: fri_fold_kernel<D, 2><<<blocks, 256, 0, st>>>(evals, m, ld, a, d_alpha, master, logL, next, next_ld); break;
+        case 8: fri_fold_kernel<D, 3><<<blocks, 256, 0, st>>>(evals, m, ld, a, d_alpha, master, logL, next, next_ld); break;
+        case 16: fri_fold_kernel<D, 4><<<blocks, 256, 0, st>>>(evals, m, ld, a, d_alpha, master, logL, next, next_ld); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
 cudaError_t fri_fold_layer(const u64* evals, size_t len, int d, int ld, int nf, const u64* alpha, const u64* master,
-                           u64* next, int next_ld, cudaStream_t st) {
+                           u64* next, int next_ld, cudaStream_t st, const u64* d_alpha) {
     switch (d) {
-        case 1: return fold_dispatch<1>(evals, len, ld, nf, alpha, master, next, next_ld, st);
-        case 2: return fold_dispatch<2>(evals, len, ld, nf, alpha, master, next, next_ld, st);
-        case 3: return fold_dispatch<3>(evals, len, ld, nf, alpha, master, next, next_ld, st);
+        case 1: return fold_dispatch<1>(evals, len, ld, nf, alpha, d_alpha, master, next, next_ld, st);
+        case 2: return fold_dispatch<2>(evals, len, ld, nf, alpha, d_alpha, master, next, next_ld, st);
+        case 3: return fold_dispatch<3>(evals, len, ld, nf, alpha, d_alpha, master, next, next_ld, st);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// ---- device copy of the public coin for the FRI commit phase -----------------------------------------
+// ProverChannel::commit_fri_layer + draw_fri_alpha (prover/src/channel.rs:215-234) = DefaultRandomCoin::
+// reseed (crypto/src/random/default.rs:131-134: seed = merge(seed, root), counter = 0) followed by draw
+// (:156-170: counter += 1, merge_with_int(seed, counter), rejection of words >= p). One thread; it lets the
+// whole layer loop be enqueued without a host round trip per layer. The host replays the same steps on
+// its own coin afterwards and checks that it drew the same alphas.
+__device__ void coin_merge(int hash_id, const u64 a[4], const u64 b[4], u64 out[4]) {
+    if (hash_id == WF_HASH_BLAKE3_256) {
+        u32 m[16], cv[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { m[2 * i] = (u32)a[i]; m[2 * i + 1] = (u32)(a[i] >> 32); m[8 + 2 * i] = (u32)b[i]; m[9 + 2 * i] = (u32)(b[i] >> 32); }
+        b3_iv(cv);
+        b3_compress(cv, m, 0, 64, B3_CHUNK_START | B3_CHUNK_END | B3_ROOT);
+#pragma unroll
+        for (int i = 0; i < 4; i++) out[i] = (u64)cv[2 * i] | ((u64)cv[2 * i + 1] << 32);
+    } else {
+        u64 in[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { in[i] = a[i]; in[4 + i] = b[i]; }
+        rp64_merge(in, out);
+    }
+}
+__device__ void coin_merge_with_int(int hash_id, const u64 seed[4], u64 value, u64 out[4]) {
+    if (hash_id == WF_HASH_BLAKE3_256) {  // blake/mod.rs:41-46
+        u32 m[16], cv[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { m[2 * i] = (u32)seed[i]; m[2 * i + 1] = (u32)(seed[i] >> 32); }
+        m[8] = (u32)value; m[9] = (u32)(value >> 32);
+#pragma unroll
+        for (int i = 10; i < 16; i++) m[i] = 0;
+        b3_iv(cv);
+        b3_compress(cv, m, 0, 40, B3_CHUNK_START | B3_CHUNK_END | B3_ROOT);
+#pragma unroll
+        for (int i = 0; i < 4; i++) out[i] = (u64)cv[2 * i] | ((u64)cv[2 * i + 1] << 32);
+    } else {  // rp64_256/mod.rs:198-218
+        u64 s[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) s[4 + i] = seed[i];
+        if (value < GL_P) { s[8] = value; s[0] = 5; }
+        else { s[8] = value - GL_P; s[9] = 1; s[0] = 6; }
+        rp64_permute(s);
+#pragma unroll
+        for (int i = 0; i < 4; i++) out[i] = s[4 + i];
+    }
+}
+// state: seed[4]; log: per layer root[4] then alpha[3]
+__global__ void fri_coin_kernel(int hash_id, u64* state, const u64* root, int d, u64* alpha_out, u64* log_entry) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    u64 seed[4], r[4], v[4];
+    for (int i = 0; i < 4; i++) { seed[i] = state[i]; r[i] = root[i]; }
+    coin_merge(hash_id, seed, r, seed);  // reseed
+    u64 counter = 0;
+    bool ok = false;
+    for (int t = 0; t < 1000 && !ok; t++) {
+        counter += 1;
+        coin_merge_with_int(hash_id, seed, counter, v);
+        ok = true;
+        for (int k = 0; k < d; k++) ok = ok && v[k] < GL_P;
+    }
+    for (int i = 0; i < 4; i++) { state[i] = seed[i]; log_entry[i] = r[i]; }
+    state[4] = counter;
+    for (int k = 0; k < 3; k++) { u64 a = (ok && k < d) ? v[k] : 0; alpha_out[k] = a; log_entry[4 + k] = a; }
+    log_entry[7] = ok ? 1 : 0;
+}
+cudaError_t fri_coin_step(int hash_id, u64* state, const u64* root, int d, u64* alpha_out, u64* log_entry, cudaStream_t st) {
+    fri_coin_kernel<<<1, 32, 0, st>>>(hash_id, state, root, d, alpha_out, log_entry);
+    return cudaGetLastError();
 }

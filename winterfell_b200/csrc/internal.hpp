@@ -98,6 +98,11 @@ int wf_dev_alloc(wf_ctx* ctx, size_t bytes, void** out);
 void wf_dev_free(wf_ctx* ctx, void* p);
 int wf_mat_alloc(wf_ctx* ctx, size_t rows, u32 cols, wf_mat** out);
 int wf_mat_alloc_w(wf_ctx* ctx, size_t rows, u32 cols, int W, wf_mat** out);
+struct PublicCoin;
+struct Digest;
+struct wf_fri;
+int wf_fri_build_layers_coin(wf_ctx* ctx, int hash_id, const wf_mat* evals, int d, uint32_t folding, uint32_t rem_max_deg,
+                             uint32_t blowup, PublicCoin& coin, std::vector<Digest>& commitments, wf_fri** out);
 int wf_get_twiddles(wf_ctx* ctx, u32 log_n, const u64** out);
 struct OpenPlan {
     u32 depth;

@@ -73,9 +73,7 @@ __global__ void __launch_bounds__(256) fib_constraints_kernel(FibEvalParams p) {
         if (i >= ce) continue;
         const size_t ls = i << lde_shift;
         const size_t nx = (ls + ((size_t)1 << p.log_blowup)) & (N - 1);  // trace_lde/default/mod.rs:169-180
-        for (u32 j = 0; j < p.k; j++) {
-            u64 c0 = seg_at(p.lde, ls, 2 * j), c1 = seg_at(p.lde, ls, 2 * j + 1);
-            u64 n0 = seg_at(p.lde, nx, 2 * j), n1 = seg_at(p.lde, nx, 2 * j + 1);
+        auto pair_terms = [&](u32 j, u64 c0, u64 c1, u64 n0, u64 n1) {
             u64 t0 = gl_sub(n0, gl_add(c0, c1));  // fib_small/air.rs:58
             u64 t1 = gl_sub(n1, gl_add(c1, n0));  // :59
             T[r] = ext_add(T[r], ext_mul_base(ld_ext<D>(p.tcoef + (size_t)(2 * j) * D), t0));
@@ -84,6 +82,24 @@ __global__ void __launch_bounds__(256) fib_constraints_kernel(FibEvalParams p) {
             B0[r] = ext_add(B0[r], ext_mul_base(ld_ext<D>(p.bcoef0 + (size_t)(2 * j) * D), gl_sub(c0, v)));
             B0[r] = ext_add(B0[r], ext_mul_base(ld_ext<D>(p.bcoef0 + (size_t)(2 * j + 1) * D), gl_sub(c1, v)));
             B1[r] = ext_add(B1[r], ext_mul_base(ld_ext<D>(p.bcoef1 + (size_t)j * D), gl_sub(c1, p.results[j])));
+        };
+        if (p.lde.W == 8) {
+            // one 64-byte segment row (four pairs) = four 16-byte loads, for the current and the next row
+            for (u32 g = 0; g * 4 < p.k; g++) {
+                const ulonglong2* cp = reinterpret_cast<const ulonglong2*>(p.lde.base + (size_t)g * p.lde.seg_stride + ls * 8);
+                const ulonglong2* np = reinterpret_cast<const ulonglong2*>(p.lde.base + (size_t)g * p.lde.seg_stride + nx * 8);
+                ulonglong2 cv[4], nv[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) { cv[q] = __ldg(cp + q); nv[q] = __ldg(np + q); }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    u32 j = g * 4 + q;
+                    if (j < p.k) pair_terms(j, cv[q].x, cv[q].y, nv[q].x, nv[q].y);
+                }
+            }
+        } else {
+            for (u32 j = 0; j < p.k; j++)
+                pair_terms(j, seg_at(p.lde, ls, 2 * j), seg_at(p.lde, ls, 2 * j + 1), seg_at(p.lde, nx, 2 * j), seg_at(p.lde, nx, 2 * j + 1));
         }
         u64 w = p.tw_ce[i & (half - 1)];
         if (i & half) w = gl_neg(w);
@@ -714,10 +730,6 @@ struct Channel {  // ProverChannel (prover/src/channel.rs)
         return r;
     }
 };
-template <int D>
-void fri_commit_cb(void* u, const uint8_t root[32]) { ((Channel<D>*)u)->commit(root); }
-template <int D>
-void fri_draw_cb(void* u, uint64_t* alpha) { GlExt<D> a = ((Channel<D>*)u)->draw(); for (int i = 0; i < D; i++) alpha[i] = a.v[i]; }
 
 template <int D>
 int upload_ext(wf_ctx* ctx, const std::vector<GlExt<D>>& v, size_t first, size_t count, u64** out) {
@@ -1040,9 +1052,9 @@ int deep_compose(wf_ctx* ctx, const wf_mat* lde, const wf_mat* alde, const wf_ma
     const u32 c = lde->m.cols, aw = alde ? alde->m.cols / D : 0, ct = c + aw;
     const size_t N = (size_t)1 << log_N;
     u64 *d_dt, *d_dq, *d_da;
-    CKI(upload_ext<D>(ctx, dc, 0, c, &d_dt));
-    CKI(upload_ext<D>(ctx, dc, c, aw, &d_da));
-    CKI(upload_ext<D>(ctx, dc, ct, kc, &d_dq));
+    CKI(upload_ext<D>(ctx, dc, 0, ct + kc, &d_dt));  // one upload (one synchronisation) for all coefficients
+    d_da = d_dt + (size_t)c * D;
+    d_dq = d_dt + (size_t)ct * D;
     wf_mat* deep;
     CKI(wf_mat_alloc(ctx, N, D, &deep));
     if (deep->m.W > D) CK(cudaMemsetAsync(deep->m.base, 0, deep->m.words() * 8, ctx->st));
@@ -1059,7 +1071,7 @@ int deep_compose(wf_ctx* ctx, const wf_mat* lde, const wf_mat* alde, const wf_ma
     ctx->launches += 2;
     CK(cudaGetLastError());
     // the coefficient buffers are pool allocations on the same stream: safe to release after the launch
-    for (u64* q : {d_dt, d_dq, d_da}) wf_dev_free(ctx, q);
+    wf_dev_free(ctx, d_dt);
     *out = deep;
     return WF_OK;
 }
@@ -1204,7 +1216,11 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     wf_mark(ctx, "deep_composition");
     // ---- 6. FRI (lib.rs:442-448) ----
     wf_fri* fri;
-    CKI(wf_fri_build_layers(ctx, h, deep, D, o.folding, o.rem_max_deg, o.blowup, fri_commit_cb<D>, fri_draw_cb<D>, &ch, &fri));
+    {   // transcript replicated on the device: one synchronisation for the whole commit phase (capi.cu)
+        std::vector<Digest> fri_roots;
+        CKI(wf_fri_build_layers_coin(ctx, h, deep, D, o.folding, o.rem_max_deg, o.blowup, ch.coin, fri_roots, &fri));
+        for (auto& r : fri_roots) ch.commitments.bytes(r.b, 32);
+    }
     wf_mat_free(ctx, deep);
     wf_mark(ctx, "fri_layers");
     // ---- 7. grinding + query positions (channel.rs:151-184; serial semantics: smallest nonce) ----
