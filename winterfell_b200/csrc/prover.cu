@@ -83,24 +83,10 @@ __global__ void __launch_bounds__(256) fib_constraints_kernel(FibEvalParams p) {
             B0[r] = ext_add(B0[r], ext_mul_base(ld_ext<D>(p.bcoef0 + (size_t)(2 * j + 1) * D), gl_sub(c1, v)));
             B1[r] = ext_add(B1[r], ext_mul_base(ld_ext<D>(p.bcoef1 + (size_t)j * D), gl_sub(c1, p.results[j])));
         };
-        if (p.lde.W == 8) {
-            // one 64-byte segment row (four pairs) = four 16-byte loads, for the current and the next row
-            for (u32 g = 0; g * 4 < p.k; g++) {
-                const ulonglong2* cp = reinterpret_cast<const ulonglong2*>(p.lde.base + (size_t)g * p.lde.seg_stride + ls * 8);
-                const ulonglong2* np = reinterpret_cast<const ulonglong2*>(p.lde.base + (size_t)g * p.lde.seg_stride + nx * 8);
-                ulonglong2 cv[4], nv[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) { cv[q] = __ldg(cp + q); nv[q] = __ldg(np + q); }
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    u32 j = g * 4 + q;
-                    if (j < p.k) pair_terms(j, cv[q].x, cv[q].y, nv[q].x, nv[q].y);
-                }
-            }
-        } else {
-            for (u32 j = 0; j < p.k; j++)
-                pair_terms(j, seg_at(p.lde, ls, 2 * j), seg_at(p.lde, ls, 2 * j + 1), seg_at(p.lde, nx, 2 * j), seg_at(p.lde, nx, 2 * j + 1));
-        }
+        // (16-byte vector loads of whole segment rows were tried here: neutral in the base field, 60 % slower
+        // with cubic coefficients — the staged rows cost registers the accumulators need)
+        for (u32 j = 0; j < p.k; j++)
+            pair_terms(j, seg_at(p.lde, ls, 2 * j), seg_at(p.lde, ls, 2 * j + 1), seg_at(p.lde, nx, 2 * j), seg_at(p.lde, nx, 2 * j + 1));
         u64 w = p.tw_ce[i & (half - 1)];
         if (i & half) w = gl_neg(w);
         u64 x = gl_mul(w, GL_GENERATOR);  // domain.rs:123 get_ce_x_at
