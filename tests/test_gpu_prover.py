@@ -157,3 +157,34 @@ def test_invalid_sequence_is_refused(ctx, oracle):
     opts = oracle.make_opts(num_queries=8, blowup=8)
     with pytest.raises(wf.WfError):
         ctx.prove_air(desc, trace[:, :32].copy(), opts)  # n / stride no longer equals the number of values
+
+
+# ---- the corners of ProofOptions::new (air/src/options.rs:132-190) and TraceInfo (trace_info.rs:60-110) ----
+EDGE_CASES = [
+    (1, 3, dict(num_queries=5, blowup=128, grinding=0, ext=1, folding=16, rem_max_deg=7)),     # N = (7 + 1) * 128: no FRI layer at all
+    (1, 3, dict(num_queries=255, blowup=2, grinding=0, ext=3, folding=2, rem_max_deg=0)),      # minimum length / blowup / remainder, maximum queries
+    (127, 4, dict(num_queries=16, blowup=4, grinding=3, ext=2, folding=4, rem_max_deg=1)),     # 254 columns (MAX_TRACE_WIDTH = 255)
+    (2, 10, dict(num_queries=64, blowup=16, grinding=0, ext=1, folding=16, rem_max_deg=255)),  # maximum remainder degree
+    (1, 6, dict(num_queries=1, blowup=8, grinding=0, ext=1, folding=8, rem_max_deg=3, batch_c=1, batch_d=2)),
+    (3, 5, dict(num_queries=40, blowup=64, grinding=0, ext=2, folding=2, rem_max_deg=15, hash_id=1)),
+]
+
+
+@pytest.mark.parametrize("k,log_n,kw", EDGE_CASES)
+def test_option_corners_match_oracle(ctx, oracle, k, log_n, kw):
+    trace, results = oracle.build_fib_trace(k, 1 << log_n)
+    opts = oracle.make_opts(**kw)
+    got = ctx.prove_fib(trace, results, opts)
+    assert got == oracle.prove_fib(trace, results, opts)
+    assert oracle.verify_fib(got, k, results, kw.get("hash_id", 0)) == 0
+
+
+@pytest.mark.parametrize("kw", [dict(blowup=3), dict(blowup=256), dict(num_queries=0), dict(num_queries=256), dict(folding=3),
+                                dict(ext=4), dict(hash_id=7), dict(grinding=33)])
+def test_invalid_options_are_refused(ctx, oracle, kw):
+    # the reference panics in ProofOptions::new; the C ABI returns an error instead of proving
+    trace, results = oracle.build_fib_trace(1, 64)
+    base = dict(num_queries=8, blowup=8, grinding=0, ext=1, folding=4, rem_max_deg=7)
+    base.update(kw)
+    with pytest.raises(wf.WfError):
+        ctx.prove_fib(trace, results, oracle.make_opts(**base))

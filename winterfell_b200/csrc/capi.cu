@@ -595,47 +595,58 @@ int wf_trace_lde_from_host(wf_ctx* ctx, const uint64_t* const* cols, uint32_t nc
         CK(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
     }
     const u32 nchunks = (ncols + Wc - 1) / Wc;
-    wf_mat *polys, *lde, *tr;
+    wf_mat *polys = nullptr, *lde = nullptr, *tr = nullptr;
     void* stage[2] = {nullptr, nullptr};
     void* tmp = nullptr;
-    CKI(wf_mat_alloc_w(ctx, nrows, ncols, Wc, &polys));
-    CKI(wf_mat_alloc(ctx, nrows << log_blowup, ncols, &lde));
-    CKI(wf_mat_alloc_w(ctx, nrows, Wc, Wc, &tr));                       // one chunk of trace values (reused)
-    for (int i = 0; i < 2; i++) CKI(wf_dev_alloc(ctx, (size_t)Wc * nrows * 8, &stage[i]));
-    CKI(wf_dev_alloc(ctx, (size_t)Wc * nrows * 8, &tmp));               // two-pass scratch
-    if (lde->m.W > (int)ncols) CK(cudaMemsetAsync(lde->m.base, 0, lde->m.words() * 8, ctx->st));  // padding columns
-    // the copy stream must not write pool buffers before their previous users on the compute stream are done
-    CK(cudaEventRecord(ctx->ev_start, ctx->st));
-    CK(cudaStreamWaitEvent(ctx->copy_st, ctx->ev_start, 0));
-    for (u32 k = 0; k < nchunks; k++) {
-        const u32 c0 = k * Wc, cw = std::min<u32>(Wc, ncols - c0);
-        const int sb = k & 1;
-        if (k >= 2) CK(cudaStreamWaitEvent(ctx->copy_st, ctx->ev_used[sb], 0));
-        for (u32 j = 0; j < cw; j++)
-            CK(cudaMemcpyAsync((u64*)stage[sb] + (size_t)j * nrows, cols[c0 + j], nrows * 8, cudaMemcpyHostToDevice, ctx->copy_st));
-        CK(cudaEventRecord(ctx->ev_up[sb], ctx->copy_st));
-        CK(cudaStreamWaitEvent(ctx->st, ctx->ev_up[sb], 0));
-        SegMatrix trv = tr->m;
-        trv.cols = cw;
-        CK(layout_cols_to_seg((const u64*)stage[sb], nrows, 1, mont, trv, ctx->st));
-        CK(cudaEventRecord(ctx->ev_used[sb], ctx->st));
-        ctx->launches++;
-        SegMatrix pv = polys->m;                                          // segment k of the W = Wc polys matrix
-        pv.base = polys->m.base + (size_t)k * polys->m.seg_stride;
-        pv.cols = cw;
-        SegMatrix tv = trv;
-        tv.base = (u64*)tmp;
-        int r = run_ntt(ctx, trv, pv, &tv, log_n, 1);
-        if (r != WF_OK) return r;
-        SegMatrix ov = lde->m;                                            // out segment holding columns c0..
-        ov.base = lde->m.base + (size_t)(c0 / Wout) * lde->m.seg_stride;
-        ov.cols = cw;
-        r = run_lde(ctx, pv, ov, log_n, log_blowup, c0 % Wout);
-        if (r != WF_OK) return r;
+    auto release = [&](bool results_too) {  // buffers return to the pool in stream order
+        wf_mat_free(ctx, tr);
+        for (int i = 0; i < 2; i++) wf_dev_free(ctx, stage[i]);
+        wf_dev_free(ctx, tmp);
+        if (results_too) { wf_mat_free(ctx, polys); wf_mat_free(ctx, lde); }
+    };
+    auto body = [&]() -> int {
+        CKI(wf_mat_alloc_w(ctx, nrows, ncols, Wc, &polys));
+        CKI(wf_mat_alloc(ctx, nrows << log_blowup, ncols, &lde));
+        CKI(wf_mat_alloc_w(ctx, nrows, Wc, Wc, &tr));                       // one chunk of trace values (reused)
+        for (int i = 0; i < 2; i++) CKI(wf_dev_alloc(ctx, (size_t)Wc * nrows * 8, &stage[i]));
+        CKI(wf_dev_alloc(ctx, (size_t)Wc * nrows * 8, &tmp));               // two-pass scratch
+        if (lde->m.W > (int)ncols) CK(cudaMemsetAsync(lde->m.base, 0, lde->m.words() * 8, ctx->st));  // padding columns
+        // the copy stream must not write pool buffers before their previous users on the compute stream are done
+        CK(cudaEventRecord(ctx->ev_start, ctx->st));
+        CK(cudaStreamWaitEvent(ctx->copy_st, ctx->ev_start, 0));
+        for (u32 k = 0; k < nchunks; k++) {
+            const u32 c0 = k * Wc, cw = std::min<u32>(Wc, ncols - c0);
+            const int sb = k & 1;
+            if (k >= 2) CK(cudaStreamWaitEvent(ctx->copy_st, ctx->ev_used[sb], 0));
+            for (u32 j = 0; j < cw; j++)
+                CK(cudaMemcpyAsync((u64*)stage[sb] + (size_t)j * nrows, cols[c0 + j], nrows * 8, cudaMemcpyHostToDevice, ctx->copy_st));
+            CK(cudaEventRecord(ctx->ev_up[sb], ctx->copy_st));
+            CK(cudaStreamWaitEvent(ctx->st, ctx->ev_up[sb], 0));
+            SegMatrix trv = tr->m;
+            trv.cols = cw;
+            CK(layout_cols_to_seg((const u64*)stage[sb], nrows, 1, mont, trv, ctx->st));
+            CK(cudaEventRecord(ctx->ev_used[sb], ctx->st));
+            ctx->launches++;
+            SegMatrix pv = polys->m;                                          // segment k of the W = Wc polys matrix
+            pv.base = polys->m.base + (size_t)k * polys->m.seg_stride;
+            pv.cols = cw;
+            SegMatrix tv = trv;
+            tv.base = (u64*)tmp;
+            CKI(run_ntt(ctx, trv, pv, &tv, log_n, 1));
+            SegMatrix ov = lde->m;                                            // out segment holding columns c0..
+            ov.base = lde->m.base + (size_t)(c0 / Wout) * lde->m.seg_stride;
+            ov.cols = cw;
+            CKI(run_lde(ctx, pv, ov, log_n, log_blowup, c0 % Wout));
+        }
+        return WF_OK;
+    };
+    int rc = body();
+    if (rc != WF_OK) {
+        cudaStreamSynchronize(ctx->copy_st);  // no copy may still target a buffer that goes back to the pool
+        release(true);
+        return rc;
     }
-    wf_mat_free(ctx, tr);
-    for (int i = 0; i < 2; i++) wf_dev_free(ctx, stage[i]);
-    wf_dev_free(ctx, tmp);
+    release(false);
     *polys_out = polys;
     *lde_out = lde;
     return WF_OK;

@@ -1062,6 +1062,24 @@ int deep_compose(wf_ctx* ctx, const wf_mat* lde, const wf_mat* alde, const wf_ma
     return WF_OK;
 }
 
+// Device objects of one proof: whatever is still registered when prove_air leaves (normally or through
+// an error return) goes back to the context's pool.
+struct ProofScope {
+    wf_ctx* ctx;
+    std::vector<wf_mat**> mats;
+    std::vector<wf_tree**> trees;
+    wf_fri** fri = nullptr;
+    explicit ProofScope(wf_ctx* c) : ctx(c) {}
+    void own(std::initializer_list<wf_mat**> l) { mats.insert(mats.end(), l); }
+    void own(std::initializer_list<wf_tree**> l) { trees.insert(trees.end(), l); }
+    void drop(wf_mat*& m) { wf_mat_free(ctx, m); m = nullptr; }
+    ~ProofScope() {
+        if (fri && *fri) wf_fri_free(ctx, *fri);
+        for (wf_mat** m : mats) if (*m) wf_mat_free(ctx, *m);
+        for (wf_tree** t : trees) if (*t) wf_tree_free(ctx, *t);
+    }
+};
+
 template <int D>
 int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont, u32 log_n,
               const Options& o, wf_aux_builder_fn aux_builder, void* aux_user, std::vector<u8>& proof_out) {
@@ -1089,14 +1107,20 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     Channel<D> ch(h, seed);
 
     // ---- 1. trace commitment (lib.rs:497-522) ----
-    wf_mat *trace = nullptr, *polys = nullptr, *lde = nullptr;
-    wf_tree* ttree = nullptr;
+    wf_mat *trace = nullptr, *polys = nullptr, *lde = nullptr, *apolys = nullptr, *alde = nullptr, *comp = nullptr, *cpolys = nullptr,
+           *clde = nullptr, *deep = nullptr;
+    wf_tree *ttree = nullptr, *atree = nullptr, *ctree = nullptr;
+    wf_fri* fri = nullptr;
+    ProofScope scope(ctx);
+    scope.own({&trace, &polys, &lde, &apolys, &alde, &comp, &cpolys, &clde, &deep});
+    scope.own({&ttree, &atree, &ctree});
+    scope.fri = &fri;
     wf_mark(ctx, "start");
     if (d_trace) {
         CKI(wf_mat_from_device_columns(ctx, d_trace, c, n, &trace));
         wf_mark(ctx, "trace_upload_layout");
         CKI(wf_mat_interpolate(ctx, trace, &polys));
-        wf_mat_free(ctx, trace);
+        scope.drop(trace);
         wf_mark(ctx, "trace_interpolate");
         CKI(wf_mat_lde(ctx, polys, log_b, &lde));
     } else {
@@ -1112,8 +1136,6 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
 
     // ---- 1b. auxiliary segment (lib.rs:309-349; Air::get_aux_rand_elements air/src/air/mod.rs:292-306;
     //          DefaultTraceLde::set_aux_trace trace_lde/default/mod.rs:140-166) ----
-    wf_mat *apolys = nullptr, *alde = nullptr;
-    wf_tree* atree = nullptr;
     std::vector<u64> rnd_flat;  // [nr][D], canonical
     if (aw) {
         for (u32 i = 0; i < air.nr; i++) { GlExt<D> e = ch.draw(); for (int q = 0; q < D; q++) rnd_flat.push_back(e.v[q]); }
@@ -1139,14 +1161,11 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     // coefficient order: main transition, aux transition (transition/mod.rs:63-72), main assertions,
     // aux assertions (boundary/mod.rs:108-110)
     std::vector<GlExt<D>> cc = ch.draw_coeffs(o.batch_c, n_tr + n_as);
-    wf_mat* comp;
     CKI(eval_constraints<D>(ctx, air, lde, alde, cc, rnd_flat, log_n, log_b, &comp));
     wf_mark(ctx, "constraint_eval");
     // ---- 3. composition polynomial + commitment (lib.rs:527-552) ----
-    wf_mat *cpolys, *clde;
-    wf_tree* ctree;
     CKI(composition_commit(ctx, h, comp, log_n, log_b, D, kc, &cpolys, &clde, &ctree));
-    wf_mat_free(ctx, comp);
+    scope.drop(comp);
     CKI(wf_tree_root(ctx, ctree, root));
     wf_mark(ctx, "composition_commit");
     ch.commit(root);
@@ -1197,17 +1216,15 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     GlExt<D> Sz = ext_zero<D>(), Szg = ext_zero<D>();  // S(z), S(zg): the constant terms composer/mod.rs:202-210 subtracts
     for (u32 j = 0; j < ct; j++) { Sz = ext_add(Sz, ext_mul(dc[j], t_cur[j])); Szg = ext_add(Szg, ext_mul(dc[j], t_nxt[j])); }
     for (u32 j = 0; j < kc; j++) { Sz = ext_add(Sz, ext_mul(dc[ct + j], q_cur[j])); Szg = ext_add(Szg, ext_mul(dc[ct + j], q_nxt[j])); }
-    wf_mat* deep;
     CKI(deep_compose<D>(ctx, lde, alde, clde, kc, log_n + log_b, dc, z, zg, Sz, Szg, &deep));
     wf_mark(ctx, "deep_composition");
     // ---- 6. FRI (lib.rs:442-448) ----
-    wf_fri* fri;
     {   // transcript replicated on the device: one synchronisation for the whole commit phase (capi.cu)
         std::vector<Digest> fri_roots;
         CKI(wf_fri_build_layers_coin(ctx, h, deep, D, o.folding, o.rem_max_deg, o.blowup, ch.coin, fri_roots, &fri));
         for (auto& r : fri_roots) ch.commitments.bytes(r.b, 32);
     }
-    wf_mat_free(ctx, deep);
+    scope.drop(deep);
     wf_mark(ctx, "fri_layers");
     // ---- 7. grinding + query positions (channel.rs:151-184; serial semantics: smallest nonce) ----
     u64 nonce;
@@ -1250,11 +1267,7 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     w.u64_(nonce);
     wf_mark(ctx, "queries_and_proof");
     proof_out.swap(w.v);
-    wf_fri_free(ctx, fri);
-    for (wf_mat* m : {polys, lde, cpolys, clde}) wf_mat_free(ctx, m);
-    if (aw) { wf_mat_free(ctx, apolys); wf_mat_free(ctx, alde); wf_tree_free(ctx, atree); }
-    wf_tree_free(ctx, ttree);
-    wf_tree_free(ctx, ctree);
+    // `scope` returns every device object of this proof to the pool
     return WF_OK;
 }
 
@@ -1272,8 +1285,9 @@ static int parse_options(wf_ctx* ctx, const uint32_t* opts, Options& o) {
     o.rem_max_deg = opts[5]; o.batch_c = opts[6]; o.batch_d = opts[7]; o.hash_id = (int)opts[8];
     o.num_partitions = 1; o.hash_rate = 1;
     if (o.blowup < 2 || o.blowup > 128 || (o.blowup & (o.blowup - 1)) || o.num_queries == 0 || o.num_queries > 255 || o.batch_c > 2 ||
-        o.batch_d > 2 || o.grinding > 32 || o.rem_max_deg > 255)
-        return wf_fail(ctx, WF_ERR_INVALID, "bad proof options");
+        o.batch_d > 2 || o.grinding > 32 || o.rem_max_deg > 255 || ((o.rem_max_deg + 1) & o.rem_max_deg) ||
+        (o.folding != 2 && o.folding != 4 && o.folding != 8 && o.folding != 16) || o.ext < 1 || o.ext > 3)
+        return wf_fail(ctx, WF_ERR_INVALID, "bad proof options");  // ProofOptions::new asserts (air/src/options.rs:132-190)
     if (o.hash_id != WF_HASH_BLAKE3_256 && o.hash_id != WF_HASH_RP64_256) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "unknown hash %d", o.hash_id);
     return WF_OK;
 }
