@@ -98,3 +98,28 @@ def test_sequence_assertions_roundtrip(oracle, n):
     t2 = trace.copy()
     t2[2, 1] = 8  # periodic assertion (column 2, first step 1) expects 7; column 2 has no transition constraint
     assert oracle.verify_air(desc, oracle.prove_air(desc, t2, opts)) != 0
+
+
+# ---- committed golden fixtures (tests/golden/proof_digests.json, made by tests/golden/make_proof_digests.py) ----
+def _golden():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "proof_digests.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("idx", range(11))
+def test_oracle_reproduces_golden_proof_digests(oracle, idx):
+    import hashlib
+    rec = _golden()[idx]
+    opts = oracle.make_opts(**rec["opts"])
+    if rec["kind"] == "fib":
+        trace, res = oracle.build_fib_trace(rec["k"], 1 << rec["log_n"])
+        proof = oracle.prove_fib(trace, res, opts)
+    elif rec["air"] == "perm_rap":
+        desc, trace, builder = airs.perm_rap(rec["n"])
+        proof = oracle.prove_air_aux(desc, trace, opts, builder, airs.PERM_RAP_AUX_WIDTH, 2)
+    else:
+        desc, trace = getattr(airs, rec["air"])(rec["n"])
+        proof = oracle.prove_air(desc, trace, opts)
+    assert len(proof) == rec["bytes"] and hashlib.sha256(proof).hexdigest() == rec["sha256"]
