@@ -91,6 +91,12 @@ int wf_mat_evaluate(wf_ctx* ctx, const wf_mat* polys, wf_mat** evals);
 /* RowMatrix::evaluate_polys_over::<8> (row_matrix.rs:84-100): LDE over the coset 7 * <w_N>,
  * N = n << log_blowup, row i <-> point 7 * w_N^i (natural order). */
 int wf_mat_lde(wf_ctx* ctx, const wf_mat* polys, uint32_t log_blowup, wf_mat** lde);
+/* same, into a matrix the caller provides (e.g. a wf_mat_wrap_device view of a collective's send buffer) */
+int wf_mat_lde_into(wf_ctx* ctx, const wf_mat* polys, uint32_t log_blowup, wf_mat* lde);
+/* non-owning handle over device memory that already holds a rows x cols matrix in segment layout
+ * (ceil(cols / W) segments of rows x W words, W = 8 for cols >= 8, else the next power of two >= cols);
+ * wf_mat_free releases the handle, not the memory */
+int wf_mat_wrap_device(wf_ctx* ctx, uint64_t* d_segments, size_t rows, uint32_t cols, wf_mat** out);
 /* DefaultTraceLde::new up to the commitment (prover/src/trace/trace_lde/default/mod.rs:63-100,
  * build_trace_commitment :245-265) straight from HOST columns: equivalent to wf_mat_from_host_columns ->
  * wf_mat_interpolate -> wf_mat_lde, but the upload of column chunk k+1 overlaps the layout / iNTT / LDE of

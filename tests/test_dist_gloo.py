@@ -16,16 +16,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 class OracleBackend:
-    def lde_rows(self, cols, ncols, n, log_blowup):
+    """CPU stand-in for CudaBackend (row-major exchange format)."""
+
+    def pack(self, cols, ncols, n, log_blowup, world):
         from oracle import oracle as o
         polys = o.interpolate_columns(cols.numpy().view(np.uint64))
-        return torch.from_numpy(o.lde_rows(polys, 1 << log_blowup).view(np.int64))
+        rows = torch.from_numpy(o.lde_rows(polys, 1 << log_blowup).view(np.int64))
+        return rows.view(world, -1)
 
-    def subtree_root(self, hash_id, rows):
+    def commit(self, hash_id, recv, rows_per, ncols_total, cl):
         from oracle import oracle as o
+        world = recv.shape[0]
+        rows = recv.view(world, rows_per, cl).permute(1, 0, 2).reshape(rows_per, ncols_total).contiguous()
         lv = o.hash_rows(hash_id, rows.numpy().view(np.uint64))
         nd = o.merkle_nodes(hash_id, lv)
-        return nd[1].tobytes(), torch.from_numpy(lv), torch.from_numpy(nd)
+        return nd[1].tobytes(), rows, torch.from_numpy(lv), torch.from_numpy(nd)
 
 
 def _worker(rank, world, port, hash_id, log_n, cols, q):

@@ -51,6 +51,8 @@ _SIGS = [
     ("wf_mat_interpolate", C.c_int, [vp, vp, C.POINTER(vp)]),
     ("wf_mat_evaluate", C.c_int, [vp, vp, C.POINTER(vp)]),
     ("wf_mat_lde", C.c_int, [vp, vp, C.c_uint32, C.POINTER(vp)]),
+    ("wf_mat_lde_into", C.c_int, [vp, vp, C.c_uint32, vp]),
+    ("wf_mat_wrap_device", C.c_int, [vp, vp, C.c_size_t, C.c_uint32, C.POINTER(vp)]),
     ("wf_trace_lde_from_host", C.c_int, [vp, C.POINTER(u64p), C.c_uint32, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(vp), C.POINTER(vp)]),
     ("wf_mat_interpolate_with_offset", C.c_int, [vp, vp, C.c_uint64, C.POINTER(vp)]),
     ("wf_commit_rows", C.c_int, [vp, C.c_int, vp, C.POINTER(vp)]),
@@ -180,6 +182,12 @@ class Context:
         self.check(self.L.wf_trace_lde_from_host(self.h, ptrs, c, n, int(mont), log_blowup, C.byref(p), C.byref(l)))
         self.sync()  # `a` may be a temporary: the asynchronous copies must finish before it is released
         return Mat(self, p), Mat(self, l)
+
+    def mat_wrap_device(self, dptr, nrows, ncols):
+        """Non-owning Mat over device memory in segment layout (the caller keeps the memory alive)."""
+        h = vp()
+        self.check(self.L.wf_mat_wrap_device(self.h, vp(dptr), nrows, ncols, C.byref(h)))
+        return Mat(self, h)
 
     def mat_from_device_columns(self, dptr, ncols, nrows):
         h = vp()
@@ -398,6 +406,9 @@ class Mat:
 
     def evaluate(self):
         return self._unary(self.ctx.L.wf_mat_evaluate)
+
+    def lde_into(self, log_blowup, out):
+        self.ctx.check(self.ctx.L.wf_mat_lde_into(self.ctx.h, self.h, log_blowup, out.h))
 
     def lde(self, log_blowup):
         return self._unary(self.ctx.L.wf_mat_lde, log_blowup)

@@ -465,6 +465,21 @@ int wf_mat_from_host_columns(wf_ctx* ctx, const uint64_t* const* cols, uint32_t 
     *out = m;
     return WF_OK;
 }
+// Non-owning handle over caller-allocated device memory already in the segment layout of a rows x cols
+// matrix (segment width as for any matrix of `cols` columns: 8 for cols >= 8). wf_mat_free releases the
+// handle only. Lets an LDE be written into, or a commitment be taken from, a buffer that a collective
+// sends or receives (winterfell_b200/dist.py).
+int wf_mat_wrap_device(wf_ctx* ctx, uint64_t* d_segments, size_t rows, uint32_t cols, wf_mat** out) {
+    if (!ctx || !d_segments || !out || rows == 0 || cols == 0) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    wf_mat* m = new wf_mat();
+    m->m.rows = rows;
+    m->m.cols = cols;
+    m->m.W = seg_width_for(cols);
+    m->m.seg_stride = rows * m->m.W;
+    m->m.base = d_segments;  // not in ctx->live: wf_dev_free ignores it
+    *out = m;
+    return WF_OK;
+}
 int wf_mat_select_columns(wf_ctx* ctx, const wf_mat* m, uint32_t first, uint32_t count, wf_mat** out) {
     if (!ctx || !m || !out || count == 0 || first + count > m->m.cols) return wf_fail(ctx, WF_ERR_INVALID, "bad column range");
     wf_mat* o;
@@ -560,6 +575,15 @@ int wf_mat_lde(wf_ctx* ctx, const wf_mat* polys, uint32_t log_blowup, wf_mat** l
     if (r != WF_OK) { wf_mat_free(ctx, o); return r; }
     *lde = o;
     return WF_OK;
+}
+
+int wf_mat_lde_into(wf_ctx* ctx, const wf_mat* polys, uint32_t log_blowup, wf_mat* lde) {
+    if (!ctx || !polys || !lde) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    u32 log_n;
+    if (log2_exact(polys->m.rows, &log_n) || log_n < 1) return wf_fail(ctx, WF_ERR_INVALID, "rows must be a power of two >= 2");
+    if (log_blowup > 7 || lde->m.rows != (polys->m.rows << log_blowup) || lde->m.cols != polys->m.cols || lde->m.W != polys->m.W)
+        return wf_fail(ctx, WF_ERR_INVALID, "output matrix does not match the LDE shape");
+    return run_lde(ctx, polys->m, lde->m, log_n, log_blowup);
 }
 
 // DefaultTraceLde::new up to the commitment (trace_lde/default/mod.rs:63-100, build_trace_commitment

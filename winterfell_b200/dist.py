@@ -43,60 +43,83 @@ def top_levels(hash_id, roots):
 
 
 class CudaBackend:
-    """Local compute on this rank's GPU through the C ABI."""
+    """Local compute on this rank's GPU through the C ABI.
+
+    Exchange format (when the rank owns a multiple of 8 columns, i.e. whole segments): the LDE is written
+    by the library straight into a torch buffer in segment layout [local segment][N rows][8]; the send
+    buffer is that tensor regrouped by destination, [dest][local segment][rows_per][8] (one device copy);
+    what arrives, [source][local segment][rows_per][8], IS the segment layout of the rank's
+    rows_per x ncols_total row shard (global segment = source * local_segments + local segment), so the
+    commitment kernels run on the receive buffer in place. Other widths take a row-major exchange."""
 
     def __init__(self, ctx):
         self.ctx = ctx
         self.device = torch.device("cuda", torch.cuda.current_device())
 
-    def lde_rows(self, cols_dev, ncols, n, log_blowup):
-        """cols_dev: int64 CUDA tensor [ncols, n] (canonical words). Returns int64 CUDA tensor [N, ncols]."""
+    def pack(self, cols_dev, ncols, n, log_blowup, world):
+        """cols_dev: int64 CUDA tensor [ncols, n]. Returns the all-to-all send tensor [world, chunk]."""
+        N = n << log_blowup
         m = self.ctx.mat_from_device_columns(cols_dev.data_ptr(), ncols, n)
         polys = m.interpolate()
+        if ncols % 8 == 0:
+            nsl = ncols // 8
+            seg = torch.empty((nsl, N, 8), dtype=torch.int64, device=self.device)
+            out = self.ctx.mat_wrap_device(seg.data_ptr(), N, ncols)
+            polys.lde_into(log_blowup, out)
+            self.ctx.sync()
+            for h in (m, polys, out):
+                h.free()
+            rp = N // world
+            return seg.view(nsl, world, rp * 8).permute(1, 0, 2).contiguous().view(world, nsl * rp * 8)
         lde = polys.lde(log_blowup)
-        out = torch.empty((n << log_blowup, ncols), dtype=torch.int64, device=self.device)
-        lde.to_device_rows(out.data_ptr())
+        rows = torch.empty((N, ncols), dtype=torch.int64, device=self.device)
+        lde.to_device_rows(rows.data_ptr())
         self.ctx.sync()
         for h in (m, polys, lde):
             h.free()
-        return out
+        return rows.view(world, (N // world) * ncols)
 
-    def subtree_root(self, hash_id, rows):
-        """rows: int64 CUDA tensor [nrows, c]. Returns (root bytes, leaf digests tensor, nodes tensor)."""
-        nrows, c = rows.shape
-        digests = torch.empty(nrows * 32, dtype=torch.uint8, device=self.device)
-        nodes = torch.empty(nrows * 32, dtype=torch.uint8, device=self.device)
-        self.ctx.hash_rows_dev(hash_id, rows.data_ptr(), nrows, c, digests.data_ptr())
-        self.ctx.merkle_dev(hash_id, digests.data_ptr(), nrows, nodes.data_ptr())
+    def commit(self, hash_id, recv, rows_per, ncols_total, cl):
+        """recv: [world, chunk] as received. Returns (subtree root bytes, row shard tensor, leaf digests, nodes)."""
+        world = recv.shape[0]
+        if cl % 8 == 0:
+            shard = self.ctx.mat_wrap_device(recv.data_ptr(), rows_per, ncols_total)
+            tree = self.ctx.commit_rows(hash_id, shard)
+            root = tree.root()
+            leaves, nodes = tree.to_host() if rows_per <= (1 << 16) else (None, None)
+            shard.free()
+            tree.free()
+            return root, recv, leaves, nodes
+        rows = recv.view(world, rows_per, cl).permute(1, 0, 2).reshape(rows_per, ncols_total).contiguous()
+        digests = torch.empty(rows_per * 32, dtype=torch.uint8, device=self.device)
+        nodes = torch.empty(rows_per * 32, dtype=torch.uint8, device=self.device)
+        self.ctx.hash_rows_dev(hash_id, rows.data_ptr(), rows_per, ncols_total, digests.data_ptr())
+        self.ctx.merkle_dev(hash_id, digests.data_ptr(), rows_per, nodes.data_ptr())
         self.ctx.sync()
-        return bytes(nodes[32:64].cpu().numpy()), digests, nodes
+        return bytes(nodes[32:64].cpu().numpy()), rows, digests, nodes
 
 
 def sharded_trace_commit(backend, hash_id, local_cols, ncols_total, log_n, log_blowup, group=None):
     """Column-sharded trace commitment. `local_cols`: this rank's column block [c_local, n] as a
     torch int64 tensor on the backend's device. All ranks must own the same number of columns
-    (ncols_total % world == 0). Returns (root, row_shard [N/G, c], subtree leaf digests, subtree nodes)."""
+    (ncols_total % world == 0). Returns (root, row shard, subtree leaf digests, subtree nodes)."""
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
     n = 1 << log_n
     N = n << log_blowup
     assert ncols_total % world == 0, "columns must divide evenly across ranks"
     assert N % world == 0 and world & (world - 1) == 0, "world size must be a power of two"
     cl = ncols_total // world
     assert tuple(local_cols.shape) == (cl, n)
-    # 1. local LDE of the owned columns: [N, cl] row-major
-    lde = backend.lde_rows(local_cols, cl, n, log_blowup)
-    # 2. all-to-all: send row range r to rank r
     rows_per = N // world
-    send = lde.reshape(world, rows_per * cl)
+    # 1. local LDE of the owned columns, regrouped by destination rank
+    send = backend.pack(local_cols, cl, n, log_blowup, world)
+    # 2. ONE all-to-all: row range r of every column block goes to rank r
     recv = torch.empty_like(send)
-    dist.all_to_all_single(recv.view(-1), send.contiguous().view(-1), group=group)
-    # recv[g] = my row range of column block g  ->  row-major [rows_per, ncols_total]
-    rows = recv.view(world, rows_per, cl).permute(1, 0, 2).reshape(rows_per, ncols_total).contiguous()
+    dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
     # 3. leaves + subtree over my rows
-    root_local, digests, nodes = backend.subtree_root(hash_id, rows)
+    root_local, rows, digests, nodes = backend.commit(hash_id, recv, rows_per, ncols_total, cl)
     # 4. all-gather the subtree roots, finish the top of the tree on every rank
-    mine = torch.frombuffer(bytearray(root_local), dtype=torch.uint8).to(lde.device)
+    mine = torch.frombuffer(bytearray(root_local), dtype=torch.uint8).to(send.device)
     gathered = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(gathered, mine, group=group)
     roots = [bytes(g.cpu().numpy()) for g in gathered]
