@@ -27,4 +27,8 @@ if resident:
     d_trace = torch.from_numpy(trace.view(np.int64)).cuda()
 for _ in range(reps):
     proof = ctx.prove_fib_dev(d_trace.data_ptr(), pairs, log_n, res, opts) if resident else ctx.prove_fib(trace, res, opts)
+if os.environ.get("WF_STAGES"):
+    ctx.set_profiling(True)
+    proof = ctx.prove_fib_dev(d_trace.data_ptr(), pairs, log_n, res, opts) if resident else ctx.prove_fib(trace, res, opts)
+    print({k: round(v, 3) for k, v in ctx.stage_times()})
 print("ok", len(proof))

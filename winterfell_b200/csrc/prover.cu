@@ -413,9 +413,21 @@ __global__ void __launch_bounds__(DEEP_SUM_THREADS) deep_sum_kernel(DeepParams p
 }
 
 // rows per thread sharing one batch inversion
-#define DEEP_ROWS (D == 1 ? 16 : (D == 2 ? 8 : 4))
+#ifndef DEEP_ROWS1
+#define DEEP_ROWS1 16
+#endif
+#ifndef DEEP_ROWS2
+#define DEEP_ROWS2 8
+#endif
+#ifndef DEEP_ROWS3
+#define DEEP_ROWS3 4
+#endif
+#ifndef DEEP_DIV_MINB
+#define DEEP_DIV_MINB 2  // <= 128 registers: measured 0.55 -> 0.44 ms on cfg2, 1.20 -> 0.98 ms on 2^18 x 64 cubic
+#endif
+#define DEEP_ROWS (D == 1 ? DEEP_ROWS1 : (D == 2 ? DEEP_ROWS2 : DEEP_ROWS3))
 template <int D>
-__global__ void __launch_bounds__(256) deep_div_kernel(DeepParams p, GlExt<D> z, GlExt<D> zg, GlExt<D> Sz, GlExt<D> Szg) {
+__global__ void __launch_bounds__(256, DEEP_DIV_MINB) deep_div_kernel(DeepParams p, GlExt<D> z, GlExt<D> zg, GlExt<D> Sz, GlExt<D> Szg) {
     const size_t N = (size_t)1 << p.log_N;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
