@@ -43,10 +43,33 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nv, self.h = self._nvml()  # initialised here, before the timed region starts
+
+    def _nvml(self):
+        """NVML in-process (the library nvidia-smi itself reads): no process spawn inside the timed region —
+        a cold `nvidia-smi` start takes a driver lock for several ms and once stretched a 10-step mean by 14 %."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            return None, None
 
     def run(self):
+        nv, h = self.nv, self.h
         while not self.stop_flag:
             try:
+                if nv is not None:
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    bit = lambda name: "Active" if r & getattr(nv, name, 0) else "Not Active"
+                    self.samples.append([str(sm), str(mx), bit("nvmlClocksThrottleReasonHwSlowdown"),
+                                         bit("nvmlClocksThrottleReasonHwThermalSlowdown"), bit("nvmlClocksThrottleReasonSwThermalSlowdown"),
+                                         bit("nvmlClocksThrottleReasonSwPowerCap")])
+                    time.sleep(0.01)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
