@@ -2,8 +2,11 @@
 // for the benchmark AIRs (TEST INFRASTRUCTURE; see wf_oracle.h). Follows prover/src/lib.rs:282-492,
 // prover/src/channel.rs, prover/src/constraints/**, prover/src/composer/mod.rs, fri/src/prover/mod.rs,
 // air/src/proof/*.rs (wire format) and verifier/src/{lib,channel,evaluator,composer}.rs +
-// fri/src/verifier/mod.rs. The reference holds no golden proof bytes: "byte-identical"
-// is therefore established as identical to this restatement + accepted by the restated verifier.
+// fri/src/verifier/mod.rs. PARITY UNPINNED at the proof level: the reference holds no golden proof bytes
+//  and cannot be built here (Rust, no cargo), so "byte-identical" is established as identical
+// to this restatement + accepted by the restated verifier; the building blocks (field, NTT, LDE, hashes,
+// Merkle, folding, coin) are pinned by the reference's own vectors in tests/test_oracle_kats.py, and this
+// file's own output is pinned by tests/golden/proof_digests.json.
 //
 // AIR family "FibSmall x k": k independent copies of examples/src/fibonacci/fib_small/air.rs:16-69
 // side by side (trace width 2k). k = 1 with start (1, 1) IS the reference's fib_small example

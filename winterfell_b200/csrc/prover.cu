@@ -1,14 +1,16 @@
-// prover.cu — the full proving pipeline on device behind one C-ABI call (wf_prove_fib), i.e. the body
-// of winterfell's Prover::generate_proof (prover/src/lib.rs:282-492) with every hot loop on the GPU:
-//   K1-K4  trace commitment          (ntt.cu, commit.cu)         DefaultTraceLde::new
-//   K5     constraint evaluation     (fib_constraints_kernel)     DefaultConstraintEvaluator::evaluate
-//   K6/K7  composition poly + commit (ntt.cu, commit.cu)         DefaultConstraintCommitment::new
+// prover.cu — the full proving pipeline on device behind one C-ABI call (wf_prove_fib / wf_prove_air /
+// wf_prove_air_aux), i.e. the body of winterfell's Prover::generate_proof (prover/src/lib.rs:282-492) with
+// every hot loop on the GPU, and the same steps as separate exports (wf_eval_constraints, ...):
+//   K1-K4  trace commitment          (ntt.cu, commit.cu)          DefaultTraceLde::new, set_aux_trace
+//   K5     constraint evaluation     (fib_ / generic_constraints) DefaultConstraintEvaluator::evaluate
+//   K6/K7  composition poly + commit (ntt.cu, commit.cu)          DefaultConstraintCommitment::new
 //   K8     out-of-domain frames      (ood_partial_kernel)         TracePolyTable/CompositionPoly::get_ood_frame
 //   K9/K10 DEEP composition          (deep_sum/div_kernel)        DeepCompositionPoly::{add_trace_polys, evaluate}
-//   K11    FRI commit phase          (fri.cu)                     FriProver::build_layers
-//   K13    proof-of-work grinding    (host, serial semantics: smallest nonce)
+//   K11    FRI commit phase          (fri.cu, device coin)        FriProver::build_layers
+//   K13    proof-of-work grinding    (grind_kernel)               ProverChannel::grind_query_seed, smallest nonce
 // The Fiat-Shamir transcript (ProverChannel, prover/src/channel.rs) and the proof wire format
-// (air/src/proof/*.rs) are host code here, bit-exact with the reference.
+// (air/src/proof/*.rs) are host code here, bit-exact with the reference; during the FRI commit phase the
+// coin is mirrored on the device and the host replays it afterwards.
 //
 // The DEEP composition is computed in EVALUATION form over the LDE domain,
 //   D(x) = (S(x) - S(z)) / (x - z) + (S(x) - S(zg)) / (x - zg),  S = sum_j cc_j T_j + sum_j cc'_j H_j,
@@ -16,9 +18,12 @@
 // (composer/mod.rs:67-210) and evaluates by LDE (:171): exact field arithmetic, identical values
 // (SURVEY.md A.4), but row-parallel and without the extra LDE.
 //
-// Constraint evaluation needs a device functor per AIR (Air::evaluate_transition is user Rust code,
-// air/src/air/mod.rs:210). Built in: the "FibSmall x k" family = k copies of
-// examples/src/fibonacci/fib_small/air.rs:16-69 side by side (k = 1 is the reference example).
+// Constraint evaluation needs the AIR on the device (Air::evaluate_transition is user Rust code,
+// air/src/air/mod.rs:210): generic AIRs arrive as a flat description (transition programs for both
+// segments, periodic columns, single / periodic / sequence assertions, exemptions; format in
+// include/winterfell_b200.h) and run on a bytecode evaluator; the "FibSmall x k" family = k copies of
+// examples/src/fibonacci/fib_small/air.rs:16-69 side by side (k = 1 is the reference example, k = 4 / 32
+// the 8- / 64-column configurations of BASELINE.json) has a specialised kernel.
 #include <algorithm>
 
 #include "internal.hpp"
