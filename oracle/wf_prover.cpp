@@ -1166,6 +1166,52 @@ void wfo_perm_rap_aux(const uint64_t* trace, size_t n, int d, const uint64_t* ra
         p = F.mul(F.mul(p, num), F.inv(den));
     }
 }
+// Boundary constraint groups of the main segment as the prover and verifier use them, flattened for the
+// known-answer test against air/src/air/tests.rs::get_boundary_constraints:
+//   [ngroups, {a, b, nentries, {column, cc (first word), x_offset, poly_len, poly...}*}*]; returns words written
+long wfo_boundary_groups(const uint64_t* desc, size_t desc_len, size_t n, const uint64_t* coeffs, uint64_t* out, size_t cap) {
+    Air air;
+    if (!parse_air(desc, desc_len, air)) return -2;
+    air.n = n;
+    memset(&air.o, 0, sizeof(air.o));
+    air.o.ext = 1;
+    std::vector<EE> cc;
+    for (size_t i = 0; i < air.asserts.size(); i++) cc.push_back(EE{{coeffs[i], 0, 0}});
+    std::vector<u64> w;
+    auto groups = boundary_groups(air, cc);
+    w.push_back(groups.size());
+    for (auto& G : groups) {
+        w.push_back(G.a); w.push_back(G.b); w.push_back(G.e.size());
+        for (auto& e : G.e) {
+            w.push_back(e.col); w.push_back(e.cc.v[0]); w.push_back(e.x_offset); w.push_back(e.poly.size());
+            for (auto& c : e.poly) w.push_back(c.v[0]);
+        }
+    }
+    if (w.size() > cap) return -1;
+    memcpy(out, w.data(), w.size() * 8);
+    return (long)w.size();
+}
+// Context::to_elements (air/src/proof/context.rs:119-136) for arbitrary parameters; returns the count
+size_t wfo_context_elements(size_t main_width, size_t aux_width, size_t aux_rands, size_t trace_length, size_t num_constraints,
+                            const uint32_t* opts, uint64_t* out) {
+    Air a;
+    a.w = main_width; a.aw = aux_width; a.nr = aux_rands; a.n = trace_length; a.o = make_opts(opts);
+    // num_constraints is carried by the (assertions + transition) count of the description
+    a.degrees.assign(num_constraints, {1, {}});
+    std::vector<u64> e = context_elements(a);
+    memcpy(out, e.data(), e.size() * 8);
+    return e.size();
+}
+// PartitionOptions::partition_size / num_partitions (air/src/options.rs:428-444)
+size_t wfo_partition_size(size_t num_partitions, size_t hash_rate, size_t ext_degree, size_t num_columns) {
+    if (num_partitions == 1) return num_columns;
+    size_t min_partition_size = hash_rate / ext_degree;
+    return std::max((num_columns + num_partitions - 1) / num_partitions, min_partition_size);
+}
+size_t wfo_num_partitions(size_t num_partitions, size_t hash_rate, size_t ext_degree, size_t num_columns) {
+    size_t ps = wfo_partition_size(num_partitions, hash_rate, ext_degree, num_columns);
+    return (num_columns + ps - 1) / ps;
+}
 // builds the FibSmall x k trace: pair j starts at (j+1, j+1); results[j] = last value of column 2j+1
 void wfo_build_fib_trace(size_t k, size_t n, uint64_t* trace, uint64_t* results) {
     for (size_t j = 0; j < k; j++) {

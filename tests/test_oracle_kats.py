@@ -340,3 +340,109 @@ def test_random_coin(oracle):
     assert lz == (head & -head).bit_length() - 1
     ints = c.draw_integers(20, 1024, 77)
     assert len(ints) == 20 and all(int(v) < 1024 for v in ints)
+
+
+def test_context_and_options_to_elements(oracle):
+    # air/src/proof/context.rs tests::context_to_elements, air/src/air/trace_info.rs tests::trace_info_to_elements,
+    # air/src/options.rs tests::proof_options_to_elements: exact packing of the channel seed prefix
+    import ctypes as C
+    L = oracle.lib()
+    L.wfo_context_elements.restype = C.c_size_t
+    out = np.zeros(16, dtype=np.uint64)
+    opts = oracle.make_opts(num_queries=30, blowup=8, grinding=20, ext=1, folding=8, rem_max_deg=127)
+    n = L.wfo_context_elements(C.c_size_t(20), C.c_size_t(9), C.c_size_t(12), C.c_size_t(4096), C.c_size_t(128),
+                               opts.ctypes.data_as(C.POINTER(C.c_uint32)), out.ctypes.data_as(C.POINTER(C.c_uint64)))
+    first = int.from_bytes(bytes([12, 9, 1, 20]), "little")            # [aux_rands, aux_width, num_aux_segments, main_width]
+    ext_fri = int.from_bytes(bytes([8, 127, 8, 1]), "little")          # [blowup, remainder degree, folding, FieldExtension::None = 1]
+    assert [int(x) for x in out[:n]] == [first, 4096, 1, 0xFFFFFFFF, 128, ext_fri, 20, 30]
+    # single-segment trace info: [num_aux_segments = 0, main_width, 0, 0]
+    n = L.wfo_context_elements(C.c_size_t(20), C.c_size_t(0), C.c_size_t(0), C.c_size_t(64), C.c_size_t(5),
+                               opts.ctypes.data_as(C.POINTER(C.c_uint32)), out.ctypes.data_as(C.POINTER(C.c_uint64)))
+    assert [int(x) for x in out[:2]] == [int.from_bytes(bytes([0, 20, 0, 0]), "little"), 64]
+
+
+def test_partition_sizes(oracle):
+    # air/src/options.rs tests::correct_partition_sizes
+    import ctypes as C
+    L = oracle.lib()
+    L.wfo_partition_size.restype = C.c_size_t
+    L.wfo_num_partitions.restype = C.c_size_t
+    ps = lambda np_, rate, d, cols: L.wfo_partition_size(C.c_size_t(np_), C.c_size_t(rate), C.c_size_t(d), C.c_size_t(cols))
+    npn = lambda np_, rate, d, cols: L.wfo_num_partitions(C.c_size_t(np_), C.c_size_t(rate), C.c_size_t(d), C.c_size_t(cols))
+    assert (ps(4, 8, 1, 7), npn(4, 8, 1, 7)) == (8, 1)
+    assert (ps(4, 8, 1, 70), npn(4, 8, 1, 70)) == (18, 4)
+    assert (ps(2, 8, 3, 7), npn(2, 8, 3, 7)) == (4, 2)
+    assert (ps(4, 8, 3, 7), npn(4, 8, 3, 7)) == (2, 4)
+    assert (ps(4, 8, 3, 3), npn(4, 8, 3, 3)) == (2, 2)
+
+
+def test_boundary_constraint_groups_kat(oracle):
+    # air/src/air/tests.rs::get_boundary_constraints (:64-230): eight assertions on a 16-step trace ->
+    # five groups ordered by (stride, first step), divisor x^a - g^(a * first_step), coefficients handed out
+    # in the sorted-assertion order, sequence polynomials = interpolants over the size-len subgroup with
+    # x offset g^(-first_step). Expected values are recomputed here with Python integers.
+    import ctypes as C
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import airs
+    P = airs.P
+    A = airs.AirBuilder(2)
+    A.constraint(A.sub(A.nxt(0), A.cur(0)), 1)
+    A.assert_single(0, 0, 3)
+    A.assert_single(0, 9, 5)
+    A.assert_single(1, 9, 9)
+    A.assert_sequence(0, 2, 4, [1, 2, 3, 4])
+    A.assert_sequence(1, 2, 4, [1, 2, 3, 4])
+    A.assert_sequence(1, 0, 8, [1, 2])
+    A.assert_sequence(0, 3, 8, [1, 2])
+    A.assert_periodic(1, 3, 8, 7)
+    desc = A.build()
+    n = 16
+    g = oracle.root_of_unity(4)
+    coeffs = np.array([1000 + i for i in range(8)], dtype=np.uint64)   # draw order = sorted-assertion order
+    out = np.zeros(256, dtype=np.uint64)
+    L = oracle.lib()
+    L.wfo_boundary_groups.restype = C.c_long
+    u64p = C.POINTER(C.c_uint64)
+    k = L.wfo_boundary_groups(desc.ctypes.data_as(u64p), C.c_size_t(desc.size), C.c_size_t(n), coeffs.ctypes.data_as(u64p),
+                              out.ctypes.data_as(u64p), C.c_size_t(out.size))
+    assert k > 0
+    w = [int(x) for x in out[:k]]
+    pos = 1
+    groups = []
+    for _ in range(w[0]):
+        a, b, ne = w[pos:pos + 3]
+        pos += 3
+        ents = []
+        for _ in range(ne):
+            col, cc, xo, pl = w[pos:pos + 4]
+            pos += 4
+            ents.append((col, cc, xo, w[pos:pos + pl]))
+            pos += pl
+        groups.append((a, b, ents))
+    assert pos == k
+
+    def interp(values):  # polynom::interpolate over the subgroup of size len(values) (tests.rs:305-311)
+        m = len(values)
+        h = pow(g, n // m, P)
+        xs = [pow(h, i, P) for i in range(m)]
+        coef = [0] * m
+        for i, (xi, yi) in enumerate(zip(xs, values)):  # Lagrange basis, expanded
+            num, den = [1], 1
+            for j, xj in enumerate(xs):
+                if j != i:
+                    num = [(a0 - xj * a1) % P for a0, a1 in zip([0] + num, num + [0])]
+                    den = den * (xi - xj) % P
+            sc = yi * pow(den, P - 2, P) % P
+            coef = [(c + sc * t) % P for c, t in zip(coef, num)]
+        return coef
+
+    ginv = pow(g, P - 2, P)
+    want = [
+        (1, pow(g, 0, P), [(0, 1000, 1, [3])]),                                                   # group 0: step 0
+        (1, pow(g, 9, P), [(0, 1001, 1, [5]), (1, 1002, 1, [9])]),                                # group 1: step 9
+        (4, pow(g, 8, P), [(0, 1003, pow(ginv, 2, P), interp([1, 2, 3, 4])), (1, 1004, pow(ginv, 2, P), interp([1, 2, 3, 4]))]),
+        (2, pow(g, 0, P), [(1, 1005, 1, interp([1, 2]))]),                                        # group 3: steps 0, 8
+        (2, pow(g, 6, P), [(0, 1006, pow(ginv, 3, P), interp([1, 2])), (1, 1007, 1, [7])]),       # group 4: steps 3, 11
+    ]
+    assert groups == want
