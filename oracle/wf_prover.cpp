@@ -402,6 +402,20 @@ static std::vector<u64> exemption_points(const Air& air) {
     return r;
 }
 
+// PeriodicValueTable::new (prover/src/constraints/evaluator/periodic_table.rs:24-76): column j evaluated
+// over the coset offset^(n/L) <w_(L*ceb)>; row i of the CE domain reads entry i mod (L * ce_blowup)
+static std::vector<std::vector<u64>> periodic_value_table(const Air& air) {
+    std::vector<std::vector<u64>> ptab;
+    for (auto& poly : air.periodic_polys()) {
+        size_t L = poly.size();
+        std::vector<u64> ev(L * air.ce_blowup());
+        auto tw = get_twiddles(L);
+        evaluate_poly_with_offset(poly.data(), L, 1, tw.data(), f_exp(GENERATOR, air.n / L), air.ce_blowup(), ev.data());
+        ptab.push_back(ev);
+    }
+    return ptab;
+}
+
 // ---- the proof -----------------------------------------------------------------------------------
 struct ProofParts {
     std::vector<u8> bytes;
@@ -492,17 +506,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[w][n]*/,
     const std::vector<u64> exempt = exemption_points(air);
     // periodic value table (evaluator/periodic_table.rs:24-76): column j evaluated over the coset
     // offset^(n/L) <w_(L*ceb)>, row i of the CE domain reads entry i mod (L*ceb)
-    std::vector<std::vector<u64>> ptab;
-    {
-        auto pp = air.periodic_polys();
-        for (auto& poly : pp) {
-            size_t L = poly.size();
-            std::vector<u64> ev(L * air.ce_blowup());
-            auto tw = get_twiddles(L);
-            evaluate_poly_with_offset(poly.data(), L, 1, tw.data(), f_exp(GENERATOR, n / L), air.ce_blowup(), ev.data());
-            ptab.push_back(ev);
-        }
-    }
+    std::vector<std::vector<u64>> ptab = periodic_value_table(air);
     std::vector<std::vector<std::vector<u64>>> gtab(groups.size()), agtab(aux_groups.size());
     for (size_t gi = 0; gi < groups.size(); gi++) for (auto& e : groups[gi].e) gtab[gi].push_back(sequence_table(e, 1, ce));
     for (size_t gi = 0; gi < aux_groups.size(); gi++) for (auto& e : aux_groups[gi].e) agtab[gi].push_back(sequence_table(e, d, ce));
@@ -1190,6 +1194,27 @@ long wfo_boundary_groups(const uint64_t* desc, size_t desc_len, size_t n, const 
     if (w.size() > cap) return -1;
     memcpy(out, w.data(), w.size() * 8);
     return (long)w.size();
+}
+// periodic values the evaluator reads at CE step `step` (PeriodicValueTable::get_row, periodic_table.rs:78-82)
+long wfo_periodic_row(const uint64_t* desc, size_t desc_len, size_t n, size_t step, uint64_t* out) {
+    Air air;
+    if (!parse_air(desc, desc_len, air)) return -2;
+    air.n = n;
+    auto t = periodic_value_table(air);
+    for (size_t j = 0; j < t.size(); j++) out[j] = t[j][step % t[j].size()];
+    return (long)t.size();
+}
+size_t wfo_ce_blowup(const uint64_t* desc, size_t desc_len) {
+    Air air;
+    if (!parse_air(desc, desc_len, air)) return 0;
+    return air.ce_blowup();
+}
+// ByteWriter::write_usize (utils/core/src/serde/byte_writer.rs:77-92): vint64; returns the encoded length
+size_t wfo_write_usize(uint64_t value, uint8_t out[9]) {
+    std::vector<u8> b;
+    write_vint64(b, value);
+    memcpy(out, b.data(), b.size());
+    return b.size();
 }
 // Context::to_elements (air/src/proof/context.rs:119-136) for arbitrary parameters; returns the count
 size_t wfo_context_elements(size_t main_width, size_t aux_width, size_t aux_rands, size_t trace_length, size_t num_constraints,

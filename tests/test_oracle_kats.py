@@ -446,3 +446,71 @@ def test_boundary_constraint_groups_kat(oracle):
         (2, pow(g, 6, P), [(0, 1006, pow(ginv, 3, P), interp([1, 2])), (1, 1007, 1, [7])]),       # group 4: steps 3, 11
     ]
     assert groups == want
+    # air/src/air/divisor.rs::constraint_divisor_equivalence: x^a - b vanishes exactly on the asserted steps
+    asserted = [{0}, {9}, {2, 6, 10, 14}, {0, 8}, {3, 11}]
+    for (a_, b_, _), steps in zip(groups, asserted):
+        zeros = {i for i in range(n) if (pow(pow(g, i, P), a_, P) - b_) % P == 0}
+        assert zeros == steps
+
+
+def test_usize_vint64_encoding(oracle):
+    # utils/core/src/tests.rs::write_serializable_usize: encoded lengths 1, 1, 2, 3, 9 and round trip
+    import ctypes as C
+    L = oracle.lib()
+    L.wfo_write_usize.restype = C.c_size_t
+    buf = (C.c_uint8 * 9)()
+    total = 0
+    for v, want_total in [(0, 1), (1, 2), (255, 4), (234567, 7), (2**64 - 1, 16)]:
+        ln = L.wfo_write_usize(C.c_uint64(v), buf)
+        total += ln
+        assert total == want_total
+        b = bytes(buf[:ln])
+        # reader (byte_reader.rs read_usize): length from the trailing zeros of the first byte
+        first = b[0]
+        length = 9 if first == 0 else ((first & -first).bit_length())
+        assert length == ln
+        got = int.from_bytes(b[1:9], "little") if length == 9 else int.from_bytes(b, "little") >> length
+        assert got == v
+
+
+def test_periodic_value_table(oracle):
+    # prover/src/constraints/evaluator/periodic_table.rs::periodic_value_table: trace length 32, columns [1, 2] and
+    # [3, 4, 5, 6]; row i of the CE domain = poly_j((7 w_ce^i)^(n / L_j)), polys = interpolants over the cycle
+    import ctypes as C
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import airs
+    P = airs.P
+    n = 32
+    A = airs.AirBuilder(1)
+    A.periodic = [[1, 2], [3, 4, 5, 6]]
+    A.constraint(A.mul(A.mul(A.cur(0), A.per(0)), A.per(1)), 1, [2, 4])   # any constraint that gives ce_blowup 4
+    A.assert_single(0, 0, 0)
+    desc = A.build()
+    L = oracle.lib()
+    u64p = C.POINTER(C.c_uint64)
+    L.wfo_ce_blowup.restype = C.c_size_t
+    ceb = L.wfo_ce_blowup(desc.ctypes.data_as(u64p), C.c_size_t(desc.size))
+    ce = n * ceb
+    g_ce = oracle.root_of_unity(ce.bit_length() - 1)
+
+    def interp_eval(values, x):  # Lagrange over the subgroup of size len(values)
+        m = len(values)
+        h = pow(oracle.root_of_unity(5), n // m, P)
+        xs = [pow(h, i, P) for i in range(m)]
+        acc = 0
+        for i, (xi, yi) in enumerate(zip(xs, values)):
+            num, den = 1, 1
+            for j, xj in enumerate(xs):
+                if j != i:
+                    num = num * (x - xj) % P
+                    den = den * (xi - xj) % P
+            acc = (acc + yi * num * pow(den, P - 2, P)) % P
+        return acc
+
+    row = np.zeros(2, dtype=np.uint64)
+    for i in range(ce):
+        assert L.wfo_periodic_row(desc.ctypes.data_as(u64p), C.c_size_t(desc.size), C.c_size_t(n), C.c_size_t(i), row.ctypes.data_as(u64p)) == 2
+        x = 7 * pow(g_ce, i, P) % P
+        assert int(row[0]) == interp_eval([1, 2], pow(x, n // 2, P))
+        assert int(row[1]) == interp_eval([3, 4, 5, 6], pow(x, n // 4, P))
