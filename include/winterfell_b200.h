@@ -265,6 +265,13 @@ uint64_t wf_host_mul(uint64_t a, uint64_t b);           /* canonical Goldilocks 
 uint64_t wf_host_mul_2exp(uint64_t x, uint32_t k);      /* x * 2^k mod p, k <= 96 (kernel twiddle path) */
 uint64_t wf_host_mont_to_canonical(uint64_t m);
 uint64_t wf_host_canonical_to_mont(uint64_t x);
+/* ByteWriter::write_usize (utils/core/src/serde/byte_writer.rs:77-92), the vint64 of the proof format;
+ * returns the number of bytes written (1..9) */
+size_t wf_host_write_usize(uint64_t value, uint8_t out[9]);
+/* DefaultRandomCoin::new(seed elements) [+ reseed(digest)] + draw x count (crypto/src/random/default.rs:95-170):
+ * the transcript arithmetic the proof path runs on the host. out[count][d]; 0 on success */
+int wf_host_coin_draw(int hash_id, const uint64_t* seed_elems, size_t n_seed, const uint8_t* reseed32, int d, size_t count,
+                      uint64_t* out);
 
 #ifdef __cplusplus
 }

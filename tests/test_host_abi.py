@@ -53,3 +53,37 @@ def test_host_hashers_match_oracle(oracle, h):
     assert wf.host_merge(h, a, b) == oracle.merge(h, a, b)
     for v in (0, 5, P - 1, P, P + 2, 2**64 - 1):
         assert wf.host_merge_with_int(h, a, v) == oracle.merge_with_int(h, a, v), v
+
+
+def test_host_usize_encoding_matches_reference_test():
+    # utils/core/src/tests.rs::write_serializable_usize, through the product's serializer
+    import ctypes as C
+    L = wf.lib()
+    buf = (C.c_uint8 * 9)()
+    total = 0
+    for v, want_total in [(0, 1), (1, 2), (255, 4), (234567, 7), (2**64 - 1, 16)]:
+        ln = L.wf_host_write_usize(v, buf)
+        total += ln
+        assert total == want_total
+        b = bytes(buf[:ln])
+        length = 9 if b[0] == 0 else ((b[0] & -b[0]).bit_length())
+        assert length == ln
+        assert (int.from_bytes(b[1:9], "little") if length == 9 else int.from_bytes(b, "little") >> length) == v
+
+
+@pytest.mark.parametrize("h", [0, 1])
+@pytest.mark.parametrize("d", [1, 2, 3])
+def test_host_coin_matches_oracle(oracle, h, d):
+    # the product's DefaultRandomCoin (host_transcript.hpp) against the oracle's (crypto/src/random/default.rs)
+    import ctypes as C
+    L = wf.lib()
+    seed = oracle.rand_elems((7,), 3 + d)
+    root = bytes(range(32))
+    out = np.zeros((20, d), dtype=np.uint64)
+    u64p, u8p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)
+    rb = (C.c_uint8 * 32)(*root)
+    assert L.wf_host_coin_draw(h, seed.ctypes.data_as(u64p), seed.size, rb, d, 20, out.ctypes.data_as(u64p)) == 0
+    coin = oracle.RandomCoin(h, seed)
+    coin.reseed(root)
+    for i in range(20):
+        assert (coin.draw(d) == out[i]).all()

@@ -91,6 +91,8 @@ _SIGS = [
     ("wf_host_mul_2exp", C.c_uint64, [C.c_uint64, C.c_uint32]),
     ("wf_host_mont_to_canonical", C.c_uint64, [C.c_uint64]),
     ("wf_host_canonical_to_mont", C.c_uint64, [C.c_uint64]),
+    ("wf_host_write_usize", C.c_size_t, [C.c_uint64, u8p]),
+    ("wf_host_coin_draw", C.c_int, [C.c_int, u64p, C.c_size_t, u8p, C.c_int, C.c_size_t, u64p]),
 ]
 
 

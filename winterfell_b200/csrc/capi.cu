@@ -1231,5 +1231,21 @@ uint64_t wf_host_mul_2exp(uint64_t x, uint32_t k) {
 }
 uint64_t wf_host_mont_to_canonical(uint64_t m) { return gl_from_mont(m); }
 uint64_t wf_host_canonical_to_mont(uint64_t x) { return gl_to_mont(x); }
+size_t wf_host_write_usize(uint64_t value, uint8_t out[9]) {  // the serializer's vint64 (byte_writer.rs:77-92)
+    ByteVec b;
+    b.usize(value);
+    memcpy(out, b.v.data(), b.v.size());
+    return b.v.size();
+}
+// DefaultRandomCoin on the host (crypto/src/random/default.rs): seed from elements, optional reseed with a
+// digest, then draw `count` elements of extension degree d -> out[count][d]. Returns 0, or -1 if a draw fails.
+int wf_host_coin_draw(int hash_id, const uint64_t* seed_elems, size_t n_seed, const uint8_t* reseed32, int d, size_t count,
+                      uint64_t* out) {
+    if (d < 1 || d > 3 || !out) return -1;
+    PublicCoin coin(hash_id, seed_elems, n_seed);
+    if (reseed32) { Digest dg; memcpy(dg.b, reseed32, 32); coin.reseed(dg); }
+    for (size_t i = 0; i < count; i++) if (!coin.draw(d, out + i * d)) return -1;
+    return 0;
+}
 
 }  // extern "C"
