@@ -87,3 +87,50 @@ def test_host_coin_matches_oracle(oracle, h, d):
     coin.reseed(root)
     for i in range(20):
         assert (coin.draw(d) == out[i]).all()
+
+
+@pytest.mark.parametrize("h,d", [(0, 1), (1, 3), (0, 2)])
+def test_cpp_mirror_host_logic(oracle, tmp_path, h, d):
+    # include/winterfell_b200.hpp builds with plain g++ on a machine without a GPU, and its transcript pieces
+    # (AIR description parsing, Context::to_elements, vint64 writer, coin, coefficient batching) agree with the oracle
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import airs
+    exe = tmp_path / "host_logic_main"
+    lib_dir = os.path.dirname(wf.LIB_PATH)
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "shim", "host_logic_main.cpp"), "-o", str(exe), "-L", lib_dir,
+                           "-lwinterfell_b200", f"-Wl,-rpath,{lib_dir}", "-Wl,-rpath-link,/usr/local/cuda/lib64"])
+    desc, trace, _ = airs.perm_rap(64)
+    f = tmp_path / "desc.bin"
+    desc.tofile(f)
+    out = subprocess.run([str(exe), str(f), str(h), str(d)], capture_output=True, text=True, check=True).stdout.splitlines()
+    rows = {ln.split()[0]: [int(x) for x in ln.split()[1:]] for ln in out}
+    # perm_rap: 3 main + 3 aux columns, 2 random elements, 2 + 3 transition constraints, 3 + 4 assertions, degree 2 -> ce blowup 2
+    assert rows["air"][:6] == [3, airs.PERM_RAP_AUX_WIDTH, 2, 5, 7, 2]
+    import ctypes as C
+    L = oracle.lib()
+    L.wfo_context_elements.restype = C.c_size_t
+    want = np.zeros(16, dtype=np.uint64)
+    opts = oracle.make_opts(num_queries=30, blowup=8, grinding=20, ext=d, folding=8, rem_max_deg=127, hash_id=h)
+    n = L.wfo_context_elements(C.c_size_t(3), C.c_size_t(airs.PERM_RAP_AUX_WIDTH), C.c_size_t(2), C.c_size_t(64), C.c_size_t(12),
+                               opts.ctypes.data_as(C.POINTER(C.c_uint32)), want.ctypes.data_as(C.POINTER(C.c_uint64)))
+    pub = [int(trace[1, 63])]
+    assert rows["ctx"] == [int(x) for x in want[:n]] + pub
+    enc = b""
+    buf = (C.c_uint8 * 9)()
+    L.wfo_write_usize.restype = C.c_size_t
+    for v in (0, 1, 255, 234567, 2**64 - 1):
+        enc += bytes(buf[:L.wfo_write_usize(C.c_uint64(v), buf)])
+    assert bytes(rows["usize"]) == enc
+    coin = oracle.RandomCoin(h, np.array(rows["ctx"], dtype=np.uint64))
+    coin.reseed(bytes(range(32)))
+    lin = [int(x) for _ in range(5) for x in coin.draw(d)]
+    assert rows["draw"] == lin
+    alpha = coin.draw(d)
+    pw, x = [], np.array([1] + [0] * (d - 1), dtype=np.uint64)
+    for _ in range(4):
+        pw.append(x)
+        x = oracle.ext_mul(x, alpha)
+    assert rows["alg"] == [int(v) for e in reversed(pw) for v in e]   # Horner: reversed powers (coefficients.rs:84-94)
