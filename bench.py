@@ -68,7 +68,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([str(sm), str(mx), bit("nvmlClocksThrottleReasonHwSlowdown"),
                                          bit("nvmlClocksThrottleReasonHwThermalSlowdown"), bit("nvmlClocksThrottleReasonSwThermalSlowdown"),
                                          bit("nvmlClocksThrottleReasonSwPowerCap")])
-                    time.sleep(0.01)
+                    time.sleep(0.2)
                     continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -227,8 +227,10 @@ def main():
     def step_resident():
         return ctx.prove_fib_dev(dev.data_ptr(), pairs, log_n, results, opts, out_buf)
 
+    e2e_buf = np.zeros(1 << 23, dtype=np.uint8)  # proof bytes land here (allocated once, like a caller's buffer)
+
     def step_e2e():
-        return ctx.prove_fib(host_np, results, opts)     # H2D of the trace and D2H of the proof inside
+        return ctx.prove_fib(host_np, results, opts, out_buf=e2e_buf)     # H2D of the trace and D2H of the proof inside
 
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
@@ -236,6 +238,9 @@ def main():
         p_e2e = step_e2e()
         assert p_res == p_e2e, "resident and e2e arms produced different proofs"
 
+        import gc
+        gc.collect()
+        gc.disable()  # no collector pauses inside the timed regions (a single 30 ms host stall moves a 30-step mean by 1 ms)
         sampler = ClockSampler(local_rank)
         sampler.start()
         barrier()
@@ -250,6 +255,8 @@ def main():
             b.record(stream)
             b.synchronize()
             total_ms += a.elapsed_time(b)
+            if os.environ.get("WF_BENCH_TRACE"):
+                print(f"resident step {a.elapsed_time(b):.3f} ms", file=sys.stderr)
         barrier()
         wall_ms = (time.perf_counter() - t_wall0) * 1e3
         launches = int(ctx.launches - l0)
@@ -265,10 +272,13 @@ def main():
             b.record(stream)
             b.synchronize()
             e2e_ms += a.elapsed_time(b)
+            if os.environ.get("WF_BENCH_TRACE"):
+                print(f"e2e step {a.elapsed_time(b):.3f} ms", file=sys.stderr)
         barrier()
         e2e_step = e2e_ms / args.steps
         sampler.stop_flag = True
         sampler.join(timeout=2)
+        gc.enable()
 
         # stage breakdown: one extra proof with the library's stage events on
         flush.zero_()

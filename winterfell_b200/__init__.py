@@ -255,15 +255,16 @@ class Context:
                                           C.byref(h)))
         return Mat(self, h)
 
-    def prove_fib(self, trace, results, opts, mont=False):
-        """trace: [2k, n] uint64; results: [k]; opts: uint32[9] (see wf_prove_fib). Returns proof bytes."""
+    def prove_fib(self, trace, results, opts, mont=False, out_buf=None):
+        """trace: [2k, n] uint64; results: [k]; opts: uint32[9] (see wf_prove_fib). Returns proof bytes.
+        out_buf: optional preallocated uint8 array for the proof (a caller proving in a loop reuses one)."""
         a = np.ascontiguousarray(trace, dtype=np.uint64)
         c, n = a.shape
         ptrs = (u64p * c)(*[a[j].ctypes.data_as(u64p) for j in range(c)])
         r_, rp = _u64(results)
         o_ = np.ascontiguousarray(opts, dtype=np.uint32)
-        cap = 1 << 23
-        buf = np.zeros(cap, dtype=np.uint8)
+        buf = out_buf if out_buf is not None else np.zeros(1 << 23, dtype=np.uint8)
+        cap = buf.size
         ln = C.c_size_t(cap)
         self.check(self.L.wf_prove_fib(self.h, ptrs, int(mont), c // 2, int(n).bit_length() - 1, rp,
                                        o_.ctypes.data_as(C.POINTER(C.c_uint32)), buf.ctypes.data_as(u8p), C.byref(ln)))

@@ -152,8 +152,9 @@ cudaError_t fri_fold_layer(const u64* evals, size_t len, int d, int ld, int nf, 
 // (:156-170: counter += 1, merge_with_int(seed, counter), rejection of words >= p). One thread; it lets the
 // whole layer loop be enqueued without a host round trip per layer. The host replays the same steps on
 // its own coin afterwards and checks that it drew the same alphas.
-__device__ void coin_merge(int hash_id, const u64 a[4], const u64 b[4], u64 out[4]) {
-    if (hash_id == WF_HASH_BLAKE3_256) {
+template <int HASH>
+__device__ __forceinline__ void coin_merge(const u64 a[4], const u64 b[4], u64 out[4]) {
+    if (HASH == WF_HASH_BLAKE3_256) {
         u32 m[16], cv[8];
 #pragma unroll
         for (int i = 0; i < 4; i++) { m[2 * i] = (u32)a[i]; m[2 * i + 1] = (u32)(a[i] >> 32); m[8 + 2 * i] = (u32)b[i]; m[9 + 2 * i] = (u32)(b[i] >> 32); }
@@ -168,8 +169,9 @@ __device__ void coin_merge(int hash_id, const u64 a[4], const u64 b[4], u64 out[
         rp64_merge(in, out);
     }
 }
-__device__ void coin_merge_with_int(int hash_id, const u64 seed[4], u64 value, u64 out[4]) {
-    if (hash_id == WF_HASH_BLAKE3_256) {  // blake/mod.rs:41-46
+template <int HASH>
+__device__ __forceinline__ void coin_merge_with_int(const u64 seed[4], u64 value, u64 out[4]) {
+    if (HASH == WF_HASH_BLAKE3_256) {  // blake/mod.rs:41-46
         u32 m[16], cv[8];
 #pragma unroll
         for (int i = 0; i < 4; i++) { m[2 * i] = (u32)seed[i]; m[2 * i + 1] = (u32)(seed[i] >> 32); }
@@ -194,16 +196,17 @@ __device__ void coin_merge_with_int(int hash_id, const u64 seed[4], u64 value, u
     }
 }
 // state: seed[4]; log: per layer root[4] then alpha[3]
-__global__ void fri_coin_kernel(int hash_id, u64* state, const u64* root, int d, u64* alpha_out, u64* log_entry) {
+template <int HASH>  // one instantiation per hasher: the Blake3 coin does not carry the Rp64 permutation's registers
+__global__ void fri_coin_kernel(u64* state, const u64* root, int d, u64* alpha_out, u64* log_entry) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     u64 seed[4], r[4], v[4];
     for (int i = 0; i < 4; i++) { seed[i] = state[i]; r[i] = root[i]; }
-    coin_merge(hash_id, seed, r, seed);  // reseed
+    coin_merge<HASH>(seed, r, seed);  // reseed
     u64 counter = 0;
     bool ok = false;
     for (int t = 0; t < 1000 && !ok; t++) {
         counter += 1;
-        coin_merge_with_int(hash_id, seed, counter, v);
+        coin_merge_with_int<HASH>(seed, counter, v);
         ok = true;
         for (int k = 0; k < d; k++) ok = ok && v[k] < GL_P;
     }
@@ -213,6 +216,7 @@ __global__ void fri_coin_kernel(int hash_id, u64* state, const u64* root, int d,
     log_entry[7] = ok ? 1 : 0;
 }
 cudaError_t fri_coin_step(int hash_id, u64* state, const u64* root, int d, u64* alpha_out, u64* log_entry, cudaStream_t st) {
-    fri_coin_kernel<<<1, 32, 0, st>>>(hash_id, state, root, d, alpha_out, log_entry);
+    if (hash_id == WF_HASH_BLAKE3_256) fri_coin_kernel<WF_HASH_BLAKE3_256><<<1, 32, 0, st>>>(state, root, d, alpha_out, log_entry);
+    else fri_coin_kernel<WF_HASH_RP64_256><<<1, 32, 0, st>>>(state, root, d, alpha_out, log_entry);
     return cudaGetLastError();
 }
