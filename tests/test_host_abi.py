@@ -134,3 +134,14 @@ def test_cpp_mirror_host_logic(oracle, tmp_path, h, d):
         pw.append(x)
         x = oracle.ext_mul(x, alpha)
     assert rows["alg"] == [int(v) for e in reversed(pw) for v in e]   # Horner: reversed powers (coefficients.rs:84-94)
+
+
+def test_header_is_plain_c(tmp_path):
+    # the boundary is a C ABI: include/winterfell_b200.h must compile as C99 (no C++-isms, no CUDA or torch types)
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "winterfell_b200.h"\nint main(void) { wf_ctx* c = 0; (void)c; return wf_version() == 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-c", str(src), "-o", str(tmp_path / "t.o")])
+    text = open(os.path.join(ROOT, "include", "winterfell_b200.h")).read()
+    assert "torch" not in text and "cuda_runtime" not in text and "at::" not in text
