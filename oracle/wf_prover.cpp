@@ -1195,6 +1195,20 @@ long wfo_boundary_groups(const uint64_t* desc, size_t desc_len, size_t n, const 
     memcpy(out, w.data(), w.size() * 8);
     return (long)w.size();
 }
+// MerkleTree::verify_batch (crypto/src/merkle/mod.rs:300-330) = BatchMerkleProof::get_root + comparison:
+// serialized batch proof, the opened leaves (k x 32 bytes, in the order of `indexes`). 0 = accepted.
+int wfo_merkle_verify_batch(int hash_id, const uint8_t root[32], const uint64_t* indexes, size_t k, const uint8_t* leaves,
+                            const uint8_t* proof, size_t proof_len) {
+    Reader r{proof, proof_len};
+    BatchProof bp;
+    if (!read_batch_proof(r, bp) || r.pos != proof_len) return 1;
+    std::vector<u64> idx(indexes, indexes + k);
+    std::vector<std::array<u8, 32>> lv(k);
+    for (size_t i = 0; i < k; i++) memcpy(lv[i].data(), leaves + 32 * i, 32);
+    u8 got[32];
+    if (!batch_root(hash_id, bp, idx, lv, got)) return 2;
+    return memcmp(got, root, 32) ? 3 : 0;
+}
 // periodic values the evaluator reads at CE step `step` (PeriodicValueTable::get_row, periodic_table.rs:78-82)
 long wfo_periodic_row(const uint64_t* desc, size_t desc_len, size_t n, size_t step, uint64_t* out) {
     Air air;

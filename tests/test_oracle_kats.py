@@ -268,6 +268,39 @@ def test_merkle_prove_batch_fixtures(oracle):
         oracle.merkle_prove_batch(l8, n8, [1, 1])
 
 
+def test_merkle_verify_batch_fixtures(oracle):
+    # merkle/tests.rs:189-213 verify_batch: the verifier-side root recomputation (BatchMerkleProof::get_root,
+    # proofs.rs:90-205) the oracle verifier uses to accept trace / constraint / FRI openings
+    import ctypes as C
+    l8 = np.array(LEAVES8, dtype=np.uint8)
+    n8 = oracle.merkle_nodes(oracle.BLAKE3, l8)
+    root = n8[1].tobytes()
+    u8p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)
+
+    def verify(indexes, lv, pr):
+        idx = np.array(indexes, dtype=np.uint64)
+        lvb = np.ascontiguousarray(lv, dtype=np.uint8)
+        prb = np.frombuffer(pr, dtype=np.uint8)
+        rb = np.frombuffer(root, dtype=np.uint8)
+        return oracle.lib().wfo_merkle_verify_batch(C.c_int(oracle.BLAKE3), rb.ctypes.data_as(u8p), idx.ctypes.data_as(u64p),
+                                                    C.c_size_t(idx.size), lvb.ctypes.data_as(u8p), prb.ctypes.data_as(u8p),
+                                                    C.c_size_t(prb.size))
+
+    lv, pr = oracle.merkle_prove_batch(l8, n8, [1])
+    assert verify([1], lv, pr) == 0 and verify([2], lv, pr) != 0
+    lv, pr = oracle.merkle_prove_batch(l8, n8, [1, 2])
+    assert verify([1, 2], lv, pr) == 0
+    assert verify([1], lv[:1], pr) != 0 and verify([1, 3], lv, pr) != 0 and verify([1, 2, 3], np.concatenate([lv, lv[:1]]), pr) != 0
+    for idx in ([1, 6], [1, 3, 6], list(range(8))):
+        lv, pr = oracle.merkle_prove_batch(l8, n8, idx)
+        assert verify(idx, lv, pr) == 0
+    # a flipped leaf is rejected
+    lv, pr = oracle.merkle_prove_batch(l8, n8, [1, 3, 6])
+    bad = np.array(lv, dtype=np.uint8).copy()
+    bad[1, 0] ^= 1
+    assert verify([1, 3, 6], bad, pr) != 0
+
+
 # ---- FRI ----
 def test_transpose_and_fold_positions(oracle):
     # utils/core/src/lib.rs:158-165; fri/src/folding/mod.rs:129-136
