@@ -299,5 +299,5 @@ def sequence_mix(n, stride=4):
     A.assert_single(1, n - 1, int(tr[1, n - 1]))
     A.assert_sequence(0, 1, stride, [int(v) for v in tr[0, 1::stride]])   # first_step != 0: x offset g^-1
     A.assert_periodic(2, 1, stride, 7)                                    # same divisor as the sequence
-    A.assert_sequence(1, 0, n // 2, [int(tr[1, 0]), int(tr[1, n // 2])])  # two values, first_step 0
+    A.assert_sequence(2, 0, n // 2, [int(tr[2, 0]), int(tr[2, n // 2])])  # two values, first_step 0 (no cell asserted twice)
     return A.build(), tr

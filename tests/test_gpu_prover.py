@@ -209,3 +209,29 @@ def test_device_reproduces_golden_proof_digests(ctx, oracle, idx):
         desc, trace = getattr(airs, rec["air"])(rec["n"])
         proof = ctx.prove_air(desc, trace, opts)
     assert len(proof) == rec["bytes"] and hashlib.sha256(proof).hexdigest() == rec["sha256"]
+
+
+def test_overlapping_assertions_are_refused(ctx, oracle):
+    # the reference panics in prepare_assertions when two assertions cover the same cell
+    # (air/src/air/boundary/mod.rs:205-210, Assertion::overlaps_with assertions/mod.rs:175-208)
+    n = 64
+    desc, trace = airs.mulfib2(n)
+    A = airs.AirBuilder(2)
+    A.pub = [int(trace[0, n - 1])]
+    A.constraint(A.sub(A.nxt(0), A.mul(A.cur(0), A.cur(1))), 2)
+    A.constraint(A.sub(A.nxt(1), A.mul(A.cur(1), A.nxt(0))), 2)
+    A.assert_single(0, 0, 1)
+    A.assert_single(1, 0, 2)
+    A.assert_sequence(1, 0, n // 2, [2, int(trace[1, n // 2])])   # step 0 of column 1 is asserted twice
+    opts = oracle.make_opts(num_queries=8, blowup=8)
+    with pytest.raises(wf.WfError, match="overlaps"):
+        ctx.prove_air(A.build(), trace, opts)
+    B = airs.AirBuilder(2)
+    B.pub = A.pub
+    B.constraint(B.sub(B.nxt(0), B.mul(B.cur(0), B.cur(1))), 2)
+    B.constraint(B.sub(B.nxt(1), B.mul(B.cur(1), B.nxt(0))), 2)
+    B.assert_single(0, 0, 1)
+    B.assert_periodic(1, 0, 4, 2)
+    B.assert_single(1, 8, 5)                                         # step 8 = 0 + 2 * 4 is covered by the periodic one
+    with pytest.raises(wf.WfError, match="overlaps"):
+        ctx.prove_air(B.build(), trace, opts)

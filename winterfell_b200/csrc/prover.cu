@@ -812,6 +812,21 @@ static int validate_assertions(wf_ctx* ctx, const std::vector<AirAssertion>& as,
         if (nv > 1) ok = ok && a.stride != 0 && !(nv & (nv - 1)) && nv * a.stride == n;   // sequence: one value per asserted step
         if (!ok) return wf_fail(ctx, WF_ERR_INVALID, "invalid %s", what);
     }
+    // no two assertions may cover the same cell (Assertion::overlaps_with, assertions/mod.rs:175-208;
+    // prepare_assertions panics on it, boundary/mod.rs:205-210)
+    auto overlaps = [](const AirAssertion& s, const AirAssertion& o) {
+        if (s.column != o.column) return false;
+        if (s.first_step == o.first_step) return true;
+        if (s.stride == o.stride) return false;
+        const AirAssertion& lo = s.first_step < o.first_step ? s : o;
+        const AirAssertion& hi = s.first_step < o.first_step ? o : s;
+        if (lo.stride == 0) return false;  // the earlier one is a single assertion
+        if (hi.stride == 0 || lo.stride < hi.stride) return (hi.first_step - lo.first_step) % lo.stride == 0;
+        return false;
+    };
+    for (size_t i = 0; i < as.size(); i++)
+        for (size_t j = i + 1; j < as.size(); j++)
+            if (overlaps(as[i], as[j])) return wf_fail(ctx, WF_ERR_INVALID, "%s %zu overlaps with %zu", what, j, i);
     return WF_OK;
 }
 
