@@ -1,4 +1,4 @@
-"""world_size-2 `gloo` test of the multi-GPU host logic (winterfell_b200/dist.py) on CPU: the sharding
+"""world_size-2 and -4 `gloo` tests of the multi-GPU host logic (winterfell_b200/dist.py) on CPU: the sharding
 plan, the all-to-all row re-sharding, the subtree-root all-gather and the top-of-tree merge. Local
 compute is done by a CPU test backend built on the oracle; the result must equal the single-device
 commitment of the whole trace."""
@@ -57,21 +57,21 @@ def _worker(rank, world, port, hash_id, log_n, cols, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("hash_id,log_n,cols", [(0, 6, 4), (1, 5, 2)])
-def test_sharded_trace_commit_world2(hash_id, log_n, cols):
+@pytest.mark.parametrize("hash_id,log_n,cols,world", [(0, 6, 4, 2), (1, 5, 2, 2), (0, 5, 8, 4)])
+def test_sharded_trace_commit_gloo(hash_id, log_n, cols, world):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, hash_id, log_n, cols, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, hash_id, log_n, cols, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=180) for _ in procs)
     for p in procs:
         p.join(timeout=60)
-    assert res == [(0, True), (1, True)]
+    assert res == [(r, True) for r in range(world)]
 
 
 def test_column_ranges_and_top_levels(oracle):
