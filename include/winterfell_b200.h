@@ -273,6 +273,10 @@ size_t wf_host_write_usize(uint64_t value, uint8_t out[9]);
 int wf_host_coin_draw(int hash_id, const uint64_t* seed_elems, size_t n_seed, const uint8_t* reseed32, int d, size_t count,
                       uint64_t* out);
 
+/* FibSmallProver::build_trace (examples/src/fibonacci/fib_small/prover.rs:37-53) for the built-in "FibSmall x k"
+ * family: cols = [2k][n] canonical words, pair j starting at (j+1, j+1); results[j] = its public input. Host code. */
+int wf_host_build_fib_trace(uint32_t k, size_t n, uint64_t* cols, uint64_t* results);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,6 +115,18 @@ def get_inv_twiddles(n):
     return o
 
 
+def fft_in_place(v, d=1, inverse=False, split_radix_threads=0):
+    """fft_in_place (fft_inputs.rs:215-252; permuted output) or, with split_radix_threads > 0, the `concurrent`
+    split_radix_fft (fft/concurrent.rs:131-171) on that many threads."""
+    a, ap = _u64(np.array(v, dtype=np.uint64).copy())
+    n = a.size // d
+    if split_radix_threads:
+        lib().wfo_split_radix_fft(ap, C.c_size_t(n), C.c_int(d), C.c_int(int(inverse)), C.c_int(split_radix_threads))
+    else:
+        lib().wfo_fft_in_place(ap, C.c_size_t(n), C.c_int(d), C.c_int(int(inverse)))
+    return a
+
+
 def evaluate_poly(p, d=1):
     v = np.array(p, dtype=np.uint64, copy=True).reshape(-1)
     lib().wfo_evaluate_poly(v.ctypes.data_as(u64p), C.c_size_t(v.size // d), C.c_int(d))

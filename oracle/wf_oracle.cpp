@@ -126,9 +126,12 @@ static void e_inv(int d, const u64* a, u64* o) {
 static inline size_t permute_index(size_t size, size_t index) {  // fft/mod.rs:570-578
     u32 bits = (u32)__builtin_ctzll(size);
     if (bits == 0) return 0;
-    u64 r = 0;
-    for (u32 i = 0; i < bits; i++) r |= ((index >> i) & 1ULL) << (bits - 1 - i);
-    return (size_t)r;
+    u64 r = index;  // index.reverse_bits() >> (usize::BITS - bits)
+    r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);
+    r = ((r >> 2) & 0x3333333333333333ULL) | ((r & 0x3333333333333333ULL) << 2);
+    r = ((r >> 4) & 0x0f0f0f0f0f0f0f0fULL) | ((r & 0x0f0f0f0f0f0f0f0fULL) << 4);
+    r = __builtin_bswap64(r);
+    return (size_t)(r >> (64 - bits));
 }
 static std::vector<u64> power_series(u64 b, size_t n) {  // math/src/utils/mod.rs:36
     std::vector<u64> r(n);
@@ -136,7 +139,17 @@ static std::vector<u64> power_series(u64 b, size_t n) {  // math/src/utils/mod.r
     for (size_t i = 0; i < n; i++) { r[i] = x; x = f_mul(x, b); }
     return r;
 }
-static void permute_words(u64* v, size_t n, int d) {  // fft_inputs.rs permute (swap i <-> bitrev(i))
+// threads available to one of `outer_tasks` concurrently running transforms (rayon's work stealing lets the
+// reference's nested par_iter use every core; OpenMP needs the split stated: outer x inner <= threads)
+static int inner_threads(size_t outer_tasks) {
+    if (omp_in_parallel()) return 1;
+    size_t t = (size_t)omp_get_max_threads();
+    return (int)std::max<size_t>(1, t / std::max<size_t>(outer_tasks, 1));
+}
+// fft_inputs.rs permute (swap i <-> bitrev(i)); with nt > 1 the batches of concurrent.rs:103-124 (disjoint
+// index ranges; a swap happens only from its smaller index, so no two threads touch the same pair)
+static void permute_words(u64* v, size_t n, int d, int nt = 1) {
+#pragma omp parallel for schedule(static) num_threads(nt) if (nt > 1 && n >= 1024)
     for (size_t i = 0; i < n; i++) {
         size_t j = permute_index(n, i);
         if (j > i) for (int k = 0; k < d; k++) std::swap(v[i * d + k], v[j * d + k]);
@@ -202,25 +215,75 @@ static void ref_fft_in_place(u64* v, size_t n, int d, const u64* tw) {
     ref_fft_rec(v, n, d, tw, 1, 1, 0);  // fft_inputs.rs:103-105: fft_in_place(self, twiddles, 1, 1, 0)
 }
 
-static void evaluate_poly(u64* p, size_t n, int d, const u64* tw) {  // fft/serial.rs:18-25
-    ref_fft_in_place(p, n, d, tw);
-    permute_words(p, n, d);
+// fft/concurrent.rs:131-171 split_radix_fft: the `concurrent` build's transform for >= 1024 points — an
+// inner x outer decomposition whose row transforms run in parallel (par_chunks_mut), joined by two serial
+// square transpositions (:176-218). Same permuted output as fft_in_place. `tw` is the bit-reversed twiddle
+// table of the full size (its prefixes serve the row transforms), nt the threads this transform may use.
+static void transpose_square_stretch(u64* m, size_t size, size_t stretch, int d) {  // concurrent.rs:176-218
+    const size_t it = stretch * (size_t)d;  // words per transposed item
+    for (size_t row = 0; row < size; row++)
+        for (size_t col = row + 1; col < size; col++) {
+            u64 *a = m + (row * size + col) * it, *b = m + (col * size + row) * it;
+            for (size_t k = 0; k < it; k++) std::swap(a[k], b[k]);
+        }
+}
+static void split_radix_fft(u64* v, size_t n, int d, const u64* tw, int nt) {
+    const u32 log_n = (u32)__builtin_ctzll(n);
+    const u64 g = tw[(n / 2) / 2];                 // "generator of the domain should be in the middle of twiddles"
+    const size_t inner_len = (size_t)1 << (log_n / 2), outer_len = n / inner_len, stretch = outer_len / inner_len;
+    transpose_square_stretch(v, inner_len, stretch, d);
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (size_t r = 0; r < inner_len; r++)          // row.fft_in_place_raw(twiddles, stretch, stretch, 0)
+        ref_fft_rec(v + r * outer_len * d, outer_len, d, tw, stretch, stretch, 0);
+    transpose_square_stretch(v, inner_len, stretch, d);
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (size_t i = 0; i < inner_len; i++) {
+        u64* row = v + i * outer_len * d;
+        if (i > 0) {
+            u64 inner_twiddle = f_exp(g, permute_index(inner_len, i)), outer_twiddle = inner_twiddle;
+            for (size_t e = 1; e < outer_len; e++) {
+                for (int k = 0; k < d; k++) row[e * d + k] = f_mul(row[e * d + k], outer_twiddle);
+                outer_twiddle = f_mul(outer_twiddle, inner_twiddle);
+            }
+        }
+        ref_fft_rec(row, outer_len, d, tw, 1, 1, 0);  // row.fft_in_place(twiddles)
+    }
+}
+// fft/mod.rs:95-110 (and :180, :275, :362): the concurrent implementation is chosen for >= MIN_CONCURRENT_SIZE
+// (1024) points when the `concurrent` feature is on — here: when this transform has more than one thread
+static void fft_in_place_auto(u64* v, size_t n, int d, const u64* tw, int nt) {
+    if (nt > 1 && n >= 1024) split_radix_fft(v, n, d, tw, nt);
+    else ref_fft_in_place(v, n, d, tw);
+}
+
+static void evaluate_poly(u64* p, size_t n, int d, const u64* tw) {  // fft/serial.rs:18-25, concurrent.rs:17-20
+    const int nt = inner_threads(1);
+    fft_in_place_auto(p, n, d, tw, nt);
+    permute_words(p, n, d, nt);
 }
 static void interpolate_poly(u64* v, size_t n, int d, const u64* inv_tw) {  // fft/serial.rs:66-76
     u64 inv_len = f_inv((u64)n % P);
-    ref_fft_in_place(v, n, d, inv_tw);
+    const int nt = inner_threads(1);                 // concurrent.rs:59-70
+    fft_in_place_auto(v, n, d, inv_tw, nt);
+#pragma omp parallel for schedule(static) num_threads(nt) if (nt > 1 && n >= 1024)
     for (size_t i = 0; i < n * d; i++) v[i] = f_mul(v[i], inv_len);  // shift_by
-    permute_words(v, n, d);
+    permute_words(v, n, d, nt);
 }
 static void interpolate_poly_with_offset(u64* v, size_t n, int d, const u64* inv_tw, u64 domain_offset) {
-    // fft/serial.rs:84-101
-    ref_fft_in_place(v, n, d, inv_tw);
-    permute_words(v, n, d);
-    u64 inc = f_inv(domain_offset);
-    u64 off = f_inv((u64)n % P);
-    for (size_t i = 0; i < n; i++) {  // shift_by_series(offset, increment)
-        for (int k = 0; k < d; k++) v[i * d + k] = f_mul(v[i * d + k], off);
-        off = f_mul(off, inc);
+    // fft/serial.rs:84-101; concurrent.rs:77-98 (batches, each starting from its own power of the offset)
+    const int nt = inner_threads(1);
+    fft_in_place_auto(v, n, d, inv_tw, nt);
+    permute_words(v, n, d, nt);
+    const u64 inc = f_inv(domain_offset), inv_len = f_inv((u64)n % P);
+    const size_t nb = (nt > 1 && n >= 1024) ? (size_t)nt : 1, bs = (n + nb - 1) / nb;
+#pragma omp parallel for schedule(static) num_threads(nt) if (nb > 1)
+    for (size_t bi = 0; bi < nb; bi++) {
+        const size_t lo = bi * bs, hi = std::min(n, lo + bs);
+        u64 off = f_mul(f_exp(inc, lo), inv_len);
+        for (size_t i = lo; i < hi; i++) {  // shift_by_series(offset, increment)
+            for (int k = 0; k < d; k++) v[i * d + k] = f_mul(v[i * d + k], off);
+            off = f_mul(off, inc);
+        }
     }
 }
 static void evaluate_poly_with_offset(const u64* p, size_t n, int d, const u64* tw, u64 domain_offset,
@@ -228,19 +291,20 @@ static void evaluate_poly_with_offset(const u64* p, size_t n, int d, const u64* 
     // fft/serial.rs:29-56 (chunks are independent: concurrent.rs:26-49 runs them via rayon)
     size_t domain = n * blowup;
     u64 g = root_of_unity((u32)__builtin_ctzll(domain));
-#pragma omp parallel for schedule(dynamic, 1)
+    const int total = inner_threads(1), nt_in = inner_threads(blowup), nt_out = (int)std::min<size_t>(blowup, (size_t)total);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt_out)
     for (size_t i = 0; i < blowup; i++) {
         u64* chunk = result + i * n * d;
         u64 idx = permute_index(blowup, i);
         u64 offset = f_mul(f_exp(g, idx), domain_offset);
         u64 factor = 1;
-        for (size_t j = 0; j < n; j++) {
+        for (size_t j = 0; j < n; j++) {  // clone_and_shift (concurrent.rs:223-236)
             for (int k = 0; k < d; k++) chunk[j * d + k] = f_mul(p[j * d + k], factor);
             factor = f_mul(factor, offset);
         }
-        ref_fft_in_place(chunk, n, d, tw);
+        fft_in_place_auto(chunk, n, d, tw, nt_in);
     }
-    permute_words(result, domain, d);
+    permute_words(result, domain, d, total);
 }
 
 // polynom::eval (math/src/polynom/mod.rs:55-62): Horner, coefficients of degree dp, point of degree dx
@@ -263,8 +327,16 @@ static void eval_poly_at(const u64* p, size_t n, int dp, const u64* x, int dx, u
 // =================================================================================================
 static void interpolate_columns(u64* cols, size_t c, size_t n, int d) {  // col_matrix.rs:192-202
     std::vector<u64> inv_tw = get_inv_twiddles(n);
-#pragma omp parallel for schedule(dynamic, 1)
-    for (size_t j = 0; j < c; j++) interpolate_poly(cols + j * n * d, n, d, inv_tw.data());
+    // iter_mut!(columns) over fft::interpolate_poly, itself concurrent (nested rayon): columns x inner threads
+    const int total = inner_threads(1), nt_in = inner_threads(c), nt_out = (int)std::min<size_t>(c, (size_t)total);
+    const u64 inv_len = f_inv((u64)n % P);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt_out)
+    for (size_t j = 0; j < c; j++) {
+        u64* v = cols + j * n * d;
+        fft_in_place_auto(v, n, d, inv_tw.data(), nt_in);
+        for (size_t i = 0; i < n * d; i++) v[i] = f_mul(v[i], inv_len);
+        permute_words(v, n, d, nt_in);
+    }
 }
 
 // row_matrix.rs:84-100 evaluate_polys_over::<8> + get_evaluation_offsets :238-271 +
@@ -281,7 +353,9 @@ static void lde_rows(const u64* polys, size_t c, size_t n, int d, size_t blowup,
     std::vector<u64> seg_off(blowup);
     for (size_t k = 0; k < blowup; k++) seg_off[k] = f_mul(f_exp(g, permute_index(blowup, k)), GENERATOR);
     size_t num_seg = (w + 7) / 8;
-#pragma omp parallel for collapse(2) schedule(dynamic, 1)
+    // segments.rs:127-141 (`concurrent`): par_chunks_mut over the cosets, split_radix_fft inside each
+    const int total = inner_threads(1), nt_in = inner_threads(num_seg * blowup), nt_out = (int)std::min<size_t>(num_seg * blowup, (size_t)total);
+#pragma omp parallel for collapse(2) schedule(dynamic, 1) num_threads(nt_out)
     for (size_t s = 0; s < num_seg; s++) {
         for (size_t k = 0; k < blowup; k++) {  // segments.rs:130 par_chunks_mut(poly_size)
             size_t q0 = s * 8, q1 = std::min(w, q0 + 8), nq = q1 - q0;
@@ -295,7 +369,7 @@ static void lde_rows(const u64* polys, size_t c, size_t n, int d, size_t blowup,
                 }
                 factor = f_mul(factor, seg_off[k]);
             }
-            ref_fft_in_place(buf.data(), n, (int)nq, tw.data());
+            fft_in_place_auto(buf.data(), n, (int)nq, tw.data(), nt_in);
             // whole-buffer bit reversal (segments.rs:279-301) maps (coset k, bitrev position) to
             // natural row order: row = permute_index(N, k*n + pos)
             for (size_t pos = 0; pos < n; pos++) {
@@ -654,7 +728,17 @@ static size_t fri_num_layers(size_t domain, size_t nf, size_t rem_max_deg, size_
 // C API
 // =================================================================================================
 extern "C" {
-void wfo_set_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }
+void wfo_set_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); omp_set_max_active_levels(2); }
+// split_radix_fft (fft/concurrent.rs:131-171) with nt threads, for the parity test against the serial network
+void wfo_split_radix_fft(uint64_t* v, size_t n, int d, int inverse, int nt) {
+    omp_set_max_active_levels(2);
+    auto t = inverse ? get_inv_twiddles(n) : get_twiddles(n);
+    split_radix_fft(v, n, d, t.data(), nt);
+}
+void wfo_fft_in_place(uint64_t* v, size_t n, int d, int inverse) {
+    auto t = inverse ? get_inv_twiddles(n) : get_twiddles(n);
+    ref_fft_in_place(v, n, d, t.data());
+}
 int wfo_get_threads(void) { return omp_get_max_threads(); }
 uint64_t wfo_add(uint64_t a, uint64_t b) { return f_add(a, b); }
 uint64_t wfo_sub(uint64_t a, uint64_t b) { return f_sub(a, b); }

@@ -574,6 +574,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[w][n]*/,
     }
     // 3. composition polynomial + commitment (composition_poly.rs:58-78, commitment/default.rs:109-150)
     std::vector<u64> cp(ce * d);
+#pragma omp parallel for schedule(static)
     for (size_t i = 0; i < ce; i++) for (int k = 0; k < d; k++) cp[i * d + k] = comp[i].v[k];
     { auto itw = get_inv_twiddles(ce); interpolate_poly_with_offset(cp.data(), ce, d, itw.data(), GENERATOR); }
     const size_t kc = air.num_comp_cols();
@@ -593,16 +594,24 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[w][n]*/,
     EE zg = F.mul_base(z, g_tr);
     const size_t ct = c + aw;  // main columns then aux columns (ood_frame.rs:40-72)
     std::vector<EE> t_cur(ct), t_nxt(ct), q_cur(kc), q_nxt(kc);
-    for (size_t j = 0; j < c; j++) { t_cur[j] = horner_base(F, &polys[j * n], n, z); t_nxt[j] = horner_base(F, &polys[j * n], n, zg); }
+    // ColMatrix::evaluate_columns_at (col_matrix.rs:245-252): iter!(columns) — parallel over columns in the `concurrent` build
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t jj = 0; jj < 2 * c; jj++) {
+        const size_t j = jj >> 1;
+        if (jj & 1) t_nxt[j] = horner_base(F, &polys[j * n], n, zg); else t_cur[j] = horner_base(F, &polys[j * n], n, z);
+    }
+#pragma omp parallel for schedule(dynamic, 1)
     for (size_t j = 0; j < aw; j++) {
         std::vector<EE> pe(n);
         for (size_t i = 0; i < n; i++) { pe[i] = F.zero(); for (int k = 0; k < d; k++) pe[i].v[k] = apolys[(j * n + i) * d + k]; }
         t_cur[c + j] = horner_ext(F, pe.data(), n, z); t_nxt[c + j] = horner_ext(F, pe.data(), n, zg);
     }
-    for (size_t j = 0; j < kc; j++) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t jj = 0; jj < 2 * kc; jj++) {
+        const size_t j = jj >> 1;
         std::vector<EE> pe(n);
         for (size_t i = 0; i < n; i++) { pe[i] = F.zero(); for (int k = 0; k < d; k++) pe[i].v[k] = cpolys[(j * n + i) * d + k]; }
-        q_cur[j] = horner_ext(F, pe.data(), n, z); q_nxt[j] = horner_ext(F, pe.data(), n, zg);
+        if (jj & 1) q_nxt[j] = horner_ext(F, pe.data(), n, zg); else q_cur[j] = horner_ext(F, pe.data(), n, z);
     }
     Writer ood_t, ood_q;
     ood_t.u8_(2); ood_t.elems(F, t_cur.data(), ct); ood_t.elems(F, t_nxt.data(), ct); // ood_frame.rs:59-72
@@ -619,7 +628,8 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[w][n]*/,
     // 5. DEEP composition polynomial, coefficient form (composer/mod.rs:67-210)
     std::vector<EE> dcoef = coin.draw_coeffs(F, (int)o.batch_d, ct + kc);
     std::vector<EE> comp_z(n, F.zero()), comp_gz(n, F.zero());
-    for (size_t j = 0; j < c; j++) {  // acc_trace_poly: mul_acc + constant term
+    for (size_t j = 0; j < c; j++) {  // acc_trace_poly: mul_acc (iter_mut!: parallel over i when `concurrent`) + constant term
+#pragma omp parallel for schedule(static) if (n >= 1024)
         for (size_t i = 0; i < n; i++) {
             EE t = F.mul_base(dcoef[j], polys[j * n + i]);
             comp_z[i] = F.add(comp_z[i], t); comp_gz[i] = F.add(comp_gz[i], t);
@@ -628,6 +638,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[w][n]*/,
         comp_gz[0] = F.sub(comp_gz[0], F.mul(t_nxt[j], dcoef[j]));
     }
     for (size_t j = 0; j < aw; j++) {  // composer/mod.rs:100-125 aux trace polys, acc_trace_poly::<E, E>
+#pragma omp parallel for schedule(static) if (n >= 1024)
         for (size_t i = 0; i < n; i++) {
             EE pe = F.zero(); for (int k = 0; k < d; k++) pe.v[k] = apolys[(j * n + i) * d + k];
             EE t = F.mul(pe, dcoef[c + j]);
@@ -637,6 +648,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[w][n]*/,
         comp_gz[0] = F.sub(comp_gz[0], F.mul(t_nxt[c + j], dcoef[c + j]));
     }
     for (size_t j = 0; j < kc; j++) {
+#pragma omp parallel for schedule(static) if (n >= 1024)
         for (size_t i = 0; i < n; i++) {
             EE pe = F.zero(); for (int k = 0; k < d; k++) pe.v[k] = cpolys[(j * n + i) * d + k];
             EE t = F.mul(pe, dcoef[ct + j]);
@@ -649,8 +661,16 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[w][n]*/,
         EE cc = F.zero();
         for (size_t i = p.size(); i-- > 0;) { p[i] = F.add(p[i], F.mul(bb, cc)); std::swap(p[i], cc); }
     };
-    syn_div(comp_z, z); syn_div(comp_gz, zg);
+    // merge_compositions (composer/mod.rs:186-200): iter_mut!(polys).zip(divisors) — the two divisions run side by side
+#pragma omp parallel sections num_threads(2)
+    {
+#pragma omp section
+        syn_div(comp_z, z);
+#pragma omp section
+        syn_div(comp_gz, zg);
+    }
     std::vector<u64> deep(n * d);
+#pragma omp parallel for schedule(static)
     for (size_t i = 0; i < n; i++) { EE s = F.add(comp_z[i], comp_gz[i]); for (int k = 0; k < d; k++) deep[i * d + k] = s.v[k]; }
     std::vector<u64> deep_ev(N * d);
     { auto tw = get_twiddles(n); evaluate_poly_with_offset(deep.data(), n, d, tw.data(), GENERATOR, b, deep_ev.data()); }

@@ -547,3 +547,16 @@ def test_periodic_value_table(oracle):
         x = 7 * pow(g_ce, i, P) % P
         assert int(row[0]) == interp_eval([1, 2], pow(x, n // 2, P))
         assert int(row[1]) == interp_eval([3, 4, 5, 6], pow(x, n // 4, P))
+
+
+def test_split_radix_fft_equals_serial_network(oracle):
+    o = oracle
+    # math/src/fft/tests.rs checks the concurrent transforms against the serial ones; the oracle's restatement of
+    # concurrent::split_radix_fft (the CPU baseline's parallel decomposition) must give the serial network's words
+    for log_n in (10, 11, 12, 13):           # even sizes: stretch 1, odd sizes: stretch 2
+        for d in (1, 3):
+            v = o.rand_elems(((1 << log_n) * d,), 77 + log_n + d)
+            for inverse in (False, True):
+                want = o.fft_in_place(v, d, inverse)
+                for nt in (1, 3, 8):
+                    assert (o.fft_in_place(v, d, inverse, split_radix_threads=nt) == want).all(), (log_n, d, inverse, nt)

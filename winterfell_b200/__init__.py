@@ -93,6 +93,7 @@ _SIGS = [
     ("wf_host_canonical_to_mont", C.c_uint64, [C.c_uint64]),
     ("wf_host_write_usize", C.c_size_t, [C.c_uint64, u8p]),
     ("wf_host_coin_draw", C.c_int, [C.c_int, u64p, C.c_size_t, u8p, C.c_int, C.c_size_t, u64p]),
+    ("wf_host_build_fib_trace", C.c_int, [C.c_uint32, C.c_size_t, u64p, u64p]),
 ]
 
 
@@ -485,6 +486,17 @@ class Fri:
 
 
 # ---- host helpers (usable without a GPU) ----
+def build_fib_trace(k, n, out=None):
+    """FibSmall x k trace (examples/src/fibonacci/fib_small/prover.rs:37-53): ([2k, n] uint64, results [k]).
+    `out`: optional preallocated [2k, n] uint64 array (e.g. a view of pinned memory)."""
+    tr = out if out is not None else np.empty((2 * k, n), dtype=np.uint64)
+    assert tr.shape == (2 * k, n) and tr.dtype == np.uint64 and tr.flags["C_CONTIGUOUS"]
+    res = np.zeros(k, dtype=np.uint64)
+    if lib().wf_host_build_fib_trace(k, n, tr.ctypes.data_as(u64p), res.ctypes.data_as(u64p)) != WF_OK:
+        raise WfError("wf_host_build_fib_trace: bad arguments")
+    return tr, res
+
+
 def host_hash_elements(hash_id, elems):
     e_, ep = _u64(np.asarray(elems, dtype=np.uint64).reshape(-1))
     o = np.zeros(32, dtype=np.uint8)

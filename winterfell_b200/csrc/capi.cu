@@ -9,6 +9,7 @@
 #include <map>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "internal.hpp"
@@ -1236,6 +1237,28 @@ size_t wf_host_write_usize(uint64_t value, uint8_t out[9]) {  // the serializer'
     b.usize(value);
     memcpy(out, b.v.data(), b.v.size());
     return b.v.size();
+}
+// FibSmallProver::build_trace (examples/src/fibonacci/fib_small/prover.rs:37-53) for the "FibSmall x k" family:
+// pair j starts at (j + 1, j + 1) and steps state[0] += state[1]; state[1] += state[0]. cols: [2k][n] canonical
+// words (column-major, the layout wf_prove_fib / wf_prove_fib_dev take); results[j] = last value of column 2j+1.
+int wf_host_build_fib_trace(uint32_t k, size_t n, uint64_t* cols, uint64_t* results) {
+    if (!cols || !results || k == 0 || n == 0) return WF_ERR_INVALID;
+    auto pair = [&](uint32_t j) {
+        u64 a = j + 1, b = j + 1;
+        u64 *ca = cols + (size_t)(2 * j) * n, *cb = ca + n;
+        for (size_t i = 0; i < n; i++) {
+            ca[i] = a;
+            cb[i] = b;
+            a = gl_add_host(a, b);
+            b = gl_add_host(b, a);
+        }
+        results[j] = cb[n - 1];
+    };
+    const unsigned nt = std::max(1u, std::min(std::min(k, 16u), std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;  // pairs are independent
+    for (unsigned t = 0; t < nt; t++) th.emplace_back([&, t]() { for (uint32_t j = t; j < k; j += nt) pair(j); });
+    for (auto& x : th) x.join();
+    return WF_OK;
 }
 // DefaultRandomCoin on the host (crypto/src/random/default.rs): seed from elements, optional reseed with a
 // digest, then draw `count` elements of extension degree d -> out[count][d]. Returns 0, or -1 if a draw fails.

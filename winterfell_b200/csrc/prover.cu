@@ -147,7 +147,7 @@ struct GenEvalParams {
     const u32* e_tstride;  // words per table row
     const u32* e_shift;    // (first_step * ce_blowup) mod ce
     const u64* tw_ce;      // w_ce^i, i < ce/2
-    u64 zt[8];             // 1 / (x^n - 1) at CE step i mod ce_blowup
+    const u64* zt;         // [ce_blowup] 1 / (x^n - 1) at CE step i mod ce_blowup (device table: ce_blowup <= 128)
     u64 exempt[8];
     u32 num_exempt;
     // auxiliary segment (Air::evaluate_aux_transition, air/src/air/mod.rs:248-260): program over E
@@ -632,7 +632,9 @@ static bool parse_air_host(const u64* d, size_t len, AirHost& a) {
         u64 base, nc;
         if (!rd(base) || !rd(nc) || base == 0 || nc > 16) return false;
         std::vector<u32> cyc;
-        for (u64 j = 0; j < nc; j++) { if (!rd(v)) return false; cyc.push_back((u32)v); }
+        // TransitionConstraintDegree::with_cycles asserts cycle lengths that are powers of two >= 2 (transition/degree.rs:62-79)
+        for (u64 j = 0; j < nc; j++) { if (!rd(v) || v < 2 || (v & (v - 1)) || v > (1ull << 32)) return false; cyc.push_back((u32)v); }
+        if (base + nc - 1 > 128) return false;  // min_blowup_factor would exceed the largest blowup (options.rs:132-190)
         a.degrees.push_back({(u32)base, cyc});
     }
     if (!rd(cnt) || cnt > 64) return false;
@@ -681,7 +683,8 @@ static bool parse_air_host(const u64* d, size_t len, AirHost& a) {
         u64 base, nc;
         if (!rd(base) || !rd(nc) || base == 0 || nc > 16) return false;
         std::vector<u32> cyc;
-        for (u64 j = 0; j < nc; j++) { if (!rd(v)) return false; cyc.push_back((u32)v); }
+        for (u64 j = 0; j < nc; j++) { if (!rd(v) || v < 2 || (v & (v - 1)) || v > (1ull << 32)) return false; cyc.push_back((u32)v); }
+        if (base + nc - 1 > 128) return false;
         a.aux_degrees.push_back({(u32)base, cyc});
     }
     const u64 first_tmp = 2 * a.w + 2 * a.aw + a.periodic.size() + a.nr;
@@ -803,6 +806,15 @@ void write_queries(const GatherBatch& gb, size_t row_id, size_t dig_id, size_t n
     w.bytes(proof.v.data(), proof.v.size());
 }
 
+// cycle lengths of a TransitionConstraintDegree must not exceed the trace length (get_evaluation_degree,
+// air/src/air/transition/degree.rs:85-97, divides trace_length by each cycle)
+static int validate_degrees(wf_ctx* ctx, const std::vector<std::pair<u32, std::vector<u32>>>& degs, size_t n) {
+    for (auto& dg : degs)
+        for (u32 cyc : dg.second)
+            if (cyc < 2 || (cyc & (cyc - 1)) || cyc > n) return wf_fail(ctx, WF_ERR_INVALID, "constraint degree cycle %u does not fit a trace of %zu rows", cyc, n);
+    return WF_OK;
+}
+
 // Assertion validity (air/src/air/assertions/mod.rs:62-120, :166-230 validate_*)
 static int validate_assertions(wf_ctx* ctx, const std::vector<AirAssertion>& as, size_t n, size_t words_per_value, const char* what) {
     for (auto& a : as) {
@@ -875,7 +887,7 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
     CKI(wf_mat_alloc(ctx, ce, D, &comp));
     if (comp->m.W > D) CK(cudaMemsetAsync(comp->m.base, 0, comp->m.words() * 8, ctx->st));
     const u64 g_tr = gl_root_of_unity(log_n);
-    u64 zt[8];
+    std::vector<u64> zt((size_t)1 << log_ceb);  // ce_blowup <= blowup <= 128 entries
     {   // x^n over the CE domain takes ce_blowup values: (7 w_ce^i)^n = 7^n * w_ceb^i
         u64 o_n = gl_pow(GL_GENERATOR, n), w_ceb = gl_root_of_unity(log_ceb);
         for (u32 i = 0; i < (1u << log_ceb); i++) zt[i] = gl_inv(gl_sub(gl_mul(o_n, gl_pow(w_ceb, i)), 1));
@@ -910,6 +922,7 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
         p.tcoef = (u64*)d_tc; p.bcoef0 = (u64*)d_b0; p.bcoef1 = (u64*)d_b1; p.results = (u64*)d_res;
         CKI(wf_get_twiddles(ctx, log_n + log_ceb, &p.tw_ce));
         p.last = gl_pow(g_tr, n - 1);
+        if (log_ceb > 3) return wf_fail(ctx, WF_ERR_STATE, "FibSmall has degree-1 constraints");  // FibEvalParams::zt[8]
         for (u32 i = 0; i < (1u << log_ceb); i++) p.zt[i] = zt[i];
         size_t threads = (ce + FIB_ROWS - 1) / FIB_ROWS;
         fib_constraints_kernel<D><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->st>>>(p);
@@ -979,7 +992,7 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
         CKI(upload(etstride.data(), etstride.size() * 4, &dp)); p.e_tstride = (u32*)dp;
         CKI(upload(eshift.data(), eshift.size() * 4, &dp)); p.e_shift = (u32*)dp;
         CKI(wf_get_twiddles(ctx, log_n + log_ceb, &p.tw_ce));
-        for (u32 i = 0; i < (1u << log_ceb); i++) p.zt[i] = zt[i];
+        CKI(upload(zt.data(), zt.size() * 8, &dp)); p.zt = (const u64*)dp;
         p.num_exempt = air.exemptions;
         for (u32 e = 0; e < air.exemptions; e++) p.exempt[e] = gl_pow(g_tr, n - air.exemptions + e);  // divisor.rs:31-41
         std::vector<u32> agoff = {0}, aecol, aetstride, aeshift;
@@ -1127,6 +1140,7 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     if (aw && !aux_builder) return wf_fail(ctx, WF_ERR_INVALID, "multi-segment AIR needs an aux trace builder");
     if (log_ceb > log_b) return wf_fail(ctx, WF_ERR_INVALID, "blowup factor too small for the constraint degrees");
     for (auto& col : air.periodic) if (col.size() > n) return wf_fail(ctx, WF_ERR_INVALID, "periodic column longer than the trace");
+    CKI(validate_degrees(ctx, air.all_degrees(), n));
     CKI(validate_assertions(ctx, air.aux_asserts, n, 3, "aux assertion"));
     CKI(validate_assertions(ctx, air.asserts, n, 1, "assertion"));
     // ---- channel seed: Context::to_elements || pub inputs (channel.rs:57-82, context.rs:119-136) ----
@@ -1399,6 +1413,7 @@ extern "C" int wf_eval_constraints(wf_ctx* ctx, const uint64_t* air_desc, size_t
     if (air.aw && (!aux_lde || !aux_rand || aux_lde->m.rows != N || aux_lde->m.cols != air.aw * ext))
         return wf_fail(ctx, WF_ERR_INVALID, "aux LDE / random elements missing or of the wrong shape");
     for (auto& col : air.periodic) if (col.size() > ((size_t)1 << log_n)) return wf_fail(ctx, WF_ERR_INVALID, "periodic column longer than the trace");
+    CKI(validate_degrees(ctx, air.all_degrees(), (size_t)1 << log_n));
     CKI(validate_assertions(ctx, air.aux_asserts, (size_t)1 << log_n, 3, "aux assertion"));
     CKI(validate_assertions(ctx, air.asserts, (size_t)1 << log_n, 1, "assertion"));
     const wf_mat* al = air.aw ? aux_lde : nullptr;
