@@ -238,6 +238,39 @@ int wf_deep_compose(wf_ctx* ctx, uint32_t ext, const wf_mat* main_lde, const wf_
  * nonce >= 1 with trailing_zeros(first 8 LE bytes of H::merge_with_int(seed, nonce)) >= grinding. */
 int wf_grind(wf_ctx* ctx, int hash_id, const uint8_t seed[32], uint32_t grinding, uint64_t* nonce);
 
+/* ---- one proof sharded over several GPUs (one process and one wf_ctx per GPU) ------------------
+ * The reference has no distributed prover; its unit of distribution is the column (ColMatrix columns are independent,
+ * prover/src/matrix/col_matrix.rs:192-202) and PartitionOptions (air/src/options.rs:405-445). Here rank r of `world`
+ * owns trace columns [r*w/world, (r+1)*w/world): it interpolates and extends them locally, the LDE is exchanged into
+ * row shards (rank r holds LDE rows [r*N/world, (r+1)*N/world) of ALL columns plus `blowup` halo rows), and leaf
+ * hashing, constraint evaluation, DEEP composition and the first FRI layers run on row shards; every Merkle tree is a
+ * local subtree per rank plus log2(world) top levels built from an all-gather of the subtree roots; query openings are
+ * gathered from their owners. The proof is byte-identical to wf_prove_fib's on one GPU.
+ * The host program supplies the collectives (torch.distributed / NCCL in bench.py; any MPI-like layer works): */
+typedef struct wf_comm {
+    void* user;
+    int rank, world; /* world: a power of two */
+    /* Point-to-point exchange of DEVICE buffers of `bytes` bytes each: send[i] goes to rank send_peer[i], recv[i] is
+     * filled by rank recv_peer[i]; transfers between one pair of ranks match in list order; no entry names the caller's
+     * own rank. Must be ordered after the work already enqueued on the ctx stream and be complete, or ordered on that
+     * stream, when it returns. */
+    int (*exchange)(void* user, size_t nsend, const int* send_peer, const void* const* send, size_t nrecv,
+                    const int* recv_peer, void* const* recv, size_t bytes);
+    /* all-gather of `bytes` bytes per rank between HOST buffers: recv = world x bytes in rank order */
+    int (*all_gather_host)(void* user, const void* send, void* recv, size_t bytes);
+    /* element-wise wrapping sum over the ranks of `words` 64-bit words of a DEVICE buffer, in place (merges gathers
+     * whose entries are non-zero on exactly one rank); same ordering rule as exchange */
+    int (*all_reduce_sum)(void* user, void* d_buf, size_t words);
+} wf_comm;
+/* FibSmall x k (as wf_prove_fib) sharded over comm->world GPUs: this rank passes ITS 2k/world columns (host columns, or
+ * d_local = device column-major [2k/world][2^log_n]); 2k/world must be a multiple of 8 (whole 8-column segments).
+ * `results` and `opts` are the full proof's; every rank returns the same proof bytes.
+ * stats (optional, 8 doubles): [0] bytes this rank sent through exchange, [1] ms inside exchange, [2] number of
+ * collectives, [3] ms inside all_gather_host + all_reduce_sum. */
+int wf_prove_fib_sharded(wf_ctx* ctx, const wf_comm* comm, const uint64_t* const* local_cols, const uint64_t* d_local, int mont,
+                         uint32_t k, uint32_t log_n, const uint64_t* results, const uint32_t* opts, uint8_t* proof,
+                         size_t* proof_len, double* stats);
+
 /* ---- plain kernels on caller-owned DEVICE buffers (unit parity + bench legs) ------------------- */
 /* in-place NTT (inverse=0) / iNTT (inverse=1) of `cols` columns, column-major [cols][n], n = 1 << log_n */
 int wf_ntt_dev(wf_ctx* ctx, uint64_t* d_data, uint32_t log_n, uint32_t cols, int inverse);

@@ -94,6 +94,8 @@ _SIGS = [
     ("wf_host_write_usize", C.c_size_t, [C.c_uint64, u8p]),
     ("wf_host_coin_draw", C.c_int, [C.c_int, u64p, C.c_size_t, u8p, C.c_int, C.c_size_t, u64p]),
     ("wf_host_build_fib_trace", C.c_int, [C.c_uint32, C.c_size_t, u64p, u64p]),
+    ("wf_prove_fib_sharded", C.c_int, [vp, vp, C.POINTER(u64p), vp, C.c_int, C.c_uint32, C.c_uint32, u64p, C.POINTER(C.c_uint32), u8p,
+                                       C.POINTER(C.c_size_t), C.POINTER(C.c_double)]),
 ]
 
 

@@ -106,14 +106,60 @@ int wf_get_twiddles(wf_ctx* ctx, u32 log_n, const u64** out) {
     return WF_OK;
 }
 
-// n = R * C split for the two-pass schedule
-// The strided pass also holds S*T post twiddles in shared memory (T = 8/W tile columns), so for
-// single-column segments (W = 1) its sub-transform is capped at 2^10 to stay under 227 KB.
-static void split_log(u32 log_n, int W, u32* logR, u32* logC) {
+// w_(2^log_order)^i for i < 2^log_count (full power table; two of them replace the gather over w_M^i, i < M/2)
+static int get_pow_table(wf_ctx* ctx, u32 log_order, u32 log_count, const u64** out) {
+    auto key = std::make_pair(log_order, log_count);
+    auto it = ctx->pow_tab.find(key);
+    if (it != ctx->pow_tab.end()) { *out = it->second; return WF_OK; }
+    size_t cnt = (size_t)1 << log_count;
+    void* p;
+    cudaError_t e = cudaMalloc(&p, std::max(cnt * 8, (size_t)16));
+    if (e != cudaSuccess) return wf_fail(ctx, WF_ERR_CUDA, "cudaMalloc power table: %s", cudaGetErrorString(e));
+    pow_table_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->st>>>((u64*)p, log_order ? gl_root_of_unity(log_order) : 1, 1, cnt);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->pow_tab[key] = (u64*)p;
+    *out = (u64*)p;
+    return WF_OK;
+}
+static int get_round_tw(wf_ctx* ctx, u32 logS, const u64** out) {
+    auto it = ctx->round_tw.find(logS);
+    if (it != ctx->round_tw.end()) { *out = it->second; return WF_OK; }
+    void* p;
+    cudaError_t e = cudaMalloc(&p, ntt2_tw_entries((int)logS) * 8);
+    if (e != cudaSuccess) return wf_fail(ctx, WF_ERR_CUDA, "cudaMalloc round twiddles: %s", cudaGetErrorString(e));
+    CK(ntt2_build_tw((int)logS, (u64*)p, ctx->st));
+    ctx->launches++;
+    ctx->round_tw[logS] = (u64*)p;
+    *out = (u64*)p;
+    return WF_OK;
+}
+// One pass: fills in the twiddle tables the kernel family of this sub-transform size reads, then launches.
+// p.logS, p.logM, p.has_post, p.W and the geometry must be set; sub_tw / master / tw_hi / tw_lo are set here.
+static int launch_pass(wf_ctx* ctx, int mode, NttPassParams& p, u32 n_segments, u32 n_batch) {
+    if (p.logS >= NTT2_MIN_LOGS) {
+        CKI(get_round_tw(ctx, (u32)p.logS, &p.sub_tw));
+        if (p.has_post) {
+            p.tw_split = p.logM / 2;
+            CKI(get_pow_table(ctx, p.logM, p.tw_split, &p.tw_lo));
+            CKI(get_pow_table(ctx, p.logM - p.tw_split, p.logM - p.tw_split, &p.tw_hi));
+        }
+        p.vec_in = p.vec_out = (p.W >= 2 || mode == NTT_STRIDED) ? 1 : 0;
+        CK(ntt2_launch_pass(mode, p, n_segments, n_batch, ctx->st));
+    } else {
+        CKI(wf_get_twiddles(ctx, std::max((u32)p.logS, 1u), &p.sub_tw));
+        if (p.has_post) CKI(wf_get_twiddles(ctx, p.logM, &p.master));
+        CK(ntt_launch_pass(mode, p, n_segments, n_batch, ctx->st));
+    }
+    ctx->launches++;
+    return WF_OK;
+}
+
+// n = R * C split for the two-pass schedule (sub-transforms of at most 2^NTT_MAX_LOGS points)
+static void split_log(u32 log_n, u32* logR, u32* logC) {
     if (log_n <= NTT_MAX_LOGS) { *logR = 0; *logC = log_n; return; }
-    u32 max_r = W == 1 ? NTT_MAX_LOGS - 1 : NTT_MAX_LOGS;
     u32 r = (log_n + 1) / 2;
-    if (r > max_r) r = max_r;
+    if (r > NTT_MAX_LOGS) r = NTT_MAX_LOGS;
     *logR = r;
     *logC = log_n - r;
 }
@@ -171,73 +217,62 @@ static void pass_defaults(NttPassParams& p, const SegMatrix& in, const SegMatrix
     p.out_row_mul = 1;
     p.cconst = 1;
 }
+// three-pass split for n > 2^22: n = 2^lr * 2^lc with the size-2^lc step itself two-pass (2^lr2 * 2^lc2)
+static int split3(wf_ctx* ctx, u32 log_n, u32* lr, u32* lc, u32* lr2, u32* lc2) {
+    *lr = (log_n + 2) / 3;
+    *lc = log_n - *lr;
+    split_log(*lc, lr2, lc2);
+    if (*lr2 == 0 || *lc2 > NTT_MAX_LOGS || *lr > NTT_MAX_LOGS)
+        return wf_fail(ctx, WF_ERR_UNSUPPORTED, "transform of 2^%u points exceeds the three-pass limit", log_n);
+    return WF_OK;
+}
 
 // out = DFT (inverse: iDFT with 1/n) of every column of `in`; in/out: n rows. `tmp` (n rows, same
 // shape) is needed when log_n > NTT_MAX_LOGS. in == out is allowed.
 static int run_ntt(wf_ctx* ctx, const SegMatrix& in, SegMatrix& out, const SegMatrix* tmp, u32 log_n, int inverse) {
     u32 logR, logC;
-    split_log(log_n, in.W, &logR, &logC);
+    split_log(log_n, &logR, &logC);
     u64 inv_n = gl_inv(((u64)1 << log_n) % GL_P);
     NttPassParams p;
     if (logC > NTT_MAX_LOGS) {
-        // THREE passes (n > 2^22): n = R * C with C itself two-pass. Pass A is the strided size-R step
-        // of the four-step scheme over the whole array; the contiguous size-C step is then a batch of R
-        // independent two-pass transforms (batch index = j1) whose last pass writes X[j1 + R * j].
+        // THREE passes (n > 2^22): pass A is the strided size-R step of the four-step scheme over the whole array; the
+        // contiguous size-C step is then a batch of R independent two-pass transforms (batch index = j1) whose last
+        // pass writes X[j1 + R * j].
         if (!tmp) return wf_fail(ctx, WF_ERR_STATE, "run_ntt: scratch matrix required");
-        u32 lr = (log_n + 2) / 3, lc = log_n - lr, lr2, lc2;
-        split_log(lc, in.W, &lr2, &lc2);
-        if (lr2 == 0 || lc2 > NTT_MAX_LOGS || lr > NTT_MAX_LOGS - (in.W == 1 ? 1 : 0))
-            return wf_fail(ctx, WF_ERR_UNSUPPORTED, "NTT size 2^%u exceeds the three-pass limit", log_n);
+        u32 lr, lc, lr2, lc2;
+        CKI(split3(ctx, log_n, &lr, &lc, &lr2, &lc2));
         pass_defaults(p, in, *tmp);  // pass A
         p.logS = (int)lr; p.logR = lr; p.logC = lc; p.inverse = inverse;
-        CKI(wf_get_twiddles(ctx, lr, &p.sub_tw));
-        p.has_post = 1;
-        CKI(wf_get_twiddles(ctx, log_n, &p.master));
-        p.logM = log_n; p.a_mul = 1; p.b_mul = 0; p.cconst = inverse ? inv_n : 1;
-        CK(ntt_launch_pass(NTT_STRIDED, p, in.nseg(), 1, ctx->st));
+        p.has_post = 1; p.logM = log_n; p.a_mul = 1; p.b_mul = 0; p.cconst = inverse ? inv_n : 1;
+        CKI(launch_pass(ctx, NTT_STRIDED, p, in.nseg(), 1));
         pass_defaults(p, *tmp, *tmp);  // pass B: in place, batch = row j1 of the R x C matrix
         p.in_batch_stride = p.out_batch_stride = ((size_t)1 << lc) * in.W;
         p.logS = (int)lr2; p.logR = lr2; p.logC = lc2; p.inverse = inverse;
-        CKI(wf_get_twiddles(ctx, lr2, &p.sub_tw));
-        p.has_post = 1;
-        CKI(wf_get_twiddles(ctx, lc, &p.master));
-        p.logM = lc; p.a_mul = 1; p.b_mul = 0;
-        CK(ntt_launch_pass(NTT_STRIDED, p, in.nseg(), 1u << lr, ctx->st));
+        p.has_post = 1; p.logM = lc; p.a_mul = 1; p.b_mul = 0;
+        CKI(launch_pass(ctx, NTT_STRIDED, p, in.nseg(), 1u << lr));
         pass_defaults(p, *tmp, out);  // pass C: X[j1 + R * (inner index)]
         p.in_batch_stride = ((size_t)1 << lc) * in.W;
         p.logS = (int)lc2; p.logR = lr2; p.logC = lc2; p.inverse = inverse;
         p.out_row_mul = 1u << lr; p.out_row_add = 1;
-        CKI(wf_get_twiddles(ctx, lc2, &p.sub_tw));
-        CK(ntt_launch_pass(NTT_CONTIG, p, in.nseg(), 1u << lr, ctx->st));
-        ctx->launches += 3;
+        CKI(launch_pass(ctx, NTT_CONTIG, p, in.nseg(), 1u << lr));
         return WF_OK;
     }
     if (logR == 0) {
         pass_defaults(p, in, out);
         p.logS = (int)logC; p.logR = 0; p.logC = logC; p.inverse = inverse;
-        CKI(wf_get_twiddles(ctx, std::max(log_n, 1u), &p.sub_tw));
         if (inverse) p.cconst = inv_n;
-        CK(ntt_launch_pass(NTT_CONTIG, p, in.nseg(), 1, ctx->st));
-        ctx->launches++;
-        return WF_OK;
+        return launch_pass(ctx, NTT_CONTIG, p, in.nseg(), 1);
     }
     if (!tmp) return wf_fail(ctx, WF_ERR_STATE, "run_ntt: scratch matrix required");
     // pass 1: strided size-R transforms + twiddle w_n^(+-j1*m2) (and 1/n for the inverse)
     pass_defaults(p, in, *tmp);
     p.logS = (int)logR; p.logR = logR; p.logC = logC; p.inverse = inverse;
-    CKI(wf_get_twiddles(ctx, logR, &p.sub_tw));
-    p.has_post = 1;
-    CKI(wf_get_twiddles(ctx, log_n, &p.master));
-    p.logM = log_n; p.a_mul = 1; p.b_mul = 0; p.cconst = inverse ? inv_n : 1;
-    CK(ntt_launch_pass(NTT_STRIDED, p, in.nseg(), 1, ctx->st));
-    ctx->launches++;
+    p.has_post = 1; p.logM = log_n; p.a_mul = 1; p.b_mul = 0; p.cconst = inverse ? inv_n : 1;
+    CKI(launch_pass(ctx, NTT_STRIDED, p, in.nseg(), 1));
     // pass 2: contiguous size-C transforms, transposed write-back
     pass_defaults(p, *tmp, out);
     p.logS = (int)logC; p.logR = logR; p.logC = logC; p.inverse = inverse;
-    CKI(wf_get_twiddles(ctx, logC, &p.sub_tw));
-    CK(ntt_launch_pass(NTT_CONTIG, p, in.nseg(), 1, ctx->st));
-    ctx->launches++;
-    return WF_OK;
+    return launch_pass(ctx, NTT_CONTIG, p, in.nseg(), 1);
 }
 
 // LDE of coefficient columns over 7 * <w_N>: out has n << log_b rows, row b*j + k = P(7 w_N^k w_n^j).
@@ -245,7 +280,7 @@ static int run_ntt(wf_ctx* ctx, const SegMatrix& in, SegMatrix& out, const SegMa
 // column offset out_col0 of each out row (column-chunked trace pipeline, wf_trace_lde_from_host).
 static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_n, u32 log_b, u32 out_col0 = 0) {
     u32 logR, logC;
-    split_log(log_n, polys.W, &logR, &logC);
+    split_log(log_n, &logR, &logC);
     u32 b = 1u << log_b;
     LdeTables tabs;
     NttPassParams p;
@@ -253,93 +288,81 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
         // THREE passes per coset (n > 2^22), same structure as run_ntt: pass A carries the coset scaling
         // and the four-step twiddle, the contiguous size-C step is a batch of R two-pass transforms whose
         // last pass writes row b*(j1 + R*j) + k.
-        u32 lr = (log_n + 2) / 3, lc = log_n - lr, lr2, lc2;
-        split_log(lc, polys.W, &lr2, &lc2);
-        if (lr2 == 0 || lc2 > NTT_MAX_LOGS || lr > NTT_MAX_LOGS - (polys.W == 1 ? 1 : 0))
-            return wf_fail(ctx, WF_ERR_UNSUPPORTED, "LDE of 2^%u rows exceeds the three-pass limit", log_n);
+        u32 lr, lc, lr2, lc2;
+        CKI(split3(ctx, log_n, &lr, &lc, &lr2, &lc2));
         CKI(get_lde_tables(ctx, log_n, log_b, lr, &tabs));
         SegMatrix y = polys;
         void* yp;
         CKI(wf_dev_alloc(ctx, polys.words() * 8, &yp));
         y.base = (u64*)yp;
-        const u64 *twA, *twB, *twC2, *twN, *twInner;
-        CKI(wf_get_twiddles(ctx, lr, &twA));
-        CKI(wf_get_twiddles(ctx, lr2, &twB));
-        CKI(wf_get_twiddles(ctx, lc2, &twC2));
-        CKI(wf_get_twiddles(ctx, log_n + log_b, &twN));
-        CKI(wf_get_twiddles(ctx, lc, &twInner));
-        for (u32 k = 0; k < b; k++) {
+        int rc = WF_OK;
+        for (u32 k = 0; k < b && rc == WF_OK; k++) {
             pass_defaults(p, polys, y);  // pass A
-            p.logS = (int)lr; p.logR = lr; p.logC = lc; p.sub_tw = twA;
+            p.logS = (int)lr; p.logR = lr; p.logC = lc;
             p.pre_tab = tabs.pre + ((size_t)k << lr); p.pre_batch_stride = 0;
-            p.has_post = 1; p.master = twN; p.logM = log_n + log_b; p.a_mul = b; p.b_mul = 1; p.batch0 = k;
+            p.has_post = 1; p.logM = log_n + log_b; p.a_mul = b; p.b_mul = 1; p.batch0 = k;
             p.ctab = tabs.pow7;
-            CK(ntt_launch_pass(NTT_STRIDED, p, polys.nseg(), 1, ctx->st));
+            rc = launch_pass(ctx, NTT_STRIDED, p, polys.nseg(), 1);
+            if (rc != WF_OK) break;
             pass_defaults(p, y, y);  // pass B (in place), batch = j1
             p.in_batch_stride = p.out_batch_stride = ((size_t)1 << lc) * polys.W;
-            p.logS = (int)lr2; p.logR = lr2; p.logC = lc2; p.sub_tw = twB;
-            p.has_post = 1; p.master = twInner; p.logM = lc; p.a_mul = 1; p.b_mul = 0;
-            CK(ntt_launch_pass(NTT_STRIDED, p, polys.nseg(), 1u << lr, ctx->st));
+            p.logS = (int)lr2; p.logR = lr2; p.logC = lc2;
+            p.has_post = 1; p.logM = lc; p.a_mul = 1; p.b_mul = 0;
+            rc = launch_pass(ctx, NTT_STRIDED, p, polys.nseg(), 1u << lr);
+            if (rc != WF_OK) break;
             pass_defaults(p, y, out);  // pass C: row b*(j1 + R*j) + k
             p.in_batch_stride = ((size_t)1 << lc) * polys.W;
-            p.logS = (int)lc2; p.logR = lr2; p.logC = lc2; p.sub_tw = twC2;
+            p.logS = (int)lc2; p.logR = lr2; p.logC = lc2;
             p.out_row_mul = b << lr; p.out_row_add = b; p.out_col0 = out_col0;
             p.out = out.base + (size_t)k * out.W;
-            CK(ntt_launch_pass(NTT_CONTIG, p, polys.nseg(), 1u << lr, ctx->st));
-            ctx->launches += 3;
+            rc = launch_pass(ctx, NTT_CONTIG, p, polys.nseg(), 1u << lr);
         }
-        wf_dev_free(ctx, yp);
-        return WF_OK;
+        wf_dev_free(ctx, yp);  // stream-ordered pool: also correct on the error path
+        return rc;
     }
     CKI(get_lde_tables(ctx, log_n, log_b, logR, &tabs));
     if (logR == 0) {
         pass_defaults(p, polys, out);
         p.logS = (int)logC; p.logR = 0; p.logC = logC;
-        CKI(wf_get_twiddles(ctx, std::max(log_n, 1u), &p.sub_tw));
         p.pre_tab = tabs.pre; p.pre_batch_stride = (size_t)1 << log_n;
         p.out_row_mul = b; p.out_row_add = 1; p.out_col0 = out_col0;
-        CK(ntt_launch_pass(NTT_CONTIG, p, polys.nseg(), b, ctx->st));
-        ctx->launches++;
-        return WF_OK;
+        return launch_pass(ctx, NTT_CONTIG, p, polys.nseg(), b);
     }
-    // Cosets per launch (grid.z = coset): as many as keep the scratch Y within 1 GiB. The passes are
-    // ALU-bound (DRAM ~10 %), so a scratch that no longer fits L2 costs nothing, while one launch per
-    // coset leaves a partial last wave every time (1024 tiles on 296 resident blocks: measured 6 % on
-    // the cfg2 trace LDE, 35 % on its one-column composition LDE).
+    // Cosets per launch (grid.z = coset). The scratch Y of one coset is as large as the polynomials; while
+    // it fits in half of the 126 MB L2 the contiguous pass finds most of it there, so cosets are processed
+    // kb at a time with kb chosen to keep kb * |polys| <= 64 MiB (never less than one coset; narrow matrices
+    // whose tiles would not fill the SMs take all cosets at once).
+    const size_t poly_bytes = polys.words() * 8;
+    const size_t tiles_per_coset = (((size_t)1 << logC) * polys.nseg());  // strided-pass blocks (x chunks)
     u32 kb = b;
-    while (kb > 1 && polys.words() * 8 * kb > ((size_t)1 << 30)) kb >>= 1;
+    while (kb > 1 && poly_bytes * kb > ((size_t)64 << 20) && tiles_per_coset * (kb / 2) >= 4 * 296) kb >>= 1;
+    while (kb > 1 && poly_bytes * kb > ((size_t)1 << 30)) kb >>= 1;
     SegMatrix y = polys;
     void* yp;
-    CKI(wf_dev_alloc(ctx, polys.words() * 8 * kb, &yp));
+    CKI(wf_dev_alloc(ctx, poly_bytes * kb, &yp));
     y.base = (u64*)yp;
-    const u64 *twR, *twC, *twN;
-    CKI(wf_get_twiddles(ctx, logR, &twR));
-    CKI(wf_get_twiddles(ctx, logC, &twC));
-    CKI(wf_get_twiddles(ctx, log_n + log_b, &twN));
-    for (u32 k = 0; k < b; k += kb) {
+    int rc = WF_OK;
+    for (u32 k = 0; k < b && rc == WF_OK; k += kb) {
         // pass 1: Y_k[j1][m2] = 7^m2 w_N^((b j1 + k) m2) sum_m1 a[C m1 + m2] (s_k^C)^m1 w_R^(j1 m1)
         pass_defaults(p, polys, y);
         p.logS = (int)logR; p.logR = logR; p.logC = logC;
-        p.sub_tw = twR;
         p.pre_tab = tabs.pre + ((size_t)k << logR); p.pre_batch_stride = (size_t)1 << logR;
         p.out_batch_stride = polys.words();
         // exponent (b*j1 + k)*m2 = (j1*a_mul + (batch0 + z)*b_mul)*m2
-        p.has_post = 1; p.master = twN; p.logM = log_n + log_b; p.a_mul = b; p.b_mul = 1; p.batch0 = k;
+        p.has_post = 1; p.logM = log_n + log_b; p.a_mul = b; p.b_mul = 1; p.batch0 = k;
         p.ctab = tabs.pow7;
-        CK(ntt_launch_pass(NTT_STRIDED, p, polys.nseg(), kb, ctx->st));
-        ctx->launches++;
+        rc = launch_pass(ctx, NTT_STRIDED, p, polys.nseg(), kb);
+        if (rc != WF_OK) break;
         // pass 2: X_k[j1 + R j2] = sum_m2 Y_k[j1][m2] w_C^(j2 m2)  -> row b*(j1 + R j2) + k
         pass_defaults(p, y, out);
         p.logS = (int)logC; p.logR = logR; p.logC = logC;
-        p.sub_tw = twC;
         p.in_batch_stride = polys.words();
         p.out_row_mul = b; p.out_row_add = 1; p.out_col0 = out_col0;
         p.out = out.base + (size_t)k * out.W;  // + k rows; the launch's coset z adds z rows
-        CK(ntt_launch_pass(NTT_CONTIG, p, polys.nseg(), kb, ctx->st));
-        ctx->launches++;
+        rc = launch_pass(ctx, NTT_CONTIG, p, polys.nseg(), kb);
     }
     wf_dev_free(ctx, yp);
-    return WF_OK;
+    return rc;
 }
 
 // =================================================================================================
@@ -854,6 +877,34 @@ int GatherBatch::add_opening(wf_ctx* ctx, const wf_tree* t, const std::vector<u6
     digs.emplace_back();
     digs.back().t = t;
     CKI(wf_open_plan(ctx, t->nleaves, pos.data(), pos.size(), digs.back().plan));
+    digs.back().idx = digs.back().plan.want;
+    *id = digs.size() - 1;
+    return WF_OK;
+}
+int GatherBatch::add_opening_sharded(wf_ctx* ctx, const wf_tree* t, size_t n_global, int world, int rank, const std::vector<u64>& pos,
+                                     size_t* id, std::vector<std::pair<size_t, u64>>* top_slots) {
+    digs.emplace_back();
+    DigJob& j = digs.back();
+    j.t = t;
+    CKI(wf_open_plan(ctx, n_global, pos.data(), pos.size(), j.plan));
+    const size_t n_local = n_global / (size_t)world;
+    u32 log_w = 0;
+    while ((1 << log_w) < world) log_w++;
+    j.idx.assign(j.plan.want.size(), ~(u64)0);
+    for (size_t s = 0; s < j.plan.want.size(); s++) {
+        const u64 e = j.plan.want[s];
+        if (e >= n_global) {  // leaf digest e - n
+            const u64 leaf = e - n_global;
+            if ((int)(leaf / n_local) == rank) j.idx[s] = n_local + leaf % n_local;
+        } else if (e < (u64)world) {  // node of the top log2(world) levels: held on the host by every rank
+            if (top_slots) top_slots->push_back({s, e});
+        } else {
+            u32 depth = 63 - (u32)__builtin_clzll(e);        // node e sits at depth `depth` (root = depth 0)
+            const u32 rel = depth - log_w;                     // depth inside its subtree
+            const u64 owner = (e >> rel) - (u64)world;
+            if ((int)owner == rank) j.idx[s] = ((u64)1 << rel) | (e & (((u64)1 << rel) - 1));
+        }
+    }
     *id = digs.size() - 1;
     return WF_OK;
 }
@@ -866,7 +917,7 @@ int GatherBatch::run(wf_ctx* ctx) {
     u64* h_idx = (u64*)ctx->pinned;
     u64* h_out = h_idx + idx_words;
     for (auto& j : rows) memcpy(h_idx + j.idx_off, j.pos.data(), j.pos.size() * 8);
-    for (auto& j : digs) memcpy(h_idx + j.idx_off, j.plan.want.data(), j.plan.want.size() * 8);
+    for (auto& j : digs) memcpy(h_idx + j.idx_off, j.idx.data(), j.idx.size() * 8);
     void *d_idx, *d_out;
     CKI(wf_dev_alloc(ctx, idx_words * 8, &d_idx));
     CKI(wf_dev_alloc(ctx, out_words * 8, &d_out));
@@ -880,6 +931,8 @@ int GatherBatch::run(wf_ctx* ctx) {
                                  (u64*)d_out + j.out_off, ctx->st));
         ctx->launches++;
     }
+    if (comm && comm->world > 1 && comm->all_reduce_sum(comm->user, d_out, out_words) != 0)
+        return wf_fail(ctx, WF_ERR_STATE, "all_reduce_sum callback failed");
     CK(cudaMemcpyAsync(h_out, d_out, out_words * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     wf_dev_free(ctx, d_idx);
@@ -909,6 +962,20 @@ int wf_tree_open_many(wf_ctx* ctx, const wf_tree* t, const uint64_t* positions, 
     return WF_OK;
 }
 
+}  // extern "C"
+// leaf digests of one FRI layer + the Merkle tree over them (fri/src/prover/mod.rs:202-222, :321-336); vals: `len`
+// evaluations of degree d, ld words apart, natural order
+int wf_fri_layer_tree(wf_ctx* ctx, int hash_id, const u64* vals, size_t len, int d, int ld, int nf, wf_tree** out) {
+    const size_t m = len / (size_t)nf;
+    wf_tree* t;
+    CKI(tree_alloc(ctx, hash_id, m, &t));
+    CK(fri_hash_layer(hash_id, vals, len, d, ld, nf, t->leaves, ctx->st));
+    CK(commit_merkle_nodes(hash_id, t->leaves, m, t->nodes, ctx->st));
+    ctx->launches += 1 + merkle_launches(m);
+    *out = t;
+    return WF_OK;
+}
+extern "C" {
 // ---- FRI ----------------------------------------------------------------------------------------
 int wf_fri_free(wf_ctx* ctx, wf_fri* f) {
     if (!f) return WF_OK;

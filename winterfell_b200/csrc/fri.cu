@@ -65,7 +65,9 @@ __host__ __device__ constexpr u32 cbrev(u32 v, int bits) {
 template <int D, int LOGNF>
 __global__ void __launch_bounds__(256) fri_fold_kernel(const u64* __restrict__ ev, size_t m, int ld, GlExt<D> alpha,
                                                        const u64* __restrict__ d_alpha, const u64* __restrict__ master,
-                                                       u32 logL, u64* __restrict__ next, int next_ld) {
+                                                       u32 logL, u64* __restrict__ next, int next_ld, size_t i0) {
+    // i0: index of this launch's first row in the (global) layer of 2^logL points; `ev` holds rows i0 .. i0 + m of each
+    // of the NF strided pieces back to back (the whole layer when i0 = 0 and m = 2^logL / NF)
     constexpr int NF = 1 << LOGNF;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(256) fri_fold_kernel(const u64* __restrict__ e
     for (int c = 0; c < D; c++) mini_dft<LOGNF>(x[c]);
     // x[c][pos] = F[bitrev(pos)], F = forward size-NF DFT; inverse coefficient j = F[(NF - j) % NF] / NF
     const u32 L = 1u << logL;
-    u32 e = (L - (u32)i) & (L - 1);
+    u32 e = (L - (u32)(i + i0)) & (L - 1);
     u64 winv = (e & (L >> 1)) ? gl_neg(master[e & ((L >> 1) - 1)]) : master[e & ((L >> 1) - 1)];
     u64 xinv = gl_mul(winv, 2635249152773512046ULL);  // 7^-1 mod p
     GlExt<D> beta = ext_mul_base(alpha, xinv);
@@ -119,29 +121,30 @@ cudaError_t fri_hash_layer(int hash_id, const u64* evals, size_t len, int d, int
 
 template <int D>
 static cudaError_t fold_dispatch(const u64* evals, size_t len, int ld, int nf, const u64* alpha, const u64* d_alpha,
-                                 const u64* master, u64* next, int next_ld, cudaStream_t st) {
+                                 const u64* master, u64* next, int next_ld, cudaStream_t st, size_t i0, u32 logL_global) {
     size_t m = len / nf;
     u32 logL = 0;
     while (((size_t)1 << logL) < len) logL++;
+    if (logL_global) logL = logL_global;
     GlExt<D> a;
     for (int c = 0; c < D; c++) a.v[c] = alpha ? alpha[c] : 0;
     unsigned blocks = (unsigned)((m + 255) / 256);
     switch (nf) {
-        case 2: fri_fold_kernel<D, 1><<<blocks, 256, 0, st>>>(evals, m, ld, a, d_alpha, master, logL, next, next_ld); break;
-        case 4: fri_fold_kernel<D, 2><<<blocks, 256, 0, st>>>(evals, m, ld, a, d_alpha, master, logL, next, next_ld); break;
-        case 8: fri_fold_kernel<D, 3><<<blocks, 256, 0, st>>>(evals, m, ld, a, d_alpha, master, logL, next, next_ld); break;
-        case 16: fri_fold_kernel<D, 4><<<blocks, 256, 0, st>>>(evals, m, ld, a, d_alpha, master, logL, next, next_ld); break;
+        case 2: fri_fold_kernel<D, 1><<<blocks, 256, 0, st>>>(evals, m, ld, a, d_alpha, master, logL, next, next_ld, i0); break;
+        case 4: fri_fold_kernel<D, 2><<<blocks, 256, 0, st>>>(evals, m, ld, a, d_alpha, master, logL, next, next_ld, i0); break;
+        case 8: fri_fold_kernel<D, 3><<<blocks, 256, 0, st>>>(evals, m, ld, a, d_alpha, master, logL, next, next_ld, i0); break;
+        case 16: fri_fold_kernel<D, 4><<<blocks, 256, 0, st>>>(evals, m, ld, a, d_alpha, master, logL, next, next_ld, i0); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
 cudaError_t fri_fold_layer(const u64* evals, size_t len, int d, int ld, int nf, const u64* alpha, const u64* master,
-                           u64* next, int next_ld, cudaStream_t st, const u64* d_alpha) {
+                           u64* next, int next_ld, cudaStream_t st, const u64* d_alpha, size_t i0, u32 logL_global) {
     switch (d) {
-        case 1: return fold_dispatch<1>(evals, len, ld, nf, alpha, d_alpha, master, next, next_ld, st);
-        case 2: return fold_dispatch<2>(evals, len, ld, nf, alpha, d_alpha, master, next, next_ld, st);
-        case 3: return fold_dispatch<3>(evals, len, ld, nf, alpha, d_alpha, master, next, next_ld, st);
+        case 1: return fold_dispatch<1>(evals, len, ld, nf, alpha, d_alpha, master, next, next_ld, st, i0, logL_global);
+        case 2: return fold_dispatch<2>(evals, len, ld, nf, alpha, d_alpha, master, next, next_ld, st, i0, logL_global);
+        case 3: return fold_dispatch<3>(evals, len, ld, nf, alpha, d_alpha, master, next, next_ld, st, i0, logL_global);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -31,6 +31,8 @@ struct wf_ctx {
     std::multimap<size_t, void*> pool;       // free device buffers by size
     std::map<void*, size_t> live;            // allocated device buffers
     std::map<u32, u64*> tw;                  // log_n -> w_n^i, i < n/2
+    std::map<u32, u64*> round_tw;            // logS -> round-twiddle table of the ntt2 plan
+    std::map<std::pair<u32, u32>, u64*> pow_tab;  // (log order, log count) -> w_(2^order)^i, i < 2^count
     std::map<std::pair<u32, u32>, LdeTables> lde_tabs;  // (log_n, log_blowup)
     void* pinned;                            // staging buffer (pinned host)
     size_t pinned_bytes;
@@ -104,6 +106,8 @@ struct wf_fri;
 int wf_fri_build_layers_coin(wf_ctx* ctx, int hash_id, const wf_mat* evals, int d, uint32_t folding, uint32_t rem_max_deg,
                              uint32_t blowup, PublicCoin& coin, std::vector<Digest>& commitments, wf_fri** out);
 int wf_get_twiddles(wf_ctx* ctx, u32 log_n, const u64** out);
+struct wf_tree;
+int wf_fri_layer_tree(wf_ctx* ctx, int hash_id, const u64* vals, size_t len, int d, int ld, int nf, wf_tree** out);
 struct OpenPlan {
     u32 depth;
     std::vector<u64> want;                       // < n: nodes[want]; >= n: leaves[want - n]
@@ -113,17 +117,25 @@ struct OpenPlan {
 int wf_open_plan(wf_ctx* ctx, size_t n, const uint64_t* positions, size_t k, OpenPlan& pl);
 void wf_open_finish(const OpenPlan& pl, const uint8_t* got, uint8_t* leaves_out, ByteVec& proof);
 // all row / digest gathers of one proof: one upload, one download, one synchronisation
+// Sharded proofs (wf_comm): every rank queues the SAME jobs; a row / digest this rank does not hold is queued with the
+// index ~0 (gathered as zero) and the gathered words are summed over the ranks before the download.
 struct GatherBatch {
     struct RowJob { SegMatrix m; std::vector<u64> pos; size_t idx_off, out_off; };
-    struct DigJob { const wf_tree* t; OpenPlan plan; size_t idx_off, out_off; };
+    struct DigJob { const wf_tree* t; OpenPlan plan; std::vector<u64> idx; size_t idx_off, out_off; };  // idx: indices into t (or ~0)
     std::vector<RowJob> rows;
     std::vector<DigJob> digs;
-    const u64* result = nullptr;  // pinned host buffer, valid until the next run()
+    const wf_comm* comm = nullptr;
+    u64* result = nullptr;  // pinned host buffer, valid until the next run()
     size_t add_rows(const SegMatrix& m, const std::vector<u64>& pos);
     int add_opening(wf_ctx* ctx, const wf_tree* t, const std::vector<u64>& pos, size_t* id);
+    // opening in a tree of n_global leaves stored as `world` local subtrees (this rank: `t`, n_global / world leaves):
+    // nodes above the subtree roots are not gathered (the caller patches them in from its host copy, see top_slots)
+    int add_opening_sharded(wf_ctx* ctx, const wf_tree* t, size_t n_global, int world, int rank, const std::vector<u64>& pos,
+                            size_t* id, std::vector<std::pair<size_t, u64>>* top_slots);
     int run(wf_ctx* ctx);
     const u64* row_result(size_t id) const { return result + rows[id].out_off; }
     const u8* digest_result(size_t id) const { return (const u8*)(result + digs[id].out_off); }
+    u64* digest_words(size_t id) { return result + digs[id].out_off; }
 };
 struct FriLayer {
     u64* evals;   // len x ld words (natural order)

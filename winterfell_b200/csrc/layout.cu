@@ -49,6 +49,7 @@ __global__ void gather_rows_kernel(SegMatrix src, const u64* __restrict__ pos, s
     size_t i = idx / src.cols;
     u32 col = (u32)(idx % src.cols);
     size_t row = pos[i];
+    if (row == ~(size_t)0) { dst[idx] = 0; return; }  // not held by this rank (sharded proof): another rank's words are summed in
     u64 v = src.base[(size_t)(col / src.W) * src.seg_stride + row * src.W + (col % src.W)];
     dst[idx] = mont ? gl_to_mont(v) : v;
 }
@@ -58,6 +59,7 @@ __global__ void gather_digests_kernel(const u64* __restrict__ nodes, const u64* 
     if (idx >= k * 4) return;
     size_t i = idx >> 2, w = idx & 3;
     u64 e = want[i];
+    if (e == ~(u64)0) { dst[idx] = 0; return; }       // not held by this rank
     dst[idx] = e < n ? nodes[e * 4 + w] : leaves[(e - n) * 4 + w];
 }
 // row r *= base^r. Each thread walks SCALE_ROWS rows spaced one block apart (coalesced), computing

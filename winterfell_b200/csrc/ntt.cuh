@@ -65,6 +65,11 @@ struct NttPassParams {
     u32 logM;
     u32 a_mul, b_mul;
     u32 batch0;                                // added to the batch index in the twiddle exponent
+    // ntt2 kernels (logS >= 6) read w_M^e as tw_hi[e >> tw_split] * tw_lo[e & (2^tw_split - 1)]: two tables of
+    // 2^(logM - tw_split) and 2^tw_split entries instead of a gather over M/2 entries
+    const u64 *tw_hi, *tw_lo;
+    u32 tw_split;
+    int vec_in, vec_out;                       // lane pairs are contiguous (16-byte aligned) in the input / output
     const u64* ctab;                           // optional per-column constant table
     u64 cconst;                                // constant factor (e.g. 1/n) folded into the post twiddle, or applied
                                                // alone at write-back when has_post == 0; 1 if unused
@@ -73,4 +78,11 @@ struct NttPassParams {
 enum { NTT_STRIDED = 0, NTT_CONTIG = 1 };
 
 size_t ntt_pass_smem_bytes(const NttPassParams& p);
+// small sub-transforms (logS < NTT2_MIN_LOGS): generic kernel of ntt.cu; sub_tw = half table w_S^i, master = half table w_M^i
 cudaError_t ntt_launch_pass(int mode, const NttPassParams& p, u32 n_segments, u32 n_batch, cudaStream_t st);
+// sub-transforms of 2^6 .. 2^11 points (ntt2.cu): sub_tw = the plan's round-twiddle table (ntt2_build_tw), post
+// twiddles through tw_hi / tw_lo
+#define NTT2_MIN_LOGS 6
+cudaError_t ntt2_launch_pass(int mode, const NttPassParams& p, u32 n_segments, u32 n_batch, cudaStream_t st);
+size_t ntt2_tw_entries(int logS);
+cudaError_t ntt2_build_tw(int logS, u64* d_out, cudaStream_t st);

@@ -25,6 +25,7 @@
 // examples/src/fibonacci/fib_small/air.rs:16-69 side by side (k = 1 is the reference example, k = 4 / 32
 // the 8- / 64-column configurations of BASELINE.json) has a specialised kernel.
 #include <algorithm>
+#include <chrono>
 
 #include "internal.hpp"
 #include "blake3.cuh"
@@ -48,50 +49,76 @@ struct FibEvalParams {
     SegMatrix lde;      // N x 2k trace LDE
     SegMatrix out;      // ce x D combined constraint evaluations
     u32 k, log_n, log_blowup, log_ce_blowup;
-    const u64* tcoef;   // [2k][D] transition coefficients
-    const u64* bcoef0;  // [2k][D] boundary coefficients, group (step 0): column q = value q/2 + 1
-    const u64* bcoef1;  // [k][D]  boundary coefficients, group (step n-1): column 2j+1 = results[j]
-    const u64* results; // [k]
+    const u64* coef;    // [k][5][D]: per pair j the coefficients of t0, t1 (transition), of column 2j and 2j+1 in the
+                        // step-0 boundary group, and of column 2j+1 in the last-step group
+    u64 K0[3], K1[3];   // constants of the two boundary groups: sum_q bcoef0_q * value_q, sum_j bcoef1_j * result_j
     const u64* tw_ce;   // w_ce^i, i < ce/2
     u64 zt[8];          // 1 / (x^n - 1) at CE step i mod ce_blowup
     u64 last;           // g_trace^(n-1): transition exemption point and divisor offset of group 1
+    // row-sharded evaluation (multi-GPU): this launch covers CE rows [row0, row0 + ce_rows); `lde` then holds the LDE
+    // rows of that range followed by `blowup` halo rows (the first rows of the next shard), so the next-state row is
+    // local row + blowup without wrap-around. ce_rows = 0: the whole domain.
+    size_t row0, ce_rows;
 };
 
 // CE-domain rows, FIB_ROWS per thread sharing one field inversion (evaluator/default.rs:165-214
-// evaluate_fragment_main + evaluation_table.rs:317-367 acc_column, fused).
-#define FIB_ROWS 4
+// evaluate_fragment_main + evaluation_table.rs:317-367 acc_column, fused). The three linear forms of a row
+// (transition combination, the two boundary groups) are dot products of base-field frame values with extension
+// coefficients: they run on delayed-reduction accumulators (GlAcc), one reduction per row and form instead of one per
+// term — the first version spent 22 k instructions per row of the 64-column cubic configuration in gl_mul / gl_add.
 template <int D>
 __global__ void __launch_bounds__(256) fib_constraints_kernel(FibEvalParams p) {
-    const size_t ce = (size_t)1 << (p.log_n + p.log_ce_blowup);
+    extern __shared__ __align__(16) u64 fsm[];
+    constexpr int ROWS = D == 3 ? 2 : 4;
+    for (u32 i = threadIdx.x; i < p.k * 5 * D; i += blockDim.x) fsm[i] = p.coef[i];
+    __syncthreads();
+    const size_t ce_all = (size_t)1 << (p.log_n + p.log_ce_blowup);
+    const size_t ce = p.ce_rows ? p.ce_rows : ce_all;   // rows of this launch
     const size_t N = (size_t)1 << (p.log_n + p.log_blowup);
     const u32 lde_shift = p.log_blowup - p.log_ce_blowup;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const u32 half = (u32)(ce >> 1);
-    GlExt<D> T[FIB_ROWS], B0[FIB_ROWS], B1[FIB_ROWS];
-    u64 d0[FIB_ROWS], d1[FIB_ROWS];
+    const u32 half = (u32)(ce_all >> 1);
+    const int W = p.lde.W;
+    GlExt<D> T[ROWS], B0[ROWS], B1[ROWS];
+    u64 d0[ROWS], d1[ROWS];
 #pragma unroll
-    for (int r = 0; r < FIB_ROWS; r++) {
-        const size_t i = tid + r * stride;
+    for (int r = 0; r < ROWS; r++) {
+        const size_t il = tid + r * stride;   // row of this launch
+        const size_t i = il + p.row0;         // row of the CE domain
         T[r] = ext_zero<D>(); B0[r] = ext_zero<D>(); B1[r] = ext_zero<D>();
         d0[r] = 1; d1[r] = 1;
-        if (i >= ce) continue;
-        const size_t ls = i << lde_shift;
-        const size_t nx = (ls + ((size_t)1 << p.log_blowup)) & (N - 1);  // trace_lde/default/mod.rs:169-180
-        auto pair_terms = [&](u32 j, u64 c0, u64 c1, u64 n0, u64 n1) {
-            u64 t0 = gl_sub(n0, gl_add(c0, c1));  // fib_small/air.rs:58
-            u64 t1 = gl_sub(n1, gl_add(c1, n0));  // :59
-            T[r] = ext_add(T[r], ext_mul_base(ld_ext<D>(p.tcoef + (size_t)(2 * j) * D), t0));
-            T[r] = ext_add(T[r], ext_mul_base(ld_ext<D>(p.tcoef + (size_t)(2 * j + 1) * D), t1));
-            u64 v = j + 1;
-            B0[r] = ext_add(B0[r], ext_mul_base(ld_ext<D>(p.bcoef0 + (size_t)(2 * j) * D), gl_sub(c0, v)));
-            B0[r] = ext_add(B0[r], ext_mul_base(ld_ext<D>(p.bcoef0 + (size_t)(2 * j + 1) * D), gl_sub(c1, v)));
-            B1[r] = ext_add(B1[r], ext_mul_base(ld_ext<D>(p.bcoef1 + (size_t)j * D), gl_sub(c1, p.results[j])));
-        };
-        // (16-byte vector loads of whole segment rows were tried here: neutral in the base field, 60 % slower
-        // with cubic coefficients — the staged rows cost registers the accumulators need)
-        for (u32 j = 0; j < p.k; j++)
-            pair_terms(j, seg_at(p.lde, ls, 2 * j), seg_at(p.lde, ls, 2 * j + 1), seg_at(p.lde, nx, 2 * j), seg_at(p.lde, nx, 2 * j + 1));
+        if (il >= ce) continue;
+        const size_t ls = il << lde_shift;
+        const size_t nx = p.ce_rows ? ls + ((size_t)1 << p.log_blowup)
+                                    : ((ls + ((size_t)1 << p.log_blowup)) & (N - 1));  // trace_lde/default/mod.rs:169-180
+        GlAcc aT[D], a0[D], a1[D];
+#pragma unroll
+        for (int q = 0; q < D; q++) { aT[q] = acc_zero(); a0[q] = acc_zero(); a1[q] = acc_zero(); }
+#pragma unroll 2
+        for (u32 j = 0; j < p.k; j++) {
+            // columns 2j, 2j+1 are adjacent words of one segment row: one 16-byte load per frame row
+            const size_t off = (size_t)((2 * j) / W) * p.lde.seg_stride + (2 * j) % W;
+            const ulonglong2 cur = __ldg(reinterpret_cast<const ulonglong2*>(p.lde.base + off + ls * W));
+            const ulonglong2 nxt = __ldg(reinterpret_cast<const ulonglong2*>(p.lde.base + off + nx * W));
+            const u64 t0 = gl_sub(nxt.x, gl_add(cur.x, cur.y));  // fib_small/air.rs:58
+            const u64 t1 = gl_sub(nxt.y, gl_add(cur.y, nxt.x));  // :59
+            const u64* cf = fsm + (size_t)j * 5 * D;
+#pragma unroll
+            for (int q = 0; q < D; q++) {
+                acc_mad(aT[q], cf[q], t0);
+                acc_mad(aT[q], cf[D + q], t1);
+                acc_mad(a0[q], cf[2 * D + q], cur.x);
+                acc_mad(a0[q], cf[3 * D + q], cur.y);
+                acc_mad(a1[q], cf[4 * D + q], cur.y);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < D; q++) {
+            T[r].v[q] = acc_reduce(aT[q]);
+            B0[r].v[q] = gl_sub(acc_reduce(a0[q]), p.K0[q]);
+            B1[r].v[q] = gl_sub(acc_reduce(a1[q]), p.K1[q]);
+        }
         u64 w = p.tw_ce[i & (half - 1)];
         if (i & half) w = gl_neg(w);
         u64 x = gl_mul(w, GL_GENERATOR);  // domain.rs:123 get_ce_x_at
@@ -99,20 +126,20 @@ __global__ void __launch_bounds__(256) fib_constraints_kernel(FibEvalParams p) {
         d1[r] = gl_sub(x, p.last);        // boundary divisor of the last-step group = transition exemption
     }
     // batch inversion of the products d0*d1 (never zero: x lies on the coset 7<w>, 1 and g^(n-1) do not)
-    u64 prod[FIB_ROWS], pre[FIB_ROWS], run = 1;
+    u64 prod[ROWS], pre[ROWS], run = 1;
 #pragma unroll
-    for (int r = 0; r < FIB_ROWS; r++) { prod[r] = gl_mul(d0[r], d1[r]); pre[r] = run; run = gl_mul(run, prod[r]); }
+    for (int r = 0; r < ROWS; r++) { prod[r] = gl_mul(d0[r], d1[r]); pre[r] = run; run = gl_mul(run, prod[r]); }
     run = gl_inv(run);
 #pragma unroll
-    for (int r = FIB_ROWS - 1; r >= 0; r--) { u64 inv = gl_mul(run, pre[r]); run = gl_mul(run, prod[r]); prod[r] = inv; }
+    for (int r = ROWS - 1; r >= 0; r--) { u64 inv = gl_mul(run, pre[r]); run = gl_mul(run, prod[r]); prod[r] = inv; }
 #pragma unroll
-    for (int r = 0; r < FIB_ROWS; r++) {
-        const size_t i = tid + r * stride;
-        if (i >= ce) continue;
+    for (int r = 0; r < ROWS; r++) {
+        const size_t il = tid + r * stride, i = il + p.row0;
+        if (il >= ce) continue;
         u64 z0 = gl_mul(prod[r], d1[r]), z1 = gl_mul(prod[r], d0[r]);                   // 1/(x - 1), 1/(x - g^(n-1))
         u64 zt = gl_mul(p.zt[i & (((size_t)1 << p.log_ce_blowup) - 1)], d1[r]);         // e(x) / (x^n - 1)
         GlExt<D> acc = ext_add(ext_add(ext_mul_base(T[r], zt), ext_mul_base(B0[r], z0)), ext_mul_base(B1[r], z1));
-        u64* o = p.out.base + i * p.out.W;
+        u64* o = p.out.base + il * p.out.W;
 #pragma unroll
         for (int q = 0; q < D; q++) o[q] = acc.v[q];
     }
@@ -270,73 +297,89 @@ __global__ void comp_split_kernel(SegMatrix coefs, size_t n, u32 kc, int D, SegM
     out.base[(size_t)(col / out.W) * out.seg_stride + i * out.W + (col % out.W)] = v;
 }
 
-// Horner evaluation of every base-coefficient column at TWO extension points (z and z*g), as
-// per-chunk partial sums (polynom::eval, math/src/polynom/mod.rs:55-62; ColMatrix::evaluate_columns_at
-// :245; TracePolyTable::get_ood_frame poly_table.rs:68-76). Block = 256 threads x OOD_PER_THREAD
-// coefficients of one segment; partial[col][chunk][point] = sum_{m in chunk} a_m z^m.
-#define OOD_PER_THREAD 16
+// Evaluation of every base-coefficient column at TWO extension points (z and z*g), as per-block partial sums
+// (polynom::eval, math/src/polynom/mod.rs:55-62; ColMatrix::evaluate_columns_at :245; TracePolyTable::get_ood_frame
+// poly_table.rs:68-76). Block = 32 row groups x 8 lanes (lane = column of the segment); a thread owns OOD_RPT
+// consecutive coefficients of ONE column and accumulates sum_r a_r z^r for both points on delayed-reduction
+// accumulators against a shared table of z^r (one base-by-extension product per coefficient and point, no reduction
+// inside the loop); the row-group power (z^OOD_RPT)^rg and the block power z^(first row of the block) — the latter
+// from a table filled by ood_pow_kernel, an ext_pow per thread there instead of per coefficient chunk here — are
+// applied once per thread / once per block. partial[col][chunk][point] = sum_{m in chunk} a_m z^m.
+#define OOD_RPT 64
+#define OOD_ROWS_PER_BLOCK (32 * OOD_RPT)
 template <int D>
-__global__ void __launch_bounds__(256) ood_partial_kernel(SegMatrix polys, GlExt<D> z0, GlExt<D> z1,
+__global__ void ood_pow_kernel(GlExt<D> z0, GlExt<D> z1, u32 chunks, u64* zb /*[2][chunks][D]*/) {
+    const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 2 * chunks) return;
+    const u32 pt = idx / chunks, c = idx % chunks;
+    const GlExt<D> v = ext_pow(pt ? z1 : z0, (u64)c * OOD_ROWS_PER_BLOCK);
+#pragma unroll
+    for (int d = 0; d < D; d++) zb[(size_t)idx * D + d] = v.v[d];
+}
+template <int D>
+__global__ void __launch_bounds__(256) ood_partial_kernel(SegMatrix polys, GlExt<D> z0, GlExt<D> z1, const u64* zb,
                                                           u64* partial /*[cols][chunks][2][D]*/, u32 chunks) {
     const u32 g = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
     const int W = polys.W;
     const size_t n = polys.rows;
-    const size_t start = ((size_t)chunk * 256 + t) * OOD_PER_THREAD;
     const u64* base = polys.base + (size_t)g * polys.seg_stride;
-    __shared__ u64 red[2][8][8][D];
-    // z^r, r < OOD_PER_THREAD, for both points: a coefficient then costs one base-by-extension product per
-    // point (D multiplications) instead of the D^2 of a Horner step, and is loaded once for both points
-    __shared__ u64 zpow[2][OOD_PER_THREAD][D];
-    if (t < 2 * OOD_PER_THREAD) {
-        GlExt<D> v = ext_pow(t < OOD_PER_THREAD ? z0 : z1, t % OOD_PER_THREAD);
+    __shared__ u64 zpow[2][OOD_RPT][D];   // z^r
+    __shared__ u64 zrg[2][32][D];         // z^(OOD_RPT * rg)
+    __shared__ u64 red[2][32][8][D];
+    if (t < 2 * OOD_RPT) {
+        const GlExt<D> v = ext_pow(t < OOD_RPT ? z0 : z1, t % OOD_RPT);
 #pragma unroll
-        for (int c = 0; c < D; c++) zpow[t / OOD_PER_THREAD][t % OOD_PER_THREAD][c] = v.v[c];
+        for (int d = 0; d < D; d++) zpow[t / OOD_RPT][t % OOD_RPT][d] = v.v[d];
+    } else if (t < 2 * OOD_RPT + 64) {
+        const u32 u = t - 2 * OOD_RPT, pt = u / 32, rg = u % 32;
+        const GlExt<D> v = ext_pow(pt ? z1 : z0, (u64)rg * OOD_RPT);
+#pragma unroll
+        for (int d = 0; d < D; d++) zrg[pt][rg][d] = v.v[d];
     }
     __syncthreads();
-    GlExt<D> acc[2][8];
+    const u32 rg = t >> 3, lane = t & 7;
+    const size_t start = (size_t)chunk * OOD_ROWS_PER_BLOCK + (size_t)rg * OOD_RPT;
+    GlAcc acc[2][D];
 #pragma unroll
-    for (int q = 0; q < 8; q++) { acc[0][q] = ext_zero<D>(); acc[1][q] = ext_zero<D>(); }
-    for (int r = 0; r < OOD_PER_THREAD; r++) {
-        size_t row = start + r;
-        if (row >= n) break;
-        const GlExt<D> p0 = ld_ext<D>(&zpow[0][r][0]), p1 = ld_ext<D>(&zpow[1][r][0]);
+    for (int pt = 0; pt < 2; pt++)
 #pragma unroll
-        for (int q = 0; q < 8; q++) {  // fully unrolled with a guard: acc[][] must stay in registers
-            if (q < W) {
-                const u64 cf = base[row * W + q];
-                acc[0][q] = ext_add(acc[0][q], ext_mul_base(p0, cf));
-                acc[1][q] = ext_add(acc[1][q], ext_mul_base(p1, cf));
+        for (int d = 0; d < D; d++) acc[pt][d] = acc_zero();
+    if (lane < (u32)W) {
+        const u64* src = base + start * W + lane;
+#pragma unroll 1
+        for (int r0 = 0; r0 < OOD_RPT; r0 += 8) {
+            u64 cf[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) cf[k] = (start + r0 + k < n) ? __ldg(src + (size_t)(r0 + k) * W) : 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+#pragma unroll
+                for (int d = 0; d < D; d++) {
+                    acc_mad(acc[0][d], zpow[0][r0 + k][d], cf[k]);
+                    acc_mad(acc[1][d], zpow[1][r0 + k][d], cf[k]);
+                }
             }
         }
     }
 #pragma unroll
     for (int pt = 0; pt < 2; pt++) {
-        GlExt<D> zp = ext_pow(pt == 0 ? z0 : z1, start);  // z^(first row of this thread)
+        GlExt<D> v;
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            if (q >= W) break;
-            GlExt<D> v = ext_mul(acc[pt][q], zp);
+        for (int d = 0; d < D; d++) v.v[d] = acc_reduce(acc[pt][d]);
+        v = ext_mul(v, ld_ext<D>(&zrg[pt][rg][0]));
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-                for (int c = 0; c < D; c++) v.v[c] = gl_add(v.v[c], __shfl_down_sync(0xffffffffu, v.v[c], off));
-            }
-            if ((t & 31) == 0) {
-#pragma unroll
-                for (int c = 0; c < D; c++) red[pt][t >> 5][q][c] = v.v[c];
-            }
-        }
+        for (int d = 0; d < D; d++) red[pt][rg][lane][d] = v.v[d];
     }
     __syncthreads();
-    if (t < (u32)(2 * W)) {
-        const u32 pt = t / W, q = t % W;
-        u32 col = g * W + q;
-        if (col < polys.cols) {
-            GlExt<D> s = ext_zero<D>();
-            for (int wp = 0; wp < 8; wp++) s = ext_add(s, ld_ext<D>(&red[pt][wp][q][0]));
+    if (t < 16) {
+        const u32 pt = t >> 3, q = t & 7, col = g * W + q;
+        if (q < (u32)W && col < polys.cols) {
+            GlExt<D> sacc = ext_zero<D>();
+            for (int k = 0; k < 32; k++) sacc = ext_add(sacc, ld_ext<D>(&red[pt][k][q][0]));
+            sacc = ext_mul(sacc, ld_ext<D>(zb + ((size_t)pt * chunks + chunk) * D));
             u64* o = partial + (((size_t)col * chunks + chunk) * 2 + pt) * D;
 #pragma unroll
-            for (int c = 0; c < D; c++) o[c] = s.v[c];
+            for (int d = 0; d < D; d++) o[d] = sacc.v[d];
         }
     }
 }
@@ -360,6 +403,7 @@ struct DeepParams {
     const u64* tcc;    // [c][D]  DEEP coefficients for trace columns
     const u64* ccc;    // [kc][D] DEEP coefficients for composition columns
     const u64* tw_N;   // w_N^i, i < N/2
+    size_t row0, nrows;  // row-sharded launch: rows [row0, row0 + nrows) of the LDE domain (nrows = 0: all N rows)
 };
 // DeepCompositionPoly in evaluation form, two kernels:
 //   deep_sum_kernel: S(x) = sum_j cc_j T_j(x) + sum_j cc'_j A_j(x) + sum_j cc''_j H_j(x) for every LDE row — the
@@ -381,10 +425,14 @@ __global__ void __launch_bounds__(DEEP_SUM_THREADS) deep_sum_kernel(DeepParams p
     for (u32 i = threadIdx.x; i < p.aw * D; i += DEEP_SUM_THREADS) s_a[i] = p.acc[i];
     for (u32 i = threadIdx.x; i < p.kc * D; i += DEEP_SUM_THREADS) s_c[i] = p.ccc[i];
     __syncthreads();
-    const size_t N = (size_t)1 << p.log_N;
+    const size_t N = p.nrows ? p.nrows : ((size_t)1 << p.log_N);   // rows of this launch
     const size_t row = (size_t)blockIdx.x * DEEP_SUM_THREADS + threadIdx.x;
     if (row >= N) return;
-    GlExt<D> S = ext_zero<D>();
+    // S over the base-field trace columns = D dot products of the row with the coefficient components: delayed-reduction
+    // accumulators, one reduction per component per row
+    GlAcc acc[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) acc[d] = acc_zero();
     if (p.trace.W == 8) {
         for (u32 g = 0; g * 8 < p.c; g++) {  // one 64-byte segment row = four 16-byte loads
             const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(p.trace.base + (size_t)g * p.trace.seg_stride + row * 8);
@@ -394,12 +442,22 @@ __global__ void __launch_bounds__(DEEP_SUM_THREADS) deep_sum_kernel(DeepParams p
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 u32 j = g * 8 + q;
-                if (j < p.c) S = ext_add(S, ext_mul_base(ld_ext<D>(s_t + (size_t)j * D), v[q]));
+                if (j < p.c) {
+#pragma unroll
+                    for (int d = 0; d < D; d++) acc_mad(acc[d], s_t[(size_t)j * D + d], v[q]);
+                }
             }
         }
     } else {
-        for (u32 j = 0; j < p.c; j++) S = ext_add(S, ext_mul_base(ld_ext<D>(s_t + (size_t)j * D), seg_at(p.trace, row, j)));
+        for (u32 j = 0; j < p.c; j++) {
+            const u64 v = seg_at(p.trace, row, j);
+#pragma unroll
+            for (int d = 0; d < D; d++) acc_mad(acc[d], s_t[(size_t)j * D + d], v);
+        }
     }
+    GlExt<D> S;
+#pragma unroll
+    for (int d = 0; d < D; d++) S.v[d] = acc_reduce(acc[d]);
     for (u32 j = 0; j < p.aw; j++) {
         GlExt<D> av;
 #pragma unroll
@@ -433,20 +491,21 @@ __global__ void __launch_bounds__(DEEP_SUM_THREADS) deep_sum_kernel(DeepParams p
 #define DEEP_ROWS (D == 1 ? DEEP_ROWS1 : (D == 2 ? DEEP_ROWS2 : DEEP_ROWS3))
 template <int D>
 __global__ void __launch_bounds__(256, DEEP_DIV_MINB) deep_div_kernel(DeepParams p, GlExt<D> z, GlExt<D> zg, GlExt<D> Sz, GlExt<D> Szg) {
-    const size_t N = (size_t)1 << p.log_N;
+    const size_t N = p.nrows ? p.nrows : ((size_t)1 << p.log_N);   // rows of this launch
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     constexpr int ROWS = DEEP_ROWS;
     GlExt<D> den[2 * ROWS];
-    const u32 half = (u32)(N >> 1);
+    const u32 half = (u32)(((size_t)1 << p.log_N) >> 1);
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
         size_t row = tid + r * stride;
         den[2 * r] = ext_from_base<D>(1);
         den[2 * r + 1] = ext_from_base<D>(1);
         if (row >= N) continue;
-        u64 w = p.tw_N[row & (half - 1)];
-        if (row & half) w = gl_neg(w);
+        const size_t grow = row + p.row0;   // row of the LDE domain
+        u64 w = p.tw_N[grow & (half - 1)];
+        if (grow & half) w = gl_neg(w);
         GlExt<D> x = ext_from_base<D>(gl_mul(w, GL_GENERATOR));
         den[2 * r] = ext_sub(x, z);
         den[2 * r + 1] = ext_sub(x, zg);
@@ -762,14 +821,17 @@ int ood_eval(wf_ctx* ctx, const std::vector<const wf_mat*>& mats, const GlExt<D>
     out.assign(2 * nm, {});
     CKI(wf_dev_alloc(ctx, total_cols * 2 * D * 8, &res));
     size_t off = 0;
+    std::vector<void*> zbs(nm, nullptr);
     for (int m = 0; m < nm; m++) {
         const size_t n = mats[m]->m.rows;
-        const u32 chunks = (u32)((n + 256 * OOD_PER_THREAD - 1) / (256 * OOD_PER_THREAD));
+        const u32 chunks = (u32)((n + OOD_ROWS_PER_BLOCK - 1) / OOD_ROWS_PER_BLOCK);
         const u32 cols = mats[m]->m.cols;
         CKI(wf_dev_alloc(ctx, (size_t)cols * chunks * 2 * D * 8, &part[m]));
-        ood_partial_kernel<D><<<dim3(chunks, mats[m]->m.nseg()), 256, 0, ctx->st>>>(mats[m]->m, z0, z1, (u64*)part[m], chunks);
+        CKI(wf_dev_alloc(ctx, (size_t)2 * chunks * D * 8, &zbs[m]));
+        ood_pow_kernel<D><<<(2 * chunks + 127) / 128, 128, 0, ctx->st>>>(z0, z1, chunks, (u64*)zbs[m]);
+        ood_partial_kernel<D><<<dim3(chunks, mats[m]->m.nseg()), 256, 0, ctx->st>>>(mats[m]->m, z0, z1, (const u64*)zbs[m], (u64*)part[m], chunks);
         ood_reduce_kernel<D><<<(2 * cols + 63) / 64, 64, 0, ctx->st>>>((const u64*)part[m], cols, chunks, (u64*)res + off);
-        ctx->launches += 2;
+        ctx->launches += 3;
         CK(cudaGetLastError());
         off += (size_t)cols * 2 * D;
     }
@@ -777,6 +839,7 @@ int ood_eval(wf_ctx* ctx, const std::vector<const wf_mat*>& mats, const GlExt<D>
     CK(cudaMemcpyAsync(host.data(), res, host.size() * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     for (void* pp : part) wf_dev_free(ctx, pp);
+    for (void* pp : zbs) wf_dev_free(ctx, pp);
     wf_dev_free(ctx, res);
     off = 0;
     for (int m = 0; m < nm; m++) {
@@ -877,14 +940,17 @@ static int sequence_table(wf_ctx* ctx, const u64* values, size_t L, u32 words_pe
 // cc: main transition, aux transition, main assertions, aux assertions (sorted order).
 template <int D>
 int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const wf_mat* alde, const std::vector<GlExt<D>>& cc,
-                     const std::vector<u64>& rnd_flat, u32 log_n, u32 log_b, wf_mat** out) {
+                     const std::vector<u64>& rnd_flat, u32 log_n, u32 log_b, wf_mat** out, size_t row0 = 0, size_t ce_rows = 0) {
+    // ce_rows != 0: row-sharded call — CE rows [row0, row0 + ce_rows) only; `lde` then holds the LDE rows of that range
+    // followed by `blowup` halo rows (FibEvalParams::row0)
     const size_t n = (size_t)1 << log_n;
     const u32 c = air.w, aw = air.aw, log_ceb = air.log_ce_blowup();
     const u32 n_atr = (u32)air.aux_degrees.size(), n_mtr = (u32)air.degrees.size(), n_mas = (u32)air.asserts.size();
     const u32 n_tr = n_mtr + n_atr;
     const size_t ce = n << log_ceb;
+    if (ce_rows && !air.is_fib) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "row-sharded constraint evaluation covers the FibSmall family");
     wf_mat* comp;
-    CKI(wf_mat_alloc(ctx, ce, D, &comp));
+    CKI(wf_mat_alloc(ctx, ce_rows ? ce_rows : ce, D, &comp));
     if (comp->m.W > D) CK(cudaMemsetAsync(comp->m.base, 0, comp->m.words() * 8, ctx->st));
     const u64 g_tr = gl_root_of_unity(log_n);
     std::vector<u64> zt((size_t)1 << log_ceb);  // ce_blowup <= blowup <= 128 entries
@@ -911,21 +977,33 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
         // boundary coefficients follow the assertions sorted by (stride, first_step, column)
         // (air/src/air/assertions/mod.rs:301-315): 2k assertions at step 0, then k at step n-1
         const u32 k = air.fib_k;
-        void *d_tc = nullptr, *d_b0 = nullptr, *d_b1 = nullptr, *d_res = nullptr;
-        auto f0 = flat(0, n_tr), f1 = flat(n_tr, 2 * k), f2 = flat(n_tr + 2 * k, k);
-        CKI(upload(f0.data(), f0.size() * 8, &d_tc));
-        CKI(upload(f1.data(), f1.size() * 8, &d_b0));
-        CKI(upload(f2.data(), f2.size() * 8, &d_b1));
-        CKI(upload(air.fib_results.data(), k * 8, &d_res));
+        void* d_cf = nullptr;
+        std::vector<u64> cf((size_t)k * 5 * D);
+        GlExt<D> K0 = ext_zero<D>(), K1 = ext_zero<D>();
+        for (u32 j = 0; j < k; j++) {
+            const GlExt<D>&tc0 = cc[2 * j], &tc1 = cc[2 * j + 1], &b0a = cc[n_tr + 2 * j], &b0b = cc[n_tr + 2 * j + 1], &b1 = cc[n_tr + 2 * k + j];
+            for (int q = 0; q < D; q++) {
+                u64* o = &cf[(size_t)j * 5 * D];
+                o[q] = tc0.v[q]; o[D + q] = tc1.v[q]; o[2 * D + q] = b0a.v[q]; o[3 * D + q] = b0b.v[q]; o[4 * D + q] = b1.v[q];
+            }
+            // asserted values: columns 2j and 2j+1 start at j + 1, column 2j+1 ends at results[j] (fib_air_host)
+            K0 = ext_add(K0, ext_mul_base(ext_add(b0a, b0b), (u64)(j + 1)));
+            K1 = ext_add(K1, ext_mul_base(b1, air.fib_results[j]));
+        }
+        CKI(upload(cf.data(), cf.size() * 8, &d_cf));
         FibEvalParams p;
+        memset(&p, 0, sizeof(p));
         p.lde = lde->m; p.out = comp->m; p.k = k; p.log_n = log_n; p.log_blowup = log_b; p.log_ce_blowup = log_ceb;
-        p.tcoef = (u64*)d_tc; p.bcoef0 = (u64*)d_b0; p.bcoef1 = (u64*)d_b1; p.results = (u64*)d_res;
+        p.coef = (const u64*)d_cf;
+        for (int q = 0; q < D; q++) { p.K0[q] = K0.v[q]; p.K1[q] = K1.v[q]; }
         CKI(wf_get_twiddles(ctx, log_n + log_ceb, &p.tw_ce));
         p.last = gl_pow(g_tr, n - 1);
         if (log_ceb > 3) return wf_fail(ctx, WF_ERR_STATE, "FibSmall has degree-1 constraints");  // FibEvalParams::zt[8]
         for (u32 i = 0; i < (1u << log_ceb); i++) p.zt[i] = zt[i];
-        size_t threads = (ce + FIB_ROWS - 1) / FIB_ROWS;
-        fib_constraints_kernel<D><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->st>>>(p);
+        p.row0 = row0; p.ce_rows = ce_rows;
+        const size_t rows_per_thread = D == 3 ? 2 : 4;
+        size_t threads = ((ce_rows ? ce_rows : ce) + rows_per_thread - 1) / rows_per_thread;
+        fib_constraints_kernel<D><<<(unsigned)((threads + 255) / 256), 256, cf.size() * 8, ctx->st>>>(p);
         ctx->launches++;
         CK(cudaGetLastError());
     } else {
@@ -1068,7 +1146,7 @@ int composition_commit(wf_ctx* ctx, int h, const wf_mat* comp, u32 log_n, u32 lo
     wf_mark(ctx, "composition_interpolate");
     CKI(wf_mat_lde(ctx, cpolys, log_b, &clde));
     wf_mark(ctx, "composition_lde");
-    CKI(wf_commit_rows(ctx, h, clde, tree_out));
+    if (tree_out) CKI(wf_commit_rows(ctx, h, clde, tree_out));  // sharded proofs commit their own row range
     *polys_out = cpolys;
     *lde_out = clde;
     return WF_OK;
@@ -1079,9 +1157,10 @@ int composition_commit(wf_ctx* ctx, int h, const wf_mat* comp, u32 log_n, u32 lo
 template <int D>
 int deep_compose(wf_ctx* ctx, const wf_mat* lde, const wf_mat* alde, const wf_mat* clde, u32 kc, u32 log_N,
                  const std::vector<GlExt<D>>& dc, const GlExt<D>& z, const GlExt<D>& zg, const GlExt<D>& Sz, const GlExt<D>& Szg,
-                 wf_mat** out) {
+                 wf_mat** out, size_t row0 = 0, size_t nrows = 0) {
+    // nrows != 0: row-sharded call — the matrices hold LDE rows [row0, row0 + nrows) only
     const u32 c = lde->m.cols, aw = alde ? alde->m.cols / D : 0, ct = c + aw;
-    const size_t N = (size_t)1 << log_N;
+    const size_t N = nrows ? nrows : ((size_t)1 << log_N);
     u64 *d_dt, *d_dq, *d_da;
     CKI(upload_ext<D>(ctx, dc, 0, ct + kc, &d_dt));  // one upload (one synchronisation) for all coefficients
     d_da = d_dt + (size_t)c * D;
@@ -1091,6 +1170,7 @@ int deep_compose(wf_ctx* ctx, const wf_mat* lde, const wf_mat* alde, const wf_ma
     if (deep->m.W > D) CK(cudaMemsetAsync(deep->m.base, 0, deep->m.words() * 8, ctx->st));
     DeepParams p;
     p.trace = lde->m; p.cons = clde->m; p.out = deep->m; p.c = c; p.kc = kc; p.log_N = log_N;
+    p.row0 = row0; p.nrows = nrows;
     p.tcc = d_dt; p.ccc = d_dq; p.acc = d_da; p.aw = aw;
     p.aux = aw ? alde->m : lde->m;
     CKI(wf_get_twiddles(ctx, log_N, &p.tw_N));
@@ -1317,6 +1397,415 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     return WF_OK;
 }
 
+// =================================================================================================
+// One proof sharded over several GPUs (include/winterfell_b200.h: wf_comm, wf_prove_fib_sharded)
+// =================================================================================================
+struct ShardCtx {
+    wf_ctx* ctx;
+    const wf_comm* cm;
+    int G, r;
+    u32 logG;
+    double bytes_sent = 0, ncoll = 0, ms_small = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;  // around every exchange, on the ctx stream
+    ~ShardCtx() { for (auto& e : ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } }
+    // send[i] -> rank sp[i], recv[i] <- rank rp[i], all `bytes` long; entries naming this rank are not allowed
+    int exchange(const std::vector<int>& sp, const std::vector<const void*>& sv, const std::vector<int>& rp, const std::vector<void*>& rv,
+                 size_t bytes) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        ev.push_back({a, b});
+        CK(cudaEventRecord(a, ctx->st));
+        if (cm->exchange(cm->user, sp.size(), sp.data(), sv.data(), rp.size(), rp.data(), rv.data(), bytes) != 0)
+            return wf_fail(ctx, WF_ERR_STATE, "exchange callback failed");
+        CK(cudaEventRecord(b, ctx->st));
+        bytes_sent += (double)bytes * (double)sp.size();
+        ncoll += 1;
+        return WF_OK;
+    }
+    // every rank contributes `bytes` device bytes at `mine`; all[q * bytes ..] receives rank q's (all-gather over exchange)
+    int all_gather_dev(const void* mine, void* all, size_t bytes) {
+        std::vector<int> sp, rp;
+        std::vector<const void*> sv;
+        std::vector<void*> rv;
+        for (int q = 0; q < G; q++) {
+            if (q == r) continue;
+            sp.push_back(q); sv.push_back(mine);
+            rp.push_back(q); rv.push_back((u8*)all + (size_t)q * bytes);
+        }
+        if ((const u8*)mine != (u8*)all + (size_t)r * bytes)
+            CK(cudaMemcpyAsync((u8*)all + (size_t)r * bytes, mine, bytes, cudaMemcpyDeviceToDevice, ctx->st));
+        return exchange(sp, sv, rp, rv, bytes);
+    }
+    int gather_host(const void* send, void* recv, size_t bytes) {
+        cudaEvent_t a, b;  // host-side wall time is what this costs (the stream is already drained by the caller)
+        (void)a; (void)b;
+        const auto t0 = std::chrono::steady_clock::now();
+        if (cm->all_gather_host(cm->user, send, recv, bytes) != 0) return wf_fail(ctx, WF_ERR_STATE, "all_gather_host callback failed");
+        ms_small += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        ncoll += 1;
+        return WF_OK;
+    }
+    double exchange_ms() {
+        double t = 0;
+        for (auto& e : ev) { float ms = 0; if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) t += ms; }
+        return t;
+    }
+};
+
+// A Merkle tree of n_global leaves held as one subtree per rank (this rank's: `local`) plus the top log2(G) levels,
+// recomputed on every rank from the all-gathered subtree roots: exactly the reference's heap (crypto/src/merkle/mod.rs:
+// 344-368) because rank r's leaves [r n/G, (r+1) n/G) are the leaves of node G + r.
+struct ShardTree {
+    wf_tree* local = nullptr;
+    size_t n_global = 0;
+    std::vector<Digest> top;  // [1, G): internal nodes; [G, 2G): subtree roots
+};
+static int shard_tree_finish(ShardCtx& sc, int h, ShardTree& t, Digest* root) {
+    wf_ctx* ctx = sc.ctx;
+    Digest mine;
+    CKI(wf_tree_root(ctx, t.local, mine.b));
+    std::vector<Digest> all(sc.G);
+    CKI(sc.gather_host(mine.b, all.data(), 32));
+    t.top.assign(2 * sc.G, Digest{});
+    for (int q = 0; q < sc.G; q++) t.top[sc.G + q] = all[q];
+    for (int i = sc.G - 1; i >= 1; i--) t.top[i] = hh_merge(h, t.top[2 * i], t.top[2 * i + 1]);
+    *root = t.top[1];
+    return WF_OK;
+}
+
+template <int D>
+int prove_fib_sharded(wf_ctx* ctx, const wf_comm* cm, const uint64_t* const* local_cols, const uint64_t* d_local, int mont, u32 k,
+                      u32 log_n, const u64* results, const Options& o, std::vector<u8>& proof_out, double* stats) {
+    ShardCtx sc{ctx, cm, cm->world, cm->rank, 0};
+    const int G = sc.G, r = sc.r;
+    while ((1 << sc.logG) < G) sc.logG++;
+    const int h = o.hash_id;
+    const size_t n = (size_t)1 << log_n;
+    u32 log_b = 0;
+    while ((1u << log_b) < o.blowup) log_b++;
+    const size_t N = n << log_b, b = o.blowup;
+    const u32 c = 2 * k, cl = c / (u32)G, nsl = cl / 8, nsg = c / 8;
+    const size_t rows_per = N / (size_t)G;
+    if (G < 2 || (G & (G - 1)) || r < 0 || r >= G) return wf_fail(ctx, WF_ERR_INVALID, "world size must be a power of two >= 2");
+    if (c % (u32)G || cl % 8) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "each rank must own whole 8-column segments (2k / world a multiple of 8)");
+    const AirHost air = fib_air_host(k, n, results);
+    const u32 kc = air.num_comp_cols(n), log_ceb = air.log_ce_blowup();
+    const size_t ce = n << log_ceb, ce_per = ce / (size_t)G;
+    if (rows_per < 64 * b || ce_per < 64) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "trace too short to shard over %d ranks", G);
+    const u32 n_tr = (u32)air.degrees.size(), n_as = (u32)air.asserts.size();
+    std::vector<u64> seed = {(u64)c << 8, (u64)n, 1, 0xFFFFFFFFULL, (u64)(n_tr + n_as),
+                             ((u64)o.ext << 24) | ((u64)o.folding << 16) | ((u64)o.rem_max_deg << 8) | o.blowup,
+                             o.grinding, o.num_queries};
+    for (u64 v : air.pub_inputs) seed.push_back(v);
+    Channel<D> ch(h, seed);  // every rank replays the whole transcript
+
+    wf_mat *trace = nullptr, *polys = nullptr, *lde = nullptr, *shard = nullptr, *comp_l = nullptr, *comp = nullptr, *cpolys = nullptr,
+           *clde = nullptr, *deep = nullptr, *fri_in = nullptr;
+    ShardTree ttree, ctree;
+    wf_fri* fri = nullptr;
+    ProofScope scope(ctx);
+    scope.own({&trace, &polys, &lde, &shard, &comp_l, &comp, &cpolys, &clde, &deep, &fri_in});
+    scope.own({&ttree.local, &ctree.local});
+    scope.fri = &fri;
+    struct SLayer { u64* vals; size_t m_l, m_g; ShardTree tree; };
+    std::vector<SLayer> slayers;   // FRI layers folded on row shards
+    std::vector<void*> owned;      // device buffers of the sharded FRI phase
+    struct Cleanup {
+        wf_ctx* ctx; std::vector<SLayer>& sl; std::vector<void*>& ow;
+        ~Cleanup() { for (auto& l : sl) wf_tree_free(ctx, l.tree.local); for (void* p : ow) wf_dev_free(ctx, p); }
+    } cleanup{ctx, slayers, owned};
+
+    // ---- 1. interpolate + extend the local columns (no communication: columns are independent) ----
+    wf_mark(ctx, "start");
+    if (d_local) {
+        CKI(wf_mat_from_device_columns(ctx, d_local, cl, n, &trace));
+        CKI(wf_mat_interpolate(ctx, trace, &polys));
+        scope.drop(trace);
+        CKI(wf_mat_lde(ctx, polys, log_b, &lde));
+    } else {
+        CKI(wf_trace_lde_from_host(ctx, local_cols, cl, n, mont, log_b, &polys, &lde));
+    }
+    wf_mark(ctx, "trace_lde");
+    // ---- 2. column shards -> row shards: rank q receives rows [q N/G, (q+1) N/G) of every segment; the shard keeps
+    //         `blowup` extra rows per segment for the next-state halo ----
+    CKI(wf_mat_alloc(ctx, rows_per + b, c, &shard));
+    shard->m.rows = rows_per;  // seg_stride stays (rows_per + b) * 8: rows [rows_per, rows_per + b) are the halo
+    const size_t sstride = shard->m.seg_stride;
+    {
+        std::vector<int> sp, rp;
+        std::vector<const void*> sv;
+        std::vector<void*> rv;
+        for (u32 s = 0; s < nsl; s++)
+            for (int q = 0; q < G; q++) {
+                const u64* src = lde->m.base + (size_t)s * lde->m.seg_stride + (size_t)q * rows_per * 8;
+                if (q == r) CK(cudaMemcpyAsync(shard->m.base + ((size_t)r * nsl + s) * sstride, src, rows_per * 64, cudaMemcpyDeviceToDevice, ctx->st));
+                else { sp.push_back(q); sv.push_back(src); rp.push_back(q); rv.push_back(shard->m.base + ((size_t)q * nsl + s) * sstride); }
+            }
+        CKI(sc.exchange(sp, sv, rp, rv, rows_per * 64));
+    }
+    scope.drop(lde);
+    {   // halo: the first `blowup` rows of every segment of rank (r + 1) mod G
+        void *pk, *pk2;
+        const size_t hb = b * 64;
+        CKI(wf_dev_alloc(ctx, hb * nsg, &pk));
+        CKI(wf_dev_alloc(ctx, hb * nsg, &pk2));
+        CK(cudaMemcpy2DAsync(pk, hb, shard->m.base, sstride * 8, hb, nsg, cudaMemcpyDeviceToDevice, ctx->st));
+        CKI(sc.exchange({(r + G - 1) % G}, {pk}, {(r + 1) % G}, {pk2}, hb * nsg));
+        CK(cudaMemcpy2DAsync(shard->m.base + rows_per * 8, sstride * 8, pk2, hb, hb, nsg, cudaMemcpyDeviceToDevice, ctx->st));
+        wf_dev_free(ctx, pk);
+        wf_dev_free(ctx, pk2);
+    }
+    wf_mark(ctx, "trace_exchange");
+    // ---- 3. leaves + subtree over my rows, all-gather of the subtree roots ----
+    Digest root;
+    CKI(wf_commit_rows(ctx, h, shard, &ttree.local));
+    ttree.n_global = N;
+    CKI(shard_tree_finish(sc, h, ttree, &root));
+    wf_mark(ctx, "trace_commit");
+    ch.commit(root.b);
+    // ---- 4. constraint evaluation over my CE rows ----
+    std::vector<GlExt<D>> cc = ch.draw_coeffs(o.batch_c, n_tr + n_as);
+    CKI(eval_constraints<D>(ctx, air, shard, nullptr, cc, {}, log_n, log_b, &comp_l, (size_t)r * ce_per, ce_per));
+    wf_mark(ctx, "constraint_eval");
+    // ---- 5. composition polynomial: all-gather the CE evaluations (a few hundred MiB at most), interpolate + extend on
+    //         every rank (the transform is over the row index), commit my row range ----
+    CKI(wf_mat_alloc(ctx, ce, D, &comp));
+    CKI(sc.all_gather_dev(comp_l->m.base, comp->m.base, ce_per * comp->m.W * 8));
+    scope.drop(comp_l);
+    CKI(composition_commit(ctx, h, comp, log_n, log_b, D, kc, &cpolys, &clde, nullptr));
+    scope.drop(comp);
+    wf_mat cview;  // my rows of the composition LDE
+    cview.m = clde->m;
+    cview.m.base += (size_t)r * rows_per * clde->m.W;
+    cview.m.rows = rows_per;
+    CKI(wf_commit_rows(ctx, h, &cview, &ctree.local));
+    ctree.n_global = N;
+    CKI(shard_tree_finish(sc, h, ctree, &root));
+    wf_mark(ctx, "composition_commit");
+    ch.commit(root.b);
+    // ---- 6. out-of-domain frames: my columns' polynomials, all-gathered; composition columns are replicated ----
+    GlExt<D> z = ch.draw();
+    GlExt<D> zg = ext_mul_base(z, gl_root_of_unity(log_n));
+    std::vector<std::vector<GlExt<D>>> ood;
+    CKI(ood_eval<D>(ctx, {polys, cpolys}, z, zg, ood));
+    std::vector<GlExt<D>> t_cur(c), t_nxt(c);
+    {
+        std::vector<u64> mine((size_t)cl * 2 * D), all((size_t)c * 2 * D);
+        for (u32 j = 0; j < cl; j++)
+            for (int q = 0; q < D; q++) { mine[((size_t)j * 2) * D + q] = ood[0][j].v[q]; mine[((size_t)j * 2 + 1) * D + q] = ood[1][j].v[q]; }
+        CKI(sc.gather_host(mine.data(), all.data(), mine.size() * 8));
+        for (u32 j = 0; j < c; j++)
+            for (int q = 0; q < D; q++) { t_cur[j].v[q] = all[((size_t)j * 2) * D + q]; t_nxt[j].v[q] = all[((size_t)j * 2 + 1) * D + q]; }
+    }
+    auto combine = [&](const std::vector<GlExt<D>>& comp_evals) {  // H_j(z) from its base-component columns
+        std::vector<GlExt<D>> rr(comp_evals.size() / D);
+        for (u32 j = 0; j < rr.size(); j++) {
+            GlExt<D> acc = ext_zero<D>();
+            for (int q = 0; q < D; q++) {
+                GlExt<D> basis = ext_zero<D>();
+                basis.v[q] = 1;
+                acc = ext_add(acc, ext_mul(basis, comp_evals[j * D + q]));
+            }
+            rr[j] = acc;
+        }
+        return rr;
+    };
+    std::vector<GlExt<D>> q_cur = combine(ood[2]), q_nxt = combine(ood[3]);
+    ByteVec ood_t, ood_q;
+    ood_t.u8_(2); write_elems<D>(ood_t, t_cur); write_elems<D>(ood_t, t_nxt);
+    ood_q.u8_(2); write_elems<D>(ood_q, q_cur); write_elems<D>(ood_q, q_nxt);
+    {
+        ByteVec m;
+        write_elems<D>(m, t_cur); write_elems<D>(m, q_cur); write_elems<D>(m, t_nxt); write_elems<D>(m, q_nxt);
+        Digest dg = hh_hash_elements(h, (const u64*)m.v.data(), m.v.size() / 8);
+        ch.coin.reseed(dg);
+    }
+    wf_mark(ctx, "ood_frames");
+    // ---- 7. DEEP composition over my LDE rows (evaluation form is row-local) ----
+    std::vector<GlExt<D>> dc = ch.draw_coeffs(o.batch_d, c + kc);
+    GlExt<D> Sz = ext_zero<D>(), Szg = ext_zero<D>();
+    for (u32 j = 0; j < c; j++) { Sz = ext_add(Sz, ext_mul(dc[j], t_cur[j])); Szg = ext_add(Szg, ext_mul(dc[j], t_nxt[j])); }
+    for (u32 j = 0; j < kc; j++) { Sz = ext_add(Sz, ext_mul(dc[c + j], q_cur[j])); Szg = ext_add(Szg, ext_mul(dc[c + j], q_nxt[j])); }
+    CKI(deep_compose<D>(ctx, shard, nullptr, &cview, kc, log_n + log_b, dc, z, zg, Sz, Szg, &deep, (size_t)r * rows_per, rows_per));
+    wf_mark(ctx, "deep_composition");
+    // ---- 8. FRI: layers folded on shards while they are large. A layer of L points is held as contiguous position
+    //         ranges; leaf i joins positions i, i + L/nf, ...: one exchange gives the owner of leaf range o (L/nf/G leaves)
+    //         its nf pieces, which then look like a complete layer of nf * L/nf/G points to the hash and fold kernels ----
+    const u32 nf = o.folding;
+    const int ld = deep->m.W;
+    const size_t max_rem = (size_t)(o.rem_max_deg + 1) * o.blowup;
+    u64* cur = deep->m.base;  // my range of the current layer: L / G elements, ld words each
+    size_t L = N;
+    // a layer stays sharded while a rank's range has >= 2^17 elements (below that one exchange + two host round trips per
+    // layer cost more than folding the whole layer everywhere); WF_SHARD_FRI_MIN_LOG lowers the bound for small tests
+    u32 min_log = 17;
+    if (const char* e = getenv("WF_SHARD_FRI_MIN_LOG")) min_log = (u32)atoi(e);
+    while (L > max_rem && L / (size_t)G >= ((size_t)1 << min_log) && (L / nf) % (size_t)G == 0 && L / nf / (size_t)G >= 2) {
+        SLayer sl;
+        sl.m_g = L / nf;
+        sl.m_l = sl.m_g / (size_t)G;
+        void* vp;
+        CKI(wf_dev_alloc(ctx, (size_t)nf * sl.m_l * ld * 8, &vp));
+        owned.push_back(vp);
+        sl.vals = (u64*)vp;
+        std::vector<int> sp, rp;
+        std::vector<const void*> sv;
+        std::vector<void*> rv;
+        for (u32 t = 0; t < nf; t++) {  // my range = pieces nf*r .. nf*r + nf - 1 of the layer; piece P belongs to leaf range P % G, slot P / G
+            const size_t P = (size_t)nf * r + t;
+            const int owner = (int)(P % (size_t)G);
+            const size_t q = P / (size_t)G;
+            const u64* src = cur + (size_t)t * sl.m_l * ld;
+            if (owner == r) CK(cudaMemcpyAsync(sl.vals + q * sl.m_l * ld, src, sl.m_l * ld * 8, cudaMemcpyDeviceToDevice, ctx->st));
+            else { sp.push_back(owner); sv.push_back(src); }
+        }
+        for (u32 q = 0; q < nf; q++) {
+            const size_t P = (size_t)q * G + r;
+            const int src_rank = (int)(P / nf);
+            if (src_rank != r) { rp.push_back(src_rank); rv.push_back(sl.vals + (size_t)q * sl.m_l * ld); }
+        }
+        CKI(sc.exchange(sp, sv, rp, rv, sl.m_l * ld * 8));
+        CKI(wf_fri_layer_tree(ctx, h, sl.vals, (size_t)nf * sl.m_l, D, ld, (int)nf, &sl.tree.local));
+        sl.tree.n_global = sl.m_g;
+        slayers.push_back(sl);
+        CKI(shard_tree_finish(sc, h, slayers.back().tree, &root));
+        ch.commit(root.b);              // commit_fri_layer, then draw_fri_alpha (prover/src/channel.rs:215-234)
+        GlExt<D> alpha = ch.draw();
+        u32 logL = 0;
+        while (((size_t)1 << logL) < L) logL++;
+        const u64* master;
+        CKI(wf_get_twiddles(ctx, logL, &master));
+        void* nx;
+        CKI(wf_dev_alloc(ctx, sl.m_l * ld * 8, &nx));
+        owned.push_back(nx);
+        if (ld > D) CK(cudaMemsetAsync(nx, 0, sl.m_l * ld * 8, ctx->st));
+        u64 av[3] = {0, 0, 0};
+        for (int q = 0; q < D; q++) av[q] = alpha.v[q];
+        CK(fri_fold_layer(sl.vals, (size_t)nf * sl.m_l, D, ld, (int)nf, av, master, (u64*)nx, ld, ctx->st, nullptr, (size_t)r * sl.m_l, logL));
+        ctx->launches++;
+        cur = (u64*)nx;
+        L = sl.m_g;
+    }
+    // the rest of the commit phase on every rank: all-gather the current layer (small by now)
+    CKI(wf_mat_alloc(ctx, L, D, &fri_in));
+    CKI(sc.all_gather_dev(cur, fri_in->m.base, (L / (size_t)G) * ld * 8));
+    scope.drop(deep);
+    {
+        std::vector<Digest> fri_roots;
+        CKI(wf_fri_build_layers_coin(ctx, h, fri_in, D, o.folding, o.rem_max_deg, o.blowup, ch.coin, fri_roots, &fri));
+        for (auto& rt : fri_roots) ch.commitments.bytes(rt.b, 32);
+    }
+    scope.drop(fri_in);
+    wf_mark(ctx, "fri_layers");
+    // ---- 9. grinding + query positions (every rank; deterministic) ----
+    u64 nonce;
+    CKI(grind_on_device(ctx, h, ch.coin.seed, o.grinding, &nonce));
+    if (ch.coin.check_leading_zeros(nonce) < o.grinding) return wf_fail(ctx, WF_ERR_STATE, "grinding self-check failed");
+    std::vector<u64> pos;
+    if (!ch.coin.draw_integers(o.num_queries, N, nonce, pos)) return wf_fail(ctx, WF_ERR_STATE, "failed to draw query positions");
+    std::sort(pos.begin(), pos.end());
+    pos.erase(std::unique(pos.begin(), pos.end()), pos.end());
+    wf_mark(ctx, "grinding");
+    // ---- 10. proof object: every rank queues the same gathers, contributes what it holds, the words are summed ----
+    ByteVec w;
+    w.u8_((u8)c); w.u8_(0); w.u8_(0); w.u8_((u8)log_n); w.u16_(0);
+    w.u8_(8); w.u64_(GL_P);
+    w.u8_((u8)o.num_queries); w.u8_((u8)o.blowup); w.u8_((u8)o.grinding); w.u8_((u8)o.ext); w.u8_((u8)o.folding);
+    w.u8_((u8)o.rem_max_deg); w.u8_((u8)o.batch_c); w.u8_((u8)o.batch_d); w.u8_((u8)o.num_partitions); w.u8_((u8)o.hash_rate);
+    w.usize(n_tr + n_as);
+    w.u8_((u8)pos.size());
+    w.u16_((uint16_t)ch.commitments.v.size());
+    w.bytes(ch.commitments.v.data(), ch.commitments.v.size());
+    GatherBatch gb;
+    gb.comm = cm;
+    const u64 NONE = ~(u64)0;
+    auto owned_rows = [&](const std::vector<u64>& p, size_t per) {  // global row -> my local row, or NONE
+        std::vector<u64> l(p.size(), NONE);
+        for (size_t i = 0; i < p.size(); i++) if ((int)(p[i] / per) == r) l[i] = p[i] % per;
+        return l;
+    };
+    std::vector<std::pair<size_t, u64>> top_t, top_c;
+    size_t tr_rows = gb.add_rows(shard->m, owned_rows(pos, rows_per));
+    size_t cr_rows = gb.add_rows(clde->m, r == 0 ? pos : std::vector<u64>(pos.size(), NONE));  // replicated: rank 0 contributes
+    size_t tr_dig, cr_dig;
+    CKI(gb.add_opening_sharded(ctx, ttree.local, N, G, r, pos, &tr_dig, &top_t));
+    CKI(gb.add_opening_sharded(ctx, ctree.local, N, G, r, pos, &cr_dig, &top_c));
+    struct SQ { size_t row_id, dig_id, nq; std::vector<std::pair<size_t, u64>> top; };
+    std::vector<SQ> sq;
+    std::vector<u64> fpos = pos;
+    for (auto& sl : slayers) {  // FriProver::build_proof (fri/src/prover/mod.rs:254-319) on the sharded layers
+        std::vector<u64> fp;    // fold_positions (fri/src/folding/mod.rs:159-176)
+        for (u64 p : fpos) { u64 q = p % sl.m_g; if (std::find(fp.begin(), fp.end(), q) == fp.end()) fp.push_back(q); }
+        fpos = fp;
+        std::vector<u64> gpos(fpos.size() * nf, NONE);
+        for (size_t i = 0; i < fpos.size(); i++)
+            if ((int)(fpos[i] / sl.m_l) == r)
+                for (u32 j = 0; j < nf; j++) gpos[i * nf + j] = (u64)j * sl.m_l + fpos[i] % sl.m_l;
+        SegMatrix lm;
+        lm.base = sl.vals; lm.rows = (size_t)nf * sl.m_l; lm.cols = (u32)D; lm.W = ld; lm.seg_stride = lm.rows * ld;
+        SQ e;
+        e.row_id = gb.add_rows(lm, gpos);
+        CKI(gb.add_opening_sharded(ctx, sl.tree.local, sl.m_g, G, r, fpos, &e.dig_id, &e.top));
+        e.nq = fpos.size();
+        sq.push_back(e);
+    }
+    FriProofPlan fplan;
+    {
+        const size_t r0 = gb.rows.size(), d0 = gb.digs.size();
+        CKI(wf_fri_queue_proof(ctx, fri, fpos, gb, fplan));
+        if (r != 0) {  // replicated layers: rank 0 contributes
+            for (size_t i = r0; i < gb.rows.size(); i++) std::fill(gb.rows[i].pos.begin(), gb.rows[i].pos.end(), NONE);
+            for (size_t i = d0; i < gb.digs.size(); i++) std::fill(gb.digs[i].idx.begin(), gb.digs[i].idx.end(), NONE);
+        }
+    }
+    CKI(gb.run(ctx));
+    auto patch = [&](size_t dig_id, const std::vector<std::pair<size_t, u64>>& slots, const ShardTree& t) {
+        for (auto& se : slots) memcpy(gb.digest_words(dig_id) + se.first * 4, t.top[se.second].b, 32);
+    };
+    patch(tr_dig, top_t, ttree);
+    patch(cr_dig, top_c, ctree);
+    for (size_t i = 0; i < sq.size(); i++) patch(sq[i].dig_id, sq[i].top, slayers[i].tree);
+    write_queries(gb, tr_rows, tr_dig, pos.size() * c, w);
+    write_queries(gb, cr_rows, cr_dig, pos.size() * kc * D, w);
+    w.u16_((uint16_t)ood_t.v.size()); w.bytes(ood_t.v.data(), ood_t.v.size());
+    w.u16_((uint16_t)ood_q.v.size()); w.bytes(ood_q.v.data(), ood_q.v.size());
+    {   // FriProof (fri/src/proof.rs:149-163, 275-285): sharded layers, then the replicated ones
+        w.u8_((u8)(slayers.size() + fri->layers.size()));
+        for (size_t l = 0; l < sq.size(); l++) {
+            const size_t nvals = sq[l].nq * nf * D;
+            ByteVec paths;
+            wf_open_finish(gb.digs[sq[l].dig_id].plan, gb.digest_result(sq[l].dig_id), nullptr, paths);
+            w.u32_((u32)(nvals * 8));
+            w.bytes(gb.row_result(sq[l].row_id), nvals * 8);
+            w.u32_((u32)paths.v.size());
+            w.bytes(paths.v.data(), paths.v.size());
+        }
+        for (size_t l = 0; l < fri->layers.size(); l++) {
+            const size_t nvals = fplan.nq[l] * fri->folding * fri->d;
+            ByteVec paths;
+            wf_open_finish(gb.digs[fplan.dig_ids[l]].plan, gb.digest_result(fplan.dig_ids[l]), nullptr, paths);
+            w.u32_((u32)(nvals * 8));
+            w.bytes(gb.row_result(fplan.row_ids[l]), nvals * 8);
+            w.u32_((u32)paths.v.size());
+            w.bytes(paths.v.data(), paths.v.size());
+        }
+        w.u16_((uint16_t)(fri->remainder.size() * 8));
+        w.bytes(fri->remainder.data(), fri->remainder.size() * 8);
+        w.u8_(0);
+    }
+    w.u64_(nonce);
+    wf_mark(ctx, "queries_and_proof");
+    proof_out.swap(w.v);
+    if (stats) {
+        CK(cudaStreamSynchronize(ctx->st));
+        stats[0] = sc.bytes_sent; stats[1] = sc.exchange_ms(); stats[2] = sc.ncoll + 1; stats[3] = sc.ms_small;
+        for (int i = 4; i < 8; i++) stats[i] = 0;
+        stats[4] = (double)slayers.size();
+    }
+    return WF_OK;
+}
+
 }  // namespace
 
 extern "C" int wf_grind(wf_ctx* ctx, int hash_id, const uint8_t seed[32], uint32_t grinding, uint64_t* nonce) {
@@ -1500,6 +1989,27 @@ extern "C" int wf_deep_compose(wf_ctx* ctx, uint32_t ext, const wf_mat* main_lde
     }
 }
 
+extern "C" int wf_prove_fib_sharded(wf_ctx* ctx, const wf_comm* comm, const uint64_t* const* local_cols, const uint64_t* d_local, int mont,
+                                    uint32_t k, uint32_t log_n, const uint64_t* results, const uint32_t* opts, uint8_t* proof,
+                                    size_t* proof_len, double* stats) {
+    if (!ctx || !comm || !comm->exchange || !comm->all_gather_host || !comm->all_reduce_sum || (!local_cols && !d_local) || !results ||
+        !opts || !proof || !proof_len || k == 0 || 2 * k > 255 || log_n < 3)
+        return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    Options o;
+    CKI(parse_options(ctx, opts, o));
+    std::vector<u8> out;
+    int r;
+    switch (o.ext) {
+        case 1: r = prove_fib_sharded<1>(ctx, comm, local_cols, d_local, mont, k, log_n, results, o, out, stats); break;
+        case 2: r = prove_fib_sharded<2>(ctx, comm, local_cols, d_local, mont, k, log_n, results, o, out, stats); break;
+        default: r = prove_fib_sharded<3>(ctx, comm, local_cols, d_local, mont, k, log_n, results, o, out, stats); break;
+    }
+    if (r != WF_OK) return r;
+    if (out.size() > *proof_len) return wf_fail(ctx, WF_ERR_INVALID, "proof buffer too small (%zu needed)", out.size());
+    memcpy(proof, out.data(), out.size());
+    *proof_len = out.size();
+    return WF_OK;
+}
 extern "C" int wf_prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, uint32_t k, uint32_t log_n,
                             const uint64_t* results, const uint32_t* opts, uint8_t* proof, size_t* proof_len) {
     return prove_fib_entry(ctx, trace_cols, nullptr, mont, k, log_n, results, opts, proof, proof_len);

@@ -124,3 +124,136 @@ def sharded_trace_commit(backend, hash_id, local_cols, ncols_total, log_n, log_b
     dist.all_gather(gathered, mine, group=group)
     roots = [bytes(g.cpu().numpy()) for g in gathered]
     return top_levels(hash_id, roots), rows, digests, nodes
+
+
+# --------------------------------------------------------------------------------------------------
+# One proof sharded over the ranks of a torch.distributed group (wf_prove_fib_sharded, include/winterfell_b200.h).
+# The library does all arithmetic and orchestration; this module only supplies the three collectives of `wf_comm`.
+# --------------------------------------------------------------------------------------------------
+import ctypes as C
+import time
+
+_EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.c_size_t, C.POINTER(C.c_int),
+                           C.POINTER(C.c_void_p), C.c_size_t)
+_GATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+_REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class WfComm(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("rank", C.c_int), ("world", C.c_int), ("exchange", _EXCHANGE_FN), ("all_gather_host", _GATHER_FN),
+                ("all_reduce_sum", _REDUCE_FN)]
+
+
+class _DevBuf:
+    """Raw device memory as a CUDA-array-interface object (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def _dev_tensor(ptr, nbytes, device):
+    return torch.as_tensor(_DevBuf(ptr, nbytes), device=device)
+
+
+class TorchComm:
+    """wf_comm over torch.distributed. backend "nccl": device buffers go straight into NCCL send/recv on the context's
+    stream (NVLink / NVSwitch peer copies). backend "gloo": staged through host memory — the CPU-side test double of the
+    same call sequence (lets two ranks share one GPU in the tests)."""
+
+    def __init__(self, stream=None, group=None, device=None):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.nccl = dist.get_backend(group) == "nccl"
+        self.stream = stream
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.error = None
+        self._keep = (_EXCHANGE_FN(self._exchange), _GATHER_FN(self._gather), _REDUCE_FN(self._reduce))
+        self.struct = WfComm(None, self.rank, self.world, *self._keep)
+
+    def _ctx(self):
+        return torch.cuda.stream(self.stream) if self.stream is not None else torch.cuda.stream(torch.cuda.current_stream())
+
+    def _guard(self, fn):
+        try:
+            fn()
+            return 0
+        except Exception as e:  # must not unwind through the C caller
+            import traceback
+            traceback.print_exc()
+            self.error = e
+            return 1
+
+    def _exchange(self, _user, nsend, send_peer, send_ptr, nrecv, recv_peer, recv_ptr, nbytes):
+        def run():
+            with self._ctx():
+                sends = [(send_peer[i], _dev_tensor(send_ptr[i], nbytes, self.device)) for i in range(nsend)]
+                recvs = [(recv_peer[i], _dev_tensor(recv_ptr[i], nbytes, self.device)) for i in range(nrecv)]
+                if self.nccl:
+                    ops = [dist.P2POp(dist.isend, t, p, self.group) for p, t in sends] + [dist.P2POp(dist.irecv, t, p, self.group) for p, t in recvs]
+                    if ops:
+                        for req in dist.batch_isend_irecv(ops):
+                            req.wait()   # stream-ordered on the current (= context) stream, not a host wait
+                else:
+                    if self.stream is not None:
+                        self.stream.synchronize()
+                    host_in = [torch.empty(nbytes, dtype=torch.uint8) for _ in recvs]
+                    reqs = [dist.isend(t.cpu(), p, group=self.group) for p, t in sends]
+                    reqs += [dist.irecv(h, p, group=self.group) for (p, _), h in zip(recvs, host_in)]
+                    for q in reqs:
+                        q.wait()
+                    for (_, t), h in zip(recvs, host_in):
+                        t.copy_(h)
+        return self._guard(run)
+
+    def _gather(self, _user, send, recv, nbytes):
+        def run():
+            mine = torch.frombuffer((C.c_uint8 * nbytes).from_address(send), dtype=torch.uint8).clone()
+            out = torch.frombuffer((C.c_uint8 * (nbytes * self.world)).from_address(recv), dtype=torch.uint8)
+            if self.nccl:
+                with self._ctx():
+                    d_all = torch.empty(nbytes * self.world, dtype=torch.uint8, device=self.device)
+                    dist.all_gather_into_tensor(d_all, mine.to(self.device), group=self.group)
+                    out.copy_(d_all.cpu())
+            else:
+                parts = [torch.empty(nbytes, dtype=torch.uint8) for _ in range(self.world)]
+                dist.all_gather(parts, mine, group=self.group)
+                out.copy_(torch.cat(parts))
+        return self._guard(run)
+
+    def _reduce(self, _user, d_buf, words):
+        def run():
+            with self._ctx():
+                t = _dev_tensor(d_buf, words * 8, self.device).view(torch.int64)
+                if self.nccl:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                else:
+                    if self.stream is not None:
+                        self.stream.synchronize()
+                    h = t.cpu()
+                    dist.all_reduce(h, op=dist.ReduceOp.SUM, group=self.group)
+                    t.copy_(h)
+        return self._guard(run)
+
+
+def prove_fib_sharded(ctx, comm, local_trace, k, log_n, results, opts, out_buf=None, device_ptr=None, stats=None):
+    """One FibSmall x k proof over comm.world GPUs. local_trace: this rank's [2k / world, n] uint64 columns (host), or
+    device_ptr = raw pointer to the same block column-major in HBM. Returns the proof bytes (identical on every rank)."""
+    L = wf.lib()
+    r_ = np.ascontiguousarray(results, dtype=np.uint64)
+    o_ = np.ascontiguousarray(opts, dtype=np.uint32)
+    buf = out_buf if out_buf is not None else np.zeros(1 << 23, dtype=np.uint8)
+    ln = C.c_size_t(buf.size)
+    st = (C.c_double * 8)()
+    if device_ptr is None:
+        a = np.ascontiguousarray(local_trace, dtype=np.uint64)
+        ptrs = (wf.u64p * a.shape[0])(*[a[j].ctypes.data_as(wf.u64p) for j in range(a.shape[0])])
+        dptr = None
+    else:
+        ptrs, dptr = None, C.c_void_p(device_ptr)
+    ctx.check(L.wf_prove_fib_sharded(ctx.h, C.byref(comm.struct), ptrs, dptr, 0, k, log_n, r_.ctypes.data_as(wf.u64p),
+                                     o_.ctypes.data_as(C.POINTER(C.c_uint32)), buf.ctypes.data_as(wf.u8p), C.byref(ln), st))
+    if comm.error is not None:
+        raise comm.error
+    if stats is not None:
+        stats.update({"bytes_sent": st[0], "exchange_ms": st[1], "collectives": st[2], "small_collective_ms": st[3], "sharded_fri_layers": st[4]})
+    return buf[: ln.value].tobytes()
