@@ -306,6 +306,12 @@ size_t wf_host_write_usize(uint64_t value, uint8_t out[9]);
 int wf_host_coin_draw(int hash_id, const uint64_t* seed_elems, size_t n_seed, const uint8_t* reseed32, int d, size_t count,
                       uint64_t* out);
 
+/* index arithmetic of an opening in a tree stored as one subtree per rank (wf_prove_fib_sharded): want[i] = heap node
+ * (< n_global) or n_global + leaf that MerkleTree::prove_batch (crypto/src/merkle/mod.rs:217-272) reads for `positions`;
+ * idx[i] = its index in rank `rank`'s subtree (node < n_local, else n_local + leaf), ~0 when another rank holds it,
+ * ~0 - 1 for a node of the top log2(world) levels. Returns the number of entries or -1. Host code. */
+long wf_host_sharded_opening_plan(size_t n_global, int world, int rank, const uint64_t* positions, size_t k, uint64_t* want,
+                                  uint64_t* idx, size_t cap);
 /* FibSmallProver::build_trace (examples/src/fibonacci/fib_small/prover.rs:37-53) for the built-in "FibSmall x k"
  * family: cols = [2k][n] canonical words, pair j starting at (j+1, j+1); results[j] = its public input. Host code. */
 int wf_host_build_fib_trace(uint32_t k, size_t n, uint64_t* cols, uint64_t* results);

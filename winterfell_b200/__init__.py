@@ -94,6 +94,7 @@ _SIGS = [
     ("wf_host_write_usize", C.c_size_t, [C.c_uint64, u8p]),
     ("wf_host_coin_draw", C.c_int, [C.c_int, u64p, C.c_size_t, u8p, C.c_int, C.c_size_t, u64p]),
     ("wf_host_build_fib_trace", C.c_int, [C.c_uint32, C.c_size_t, u64p, u64p]),
+    ("wf_host_sharded_opening_plan", C.c_long, [C.c_size_t, C.c_int, C.c_int, u64p, C.c_size_t, u64p, u64p, C.c_size_t]),
     ("wf_prove_fib_sharded", C.c_int, [vp, vp, C.POINTER(u64p), vp, C.c_int, C.c_uint32, C.c_uint32, u64p, C.POINTER(C.c_uint32), u8p,
                                        C.POINTER(C.c_size_t), C.POINTER(C.c_double)]),
 ]
@@ -497,6 +498,17 @@ def build_fib_trace(k, n, out=None):
     if lib().wf_host_build_fib_trace(k, n, tr.ctypes.data_as(u64p), res.ctypes.data_as(u64p)) != WF_OK:
         raise WfError("wf_host_build_fib_trace: bad arguments")
     return tr, res
+
+
+def sharded_opening_plan(n_global, world, rank, positions):
+    """(want, idx) of wf_host_sharded_opening_plan as uint64 arrays."""
+    p_, pp = _u64(positions)
+    cap = 64 * max(len(p_), 1) * 64
+    want, idx = np.zeros(cap, dtype=np.uint64), np.zeros(cap, dtype=np.uint64)
+    cnt = lib().wf_host_sharded_opening_plan(n_global, world, rank, pp, len(p_), want.ctypes.data_as(u64p), idx.ctypes.data_as(u64p), cap)
+    if cnt < 0:
+        raise WfError("wf_host_sharded_opening_plan: bad arguments")
+    return want[:cnt].copy(), idx[:cnt].copy()
 
 
 def host_hash_elements(hash_id, elems):

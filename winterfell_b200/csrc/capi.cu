@@ -1327,6 +1327,24 @@ int wf_host_build_fib_trace(uint32_t k, size_t n, uint64_t* cols, uint64_t* resu
     for (auto& x : th) x.join();
     return WF_OK;
 }
+// Index arithmetic of a sharded opening (GatherBatch::add_opening_sharded), exposed for the CPU tests of the multi-rank
+// logic: the batch proof of `positions` in a tree of n_global leaves needs the digests want[0..count) (entries < n_global:
+// heap nodes, else leaves, as MerkleTree::prove_batch walks them, crypto/src/merkle/mod.rs:217-272); idx[i] = where rank
+// `rank` of `world` finds want[i] in ITS subtree (node index < n_local, else n_local + leaf), ~0 if another rank holds it,
+// ~0 - 1 if it is one of the top log2(world) levels every rank keeps on the host. Returns count, or -1.
+long wf_host_sharded_opening_plan(size_t n_global, int world, int rank, const uint64_t* positions, size_t k, uint64_t* want,
+                                  uint64_t* idx, size_t cap) {
+    if (!positions || !want || !idx || world < 1 || (world & (world - 1)) || n_global % (size_t)world) return -1;
+    GatherBatch gb;
+    size_t id;
+    std::vector<std::pair<size_t, u64>> top;
+    if (gb.add_opening_sharded(nullptr, nullptr, n_global, world, rank, std::vector<u64>(positions, positions + k), &id, &top) != WF_OK) return -1;
+    const auto& j = gb.digs[id];
+    if (j.idx.size() > cap) return -1;
+    for (size_t i = 0; i < j.idx.size(); i++) { want[i] = j.plan.want[i]; idx[i] = j.idx[i]; }
+    for (auto& t : top) idx[t.first] = ~(u64)0 - 1;
+    return (long)j.idx.size();
+}
 // DefaultRandomCoin on the host (crypto/src/random/default.rs): seed from elements, optional reseed with a
 // digest, then draw `count` elements of extension degree d -> out[count][d]. Returns 0, or -1 if a draw fails.
 int wf_host_coin_draw(int hash_id, const uint64_t* seed_elems, size_t n_seed, const uint8_t* reseed32, int d, size_t count,

@@ -139,44 +139,45 @@ __device__ __forceinline__ u64 gl_canon(u64 r) {
         : "l"(r));
     return o;
 }
-// lo + 2^64 hi mod p, canonical: V = x0 + 2^32 x1 + (2^32 - 1) x2 - x3 as W + adj * 2^64 with
-// adj = carry - borrow in {-1, 0, 1}; then W + adj * (2^32 - 1), which cannot wrap: adj = 1 means
-// V < 2^65 - 2^33 + 1 so W < 2^64 - 2^33 + 1; adj = -1 means V > -2^32 so W > 2^64 - 2^32.
-// The mad.lo.cc / madc.hi.cc pair compiles to IMAD.WIDE.U32 with carry predicates (FMA pipe).
+// lo + 2^64 hi mod p, canonical: V = x0 + 2^32 x1 + (2^32 - 1) x2 - x3 in two one-sided steps (the order of
+// reduce128 in math/src/field/f64/mod.rs:714-730 mont_red_cst's Goldilocks analogue):
+//   t = (x1:x0) - x3; a borrow is repaid with - (2^32 - 1) (t + p: cannot borrow twice, t_wrapped >= 2^64 - 2^32 + 1);
+//   U = t + x2 * (2^32 - 1) < 2p as carry * 2^64 + r; U >= p exactly when carry or r + (2^32 - 1) carries (never
+//   both), and then U - p = r + (2^32 - 1) mod 2^64. One add chain decides, one IMAD.WIDE applies it.
+// 12 SASS instructions; the first version (carry - borrow as a signed adjustment, then a separate canonicalisation)
+// compiled to 17.
 __device__ __forceinline__ u64 gl_reduce128(u64 lo, u64 hi) {
     u64 r;
     asm("{\n\t"
-        ".reg .u32 c0, c1, c2, c3, k, m;\n\t"
-        ".reg .s32 adj;\n\t"
-        ".reg .u64 t;\n\t"
+        ".reg .u32 c0, c1, c2, c3, k, m, t0, t1;\n\t"
         "mov.b64 {c0, c1}, %1;\n\t"
         "mov.b64 {c2, c3}, %2;\n\t"
-        "mad.lo.cc.u32 c0, c2, 0xffffffff, c0;\n\t"
-        "madc.hi.cc.u32 c1, c2, 0xffffffff, c1;\n\t"
-        "addc.u32 k, 0, 0;\n\t"
         "sub.cc.u32 c0, c0, c3;\n\t"
         "subc.cc.u32 c1, c1, 0;\n\t"
         "subc.u32 m, 0, 0;\n\t"
-        "add.s32 adj, k, m;\n\t"
-        "mov.b64 t, {c0, c1};\n\t"
-        "mad.wide.s32 t, adj, -1, t;\n\t"
-        "mov.b64 {c0, c1}, t;\n\t"
-        "add.u32 c1, c1, adj;\n\t"
+        "sub.cc.u32 c0, c0, m;\n\t"
+        "subc.u32 c1, c1, 0;\n\t"
+        "mad.lo.cc.u32 c0, c2, 0xffffffff, c0;\n\t"
+        "madc.hi.cc.u32 c1, c2, 0xffffffff, c1;\n\t"
+        "addc.u32 k, 0, 0;\n\t"
+        "add.cc.u32 t0, c0, 0xffffffff;\n\t"
+        "addc.cc.u32 t1, c1, 0;\n\t"
+        "addc.u32 k, k, 0;\n\t"
+        "mad.lo.cc.u32 c0, k, 0xffffffff, c0;\n\t"
+        "madc.hi.u32 c1, k, 0xffffffff, c1;\n\t"
         "mov.b64 %0, {c0, c1};\n\t"
         "}"
         : "=l"(r)
         : "l"(lo), "l"(hi));
-    return gl_canon(r);
+    return r;
 }
-// 64 x 64 -> 128 as even columns (a0 b0 | a1 b1) plus the odd column a0 b1 + a1 b0 shifted by 32,
-// carries chained through the multiply-adds (IMAD.WIDE.U32 with carry in / out), fused with the
-// reduction above.
+// 64 x 64 -> 128 as even columns (a0 b0 | a1 b1) plus the odd column a0 b1 + a1 b0 shifted by 32 (ptxas turns the
+// mul.lo / mul.hi pairs into IMAD.WIDE.U32 with carry predicates), fused with the reduction above: ~20 SASS
+// instructions, canonical result.
 __device__ __forceinline__ u64 gl_mul(u64 a, u64 b) {
     u64 r;
     asm("{\n\t"
-        ".reg .u32 a0, a1, b0, b1, c0, c1, c2, c3, o0, o1, o2, k, m;\n\t"
-        ".reg .s32 adj;\n\t"
-        ".reg .u64 t;\n\t"
+        ".reg .u32 a0, a1, b0, b1, c0, c1, c2, c3, o0, o1, o2, k, m, t0, t1;\n\t"
         "mov.b64 {a0, a1}, %1;\n\t"
         "mov.b64 {b0, b1}, %2;\n\t"
         "mul.lo.u32 c0, a0, b0;\n\t"
@@ -191,22 +192,81 @@ __device__ __forceinline__ u64 gl_mul(u64 a, u64 b) {
         "add.cc.u32 c1, c1, o0;\n\t"
         "addc.cc.u32 c2, c2, o1;\n\t"
         "addc.u32 c3, c3, o2;\n\t"
-        "mad.lo.cc.u32 c0, c2, 0xffffffff, c0;\n\t"
-        "madc.hi.cc.u32 c1, c2, 0xffffffff, c1;\n\t"
-        "addc.u32 k, 0, 0;\n\t"
         "sub.cc.u32 c0, c0, c3;\n\t"
         "subc.cc.u32 c1, c1, 0;\n\t"
         "subc.u32 m, 0, 0;\n\t"
-        "add.s32 adj, k, m;\n\t"
-        "mov.b64 t, {c0, c1};\n\t"
-        "mad.wide.s32 t, adj, -1, t;\n\t"
-        "mov.b64 {c0, c1}, t;\n\t"
-        "add.u32 c1, c1, adj;\n\t"
+        "sub.cc.u32 c0, c0, m;\n\t"
+        "subc.u32 c1, c1, 0;\n\t"
+        "mad.lo.cc.u32 c0, c2, 0xffffffff, c0;\n\t"
+        "madc.hi.cc.u32 c1, c2, 0xffffffff, c1;\n\t"
+        "addc.u32 k, 0, 0;\n\t"
+        "add.cc.u32 t0, c0, 0xffffffff;\n\t"
+        "addc.cc.u32 t1, c1, 0;\n\t"
+        "addc.u32 k, k, 0;\n\t"
+        "mad.lo.cc.u32 c0, k, 0xffffffff, c0;\n\t"
+        "madc.hi.u32 c1, k, 0xffffffff, c1;\n\t"
         "mov.b64 %0, {c0, c1};\n\t"
         "}"
         : "=l"(r)
         : "l"(a), "l"(b));
-    return gl_canon(r);
+    return r;
+}
+// x * 2^K for a compile-time K < 96 and canonical x, written on the three words y = x << (K mod 32) (y2 < 2^(K mod 32)):
+//   K < 32      : (y1:y0) + (2^32 - 1) y2                      -> carry * 2^64 + r < 2p, folded as in gl_reduce128 (11 instr.)
+//   32 <= K < 64: 2^32 y0 + (2^32 - 1) y1 - y2 = ((y0:0) - y2, a borrow repaid with -(2^32 - 1)) + (2^32 - 1) y1 -> fold
+//   64 <= K < 96: (2^32 - 1) y0 - (y2:y1) (2^96 = -1, 2^128 = -2^32): below p already, a borrow repaid with -(2^32 - 1):
+//                 canonical without a fold (11 instr.; the first version went through two 128-bit reductions: 45)
+template <int K>
+__device__ __forceinline__ u64 gl_shl_dev(u64 x) {
+    constexpr int R = K & 31;
+    const u32 x0 = (u32)x, x1 = (u32)(x >> 32);
+    const u32 y0 = x0 << R, y1 = R ? __funnelshift_l(x0, x1, R) : x1, y2 = R ? (x1 >> ((32 - R) & 31)) : 0;
+    u64 o;
+    if (K < 32) {
+        asm("{\n\t"
+            ".reg .u32 r0, r1, k, t0, t1;\n\t"
+            "mad.lo.cc.u32 r0, %3, 0xffffffff, %1;\n\t"
+            "madc.hi.cc.u32 r1, %3, 0xffffffff, %2;\n\t"
+            "addc.u32 k, 0, 0;\n\t"
+            "add.cc.u32 t0, r0, 0xffffffff;\n\t"
+            "addc.cc.u32 t1, r1, 0;\n\t"
+            "addc.u32 k, k, 0;\n\t"
+            "mad.lo.cc.u32 r0, k, 0xffffffff, r0;\n\t"
+            "madc.hi.u32 r1, k, 0xffffffff, r1;\n\t"
+            "mov.b64 %0, {r0, r1};\n\t"
+            "}" : "=l"(o) : "r"(y0), "r"(y1), "r"(y2));
+    } else if (K < 64) {
+        asm("{\n\t"
+            ".reg .u32 r0, r1, k, m, t0, t1;\n\t"
+            "sub.cc.u32 r0, 0, %3;\n\t"                 // (y0 : 0) - y2
+            "subc.cc.u32 r1, %1, 0;\n\t"
+            "subc.u32 m, 0, 0;\n\t"
+            "sub.cc.u32 r0, r0, m;\n\t"
+            "subc.u32 r1, r1, 0;\n\t"
+            "mad.lo.cc.u32 r0, %2, 0xffffffff, r0;\n\t"  // + y1 * (2^32 - 1)
+            "madc.hi.cc.u32 r1, %2, 0xffffffff, r1;\n\t"
+            "addc.u32 k, 0, 0;\n\t"
+            "add.cc.u32 t0, r0, 0xffffffff;\n\t"
+            "addc.cc.u32 t1, r1, 0;\n\t"
+            "addc.u32 k, k, 0;\n\t"
+            "mad.lo.cc.u32 r0, k, 0xffffffff, r0;\n\t"
+            "madc.hi.u32 r1, k, 0xffffffff, r1;\n\t"
+            "mov.b64 %0, {r0, r1};\n\t"
+            "}" : "=l"(o) : "r"(y0), "r"(y1), "r"(y2));
+    } else {
+        asm("{\n\t"
+            ".reg .u32 m0, m1, b;\n\t"
+            "mul.lo.u32 m0, %1, 0xffffffff;\n\t"
+            "mul.hi.u32 m1, %1, 0xffffffff;\n\t"
+            "sub.cc.u32 m0, m0, %2;\n\t"
+            "subc.cc.u32 m1, m1, %3;\n\t"
+            "subc.u32 b, 0, 0;\n\t"
+            "sub.cc.u32 m0, m0, b;\n\t"
+            "subc.u32 m1, m1, 0;\n\t"
+            "mov.b64 %0, {m0, m1};\n\t"
+            "}" : "=l"(o) : "r"(y0), "r"(y1), "r"(y2));
+    }
+    return o;
 }
 #else
 GL_HD u64 gl_add(u64 a, u64 b) { return gl_add_host(a, b); }
@@ -271,13 +331,17 @@ GL_HD u64 gl_sqr(u64 a) { return gl_mul(a, a); }
 template <int K>
 GL_HD u64 gl_mul_2exp(u64 x) {
     if (K == 0) return x;
-    if (K < 64) return gl_reduce128(x << (K & 63), x >> ((64 - K) & 63));
     if (K == 96) return gl_neg(x);
+#ifdef __CUDA_ARCH__
+    return gl_shl_dev<K>(x);
+#else
+    if (K < 64) return gl_reduce128(x << (K & 63), x >> ((64 - K) & 63));
     // 64 <= K < 96: x * 2^K = (x << (K - 64)) * 2^64; let y = x << (K-64) = yl + 2^64 yh (yh < 2^32)
     // => yl * 2^64 + yh * 2^128, and 2^128 = -2^32 (mod p).
     u64 yl = x << ((K - 64) & 63), yh = (K == 64) ? 0 : (x >> ((128 - K) & 63));
     u64 r = gl_reduce128(0, yl);
     return gl_sub(r, gl_reduce128(yh << 32, 0));
+#endif
 }
 
 GL_HD u64 gl_pow(u64 a, u64 e) {
