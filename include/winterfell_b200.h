@@ -159,8 +159,12 @@ int wf_fri_free(wf_ctx* ctx, wf_fri* f);
  * serialized Proof (air/src/proof/mod.rs:189-200). trace_cols: 2k host columns of 2^log_n words;
  * results: the k public inputs (last value of column 2j+1).
  * opts[9] = { num_queries, blowup, grinding, field_extension (1|2|3), fri_folding, fri_remainder_max_degree,
- *             constraint batching (0 Linear | 1 Algebraic | 2 Horner), DEEP batching, hash_id }
- * (ProofOptions::new, air/src/options.rs:132). *proof_len: in = capacity, out = bytes written. */
+ *             constraint batching (0 Linear | 1 Algebraic | 2 Horner), DEEP batching,
+ *             hash_id | num_partitions << 8 | hash_rate << 16 }
+ * (ProofOptions::new, air/src/options.rs:132; the two upper fields of opts[8] are ProofOptions::with_partitions,
+ * options.rs:193-200 — 0 means the default PartitionOptions::new(1, 1); with more than one partition the main, auxiliary
+ * and constraint commitments hash every row as merge_many of the digests of its column partitions, row_matrix.rs:204-223,
+ * and the two bytes are written into the proof's serialized options). *proof_len: in = capacity, out = bytes written. */
 int wf_prove_fib(wf_ctx* ctx, const uint64_t* const* trace_cols, int mont, uint32_t k, uint32_t log_n,
                  const uint64_t* results, const uint32_t* opts, uint8_t* proof, size_t* proof_len);
 
@@ -222,6 +226,11 @@ int wf_eval_constraints(wf_ctx* ctx, const uint64_t* air_desc, size_t air_desc_l
  * degree < n (CompositionPoly, n x num_cols*ext), their LDE (N x num_cols*ext) and its row commitment */
 int wf_composition_commit(wf_ctx* ctx, int hash_id, const wf_mat* comp_trace, uint32_t log_n, uint32_t blowup, uint32_t ext,
                           uint32_t num_cols, wf_mat** polys, wf_mat** lde, wf_tree** tree);
+/* same with the PartitionOptions argument of build_constraint_commitment (lib.rs:220): partition_size in BASE columns =
+ * PartitionOptions::partition_size::<E>(num_cols) * ext (0 or num_cols * ext = whole rows), as wf_commit_rows_partitioned */
+int wf_composition_commit_partitioned(wf_ctx* ctx, int hash_id, const wf_mat* comp_trace, uint32_t log_n, uint32_t blowup,
+                                      uint32_t ext, uint32_t num_cols, uint32_t partition_size, wf_mat** polys, wf_mat** lde,
+                                      wf_tree** tree);
 /* ColMatrix::evaluate_columns_at (prover/src/matrix/col_matrix.rs:245) at two points of E (z and z*g for
  * TracePolyTable::get_ood_frame, trace/poly_table.rs:68-76; CompositionPoly::get_ood_frame,
  * composition_poly.rs:101-108). col_ext = 1: base columns; col_ext = ext: the matrix holds columns of E
@@ -246,7 +255,7 @@ int wf_grind(wf_ctx* ctx, int hash_id, const uint8_t seed[32], uint32_t grinding
  * hashing, constraint evaluation, DEEP composition and the first FRI layers run on row shards; every Merkle tree is a
  * local subtree per rank plus log2(world) top levels built from an all-gather of the subtree roots; query openings are
  * gathered from their owners. The proof is byte-identical to wf_prove_fib's on one GPU.
- * The host program supplies the collectives (torch.distributed / NCCL in bench.py; any MPI-like layer works): */
+ * The host program supplies the collectives (NCCL point-to-point in bench.py; any MPI-like layer works): */
 typedef struct wf_comm {
     void* user;
     int rank, world; /* world: a power of two */
@@ -288,6 +297,10 @@ int wf_fri_fold_dev(wf_ctx* ctx, const uint64_t* d_evals, size_t len, int ext_de
  * d_out holds 22 n words. */
 #define WF_FIELD_TEST_SHIFTS {1, 3, 6, 12, 24, 31, 32, 33, 48, 63, 64, 65, 72, 80, 84, 90, 95, 96}
 int wf_field_ops_dev(wf_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, size_t n, uint64_t* d_out);
+/* extension-field arithmetic of the device code (ExtensibleField<2> / <3> for BaseElement, math/src/field/f64/mod.rs:401-499;
+ * inverses extensions/quadratic.rs:81-94, cubic.rs:81-97): a, b = n elements of `ext` (2 | 3) canonical words each (device);
+ * d_out = 6 blocks of n elements: a*b, 1/a (0 for 0), frobenius(a), a.mul_base(b[0]), a+b, a-b. */
+int wf_ext_ops_dev(wf_ctx* ctx, uint32_t ext, const uint64_t* d_a, const uint64_t* d_b, size_t n, uint64_t* d_out);
 
 /* ---- host-side helpers of the product (transcript arithmetic; no GPU needed) ------------------- */
 /* H::hash_elements / merge / merge_with_int on the host (crypto/src/hash/mod.rs:31-64) */

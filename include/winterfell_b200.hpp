@@ -71,11 +71,22 @@ inline Elem e_mul(int d, const Elem& a, const Elem& b) {
 
 // ---- air::ProofOptions (air/src/options.rs:132) ----
 enum class BatchingMethod : u32 { Linear = 0, Algebraic = 1, Horner = 2 };
+// air::PartitionOptions (air/src/options.rs:405-445)
+struct PartitionOptions {
+    u32 num_partitions = 1, hash_rate = 1;
+    // partition_size::<E>(num_columns), E of extension degree `ext_degree`, in columns of E (:428-438)
+    u32 partition_size(u32 ext_degree, u32 num_columns) const {
+        if (num_partitions == 1) return num_columns;
+        const u32 min_partition_size = hash_rate / ext_degree, per = (num_columns + num_partitions - 1) / num_partitions;
+        return per > min_partition_size ? per : min_partition_size;
+    }
+};
 struct ProofOptions {
     u32 num_queries = 28, blowup_factor = 8, grinding_factor = 0, field_extension = 1, fri_folding_factor = 4,
         fri_remainder_max_degree = 7;
     BatchingMethod batching_constraints = BatchingMethod::Linear, batching_deep = BatchingMethod::Linear;
     int hash_id = WF_HASH_BLAKE3_256;
+    PartitionOptions partition_options;  // ProofOptions::with_partitions (options.rs:193-200)
 };
 
 // ---- Air (air/src/air/mod.rs:174): the flat description the device evaluator consumes ----
@@ -251,15 +262,18 @@ class TraceLde {
     wf_ctx* ctx;
     int hash_id;
     u32 log_n, blowup_factor, ext;
+    PartitionOptions partition_options;
     wf_mat *main_lde = nullptr, *aux_lde = nullptr;
     wf_tree *main_tree = nullptr, *aux_tree = nullptr;
     TracePolyTable polys;
 
     // DefaultTraceLde::new (:63-100): interpolate, extend, commit the main segment
-    TraceLde(wf_ctx* c, int h, const u64* const* main_trace_cols, u32 width, u32 log_n_, u32 blowup, u32 ext_, int mont)
-        : ctx(c), hash_id(h), log_n(log_n_), blowup_factor(blowup), ext(ext_) {
+    TraceLde(wf_ctx* c, int h, const u64* const* main_trace_cols, u32 width, u32 log_n_, u32 blowup, u32 ext_, int mont,
+             PartitionOptions partition_options_ = PartitionOptions())
+        : ctx(c), hash_id(h), log_n(log_n_), blowup_factor(blowup), ext(ext_), partition_options(partition_options_) {
         check(ctx, wf_trace_lde_from_host(ctx, main_trace_cols, width, (size_t)1 << log_n, mont, log2(blowup), &polys.main_polys, &main_lde));
-        check(ctx, wf_commit_rows(ctx, hash_id, main_lde, &main_tree));
+        // build_trace_commitment::<E, E::BaseField, ..> (:71): the main segment is a matrix over the base field
+        check(ctx, wf_commit_rows_partitioned(ctx, hash_id, main_lde, partition_options.partition_size(1, width), &main_tree));
     }
     ~TraceLde() {
         for (wf_mat* m : {main_lde, aux_lde, polys.main_polys, polys.aux_polys}) if (m) wf_mat_free(ctx, m);
@@ -278,7 +292,7 @@ class TraceLde {
         check(ctx, wf_mat_interpolate(ctx, trace, &polys.aux_polys));
         wf_mat_free(ctx, trace);
         check(ctx, wf_mat_lde(ctx, polys.aux_polys, log2(blowup_factor), &aux_lde));
-        check(ctx, wf_commit_rows(ctx, hash_id, aux_lde, &aux_tree));
+        check(ctx, wf_commit_rows_partitioned(ctx, hash_id, aux_lde, partition_options.partition_size(ext, aux_width) * ext, &aux_tree));
         check(ctx, wf_tree_root(ctx, aux_tree, root));
     }
     // read_main_trace_frame_into (:169-180): rows lde_step and (lde_step + blowup) mod N
@@ -337,8 +351,11 @@ class ConstraintCommitment {
     wf_mat *composition_poly = nullptr, *lde = nullptr;  // CompositionPoly columns; their LDE
     wf_tree* tree = nullptr;
     // Prover::build_constraint_commitment (lib.rs:215-223); consumes the composition trace
-    ConstraintCommitment(CompositionPolyTrace trace, int hash_id, u32 num_columns, u32 log_n, u32 blowup, u32 ext) : ctx(trace.ctx) {
-        int rc = wf_composition_commit(ctx, hash_id, trace.evaluations, log_n, blowup, ext, num_columns, &composition_poly, &lde, &tree);
+    ConstraintCommitment(CompositionPolyTrace trace, int hash_id, u32 num_columns, u32 log_n, u32 blowup, u32 ext,
+                         PartitionOptions partition_options = PartitionOptions())
+        : ctx(trace.ctx) {
+        int rc = wf_composition_commit_partitioned(ctx, hash_id, trace.evaluations, log_n, blowup, ext, num_columns,
+                                                   partition_options.partition_size(ext, num_columns) * ext, &composition_poly, &lde, &tree);
         wf_mat_free(ctx, trace.evaluations);
         check(ctx, rc);
     }
@@ -442,7 +459,7 @@ class ProverChannel {
         w.write_u8(8); w.write_u64(P);
         w.write_u8((u8)o.num_queries); w.write_u8((u8)o.blowup_factor); w.write_u8((u8)o.grinding_factor); w.write_u8((u8)o.field_extension);
         w.write_u8((u8)o.fri_folding_factor); w.write_u8((u8)o.fri_remainder_max_degree); w.write_u8((u8)o.batching_constraints);
-        w.write_u8((u8)o.batching_deep); w.write_u8(1); w.write_u8(1);
+        w.write_u8((u8)o.batching_deep); w.write_u8((u8)o.partition_options.num_partitions); w.write_u8((u8)o.partition_options.hash_rate);
         w.write_usize(air.num_transition_constraints() + air.num_all_assertions());
         w.write_u8((u8)num_unique_queries);
         w.write_u16((uint16_t)commitments.v.size()); w.write_bytes(commitments.v.data(), commitments.v.size());
@@ -501,7 +518,7 @@ inline std::vector<u8> generate_proof(wf_ctx* ctx, const Air& air, const u64* co
     const size_t n = (size_t)1 << log_n;
     ProverChannel channel(air, options, log_n);                                            // :296-297
     // 1 ----- commit to the execution trace (:304-349)
-    TraceLde trace_lde(ctx, options.hash_id, main_trace_cols, air.trace_width, log_n, options.blowup_factor, d, mont);
+    TraceLde trace_lde(ctx, options.hash_id, main_trace_cols, air.trace_width, log_n, options.blowup_factor, d, mont, options.partition_options);
     u8 root[32];
     trace_lde.get_main_trace_commitment(root);
     channel.commit_trace(root);
@@ -519,7 +536,8 @@ inline std::vector<u8> generate_proof(wf_ctx* ctx, const Air& air, const u64* co
     CompositionPolyTrace composition_poly_trace = evaluator.evaluate(trace_lde);
     // 3 ----- commit to constraint evaluations (:381-384, :527-552)
     const u32 num_quotients = air.num_constraint_composition_columns(n);
-    ConstraintCommitment constraint_commitment(composition_poly_trace, options.hash_id, num_quotients, log_n, options.blowup_factor, d);
+    ConstraintCommitment constraint_commitment(composition_poly_trace, options.hash_id, num_quotients, log_n, options.blowup_factor, d,
+                                               options.partition_options);
     constraint_commitment.commitment(root);
     channel.commit_constraints(root);
     // 4 ----- build DEEP composition polynomial (:386-440)

@@ -333,8 +333,12 @@ class RandomCoin:
 
 
 # ---- full prover / verifier restatement (oracle/wf_prover.cpp) ----
-def make_opts(num_queries=28, blowup=8, grinding=0, ext=1, folding=4, rem_max_deg=7, batch_c=0, batch_d=0, hash_id=BLAKE3):
-    return np.array([num_queries, blowup, grinding, ext, folding, rem_max_deg, batch_c, batch_d, hash_id], dtype=np.uint32)
+def make_opts(num_queries=28, blowup=8, grinding=0, ext=1, folding=4, rem_max_deg=7, batch_c=0, batch_d=0, hash_id=BLAKE3,
+              num_partitions=1, hash_rate=1):
+    """ProofOptions::new(...).with_partitions(num_partitions, hash_rate) (air/src/options.rs:132-200) as the opts[9] array
+    of the C ABI: the partition options ride in opts[8] above the hash id (0 = the default 1, 1)."""
+    part = 0 if (num_partitions, hash_rate) == (1, 1) else (num_partitions << 8) | (hash_rate << 16)
+    return np.array([num_queries, blowup, grinding, ext, folding, rem_max_deg, batch_c, batch_d, hash_id | part], dtype=np.uint32)
 
 
 def build_fib_trace(k, n):

@@ -557,7 +557,8 @@ static void merge_with_int(int h, const u8 seed[32], u64 value, u8 out[32]) {
 
 static void hash_rows(int h, const u64* rows, size_t nrows, size_t w, size_t part, u8* digests) {
     // row_matrix.rs:184-228 (batch_iter_mut! with min batch 128 -> static row batches)
-    if (part >= w || part == 0) {
+    if (part == w || part == 0) {  // partition_size == num_cols (row_matrix.rs:193); a partition size ABOVE the width (hash_rate
+                                    // larger than the row) takes the other branch with one partition: merge_many of one digest
 #pragma omp parallel for schedule(static)
         for (size_t i = 0; i < nrows; i++) hash_elements(h, rows + i * w, w, digests + i * 32);
     } else {

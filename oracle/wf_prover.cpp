@@ -19,11 +19,16 @@
 
 #include "wf_oracle.cpp"
 
+extern "C" size_t wfo_partition_size(size_t num_partitions, size_t hash_rate, size_t ext_degree, size_t num_columns);
+
 namespace {
 
 struct Opts {
     u32 num_queries, blowup, grinding, ext, folding, rem_max_deg, batch_c, batch_d, num_partitions, hash_rate;
     int hash_id;
+    // PartitionOptions::partition_size::<E>(num_columns) in BASE elements (air/src/options.rs:428-438): `cols` columns of
+    // extension degree `deg`; == cols * deg when the row is hashed whole
+    size_t part_words(size_t cols, size_t deg) const { return wfo_partition_size(num_partitions, hash_rate, deg, cols) * deg; }
 };
 
 struct EE {  // extension element of degree <= 3
@@ -461,7 +466,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[w][n]*/,
     std::vector<u64> lde(N * c);
     lde_rows(polys.data(), c, n, 1, b, lde.data());
     std::vector<u8> t_leaves(N * 32), t_nodes(N * 32);
-    hash_rows(h, lde.data(), N, c, c, t_leaves.data());
+    hash_rows(h, lde.data(), N, c, o.part_words(c, 1), t_leaves.data());  // row_matrix.rs:191 with E = BaseField
     merkle_nodes(h, t_leaves.data(), N, t_nodes.data());
     commitments.bytes(t_nodes.data() + 32, 32);
     coin.reseed(t_nodes.data() + 32);
@@ -480,7 +485,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[w][n]*/,
         alde.resize(N * aw * d);
         lde_rows(apolys.data(), aw, n, d, b, alde.data());
         a_leaves.resize(N * 32); a_nodes.resize(N * 32);
-        hash_rows(h, alde.data(), N, aw * d, aw * d, a_leaves.data());
+        hash_rows(h, alde.data(), N, aw * d, o.part_words(aw, d), a_leaves.data());
         merkle_nodes(h, a_leaves.data(), N, a_nodes.data());
         commitments.bytes(a_nodes.data() + 32, 32);
         coin.reseed(a_nodes.data() + 32);
@@ -583,7 +588,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[w][n]*/,
     std::vector<u64> clde(N * kc * d);
     lde_rows(cpolys.data(), kc, n, d, b, clde.data());
     std::vector<u8> c_leaves(N * 32), c_nodes(N * 32);
-    hash_rows(h, clde.data(), N, kc * d, kc * d, c_leaves.data());
+    hash_rows(h, clde.data(), N, kc * d, o.part_words(kc, d), c_leaves.data());
     merkle_nodes(h, c_leaves.data(), N, c_nodes.data());
     commitments.bytes(c_nodes.data() + 32, 32);
     coin.reseed(c_nodes.data() + 32);
@@ -1000,19 +1005,20 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
     pos.erase(std::unique(pos.begin(), pos.end()), pos.end());
     if (pos.size() != nuq) return V_MALFORMED;
     // trace / constraint queries (verifier/src/channel.rs:206-260)
-    auto check_q = [&](const std::vector<u8>& vals, const std::vector<u8>& pr, size_t row_words, const u8* root) {
+    // hash_row (verifier/src/channel.rs:431-453): rows are re-hashed in partitions of `part` base elements
+    auto check_q = [&](const std::vector<u8>& vals, const std::vector<u8>& pr, size_t row_words, size_t part, const u8* root) {
         if (vals.size() != pos.size() * row_words * 8) return false;
         std::vector<std::array<u8, 32>> lv(pos.size());
-        for (size_t i = 0; i < pos.size(); i++) hash_elements(h, (const u64*)(vals.data() + i * row_words * 8), row_words, lv[i].data());
+        for (size_t i = 0; i < pos.size(); i++) hash_rows(h, (const u64*)(vals.data() + i * row_words * 8), 1, row_words, part, lv[i].data());
         Reader pr_r{pr.data(), pr.size()};
         BatchProof bp;
         if (!read_batch_proof(pr_r, bp) || pr_r.pos != pr.size() || ((size_t)1 << bp.depth) != N) return false;
         u8 got[32];
         return batch_root(h, bp, pos, lv, got) && !memcmp(got, root, 32);
     };
-    if (!check_q(tq_vals, tq_pr, c, trace_root)) return V_TRACE_QUERY;
-    if (air.aw && !check_q(aq_vals, aq_pr, air.aw * d, aux_root)) return V_TRACE_QUERY;  // channel.rs:206-240
-    if (!check_q(cq_vals, cq_pr, kc * d, cons_root)) return V_CONSTRAINT_QUERY;
+    if (!check_q(tq_vals, tq_pr, c, o.part_words(c, 1), trace_root)) return V_TRACE_QUERY;
+    if (air.aw && !check_q(aq_vals, aq_pr, air.aw * d, o.part_words(air.aw, d), aux_root)) return V_TRACE_QUERY;  // channel.rs:206-240
+    if (!check_q(cq_vals, cq_pr, kc * d, o.part_words(kc, d), cons_root)) return V_CONSTRAINT_QUERY;
     // DEEP composition at the query positions (verifier/src/composer.rs)
     u64 g_lde = root_of_unity((u32)__builtin_ctzll(N)), g_tr = root_of_unity((u32)__builtin_ctzll(n));
     EE zg = F.mul_base(z, g_tr);
@@ -1111,11 +1117,16 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
 }  // namespace
 
 extern "C" {
-// opts: [num_queries, blowup, grinding, ext, folding, rem_max_deg, batch_constraints, batch_deep, hash_id]
+// opts: [num_queries, blowup, grinding, ext, folding, rem_max_deg, batch_constraints, batch_deep,
+//        hash_id | num_partitions << 8 | hash_rate << 16]  (ProofOptions::with_partitions, air/src/options.rs:193-200;
+//        0 in either partition field = the default PartitionOptions::new(1, 1))
 static Opts make_opts(const uint32_t* v) {
     Opts o;
     o.num_queries = v[0]; o.blowup = v[1]; o.grinding = v[2]; o.ext = v[3]; o.folding = v[4]; o.rem_max_deg = v[5];
-    o.batch_c = v[6]; o.batch_d = v[7]; o.hash_id = (int)v[8]; o.num_partitions = 1; o.hash_rate = 1;
+    o.batch_c = v[6]; o.batch_d = v[7]; o.hash_id = (int)(v[8] & 0xff);
+    o.num_partitions = (v[8] >> 8) & 0xff; o.hash_rate = (v[8] >> 16) & 0xff;
+    if (o.num_partitions == 0) o.num_partitions = 1;
+    if (o.hash_rate == 0) o.hash_rate = 1;
     return o;
 }
 // trace: [2k][n] canonical words; results: k words. Returns proof length (bytes written to out), or -1.

@@ -29,7 +29,13 @@ int main(int argc, char** argv) {
     ProofOptions o;
     o.num_queries = (u32)w[p++]; o.blowup_factor = (u32)w[p++]; o.grinding_factor = (u32)w[p++]; o.field_extension = (u32)w[p++];
     o.fri_folding_factor = (u32)w[p++]; o.fri_remainder_max_degree = (u32)w[p++];
-    o.batching_constraints = (BatchingMethod)w[p++]; o.batching_deep = (BatchingMethod)w[p++]; o.hash_id = (int)w[p++];
+    o.batching_constraints = (BatchingMethod)w[p++]; o.batching_deep = (BatchingMethod)w[p++];
+    {   // hash_id | num_partitions << 8 | hash_rate << 16 (the packing of opts[8] in winterfell_b200.h)
+        const u64 h = w[p++];
+        o.hash_id = (int)(h & 0xff);
+        if ((h >> 8) & 0xff) o.partition_options.num_partitions = (u32)((h >> 8) & 0xff);
+        if ((h >> 16) & 0xff) o.partition_options.hash_rate = (u32)((h >> 16) & 0xff);
+    }
     const size_t desc_len = w[p++];
     std::vector<u64> desc(w.begin() + p, w.begin() + p + desc_len);
     p += desc_len;

@@ -248,6 +248,90 @@ def test_field_ops_edge_cases(ctx):
             assert int(got[4 + k, i]) == (x << sh) % P, ("shift", sh, hex(x))
 
 
+def _py_ext_mul(d, a, b):
+    P = wf.P
+    if d == 2:   # x^2 = x - 2 (math/src/field/f64/mod.rs:403-409)
+        return [(a[0] * b[0] - 2 * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0] + a[1] * b[1]) % P]
+    # x^3 = x + 1 (mod.rs:445-466)
+    c = [0] * 5
+    for i in range(3):
+        for j in range(3):
+            c[i + j] += a[i] * b[j]
+    c[2] += c[4]; c[1] += c[4]      # x^4 = x^2 + x
+    c[1] += c[3]; c[0] += c[3]      # x^3 = x + 1
+    return [c[0] % P, c[1] % P, c[2] % P]
+
+
+def _py_ext_pow(d, a, e):
+    r = [1] + [0] * (d - 1)
+    while e:
+        if e & 1:
+            r = _py_ext_mul(d, r, a)
+        a = _py_ext_mul(d, a, a)
+        e >>= 1
+    return r
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_extension_field_ops_on_reference_vectors(ctx, d):
+    """Device quadratic / cubic extension arithmetic (gl64.cuh ext_mul / ext_inv / ext_frobenius / ext_mul_base) on the
+    reference's own product vectors, including its two overflow cases per extension (math/src/field/f64/tests.rs:220-246,
+    288-345), its conjugate vectors (:259-283), and on edge / random operands against big-integer arithmetic in the
+    quotient ring; inverses are checked by a * a^-1 = 1 and against a^(p^d - 2)."""
+    import torch
+    P = wf.P
+    m = P
+    if d == 2:
+        kat = [([3, 1], [4, 2], [8, 12]), ([3, m - 1], [m - 3, 5], [1, 13]), ([3, m - 1], [10, m - 2], [26, 18446744069414584307])]
+        conj = [([m - 1, 3], [2, 18446744069414584318]), ([m - 3, m - 2], [18446744069414584316, 2]), ([4, 7], [11, 18446744069414584314])]
+    else:
+        kat = [([3, 5, 2], [320, 68, 3], [1111, 1961, 995]),
+               ([18446744069414584267, 18446744069414584309, 9223372034707292160], [18446744069414584101, 420, 18446744069414584121],
+                [14070, 18446744069414566571, 5970]),
+               ([18446744069414584266, 18446744069412558094, 5268562], [18446744069414583589, 1226, 5346],
+                [18446744065041672051, 25275910656, 21824696736])]
+        conj = []
+    for a, b, want in kat:   # the test's own model must reproduce the reference vectors first
+        assert _py_ext_mul(d, a, b) == want
+    rng = np.random.default_rng(7 + d)
+    edge = [0, 1, 2, P - 1, P - 2, 2**32 - 1, 2**32, P - 2**32, 2**63]
+    A = [k[0] for k in kat] + [c[0] for c in conj]
+    B = [k[1] for k in kat] + [[1] + [0] * (d - 1) for _ in conj]
+    for _ in range(300):
+        A.append([edge[int(rng.integers(0, len(edge)))] for _ in range(d)])
+        B.append([edge[int(rng.integers(0, len(edge)))] for _ in range(d)])
+    for _ in range(1500):
+        A.append([int(rng.integers(0, 2**63)) * 2 % P for _ in range(d)])
+        B.append([int(rng.integers(0, 2**63)) * 2 % P for _ in range(d)])
+    n = len(A)
+    ta = torch.from_numpy(np.array(A, dtype=np.uint64).view(np.int64)).cuda()
+    tb = torch.from_numpy(np.array(B, dtype=np.uint64).view(np.int64)).cuda()
+    out = torch.empty(6 * n * d, dtype=torch.int64, device="cuda")
+    ctx.ext_ops_dev(d, ta.data_ptr(), tb.data_ptr(), n, out.data_ptr())
+    ctx.sync()
+    got = out.cpu().numpy().view(np.uint64).reshape(6, n, d)
+    for i, (a, b, want) in enumerate(kat):
+        assert [int(v) for v in got[0, i]] == want
+    for i, (a, want) in enumerate(conj):
+        assert [int(v) for v in got[2, len(kat) + i]] == want     # Frobenius = conjugation in the quadratic extension
+    one = [1] + [0] * (d - 1)
+    for i in range(n):
+        a, b = A[i], B[i]
+        assert [int(v) for v in got[0, i]] == _py_ext_mul(d, a, b), ("mul", a, b)
+        inv = [int(v) for v in got[1, i]]
+        if any(a):
+            assert _py_ext_mul(d, a, inv) == one, ("inv", a)
+        else:
+            assert inv == [0] * d
+        assert [int(v) for v in got[2, i]] == _py_ext_pow(d, a, P), ("frobenius", a)
+        assert [int(v) for v in got[3, i]] == [x * b[0] % P for x in a]
+        assert [int(v) for v in got[4, i]] == [(x + y) % P for x, y in zip(a, b)]
+        assert [int(v) for v in got[5, i]] == [(x - y) % P for x, y in zip(a, b)]
+    for i in range(0, 40):  # a^-1 == a^(p^d - 2) on a sample (slow in Python)
+        if any(A[i]):
+            assert [int(v) for v in got[1, i]] == _py_ext_pow(d, A[i], P**d - 2)
+
+
 @pytest.mark.parametrize("ncols,log_n", [(8, 13), (16, 12), (12, 13), (3, 12), (5, 14), (8, 9), (24, 12)])
 def test_pipelined_trace_lde_equals_stepwise(ctx, oracle, ncols, log_n):
     # wf_trace_lde_from_host cuts the columns into chunks (whole segments for >= 2 segments, halves of the

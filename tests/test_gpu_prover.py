@@ -235,3 +235,39 @@ def test_overlapping_assertions_are_refused(ctx, oracle):
     B.assert_single(1, 8, 5)                                         # step 8 = 0 + 2 * 4 is covered by the periodic one
     with pytest.raises(wf.WfError, match="overlaps"):
         ctx.prove_air(B.build(), trace, opts)
+
+
+# ProofOptions::with_partitions (air/src/options.rs:193-200) through the one-call entry points: main / aux / constraint rows
+# hashed as merge_many over column partitions (row_matrix.rs:204-223). (G, hash_rate) = (2,8), (4,8), (8,8) are the
+# multi-GPU-motivated settings of SURVEY.md 8e option 2; (4, 64) makes partition_size exceed the row width (one partition,
+# still merge_many); (16, 1) is the maximum partition count.
+@pytest.mark.parametrize("k,log_n,ext,h,parts,rate", [
+    (4, 10, 1, wf.HASH_BLAKE3_256, 2, 8), (4, 10, 3, wf.HASH_BLAKE3_256, 4, 8), (32, 9, 3, wf.HASH_BLAKE3_256, 8, 8),
+    (8, 9, 2, wf.HASH_RP64_256, 2, 8), (4, 9, 1, wf.HASH_RP64_256, 8, 8), (1, 9, 3, wf.HASH_BLAKE3_256, 4, 64),
+    (16, 9, 1, wf.HASH_BLAKE3_256, 16, 1)])
+def test_partitioned_commitments_match_oracle(ctx, oracle, k, log_n, ext, h, parts, rate):
+    trace, results = oracle.build_fib_trace(k, 1 << log_n)
+    opts = oracle.make_opts(num_queries=24, grinding=3, ext=ext, folding=4, rem_max_deg=7, hash_id=h, num_partitions=parts, hash_rate=rate)
+    want = oracle.prove_fib(trace, results, opts)
+    got = ctx.prove_fib(trace, results, opts)
+    assert got == want
+    assert oracle.verify_fib(got, k, results, h) == 0
+    assert got != ctx.prove_fib(trace, results, oracle.make_opts(num_queries=24, grinding=3, ext=ext, folding=4, rem_max_deg=7, hash_id=h))
+
+
+@pytest.mark.parametrize("ext,h,parts,rate", [(2, wf.HASH_BLAKE3_256, 2, 2), (3, wf.HASH_RP64_256, 3, 8)])
+def test_partitioned_aux_segment_vs_oracle(ctx, oracle, ext, h, parts, rate):
+    # the auxiliary commitment uses partition_size::<E>(aux_width) (trace_lde/default/mod.rs:147), the constraint commitment
+    # partition_size::<E>(num composition columns) (constraints/commitment/default.rs:147)
+    desc, trace, builder = airs.perm_rap(1 << 8)
+    opts = oracle.make_opts(num_queries=20, grinding=2, ext=ext, folding=4, rem_max_deg=7, hash_id=h, num_partitions=parts, hash_rate=rate)
+    got = ctx.prove_air_aux(desc, trace, opts, builder, airs.PERM_RAP_AUX_WIDTH, 2)
+    assert got == oracle.prove_air_aux(desc, trace, opts, builder, airs.PERM_RAP_AUX_WIDTH, 2)
+    assert oracle.verify_air(desc, got, h) == 0
+
+
+def test_too_many_partitions_refused(ctx, oracle):
+    trace, results = oracle.build_fib_trace(1, 256)
+    opts = oracle.make_opts(num_partitions=17, hash_rate=8)   # PartitionOptions::new asserts <= 16 (air/src/options.rs:413-414)
+    with pytest.raises(wf.WfError):
+        ctx.prove_fib(trace, results, opts)

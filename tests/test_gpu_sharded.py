@@ -41,3 +41,8 @@ def test_sharded_proof_default_fri_threshold_and_device_trace():
 
 def test_sharded_proof_rp64():
     _run(2, 8, 12, 1, hash_id=1, fri_min_log=6)
+
+
+def test_sharded_proof_with_partitions():
+    # ProofOptions::with_partitions(2, 8) (hash_id | 2 << 8 | 8 << 16): the row shards hash column partitions like one GPU does
+    _run(2, 8, 12, 3, hash_id=0 | (2 << 8) | (8 << 16), fri_min_log=6)

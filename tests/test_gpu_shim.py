@@ -64,6 +64,17 @@ def test_cpp_generate_proof_double(ctx, oracle, tmp_path, name, log_n, ext, h, b
     assert oracle.verify_air(desc, got, h) == 0
 
 
+def test_cpp_double_with_partitions(ctx, oracle, tmp_path):
+    # new_trace_lde / build_constraint_commitment take the PartitionOptions (prover/src/lib.rs:187,220): the C++ mirror passes
+    # them to wf_commit_rows_partitioned / wf_composition_commit_partitioned
+    desc, trace = airs.fib_small_x(4, 512)
+    opts = oracle.make_opts(num_queries=20, grinding=3, ext=3, folding=4, rem_max_deg=7, num_partitions=4, hash_rate=8)
+    got = run_double(tmp_path, desc, trace, opts)
+    assert got == ctx.prove_air(desc, trace, opts)
+    assert got == oracle.prove_air(desc, trace, opts)
+    assert oracle.verify_air(desc, got, 0) == 0
+
+
 def test_cpp_double_montgomery_trace(ctx, oracle, tmp_path):
     # a Rust caller hands over &[BaseElement] memory = Montgomery words (math/src/field/f64/mod.rs:57-64)
     desc, trace = airs.mulfib2(256)

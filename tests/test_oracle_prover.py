@@ -123,3 +123,24 @@ def test_oracle_reproduces_golden_proof_digests(oracle, idx):
         desc, trace = getattr(airs, rec["air"])(rec["n"])
         proof = oracle.prove_air(desc, trace, opts)
     assert len(proof) == rec["bytes"] and hashlib.sha256(proof).hexdigest() == rec["sha256"]
+
+
+@pytest.mark.parametrize("k,ext,h,parts,rate", [(4, 1, 0, 2, 8), (4, 3, 0, 4, 8), (8, 1, 0, 8, 8), (4, 2, 1, 2, 8), (1, 3, 0, 4, 64)])
+def test_partitioned_commitments_round_trip(oracle, k, ext, h, parts, rate):
+    # ProofOptions::with_partitions (air/src/options.rs:193-200): rows are hashed as merge_many of the digests of their
+    # column partitions (row_matrix.rs:204-223) and the verifier re-hashes the queried rows the same way
+    # (verifier/src/channel.rs:431-453); the last case has partition_size > row width: ONE partition, still merge_many
+    n = 256
+    trace, res = oracle.build_fib_trace(k, n)
+    plain = oracle.prove_fib(trace, res, oracle.make_opts(ext=ext, hash_id=h, grinding=2))
+    opts = oracle.make_opts(ext=ext, hash_id=h, grinding=2, num_partitions=parts, hash_rate=rate)
+    proof = oracle.prove_fib(trace, res, opts)
+    assert oracle.verify_fib(proof, k, res, h) == 0
+    assert proof != plain
+    # the partition options travel in the proof's serialized ProofOptions (options.rs:318-319): a verifier told otherwise
+    # re-hashes the rows differently and must reject
+    i = next(j for j in range(len(proof)) if proof[j] != plain[j])
+    assert (proof[i], proof[i + 1]) == (parts, rate) and (plain[i], plain[i + 1]) == (1, 1)
+    t = bytearray(proof)
+    t[i], t[i + 1] = 1, 1
+    assert oracle.verify_fib(bytes(t), k, res, h) != 0

@@ -389,6 +389,22 @@ __global__ void field_ops_kernel(const u64* a, const u64* b, size_t n, u64* out)
     field_shift_store<90>(x, out, n, i, 15); field_shift_store<95>(x, out, n, i, 16); field_shift_store<96>(x, out, n, i, 17);
 }
 
+// extension-field KAT kernel: out[0] = a * b, out[1] = a^-1, out[2] = frobenius(a), out[3] = a.mul_base(b[0]),
+// out[4] = a + b, out[5] = a - b, each [n][D] (ExtensibleField<2>/<3> for BaseElement, math/src/field/f64/mod.rs:401-499)
+template <int D>
+__global__ void ext_ops_kernel(const u64* a, const u64* b, size_t n, u64* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    GlExt<D> x, y;
+#pragma unroll
+    for (int q = 0; q < D; q++) { x.v[q] = a[i * D + q]; y.v[q] = b[i * D + q]; }
+    const GlExt<D> r[6] = {ext_mul(x, y), ext_inv(x), ext_frobenius(x), ext_mul_base(x, y.v[0]), ext_add(x, y), ext_sub(x, y)};
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+#pragma unroll
+        for (int q = 0; q < D; q++) out[((size_t)k * n + i) * D + q] = r[k].v[q];
+}
+
 template <int K>
 static u64 m2e(u64 x) { return gl_mul_2exp<K>(x); }
 
@@ -742,7 +758,7 @@ static u32 merkle_launches(size_t nleaves) {
 int wf_commit_rows_partitioned(wf_ctx* ctx, int hash_id, const wf_mat* m, uint32_t partition_size, wf_tree** out) {
     if (!ctx || !m || !out) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     if (hash_id != WF_HASH_BLAKE3_256 && hash_id != WF_HASH_RP64_256) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "unknown hash %d", hash_id);
-    if (partition_size != 0 && partition_size < m->m.cols && (m->m.cols + partition_size - 1) / partition_size > 16)
+    if (partition_size != 0 && partition_size != m->m.cols && (m->m.cols + partition_size - 1) / partition_size > 16)
         return wf_fail(ctx, WF_ERR_INVALID, "more than 16 partitions");
     wf_tree* t;
     CKI(tree_alloc(ctx, hash_id, m->m.rows, &t));
@@ -1250,6 +1266,15 @@ int wf_merkle_dev(wf_ctx* ctx, int hash_id, const uint8_t* d_leaves, size_t nlea
 int wf_field_ops_dev(wf_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, size_t n, uint64_t* d_out) {
     if (!ctx || !d_a || !d_b || !d_out || n == 0) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     field_ops_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->st>>>(d_a, d_b, n, d_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return WF_OK;
+}
+int wf_ext_ops_dev(wf_ctx* ctx, uint32_t ext, const uint64_t* d_a, const uint64_t* d_b, size_t n, uint64_t* d_out) {
+    if (!ctx || !d_a || !d_b || !d_out || n == 0 || (ext != 2 && ext != 3)) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    if (ext == 2) ext_ops_kernel<2><<<blocks, 128, 0, ctx->st>>>(d_a, d_b, n, d_out);
+    else ext_ops_kernel<3><<<blocks, 128, 0, ctx->st>>>(d_a, d_b, n, d_out);
     ctx->launches++;
     CK(cudaGetLastError());
     return WF_OK;

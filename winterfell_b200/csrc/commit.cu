@@ -267,7 +267,7 @@ cudaError_t commit_hash_rows(int hash_id, const SegMatrix& m, u64* digests, cuda
     RowSrc src;
     src.base = m.base; src.seg_stride = m.seg_stride; src.W = m.W; src.cols = m.cols;
     src.logW = m.W == 8 ? 3 : m.W == 4 ? 2 : m.W == 2 ? 1 : 0;
-    if (partition_size != 0 && partition_size < m.cols) {
+    if (partition_size != 0 && partition_size != m.cols) {  // > cols: one partition, still merge_many (row_matrix.rs:204-223)
         if ((m.cols + partition_size - 1) / partition_size > 16) return cudaErrorInvalidValue;
         hash_rows_partitioned_kernel<<<(unsigned)((m.rows + 127) / 128), 128, 0, st>>>(hash_id, src, m.rows, partition_size, digests);
         return cudaGetLastError();

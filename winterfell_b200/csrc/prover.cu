@@ -599,6 +599,13 @@ namespace {
 struct Options {
     u32 num_queries, blowup, grinding, ext, folding, rem_max_deg, batch_c, batch_d, num_partitions, hash_rate;
     int hash_id;
+    // PartitionOptions::partition_size::<E>(num_columns) (air/src/options.rs:428-438) in BASE columns, for `cols` columns of
+    // extension degree `deg`; cols * deg = the row is hashed whole (RowMatrix::commit_to_rows, row_matrix.rs:191-193)
+    u32 part_words(u32 cols, u32 deg) const {
+        if (num_partitions <= 1) return cols * deg;
+        const u32 min_ps = hash_rate / deg, ps = (cols + num_partitions - 1) / num_partitions;
+        return (ps > min_ps ? ps : min_ps) * deg;
+    }
 };
 
 // Host-side AIR description (mirrors oracle/wf_prover.cpp `Air`; flat format documented at
@@ -1132,7 +1139,7 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
 // trace (CE-domain evaluations, ce x D) -> CompositionPoly columns (n x kc*D coefficient matrix,
 // composition_poly.rs:58-78,128-140), their LDE (N x kc*D) and the row commitment.
 int composition_commit(wf_ctx* ctx, int h, const wf_mat* comp, u32 log_n, u32 log_b, int D, u32 kc, wf_mat** polys_out,
-                       wf_mat** lde_out, wf_tree** tree_out) {
+                       wf_mat** lde_out, wf_tree** tree_out, u32 partition_words = 0) {
     const size_t n = (size_t)1 << log_n;
     if (comp->m.rows < n * kc || (int)comp->m.cols != D) return wf_fail(ctx, WF_ERR_INVALID, "composition trace shape");
     wf_mat *ccoefs, *cpolys, *clde;
@@ -1146,7 +1153,7 @@ int composition_commit(wf_ctx* ctx, int h, const wf_mat* comp, u32 log_n, u32 lo
     wf_mark(ctx, "composition_interpolate");
     CKI(wf_mat_lde(ctx, cpolys, log_b, &clde));
     wf_mark(ctx, "composition_lde");
-    if (tree_out) CKI(wf_commit_rows(ctx, h, clde, tree_out));  // sharded proofs commit their own row range
+    if (tree_out) CKI(wf_commit_rows_partitioned(ctx, h, clde, partition_words, tree_out));  // sharded proofs commit their own row range
     *polys_out = cpolys;
     *lde_out = clde;
     return WF_OK;
@@ -1254,7 +1261,7 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
         CKI(wf_trace_lde_from_host(ctx, trace_cols, c, n, mont, log_b, &polys, &lde));
     }
     wf_mark(ctx, "trace_lde");
-    CKI(wf_commit_rows(ctx, h, lde, &ttree));
+    CKI(wf_commit_rows_partitioned(ctx, h, lde, o.part_words(c, 1), &ttree));
     u8 root[32];
     CKI(wf_tree_root(ctx, ttree, root));
     wf_mark(ctx, "trace_commit");
@@ -1277,7 +1284,7 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
         CKI(wf_mat_interpolate(ctx, atrace, &apolys));
         wf_mat_free(ctx, atrace);
         CKI(wf_mat_lde(ctx, apolys, log_b, &alde));
-        CKI(wf_commit_rows(ctx, h, alde, &atree));
+        CKI(wf_commit_rows_partitioned(ctx, h, alde, o.part_words(aw, D), &atree));
         CKI(wf_tree_root(ctx, atree, root));
         wf_mark(ctx, "aux_commit");
         ch.commit(root);
@@ -1290,7 +1297,7 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
     CKI(eval_constraints<D>(ctx, air, lde, alde, cc, rnd_flat, log_n, log_b, &comp));
     wf_mark(ctx, "constraint_eval");
     // ---- 3. composition polynomial + commitment (lib.rs:527-552) ----
-    CKI(composition_commit(ctx, h, comp, log_n, log_b, D, kc, &cpolys, &clde, &ctree));
+    CKI(composition_commit(ctx, h, comp, log_n, log_b, D, kc, &cpolys, &clde, &ctree, o.part_words(kc, D)));
     scope.drop(comp);
     CKI(wf_tree_root(ctx, ctree, root));
     wf_mark(ctx, "composition_commit");
@@ -1559,7 +1566,7 @@ int prove_fib_sharded(wf_ctx* ctx, const wf_comm* cm, const uint64_t* const* loc
     wf_mark(ctx, "trace_exchange");
     // ---- 3. leaves + subtree over my rows, all-gather of the subtree roots ----
     Digest root;
-    CKI(wf_commit_rows(ctx, h, shard, &ttree.local));
+    CKI(wf_commit_rows_partitioned(ctx, h, shard, o.part_words(c, 1), &ttree.local));
     ttree.n_global = N;
     CKI(shard_tree_finish(sc, h, ttree, &root));
     wf_mark(ctx, "trace_commit");
@@ -1579,7 +1586,7 @@ int prove_fib_sharded(wf_ctx* ctx, const wf_comm* cm, const uint64_t* const* loc
     cview.m = clde->m;
     cview.m.base += (size_t)r * rows_per * clde->m.W;
     cview.m.rows = rows_per;
-    CKI(wf_commit_rows(ctx, h, &cview, &ctree.local));
+    CKI(wf_commit_rows_partitioned(ctx, h, &cview, o.part_words(kc, D), &ctree.local));
     ctree.n_global = N;
     CKI(shard_tree_finish(sc, h, ctree, &root));
     wf_mark(ctx, "composition_commit");
@@ -1817,8 +1824,13 @@ extern "C" int wf_grind(wf_ctx* ctx, int hash_id, const uint8_t seed[32], uint32
 
 static int parse_options(wf_ctx* ctx, const uint32_t* opts, Options& o) {
     o.num_queries = opts[0]; o.blowup = opts[1]; o.grinding = opts[2]; o.ext = opts[3]; o.folding = opts[4];
-    o.rem_max_deg = opts[5]; o.batch_c = opts[6]; o.batch_d = opts[7]; o.hash_id = (int)opts[8];
-    o.num_partitions = 1; o.hash_rate = 1;
+    o.rem_max_deg = opts[5]; o.batch_c = opts[6]; o.batch_d = opts[7]; o.hash_id = (int)(opts[8] & 0xff);
+    // ProofOptions::with_partitions (air/src/options.rs:193-200): opts[8] = hash_id | num_partitions << 8 | hash_rate << 16;
+    // 0 in either field is the default PartitionOptions::new(1, 1)
+    o.num_partitions = (opts[8] >> 8) & 0xff; o.hash_rate = (opts[8] >> 16) & 0xff;
+    if (o.num_partitions == 0) o.num_partitions = 1;
+    if (o.hash_rate == 0) o.hash_rate = 1;
+    if (o.num_partitions > 16) return wf_fail(ctx, WF_ERR_INVALID, "at most 16 partitions (air/src/options.rs:413-414)");
     if (o.blowup < 2 || o.blowup > 128 || (o.blowup & (o.blowup - 1)) || o.num_queries == 0 || o.num_queries > 255 || o.batch_c > 2 ||
         o.batch_d > 2 || o.grinding > 32 || o.rem_max_deg > 255 || ((o.rem_max_deg + 1) & o.rem_max_deg) ||
         (o.folding != 2 && o.folding != 4 && o.folding != 8 && o.folding != 16) || o.ext < 1 || o.ext > 3)
@@ -1921,6 +1933,15 @@ extern "C" int wf_composition_commit(wf_ctx* ctx, int hash_id, const wf_mat* com
     u32 log_b = 0;
     while ((1u << log_b) < blowup) log_b++;
     return composition_commit(ctx, hash_id, comp_trace, log_n, log_b, (int)ext, num_cols, polys, lde, tree);
+}
+extern "C" int wf_composition_commit_partitioned(wf_ctx* ctx, int hash_id, const wf_mat* comp_trace, uint32_t log_n, uint32_t blowup,
+                                                 uint32_t ext, uint32_t num_cols, uint32_t partition_size, wf_mat** polys, wf_mat** lde,
+                                                 wf_tree** tree) {
+    if (!ctx || !comp_trace || !polys || !lde || !tree || ext < 1 || ext > 3 || num_cols == 0 || blowup < 2 || (blowup & (blowup - 1)))
+        return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    u32 log_b = 0;
+    while ((1u << log_b) < blowup) log_b++;
+    return composition_commit(ctx, hash_id, comp_trace, log_n, log_b, (int)ext, num_cols, polys, lde, tree, partition_size);
 }
 
 template <int D>
