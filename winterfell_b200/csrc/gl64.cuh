@@ -49,6 +49,17 @@ static inline u64 gl_reduce128_host(u64 lo, u64 hi) {
     return r;
 }
 
+#if defined(__CUDACC__) && defined(GL_RUNTIME_EPS)
+// 2^32 - 1 as a constant-bank operand ptxas cannot fold: with the literal, "x * 0xffffffff + y" is strength-reduced to
+// IMAD.IADD + IMAD.HI.U32 (the latter takes two issue slots of the FMA pipe on the B200); with an opaque multiplier the
+// mad.lo.cc / madc.hi.cc pair becomes ONE IMAD.WIDE.U32 with a carry-out predicate.
+static __constant__ u32 GL_EPS_CONST = 0xffffffffu;
+#define GL_EPS_OPERAND , "r"(GL_EPS_CONST)
+#define GL_EPSM(n) "%" #n
+#else
+#define GL_EPS_OPERAND
+#define GL_EPSM(n) "0xffffffff"
+#endif
 #ifdef __CUDA_ARCH__
 // ---- device forms: explicit carry chains (ncu on the first version showed 35% of all issued
 // instructions were ISETP/SEL pairs from the C conditionals above, on the saturated ALU pipe) ----
@@ -157,18 +168,18 @@ __device__ __forceinline__ u64 gl_reduce128(u64 lo, u64 hi) {
         "subc.u32 m, 0, 0;\n\t"
         "sub.cc.u32 c0, c0, m;\n\t"
         "subc.u32 c1, c1, 0;\n\t"
-        "mad.lo.cc.u32 c0, c2, 0xffffffff, c0;\n\t"
-        "madc.hi.cc.u32 c1, c2, 0xffffffff, c1;\n\t"
+        "mad.lo.cc.u32 c0, c2, " GL_EPSM(3) ", c0;\n\t"
+        "madc.hi.cc.u32 c1, c2, " GL_EPSM(3) ", c1;\n\t"
         "addc.u32 k, 0, 0;\n\t"
         "add.cc.u32 t0, c0, 0xffffffff;\n\t"
         "addc.cc.u32 t1, c1, 0;\n\t"
         "addc.u32 k, k, 0;\n\t"
-        "mad.lo.cc.u32 c0, k, 0xffffffff, c0;\n\t"
-        "madc.hi.u32 c1, k, 0xffffffff, c1;\n\t"
+        "mad.lo.cc.u32 c0, k, " GL_EPSM(3) ", c0;\n\t"
+        "madc.hi.u32 c1, k, " GL_EPSM(3) ", c1;\n\t"
         "mov.b64 %0, {c0, c1};\n\t"
         "}"
         : "=l"(r)
-        : "l"(lo), "l"(hi));
+        : "l"(lo), "l"(hi) GL_EPS_OPERAND);
     return r;
 }
 // 64 x 64 -> 128 as even columns (a0 b0 | a1 b1) plus the odd column a0 b1 + a1 b0 shifted by 32 (ptxas turns the
@@ -197,18 +208,18 @@ __device__ __forceinline__ u64 gl_mul(u64 a, u64 b) {
         "subc.u32 m, 0, 0;\n\t"
         "sub.cc.u32 c0, c0, m;\n\t"
         "subc.u32 c1, c1, 0;\n\t"
-        "mad.lo.cc.u32 c0, c2, 0xffffffff, c0;\n\t"
-        "madc.hi.cc.u32 c1, c2, 0xffffffff, c1;\n\t"
+        "mad.lo.cc.u32 c0, c2, " GL_EPSM(3) ", c0;\n\t"
+        "madc.hi.cc.u32 c1, c2, " GL_EPSM(3) ", c1;\n\t"
         "addc.u32 k, 0, 0;\n\t"
         "add.cc.u32 t0, c0, 0xffffffff;\n\t"
         "addc.cc.u32 t1, c1, 0;\n\t"
         "addc.u32 k, k, 0;\n\t"
-        "mad.lo.cc.u32 c0, k, 0xffffffff, c0;\n\t"
-        "madc.hi.u32 c1, k, 0xffffffff, c1;\n\t"
+        "mad.lo.cc.u32 c0, k, " GL_EPSM(3) ", c0;\n\t"
+        "madc.hi.u32 c1, k, " GL_EPSM(3) ", c1;\n\t"
         "mov.b64 %0, {c0, c1};\n\t"
         "}"
         : "=l"(r)
-        : "l"(a), "l"(b));
+        : "l"(a), "l"(b) GL_EPS_OPERAND);
     return r;
 }
 // x * 2^K for a compile-time K < 96 and canonical x, written on the three words y = x << (K mod 32) (y2 < 2^(K mod 32)):
@@ -225,16 +236,16 @@ __device__ __forceinline__ u64 gl_shl_dev(u64 x) {
     if (K < 32) {
         asm("{\n\t"
             ".reg .u32 r0, r1, k, t0, t1;\n\t"
-            "mad.lo.cc.u32 r0, %3, 0xffffffff, %1;\n\t"
-            "madc.hi.cc.u32 r1, %3, 0xffffffff, %2;\n\t"
+            "mad.lo.cc.u32 r0, %3, " GL_EPSM(4) ", %1;\n\t"
+            "madc.hi.cc.u32 r1, %3, " GL_EPSM(4) ", %2;\n\t"
             "addc.u32 k, 0, 0;\n\t"
             "add.cc.u32 t0, r0, 0xffffffff;\n\t"
             "addc.cc.u32 t1, r1, 0;\n\t"
             "addc.u32 k, k, 0;\n\t"
-            "mad.lo.cc.u32 r0, k, 0xffffffff, r0;\n\t"
-            "madc.hi.u32 r1, k, 0xffffffff, r1;\n\t"
+            "mad.lo.cc.u32 r0, k, " GL_EPSM(4) ", r0;\n\t"
+            "madc.hi.u32 r1, k, " GL_EPSM(4) ", r1;\n\t"
             "mov.b64 %0, {r0, r1};\n\t"
-            "}" : "=l"(o) : "r"(y0), "r"(y1), "r"(y2));
+            "}" : "=l"(o) : "r"(y0), "r"(y1), "r"(y2) GL_EPS_OPERAND);
     } else if (K < 64) {
         asm("{\n\t"
             ".reg .u32 r0, r1, k, m, t0, t1;\n\t"
@@ -243,28 +254,28 @@ __device__ __forceinline__ u64 gl_shl_dev(u64 x) {
             "subc.u32 m, 0, 0;\n\t"
             "sub.cc.u32 r0, r0, m;\n\t"
             "subc.u32 r1, r1, 0;\n\t"
-            "mad.lo.cc.u32 r0, %2, 0xffffffff, r0;\n\t"  // + y1 * (2^32 - 1)
-            "madc.hi.cc.u32 r1, %2, 0xffffffff, r1;\n\t"
+            "mad.lo.cc.u32 r0, %2, " GL_EPSM(4) ", r0;\n\t"  // + y1 * (2^32 - 1)
+            "madc.hi.cc.u32 r1, %2, " GL_EPSM(4) ", r1;\n\t"
             "addc.u32 k, 0, 0;\n\t"
             "add.cc.u32 t0, r0, 0xffffffff;\n\t"
             "addc.cc.u32 t1, r1, 0;\n\t"
             "addc.u32 k, k, 0;\n\t"
-            "mad.lo.cc.u32 r0, k, 0xffffffff, r0;\n\t"
-            "madc.hi.u32 r1, k, 0xffffffff, r1;\n\t"
+            "mad.lo.cc.u32 r0, k, " GL_EPSM(4) ", r0;\n\t"
+            "madc.hi.u32 r1, k, " GL_EPSM(4) ", r1;\n\t"
             "mov.b64 %0, {r0, r1};\n\t"
-            "}" : "=l"(o) : "r"(y0), "r"(y1), "r"(y2));
+            "}" : "=l"(o) : "r"(y0), "r"(y1), "r"(y2) GL_EPS_OPERAND);
     } else {
         asm("{\n\t"
             ".reg .u32 m0, m1, b;\n\t"
-            "mul.lo.u32 m0, %1, 0xffffffff;\n\t"
-            "mul.hi.u32 m1, %1, 0xffffffff;\n\t"
+            "mul.lo.u32 m0, %1, " GL_EPSM(4) ";\n\t"
+            "mul.hi.u32 m1, %1, " GL_EPSM(4) ";\n\t"
             "sub.cc.u32 m0, m0, %2;\n\t"
             "subc.cc.u32 m1, m1, %3;\n\t"
             "subc.u32 b, 0, 0;\n\t"
             "sub.cc.u32 m0, m0, b;\n\t"
             "subc.u32 m1, m1, 0;\n\t"
             "mov.b64 %0, {m0, m1};\n\t"
-            "}" : "=l"(o) : "r"(y0), "r"(y1), "r"(y2));
+            "}" : "=l"(o) : "r"(y0), "r"(y1), "r"(y2) GL_EPS_OPERAND);
     }
     return o;
 }
@@ -319,6 +330,35 @@ __device__ __forceinline__ void acc_mad(GlAcc& a, u64 x, u64 y) {
 __device__ __forceinline__ u64 acc_reduce(const GlAcc& a) {
     const u64 t = gl_reduce128((u64)a.w0 | ((u64)a.w1 << 32), (u64)a.w2 | ((u64)a.w3 << 32));
     return gl_sub(t, (u64)a.w4 << 32);
+}
+// Carry-free dot products (the form the wide kernels use): the coefficient is split once into limbs of 22 + 22 + 20 bits, the
+// data word into its two 32-bit halves; each of the six partial products is below 2^54 and is accumulated in its own 64-bit
+// register by ONE IMAD.WIDE.U32 (multiply + 64-bit add in the FMA pipe, no carry chain on the ALU pipe at all), so up to
+// 2^10 terms fit before any accumulator can wrap. acc_mad above is 10 FMA-pipe issue slots (IMAD.HI counts double on the
+// B200) + 5 ALU instructions per term; dot_mad is 6 + 0.
+struct GlCoef22 { u32 y0, y1, y2, pad; };   // 16 bytes: one LDS.128 from a shared-memory coefficient table
+struct GlDot { u64 a00, a01, a02, a10, a11, a12; };
+#define GL_DOT_MAX_TERMS 1024
+__host__ __device__ __forceinline__ GlCoef22 coef22(u64 y) {
+    GlCoef22 c;
+    c.y0 = (u32)y & 0x3fffffu; c.y1 = (u32)(y >> 22) & 0x3fffffu; c.y2 = (u32)(y >> 44); c.pad = 0;
+    return c;
+}
+__device__ __forceinline__ GlDot dot_zero() { return GlDot{0, 0, 0, 0, 0, 0}; }
+__device__ __forceinline__ void dot_mad(GlDot& a, const GlCoef22& c, u64 x) {
+    const u32 x0 = (u32)x, x1 = (u32)(x >> 32);
+    a.a00 += (u64)x0 * c.y0; a.a01 += (u64)x0 * c.y1; a.a02 += (u64)x0 * c.y2;
+    a.a10 += (u64)x1 * c.y0; a.a11 += (u64)x1 * c.y1; a.a12 += (u64)x1 * c.y2;
+}
+// sum = a00 + 2^22 a01 + 2^44 a02 + 2^32 a10 + 2^54 a11 + 2^76 a12 (mod p), canonical
+__device__ __forceinline__ u64 dot_reduce(const GlDot& a) {
+    u64 r = gl_reduce128(a.a00, 0);
+    r = gl_add(r, gl_reduce128(a.a01 << 22, a.a01 >> 42));
+    r = gl_add(r, gl_reduce128(a.a02 << 44, a.a02 >> 20));
+    r = gl_add(r, gl_reduce128(a.a10 << 32, a.a10 >> 32));
+    r = gl_add(r, gl_reduce128(a.a11 << 54, a.a11 >> 10));
+    const u64 t = gl_reduce128(a.a12 << 12, a.a12 >> 52);   // a12 2^12, then 2^64 on top
+    return gl_add(r, gl_reduce128(0, t));
 }
 #endif
 GL_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }

@@ -21,7 +21,12 @@
 #include "minidft.cuh"
 #include "ntt.cuh"
 
+#ifndef NTT2_THREADS
 #define NTT2_THREADS 256
+#endif
+#ifndef NTT2_MINB
+#define NTT2_MINB 2
+#endif
 #define NTT2_TILE_ELEMS 8192
 
 // ---- compile-time plan of a sub-transform of 2^LOGS points ----------------------------------------
@@ -166,7 +171,7 @@ __device__ __forceinline__ void tile_round(u64* __restrict__ s, const u64* __res
 // grid = (tile columns x chunks per row, segments, batch). Shared memory:
 //   tile [S][LANES] | round twiddles [tw_entries] | post twiddles [S][T] (STRIDED with has_post) | mbarrier
 template <int MODE, int LOGS>
-__global__ void __launch_bounds__(NTT2_THREADS, 2) ntt2_pass_kernel(const NttPassParams p) {
+__global__ void __launch_bounds__(NTT2_THREADS, NTT2_MINB) ntt2_pass_kernel(const NttPassParams p) {
     extern __shared__ __align__(16) u64 smem[];
     constexpr int LANES = Plan<LOGS>::lanes, LK = LANES == 8 ? 1 : 2, LP = LANES / 2;
     constexpr u32 S = 1u << LOGS;
@@ -194,7 +199,26 @@ __global__ void __launch_bounds__(NTT2_THREADS, 2) ntt2_pass_kernel(const NttPas
 
     // post twiddles of this tile: ctw[j][t] = w_M^(+-(j a_mul + (batch0 + b) b_mul) c) * ctab[c] * cconst, c = tile*T + t,
     // with w_M^e = hi_tab[e >> split] * lo_tab[e & (2^split - 1)]
-    if (p.has_post) {
+    if (p.has_post && T == 1) {
+        // one tile column c: ctw[j] = K g^j with g = w_M^(+-a_mul c), K = w_M^(+-(batch0 + b) b_mul c) ctab[c] cconst — a geometric
+        // progression in j: every thread starts at j = tid (one table product) and steps by g^NTT2_THREADS, one multiplication
+        // per entry instead of the two or three of the direct form below
+        const u32 M = 1u << p.logM, lo_mask = (1u << p.tw_split) - 1, c = tile;
+        auto wpow = [&](u64 e64) {
+            u32 e = (u32)(e64 & (M - 1));
+            if (p.inverse && e) e = M - e;
+            return gl_mul(p.tw_hi[e >> p.tw_split], p.tw_lo[e & lo_mask]);
+        };
+        u64 K = wpow((u64)(p.batch0 + b) * p.b_mul * c);
+        if (p.ctab) K = gl_mul(K, p.ctab[c < ncols ? c : 0]);
+        if (p.cconst != 1) K = gl_mul(K, p.cconst);
+        const u64 step = wpow((u64)NTT2_THREADS * p.a_mul * c);
+        u64 x = gl_mul(K, wpow((u64)tid * p.a_mul * c));
+        for (u32 j = tid; j < S; j += NTT2_THREADS) {
+            ctw[j] = x;
+            x = gl_mul(x, step);
+        }
+    } else if (p.has_post) {
         const u32 M = 1u << p.logM, lo_mask = (1u << p.tw_split) - 1;
         for (u32 idx = tid; idx < S * (u32)T; idx += NTT2_THREADS) {
             const u32 j = idx / T, tt = idx % T, c = tile * T + tt;
