@@ -49,7 +49,7 @@ static inline u64 gl_reduce128_host(u64 lo, u64 hi) {
     return r;
 }
 
-#if defined(__CUDACC__) && defined(GL_RUNTIME_EPS)
+#if defined(__CUDACC__) && !defined(GL_LITERAL_EPS)
 // 2^32 - 1 as a constant-bank operand ptxas cannot fold: with the literal, "x * 0xffffffff + y" is strength-reduced to
 // IMAD.IADD + IMAD.HI.U32 (the latter takes two issue slots of the FMA pipe on the B200); with an opaque multiplier the
 // mad.lo.cc / madc.hi.cc pair becomes ONE IMAD.WIDE.U32 with a carry-out predicate.
@@ -330,35 +330,6 @@ __device__ __forceinline__ void acc_mad(GlAcc& a, u64 x, u64 y) {
 __device__ __forceinline__ u64 acc_reduce(const GlAcc& a) {
     const u64 t = gl_reduce128((u64)a.w0 | ((u64)a.w1 << 32), (u64)a.w2 | ((u64)a.w3 << 32));
     return gl_sub(t, (u64)a.w4 << 32);
-}
-// Carry-free dot products (the form the wide kernels use): the coefficient is split once into limbs of 22 + 22 + 20 bits, the
-// data word into its two 32-bit halves; each of the six partial products is below 2^54 and is accumulated in its own 64-bit
-// register by ONE IMAD.WIDE.U32 (multiply + 64-bit add in the FMA pipe, no carry chain on the ALU pipe at all), so up to
-// 2^10 terms fit before any accumulator can wrap. acc_mad above is 10 FMA-pipe issue slots (IMAD.HI counts double on the
-// B200) + 5 ALU instructions per term; dot_mad is 6 + 0.
-struct GlCoef22 { u32 y0, y1, y2, pad; };   // 16 bytes: one LDS.128 from a shared-memory coefficient table
-struct GlDot { u64 a00, a01, a02, a10, a11, a12; };
-#define GL_DOT_MAX_TERMS 1024
-__host__ __device__ __forceinline__ GlCoef22 coef22(u64 y) {
-    GlCoef22 c;
-    c.y0 = (u32)y & 0x3fffffu; c.y1 = (u32)(y >> 22) & 0x3fffffu; c.y2 = (u32)(y >> 44); c.pad = 0;
-    return c;
-}
-__device__ __forceinline__ GlDot dot_zero() { return GlDot{0, 0, 0, 0, 0, 0}; }
-__device__ __forceinline__ void dot_mad(GlDot& a, const GlCoef22& c, u64 x) {
-    const u32 x0 = (u32)x, x1 = (u32)(x >> 32);
-    a.a00 += (u64)x0 * c.y0; a.a01 += (u64)x0 * c.y1; a.a02 += (u64)x0 * c.y2;
-    a.a10 += (u64)x1 * c.y0; a.a11 += (u64)x1 * c.y1; a.a12 += (u64)x1 * c.y2;
-}
-// sum = a00 + 2^22 a01 + 2^44 a02 + 2^32 a10 + 2^54 a11 + 2^76 a12 (mod p), canonical
-__device__ __forceinline__ u64 dot_reduce(const GlDot& a) {
-    u64 r = gl_reduce128(a.a00, 0);
-    r = gl_add(r, gl_reduce128(a.a01 << 22, a.a01 >> 42));
-    r = gl_add(r, gl_reduce128(a.a02 << 44, a.a02 >> 20));
-    r = gl_add(r, gl_reduce128(a.a10 << 32, a.a10 >> 32));
-    r = gl_add(r, gl_reduce128(a.a11 << 54, a.a11 >> 10));
-    const u64 t = gl_reduce128(a.a12 << 12, a.a12 >> 52);   // a12 2^12, then 2^64 on top
-    return gl_add(r, gl_reduce128(0, t));
 }
 #endif
 GL_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }

@@ -4,19 +4,29 @@
 __global__ void __launch_bounds__(256) cols_to_seg_kernel(const u64* __restrict__ src, size_t nrows, int d, int mont,
                                                           SegMatrix dst) {
     // thread = (row, segment); reads W columns at `row` (coalesced per column across the warp),
-    // writes one W*8-byte segment row
+    // writes one W*8-byte segment row. All W loads are issued before the first use: the kernel is a pure
+    // transpose and ran latency-bound (56 long-scoreboard stalls per issue) with one load in flight per thread.
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     u32 g = blockIdx.y;
     if (row >= nrows) return;
     u64* o = dst.base + (size_t)g * dst.seg_stride + row * dst.W;
-    for (int q = 0; q < dst.W; q++) {
+    u64 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
         u32 col = g * dst.W + q;
-        u64 v = 0;
-        if (col < dst.cols) {
-            v = src[(size_t)(col / d) * nrows * d + row * d + (col % d)];
-            if (mont) v = gl_from_mont(v);
-        }
-        o[q] = v;
+        v[q] = (q < dst.W && col < dst.cols) ? __ldg(src + (size_t)(col / d) * nrows * d + row * d + (col % d)) : 0;
+    }
+    if (mont) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = gl_from_mont(v[q]);
+    }
+    if (dst.W == 8) {
+        ulonglong2* o2 = reinterpret_cast<ulonglong2*>(o);
+#pragma unroll
+        for (int k = 0; k < 4; k++) o2[k] = make_ulonglong2(v[2 * k], v[2 * k + 1]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) if (q < dst.W) o[q] = v[q];
     }
 }
 __global__ void __launch_bounds__(256) rows_to_seg_kernel(const u64* __restrict__ src, SegMatrix dst) {

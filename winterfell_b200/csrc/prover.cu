@@ -64,14 +64,13 @@ struct FibEvalParams {
 // CE-domain rows, FIB_ROWS per thread sharing one field inversion (evaluator/default.rs:165-214
 // evaluate_fragment_main + evaluation_table.rs:317-367 acc_column, fused). The three linear forms of a row
 // (transition combination, the two boundary groups) are dot products of base-field frame values with extension
-// coefficients: they run on carry-free delayed-reduction accumulators (GlDot, gl64.cuh), one reduction per row and form instead of one per
+// coefficients: they run on delayed-reduction accumulators (GlAcc), one reduction per row and form instead of one per
 // term — the first version spent 22 k instructions per row of the 64-column cubic configuration in gl_mul / gl_add.
 template <int D>
 __global__ void __launch_bounds__(256) fib_constraints_kernel(FibEvalParams p) {
-    extern __shared__ __align__(16) u64 fsm_raw[];
-    GlCoef22* fsm = reinterpret_cast<GlCoef22*>(fsm_raw);   // coefficients split into 22-bit limbs (carry-free dot products)
+    extern __shared__ __align__(16) u64 fsm[];
     constexpr int ROWS = D == 3 ? 2 : 4;
-    for (u32 i = threadIdx.x; i < p.k * 5 * D; i += blockDim.x) fsm[i] = coef22(p.coef[i]);
+    for (u32 i = threadIdx.x; i < p.k * 5 * D; i += blockDim.x) fsm[i] = p.coef[i];
     __syncthreads();
     const size_t ce_all = (size_t)1 << (p.log_n + p.log_ce_blowup);
     const size_t ce = p.ce_rows ? p.ce_rows : ce_all;   // rows of this launch
@@ -93,9 +92,9 @@ __global__ void __launch_bounds__(256) fib_constraints_kernel(FibEvalParams p) {
         const size_t ls = il << lde_shift;
         const size_t nx = p.ce_rows ? ls + ((size_t)1 << p.log_blowup)
                                     : ((ls + ((size_t)1 << p.log_blowup)) & (N - 1));  // trace_lde/default/mod.rs:169-180
-        GlDot aT[D], a0[D], a1[D];   // 2k, 2k and k terms: k <= 127 < GL_DOT_MAX_TERMS / 2
+        GlAcc aT[D], a0[D], a1[D];
 #pragma unroll
-        for (int q = 0; q < D; q++) { aT[q] = dot_zero(); a0[q] = dot_zero(); a1[q] = dot_zero(); }
+        for (int q = 0; q < D; q++) { aT[q] = acc_zero(); a0[q] = acc_zero(); a1[q] = acc_zero(); }
 #pragma unroll 2
         for (u32 j = 0; j < p.k; j++) {
             // columns 2j, 2j+1 are adjacent words of one segment row: one 16-byte load per frame row
@@ -104,21 +103,21 @@ __global__ void __launch_bounds__(256) fib_constraints_kernel(FibEvalParams p) {
             const ulonglong2 nxt = __ldg(reinterpret_cast<const ulonglong2*>(p.lde.base + off + nx * W));
             const u64 t0 = gl_sub(nxt.x, gl_add(cur.x, cur.y));  // fib_small/air.rs:58
             const u64 t1 = gl_sub(nxt.y, gl_add(cur.y, nxt.x));  // :59
-            const GlCoef22* cf = fsm + (size_t)j * 5 * D;
+            const u64* cf = fsm + (size_t)j * 5 * D;
 #pragma unroll
             for (int q = 0; q < D; q++) {
-                dot_mad(aT[q], cf[q], t0);
-                dot_mad(aT[q], cf[D + q], t1);
-                dot_mad(a0[q], cf[2 * D + q], cur.x);
-                dot_mad(a0[q], cf[3 * D + q], cur.y);
-                dot_mad(a1[q], cf[4 * D + q], cur.y);
+                acc_mad(aT[q], cf[q], t0);
+                acc_mad(aT[q], cf[D + q], t1);
+                acc_mad(a0[q], cf[2 * D + q], cur.x);
+                acc_mad(a0[q], cf[3 * D + q], cur.y);
+                acc_mad(a1[q], cf[4 * D + q], cur.y);
             }
         }
 #pragma unroll
         for (int q = 0; q < D; q++) {
-            T[r].v[q] = dot_reduce(aT[q]);
-            B0[r].v[q] = gl_sub(dot_reduce(a0[q]), p.K0[q]);
-            B1[r].v[q] = gl_sub(dot_reduce(a1[q]), p.K1[q]);
+            T[r].v[q] = acc_reduce(aT[q]);
+            B0[r].v[q] = gl_sub(acc_reduce(a0[q]), p.K0[q]);
+            B1[r].v[q] = gl_sub(acc_reduce(a1[q]), p.K1[q]);
         }
         u64 w = p.tw_ce[i & (half - 1)];
         if (i & half) w = gl_neg(w);
@@ -324,13 +323,13 @@ __global__ void __launch_bounds__(256) ood_partial_kernel(SegMatrix polys, GlExt
     const int W = polys.W;
     const size_t n = polys.rows;
     const u64* base = polys.base + (size_t)g * polys.seg_stride;
-    __shared__ GlCoef22 zpow[2][OOD_RPT][D];   // z^r, split into 22-bit limbs (carry-free dot products, gl64.cuh)
+    __shared__ u64 zpow[2][OOD_RPT][D];   // z^r
     __shared__ u64 zrg[2][32][D];         // z^(OOD_RPT * rg)
     __shared__ u64 red[2][32][8][D];
     if (t < 2 * OOD_RPT) {
         const GlExt<D> v = ext_pow(t < OOD_RPT ? z0 : z1, t % OOD_RPT);
 #pragma unroll
-        for (int d = 0; d < D; d++) zpow[t / OOD_RPT][t % OOD_RPT][d] = coef22(v.v[d]);
+        for (int d = 0; d < D; d++) zpow[t / OOD_RPT][t % OOD_RPT][d] = v.v[d];
     } else if (t < 2 * OOD_RPT + 64) {
         const u32 u = t - 2 * OOD_RPT, pt = u / 32, rg = u % 32;
         const GlExt<D> v = ext_pow(pt ? z1 : z0, (u64)rg * OOD_RPT);
@@ -340,11 +339,11 @@ __global__ void __launch_bounds__(256) ood_partial_kernel(SegMatrix polys, GlExt
     __syncthreads();
     const u32 rg = t >> 3, lane = t & 7;
     const size_t start = (size_t)chunk * OOD_ROWS_PER_BLOCK + (size_t)rg * OOD_RPT;
-    GlDot acc[2][D];   // OOD_RPT terms each
+    GlAcc acc[2][D];
 #pragma unroll
     for (int pt = 0; pt < 2; pt++)
 #pragma unroll
-        for (int d = 0; d < D; d++) acc[pt][d] = dot_zero();
+        for (int d = 0; d < D; d++) acc[pt][d] = acc_zero();
     if (lane < (u32)W) {
         const u64* src = base + start * W + lane;
 #pragma unroll 1
@@ -356,8 +355,8 @@ __global__ void __launch_bounds__(256) ood_partial_kernel(SegMatrix polys, GlExt
             for (int k = 0; k < 8; k++) {
 #pragma unroll
                 for (int d = 0; d < D; d++) {
-                    dot_mad(acc[0][d], zpow[0][r0 + k][d], cf[k]);
-                    dot_mad(acc[1][d], zpow[1][r0 + k][d], cf[k]);
+                    acc_mad(acc[0][d], zpow[0][r0 + k][d], cf[k]);
+                    acc_mad(acc[1][d], zpow[1][r0 + k][d], cf[k]);
                 }
             }
         }
@@ -366,7 +365,7 @@ __global__ void __launch_bounds__(256) ood_partial_kernel(SegMatrix polys, GlExt
     for (int pt = 0; pt < 2; pt++) {
         GlExt<D> v;
 #pragma unroll
-        for (int d = 0; d < D; d++) v.v[d] = dot_reduce(acc[pt][d]);
+        for (int d = 0; d < D; d++) v.v[d] = acc_reduce(acc[pt][d]);
         v = ext_mul(v, ld_ext<D>(&zrg[pt][rg][0]));
 #pragma unroll
         for (int d = 0; d < D; d++) red[pt][rg][lane][d] = v.v[d];
@@ -384,14 +383,24 @@ __global__ void __launch_bounds__(256) ood_partial_kernel(SegMatrix polys, GlExt
         }
     }
 }
+// one warp per (column, point): lanes stride over the chunks (2048 of them for a 2^22-row column — a single thread
+// walking them serially took 0.5 ms per call), then a shuffle tree over the extension components
 template <int D>
-__global__ void ood_reduce_kernel(const u64* partial, u32 cols, u32 chunks, u64* out /*[cols][2][D]*/) {
-    u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= cols * 2) return;
-    u32 col = idx >> 1, pt = idx & 1;
+__global__ void __launch_bounds__(256) ood_reduce_kernel(const u64* partial, u32 cols, u32 chunks, u64* out /*[cols][2][D]*/) {
+    const u32 idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (idx >= cols * 2) return;   // warp-uniform
+    const u32 col = idx >> 1, pt = idx & 1;
     GlExt<D> s = ext_zero<D>();
-    for (u32 c = 0; c < chunks; c++) s = ext_add(s, ld_ext<D>(partial + (((size_t)col * chunks + c) * 2 + pt) * D));
-    for (int c = 0; c < D; c++) out[(size_t)idx * D + c] = s.v[c];
+    for (u32 c = lane; c < chunks; c += 32) s = ext_add(s, ld_ext<D>(partial + (((size_t)col * chunks + c) * 2 + pt) * D));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        GlExt<D> o;
+#pragma unroll
+        for (int c = 0; c < D; c++) o.v[c] = __shfl_down_sync(0xffffffffu, s.v[c], off);
+        s = ext_add(s, o);
+    }
+    if (lane == 0)
+        for (int c = 0; c < D; c++) out[(size_t)idx * D + c] = s.v[c];
 }
 
 struct DeepParams {
@@ -419,10 +428,10 @@ struct DeepParams {
 template <int D>
 __global__ void __launch_bounds__(DEEP_SUM_THREADS) deep_sum_kernel(DeepParams p) {
     extern __shared__ __align__(16) u64 dsm[];
-    GlCoef22* s_t = reinterpret_cast<GlCoef22*>(dsm);  // [c][D], split into 22-bit limbs for the carry-free dot product
-    u64* s_a = dsm + (size_t)p.c * D * 2;            // [aw][D]
+    u64* s_t = dsm;                                  // [c][D]
+    u64* s_a = s_t + (size_t)p.c * D;                // [aw][D]
     u64* s_c = s_a + (size_t)p.aw * D;               // [kc][D]
-    for (u32 i = threadIdx.x; i < p.c * D; i += DEEP_SUM_THREADS) s_t[i] = coef22(p.tcc[i]);
+    for (u32 i = threadIdx.x; i < p.c * D; i += DEEP_SUM_THREADS) s_t[i] = p.tcc[i];
     for (u32 i = threadIdx.x; i < p.aw * D; i += DEEP_SUM_THREADS) s_a[i] = p.acc[i];
     for (u32 i = threadIdx.x; i < p.kc * D; i += DEEP_SUM_THREADS) s_c[i] = p.ccc[i];
     __syncthreads();
@@ -431,21 +440,34 @@ __global__ void __launch_bounds__(DEEP_SUM_THREADS) deep_sum_kernel(DeepParams p
     if (row >= N) return;
     // S over the base-field trace columns = D dot products of the row with the coefficient components: delayed-reduction
     // accumulators, one reduction per component per row
-    GlDot acc[D];  // at most GL_DOT_MAX_TERMS columns (the trace width is a u8)
+    GlAcc acc[D];
 #pragma unroll
-    for (int d = 0; d < D; d++) acc[d] = dot_zero();
+    for (int d = 0; d < D; d++) acc[d] = acc_zero();
     if (p.trace.W == 8) {
-        for (u32 g = 0; g * 8 < p.c; g++) {  // one 64-byte segment row = four 16-byte loads
-            const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(p.trace.base + (size_t)g * p.trace.seg_stride + row * 8);
+        // one 64-byte segment row = four 16-byte loads; the next segment's row is requested before this one is consumed
+        // (the kernel was latency-bound on these loads: 3.2 long-scoreboard stalls per issue, profiles/r2_cubic_stages.txt)
+        const u32 nseg = (p.c + 7) / 8;
+        ulonglong2 nx[4];
+        {
+            const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(p.trace.base + row * 8);
+#pragma unroll
+            for (int k = 0; k < 4; k++) nx[k] = __ldg(rp + k);
+        }
+        for (u32 g = 0; g < nseg; g++) {
             u64 v[8];
 #pragma unroll
-            for (int k = 0; k < 4; k++) { ulonglong2 t2 = __ldg(rp + k); v[2 * k] = t2.x; v[2 * k + 1] = t2.y; }
+            for (int k = 0; k < 4; k++) { v[2 * k] = nx[k].x; v[2 * k + 1] = nx[k].y; }
+            if (g + 1 < nseg) {
+                const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(p.trace.base + (size_t)(g + 1) * p.trace.seg_stride + row * 8);
+#pragma unroll
+                for (int k = 0; k < 4; k++) nx[k] = __ldg(rp + k);
+            }
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 u32 j = g * 8 + q;
                 if (j < p.c) {
 #pragma unroll
-                    for (int d = 0; d < D; d++) dot_mad(acc[d], s_t[(size_t)j * D + d], v[q]);
+                    for (int d = 0; d < D; d++) acc_mad(acc[d], s_t[(size_t)j * D + d], v[q]);
                 }
             }
         }
@@ -453,12 +475,12 @@ __global__ void __launch_bounds__(DEEP_SUM_THREADS) deep_sum_kernel(DeepParams p
         for (u32 j = 0; j < p.c; j++) {
             const u64 v = seg_at(p.trace, row, j);
 #pragma unroll
-            for (int d = 0; d < D; d++) dot_mad(acc[d], s_t[(size_t)j * D + d], v);
+            for (int d = 0; d < D; d++) acc_mad(acc[d], s_t[(size_t)j * D + d], v);
         }
     }
     GlExt<D> S;
 #pragma unroll
-    for (int d = 0; d < D; d++) S.v[d] = dot_reduce(acc[d]);
+    for (int d = 0; d < D; d++) S.v[d] = acc_reduce(acc[d]);
     for (u32 j = 0; j < p.aw; j++) {
         GlExt<D> av;
 #pragma unroll
@@ -838,7 +860,7 @@ int ood_eval(wf_ctx* ctx, const std::vector<const wf_mat*>& mats, const GlExt<D>
         CKI(wf_dev_alloc(ctx, (size_t)2 * chunks * D * 8, &zbs[m]));
         ood_pow_kernel<D><<<(2 * chunks + 127) / 128, 128, 0, ctx->st>>>(z0, z1, chunks, (u64*)zbs[m]);
         ood_partial_kernel<D><<<dim3(chunks, mats[m]->m.nseg()), 256, 0, ctx->st>>>(mats[m]->m, z0, z1, (const u64*)zbs[m], (u64*)part[m], chunks);
-        ood_reduce_kernel<D><<<(2 * cols + 63) / 64, 64, 0, ctx->st>>>((const u64*)part[m], cols, chunks, (u64*)res + off);
+        ood_reduce_kernel<D><<<(2 * cols * 32 + 255) / 256, 256, 0, ctx->st>>>((const u64*)part[m], cols, chunks, (u64*)res + off);
         ctx->launches += 3;
         CK(cudaGetLastError());
         off += (size_t)cols * 2 * D;
@@ -1011,7 +1033,7 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
         p.row0 = row0; p.ce_rows = ce_rows;
         const size_t rows_per_thread = D == 3 ? 2 : 4;
         size_t threads = ((ce_rows ? ce_rows : ce) + rows_per_thread - 1) / rows_per_thread;
-        fib_constraints_kernel<D><<<(unsigned)((threads + 255) / 256), 256, cf.size() * sizeof(GlCoef22), ctx->st>>>(p);
+        fib_constraints_kernel<D><<<(unsigned)((threads + 255) / 256), 256, cf.size() * 8, ctx->st>>>(p);
         ctx->launches++;
         CK(cudaGetLastError());
     } else {
@@ -1182,7 +1204,7 @@ int deep_compose(wf_ctx* ctx, const wf_mat* lde, const wf_mat* alde, const wf_ma
     p.tcc = d_dt; p.ccc = d_dq; p.acc = d_da; p.aw = aw;
     p.aux = aw ? alde->m : lde->m;
     CKI(wf_get_twiddles(ctx, log_N, &p.tw_N));
-    const size_t coef_bytes = (size_t)(2 * c + aw + kc) * D * 8;   // trace coefficients as 16-byte GlCoef22
+    const size_t coef_bytes = (size_t)(c + aw + kc) * D * 8;
     deep_sum_kernel<D><<<(unsigned)((N + DEEP_SUM_THREADS - 1) / DEEP_SUM_THREADS), DEEP_SUM_THREADS, coef_bytes, ctx->st>>>(p);
     const size_t rows_per_thread = DEEP_ROWS;
     size_t threads = (N + rows_per_thread - 1) / rows_per_thread;
