@@ -342,6 +342,41 @@ def main():
         return {"ms": ms_step, "e2e_ms": e2e_step, "launches": launches, "breakdown": breakdown, "proof": p_e2e, "h2d": int(host_np.nbytes),
                 "wall_ms": wall_ms / steps, "clocks": sampler.summary() if sampler else None}
 
+    def fri_sweep():
+        """BASELINE.json configs[4]: FRI commit phase alone (fold + leaf hash + Merkle tree of every layer, device-side coin) on
+        2^20 .. 2^26-point base-field codewords (LDE, blowup 8, of random polynomials), folding 4, remainder max degree 31,
+        Blake3_256. Every rank folds its own codeword (independent objects: weak scaling, no data-path collective); CUDA
+        events on the context stream, max over ranks; GB/s over SURVEY.md 8d's algorithmic bytes."""
+        rng = np.random.default_rng(100 + rank)
+        recs = []
+        for log_len in (20, 22, 24, 26):
+            L = 1 << log_len
+            with torch.cuda.stream(stream):
+                m = ctx.mat_from_host_columns(rng.integers(0, P, size=(1, L >> LOG_BLOWUP), dtype=np.uint64))
+                cw = m.lde(LOG_BLOWUP)
+                for _ in range(3):
+                    f, _ = ctx.fri_build_layers_default(wf.HASH_BLAKE3_256, cw, 1, FOLDING, REM_MAX_DEG, 1 << LOG_BLOWUP)
+                    f.free()
+                barrier()
+                reps, tot = 5, 0.0
+                for _ in range(reps):
+                    flush.zero_()
+                    a, b = ev(), ev()
+                    a.record(stream)
+                    f, _ = ctx.fri_build_layers_default(wf.HASH_BLAKE3_256, cw, 1, FOLDING, REM_MAX_DEG, 1 << LOG_BLOWUP)
+                    b.record(stream)
+                    b.synchronize()
+                    tot += a.elapsed_time(b)
+                    f.free()
+                m.free(); cw.free()
+            ms = tot / reps
+            if world > 1:
+                t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t[0])
+            recs.append((log_len, ms))
+        return recs
+
     import gc
     gc.collect()
     gc.disable()  # no collector pauses inside the timed regions
@@ -355,6 +390,7 @@ def main():
     sub = None
     if world == 1 and args.config == "cfg3" and not args.no_sub_record:
         sub = run_config("cfg2", max(args.steps, 10), 3, False)
+    sweep = None if args.no_sub_record else fri_sweep()
     gc.enable()
 
     ms_step, e2e_step = main_rec["ms"], main_rec["e2e_ms"]
@@ -406,6 +442,14 @@ def main():
             srl = rooflines(sub["breakdown"], "cfg2", hbm, peak_src, compress_gps)
             line["cfg2"] = {"workload": workload_name("cfg2"), "value": round(sub["ms"], 4), "e2e": round(sub["e2e_ms"], 4), "unit": "ms",
                             "gpu_launches": sub["launches"], "stage_ms": sub["breakdown"], "roofline": dict(srl[0], kernels=srl)}
+        if sweep:
+            line["fri_sweep"] = {"workload": "cfg5: FRI commit phase only, 2^20..2^26-point base-field codewords, folding 4, remainder max degree 31, "
+                                             "Blake3_256; one codeword per GPU (weak scaling, no data-path collective), max over ranks",
+                                 "points": [{"log2_len": ll, "ms": round(ms, 4),
+                                             "GBps_per_gpu": round(fri_algorithmic_bytes(1 << ll, 1) / (ms * 1e-3) / 1e9, 1),
+                                             "frac_of_hbm": round(fri_algorithmic_bytes(1 << ll, 1) / (ms * 1e-3) / 1e9 / hbm, 4),
+                                             "aggregate_GBps": round(world * fri_algorithmic_bytes(1 << ll, 1) / (ms * 1e-3) / 1e9, 1)}
+                                            for ll, ms in sweep]}
         if not args.no_cpu_baseline:
             # bounded sample of the same workload in a fresh process (torch has already initialised libgomp here with the
             # spinning wait policy): the same AIR / columns / extension on 1/16 of the rows; the value is the SAMPLE's own

@@ -278,10 +278,16 @@ static int run_ntt(wf_ctx* ctx, const SegMatrix& in, SegMatrix& out, const SegMa
 // LDE of coefficient columns over 7 * <w_N>: out has n << log_b rows, row b*j + k = P(7 w_N^k w_n^j).
 // `out` may be a view of a wider matrix: segment width out.W >= polys.W, the polys' columns landing at
 // column offset out_col0 of each out row (column-chunked trace pipeline, wf_trace_lde_from_host).
-static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_n, u32 log_b, u32 out_col0 = 0) {
+// k0 <= k < k1 (k1 = 0: all cosets) selects the cosets computed; coset k, point j lands in out row j * row_mul + (k - k0) * row_add
+// (row_mul = 0: the natural order b*j + k). Coset-major output (row_mul = 1, row_add = n) is what a rank of a sharded proof
+// produces for the cosets it owns (prover.cu, composition polynomial).
+static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_n, u32 log_b, u32 out_col0 = 0, u32 k0 = 0, u32 k1 = 0,
+                   u32 row_mul = 0, u32 row_add = 1) {
     u32 logR, logC;
     split_log(log_n, &logR, &logC);
     u32 b = 1u << log_b;
+    if (k1 == 0) k1 = b;
+    if (row_mul == 0) { row_mul = b; row_add = 1; }
     LdeTables tabs;
     NttPassParams p;
     if (logC > NTT_MAX_LOGS) {
@@ -296,7 +302,7 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
         CKI(wf_dev_alloc(ctx, polys.words() * 8, &yp));
         y.base = (u64*)yp;
         int rc = WF_OK;
-        for (u32 k = 0; k < b && rc == WF_OK; k++) {
+        for (u32 k = k0; k < k1 && rc == WF_OK; k++) {
             pass_defaults(p, polys, y);  // pass A
             p.logS = (int)lr; p.logR = lr; p.logC = lc;
             p.pre_tab = tabs.pre + ((size_t)k << lr); p.pre_batch_stride = 0;
@@ -313,8 +319,8 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
             pass_defaults(p, y, out);  // pass C: row b*(j1 + R*j) + k
             p.in_batch_stride = ((size_t)1 << lc) * polys.W;
             p.logS = (int)lc2; p.logR = lr2; p.logC = lc2;
-            p.out_row_mul = b << lr; p.out_row_add = b; p.out_col0 = out_col0;
-            p.out = out.base + (size_t)k * out.W;
+            p.out_row_mul = row_mul << lr; p.out_row_add = row_mul; p.out_col0 = out_col0;
+            p.out = out.base + (size_t)(k - k0) * row_add * out.W;
             rc = launch_pass(ctx, NTT_CONTIG, p, polys.nseg(), 1u << lr);
         }
         wf_dev_free(ctx, yp);  // stream-ordered pool: also correct on the error path
@@ -324,9 +330,9 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
     if (logR == 0) {
         pass_defaults(p, polys, out);
         p.logS = (int)logC; p.logR = 0; p.logC = logC;
-        p.pre_tab = tabs.pre; p.pre_batch_stride = (size_t)1 << log_n;
-        p.out_row_mul = b; p.out_row_add = 1; p.out_col0 = out_col0;
-        return launch_pass(ctx, NTT_CONTIG, p, polys.nseg(), b);
+        p.pre_tab = tabs.pre + ((size_t)k0 << log_n); p.pre_batch_stride = (size_t)1 << log_n;
+        p.out_row_mul = row_mul; p.out_row_add = row_add; p.out_col0 = out_col0;
+        return launch_pass(ctx, NTT_CONTIG, p, polys.nseg(), k1 - k0);
     }
     // Cosets per launch (grid.z = coset). The scratch Y of one coset is as large as the polynomials; while
     // it fits in half of the 126 MB L2 the contiguous pass finds most of it there, so cosets are processed
@@ -337,12 +343,13 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
     u32 kb = b;
     while (kb > 1 && poly_bytes * kb > ((size_t)64 << 20) && tiles_per_coset * (kb / 2) >= 4 * 296) kb >>= 1;
     while (kb > 1 && poly_bytes * kb > ((size_t)1 << 30)) kb >>= 1;
+    while (kb > k1 - k0 || (k1 - k0) % kb) kb >>= 1;
     SegMatrix y = polys;
     void* yp;
     CKI(wf_dev_alloc(ctx, poly_bytes * kb, &yp));
     y.base = (u64*)yp;
     int rc = WF_OK;
-    for (u32 k = 0; k < b && rc == WF_OK; k += kb) {
+    for (u32 k = k0; k < k1 && rc == WF_OK; k += kb) {
         // pass 1: Y_k[j1][m2] = 7^m2 w_N^((b j1 + k) m2) sum_m1 a[C m1 + m2] (s_k^C)^m1 w_R^(j1 m1)
         pass_defaults(p, polys, y);
         p.logS = (int)logR; p.logR = logR; p.logC = logC;
@@ -357,8 +364,8 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
         pass_defaults(p, y, out);
         p.logS = (int)logC; p.logR = logR; p.logC = logC;
         p.in_batch_stride = polys.words();
-        p.out_row_mul = b; p.out_row_add = 1; p.out_col0 = out_col0;
-        p.out = out.base + (size_t)k * out.W;  // + k rows; the launch's coset z adds z rows
+        p.out_row_mul = row_mul; p.out_row_add = row_add; p.out_col0 = out_col0;
+        p.out = out.base + (size_t)(k - k0) * row_add * out.W;  // first coset of the launch; the launch's coset z adds z * row_add rows
         rc = launch_pass(ctx, NTT_CONTIG, p, polys.nseg(), kb);
     }
     wf_dev_free(ctx, yp);
@@ -624,6 +631,18 @@ int wf_mat_lde_into(wf_ctx* ctx, const wf_mat* polys, uint32_t log_blowup, wf_ma
     if (log_blowup > 7 || lde->m.rows != (polys->m.rows << log_blowup) || lde->m.cols != polys->m.cols || lde->m.W != polys->m.W)
         return wf_fail(ctx, WF_ERR_INVALID, "output matrix does not match the LDE shape");
     return run_lde(ctx, polys->m, lde->m, log_n, log_blowup);
+}
+
+// Cosets k0 <= k < k1 of the LDE only, coset-major: row (k - k0) * n + j of `lde` = P(7 w_N^k w_n^j). One rank's share of a
+// transform whose columns are too few to shard by column (the composition polynomial of a sharded proof).
+int wf_mat_lde_cosets(wf_ctx* ctx, const wf_mat* polys, uint32_t log_blowup, uint32_t k0, uint32_t k1, wf_mat* lde) {
+    if (!ctx || !polys || !lde) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    u32 log_n;
+    if (log2_exact(polys->m.rows, &log_n) || log_n < 1) return wf_fail(ctx, WF_ERR_INVALID, "rows must be a power of two >= 2");
+    if (log_blowup > 7 || k0 >= k1 || k1 > (1u << log_blowup) || lde->m.rows != polys->m.rows * (k1 - k0) || lde->m.cols != polys->m.cols ||
+        lde->m.W != polys->m.W || ((k1 - k0) & (k1 - k0 - 1)))
+        return wf_fail(ctx, WF_ERR_INVALID, "coset range / output matrix do not match");
+    return run_lde(ctx, polys->m, lde->m, log_n, log_blowup, 0, k0, k1, 1, (u32)polys->m.rows);
 }
 
 // DefaultTraceLde::new up to the commitment (trace_lde/default/mod.rs:63-100, build_trace_commitment

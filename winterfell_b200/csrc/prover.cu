@@ -1161,11 +1161,11 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
 // DefaultConstraintCommitment::new (prover/src/constraints/commitment/default.rs:44-150): composition
 // trace (CE-domain evaluations, ce x D) -> CompositionPoly columns (n x kc*D coefficient matrix,
 // composition_poly.rs:58-78,128-140), their LDE (N x kc*D) and the row commitment.
-int composition_commit(wf_ctx* ctx, int h, const wf_mat* comp, u32 log_n, u32 log_b, int D, u32 kc, wf_mat** polys_out,
-                       wf_mat** lde_out, wf_tree** tree_out, u32 partition_words = 0) {
+// CompositionPoly::new (composition_poly.rs:58-78): CE-domain evaluations -> kc column polynomials of degree < n
+int composition_polys(wf_ctx* ctx, const wf_mat* comp, u32 log_n, int D, u32 kc, wf_mat** polys_out) {
     const size_t n = (size_t)1 << log_n;
     if (comp->m.rows < n * kc || (int)comp->m.cols != D) return wf_fail(ctx, WF_ERR_INVALID, "composition trace shape");
-    wf_mat *ccoefs, *cpolys, *clde;
+    wf_mat *ccoefs, *cpolys;
     CKI(wf_mat_interpolate_with_offset(ctx, comp, GL_GENERATOR, &ccoefs));
     CKI(wf_mat_alloc(ctx, n, kc * D, &cpolys));
     if (cpolys->m.W > (int)(kc * D)) CK(cudaMemsetAsync(cpolys->m.base, 0, cpolys->m.words() * 8, ctx->st));
@@ -1174,6 +1174,13 @@ int composition_commit(wf_ctx* ctx, int h, const wf_mat* comp, u32 log_n, u32 lo
     CK(cudaGetLastError());
     wf_mat_free(ctx, ccoefs);
     wf_mark(ctx, "composition_interpolate");
+    *polys_out = cpolys;
+    return WF_OK;
+}
+int composition_commit(wf_ctx* ctx, int h, const wf_mat* comp, u32 log_n, u32 log_b, int D, u32 kc, wf_mat** polys_out,
+                       wf_mat** lde_out, wf_tree** tree_out, u32 partition_words = 0) {
+    wf_mat *cpolys, *clde;
+    CKI(composition_polys(ctx, comp, log_n, D, kc, &cpolys));
     CKI(wf_mat_lde(ctx, cpolys, log_b, &clde));
     wf_mark(ctx, "composition_lde");
     if (tree_out) CKI(wf_commit_rows_partitioned(ctx, h, clde, partition_words, tree_out));  // sharded proofs commit their own row range
@@ -1430,6 +1437,17 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
 // =================================================================================================
 // One proof sharded over several GPUs (include/winterfell_b200.h: wf_comm, wf_prove_fib_sharded)
 // =================================================================================================
+// staging: [b cosets][rows_j][W] (per segment) -> natural order row j * b + k of the row shard
+__global__ void __launch_bounds__(256) coset_interleave_kernel(SegMatrix src, SegMatrix dst, size_t rows_j, u32 b) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (row of dst, word)
+    const int W = dst.W;
+    if (idx >= dst.rows * (size_t)W) return;
+    const size_t row = idx / W;
+    const u32 w = (u32)(idx % W), g = blockIdx.y;
+    const size_t j = row / b, k = row % b;
+    dst.base[(size_t)g * dst.seg_stride + idx] = src.base[(size_t)g * src.seg_stride + (k * rows_j + j) * W + w];
+}
+
 struct ShardCtx {
     wf_ctx* ctx;
     const wf_comm* cm;
@@ -1603,12 +1621,63 @@ int prove_fib_sharded(wf_ctx* ctx, const wf_comm* cm, const uint64_t* const* loc
     CKI(wf_mat_alloc(ctx, ce, D, &comp));
     CKI(sc.all_gather_dev(comp_l->m.base, comp->m.base, ce_per * comp->m.W * 8));
     scope.drop(comp_l);
-    CKI(composition_commit(ctx, h, comp, log_n, log_b, D, kc, &cpolys, &clde, nullptr));
-    scope.drop(comp);
     wf_mat cview;  // my rows of the composition LDE
-    cview.m = clde->m;
-    cview.m.base += (size_t)r * rows_per * clde->m.W;
-    cview.m.rows = rows_per;
+    if (b % (size_t)G == 0) {
+        // the composition polynomial has too few columns to shard by column: shard its LDE by COSET instead. Rank r extends
+        // cosets [r b/G, (r+1) b/G) (coset-major), one exchange hands every rank the rows of its row range from every coset's
+        // owner, one kernel interleaves them into natural order (row = b j + k).
+        CKI(composition_polys(ctx, comp, log_n, D, kc, &cpolys));
+        scope.drop(comp);
+        const u32 kpr = (u32)(b / (size_t)G);
+        const size_t nj = n / (size_t)G;     // points of every coset that fall into one rank's row range
+        wf_mat *ccos = nullptr, *stage = nullptr;
+        CKI(wf_mat_alloc_w(ctx, (size_t)kpr * n, cpolys->m.cols, cpolys->m.W, &ccos));
+        int rc = wf_mat_lde_cosets(ctx, cpolys, log_b, (u32)r * kpr, (u32)(r + 1) * kpr, ccos);
+        if (rc == WF_OK) rc = wf_mat_alloc_w(ctx, rows_per, cpolys->m.cols, cpolys->m.W, &stage);
+        if (rc == WF_OK) rc = wf_mat_alloc_w(ctx, rows_per, cpolys->m.cols, cpolys->m.W, &clde);
+        if (rc != WF_OK) { wf_mat_free(ctx, ccos); wf_mat_free(ctx, stage); return rc; }
+        wf_mark(ctx, "composition_lde");
+        {
+            const int W = cpolys->m.W;
+            const size_t blk = nj * W;       // words of one (coset, destination) block of one segment
+            std::vector<int> sp, rp;
+            std::vector<const void*> sv;
+            std::vector<void*> rv;
+            for (u32 sg = 0; sg < ccos->m.nseg(); sg++) {
+                const u64* cb = ccos->m.base + (size_t)sg * ccos->m.seg_stride;
+                u64* sb = stage->m.base + (size_t)sg * stage->m.seg_stride;
+                for (u32 kl = 0; kl < kpr; kl++)
+                    for (int q = 0; q < G; q++) {
+                        const u64* src = cb + ((size_t)kl * n + (size_t)q * nj) * W;
+                        if (q == r) CK(cudaMemcpyAsync(sb + ((size_t)r * kpr + kl) * blk, src, blk * 8, cudaMemcpyDeviceToDevice, ctx->st));
+                        else { sp.push_back(q); sv.push_back(src); }
+                    }
+                for (u32 k = 0; k < (u32)b; k++) {
+                    const int owner = (int)(k / kpr);
+                    if (owner != r) { rp.push_back(owner); rv.push_back(sb + (size_t)k * blk); }
+                }
+            }
+            // pairwise order: sender r -> q lists (segment, local coset) ascending; receiver q <- s lists (segment, coset) ascending
+            rc = sc.exchange(sp, sv, rp, rv, blk * 8);
+            if (rc == WF_OK) {
+                dim3 grid((unsigned)((rows_per * W + 255) / 256), clde->m.nseg());
+                coset_interleave_kernel<<<grid, 256, 0, ctx->st>>>(stage->m, clde->m, nj, (u32)b);
+                ctx->launches++;
+                if (cudaGetLastError() != cudaSuccess) rc = wf_fail(ctx, WF_ERR_CUDA, "coset_interleave_kernel launch failed");
+            }
+        }
+        wf_mat_free(ctx, ccos);
+        wf_mat_free(ctx, stage);
+        if (rc != WF_OK) return rc;
+        cview.m = clde->m;               // clde IS my row shard
+    } else {
+        CKI(composition_commit(ctx, h, comp, log_n, log_b, D, kc, &cpolys, &clde, nullptr));
+        scope.drop(comp);
+        cview.m = clde->m;
+        cview.m.base += (size_t)r * rows_per * clde->m.W;
+        cview.m.rows = rows_per;
+    }
+    const bool comp_sharded = b % (size_t)G == 0;
     CKI(wf_commit_rows_partitioned(ctx, h, &cview, o.part_words(kc, D), &ctree.local));
     ctree.n_global = N;
     CKI(shard_tree_finish(sc, h, ctree, &root));
@@ -1757,7 +1826,8 @@ int prove_fib_sharded(wf_ctx* ctx, const wf_comm* cm, const uint64_t* const* loc
     };
     std::vector<std::pair<size_t, u64>> top_t, top_c;
     size_t tr_rows = gb.add_rows(shard->m, owned_rows(pos, rows_per));
-    size_t cr_rows = gb.add_rows(clde->m, r == 0 ? pos : std::vector<u64>(pos.size(), NONE));  // replicated: rank 0 contributes
+    size_t cr_rows = comp_sharded ? gb.add_rows(cview.m, owned_rows(pos, rows_per))
+                                  : gb.add_rows(clde->m, r == 0 ? pos : std::vector<u64>(pos.size(), NONE));  // replicated: rank 0 contributes
     size_t tr_dig, cr_dig;
     CKI(gb.add_opening_sharded(ctx, ttree.local, N, G, r, pos, &tr_dig, &top_t));
     CKI(gb.add_opening_sharded(ctx, ctree.local, N, G, r, pos, &cr_dig, &top_c));
