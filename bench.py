@@ -175,12 +175,29 @@ def run_reference(args, rank, world):
     ms, steps_run, warm_run, cores = cpu_prove(pairs, log_n, ext, args.steps, min(args.warmup, 1), budget)
     sample = (ORACLE_DESC.format(cores=cores) + f"; FULL configuration (2^{log_n} rows x {2 * pairs} columns), {steps_run} timed proof(s) "
               f"actually run inside a {budget:.0f} s wall budget ({args.steps} requested), no scaling")
+    # how the port's parallel decomposition scales on this host: the same AIR at 2^16 rows with 1 thread and with all of them
+    scaling = None
+    try:
+        from oracle import oracle as o
+        s_log = min(16, log_n)
+        tr, res = o.build_fib_trace(pairs, 1 << s_log)
+        opts = proof_opts(ext)
+        tms = {}
+        for th in (1, cores):
+            o.set_threads(th)
+            t0 = time.perf_counter()
+            o.prove_fib(tr, res, opts)
+            tms[th] = (time.perf_counter() - t0) * 1e3
+        scaling = {"rows_log2": s_log, "ms_1_thread": round(tms[1], 1), f"ms_{cores}_threads": round(tms[cores], 1),
+                   "speedup": round(tms[1] / tms[cores], 2)}
+    except Exception as e:  # never take the line down
+        scaling = {"failed": str(e)}
     line = {
         "impl": "reference", "metric": METRIC, "value": round(ms, 3), "unit": "ms", "n_gpus": args.gpus, "steps": steps_run,
         "warmup": warm_run, "steps_requested": args.steps, "warmup_requested": args.warmup,
         "ms_per_step": round(ms, 3), "higher_is_better": False, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": {"workload": workload_name(args.config)},
-        "cpu_baseline": {"value": round(ms, 3), "unit": "ms", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(ms, 3), "unit": "ms", "cores": cores, "kind": "port", "sample": sample, "thread_scaling": scaling},
         "e2e": {"value": round(ms, 3), "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -43,6 +43,7 @@ extern "C" {
 
 #define WF_HASH_BLAKE3_256 0 /* crypto/src/hash/blake/mod.rs:21 */
 #define WF_HASH_RP64_256 1   /* crypto/src/hash/rescue/rp64_256/mod.rs:118 */
+#define WF_HASH_RPJIVE64_256 2 /* crypto/src/hash/rescue/rp64_256_jive/mod.rs:112 (Jive compression for merges) */
 
 typedef struct wf_ctx wf_ctx;
 typedef struct wf_mat wf_mat;   /* device matrix of base-field columns (segment layout) */
@@ -270,12 +271,20 @@ typedef struct wf_comm {
     /* element-wise wrapping sum over the ranks of `words` 64-bit words of a DEVICE buffer, in place (merges gathers
      * whose entries are non-zero on exactly one rank); same ordering rule as exchange */
     int (*all_reduce_sum)(void* user, void* d_buf, size_t words);
+    /* Optional (may be NULL: every exchange is then ordered on the ctx stream). fork: exchanges issued from now on run on the
+     * communicator's own stream, ordered after everything enqueued on the ctx stream so far — the library keeps enqueuing
+     * kernels on the ctx stream meanwhile (the LDE of the next coset overlaps the exchange of the previous one). fork may
+     * be called repeatedly; each call adds "wait for the ctx stream's current tail" to the communicator stream. join: the
+     * ctx stream waits for every exchange issued since the first fork; later exchanges are on the ctx stream again. */
+    int (*fork)(void* user);
+    int (*join)(void* user);
 } wf_comm;
 /* FibSmall x k (as wf_prove_fib) sharded over comm->world GPUs: this rank passes ITS 2k/world columns (host columns, or
  * d_local = device column-major [2k/world][2^log_n]); 2k/world must be a multiple of 8 (whole 8-column segments).
  * `results` and `opts` are the full proof's; every rank returns the same proof bytes.
- * stats (optional, 8 doubles): [0] bytes this rank sent through exchange, [1] ms inside exchange, [2] number of
- * collectives, [3] ms inside all_gather_host + all_reduce_sum. */
+ * stats (optional, 8 doubles): [0] bytes this rank sent through exchanges ordered on the ctx stream, [1] ms inside those,
+ * [2] number of collectives, [3] ms inside all_gather_host + all_reduce_sum, [4] FRI layers folded on shards, [5] bytes sent
+ * through exchanges overlapped with compute (between fork and join: the trace LDE's cosets). */
 int wf_prove_fib_sharded(wf_ctx* ctx, const wf_comm* comm, const uint64_t* const* local_cols, const uint64_t* d_local, int mont,
                          uint32_t k, uint32_t log_n, const uint64_t* results, const uint32_t* opts, uint8_t* proof,
                          size_t* proof_len, double* stats);

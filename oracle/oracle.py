@@ -15,6 +15,7 @@ _SO = os.path.join(_HERE, "_build", "libwf_oracle.so")
 P = 0xFFFFFFFF00000001
 BLAKE3 = 0
 RP64 = 1
+RPJIVE = 2
 
 
 def build(force=False):
@@ -195,6 +196,12 @@ def blake3(data: bytes) -> bytes:
 def rp64_permute(state):
     s = np.array(state, dtype=np.uint64, copy=True)
     lib().wfo_rp64_permute(s.ctypes.data_as(u64p))
+    return s
+
+
+def rpjive_permute(state):
+    s = np.array(state, dtype=np.uint64, copy=True)
+    lib().wfo_rpjive_permute(s.ctypes.data_as(u64p))
     return s
 
 

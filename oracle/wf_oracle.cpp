@@ -532,19 +532,88 @@ static void rp_merge_with_int(const u8 seed[32], u64 value, u8 out[32]) {  // mo
 }
 
 // =================================================================================================
+// RESCUE PRIME RpJive64_256  (crypto/src/hash/rescue/rp64_256_jive/mod.rs): 8-element state, Jive compression
+// =================================================================================================
+#include "rpjive_constants.inc"
+static void rpj_mds(u64 s[8]) {  // mds_f64_8x8.rs: circulant with first row RPJ_MDS_ROW0 (naive product, as for Rp64 above)
+    u64 r[8];
+    for (int i = 0; i < 8; i++) {
+        u128 acc = 0;
+        for (int j = 0; j < 8; j++) acc += (u128)RPJ_MDS_ROW0[(j + 8 - i) % 8] * s[j];
+        r[i] = f_red128(acc % ((u128)P << 32));
+    }
+    memcpy(s, r, sizeof(r));
+}
+static u64 rpj_inv7(u64 x) {  // mod.rs:378-412: x^10540996611094048183 by plain square-and-multiply (the reference uses a chain)
+    u64 e = 10540996611094048183ULL, r = 1, b = x;
+    while (e) { if (e & 1) r = f_mul(r, b); b = f_mul(b, b); e >>= 1; }
+    return r;
+}
+static void rpj_permute(u64 s[8]) {  // mod.rs:313-333
+    for (int r = 0; r < 7; r++) {
+        for (int i = 0; i < 8; i++) s[i] = f_exp7(s[i]);
+        rpj_mds(s);
+        for (int i = 0; i < 8; i++) s[i] = f_add(s[i], RPJ_ARK1[r][i]);
+        for (int i = 0; i < 8; i++) s[i] = rpj_inv7(s[i]);
+        rpj_mds(s);
+        for (int i = 0; i < 8; i++) s[i] = f_add(s[i], RPJ_ARK2[r][i]);
+    }
+}
+static void rpj_jive(const u64 init[8], u8 out[32]) {  // permutation + apply_jive_summation (mod.rs:337-350)
+    u64 s[8], d[4];
+    memcpy(s, init, sizeof(s));
+    rpj_permute(s);
+    for (int i = 0; i < 4; i++) d[i] = f_add(f_add(init[i], init[4 + i]), f_add(s[i], s[4 + i]));
+    memcpy(out, d, 32);
+}
+static void rpj_hash_elements(const u64* e, size_t n, u8 out[32]) {  // mod.rs:240-282
+    u64 s[8] = {0};
+    if (n % 4 != 0) s[0] = 1;
+    size_t i = 0;
+    for (size_t k = 0; k < n; k++) {
+        s[4 + i] = f_add(s[4 + i], e[k]);
+        i++;
+        if (i % 4 == 0) { rpj_permute(s); i = 0; }
+    }
+    if (i > 0) {
+        s[4 + i] = 1;
+        i++;
+        while (i != 4) { s[4 + i] = 0; i++; }
+        rpj_permute(s);
+    }
+    memcpy(out, s + 4, 32);
+}
+static void rpj_merge(const u8 two[64], u8 out[32]) {  // mod.rs:186-196
+    u64 s[8];
+    memcpy(s, two, 64);
+    rpj_jive(s, out);
+}
+static void rpj_merge_with_int(const u8 seed[32], u64 value, u8 out[32]) {  // mod.rs:206-229
+    u64 s[8] = {0};
+    memcpy(s, seed, 32);
+    s[4] = value % P;
+    if (value < P) s[7] = 5;
+    else { s[5] = value / P; s[7] = 6; }
+    rpj_jive(s, out);
+}
+
+// =================================================================================================
 // HASHER DISPATCH  (crypto/src/hash/mod.rs:31-64)
 // =================================================================================================
 static void hash_elements(int h, const u64* e, size_t n, u8 out[32]) {
     if (h == WFO_HASH_BLAKE3_256) blake3_hash((const u8*)e, n * 8, out);  // blake/mod.rs:52-65: canonical LE bytes
-    else rp_hash_elements(e, n, out);
+    else if (h == WFO_HASH_RP64_256) rp_hash_elements(e, n, out);
+    else rpj_hash_elements(e, n, out);
 }
 static void merge(int h, const u8 two[64], u8 out[32]) {
     if (h == WFO_HASH_BLAKE3_256) blake3_hash(two, 64, out);  // blake/mod.rs:33
-    else rp_merge(two, out);
+    else if (h == WFO_HASH_RP64_256) rp_merge(two, out);
+    else rpj_merge(two, out);
 }
 static void merge_many(int h, const u8* dg, size_t n, u8 out[32]) {
     if (h == WFO_HASH_BLAKE3_256) blake3_hash(dg, n * 32, out);  // blake/mod.rs:37
-    else rp_hash_elements((const u64*)dg, n * 4, out);           // rp64_256/mod.rs:194
+    else if (h == WFO_HASH_RP64_256) rp_hash_elements((const u64*)dg, n * 4, out);  // rp64_256/mod.rs:194
+    else rpj_hash_elements((const u64*)dg, n * 4, out);                             // rp64_256_jive/mod.rs:198-200
 }
 static void merge_with_int(int h, const u8 seed[32], u64 value, u8 out[32]) {
     if (h == WFO_HASH_BLAKE3_256) {  // blake/mod.rs:41-46
@@ -552,7 +621,8 @@ static void merge_with_int(int h, const u8 seed[32], u64 value, u8 out[32]) {
         memcpy(data, seed, 32);
         memcpy(data + 32, &value, 8);
         blake3_hash(data, 40, out);
-    } else rp_merge_with_int(seed, value, out);
+    } else if (h == WFO_HASH_RP64_256) rp_merge_with_int(seed, value, out);
+    else rpj_merge_with_int(seed, value, out);
 }
 
 static void hash_rows(int h, const u64* rows, size_t nrows, size_t w, size_t part, u8* digests) {
@@ -770,6 +840,7 @@ void wfo_lde_rows(const uint64_t* polys, size_t c, size_t n, int d, size_t blowu
 
 void wfo_blake3(const uint8_t* data, size_t len, uint8_t out[32]) { blake3_hash(data, len, out); }
 void wfo_rp64_permute(uint64_t state[12]) { rp_permute(state); }
+void wfo_rpjive_permute(uint64_t state[8]) { rpj_permute(state); }
 void wfo_hash_elements(int h, const uint64_t* e, size_t n, uint8_t out[32]) { hash_elements(h, e, n, out); }
 void wfo_merge(int h, const uint8_t two[64], uint8_t out[32]) { merge(h, two, out); }
 void wfo_merge_many(int h, const uint8_t* dg, size_t n, uint8_t out[32]) { merge_many(h, dg, n, out); }

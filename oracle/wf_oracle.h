@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-enum { WFO_HASH_BLAKE3_256 = 0, WFO_HASH_RP64_256 = 1 };
+enum { WFO_HASH_BLAKE3_256 = 0, WFO_HASH_RP64_256 = 1, WFO_HASH_RPJIVE64_256 = 2 };
 
 void wfo_set_threads(int n);  // number of OpenMP threads for the `concurrent`-style loops
 int wfo_get_threads(void);
@@ -56,6 +56,7 @@ void wfo_lde_rows(const uint64_t* polys, size_t c, size_t n, int d, size_t blowu
 // ---- hashing (crypto/src/hash) ----
 void wfo_blake3(const uint8_t* data, size_t len, uint8_t out[32]);
 void wfo_rp64_permute(uint64_t state[12]);
+void wfo_rpjive_permute(uint64_t state[8]);  // rp64_256_jive/mod.rs:313-319
 void wfo_hash_elements(int hash_id, const uint64_t* elems, size_t n, uint8_t out[32]);
 void wfo_merge(int hash_id, const uint8_t two[64], uint8_t out[32]);
 void wfo_merge_many(int hash_id, const uint8_t* digests, size_t n, uint8_t out[32]);

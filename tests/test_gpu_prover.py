@@ -29,6 +29,9 @@ CASES = [
     (32, 9, 3, wf.HASH_BLAKE3_256, 4, 31, 2, 0, 8, 32),  # configs[2] AIR (64 columns, cubic), Horner batching
     (2, 8, 2, wf.HASH_BLAKE3_256, 2, 7, 0, 0, 4, 20),
     (3, 9, 1, wf.HASH_RP64_256, 16, 7, 2, 0, 16, 12),
+    (1, 7, 1, wf.HASH_RPJIVE64_256, 4, 7, 0, 0, 8, 28),  # fib_small with the Jive-mode hasher (rp64_256_jive/mod.rs)
+    (2, 9, 3, wf.HASH_RPJIVE64_256, 4, 7, 1, 3, 8, 20),
+    (4, 8, 2, wf.HASH_RPJIVE64_256, 8, 15, 2, 0, 4, 16),
 ]
 
 
@@ -60,7 +63,7 @@ def test_montgomery_trace_input(ctx, oracle):
     assert ctx.prove_fib(tm, results, opts, mont=True) == oracle.prove_fib(trace, results, opts)
 
 
-@pytest.mark.parametrize("h,g", [(wf.HASH_BLAKE3_256, 16), (wf.HASH_BLAKE3_256, 21), (wf.HASH_RP64_256, 10)])
+@pytest.mark.parametrize("h,g", [(wf.HASH_BLAKE3_256, 16), (wf.HASH_BLAKE3_256, 21), (wf.HASH_RP64_256, 10), (wf.HASH_RPJIVE64_256, 9)])
 def test_grinding_smallest_nonce(ctx, oracle, h, g):
     # prover/src/channel.rs:173-175 (serial branch): smallest nonce
     coin = oracle.RandomCoin(h, [1, 2, 3, g])
@@ -243,7 +246,7 @@ def test_overlapping_assertions_are_refused(ctx, oracle):
 # still merge_many); (16, 1) is the maximum partition count.
 @pytest.mark.parametrize("k,log_n,ext,h,parts,rate", [
     (4, 10, 1, wf.HASH_BLAKE3_256, 2, 8), (4, 10, 3, wf.HASH_BLAKE3_256, 4, 8), (32, 9, 3, wf.HASH_BLAKE3_256, 8, 8),
-    (8, 9, 2, wf.HASH_RP64_256, 2, 8), (4, 9, 1, wf.HASH_RP64_256, 8, 8), (1, 9, 3, wf.HASH_BLAKE3_256, 4, 64),
+    (8, 9, 2, wf.HASH_RP64_256, 2, 8), (4, 9, 1, wf.HASH_RP64_256, 8, 8), (4, 8, 3, wf.HASH_RPJIVE64_256, 4, 4), (1, 9, 3, wf.HASH_BLAKE3_256, 4, 64),
     (16, 9, 1, wf.HASH_BLAKE3_256, 16, 1)])
 def test_partitioned_commitments_match_oracle(ctx, oracle, k, log_n, ext, h, parts, rate):
     trace, results = oracle.build_fib_trace(k, 1 << log_n)
@@ -255,7 +258,7 @@ def test_partitioned_commitments_match_oracle(ctx, oracle, k, log_n, ext, h, par
     assert got != ctx.prove_fib(trace, results, oracle.make_opts(num_queries=24, grinding=3, ext=ext, folding=4, rem_max_deg=7, hash_id=h))
 
 
-@pytest.mark.parametrize("ext,h,parts,rate", [(2, wf.HASH_BLAKE3_256, 2, 2), (3, wf.HASH_RP64_256, 3, 8)])
+@pytest.mark.parametrize("ext,h,parts,rate", [(2, wf.HASH_BLAKE3_256, 2, 2), (3, wf.HASH_RP64_256, 3, 8), (2, wf.HASH_RPJIVE64_256, 2, 4)])
 def test_partitioned_aux_segment_vs_oracle(ctx, oracle, ext, h, parts, rate):
     # the auxiliary commitment uses partition_size::<E>(aux_width) (trace_lde/default/mod.rs:147), the constraint commitment
     # partition_size::<E>(num composition columns) (constraints/commitment/default.rs:147)

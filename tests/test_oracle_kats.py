@@ -197,6 +197,73 @@ def test_rp64_consistency(oracle):
     assert oracle.merge_with_int(R, seed.tobytes(), v) == oracle.hash_elements(R, np.array([int(x) for x in seed] + [v % P, 1], dtype=np.uint64))
 
 
+def test_rpjive_permutation_kat(oracle):
+    # crypto/src/hash/rescue/rp64_256_jive/tests.rs:69-101 (Sage reference vector)
+    expected = [16940713730596720799, 16218555904323712189, 11042680722444601138, 5370396747047489939,
+                6349480890410006944, 1551053614279730715, 3995941143622927528, 9350074312471431779]
+    assert [int(v) for v in oracle.rpjive_permute(np.arange(8, dtype=np.uint64))] == expected
+
+
+def _py_rpjive_hash_elements(oracle, elems):
+    # rp64_256_jive/mod.rs:240-282 restated on Python integers over the (KAT-pinned) permutation
+    s = [0] * 8
+    if len(elems) % 4:
+        s[0] = 1
+    i = 0
+    for e in elems:
+        s[4 + i] = (s[4 + i] + int(e)) % P
+        i += 1
+        if i == 4:
+            s = [int(v) for v in oracle.rpjive_permute(np.array(s, dtype=np.uint64))]
+            i = 0
+    if i > 0:
+        s[4 + i] = 1
+        for q in range(i + 1, 4):
+            s[4 + q] = 0
+        s = [int(v) for v in oracle.rpjive_permute(np.array(s, dtype=np.uint64))]
+    return np.array(s[4:8], dtype=np.uint64).tobytes()
+
+
+def _py_rpjive_compress(oracle, state):
+    out = [int(v) for v in oracle.rpjive_permute(np.array(state, dtype=np.uint64))]
+    return np.array([(state[i] + state[4 + i] + out[i] + out[4 + i]) % P for i in range(4)], dtype=np.uint64).tobytes()
+
+
+def test_rpjive_hasher_structure(oracle):
+    # the sponge (padding by overwriting, capacity flag), the Jive compression of merge / merge_with_int
+    # (rp64_256_jive/mod.rs:186-229, 337-350) and merge_many = hash_elements (:198-200), against a Python restatement; and the
+    # reference's own consistency tests (tests.rs:103-140): merge and merge_with_int must DIFFER from hash_elements
+    J = oracle.RPJIVE
+    for n in (1, 3, 4, 5, 8, 9, 12, 17):
+        e = oracle.rand_elems(n, 40 + n)
+        assert oracle.hash_elements(J, e) == _py_rpjive_hash_elements(oracle, e)
+    e = oracle.rand_elems(8, 21)
+    m = oracle.merge(J, e[:4].tobytes(), e[4:].tobytes())
+    assert m == _py_rpjive_compress(oracle, [int(v) for v in e])
+    assert m != oracle.hash_elements(J, e)
+    assert oracle.merge_many(J, e.tobytes()) == oracle.hash_elements(J, e)
+    seed = oracle.rand_elems(4, 22)
+    for v in (int(oracle.rand_elems(1, 23)[0]), P + 2, 0, P - 1, 2**64 - 1):
+        st = [int(x) for x in seed] + [v % P, v // P if v >= P else 0, 0, 6 if v >= P else 5]
+        got = oracle.merge_with_int(J, seed.tobytes(), v)
+        assert got == _py_rpjive_compress(oracle, st)
+        assert got != oracle.hash_elements(J, np.array([int(x) for x in seed] + [v % P], dtype=np.uint64))
+
+
+def test_rpjive_round_trip_and_tamper(oracle):
+    # a complete proof over RpJive64_256 (hash id 2): leaves by the sponge, tree nodes / coin by Jive compression
+    k, n = 2, 128
+    trace, res = oracle.build_fib_trace(k, n)
+    for ext in (1, 2):
+        opts = oracle.make_opts(ext=ext, hash_id=oracle.RPJIVE, grinding=3, folding=4, rem_max_deg=7)
+        proof = oracle.prove_fib(trace, res, opts)
+        assert oracle.verify_fib(proof, k, res, oracle.RPJIVE) == 0
+        assert oracle.verify_fib(proof, k, res, oracle.RP64) != 0
+        t = bytearray(proof)
+        t[len(t) // 2] ^= 4
+        assert oracle.verify_fib(bytes(t), k, res, oracle.RPJIVE) != 0
+
+
 # ---- Merkle: crypto/src/merkle/tests.rs:14-84 ----
 LEAVES4 = [
     [166, 168, 47, 140, 153, 86, 156, 86, 226, 229, 149, 76, 70, 132, 209, 109, 166, 193, 113, 197, 42, 116, 170, 144, 74, 104, 29, 110, 220, 49, 224, 123],

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("WF_LIB_PATH") or os.path.join(_HERE, "libwinterfell_b
 P = 0xFFFFFFFF00000001
 HASH_BLAKE3_256 = 0
 HASH_RP64_256 = 1
+HASH_RPJIVE64_256 = 2
 
 WF_OK = 0
 

@@ -652,22 +652,52 @@ int wf_mat_lde_cosets(wf_ctx* ctx, const wf_mat* polys, uint32_t log_blowup, uin
 // compute stream. Columns are independent, so the result equals from_host_columns -> interpolate -> lde.
 int wf_trace_lde_from_host(wf_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, size_t nrows, int mont, uint32_t log_blowup,
                            wf_mat** polys_out, wf_mat** lde_out) {
-    if (!ctx || !cols || !polys_out || !lde_out || ncols == 0) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    return wf_trace_lde_cosetwise(ctx, cols, nullptr, ncols, nrows, mont, log_blowup, polys_out, lde_out, false, nullptr);
+}
+// The same pipeline with two knobs for the sharded prover (prover.cu): coset_major = the LDE is written coset-major
+// (row k * n + j = P(7 w_N^k w_n^j); *lde_out must then be preallocated with the natural segment width) and after_coset(k)
+// is called once coset k of ALL columns has been enqueued on the ctx stream — the caller starts that coset's exchange there.
+// d_cols != NULL: the columns are already on the device (column-major), no upload stage.
+int wf_trace_lde_cosetwise(wf_ctx* ctx, const uint64_t* const* cols, const uint64_t* d_cols, uint32_t ncols, size_t nrows, int mont,
+                           uint32_t log_blowup, wf_mat** polys_out, wf_mat** lde_out, bool coset_major,
+                           const std::function<int(u32)>* after_coset) {
+    if (!ctx || (!cols && !d_cols) || !polys_out || !lde_out || ncols == 0) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     u32 log_n;
     if (log2_exact(nrows, &log_n) || log_n < 1) return wf_fail(ctx, WF_ERR_INVALID, "rows must be a power of two >= 2");
     if (log_blowup > 7 || log_n + log_blowup > 32) return wf_fail(ctx, WF_ERR_INVALID, "bad blowup");
     const int Wout = seg_width_for(ncols);
     const u32 nseg_out = (ncols + Wout - 1) / Wout;
+    const u32 nb = 1u << log_blowup;
+    if (coset_major && (!*lde_out || (*lde_out)->m.rows != (nrows << log_blowup) || (*lde_out)->m.W != Wout || (*lde_out)->m.cols != ncols))
+        return wf_fail(ctx, WF_ERR_INVALID, "coset-major output must be preallocated");
+    // cosets of one column chunk: all at once, or one by one with the callback when this is the last chunk
+    auto extend = [&](const SegMatrix& pv, SegMatrix& ov, u32 out_col0, bool last) -> int {
+        if (!after_coset || !last) {
+            if (!coset_major) return run_lde(ctx, pv, ov, log_n, log_blowup, out_col0);
+            return run_lde(ctx, pv, ov, log_n, log_blowup, out_col0, 0, nb, 1, (u32)nrows);
+        }
+        for (u32 k = 0; k < nb; k++) {   // run_lde places its FIRST coset at the view's origin: shift the view to coset k's rows
+            SegMatrix ok = ov;
+            ok.base += (coset_major ? (size_t)k * nrows : (size_t)k) * ov.W;
+            if (coset_major) CKI(run_lde(ctx, pv, ok, log_n, log_blowup, out_col0, k, k + 1, 1, (u32)nrows));
+            else CKI(run_lde(ctx, pv, ok, log_n, log_blowup, out_col0, k, k + 1, nb, 1));
+            CKI((*after_coset)(k));
+        }
+        return WF_OK;
+    };
     int Wc = nseg_out >= 2 ? Wout : (Wout >= 4 ? Wout / 2 : 0);
     // (measured on cfg2, 8 columns: halves 7.03 ms e2e, quarters 7.35 — W = 2 tiles cost more than the
     // shorter upload head saves — no pipeline 7.36)
-    if (Wc == 0 || log_n < 12) {  // too narrow / too small to be worth a pipeline
+    if (d_cols || Wc == 0 || log_n < 12) {  // resident columns, or too narrow / too small to be worth a pipeline
         wf_mat* tr;
-        CKI(wf_mat_from_host_columns(ctx, cols, ncols, nrows, 1, mont, &tr));
+        if (d_cols) CKI(wf_mat_from_device_columns(ctx, d_cols, ncols, nrows, &tr));
+        else CKI(wf_mat_from_host_columns(ctx, cols, ncols, nrows, 1, mont, &tr));
         int r = wf_mat_interpolate(ctx, tr, polys_out);
         wf_mat_free(ctx, tr);
         if (r != WF_OK) return r;
-        return wf_mat_lde(ctx, *polys_out, log_blowup, lde_out);
+        if (!coset_major && !after_coset) return wf_mat_lde(ctx, *polys_out, log_blowup, lde_out);
+        if (!coset_major) CKI(wf_mat_alloc(ctx, nrows << log_blowup, ncols, lde_out));
+        return extend((*polys_out)->m, (*lde_out)->m, 0, true);
     }
     if (!ctx->copy_st) {
         CK(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
@@ -685,11 +715,12 @@ int wf_trace_lde_from_host(wf_ctx* ctx, const uint64_t* const* cols, uint32_t nc
         wf_mat_free(ctx, tr);
         for (int i = 0; i < 2; i++) wf_dev_free(ctx, stage[i]);
         wf_dev_free(ctx, tmp);
-        if (results_too) { wf_mat_free(ctx, polys); wf_mat_free(ctx, lde); }
+        if (results_too) { wf_mat_free(ctx, polys); if (!coset_major) wf_mat_free(ctx, lde); }
     };
     auto body = [&]() -> int {
         CKI(wf_mat_alloc_w(ctx, nrows, ncols, Wc, &polys));
-        CKI(wf_mat_alloc(ctx, nrows << log_blowup, ncols, &lde));
+        if (coset_major) lde = *lde_out;
+        else CKI(wf_mat_alloc(ctx, nrows << log_blowup, ncols, &lde));
         CKI(wf_mat_alloc_w(ctx, nrows, Wc, Wc, &tr));                       // one chunk of trace values (reused)
         for (int i = 0; i < 2; i++) CKI(wf_dev_alloc(ctx, (size_t)Wc * nrows * 8, &stage[i]));
         CKI(wf_dev_alloc(ctx, (size_t)Wc * nrows * 8, &tmp));               // two-pass scratch
@@ -719,7 +750,7 @@ int wf_trace_lde_from_host(wf_ctx* ctx, const uint64_t* const* cols, uint32_t nc
             SegMatrix ov = lde->m;                                            // out segment holding columns c0..
             ov.base = lde->m.base + (size_t)(c0 / Wout) * lde->m.seg_stride;
             ov.cols = cw;
-            CKI(run_lde(ctx, pv, ov, log_n, log_blowup, c0 % Wout));
+            CKI(extend(pv, ov, c0 % Wout, k + 1 == nchunks));
         }
         return WF_OK;
     };
@@ -776,7 +807,7 @@ static u32 merkle_launches(size_t nleaves) {
 }
 int wf_commit_rows_partitioned(wf_ctx* ctx, int hash_id, const wf_mat* m, uint32_t partition_size, wf_tree** out) {
     if (!ctx || !m || !out) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
-    if (hash_id != WF_HASH_BLAKE3_256 && hash_id != WF_HASH_RP64_256) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "unknown hash %d", hash_id);
+    if (!WF_HASH_IS_KNOWN(hash_id)) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "unknown hash %d", hash_id);
     if (partition_size != 0 && partition_size != m->m.cols && (m->m.cols + partition_size - 1) / partition_size > 16)
         return wf_fail(ctx, WF_ERR_INVALID, "more than 16 partitions");
     wf_tree* t;
@@ -789,7 +820,7 @@ int wf_commit_rows_partitioned(wf_ctx* ctx, int hash_id, const wf_mat* m, uint32
 }
 int wf_commit_rows(wf_ctx* ctx, int hash_id, const wf_mat* m, wf_tree** out) {
     if (!ctx || !m || !out) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
-    if (hash_id != WF_HASH_BLAKE3_256 && hash_id != WF_HASH_RP64_256) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "unknown hash %d", hash_id);
+    if (!WF_HASH_IS_KNOWN(hash_id)) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "unknown hash %d", hash_id);
     wf_tree* t;
     CKI(tree_alloc(ctx, hash_id, m->m.rows, &t));
     CK(commit_hash_rows(hash_id, m->m, t->leaves, ctx->st));

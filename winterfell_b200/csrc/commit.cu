@@ -12,7 +12,7 @@
 #include "commit.cuh"
 
 #include "blake3.cuh"
-#include "rp64.cuh"
+#include "alg_hash.cuh"
 
 // ---- row access in segment layout -----------------------------------------------------------
 struct RowSrc {
@@ -105,27 +105,42 @@ __global__ void __launch_bounds__(256) hash_rows_blake3_kernel(RowSrc m, size_t 
     digests[2 * row + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
 
-__global__ void __launch_bounds__(128) hash_rows_rp64_kernel(RowSrc m, size_t nrows, u64* __restrict__ digests) {
+template <int HASH>
+__global__ void __launch_bounds__(128) hash_rows_alg_kernel(RowSrc m, size_t nrows, u64* __restrict__ digests) {
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nrows) return;
-    u64 s[12];
+    AlgSponge<HASH> sp;  // rp64_256/mod.rs:237-246, rp64_256_jive/mod.rs:240-282
+    sp.init(m.cols);
+    for (u32 e = 0; e < m.cols; e++) sp.absorb(row_elem(m, row, e));
+    u64 o[4];
+    sp.finish(o);
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = 0;
-    s[0] = m.cols;
-    u32 i = 0;
-    for (u32 e = 0; e < m.cols; e++) {  // rp64_256/mod.rs:237-246
-        s[4 + i] = gl_add(s[4 + i], row_elem(m, row, e));
-        if (++i == 8) { rp64_permute(s); i = 0; }
-    }
-    if (i > 0) rp64_permute(s);
-#pragma unroll
-    for (int k = 0; k < 4; k++) digests[row * 4 + k] = s[4 + k];
+    for (int k = 0; k < 4; k++) digests[row * 4 + k] = o[k];
 }
 
 // Partitioned row hashing (row_matrix.rs:204-223, PartitionOptions air/src/options.rs:405-445):
 // digest = merge_many(hash_elements(chunk_0), hash_elements(chunk_1), ...), chunks of `psize` base
 // columns. merge_many = BLAKE3 of the concatenated digests (blake/mod.rs:37) or the Rp64 sponge over
 // their elements (rp64_256/mod.rs:194).
+template <int HASH>
+__device__ __forceinline__ void partitioned_alg_row(const RowSrc& m, size_t row, u32 psize, u32 np, u64* __restrict__ digests) {
+    AlgSponge<HASH> outer;  // merge_many = hash_elements over the np * 4 digest elements
+    outer.init((size_t)np * 4);
+    for (u32 j = 0; j < np; j++) {
+        const u32 e0 = j * psize, e1 = min(m.cols, e0 + psize);
+        AlgSponge<HASH> sp;
+        sp.init(e1 - e0);
+        for (u32 e = e0; e < e1; e++) sp.absorb(row_elem(m, row, e));
+        u64 d[4];
+        sp.finish(d);
+#pragma unroll
+        for (int k = 0; k < 4; k++) outer.absorb(d[k]);
+    }
+    u64 o[4];
+    outer.finish(o);
+#pragma unroll
+    for (int k = 0; k < 4; k++) digests[row * 4 + k] = o[k];
+}
 __global__ void __launch_bounds__(128) hash_rows_partitioned_kernel(int hash_id, RowSrc m, size_t nrows, u32 psize,
                                                                     u64* __restrict__ digests) {
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -151,32 +166,10 @@ __global__ void __launch_bounds__(128) hash_rows_partitioned_kernel(int hash_id,
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) digests[row * 4 + k] = (u64)cv[2 * k] | ((u64)cv[2 * k + 1] << 32);
+    } else if (hash_id == WF_HASH_RP64_256) {
+        partitioned_alg_row<WF_HASH_RP64_256>(m, row, psize, np, digests);
     } else {
-        u64 acc[12];  // outer sponge over the np*4 digest elements
-#pragma unroll
-        for (int i = 0; i < 12; i++) acc[i] = 0;
-        acc[0] = np * 4;
-        u32 fill = 0;
-        for (u32 j = 0; j < np; j++) {
-            u64 s[12];
-#pragma unroll
-            for (int i = 0; i < 12; i++) s[i] = 0;
-            u32 e0 = j * psize, e1 = min(m.cols, e0 + psize);
-            s[0] = e1 - e0;
-            u32 i = 0;
-            for (u32 e = e0; e < e1; e++) {
-                s[4 + i] = gl_add(s[4 + i], row_elem(m, row, e));
-                if (++i == 8) { rp64_permute(s); i = 0; }
-            }
-            if (i > 0) rp64_permute(s);
-            for (int k = 0; k < 4; k++) {
-                acc[4 + fill] = gl_add(acc[4 + fill], s[4 + k]);
-                if (++fill == 8) { rp64_permute(acc); fill = 0; }
-            }
-        }
-        if (fill > 0) rp64_permute(acc);
-#pragma unroll
-        for (int k = 0; k < 4; k++) digests[row * 4 + k] = acc[4 + k];
+        partitioned_alg_row<WF_HASH_RPJIVE64_256>(m, row, psize, np, digests);
     }
 }
 
@@ -196,14 +189,14 @@ __global__ void __launch_bounds__(256) merkle_level_blake3_kernel(const uint4* _
     out[2 * i] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
     out[2 * i + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
-__global__ void __launch_bounds__(128) merkle_level_rp64_kernel(const u64* __restrict__ in, u64* __restrict__ out,
-                                                                size_t count) {
+template <int HASH>
+__global__ void __launch_bounds__(128) merkle_level_alg_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     u64 v[8], o[4];
 #pragma unroll
     for (int k = 0; k < 8; k++) v[k] = in[8 * i + k];
-    rp64_merge(v, o);
+    alg_merge<HASH>(v, o);
 #pragma unroll
     for (int k = 0; k < 4; k++) out[4 * i + k] = o[k];
 }
@@ -222,7 +215,7 @@ __device__ __forceinline__ void merge_digests(const u64* a /*8 words: two digest
 #pragma unroll
         for (int k = 0; k < 4; k++) out[k] = (u64)cv[2 * k] | ((u64)cv[2 * k + 1] << 32);
     } else {
-        rp64_merge(a, out);
+        alg_merge<HASH>(a, out);
     }
 }
 template <int HASH>
@@ -280,7 +273,8 @@ cudaError_t commit_hash_rows(int hash_id, const SegMatrix& m, u64* digests, cuda
             hash_rows_blake3_kernel<<<blocks, 256, 0, st>>>(src, m.rows, reinterpret_cast<uint4*>(digests));
     } else {
         unsigned blocks = (unsigned)((m.rows + 127) / 128);
-        hash_rows_rp64_kernel<<<blocks, 128, 0, st>>>(src, m.rows, digests);
+        if (hash_id == WF_HASH_RP64_256) hash_rows_alg_kernel<WF_HASH_RP64_256><<<blocks, 128, 0, st>>>(src, m.rows, digests);
+        else hash_rows_alg_kernel<WF_HASH_RPJIVE64_256><<<blocks, 128, 0, st>>>(src, m.rows, digests);
     }
     return cudaGetLastError();
 }
@@ -297,15 +291,18 @@ cudaError_t commit_merkle_nodes(int hash_id, const u64* leaves, size_t nleaves, 
         if (hash_id == WF_HASH_BLAKE3_256)
             merkle_level_blake3_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src),
                                                                                    reinterpret_cast<uint4*>(dst), m);
+        else if (hash_id == WF_HASH_RP64_256)
+            merkle_level_alg_kernel<WF_HASH_RP64_256><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(src, dst, m);
         else
-            merkle_level_rp64_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(src, dst, m);
+            merkle_level_alg_kernel<WF_HASH_RPJIVE64_256><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(src, dst, m);
         src = dst;
         m >>= 1;
     }
     for (;;) {
         unsigned blocks = (unsigned)((m + 255) / 256);
         if (hash_id == WF_HASH_BLAKE3_256) merkle_subtree_kernel<WF_HASH_BLAKE3_256><<<blocks, 256, 0, st>>>(src, nodes, m);
-        else merkle_subtree_kernel<WF_HASH_RP64_256><<<blocks, 256, 0, st>>>(src, nodes, m);
+        else if (hash_id == WF_HASH_RP64_256) merkle_subtree_kernel<WF_HASH_RP64_256><<<blocks, 256, 0, st>>>(src, nodes, m);
+        else merkle_subtree_kernel<WF_HASH_RPJIVE64_256><<<blocks, 256, 0, st>>>(src, nodes, m);
         if (m <= 256) break;           // this launch reached the root
         // the launch produced levels m, m/2, ..., m/256 (one node per block); continue above them
         size_t top = m >> 8;

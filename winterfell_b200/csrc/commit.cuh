@@ -6,6 +6,8 @@
 
 #define WF_HASH_BLAKE3_256 0
 #define WF_HASH_RP64_256 1
+#define WF_HASH_RPJIVE64_256 2
+#define WF_HASH_IS_KNOWN(h) ((h) == WF_HASH_BLAKE3_256 || (h) == WF_HASH_RP64_256 || (h) == WF_HASH_RPJIVE64_256)
 
 // rows x cols base-field matrix in segment layout (see ntt.cuh):
 // elem(row, col) = base[(col / W) * seg_stride + row * W + col % W]

@@ -5,7 +5,7 @@
 #include "blake3.cuh"
 #include "commit.cuh"
 #include "minidft.cuh"
-#include "rp64.cuh"
+#include "alg_hash.cuh"
 
 __global__ void __launch_bounds__(256) fri_hash_blake3_kernel(const u64* __restrict__ ev, size_t m, int d, int ld, int nf,
                                                               uint4* __restrict__ digests) {
@@ -36,24 +36,22 @@ __global__ void __launch_bounds__(256) fri_hash_blake3_kernel(const u64* __restr
     digests[2 * i + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
 
-__global__ void __launch_bounds__(128) fri_hash_rp64_kernel(const u64* __restrict__ ev, size_t m, int d, int ld, int nf,
-                                                            u64* __restrict__ digests) {
+template <int HASH>
+__global__ void __launch_bounds__(128) fri_hash_alg_kernel(const u64* __restrict__ ev, size_t m, int d, int ld, int nf,
+                                                           u64* __restrict__ digests) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const u32 ne = (u32)(nf * d);
-    u64 s[12];
-#pragma unroll
-    for (int k = 0; k < 12; k++) s[k] = 0;
-    s[0] = ne;
-    u32 r = 0;
+    AlgSponge<HASH> sp;
+    sp.init(ne);
     for (u32 e = 0; e < ne; e++) {
         u32 kk = e / d, comp = e % d;
-        s[4 + r] = gl_add(s[4 + r], ev[(i + (size_t)kk * m) * ld + comp]);
-        if (++r == 8) { rp64_permute(s); r = 0; }
+        sp.absorb(ev[(i + (size_t)kk * m) * ld + comp]);
     }
-    if (r > 0) rp64_permute(s);
+    u64 o[4];
+    sp.finish(o);
 #pragma unroll
-    for (int k = 0; k < 4; k++) digests[i * 4 + k] = s[4 + k];
+    for (int k = 0; k < 4; k++) digests[i * 4 + k] = o[k];
 }
 
 __host__ __device__ constexpr u32 cbrev(u32 v, int bits) {
@@ -114,8 +112,10 @@ cudaError_t fri_hash_layer(int hash_id, const u64* evals, size_t len, int d, int
     if (hash_id == WF_HASH_BLAKE3_256)
         fri_hash_blake3_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(evals, m, d, ld, nf,
                                                                             reinterpret_cast<uint4*>(digests));
+    else if (hash_id == WF_HASH_RP64_256)
+        fri_hash_alg_kernel<WF_HASH_RP64_256><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(evals, m, d, ld, nf, digests);
     else
-        fri_hash_rp64_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(evals, m, d, ld, nf, digests);
+        fri_hash_alg_kernel<WF_HASH_RPJIVE64_256><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(evals, m, d, ld, nf, digests);
     return cudaGetLastError();
 }
 
@@ -169,7 +169,7 @@ __device__ __forceinline__ void coin_merge(const u64 a[4], const u64 b[4], u64 o
         u64 in[8];
 #pragma unroll
         for (int i = 0; i < 4; i++) { in[i] = a[i]; in[4 + i] = b[i]; }
-        rp64_merge(in, out);
+        alg_merge<HASH>(in, out);
     }
 }
 template <int HASH>
@@ -185,17 +185,8 @@ __device__ __forceinline__ void coin_merge_with_int(const u64 seed[4], u64 value
         b3_compress(cv, m, 0, 40, B3_CHUNK_START | B3_CHUNK_END | B3_ROOT);
 #pragma unroll
         for (int i = 0; i < 4; i++) out[i] = (u64)cv[2 * i] | ((u64)cv[2 * i + 1] << 32);
-    } else {  // rp64_256/mod.rs:198-218
-        u64 s[12];
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) s[4 + i] = seed[i];
-        if (value < GL_P) { s[8] = value; s[0] = 5; }
-        else { s[8] = value - GL_P; s[9] = 1; s[0] = 6; }
-        rp64_permute(s);
-#pragma unroll
-        for (int i = 0; i < 4; i++) out[i] = s[4 + i];
+    } else {  // rp64_256/mod.rs:198-218, rp64_256_jive/mod.rs:206-229
+        alg_merge_with_int<HASH>(seed, value, out);
     }
 }
 // state: seed[4]; log: per layer root[4] then alpha[3]
@@ -220,6 +211,7 @@ __global__ void fri_coin_kernel(u64* state, const u64* root, int d, u64* alpha_o
 }
 cudaError_t fri_coin_step(int hash_id, u64* state, const u64* root, int d, u64* alpha_out, u64* log_entry, cudaStream_t st) {
     if (hash_id == WF_HASH_BLAKE3_256) fri_coin_kernel<WF_HASH_BLAKE3_256><<<1, 32, 0, st>>>(state, root, d, alpha_out, log_entry);
-    else fri_coin_kernel<WF_HASH_RP64_256><<<1, 32, 0, st>>>(state, root, d, alpha_out, log_entry);
+    else if (hash_id == WF_HASH_RP64_256) fri_coin_kernel<WF_HASH_RP64_256><<<1, 32, 0, st>>>(state, root, d, alpha_out, log_entry);
+    else fri_coin_kernel<WF_HASH_RPJIVE64_256><<<1, 32, 0, st>>>(state, root, d, alpha_out, log_entry);
     return cudaGetLastError();
 }

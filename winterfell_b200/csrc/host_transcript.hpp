@@ -13,6 +13,7 @@
 #include "blake3.cuh"
 #include "commit.cuh"
 #include "rp64.cuh"
+#include "rpjive.cuh"
 
 struct Digest {
     u8 b[32];
@@ -24,7 +25,8 @@ static inline Digest hh_hash_elements(int hash_id, const u64* e, size_t n) {
         b3_host_hash(reinterpret_cast<const u8*>(e), n * 8, d.b);  // canonical LE bytes (x86 host is LE)
     } else {
         u64 o[4];
-        rp64_host_hash_elements(e, n, o);
+        if (hash_id == WF_HASH_RP64_256) rp64_host_hash_elements(e, n, o);
+        else rpj_host_hash_elements(e, n, o);
         memcpy(d.b, o, 32);
     }
     return d;
@@ -40,7 +42,8 @@ static inline Digest hh_merge(int hash_id, const Digest& a, const Digest& b) {
         u64 in[8], o[4];
         memcpy(in, a.b, 32);
         memcpy(in + 4, b.b, 32);
-        rp64_merge(in, o);
+        if (hash_id == WF_HASH_RP64_256) rp64_merge(in, o);
+        else rpj_merge(in, o);
         memcpy(d.b, o, 32);
     }
     return d;
@@ -55,7 +58,8 @@ static inline Digest hh_merge_with_int(int hash_id, const Digest& seed, u64 valu
     } else {
         u64 s[4], o[4];
         memcpy(s, seed.b, 32);
-        rp64_host_merge_with_int(s, value, o);
+        if (hash_id == WF_HASH_RP64_256) rp64_host_merge_with_int(s, value, o);
+        else rpj_merge_with_int(s, value, o);
         memcpy(d.b, o, 32);
     }
     return d;

@@ -6,6 +6,7 @@
 #include <map>
 #include <set>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "../../include/winterfell_b200.h"
@@ -100,6 +101,9 @@ int wf_dev_alloc(wf_ctx* ctx, size_t bytes, void** out);
 void wf_dev_free(wf_ctx* ctx, void* p);
 int wf_mat_alloc(wf_ctx* ctx, size_t rows, u32 cols, wf_mat** out);
 int wf_mat_alloc_w(wf_ctx* ctx, size_t rows, u32 cols, int W, wf_mat** out);
+extern "C" int wf_trace_lde_cosetwise(wf_ctx* ctx, const uint64_t* const* cols, const uint64_t* d_cols, uint32_t ncols, size_t nrows, int mont,
+                           uint32_t log_blowup, wf_mat** polys_out, wf_mat** lde_out, bool coset_major,
+                           const std::function<int(u32)>* after_coset);
 extern "C" int wf_mat_lde_cosets(wf_ctx* ctx, const wf_mat* polys, uint32_t log_blowup, uint32_t k0, uint32_t k1, wf_mat* lde);  // internal (not in the public header)
 struct PublicCoin;
 struct Digest;

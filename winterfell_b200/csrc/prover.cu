@@ -29,7 +29,7 @@
 
 #include "internal.hpp"
 #include "blake3.cuh"
-#include "rp64.cuh"
+#include "alg_hash.cuh"
 
 // =================================================================================================
 // kernels
@@ -576,15 +576,12 @@ __global__ void __launch_bounds__(256) grind_kernel(int hash_id, const u64* seed
         b3_compress(cv, m, 0, 40, B3_CHUNK_START | B3_CHUNK_END | B3_ROOT, b3_runtime_one());  // blake/mod.rs:41-46
         head = (u64)cv[0] | ((u64)cv[1] << 32);
     } else {
-        u64 s[12];  // rp64_256/mod.rs:198-218
+        u64 sd[4], o[4];
 #pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) s[4 + i] = seed[i];
-        if (nonce < GL_P) { s[8] = nonce; s[0] = 5; }
-        else { s[8] = nonce - GL_P; s[9] = 1; s[0] = 6; }
-        rp64_permute(s);
-        head = s[4];
+        for (int i = 0; i < 4; i++) sd[i] = seed[i];
+        if (hash_id == WF_HASH_RP64_256) alg_merge_with_int<WF_HASH_RP64_256>(sd, nonce, o);       // rp64_256/mod.rs:198-218
+        else alg_merge_with_int<WF_HASH_RPJIVE64_256>(sd, nonce, o);                                // rp64_256_jive/mod.rs:206-229
+        head = o[0];
     }
     u64 mask = grinding >= 64 ? ~0ULL : ((1ULL << grinding) - 1);
     if ((head & mask) == 0) atomicMin(result, (unsigned long long)nonce);
@@ -1166,7 +1163,24 @@ int composition_polys(wf_ctx* ctx, const wf_mat* comp, u32 log_n, int D, u32 kc,
     const size_t n = (size_t)1 << log_n;
     if (comp->m.rows < n * kc || (int)comp->m.cols != D) return wf_fail(ctx, WF_ERR_INVALID, "composition trace shape");
     wf_mat *ccoefs, *cpolys;
-    CKI(wf_mat_interpolate_with_offset(ctx, comp, GL_GENERATOR, &ccoefs));
+    // The composition polynomial has degree < kc * n by the AIR's declared degrees (that is what kc is computed from), so the
+    // evaluations on the sub-coset 7 <w_m>, m = the power of two >= kc * n — every (ce / m)-th row of the CE domain — already
+    // determine it: the size-m inverse transform returns exactly the coefficients the reference reads out of its size-ce one
+    // (whose upper ce - kc * n coefficients are zero, composition_poly.rs:64-70). For FibSmall m = ce / 2.
+    size_t m = n;
+    while (m < n * kc) m <<= 1;
+    if (m < comp->m.rows && comp->m.nseg() == 1) {
+        wf_mat* sub;
+        CKI(wf_mat_alloc_w(ctx, m, comp->m.cols, comp->m.W, &sub));
+        const size_t rb = (size_t)comp->m.W * 8, stride = comp->m.rows / m;
+        cudaError_t e = cudaMemcpy2DAsync(sub->m.base, rb, comp->m.base, stride * rb, rb, m, cudaMemcpyDeviceToDevice, ctx->st);
+        int rc = e == cudaSuccess ? wf_mat_interpolate_with_offset(ctx, sub, GL_GENERATOR, &ccoefs)
+                                  : wf_fail(ctx, WF_ERR_CUDA, "composition sub-coset copy: %s", cudaGetErrorString(e));
+        wf_mat_free(ctx, sub);
+        if (rc != WF_OK) return rc;
+    } else {
+        CKI(wf_mat_interpolate_with_offset(ctx, comp, GL_GENERATOR, &ccoefs));
+    }
     CKI(wf_mat_alloc(ctx, n, kc * D, &cpolys));
     if (cpolys->m.W > (int)(kc * D)) CK(cudaMemsetAsync(cpolys->m.base, 0, cpolys->m.words() * 8, ctx->st));
     comp_split_kernel<<<(unsigned)((n * kc * D + 255) / 256), 256, 0, ctx->st>>>(ccoefs->m, n, kc, D, cpolys->m);
@@ -1453,21 +1467,34 @@ struct ShardCtx {
     const wf_comm* cm;
     int G, r;
     u32 logG;
-    double bytes_sent = 0, ncoll = 0, ms_small = 0;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;  // around every exchange, on the ctx stream
+    double bytes_sent = 0, bytes_overlapped = 0, ncoll = 0, ms_small = 0;
+    bool forked = false;
+    // exchanges issued between fork() and join() run on the communicator's stream, behind the ctx stream's tail at fork time
+    // (wf_comm::fork / join; without the callbacks they simply stay on the ctx stream)
+    int fork() {
+        if (cm->fork) { if (cm->fork(cm->user) != 0) return wf_fail(ctx, WF_ERR_STATE, "fork callback failed"); forked = true; }
+        return WF_OK;
+    }
+    int join() {
+        if (forked) { forked = false; if (cm->join(cm->user) != 0) return wf_fail(ctx, WF_ERR_STATE, "join callback failed"); }
+        return WF_OK;
+    }
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;  // around every exchange on the ctx stream (not the overlapped ones)
     ~ShardCtx() { for (auto& e : ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } }
     // send[i] -> rank sp[i], recv[i] <- rank rp[i], all `bytes` long; entries naming this rank are not allowed
     int exchange(const std::vector<int>& sp, const std::vector<const void*>& sv, const std::vector<int>& rp, const std::vector<void*>& rv,
                  size_t bytes) {
-        cudaEvent_t a, b;
-        CK(cudaEventCreate(&a));
-        CK(cudaEventCreate(&b));
-        ev.push_back({a, b});
-        CK(cudaEventRecord(a, ctx->st));
+        cudaEvent_t a = nullptr, b = nullptr;
+        if (!forked) {
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            ev.push_back({a, b});
+            CK(cudaEventRecord(a, ctx->st));
+        }
         if (cm->exchange(cm->user, sp.size(), sp.data(), sv.data(), rp.size(), rp.data(), rv.data(), bytes) != 0)
             return wf_fail(ctx, WF_ERR_STATE, "exchange callback failed");
-        CK(cudaEventRecord(b, ctx->st));
-        bytes_sent += (double)bytes * (double)sp.size();
+        if (!forked) CK(cudaEventRecord(b, ctx->st));
+        (forked ? bytes_overlapped : bytes_sent) += (double)bytes * (double)sp.size();
         ncoll += 1;
         return WF_OK;
     }
@@ -1564,35 +1591,46 @@ int prove_fib_sharded(wf_ctx* ctx, const wf_comm* cm, const uint64_t* const* loc
         ~Cleanup() { for (auto& l : sl) wf_tree_free(ctx, l.tree.local); for (void* p : ow) wf_dev_free(ctx, p); }
     } cleanup{ctx, slayers, owned};
 
-    // ---- 1. interpolate + extend the local columns (no communication: columns are independent) ----
+    // ---- 1. interpolate the local columns, then extend them coset by coset (no communication: columns are independent).
+    //         Coset k is written coset-major, so that the rows of rank q's range (n / G points of the coset) are one contiguous
+    //         block per segment: its exchange runs on the communicator's stream while coset k + 1 is being extended ----
     wf_mark(ctx, "start");
-    if (d_local) {
-        CKI(wf_mat_from_device_columns(ctx, d_local, cl, n, &trace));
-        CKI(wf_mat_interpolate(ctx, trace, &polys));
-        scope.drop(trace);
-        CKI(wf_mat_lde(ctx, polys, log_b, &lde));
-    } else {
-        CKI(wf_trace_lde_from_host(ctx, local_cols, cl, n, mont, log_b, &polys, &lde));
-    }
-    wf_mark(ctx, "trace_lde");
-    // ---- 2. column shards -> row shards: rank q receives rows [q N/G, (q+1) N/G) of every segment; the shard keeps
-    //         `blowup` extra rows per segment for the next-state halo ----
+    const size_t nj = n / (size_t)G;   // points of one coset inside one rank's row range
+    wf_mat* stage = nullptr;           // what arrives: [global segment][coset][nj][8]
+    scope.own({&stage});
+    CKI(wf_mat_alloc_w(ctx, N, cl, 8, &lde));          // mine, coset-major: [local segment][coset][n][8]
+    CKI(wf_mat_alloc_w(ctx, rows_per, c, 8, &stage));
     CKI(wf_mat_alloc(ctx, rows_per + b, c, &shard));
     shard->m.rows = rows_per;  // seg_stride stays (rows_per + b) * 8: rows [rows_per, rows_per + b) are the halo
     const size_t sstride = shard->m.seg_stride;
-    {
+    const std::function<int(u32)> after_coset = [&](u32 k) -> int {   // coset k of every local column is enqueued: ship it
         std::vector<int> sp, rp;
         std::vector<const void*> sv;
         std::vector<void*> rv;
-        for (u32 s = 0; s < nsl; s++)
+        for (u32 sg = 0; sg < nsl; sg++)
             for (int q = 0; q < G; q++) {
-                const u64* src = lde->m.base + (size_t)s * lde->m.seg_stride + (size_t)q * rows_per * 8;
-                if (q == r) CK(cudaMemcpyAsync(shard->m.base + ((size_t)r * nsl + s) * sstride, src, rows_per * 64, cudaMemcpyDeviceToDevice, ctx->st));
-                else { sp.push_back(q); sv.push_back(src); rp.push_back(q); rv.push_back(shard->m.base + ((size_t)q * nsl + s) * sstride); }
+                const u64* src = lde->m.base + (size_t)sg * lde->m.seg_stride + ((size_t)k * n + (size_t)q * nj) * 8;
+                u64* dst = stage->m.base + ((size_t)q * nsl + sg) * stage->m.seg_stride + (size_t)k * nj * 8;   // q = the SOURCE rank here
+                if (q == r) CK(cudaMemcpyAsync(dst, src, nj * 64, cudaMemcpyDeviceToDevice, ctx->st));
+                else { sp.push_back(q); sv.push_back(src); rp.push_back(q); rv.push_back(dst); }
             }
-        CKI(sc.exchange(sp, sv, rp, rv, rows_per * 64));
+        CKI(sc.fork());
+        return sc.exchange(sp, sv, rp, rv, nj * 64);
+    };
+    // (upload ->) layout -> interpolate -> extend, pipelined per column chunk for host columns; the cosets of the last chunk
+    // are extended one by one and after_coset(k) ships coset k while coset k + 1 is computed
+    CKI(wf_trace_lde_cosetwise(ctx, local_cols, d_local, cl, n, mont, log_b, &polys, &lde, true, &after_coset));
+    wf_mark(ctx, "trace_lde");
+    CKI(sc.join());
+    {   // coset-major -> natural order (row = b j + k) of my row range, every segment
+        SegMatrix dstv = shard->m;
+        dim3 grid((unsigned)((rows_per * 8 + 255) / 256), nsg);
+        coset_interleave_kernel<<<grid, 256, 0, ctx->st>>>(stage->m, dstv, nj, (u32)b);
+        ctx->launches++;
+        CK(cudaGetLastError());
     }
     scope.drop(lde);
+    scope.drop(stage);
     {   // halo: the first `blowup` rows of every segment of rank (r + 1) mod G
         void *pk, *pk2;
         const size_t hb = b * 64;
@@ -1902,6 +1940,7 @@ int prove_fib_sharded(wf_ctx* ctx, const wf_comm* cm, const uint64_t* const* loc
         stats[0] = sc.bytes_sent; stats[1] = sc.exchange_ms(); stats[2] = sc.ncoll + 1; stats[3] = sc.ms_small;
         for (int i = 4; i < 8; i++) stats[i] = 0;
         stats[4] = (double)slayers.size();
+        stats[5] = sc.bytes_overlapped;
     }
     return WF_OK;
 }
@@ -1928,7 +1967,7 @@ static int parse_options(wf_ctx* ctx, const uint32_t* opts, Options& o) {
         o.batch_d > 2 || o.grinding > 32 || o.rem_max_deg > 255 || ((o.rem_max_deg + 1) & o.rem_max_deg) ||
         (o.folding != 2 && o.folding != 4 && o.folding != 8 && o.folding != 16) || o.ext < 1 || o.ext > 3)
         return wf_fail(ctx, WF_ERR_INVALID, "bad proof options");  // ProofOptions::new asserts (air/src/options.rs:132-190)
-    if (o.hash_id != WF_HASH_BLAKE3_256 && o.hash_id != WF_HASH_RP64_256) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "unknown hash %d", o.hash_id);
+    if (!WF_HASH_IS_KNOWN(o.hash_id)) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "unknown hash %d", o.hash_id);
     return WF_OK;
 }
 static int prove_dispatch(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont,
