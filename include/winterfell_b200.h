@@ -207,6 +207,16 @@ int wf_prove_air_aux(wf_ctx* ctx, const uint64_t* air_desc, size_t air_desc_len,
                      uint32_t log_n, const uint32_t* opts, wf_aux_builder_fn aux_builder, void* aux_user, uint8_t* proof,
                      size_t* proof_len);
 
+/* Same, for AIRs whose auxiliary assertions depend on the random elements (Air::get_aux_assertions(&self, aux_rand_elements),
+ * air/src/air/mod.rs:279): after the random elements are drawn — and after aux_builder has run — `aux_assertions` is called
+ * on the HOST with the same rand_elements and with `values` = [sum of nvals over the aux assertions][d] words in description
+ * order, preloaded with the description's values; what it leaves there is asserted (positions, strides and counts stay the
+ * description's). Representation selected by `mont`; returns 0 on success. A verifier must apply the same function. */
+typedef int (*wf_aux_assertions_fn)(void* user, const uint64_t* rand_elements, uint64_t* values);
+int wf_prove_air_aux_dyn(wf_ctx* ctx, const uint64_t* air_desc, size_t air_desc_len, const uint64_t* const* trace_cols, int mont,
+                         uint32_t log_n, const uint32_t* opts, wf_aux_builder_fn aux_builder, wf_aux_assertions_fn aux_assertions,
+                         void* aux_user, uint8_t* proof, size_t* proof_len);
+
 /* same, trace already on the device: column-major [2k][2^log_n], canonical words */
 int wf_prove_fib_dev(wf_ctx* ctx, const uint64_t* d_trace, uint32_t k, uint32_t log_n, const uint64_t* results,
                      const uint32_t* opts, uint8_t* proof, size_t* proof_len);

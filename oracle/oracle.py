@@ -424,6 +424,44 @@ def prove_air_aux(desc, trace, opts, builder, aw, nr):
     return out[:ln].tobytes()
 
 
+def values_callback(values_fn, nr, nvals, d):
+    """Wraps values_fn(rand [nr, d], values [nvals, d]) -> values as the get_aux_assertions callback of both provers / the verifier."""
+    def cb(_user, rand_p, val_p):
+        try:
+            rand = np.ctypeslib.as_array(rand_p, shape=(nr, d)).copy()
+            vals = np.ctypeslib.as_array(val_p, shape=(nvals, d))
+            vals[:] = np.ascontiguousarray(values_fn(rand, vals.copy()), dtype=np.uint64).reshape(nvals, d)
+            return 0
+        except Exception:
+            import traceback
+            traceback.print_exc()
+            return 1
+    return AUX_BUILDER(cb)
+
+
+def prove_air_aux_dyn(desc, trace, opts, builder, values_fn, aw, nr, nvals):
+    d_, dp = _u64(desc)
+    t_, tp = _u64(trace)
+    cap = 1 << 23
+    out = np.zeros(cap, dtype=np.uint8)
+    L = lib()
+    L.wfo_prove_air_aux_dyn.restype = C.c_long
+    d = int(opts[3])
+    cb, cv = aux_callback(builder, aw, nr, t_.shape[1], d), values_callback(values_fn, nr, nvals, d)
+    ln = L.wfo_prove_air_aux_dyn(dp, C.c_size_t(d_.size), tp, C.c_size_t(t_.shape[1]), opts.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                 cb, cv, None, out.ctypes.data_as(u8p), C.c_size_t(cap))
+    if ln < 0:
+        raise RuntimeError(f"prove_air_aux_dyn failed ({ln})")
+    return out[:ln].tobytes()
+
+
+def verify_air_dyn(desc, proof: bytes, hash_id, values_fn, nr, nvals, d):
+    d_, dp = _u64(desc)
+    p_, pp = _u8(np.frombuffer(proof, dtype=np.uint8))
+    cv = values_callback(values_fn, nr, nvals, d)
+    return lib().wfo_verify_air_dyn(dp, C.c_size_t(d_.size), pp, C.c_size_t(len(proof)), C.c_int(hash_id), cv, None)
+
+
 def perm_rap_aux(trace, rand):
     """Aux columns [3, n, d] of tests/airs.py perm_rap for the drawn random elements rand [2, d]."""
     t_, tp = _u64(trace)

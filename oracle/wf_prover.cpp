@@ -95,6 +95,12 @@ struct Air {
     std::vector<Instr> aux_prog;
     u32 aux_num_regs = 0;
     std::vector<AuxAssertion> aux_asserts;
+    // Air::get_aux_assertions(&self, aux_rand_elements) (air/src/air/mod.rs:279): when set, the VALUES of the aux assertions
+    // are recomputed from the drawn random elements (prover: after the main commitment; verifier: same point of the
+    // transcript). rand = [nr][d] words, values = [sum of nvals][d] words in description order (in: the description's
+    // placeholders, out: the values to assert). Returns 0 on success.
+    int (*aux_values_fn)(void*, const u64*, u64*) = nullptr;
+    void* aux_values_user = nullptr;
     size_t width() const { return w; }
     size_t num_main_transition() const { return degrees.size(); }
     size_t num_transition() const { return degrees.size() + aux_degrees.size(); }  // context.rs:205-207
@@ -446,8 +452,28 @@ struct StageTimer {
     void mark(const char* name) { if (!on) return; double t = omp_get_wtime(); fprintf(stderr, "[oracle] %-26s %9.3f ms\n", name, (t - t0) * 1e3); t0 = t; }
 };
 
-static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[w][n]*/, AuxBuilder aux_builder = nullptr,
+static bool apply_aux_values(Air& air, const std::vector<EE>& rnd, int d) {
+    if (!air.aux_values_fn) return true;
+    size_t total = 0;
+    for (auto& a : air.aux_asserts) total += a.values.size();
+    std::vector<u64> rw(air.nr * d), vals(total * d);
+    for (size_t i = 0; i < air.nr; i++) for (int k = 0; k < d; k++) rw[i * d + k] = rnd[i].v[k];
+    size_t q = 0;
+    for (auto& a : air.aux_asserts) for (auto& v : a.values) { for (int k = 0; k < d; k++) vals[q * d + k] = v.v[k]; q++; }
+    if (air.aux_values_fn(air.aux_values_user, rw.data(), vals.data())) return false;
+    q = 0;
+    for (auto& a : air.aux_asserts)
+        for (auto& v : a.values) {
+            for (int k = 0; k < 3; k++) v.v[k] = k < d ? vals[q * d + k] : 0;
+            for (int k = 0; k < d; k++) if (v.v[k] >= P) return false;
+            q++;
+        }
+    return true;
+}
+
+static std::vector<u8> prove_fib(const FibAir& air_in, const u64* trace /*[w][n]*/, AuxBuilder aux_builder = nullptr,
                                   void* aux_user = nullptr) {
+    FibAir air = air_in;  // the aux assertion values may be rewritten from the random elements (get_aux_assertions)
     StageTimer tm;
     const Opts& o = air.o;
     const int h = o.hash_id;
@@ -481,6 +507,7 @@ static std::vector<u8> prove_fib(const FibAir& air, const u64* trace /*[w][n]*/,
         for (size_t i = 0; i < air.nr; i++) for (int k = 0; k < d; k++) rw[i * d + k] = rnd[i].v[k];
         apolys.assign(aw * n * d, 0);
         if (!aux_builder || aux_builder(aux_user, rw.data(), apolys.data())) abort();
+        if (!apply_aux_values(air, rnd, d)) abort();
         interpolate_columns(apolys.data(), aw, n, d);
         alde.resize(N * aw * d);
         lde_rows(apolys.data(), aw, n, d, b, alde.data());
@@ -942,6 +969,7 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
     if (air.aw) {  // verifier/src/lib.rs:170-184
         for (size_t i = 0; i < air.nr; i++) rnd.push_back(coin.draw(F));
         coin.reseed(aux_root);
+        if (!apply_aux_values(air, rnd, F.d)) return V_MALFORMED;   // Air::get_aux_assertions(aux_rand_elements)
     }
     std::vector<EE> ccoef = coin.draw_coeffs(F, (int)o.batch_c, air.num_transition() + air.num_assertions());
     coin.reseed(cons_root);
@@ -1170,6 +1198,28 @@ long wfo_prove_air_aux(const uint64_t* desc, size_t desc_len, const uint64_t* tr
     if (p.size() > cap) return -1;
     memcpy(out, p.data(), p.size());
     return (long)p.size();
+}
+// same with Air::get_aux_assertions as a callback on the random elements (prover and verifier must be given the same one)
+long wfo_prove_air_aux_dyn(const uint64_t* desc, size_t desc_len, const uint64_t* trace, size_t n, const uint32_t* opts,
+                           int (*builder)(void*, const uint64_t*, uint64_t*), int (*values_fn)(void*, const uint64_t*, uint64_t*),
+                           void* user, uint8_t* out, size_t cap) {
+    Air air;
+    if (!parse_air(desc, desc_len, air)) return -2;
+    air.n = n; air.o = make_opts(opts);
+    air.aux_values_fn = values_fn; air.aux_values_user = user;
+    std::vector<u8> p = prove_fib(air, trace, builder, user);
+    if (p.size() > cap) return -1;
+    memcpy(out, p.data(), p.size());
+    return (long)p.size();
+}
+int wfo_verify_air_dyn(const uint64_t* desc, size_t desc_len, const uint8_t* proof, size_t len, int hash_id,
+                       int (*values_fn)(void*, const uint64_t*, uint64_t*), void* user) {
+    Air air;
+    if (!parse_air(desc, desc_len, air)) return -2;
+    memset(&air.o, 0, sizeof(air.o));
+    air.o.hash_id = hash_id;
+    air.aux_values_fn = values_fn; air.aux_values_user = user;
+    return verify_fib(proof, len, air);
 }
 int wfo_verify_air(const uint64_t* desc, size_t desc_len, const uint8_t* proof, size_t len, int hash_id) {
     Air air;

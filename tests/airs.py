@@ -216,7 +216,7 @@ def periodic_mix(n, cycle=8):
 PERM_RAP_AUX_WIDTH = 3
 
 
-def perm_rap(n, seed=5):
+def perm_rap(n, seed=5, dyn_last_q=False):
     """Two-segment AIR in the style of examples/src/rescue_raps (a randomised AIR with preprocessing):
     main columns x0, x1 (the FibSmall pair) and b = a permutation of x0's first n-1 values; the aux
     segment proves the permutation with a running product and carries a running sum that mixes main
@@ -224,7 +224,10 @@ def perm_rap(n, seed=5):
         p' * (b + gamma) = p * (x0 + gamma),   p[0] = p[n-1] = 1
         q' = q + alpha * k * x1 * p,           q[0] = 0
         c' = c + 1,                            c[1 + i n/4] asserted as a SEQUENCE (values in E)
-    Returns (description, main trace, aux builder(rand [2, d]) -> [2, n, d])."""
+    Returns (description, main trace, aux builder(rand [2, d]) -> [2, n, d]).
+    dyn_last_q: also assert q[n-1], whose value depends on the random elements (Air::get_aux_assertions(aux_rand_elements),
+    air/src/air/mod.rs:279): the description carries a placeholder and `builder.values_fn(rand, values)` fills it in
+    (values: [builder.num_values, d], description order); for wf_prove_air_aux_dyn / the oracle's *_dyn entry points."""
     from oracle import oracle as O
     rng = np.random.default_rng(seed)
     tr = np.zeros((3, n), dtype=np.uint64)
@@ -255,6 +258,8 @@ def perm_rap(n, seed=5):
     X.assert_single(0, 0, (1, 0, 0))
     X.assert_single(0, n - 1, (1, 0, 0))
     X.assert_single(1, 0, (0, 0, 0))
+    if dyn_last_q:
+        X.assert_single(1, n - 1, (0, 0, 0))   # placeholder: the running sum's last value is a function of gamma and alpha
     one = X.const(1)
     X.constraint(X.sub(X.anxt(2), X.add(X.acur(2), one)), 1)
     X.assert_sequence(2, 1, n // 4, [(5 + 1 + k * (n // 4), 0, 0) for k in range(4)])
@@ -275,7 +280,14 @@ def perm_rap(n, seed=5):
     def builder(rand):  # the same columns from the C helper (oracle/wf_prover.cpp wfo_perm_rap_aux)
         return O.perm_rap_aux(tr, rand)
 
+    def values_fn(rand, values):  # get_aux_assertions: values in description order [p0, p_last, q0, q_last, 4 sequence values]
+        out = values.copy()
+        out[3] = builder(rand)[1, n - 1]
+        return out
+
     builder.reference = builder_py
+    builder.values_fn = values_fn
+    builder.num_values = 8 if dyn_last_q else 7
     return A.build(), tr, builder
 
 

@@ -274,3 +274,25 @@ def test_too_many_partitions_refused(ctx, oracle):
     opts = oracle.make_opts(num_partitions=17, hash_rate=8)   # PartitionOptions::new asserts <= 16 (air/src/options.rs:413-414)
     with pytest.raises(wf.WfError):
         ctx.prove_fib(trace, results, opts)
+
+
+@pytest.mark.parametrize("ext,h,mont", [(1, wf.HASH_BLAKE3_256, False), (3, wf.HASH_BLAKE3_256, False), (2, wf.HASH_RP64_256, True)])
+def test_aux_assertions_depending_on_random_elements(ctx, oracle, ext, h, mont):
+    # wf_prove_air_aux_dyn: Air::get_aux_assertions(aux_rand_elements) (air/src/air/mod.rs:279) as a host callback on the drawn
+    # random elements; bytes equal to the oracle's prover given the same callback, accepted by the oracle's verifier with it
+    n = 1 << 8
+    desc, trace, builder = airs.perm_rap(n, dyn_last_q=True)
+    opts = oracle.make_opts(num_queries=20, grinding=2, ext=ext, folding=4, rem_max_deg=7, hash_id=h)
+    nv = builder.num_values
+    want = oracle.prove_air_aux_dyn(desc, trace, opts, builder, builder.values_fn, airs.PERM_RAP_AUX_WIDTH, 2, nv)
+    if mont:   # every word crossing the ABI (trace, random elements, aux columns, assertion values) in Montgomery form
+        to_m = np.vectorize(lambda v: oracle.to_mont(int(v)), otypes=[np.uint64])
+        from_m = np.vectorize(lambda v: int(v) * pow(2**64, -1, wf.P) % wf.P, otypes=[np.uint64])
+        b = lambda rand: to_m(builder(from_m(rand)))
+        vf = lambda rand, values: to_m(builder.values_fn(from_m(rand), from_m(values)))
+        got = ctx.prove_air_aux_dyn(desc, to_m(trace), opts, b, vf, airs.PERM_RAP_AUX_WIDTH, 2, nv, mont=True)
+    else:
+        got = ctx.prove_air_aux_dyn(desc, trace, opts, builder, builder.values_fn, airs.PERM_RAP_AUX_WIDTH, 2, nv)
+    assert got == want
+    assert oracle.verify_air_dyn(desc, got, h, builder.values_fn, 2, nv, ext) == 0
+    assert oracle.verify_air(desc, got, h) != 0      # the description's placeholder is not the asserted value

@@ -144,3 +144,20 @@ def test_partitioned_commitments_round_trip(oracle, k, ext, h, parts, rate):
     t = bytearray(proof)
     t[i], t[i + 1] = 1, 1
     assert oracle.verify_fib(bytes(t), k, res, h) != 0
+
+
+@pytest.mark.parametrize("ext", [1, 3])
+def test_aux_assertions_depending_on_random_elements(oracle, ext):
+    # Air::get_aux_assertions receives the AuxRandElements (air/src/air/mod.rs:279): an assertion value that is a function of
+    # the drawn elements is supplied by a callback at the same transcript point in the prover and in the verifier
+    n = 64
+    desc, trace, builder = airs.perm_rap(n, dyn_last_q=True)
+    opts = oracle.make_opts(num_queries=16, grinding=2, ext=ext, folding=4, rem_max_deg=7)
+    nv = builder.num_values
+    proof = oracle.prove_air_aux_dyn(desc, trace, opts, builder, builder.values_fn, airs.PERM_RAP_AUX_WIDTH, 2, nv)
+    assert oracle.verify_air_dyn(desc, proof, 0, builder.values_fn, 2, nv, ext) == 0
+    # the placeholder value of the description (0) is not what the trace satisfies: a verifier without the callback rejects,
+    # and so does one whose callback computes a different value
+    assert oracle.verify_air(desc, proof, 0) != 0
+    wrong = lambda rand, values: np.where(np.arange(nv)[:, None] == 3, values + np.uint64(1), builder.values_fn(rand, values))
+    assert oracle.verify_air_dyn(desc, proof, 0, wrong, 2, nv, ext) != 0

@@ -74,6 +74,8 @@ _SIGS = [
     ("wf_prove_air", C.c_int, [vp, u64p, C.c_size_t, C.POINTER(u64p), C.c_int, C.c_uint32, C.POINTER(C.c_uint32), u8p, C.POINTER(C.c_size_t)]),
     ("wf_prove_air_aux", C.c_int, [vp, u64p, C.c_size_t, C.POINTER(u64p), C.c_int, C.c_uint32, C.POINTER(C.c_uint32), AUX_BUILDER, vp,
                                    u8p, C.POINTER(C.c_size_t)]),
+        ("wf_prove_air_aux_dyn", C.c_int, [vp, u64p, C.c_size_t, C.POINTER(u64p), C.c_int, C.c_uint32, C.POINTER(C.c_uint32), AUX_BUILDER, AUX_BUILDER, vp,
+                                   u8p, C.POINTER(C.c_size_t)]),
     ("wf_eval_constraints", C.c_int, [vp, u64p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, u64p, u64p, C.POINTER(vp)]),
     ("wf_composition_commit", C.c_int, [vp, C.c_int, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
     ("wf_composition_commit_partitioned", C.c_int, [vp, C.c_int, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp),
@@ -321,6 +323,44 @@ class Context:
         self.check(self.L.wf_prove_air_aux(self.h, dp, d_.size, ptrs, int(mont), int(n).bit_length() - 1,
                                            o_.ctypes.data_as(C.POINTER(C.c_uint32)), cfn, None, buf.ctypes.data_as(u8p),
                                            C.byref(ln)))
+        return buf[: ln.value].tobytes()
+
+    def prove_air_aux_dyn(self, desc, trace, opts, builder, values_fn, aux_width, num_rands, num_values, mont=False):
+        """wf_prove_air_aux_dyn: as prove_air_aux, plus values_fn(rand [num_rands, d], values [num_values, d]) -> values
+        [num_values, d] = Air::get_aux_assertions(aux_rand_elements) (air/src/air/mod.rs:279)."""
+        d_, dp = _u64(desc)
+        a = np.ascontiguousarray(trace, dtype=np.uint64)
+        c, n = a.shape
+        ptrs = (u64p * c)(*[a[j].ctypes.data_as(u64p) for j in range(c)])
+        o_ = np.ascontiguousarray(opts, dtype=np.uint32)
+        d = int(o_[3])
+
+        def guard(fn):
+            def wrapped(*args):
+                try:
+                    fn(*args)
+                    return 0
+                except Exception:  # must not unwind through the C caller
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            return wrapped
+
+        def cb_build(_user, rand_p, out_p):
+            rand = np.ctypeslib.as_array(rand_p, shape=(num_rands, d)).copy()
+            np.ctypeslib.as_array(out_p, shape=(aux_width, n, d))[:] = np.ascontiguousarray(builder(rand), dtype=np.uint64).reshape(aux_width, n, d)
+
+        def cb_values(_user, rand_p, val_p):
+            rand = np.ctypeslib.as_array(rand_p, shape=(num_rands, d)).copy()
+            vals = np.ctypeslib.as_array(val_p, shape=(num_values, d))
+            vals[:] = np.ascontiguousarray(values_fn(rand, vals.copy()), dtype=np.uint64).reshape(num_values, d)
+
+        f1, f2 = AUX_BUILDER(guard(cb_build)), AUX_BUILDER(guard(cb_values))
+        cap = 1 << 23
+        buf = np.zeros(cap, dtype=np.uint8)
+        ln = C.c_size_t(cap)
+        self.check(self.L.wf_prove_air_aux_dyn(self.h, dp, d_.size, ptrs, int(mont), int(n).bit_length() - 1,
+                                               o_.ctypes.data_as(C.POINTER(C.c_uint32)), f1, f2, None, buf.ctypes.data_as(u8p), C.byref(ln)))
         return buf[: ln.value].tobytes()
 
     def prove_fib_dev(self, d_trace, k, log_n, results, opts, out_buf=None):

@@ -1257,8 +1257,12 @@ struct ProofScope {
 };
 
 template <int D>
-int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont, u32 log_n,
-              const Options& o, wf_aux_builder_fn aux_builder, void* aux_user, std::vector<u8>& proof_out) {
+int prove_air(wf_ctx* ctx, const AirHost& air_in, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont, u32 log_n,
+              const Options& o, wf_aux_builder_fn aux_builder, void* aux_user, std::vector<u8>& proof_out,
+              wf_aux_assertions_fn aux_assertions = nullptr) {
+    AirHost air_dyn;                       // copy whose aux assertion values are rewritten from the random elements
+    if (aux_assertions) air_dyn = air_in;  // (Air::get_aux_assertions(aux_rand_elements), air/src/air/mod.rs:279)
+    const AirHost& air = aux_assertions ? air_dyn : air_in;
     const int h = o.hash_id;
     const size_t n = (size_t)1 << log_n;
     u32 log_b = 0;
@@ -1320,6 +1324,25 @@ int prove_air(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols
         if (mont) for (u64& v : rnd_user) v = gl_mul(v, 0xFFFFFFFFULL);  // x * R, R = 2^64 mod p
         std::vector<u64> aux_host((size_t)aw * n * D);  // [aw][n][D]: ColMatrix<E>, one Vec<E> per column
         if (aux_builder(aux_user, rnd_user.data(), aux_host.data()) != 0) return wf_fail(ctx, WF_ERR_INVALID, "aux trace builder failed");
+        if (aux_assertions) {
+            size_t total = 0;
+            for (auto& a : air_dyn.aux_asserts) total += a.values.size() / 3;
+            std::vector<u64> vals(total * D);
+            size_t q = 0;
+            for (auto& a : air_dyn.aux_asserts)
+                for (size_t i = 0; i < a.values.size() / 3; i++, q++)
+                    for (int k = 0; k < D; k++) vals[q * D + k] = mont ? gl_mul(a.values[i * 3 + k], 0xFFFFFFFFULL) : a.values[i * 3 + k];
+            if (aux_assertions(aux_user, rnd_user.data(), vals.data()) != 0) return wf_fail(ctx, WF_ERR_INVALID, "aux assertion callback failed");
+            q = 0;
+            for (auto& a : air_dyn.aux_asserts)
+                for (size_t i = 0; i < a.values.size() / 3; i++, q++)
+                    for (int k = 0; k < 3; k++) {
+                        u64 v = k < D ? vals[q * D + k] : 0;
+                        if (mont) v = gl_from_mont(v);
+                        else if (v >= GL_P) return wf_fail(ctx, WF_ERR_INVALID, "aux assertion value is not a canonical field element");
+                        a.values[i * 3 + k] = v;
+                    }
+        }
         // E column j -> D base columns j*D + q (rows of the LDE then serialise exactly like [E] rows)
         std::vector<const u64*> cols(aw);
         for (u32 j = 0; j < aw; j++) cols[j] = &aux_host[(size_t)j * n * D];
@@ -1972,13 +1995,13 @@ static int parse_options(wf_ctx* ctx, const uint32_t* opts, Options& o) {
 }
 static int prove_dispatch(wf_ctx* ctx, const AirHost& air, const uint64_t* const* trace_cols, const uint64_t* d_trace, int mont,
                           uint32_t log_n, const Options& o, uint8_t* proof, size_t* proof_len, wf_aux_builder_fn aux_builder = nullptr,
-                          void* aux_user = nullptr) {
+                          void* aux_user = nullptr, wf_aux_assertions_fn aux_assertions = nullptr) {
     std::vector<u8> out;
     int r;
     switch (o.ext) {
-        case 1: r = prove_air<1>(ctx, air, trace_cols, d_trace, mont, log_n, o, aux_builder, aux_user, out); break;
-        case 2: r = prove_air<2>(ctx, air, trace_cols, d_trace, mont, log_n, o, aux_builder, aux_user, out); break;
-        case 3: r = prove_air<3>(ctx, air, trace_cols, d_trace, mont, log_n, o, aux_builder, aux_user, out); break;
+        case 1: r = prove_air<1>(ctx, air, trace_cols, d_trace, mont, log_n, o, aux_builder, aux_user, out, aux_assertions); break;
+        case 2: r = prove_air<2>(ctx, air, trace_cols, d_trace, mont, log_n, o, aux_builder, aux_user, out, aux_assertions); break;
+        case 3: r = prove_air<3>(ctx, air, trace_cols, d_trace, mont, log_n, o, aux_builder, aux_user, out, aux_assertions); break;
         default: return wf_fail(ctx, WF_ERR_UNSUPPORTED, "field extension %u", o.ext);
     }
     if (r != WF_OK) return r;
@@ -2017,6 +2040,17 @@ extern "C" int wf_prove_air_aux(wf_ctx* ctx, const uint64_t* air_desc, size_t ai
     AirHost air;
     if (!parse_air_host(air_desc, air_desc_len, air)) return wf_fail(ctx, WF_ERR_INVALID, "malformed AIR description");
     return prove_dispatch(ctx, air, trace_cols, nullptr, mont, log_n, o, proof, proof_len, aux_builder, aux_user);
+}
+extern "C" int wf_prove_air_aux_dyn(wf_ctx* ctx, const uint64_t* air_desc, size_t air_desc_len, const uint64_t* const* trace_cols, int mont,
+                                    uint32_t log_n, const uint32_t* opts, wf_aux_builder_fn aux_builder,
+                                    wf_aux_assertions_fn aux_assertions, void* aux_user, uint8_t* proof, size_t* proof_len) {
+    if (!ctx || !air_desc || !trace_cols || !opts || !proof || !proof_len || log_n < 3 || !aux_assertions)
+        return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+    Options o;
+    CKI(parse_options(ctx, opts, o));
+    AirHost air;
+    if (!parse_air_host(air_desc, air_desc_len, air)) return wf_fail(ctx, WF_ERR_INVALID, "malformed AIR description");
+    return prove_dispatch(ctx, air, trace_cols, nullptr, mont, log_n, o, proof, proof_len, aux_builder, aux_user, aux_assertions);
 }
 
 // ---- stepwise exports: the seams of prover/src/lib.rs:125-223 (ConstraintEvaluator, ConstraintCommitment)
