@@ -294,10 +294,22 @@ typedef struct wf_comm {
  * `results` and `opts` are the full proof's; every rank returns the same proof bytes.
  * stats (optional, 8 doubles): [0] bytes this rank sent through exchanges ordered on the ctx stream, [1] ms inside those,
  * [2] number of collectives, [3] ms inside all_gather_host + all_reduce_sum, [4] FRI layers folded on shards, [5] bytes sent
- * through exchanges overlapped with compute (between fork and join: the trace LDE's cosets). */
+ * overlapped with compute (the trace LDE's cosets), [6] how those travelled: 2 = written by the last LDE pass itself into the
+ * owners' row shards mapped through CUDA IPC (stores over NVLink; the default when the driver allows it and world <= 8),
+ * 1 = peer copies (copy engines) into mapped staging buffers, 0 = comm->exchange between fork and join (WF_PEER_PUSH=0). */
 int wf_prove_fib_sharded(wf_ctx* ctx, const wf_comm* comm, const uint64_t* const* local_cols, const uint64_t* d_local, int mont,
                          uint32_t k, uint32_t log_n, const uint64_t* results, const uint32_t* opts, uint8_t* proof,
                          size_t* proof_len, double* stats);
+
+/* ---- constraint kernels compiled per AIR ---------------------------------------------------------------------------
+ * wf_eval_constraints / wf_prove_air[_aux] evaluate the AIR's transition programs with a kernel compiled at run time for that
+ * AIR (NVRTC: the programs become straight-line code, registers and constants are literals), cached in the context; without
+ * NVRTC on the machine, or with wf_ctx_set_jit(ctx, 0), the same programs are interpreted by the built-in kernel (same
+ * results bit for bit). wf_ctx_jit_stats: kernels compiled, launches served from the cache, compilations that failed and
+ * fell back. wf_jit_compile_air compiles the kernel of a description without a device (log: compiler output). */
+int wf_ctx_set_jit(wf_ctx* ctx, int on);
+int wf_ctx_jit_stats(wf_ctx* ctx, uint64_t* compiled, uint64_t* cache_hits, uint64_t* fallbacks);
+int wf_jit_compile_air(const uint64_t* air_desc, size_t air_desc_len, uint32_t ext, size_t* cubin_bytes, char* log, size_t log_cap);
 
 /* ---- plain kernels on caller-owned DEVICE buffers (unit parity + bench legs) ------------------- */
 /* in-place NTT (inverse=0) / iNTT (inverse=1) of `cols` columns, column-major [cols][n], n = 1 << log_n */

@@ -313,3 +313,39 @@ def sequence_mix(n, stride=4):
     A.assert_periodic(2, 1, stride, 7)                                    # same divisor as the sequence
     A.assert_sequence(2, 0, n // 2, [int(tr[2, 0]), int(tr[2, n // 2])])  # two values, first_step 0 (no cell asserted twice)
     return A.build(), tr
+
+
+def rescue_like(n, width=6):
+    """A heavy single-segment AIR for the generic evaluator (the shape of a Rescue-Prime half round,
+    examples/src/rescue/rescue.rs: S-box x^7, MDS layer, round constants): state' = M * state^7 + k with a circulant
+    M of small entries; `width` constraints of degree 7 (constraint-evaluation blowup 8), ~19 field operations per column
+    and row, 2 * width + ~19 * width registers in the transition program."""
+    m_row = [2, 3, 1, 1, 5, 7, 1, 4][:width]
+    ark = [(0x9E3779B97F4A7C15 * (j + 1)) % P for j in range(width)]
+    tr = np.zeros((width, n), dtype=np.uint64)
+    st = [j + 1 for j in range(width)]
+    for i in range(n):
+        for j in range(width):
+            tr[j, i] = st[j]
+        p7 = [pow(v, 7, P) for v in st]
+        st = [(sum(m_row[(c - j) % width] * p7[c] for c in range(width)) + ark[j]) % P for j in range(width)]
+    A = AirBuilder(width)
+    A.pub = [int(tr[0, n - 1])]
+    mc = [A.const(v) for v in m_row]
+    kc = [A.const(v) for v in ark]
+    p7 = []
+    for c in range(width):
+        x = A.cur(c)
+        x2 = A.mul(x, x)
+        x4 = A.mul(x2, x2)
+        x3 = A.mul(x2, x)
+        p7.append(A.mul(x3, x4))
+    for j in range(width):
+        acc = kc[j]
+        for c in range(width):
+            acc = A.add(acc, A.mul(mc[(c - j) % width], p7[c]))
+        A.constraint(A.sub(A.nxt(j), acc), 7)
+    for j in range(width):
+        A.assert_single(j, 0, j + 1)
+    A.assert_single(0, n - 1, int(tr[0, n - 1]))
+    return A.build(), tr

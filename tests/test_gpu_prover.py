@@ -296,3 +296,37 @@ def test_aux_assertions_depending_on_random_elements(ctx, oracle, ext, h, mont):
     assert got == want
     assert oracle.verify_air_dyn(desc, got, h, builder.values_fn, 2, nv, ext) == 0
     assert oracle.verify_air(desc, got, h) != 0      # the description's placeholder is not the asserted value
+
+
+@pytest.mark.parametrize("name,log_n,ext", [("rescue_like", 10, 1), ("rescue_like", 9, 3), ("periodic_mix", 10, 2), ("sequence_mix", 9, 3)])
+def test_compiled_constraint_kernel_equals_interpreter_and_oracle(ctx, oracle, name, log_n, ext):
+    # the per-AIR kernel compiled with NVRTC (jit.cu; registers and constants as literals) and the built-in interpreter must
+    # produce the same proof bytes, equal to the oracle's; rescue_like is the heavy case (degree-7 S-boxes, MDS layer)
+    desc, trace = getattr(airs, name)(1 << log_n)
+    opts = oracle.make_opts(num_queries=20, blowup=8, grinding=2, ext=ext, folding=4, rem_max_deg=7)
+    want = oracle.prove_air(desc, trace, opts)
+    before = ctx.jit_stats()
+    ctx.set_jit(True)
+    got_jit = ctx.prove_air(desc, trace, opts)
+    after = ctx.jit_stats()
+    ctx.set_jit(False)
+    got_int = ctx.prove_air(desc, trace, opts)
+    ctx.set_jit(True)
+    assert got_jit == want and got_int == want
+    assert oracle.verify_air(desc, got_jit, 0) == 0
+    # the compiled kernel really ran (no silent fallback to the interpreter)
+    assert after["fallbacks"] == before["fallbacks"]
+    assert after["compiled"] + after["cache_hits"] > before["compiled"] + before["cache_hits"]
+
+
+def test_compiled_constraint_kernel_aux_segment(ctx, oracle):
+    desc, trace, builder = airs.perm_rap(1 << 9)
+    opts = oracle.make_opts(num_queries=20, grinding=2, ext=3, folding=4, rem_max_deg=7)
+    want = oracle.prove_air_aux(desc, trace, opts, builder, airs.PERM_RAP_AUX_WIDTH, 2)
+    s0 = ctx.jit_stats()
+    assert ctx.prove_air_aux(desc, trace, opts, builder, airs.PERM_RAP_AUX_WIDTH, 2) == want
+    s1 = ctx.jit_stats()
+    assert s1["fallbacks"] == s0["fallbacks"] and s1["compiled"] + s1["cache_hits"] > s0["compiled"] + s0["cache_hits"]
+    ctx.set_jit(False)
+    assert ctx.prove_air_aux(desc, trace, opts, builder, airs.PERM_RAP_AUX_WIDTH, 2) == want
+    ctx.set_jit(True)

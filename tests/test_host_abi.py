@@ -145,3 +145,19 @@ def test_header_is_plain_c(tmp_path):
                            "-c", str(src), "-o", str(tmp_path / "t.o")])
     text = open(os.path.join(ROOT, "include", "winterfell_b200.h")).read()
     assert "torch" not in text and "cuda_runtime" not in text and "at::" not in text
+
+
+@pytest.mark.parametrize("name,ext", [("mulfib2", 1), ("periodic_mix", 3), ("sequence_mix", 2), ("rescue_like", 2), ("perm_rap", 3)])
+def test_constraint_kernel_compiles_at_run_time(name, ext):
+    # jit.cu: the AIR's transition programs printed as straight-line C++ in front of constraints_generic.cuh and compiled to an
+    # sm_100a cubin by NVRTC — needs no device (the GPU tests then check the compiled kernel against the interpreter and the
+    # oracle). Skipped only where NVRTC itself is not installed.
+    import airs
+    r = getattr(airs, name)(256)
+    desc = r[0]
+    rc, size, log = wf.jit_compile_air(desc, ext)
+    if rc != 0 and "NVRTC not available" in log:
+        pytest.skip(log)
+    assert rc == 0, log
+    assert size > 10_000
+    assert "error" not in log.lower()

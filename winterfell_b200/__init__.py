@@ -90,6 +90,9 @@ _SIGS = [
     ("wf_fri_fold_dev", C.c_int, [vp, vp, C.c_size_t, C.c_int, C.c_uint32, u64p, vp]),
     ("wf_field_ops_dev", C.c_int, [vp, vp, vp, C.c_size_t, vp]),
     ("wf_ext_ops_dev", C.c_int, [vp, C.c_uint32, vp, vp, C.c_size_t, vp]),
+    ("wf_ctx_set_jit", C.c_int, [vp, C.c_int]),
+    ("wf_ctx_jit_stats", C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("wf_jit_compile_air", C.c_int, [u64p, C.c_size_t, C.c_uint32, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]),
     ("wf_host_hash_elements", C.c_int, [C.c_int, u64p, C.c_size_t, u8p]),
     ("wf_host_merge", C.c_int, [C.c_int, u8p, u8p]),
     ("wf_host_merge_with_int", C.c_int, [C.c_int, u8p, C.c_uint64, u8p]),
@@ -403,6 +406,15 @@ class Context:
     def field_ops_dev(self, d_a, d_b, n, d_out):
         self.check(self.L.wf_field_ops_dev(self.h, vp(d_a), vp(d_b), n, vp(d_out)))
 
+    def set_jit(self, on):
+        """constraint kernels compiled per AIR with NVRTC (default on) vs the built-in interpreter"""
+        self.check(self.L.wf_ctx_set_jit(self.h, int(on)))
+
+    def jit_stats(self):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self.check(self.L.wf_ctx_jit_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"compiled": a.value, "cache_hits": b.value, "fallbacks": c.value}
+
     def ext_ops_dev(self, ext, d_a, d_b, n, d_out):
         self.check(self.L.wf_ext_ops_dev(self.h, ext, vp(d_a), vp(d_b), n, vp(d_out)))
 
@@ -577,3 +589,12 @@ def host_merge_with_int(hash_id, seed, value):
     o = np.zeros(32, dtype=np.uint8)
     lib().wf_host_merge_with_int(hash_id, tp, value, o.ctypes.data_as(u8p))
     return o.tobytes()
+
+
+def jit_compile_air(desc, ext):
+    """Compiles the constraint kernel of an AIR description with NVRTC; needs no device. Returns (status, cubin bytes, log)."""
+    d_, dp = _u64(desc)
+    n = C.c_size_t(0)
+    log = C.create_string_buffer(1 << 16)
+    rc = lib().wf_jit_compile_air(dp, d_.size, ext, C.byref(n), log, 1 << 16)
+    return rc, n.value, log.value.decode(errors="replace")

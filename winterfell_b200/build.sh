@@ -3,17 +3,28 @@
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-Wno-deprecated-gpu-targets -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unknown-pragmas --use_fast_math -ccbin /usr/bin/g++"
+FLAGS="-Wno-deprecated-gpu-targets -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unknown-pragmas --use_fast_math -ccbin /usr/bin/g++ -I_build"
 mkdir -p _build
+# the three headers NVRTC needs to compile a constraint kernel at run time (csrc/jit.cu), as string literals
+python3 - <<'PY'
+import os
+def lit(path):
+    return "".join('"' + l.rstrip("\n").replace("\\", "\\\\").replace('"', '\\"') + '\\n"\n' for l in open(path))
+out = "".join("static const char %s[] =\n%s;\n" % (name, lit(os.path.join("csrc", f)))
+              for name, f in (("JIT_SRC_GL64", "gl64.cuh"), ("JIT_SRC_COMMIT", "commit.cuh"), ("JIT_SRC_GENERIC", "constraints_generic.cuh")))
+old = open("_build/jit_headers.inc").read() if os.path.exists("_build/jit_headers.inc") else None
+if out != old:
+    open("_build/jit_headers.inc", "w").write(out)
+PY
 pids=()
-for f in ntt ntt2 commit fri layout capi prover ${EXTRA_SRCS}; do
+for f in ntt ntt2 commit fri layout capi prover jit ${EXTRA_SRCS}; do
   if [ ! -f _build/$f.o ] || [ csrc/$f.cu -nt _build/$f.o ] || [ -n "$(find csrc include ../include -newer _build/$f.o \( -name '*.cuh' -o -name '*.hpp' -o -name '*.h' -o -name '*.inc' \) 2>/dev/null | head -1)" ]; then
     $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c csrc/$f.cu -o _build/$f.o &
     pids+=($!)
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -Wno-deprecated-gpu-targets -shared -o libwinterfell_b200.so _build/*.o -lcudart -ccbin /usr/bin/g++
+$NVCC -Wno-deprecated-gpu-targets -shared -o libwinterfell_b200.so _build/*.o -lcudart -ldl -ccbin /usr/bin/g++
 echo "built $(pwd)/libwinterfell_b200.so"
 # the C++ mirror of the reference's plugin interface (include/winterfell_b200.hpp) + its driver: plain
 # g++ over the C ABI, proving the header has no CUDA dependency

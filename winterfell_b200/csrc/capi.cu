@@ -278,11 +278,17 @@ static int run_ntt(wf_ctx* ctx, const SegMatrix& in, SegMatrix& out, const SegMa
 // LDE of coefficient columns over 7 * <w_N>: out has n << log_b rows, row b*j + k = P(7 w_N^k w_n^j).
 // `out` may be a view of a wider matrix: segment width out.W >= polys.W, the polys' columns landing at
 // column offset out_col0 of each out row (column-chunked trace pipeline, wf_trace_lde_from_host).
+static int set_scatter(wf_ctx* ctx, NttPassParams& p, const LdeScatter& sc, u32 log_b, u32 coset) {
+    if (p.logS < NTT2_MIN_LOGS || p.W < 2) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "scattered LDE output needs sub-transforms of >= 64 points and W >= 2");
+    p.sc_on = 1; p.sc_log_nj = sc.log_nj; p.sc_log_b = log_b; p.sc_coset = coset; p.sc_seg0 = sc.seg0; p.sc_seg_stride = sc.seg_stride; p.sc_world = sc.world;
+    for (int q = 0; q < 8; q++) p.sc_peer[q] = sc.peer[q];
+    return WF_OK;
+}
 // k0 <= k < k1 (k1 = 0: all cosets) selects the cosets computed; coset k, point j lands in out row j * row_mul + (k - k0) * row_add
 // (row_mul = 0: the natural order b*j + k). Coset-major output (row_mul = 1, row_add = n) is what a rank of a sharded proof
 // produces for the cosets it owns (prover.cu, composition polynomial).
 static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_n, u32 log_b, u32 out_col0 = 0, u32 k0 = 0, u32 k1 = 0,
-                   u32 row_mul = 0, u32 row_add = 1) {
+                   u32 row_mul = 0, u32 row_add = 1, const LdeScatter* sc = nullptr) {
     u32 logR, logC;
     split_log(log_n, &logR, &logC);
     u32 b = 1u << log_b;
@@ -290,6 +296,7 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
     if (row_mul == 0) { row_mul = b; row_add = 1; }
     LdeTables tabs;
     NttPassParams p;
+    if (sc && logC > NTT_MAX_LOGS) return wf_fail(ctx, WF_ERR_UNSUPPORTED, "scattered LDE output is limited to two-pass sizes");
     if (logC > NTT_MAX_LOGS) {
         // THREE passes per coset (n > 2^22), same structure as run_ntt: pass A carries the coset scaling
         // and the four-step twiddle, the contiguous size-C step is a batch of R two-pass transforms whose
@@ -332,6 +339,7 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
         p.logS = (int)logC; p.logR = 0; p.logC = logC;
         p.pre_tab = tabs.pre + ((size_t)k0 << log_n); p.pre_batch_stride = (size_t)1 << log_n;
         p.out_row_mul = row_mul; p.out_row_add = row_add; p.out_col0 = out_col0;
+        if (sc) CKI(set_scatter(ctx, p, *sc, log_b, k0));
         return launch_pass(ctx, NTT_CONTIG, p, polys.nseg(), k1 - k0);
     }
     // Cosets per launch (grid.z = coset). The scratch Y of one coset is as large as the polynomials; while
@@ -366,6 +374,7 @@ static int run_lde(wf_ctx* ctx, const SegMatrix& polys, SegMatrix& out, u32 log_
         p.in_batch_stride = polys.words();
         p.out_row_mul = row_mul; p.out_row_add = row_add; p.out_col0 = out_col0;
         p.out = out.base + (size_t)(k - k0) * row_add * out.W;  // first coset of the launch; the launch's coset z adds z * row_add rows
+        if (sc) { rc = set_scatter(ctx, p, *sc, log_b, k); if (rc != WF_OK) break; }
         rc = launch_pass(ctx, NTT_CONTIG, p, polys.nseg(), kb);
     }
     wf_dev_free(ctx, yp);
@@ -446,6 +455,10 @@ void wf_ctx_destroy(wf_ctx* ctx) {
     for (auto& kv : ctx->tw) cudaFree(kv.second);
     for (auto& kv : ctx->lde_tabs) { cudaFree(kv.second.pre); if (kv.second.pow7) cudaFree(kv.second.pow7); }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto& kv : ctx->ipc_opened) cudaIpcCloseMemHandle(kv.second);   // other ranks' buffers mapped by sharded proofs
+    for (auto& kv : ctx->jit_cache) if (kv.second.first) cudaLibraryUnload((cudaLibrary_t)kv.second.first);
+    for (int i = 0; i < 4; i++) if (ctx->push_st[i]) { cudaStreamSynchronize(ctx->push_st[i]); cudaStreamDestroy(ctx->push_st[i]); }
+    for (int i = 0; i < 16; i++) if (ctx->push_ev[i]) cudaEventDestroy(ctx->push_ev[i]);
     if (ctx->copy_st) {
         cudaStreamSynchronize(ctx->copy_st);
         for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_up[i]); cudaEventDestroy(ctx->ev_used[i]); }
@@ -652,7 +665,7 @@ int wf_mat_lde_cosets(wf_ctx* ctx, const wf_mat* polys, uint32_t log_blowup, uin
 // compute stream. Columns are independent, so the result equals from_host_columns -> interpolate -> lde.
 int wf_trace_lde_from_host(wf_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, size_t nrows, int mont, uint32_t log_blowup,
                            wf_mat** polys_out, wf_mat** lde_out) {
-    return wf_trace_lde_cosetwise(ctx, cols, nullptr, ncols, nrows, mont, log_blowup, polys_out, lde_out, false, nullptr);
+    return wf_trace_lde_cosetwise(ctx, cols, nullptr, ncols, nrows, mont, log_blowup, polys_out, lde_out, false, nullptr, nullptr);
 }
 // The same pipeline with two knobs for the sharded prover (prover.cu): coset_major = the LDE is written coset-major
 // (row k * n + j = P(7 w_N^k w_n^j); *lde_out must then be preallocated with the natural segment width) and after_coset(k)
@@ -660,18 +673,23 @@ int wf_trace_lde_from_host(wf_ctx* ctx, const uint64_t* const* cols, uint32_t nc
 // d_cols != NULL: the columns are already on the device (column-major), no upload stage.
 int wf_trace_lde_cosetwise(wf_ctx* ctx, const uint64_t* const* cols, const uint64_t* d_cols, uint32_t ncols, size_t nrows, int mont,
                            uint32_t log_blowup, wf_mat** polys_out, wf_mat** lde_out, bool coset_major,
-                           const std::function<int(u32)>* after_coset) {
-    if (!ctx || (!cols && !d_cols) || !polys_out || !lde_out || ncols == 0) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
+                           const std::function<int(u32)>* after_coset, const LdeScatter* scatter) {
+    if (!ctx || (!cols && !d_cols) || !polys_out || (!lde_out && !scatter) || ncols == 0) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
     u32 log_n;
     if (log2_exact(nrows, &log_n) || log_n < 1) return wf_fail(ctx, WF_ERR_INVALID, "rows must be a power of two >= 2");
     if (log_blowup > 7 || log_n + log_blowup > 32) return wf_fail(ctx, WF_ERR_INVALID, "bad blowup");
     const int Wout = seg_width_for(ncols);
     const u32 nseg_out = (ncols + Wout - 1) / Wout;
     const u32 nb = 1u << log_blowup;
-    if (coset_major && (!*lde_out || (*lde_out)->m.rows != (nrows << log_blowup) || (*lde_out)->m.W != Wout || (*lde_out)->m.cols != ncols))
+    if (coset_major && !scatter && (!*lde_out || (*lde_out)->m.rows != (nrows << log_blowup) || (*lde_out)->m.W != Wout || (*lde_out)->m.cols != ncols))
         return wf_fail(ctx, WF_ERR_INVALID, "coset-major output must be preallocated");
     // cosets of one column chunk: all at once, or one by one with the callback when this is the last chunk
-    auto extend = [&](const SegMatrix& pv, SegMatrix& ov, u32 out_col0, bool last) -> int {
+    auto extend = [&](const SegMatrix& pv, SegMatrix& ov, u32 out_col0, bool last, u32 out_seg) -> int {
+        if (scatter) {  // every coset straight into the owners' row shards (natural order there); `ov` is not written
+            LdeScatter s2 = *scatter;
+            s2.seg0 += out_seg;
+            return run_lde(ctx, pv, ov, log_n, log_blowup, out_col0, 0, nb, 0, 1, &s2);
+        }
         if (!after_coset || !last) {
             if (!coset_major) return run_lde(ctx, pv, ov, log_n, log_blowup, out_col0);
             return run_lde(ctx, pv, ov, log_n, log_blowup, out_col0, 0, nb, 1, (u32)nrows);
@@ -695,9 +713,10 @@ int wf_trace_lde_cosetwise(wf_ctx* ctx, const uint64_t* const* cols, const uint6
         int r = wf_mat_interpolate(ctx, tr, polys_out);
         wf_mat_free(ctx, tr);
         if (r != WF_OK) return r;
+        if (scatter) { SegMatrix none = (*polys_out)->m; none.W = Wout; return extend((*polys_out)->m, none, 0, true, 0); }
         if (!coset_major && !after_coset) return wf_mat_lde(ctx, *polys_out, log_blowup, lde_out);
         if (!coset_major) CKI(wf_mat_alloc(ctx, nrows << log_blowup, ncols, lde_out));
-        return extend((*polys_out)->m, (*lde_out)->m, 0, true);
+        return extend((*polys_out)->m, (*lde_out)->m, 0, true, 0);
     }
     if (!ctx->copy_st) {
         CK(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
@@ -715,16 +734,16 @@ int wf_trace_lde_cosetwise(wf_ctx* ctx, const uint64_t* const* cols, const uint6
         wf_mat_free(ctx, tr);
         for (int i = 0; i < 2; i++) wf_dev_free(ctx, stage[i]);
         wf_dev_free(ctx, tmp);
-        if (results_too) { wf_mat_free(ctx, polys); if (!coset_major) wf_mat_free(ctx, lde); }
+        if (results_too) { wf_mat_free(ctx, polys); if (!coset_major && !scatter) wf_mat_free(ctx, lde); }
     };
     auto body = [&]() -> int {
         CKI(wf_mat_alloc_w(ctx, nrows, ncols, Wc, &polys));
-        if (coset_major) lde = *lde_out;
+        if (coset_major || scatter) lde = lde_out ? *lde_out : nullptr;
         else CKI(wf_mat_alloc(ctx, nrows << log_blowup, ncols, &lde));
         CKI(wf_mat_alloc_w(ctx, nrows, Wc, Wc, &tr));                       // one chunk of trace values (reused)
         for (int i = 0; i < 2; i++) CKI(wf_dev_alloc(ctx, (size_t)Wc * nrows * 8, &stage[i]));
         CKI(wf_dev_alloc(ctx, (size_t)Wc * nrows * 8, &tmp));               // two-pass scratch
-        if (lde->m.W > (int)ncols) CK(cudaMemsetAsync(lde->m.base, 0, lde->m.words() * 8, ctx->st));  // padding columns
+        if (lde && lde->m.W > (int)ncols) CK(cudaMemsetAsync(lde->m.base, 0, lde->m.words() * 8, ctx->st));  // padding columns
         // the copy stream must not write pool buffers before their previous users on the compute stream are done
         CK(cudaEventRecord(ctx->ev_start, ctx->st));
         CK(cudaStreamWaitEvent(ctx->copy_st, ctx->ev_start, 0));
@@ -747,10 +766,11 @@ int wf_trace_lde_cosetwise(wf_ctx* ctx, const uint64_t* const* cols, const uint6
             SegMatrix tv = trv;
             tv.base = (u64*)tmp;
             CKI(run_ntt(ctx, trv, pv, &tv, log_n, 1));
-            SegMatrix ov = lde->m;                                            // out segment holding columns c0..
-            ov.base = lde->m.base + (size_t)(c0 / Wout) * lde->m.seg_stride;
+            SegMatrix ov = pv;                                                // out segment holding columns c0..
+            ov.W = Wout;
+            if (lde) { ov = lde->m; ov.base = lde->m.base + (size_t)(c0 / Wout) * lde->m.seg_stride; }
             ov.cols = cw;
-            CKI(extend(pv, ov, c0 % Wout, k + 1 == nchunks));
+            CKI(extend(pv, ov, c0 % Wout, k + 1 == nchunks, c0 / Wout));
         }
         return WF_OK;
     };
@@ -762,7 +782,7 @@ int wf_trace_lde_cosetwise(wf_ctx* ctx, const uint64_t* const* cols, const uint6
     }
     release(false);
     *polys_out = polys;
-    *lde_out = lde;
+    if (lde_out) *lde_out = lde;
     return WF_OK;
 }
 

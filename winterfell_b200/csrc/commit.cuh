@@ -1,6 +1,8 @@
 // commit.cuh — segment-layout matrix descriptor + row hashing / Merkle entry points (commit.cu).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 
 #include "gl64.cuh"
 
@@ -21,6 +23,7 @@ struct SegMatrix {
     size_t words() const { return (size_t)nseg() * seg_stride; }
 };
 
+#ifndef __CUDACC_RTC__
 static inline int seg_width_for(u32 cols) { return cols >= 8 ? 8 : cols > 2 ? 4 : cols == 2 ? 2 : 1; }
 
 // digests: rows x 4 words (32 bytes each)
@@ -28,3 +31,4 @@ static inline int seg_width_for(u32 cols) { return cols >= 8 ? 8 : cols > 2 ? 4 
 cudaError_t commit_hash_rows(int hash_id, const SegMatrix& m, u64* digests, cudaStream_t st, u32 partition_size = 0);
 // nodes: nleaves x 4 words; nodes[0] = 0, nodes[1] = root
 cudaError_t commit_merkle_nodes(int hash_id, const u64* leaves, size_t nleaves, u64* nodes, cudaStream_t st);
+#endif  // !__CUDACC_RTC__

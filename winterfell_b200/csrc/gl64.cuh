@@ -8,7 +8,13 @@
 // needs no Montgomery factor and every hash input must be canonical anyway (blake/mod.rs:52-65).
 // Conversion helpers for Montgomery-form buffers crossing the C ABI are gl_from_mont / gl_to_mont.
 #pragma once
+#ifdef __CUDACC_RTC__  // runtime compilation of constraint kernels (jit.cu): NVRTC ships no <stdint.h>
+typedef unsigned long long uint64_t;
+typedef unsigned int uint32_t;
+typedef unsigned char uint8_t;
+#else
 #include <stdint.h>
+#endif
 
 #ifdef __CUDACC__
 #define GL_HD __host__ __device__ __forceinline__

@@ -39,6 +39,15 @@ struct wf_ctx {
     size_t pinned_bytes;
     cudaStream_t copy_st = nullptr;          // H2D stream of the chunked trace pipeline (created on first use)
     cudaEvent_t ev_up[2], ev_used[2], ev_start;
+    // sharded proofs: device memory of the other ranks mapped through CUDA IPC (key = the 64-byte handle), the streams the
+    // peer copies are issued on (copy engines: no SM is taken from the kernels they overlap) and one event per coset
+    std::map<std::string, void*> ipc_opened;
+    cudaStream_t push_st[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t push_ev[16] = {};
+    // constraint kernels compiled per AIR (jit.cu): generated source -> (cudaLibrary_t, cudaKernel_t); (null, null) = failed
+    std::map<std::string, std::pair<void*, void*>> jit_cache;
+    bool jit_enabled = true;
+    uint64_t jit_compiled = 0, jit_hits = 0, jit_fallbacks = 0;
     bool profiling;                          // record a CUDA event at every pipeline stage boundary
     std::vector<std::pair<std::string, cudaEvent_t>> marks;
 };
@@ -97,13 +106,26 @@ static inline void wf_host_dft(std::vector<u64>& v, size_t n, int d, bool invers
 }
 
 int wf_fail(wf_ctx* ctx, int code, const char* fmt, ...);
+// jit.cu
+std::string wf_jit_source(int D, u32 w, u32 nper, u32 nregs, const std::vector<u32>& prog, const std::vector<u64>& consts, u32 aw, u32 nr,
+                          u32 naregs, const std::vector<u32>& aprog);
+int wf_jit_compile(const std::string& src, std::vector<char>& cubin, std::string& log);
+int wf_jit_get_kernel(wf_ctx* ctx, const std::string& src, cudaKernel_t* kernel);
 int wf_dev_alloc(wf_ctx* ctx, size_t bytes, void** out);
 void wf_dev_free(wf_ctx* ctx, void* p);
 int wf_mat_alloc(wf_ctx* ctx, size_t rows, u32 cols, wf_mat** out);
 int wf_mat_alloc_w(wf_ctx* ctx, size_t rows, u32 cols, int W, wf_mat** out);
+// LDE output scattered into the row shards of the ranks of a sharded proof (NttPassParams::sc_*, ntt.cuh)
+struct LdeScatter {
+    u64* peer[8];        // shard base per rank (peer memory mapped through CUDA IPC; own rank: the local shard)
+    size_t seg_stride;   // words between segments of a shard
+    u32 seg0;            // global segment the first local segment maps to
+    u32 log_nj;          // log2(points of one coset per rank)
+    u32 world;           // > 0: also write the halo rows of the previous rank (NttPassParams::sc_world)
+};
 extern "C" int wf_trace_lde_cosetwise(wf_ctx* ctx, const uint64_t* const* cols, const uint64_t* d_cols, uint32_t ncols, size_t nrows, int mont,
                            uint32_t log_blowup, wf_mat** polys_out, wf_mat** lde_out, bool coset_major,
-                           const std::function<int(u32)>* after_coset);
+                           const std::function<int(u32)>* after_coset, const LdeScatter* scatter);
 extern "C" int wf_mat_lde_cosets(wf_ctx* ctx, const wf_mat* polys, uint32_t log_blowup, uint32_t k0, uint32_t k1, wf_mat* lde);  // internal (not in the public header)
 struct PublicCoin;
 struct Digest;

@@ -34,16 +34,7 @@
 // =================================================================================================
 // kernels
 // =================================================================================================
-template <int D>
-__device__ __forceinline__ GlExt<D> ld_ext(const u64* p) {
-    GlExt<D> r;
-#pragma unroll
-    for (int i = 0; i < D; i++) r.v[i] = p[i];
-    return r;
-}
-__device__ __forceinline__ u64 seg_at(const SegMatrix& m, size_t row, u32 col) {
-    return m.base[(size_t)(col / m.W) * m.seg_stride + row * m.W + (col % m.W)];
-}
+#include "constraints_generic.cuh"  // ld_ext / seg_at, GenEvalParams, generic_constraints_kernel (also the source NVRTC compiles per AIR)
 
 struct FibEvalParams {
     SegMatrix lde;      // N x 2k trace LDE
@@ -143,145 +134,6 @@ __global__ void __launch_bounds__(256) fib_constraints_kernel(FibEvalParams p) {
 #pragma unroll
         for (int q = 0; q < D; q++) o[q] = acc.v[q];
     }
-}
-
-// Generic constraint evaluator: Air::evaluate_transition given as a straight-line program over the
-// frame registers (r[0..w) current row, r[w..2w) next row, then periodic values, then temporaries),
-// any number of single-value boundary groups and transition exemptions. One CE row
-// per thread; registers live in local memory.
-#define GEN_MAX_REGS 160
-struct GenEvalParams {
-    SegMatrix lde, out;
-    u32 w, log_n, log_blowup, log_ce_blowup;
-    const u32* prog;       // [prog_len][4]: op, dst, a, b
-    u32 prog_len, num_regs, num_periodic, num_tc;
-    const u64* consts;
-    const u64* ptab;       // periodic tables, concatenated
-    const u32* ptab_off;   // [num_periodic]
-    const u32* ptab_len;   // [num_periodic]  (L_j * ce_blowup, a power of two)
-    const u64* tcoef;      // [num_tc][D]
-    u32 num_groups;
-    const u32* g_off;      // [num_groups + 1] offsets into the entry arrays
-    const u64* g_a;        // x^a - b divisor exponent (a divides n)
-    const u64* g_b;
-    const u64* g_oa;       // 7^a
-    const u32* e_col;
-    const u64* e_val;
-    const u64* e_cc;       // [entries][D]
-    // sequence assertions (Assertion::sequence): per entry the value polynomial evaluated over the CE
-    // domain (LargePolyConstraint, evaluator/boundary.rs:389-445); nullptr for single-value entries
-    const u64* const* e_tab;
-    const u32* e_tstride;  // words per table row
-    const u32* e_shift;    // (first_step * ce_blowup) mod ce
-    const u64* tw_ce;      // w_ce^i, i < ce/2
-    const u64* zt;         // [ce_blowup] 1 / (x^n - 1) at CE step i mod ce_blowup (device table: ce_blowup <= 128)
-    u64 exempt[8];
-    u32 num_exempt;
-    // auxiliary segment (Air::evaluate_aux_transition, air/src/air/mod.rs:248-260): program over E
-    // registers [main cur | main next | aux cur | aux next | periodic | random elements | temporaries]
-    SegMatrix alde;        // N x aw*D
-    u32 aw, nr, aprog_len, num_agroups;
-    const u32* aprog;
-    const u64* rnd;        // [nr][D]
-    const u64* atcoef;     // [aux constraints][D]
-    const u32* ag_off;     // aux boundary groups (air/src/air/boundary/mod.rs:121-128)
-    const u64* ag_a;
-    const u64* ag_b;
-    const u64* ag_oa;
-    const u32* ae_col;
-    const u64* ae_val;     // [entries][D]
-    const u64* ae_cc;      // [entries][D]
-    const u64* const* ae_tab;
-    const u32* ae_tstride;
-    const u32* ae_shift;
-};
-#define AUX_MAX_REGS 96
-template <int D, bool AUX>
-__global__ void __launch_bounds__(128) generic_constraints_kernel(GenEvalParams p) {
-    const size_t ce = (size_t)1 << (p.log_n + p.log_ce_blowup);
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ce) return;
-    const size_t N = (size_t)1 << (p.log_n + p.log_blowup);
-    const size_t ls = i << (p.log_blowup - p.log_ce_blowup);
-    const size_t nx = (ls + ((size_t)1 << p.log_blowup)) & (N - 1);
-    u64 r[GEN_MAX_REGS];
-    for (u32 c = 0; c < p.w; c++) { r[c] = seg_at(p.lde, ls, c); r[p.w + c] = seg_at(p.lde, nx, c); }
-    for (u32 j = 0; j < p.num_periodic; j++) r[2 * p.w + j] = p.ptab[p.ptab_off[j] + (u32)(i & (p.ptab_len[j] - 1))];
-    GlExt<D> T = ext_zero<D>();
-    for (u32 k = 0; k < p.prog_len; k++) {
-        const u32 op = p.prog[4 * k], dst = p.prog[4 * k + 1], a = p.prog[4 * k + 2], b = p.prog[4 * k + 3];
-        switch (op) {
-            case 0: r[dst] = gl_add(r[a], r[b]); break;
-            case 1: r[dst] = gl_sub(r[a], r[b]); break;
-            case 2: r[dst] = gl_mul(r[a], r[b]); break;
-            case 3: r[dst] = p.consts[a]; break;
-            default: T = ext_add(T, ext_mul_base(ld_ext<D>(p.tcoef + (size_t)dst * D), r[a])); break;  // OUT
-        }
-    }
-    GlExt<D> ra[AUX ? AUX_MAX_REGS : 1];
-    if constexpr (AUX) {  // evaluator/default.rs:306-341 evaluate_aux_transition
-        for (u32 c = 0; c < 2 * p.w; c++) ra[c] = ext_from_base<D>(r[c]);
-        for (u32 j = 0; j < p.aw; j++) {
-#pragma unroll
-            for (int q = 0; q < D; q++) {
-                ra[2 * p.w + j].v[q] = seg_at(p.alde, ls, j * D + q);
-                ra[2 * p.w + p.aw + j].v[q] = seg_at(p.alde, nx, j * D + q);
-            }
-        }
-        const u32 pb = 2 * p.w + 2 * p.aw;
-        for (u32 j = 0; j < p.num_periodic; j++) ra[pb + j] = ext_from_base<D>(r[2 * p.w + j]);
-        for (u32 j = 0; j < p.nr; j++) ra[pb + p.num_periodic + j] = ld_ext<D>(p.rnd + (size_t)j * D);
-        for (u32 k = 0; k < p.aprog_len; k++) {
-            const u32 op = p.aprog[4 * k], dst = p.aprog[4 * k + 1], a = p.aprog[4 * k + 2], b = p.aprog[4 * k + 3];
-            switch (op) {
-                case 0: ra[dst] = ext_add(ra[a], ra[b]); break;
-                case 1: ra[dst] = ext_sub(ra[a], ra[b]); break;
-                case 2: ra[dst] = ext_mul(ra[a], ra[b]); break;
-                case 3: ra[dst] = ext_from_base<D>(p.consts[a]); break;
-                default: T = ext_add(T, ext_mul(ra[a], ld_ext<D>(p.atcoef + (size_t)dst * D))); break;  // OUT
-            }
-        }
-    }
-    const u32 half = (u32)(ce >> 1);
-    const u32 cemask = (u32)(ce - 1);
-    u64 w = p.tw_ce[i & (half - 1)];
-    if (i & half) w = gl_neg(w);
-    const u64 x = gl_mul(w, GL_GENERATOR);
-    u64 ex = 1;
-    for (u32 k = 0; k < p.num_exempt; k++) ex = gl_mul(ex, gl_sub(x, p.exempt[k]));
-    GlExt<D> acc = ext_mul_base(T, gl_mul(p.zt[i & (((size_t)1 << p.log_ce_blowup) - 1)], ex));
-    for (u32 g = 0; g < p.num_groups; g++) {
-        GlExt<D> B = ext_zero<D>();
-        for (u32 e = p.g_off[g]; e < p.g_off[g + 1]; e++) {
-            u64 val = p.e_val[e];
-            if (const u64* tab = p.e_tab[e]) val = tab[(size_t)((u32)(i - p.e_shift[e]) & cemask) * p.e_tstride[e]];
-            B = ext_add(B, ext_mul_base(ld_ext<D>(p.e_cc + (size_t)e * D), gl_sub(r[p.e_col[e]], val)));
-        }
-        // x^a = 7^a * w_ce^(i*a mod ce)
-        u32 ia = (u32)(((u64)i * p.g_a[g]) & cemask);
-        u64 wa = p.tw_ce[ia & (half - 1)];
-        if (ia & half) wa = gl_neg(wa);
-        u64 den = gl_sub(gl_mul(wa, p.g_oa[g]), p.g_b[g]);
-        acc = ext_add(acc, ext_mul_base(B, gl_inv(den)));
-    }
-    if constexpr (AUX) {  // evaluator/boundary.rs: aux_single_value constraints, values and columns in E
-        for (u32 g = 0; g < p.num_agroups; g++) {
-            GlExt<D> B = ext_zero<D>();
-            for (u32 e = p.ag_off[g]; e < p.ag_off[g + 1]; e++) {
-                GlExt<D> val = ld_ext<D>(p.ae_val + (size_t)e * D);
-                if (const u64* tab = p.ae_tab[e]) val = ld_ext<D>(tab + (size_t)((u32)(i - p.ae_shift[e]) & cemask) * p.ae_tstride[e]);
-                B = ext_add(B, ext_mul(ext_sub(ra[2 * p.w + p.ae_col[e]], val), ld_ext<D>(p.ae_cc + (size_t)e * D)));
-            }
-            u32 ia = (u32)(((u64)i * p.ag_a[g]) & cemask);
-            u64 wa = p.tw_ce[ia & (half - 1)];
-            if (ia & half) wa = gl_neg(wa);
-            u64 den = gl_sub(gl_mul(wa, p.ag_oa[g]), p.ag_b[g]);
-            acc = ext_add(acc, ext_mul_base(B, gl_inv(den)));
-        }
-    }
-    u64* o = p.out.base + i * p.out.W;
-#pragma unroll
-    for (int q = 0; q < D; q++) o[q] = acc.v[q];
 }
 
 // composition_poly.rs:128-140 segment(): column j = coefficients [j*n, (j+1)*n) of the interpolated
@@ -1141,6 +993,16 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
             CKI(upload(aetab.data(), aetab.size() * 8, &dp)); p.ae_tab = (const u64* const*)dp;
             CKI(upload(aetstride.data(), aetstride.size() * 4, &dp)); p.ae_tstride = (u32*)dp;
             CKI(upload(aeshift.data(), aeshift.size() * 4, &dp)); p.ae_shift = (u32*)dp;
+        }
+        // the kernel compiled for this AIR (NVRTC, jit.cu) when there is one, else the interpreter
+        cudaKernel_t jk = nullptr;
+        const bool jit = ctx->jit_enabled &&
+                         wf_jit_get_kernel(ctx, wf_jit_source(D, air.w, (u32)air.periodic.size(), air.num_regs, air.prog, air.consts, aw, air.nr,
+                                                              air.aux_num_regs, air.aux_prog), &jk) == WF_OK;
+        if (jit) {
+            void* args[] = {&p};
+            CK(cudaLaunchKernel((const void*)jk, dim3((unsigned)((ce + 127) / 128)), dim3(128), args, 0, ctx->st));
+        } else if (aw) {
             generic_constraints_kernel<D, true><<<(unsigned)((ce + 127) / 128), 128, 0, ctx->st>>>(p);
         } else {
             generic_constraints_kernel<D, false><<<(unsigned)((ce + 127) / 128), 128, 0, ctx->st>>>(p);
@@ -1544,6 +1406,44 @@ struct ShardCtx {
         ncoll += 1;
         return WF_OK;
     }
+    // Maps the buffer at `local_base` (a cudaMalloc allocation of the same size on every rank) of every other rank into this
+    // process (cudaIpcGetMemHandle -> all-gather of the handles -> cudaIpcOpenMemHandle, cached in the context). Returns
+    // WF_ERR_UNSUPPORTED when the driver refuses (ranks on different nodes, IPC disabled): the caller then falls back to the
+    // communicator's exchange.
+    int map_peers(void* local_base, std::vector<void*>& out) {
+        out.assign(G, nullptr);
+        if (const char* e = getenv("WF_PEER_PUSH")) if (atoi(e) == 0) return WF_ERR_UNSUPPORTED;
+        cudaIpcMemHandle_t h;
+        memset(&h, 0, sizeof(h));
+        int ok = cudaIpcGetMemHandle(&h, local_base) == cudaSuccess ? 1 : 0;
+        if (!ok) cudaGetLastError();
+        struct Msg { cudaIpcMemHandle_t h; int ok; int pad; } mine{h, ok, 0};
+        std::vector<Msg> all(G);
+        CKI(gather_host(&mine, all.data(), sizeof(Msg)));
+        for (int q = 0; q < G; q++) ok &= all[q].ok;
+        if (!ok) return WF_ERR_UNSUPPORTED;
+        int opened = 1;
+        for (int q = 0; q < G; q++) {
+            if (q == r) { out[q] = local_base; continue; }
+            std::string key((const char*)&all[q].h, sizeof(cudaIpcMemHandle_t));
+            auto it = ctx->ipc_opened.find(key);
+            if (it != ctx->ipc_opened.end()) { out[q] = it->second; continue; }
+            void* pp = nullptr;
+            if (cudaIpcOpenMemHandle(&pp, all[q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = 0; continue; }
+            ctx->ipc_opened[key] = pp;
+            out[q] = pp;
+        }
+        // every rank must take the same path: agree on the outcome
+        std::vector<int> flags(G);
+        CKI(gather_host(&opened, flags.data(), sizeof(int)));
+        for (int q = 0; q < G; q++) if (!flags[q]) return WF_ERR_UNSUPPORTED;
+        return WF_OK;
+    }
+    int host_barrier() {
+        int one = 1;
+        std::vector<int> all(G);
+        return gather_host(&one, all.data(), sizeof(int));
+    }
     double exchange_ms() {
         double t = 0;
         for (auto& e : ev) { float ms = 0; if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) t += ms; }
@@ -1619,14 +1519,65 @@ int prove_fib_sharded(wf_ctx* ctx, const wf_comm* cm, const uint64_t* const* loc
     //         block per segment: its exchange runs on the communicator's stream while coset k + 1 is being extended ----
     wf_mark(ctx, "start");
     const size_t nj = n / (size_t)G;   // points of one coset inside one rank's row range
+    CKI(wf_mat_alloc(ctx, rows_per + b, c, &shard));
+    shard->m.rows = rows_per;  // seg_stride stays (rows_per + b) * 8: rows [rows_per, rows_per + b) are the halo
+    const size_t sstride = shard->m.seg_stride;
+    // Preferred transport — the exchange fused into the LDE: every rank maps the others' row shards (CUDA IPC) and the last
+    // pass of every coset's transform writes each row straight to its owner (and the first rows of a range also into the halo
+    // of the rank before it) with stores over NVLink: natural order at the destination, no staging buffer, no copy kernel,
+    // no interleaving pass, nothing left to overlap. Closed by one stream synchronisation + host barrier.
+    std::vector<void*> peer_shard;
+    u32 log_nj = 0;
+    while (((size_t)1 << log_nj) < nj) log_nj++;
+    const bool scat = G <= 8 && log_n <= 22 && sc.map_peers(shard->m.base, peer_shard) == WF_OK;
+    bool push = false;
+    if (scat) {
+        LdeScatter sct;
+        for (int q = 0; q < 8; q++) sct.peer[q] = q < G ? (u64*)peer_shard[q] : nullptr;
+        sct.seg_stride = sstride; sct.seg0 = (u32)r * nsl; sct.log_nj = log_nj; sct.world = (u32)G;
+        CKI(wf_trace_lde_cosetwise(ctx, local_cols, d_local, cl, n, mont, log_b, &polys, nullptr, false, nullptr, &sct));
+        wf_mark(ctx, "trace_lde");
+        CK(cudaStreamSynchronize(ctx->st));   // my stores have landed; everybody's have when every rank says so
+        CKI(sc.host_barrier());
+        sc.ncoll += 1;
+        sc.bytes_overlapped += (double)(G - 1) * nsl * (double)rows_per * 64;
+        push = true;
+    } else {
     wf_mat* stage = nullptr;           // what arrives: [global segment][coset][nj][8]
     scope.own({&stage});
     CKI(wf_mat_alloc_w(ctx, N, cl, 8, &lde));          // mine, coset-major: [local segment][coset][n][8]
     CKI(wf_mat_alloc_w(ctx, rows_per, c, 8, &stage));
-    CKI(wf_mat_alloc(ctx, rows_per + b, c, &shard));
-    shard->m.rows = rows_per;  // seg_stride stays (rows_per + b) * 8: rows [rows_per, rows_per + b) are the halo
-    const size_t sstride = shard->m.seg_stride;
+    // Preferred transport: every rank maps the others' `stage` buffers (CUDA IPC) and PUSHES its blocks there with peer copies
+    // on side streams — copy engines over NVLink, no SM taken from the NTT kernels they overlap (NCCL send/recv kernels on a
+    // side stream were measured: they slow the LDE down by as much as they hide). Fallback: the communicator's exchange.
+    std::vector<void*> peer_stage;
+    push = sc.map_peers(stage->m.base, peer_stage) == WF_OK;
+    if (push) {
+        for (int i = 0; i < 4; i++) if (!ctx->push_st[i]) CK(cudaStreamCreateWithFlags(&ctx->push_st[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 16; i++) if (!ctx->push_ev[i]) CK(cudaEventCreateWithFlags(&ctx->push_ev[i], cudaEventDisableTiming));
+    }
     const std::function<int(u32)> after_coset = [&](u32 k) -> int {   // coset k of every local column is enqueued: ship it
+        if (push) {
+            cudaEvent_t ev = ctx->push_ev[k % 16];
+            CK(cudaEventRecord(ev, ctx->st));
+            for (int dq = 1; dq < G; dq++) {             // start with the next rank: no two ranks hit the same peer first
+                const int q = (r + dq) % G;
+                cudaStream_t ps = ctx->push_st[dq % 4];
+                CK(cudaStreamWaitEvent(ps, ev, 0));
+                for (u32 sg = 0; sg < nsl; sg++) {
+                    const u64* src = lde->m.base + (size_t)sg * lde->m.seg_stride + ((size_t)k * n + (size_t)q * nj) * 8;
+                    u64* dst = (u64*)peer_stage[q] + ((size_t)r * nsl + sg) * stage->m.seg_stride + (size_t)k * nj * 8;
+                    CK(cudaMemcpyAsync(dst, src, nj * 64, cudaMemcpyDeviceToDevice, ps));
+                }
+            }
+            for (u32 sg = 0; sg < nsl; sg++) {
+                const u64* src = lde->m.base + (size_t)sg * lde->m.seg_stride + ((size_t)k * n + (size_t)r * nj) * 8;
+                CK(cudaMemcpyAsync(stage->m.base + ((size_t)r * nsl + sg) * stage->m.seg_stride + (size_t)k * nj * 8, src, nj * 64,
+                                   cudaMemcpyDeviceToDevice, ctx->st));
+            }
+            sc.bytes_overlapped += (double)(G - 1) * nsl * nj * 64;
+            return WF_OK;
+        }
         std::vector<int> sp, rp;
         std::vector<const void*> sv;
         std::vector<void*> rv;
@@ -1642,9 +1593,16 @@ int prove_fib_sharded(wf_ctx* ctx, const wf_comm* cm, const uint64_t* const* loc
     };
     // (upload ->) layout -> interpolate -> extend, pipelined per column chunk for host columns; the cosets of the last chunk
     // are extended one by one and after_coset(k) ships coset k while coset k + 1 is computed
-    CKI(wf_trace_lde_cosetwise(ctx, local_cols, d_local, cl, n, mont, log_b, &polys, &lde, true, &after_coset));
+    CKI(wf_trace_lde_cosetwise(ctx, local_cols, d_local, cl, n, mont, log_b, &polys, &lde, true, &after_coset, nullptr));
     wf_mark(ctx, "trace_lde");
-    CKI(sc.join());
+    if (push) {
+        // my pushes have landed when my side streams drain; everybody's have when every rank says so
+        for (int i = 0; i < 4; i++) CK(cudaStreamSynchronize(ctx->push_st[i]));
+        CKI(sc.host_barrier());
+        sc.ncoll += 1;
+    } else {
+        CKI(sc.join());
+    }
     {   // coset-major -> natural order (row = b j + k) of my row range, every segment
         SegMatrix dstv = shard->m;
         dim3 grid((unsigned)((rows_per * 8 + 255) / 256), nsg);
@@ -1664,6 +1622,7 @@ int prove_fib_sharded(wf_ctx* ctx, const wf_comm* cm, const uint64_t* const* loc
         CK(cudaMemcpy2DAsync(shard->m.base + rows_per * 8, sstride * 8, pk2, hb, hb, nsg, cudaMemcpyDeviceToDevice, ctx->st));
         wf_dev_free(ctx, pk);
         wf_dev_free(ctx, pk2);
+    }
     }
     wf_mark(ctx, "trace_exchange");
     // ---- 3. leaves + subtree over my rows, all-gather of the subtree roots ----
@@ -1964,6 +1923,7 @@ int prove_fib_sharded(wf_ctx* ctx, const wf_comm* cm, const uint64_t* const* loc
         for (int i = 4; i < 8; i++) stats[i] = 0;
         stats[4] = (double)slayers.size();
         stats[5] = sc.bytes_overlapped;
+        stats[6] = scat ? 2.0 : (push ? 1.0 : 0.0);
     }
     return WF_OK;
 }
@@ -2051,6 +2011,22 @@ extern "C" int wf_prove_air_aux_dyn(wf_ctx* ctx, const uint64_t* air_desc, size_
     AirHost air;
     if (!parse_air_host(air_desc, air_desc_len, air)) return wf_fail(ctx, WF_ERR_INVALID, "malformed AIR description");
     return prove_dispatch(ctx, air, trace_cols, nullptr, mont, log_n, o, proof, proof_len, aux_builder, aux_user, aux_assertions);
+}
+
+// Compiles the constraint kernel of an AIR description; needs no device (a build-time / CI check of the JIT path and of the
+// generated code). *cubin_bytes = size of the sm_100a cubin; `log` receives the compiler log (warnings or errors).
+extern "C" int wf_jit_compile_air(const uint64_t* air_desc, size_t air_desc_len, uint32_t ext, size_t* cubin_bytes, char* log, size_t log_cap) {
+    if (!air_desc || ext < 1 || ext > 3) return WF_ERR_INVALID;
+    AirHost air;
+    if (!parse_air_host(air_desc, air_desc_len, air)) return WF_ERR_INVALID;
+    std::vector<char> cubin;
+    std::string lg;
+    const int rc = wf_jit_compile(wf_jit_source((int)ext, air.w, (u32)air.periodic.size(), air.num_regs, air.prog, air.consts, air.aw, air.nr,
+                                                air.aux_num_regs, air.aux_prog), cubin, lg);
+    if (log && log_cap) { strncpy(log, lg.c_str(), log_cap - 1); log[log_cap - 1] = 0; }
+    if (cubin_bytes) *cubin_bytes = cubin.size();
+    if (const char* dump = getenv("WF_JIT_DUMP")) if (rc == 0) { FILE* f = fopen(dump, "wb"); if (f) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); } }
+    return rc == 0 ? WF_OK : WF_ERR_UNSUPPORTED;
 }
 
 // ---- stepwise exports: the seams of prover/src/lib.rs:125-223 (ConstraintEvaluator, ConstraintCommitment)

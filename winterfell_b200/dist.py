@@ -282,7 +282,7 @@ def prove_fib_sharded(ctx, comm, local_trace, k, log_n, results, opts, out_buf=N
         raise comm.error
     if stats is not None:
         stats.update({"bytes_sent": st[0], "exchange_ms": st[1], "collectives": st[2], "small_collective_ms": st[3], "sharded_fri_layers": st[4],
-                      "bytes_overlapped": st[5]})
+                      "bytes_overlapped": st[5], "peer_push": st[6]})
     return buf[: ln.value].tobytes()
 
 
@@ -365,8 +365,15 @@ def bench_sharded(ctx, stream, cfg, steps, warmup, configs, proof_opts, flush, c
             "wall_ms": wall, "clocks": sampler.summary(),
             "parallelism": f"one proof sharded over {world} GPUs: column-sharded interpolate + LDE, exchange into row shards, row-sharded "
                            "commitments / constraints / DEEP / first FRI layers, subtree-root all-gathers (winterfell_b200/dist.py)",
-            "comm": {"limiting_collective": "exchange (NCCL send/recv all-to-all: column shards -> row shards of the trace LDE), issued per coset on the "
-                                             "communicator's stream and overlapped with the extension of the next coset",
+            "comm": {"limiting_collective": ("column shards -> row shards of the trace LDE fused into the LDE: the last pass of every coset's transform stores each "
+                                             "row (and the halo rows) straight into its owner's shard, peer memory mapped through CUDA IPC, over NVLink; closed "
+                                             "by one host barrier; no NCCL call on the data path"
+                                             if res_stats.get("peer_push") == 2 else
+                                             "column shards -> row shards of the trace LDE, per coset, as peer copies (copy engines over NVLink) into the other "
+                                             "ranks' buffers mapped through CUDA IPC, overlapped with the extension of the next coset; closed by one host barrier"
+                                             if res_stats.get("peer_push") else
+                                             "exchange (NCCL send/recv all-to-all: column shards -> row shards of the trace LDE), issued per coset on the "
+                                             "communicator's stream and overlapped with the extension of the next coset"),
                      "overlapped_bytes_sent_per_rank": int(res_stats.get("bytes_overlapped", 0)),
                      "exposed_trace_exchange_ms_rank0": round(bd_ex, 3),
                      "effective_GBps_per_rank_if_not_overlapped": round(res_stats.get("bytes_overlapped", 0) / max(bd_ex, 1e-9) / 1e6, 1),
