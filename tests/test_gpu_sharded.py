@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(world, k, log_n, ext, hash_id=0, resident=0, fri_min_log=None):
+def _run(world, k, log_n, ext, hash_id=0, resident=0, fri_min_log=None, extra_env=None):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
@@ -20,6 +20,7 @@ def _run(world, k, log_n, ext, hash_id=0, resident=0, fri_min_log=None):
     env = dict(os.environ)
     if fri_min_log is not None:
         env["WF_SHARD_FRI_MIN_LOG"] = str(fri_min_log)
+    env.update(extra_env or {})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "sharded_worker.py"), str(k), str(log_n), str(ext), str(hash_id), str(resident)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
@@ -46,3 +47,12 @@ def test_sharded_proof_rp64():
 def test_sharded_proof_with_partitions():
     # ProofOptions::with_partitions(2, 8) (hash_id | 2 << 8 | 8 << 16): the row shards hash column partitions like one GPU does
     _run(2, 8, 12, 3, hash_id=0 | (2 << 8) | (8 << 16), fri_min_log=6)
+
+
+@pytest.mark.parametrize("env", [{"WF_FUSED_SCATTER": "1"}, {"WF_PEER_PUSH": "0"}])
+def test_sharded_proof_other_transports(env):
+    # the trace exchange has three transports: copy-engine pushes into mapped staging buffers (default, the tests above), the
+    # LDE's last pass storing rows straight into the owners' shards (WF_FUSED_SCATTER=1), and the communicator's exchange
+    # (WF_PEER_PUSH=0: what a multi-node run would use) — same proof bytes
+    _run(2, 8, 12, 3, fri_min_log=6, extra_env=env)
+    _run(4, 16, 13, 1, resident=1, extra_env=env)

@@ -1522,14 +1522,18 @@ int prove_fib_sharded(wf_ctx* ctx, const wf_comm* cm, const uint64_t* const* loc
     CKI(wf_mat_alloc(ctx, rows_per + b, c, &shard));
     shard->m.rows = rows_per;  // seg_stride stays (rows_per + b) * 8: rows [rows_per, rows_per + b) are the halo
     const size_t sstride = shard->m.seg_stride;
-    // Preferred transport — the exchange fused into the LDE: every rank maps the others' row shards (CUDA IPC) and the last
+    // Transport 1 — the exchange fused into the LDE: every rank maps the others' row shards (CUDA IPC) and the last
     // pass of every coset's transform writes each row straight to its owner (and the first rows of a range also into the halo
     // of the rank before it) with stores over NVLink: natural order at the destination, no staging buffer, no copy kernel,
     // no interleaving pass, nothing left to overlap. Closed by one stream synchronisation + host barrier.
     std::vector<void*> peer_shard;
     u32 log_nj = 0;
     while (((size_t)1 << log_nj) < nj) log_nj++;
-    const bool scat = G <= 8 && log_n <= 22 && sc.map_peers(shard->m.base, peer_shard) == WF_OK;
+    // (measured at 2 GPUs, cfg3: the remote 64-byte stores stall the pass by about what the transfer costs — 37.4 ms LDE + 0.6 ms
+    // exposed against 30.3 + 5.6 with copy-engine pushes and 28.1 + 8.1 with a blocking NCCL all-to-all — so the fused form is
+    // opt-in, WF_FUSED_SCATTER=1, and the copy-engine push below is the default)
+    const char* fused_env = getenv("WF_FUSED_SCATTER");
+    const bool scat = fused_env && atoi(fused_env) != 0 && G <= 8 && log_n <= 22 && sc.map_peers(shard->m.base, peer_shard) == WF_OK;
     bool push = false;
     if (scat) {
         LdeScatter sct;
