@@ -400,9 +400,11 @@ class ProverChannel {
         : air(a), options(o), log_n(log_n_), public_coin(o.hash_id, context_elements(a, o, log_n_)) {}
 
     int d() const { return (int)options.field_extension; }
-    void commit_trace(const u8 root[32]) { commitments.write_bytes(root, 32); public_coin.reseed(root); }        // :88-91
-    void commit_constraints(const u8 root[32]) { commitments.write_bytes(root, 32); public_coin.reseed(root); }  // :94-97
-    void commit_fri_layer(const u8 root[32]) { commitments.write_bytes(root, 32); public_coin.reseed(root); }    // :215-219
+    // digests cross the ABI in 32-byte slots; they serialize to the hasher's digest size (24 bytes for Blake3_192)
+    size_t digest_bytes() const { return options.hash_id == WF_HASH_BLAKE3_192 ? 24 : 32; }
+    void commit_trace(const u8 root[32]) { commitments.write_bytes(root, digest_bytes()); public_coin.reseed(root); }        // :88-91
+    void commit_constraints(const u8 root[32]) { commitments.write_bytes(root, digest_bytes()); public_coin.reseed(root); }  // :94-97
+    void commit_fri_layer(const u8 root[32]) { commitments.write_bytes(root, digest_bytes()); public_coin.reseed(root); }    // :215-219
     Elem draw_fri_alpha() { return public_coin.draw(d()); }                                                      // :222-224
     std::vector<Elem> get_aux_rand_elements() {  // Air::get_aux_rand_elements (air/src/air/mod.rs:292-306)
         std::vector<Elem> r;

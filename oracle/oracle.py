@@ -16,6 +16,7 @@ P = 0xFFFFFFFF00000001
 BLAKE3 = 0
 RP64 = 1
 RPJIVE = 2
+BLAKE3_192 = 3
 
 
 def build(force=False):

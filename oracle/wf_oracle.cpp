@@ -600,18 +600,31 @@ static void rpj_merge_with_int(const u8 seed[32], u64 value, u8 out[32]) {  // m
 // =================================================================================================
 // HASHER DISPATCH  (crypto/src/hash/mod.rs:31-64)
 // =================================================================================================
+// Digests live in 32-byte slots everywhere in this file; Blake3_192 (blake/mod.rs:73-123) keeps the first 24 bytes of the BLAKE3
+// output (ByteDigest<24>; the slot's last 8 bytes are zero, as ByteDigest::as_bytes pads them) and hashes / serializes 24
+// bytes per digest.
+static size_t digest_len(int h) { return h == WFO_HASH_BLAKE3_192 ? 24 : 32; }
+static void b3_192(const u8* data, size_t len, u8 out[32]) { blake3_hash(data, len, out); memset(out + 24, 0, 8); }
 static void hash_elements(int h, const u64* e, size_t n, u8 out[32]) {
     if (h == WFO_HASH_BLAKE3_256) blake3_hash((const u8*)e, n * 8, out);  // blake/mod.rs:52-65: canonical LE bytes
+    else if (h == WFO_HASH_BLAKE3_192) b3_192((const u8*)e, n * 8, out);  // :108-115
     else if (h == WFO_HASH_RP64_256) rp_hash_elements(e, n, out);
     else rpj_hash_elements(e, n, out);
 }
+static void merge_many(int h, const u8* dg, size_t n, u8 out[32]);
 static void merge(int h, const u8 two[64], u8 out[32]) {
     if (h == WFO_HASH_BLAKE3_256) blake3_hash(two, 64, out);  // blake/mod.rs:33
+    else if (h == WFO_HASH_BLAKE3_192) merge_many(h, two, 2, out);  // :85-88: BLAKE3 of the 48 digest bytes
     else if (h == WFO_HASH_RP64_256) rp_merge(two, out);
     else rpj_merge(two, out);
 }
 static void merge_many(int h, const u8* dg, size_t n, u8 out[32]) {
     if (h == WFO_HASH_BLAKE3_256) blake3_hash(dg, n * 32, out);  // blake/mod.rs:37
+    else if (h == WFO_HASH_BLAKE3_192) {                          // :90-93 digests_as_bytes: 24 bytes each, back to back
+        std::vector<u8> cat(n * 24);
+        for (size_t i = 0; i < n; i++) memcpy(cat.data() + 24 * i, dg + 32 * i, 24);
+        b3_192(cat.data(), cat.size(), out);
+    }
     else if (h == WFO_HASH_RP64_256) rp_hash_elements((const u64*)dg, n * 4, out);  // rp64_256/mod.rs:194
     else rpj_hash_elements((const u64*)dg, n * 4, out);                             // rp64_256_jive/mod.rs:198-200
 }
@@ -621,6 +634,11 @@ static void merge_with_int(int h, const u8 seed[32], u64 value, u8 out[32]) {
         memcpy(data, seed, 32);
         memcpy(data + 32, &value, 8);
         blake3_hash(data, 40, out);
+    } else if (h == WFO_HASH_BLAKE3_192) {  // :95-102: 24 seed bytes + 8 value bytes
+        u8 data[32];
+        memcpy(data, seed, 24);
+        memcpy(data + 24, &value, 8);
+        b3_192(data, 32, out);
     } else if (h == WFO_HASH_RP64_256) rp_merge_with_int(seed, value, out);
     else rpj_merge_with_int(seed, value, out);
 }
@@ -673,7 +691,7 @@ static void write_vint64(std::vector<u8>& o, u64 v) {  // utils/core/src/serde/b
 }
 
 static long merkle_prove_batch(const u8* leaves, const u8* nodes, size_t nleaves, const u64* indexes,
-                               size_t k, u8* leaves_out, u8* out, size_t cap) {
+                               size_t k, u8* leaves_out, u8* out, size_t cap, size_t dlen = 32) {
     // mod.rs:217-272
     if (k == 0) return -1;
     size_t depth = (size_t)__builtin_ctzll(nleaves);
@@ -715,7 +733,7 @@ static long merkle_prove_batch(const u8* leaves, const u8* nodes, size_t nleaves
     write_vint64(o, pn.size());
     for (auto& v : pn) {
         write_vint64(o, v.size());
-        for (const u8* dg : v) o.insert(o.end(), dg, dg + 32);
+        for (const u8* dg : v) o.insert(o.end(), dg, dg + dlen);   // digests serialize to their own length (ByteDigest<N>)
     }
     if (o.size() > cap) return -1;
     memcpy(out, o.data(), o.size());

@@ -439,7 +439,7 @@ static void queries_for(const Field& F, int h, const u64* rows_mat, size_t row_w
     Writer vals;
     for (u64 p : pos) vals.bytes(rows_mat + p * row_words, row_words * 8);
     std::vector<u8> lv(pos.size() * 32), pr(64 + pos.size() * 40 * 33);
-    long pl = merkle_prove_batch(leaves.data(), nodes.data(), N, pos.data(), pos.size(), lv.data(), pr.data(), pr.size());
+    long pl = merkle_prove_batch(leaves.data(), nodes.data(), N, pos.data(), pos.size(), lv.data(), pr.data(), pr.size(), digest_len(h));
     if (pl < 0) abort();
     (void)h;
     w.usize(vals.b.size()); w.bytes(vals.b.data(), vals.b.size());
@@ -494,7 +494,7 @@ static std::vector<u8> prove_fib(const FibAir& air_in, const u64* trace /*[w][n]
     std::vector<u8> t_leaves(N * 32), t_nodes(N * 32);
     hash_rows(h, lde.data(), N, c, o.part_words(c, 1), t_leaves.data());  // row_matrix.rs:191 with E = BaseField
     merkle_nodes(h, t_leaves.data(), N, t_nodes.data());
-    commitments.bytes(t_nodes.data() + 32, 32);
+    commitments.bytes(t_nodes.data() + 32, digest_len(h));
     coin.reseed(t_nodes.data() + 32);
 
     // 1b. auxiliary segment (lib.rs:309-349, air/src/air/mod.rs:292-306, trace_lde/default/mod.rs:140-166)
@@ -514,7 +514,7 @@ static std::vector<u8> prove_fib(const FibAir& air_in, const u64* trace /*[w][n]
         a_leaves.resize(N * 32); a_nodes.resize(N * 32);
         hash_rows(h, alde.data(), N, aw * d, o.part_words(aw, d), a_leaves.data());
         merkle_nodes(h, a_leaves.data(), N, a_nodes.data());
-        commitments.bytes(a_nodes.data() + 32, 32);
+        commitments.bytes(a_nodes.data() + 32, digest_len(h));
         coin.reseed(a_nodes.data() + 32);
     }
 
@@ -617,7 +617,7 @@ static std::vector<u8> prove_fib(const FibAir& air_in, const u64* trace /*[w][n]
     std::vector<u8> c_leaves(N * 32), c_nodes(N * 32);
     hash_rows(h, clde.data(), N, kc * d, o.part_words(kc, d), c_leaves.data());
     merkle_nodes(h, c_leaves.data(), N, c_nodes.data());
-    commitments.bytes(c_nodes.data() + 32, 32);
+    commitments.bytes(c_nodes.data() + 32, digest_len(h));
     coin.reseed(c_nodes.data() + 32);
 
     tm.mark("composition_commit");
@@ -722,7 +722,7 @@ static std::vector<u8> prove_fib(const FibAir& air_in, const u64* trace /*[w][n]
         L.leaves.resize(L.rows * 32); L.nodes.resize(L.rows * 32);
         hash_rows(h, L.tv.data(), L.rows, nf * d, nf * d, L.leaves.data());
         merkle_nodes(h, L.leaves.data(), L.rows, L.nodes.data());
-        commitments.bytes(L.nodes.data() + 32, 32);
+        commitments.bytes(L.nodes.data() + 32, digest_len(h));
         coin.reseed(L.nodes.data() + 32);
         EE alpha = coin.draw(F);
         std::vector<u64> nxt(L.rows * d);
@@ -740,7 +740,7 @@ static std::vector<u8> prove_fib(const FibAir& air_in, const u64* trace /*[w][n]
         for (size_t i = 0; i < rs; i++) for (int k = 0; k < d; k++) remainder[i * d + k] = cur[(rs - 1 - i) * d + k];
         u8 dg[32];
         hash_elements(h, remainder.data(), remainder.size(), dg);
-        commitments.bytes(dg, 32);
+        commitments.bytes(dg, digest_len(h));
         coin.reseed(dg);
     }
     tm.mark("fri_layers");
@@ -776,7 +776,7 @@ static std::vector<u8> prove_fib(const FibAir& air_in, const u64* trace /*[w][n]
             Writer vals;
             for (u64 q : p) vals.bytes(&L.tv[q * nf * d], nf * d * 8);
             std::vector<u8> lv(p.size() * 32), pr(64 + p.size() * 40 * 33);
-            long pl = merkle_prove_batch(L.leaves.data(), L.nodes.data(), L.rows, p.data(), p.size(), lv.data(), pr.data(), pr.size());
+            long pl = merkle_prove_batch(L.leaves.data(), L.nodes.data(), L.rows, p.data(), p.size(), lv.data(), pr.data(), pr.size(), digest_len(h));
             if (pl < 0) abort();
             w.u32_((u32)vals.b.size()); w.bytes(vals.b.data(), vals.b.size());
             w.u32_((u32)pl); w.bytes(pr.data(), (size_t)pl);
@@ -811,7 +811,7 @@ struct Reader {
 };
 
 struct BatchProof { u8 depth; std::vector<std::vector<std::array<u8, 32>>> nodes; };
-static bool read_batch_proof(Reader& r, BatchProof& bp) {
+static bool read_batch_proof(Reader& r, BatchProof& bp, size_t dlen = 32) {
     bp.depth = r.u8_();
     u64 nv = r.usize();
     if (!r.ok || nv > 100000) return false;
@@ -820,7 +820,7 @@ static bool read_batch_proof(Reader& r, BatchProof& bp) {
         u64 ln = r.usize();
         if (!r.ok || ln > 64) return false;
         v.resize(ln);
-        for (auto& dg : v) { const u8* q = r.take(32); if (!q) return false; memcpy(dg.data(), q, 32); }
+        for (auto& dg : v) { const u8* q = r.take(dlen); if (!q) return false; dg.fill(0); memcpy(dg.data(), q, dlen); }
     }
     return r.ok;
 }
@@ -929,7 +929,11 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
     if (!r.ok) return V_MALFORMED;
     size_t nlayers = 0;
     { size_t dom = N, max_rem = (size_t)(o.rem_max_deg + 1) * o.blowup; while (dom > max_rem) { dom /= nf; nlayers++; } }
-    if (clen != 32 * (nseg + 1 + nlayers + 1)) return V_MALFORMED;
+    const size_t dl = digest_len(h), ncm = nseg + 1 + nlayers + 1;
+    if (clen != dl * ncm) return V_MALFORMED;
+    std::vector<u8> cm32(32 * ncm, 0);   // the commitments in 32-byte slots (zero padded, as ByteDigest::as_bytes)
+    for (size_t i = 0; i < ncm; i++) memcpy(cm32.data() + 32 * i, cm + dl * i, dl);
+    cm = cm32.data();
     const u8* trace_root = cm; const u8* aux_root = cm + 32;  // air/src/proof/commitments.rs:66-100
     const u8* cons_root = cm + 32 * nseg; const u8* fri_roots = cm + 32 * (nseg + 1);
     // queries
@@ -1040,7 +1044,7 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
         for (size_t i = 0; i < pos.size(); i++) hash_rows(h, (const u64*)(vals.data() + i * row_words * 8), 1, row_words, part, lv[i].data());
         Reader pr_r{pr.data(), pr.size()};
         BatchProof bp;
-        if (!read_batch_proof(pr_r, bp) || pr_r.pos != pr.size() || ((size_t)1 << bp.depth) != N) return false;
+        if (!read_batch_proof(pr_r, bp, digest_len(h)) || pr_r.pos != pr.size() || ((size_t)1 << bp.depth) != N) return false;
         u8 got[32];
         return batch_root(h, bp, pos, lv, got) && !memcmp(got, root, 32);
     };
@@ -1088,7 +1092,7 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
             for (size_t i = 0; i < fpos.size(); i++) hash_elements(h, (const u64*)(vals.data() + i * nf * d * 8), nf * d, lv[i].data());
             Reader pr_r{fp[depth].data(), fp[depth].size()};
             BatchProof bp;
-            if (!read_batch_proof(pr_r, bp) || pr_r.pos != fp[depth].size() || ((size_t)1 << bp.depth) != dom / nf) return V_FRI_LAYER;
+            if (!read_batch_proof(pr_r, bp, digest_len(h)) || pr_r.pos != fp[depth].size() || ((size_t)1 << bp.depth) != dom / nf) return V_FRI_LAYER;
             u8 got[32];
             if (!batch_root(h, bp, fpos, lv, got) || memcmp(got, fri_roots + 32 * depth, 32)) return V_FRI_LAYER;
             // get_query_values
@@ -1282,7 +1286,7 @@ int wfo_merkle_verify_batch(int hash_id, const uint8_t root[32], const uint64_t*
                             const uint8_t* proof, size_t proof_len) {
     Reader r{proof, proof_len};
     BatchProof bp;
-    if (!read_batch_proof(r, bp) || r.pos != proof_len) return 1;
+    if (!read_batch_proof(r, bp, digest_len(hash_id)) || r.pos != proof_len) return 1;
     std::vector<u64> idx(indexes, indexes + k);
     std::vector<std::array<u8, 32>> lv(k);
     for (size_t i = 0; i < k; i++) memcpy(lv[i].data(), leaves + 32 * i, 32);

@@ -264,6 +264,30 @@ def test_rpjive_round_trip_and_tamper(oracle):
         assert oracle.verify_fib(bytes(t), k, res, oracle.RPJIVE) != 0
 
 
+def test_blake3_192_against_the_spec(oracle):
+    # Blake3_192 (crypto/src/hash/blake/mod.rs:73-123): the first 24 bytes of BLAKE3 over the element bytes / the 48 digest
+    # bytes / seed bytes + u64; pinned to the public BLAKE3 spec through the Python package, digests in zero-padded slots
+    import blake3 as b3
+    H = oracle.BLAKE3_192
+    e = oracle.rand_elems(13, 5)
+    h = oracle.hash_elements(H, e)
+    assert h[:24] == b3.blake3(e.tobytes()).digest()[:24] and h[24:] == bytes(8)
+    a, b = oracle.hash_elements(H, e[:4]), oracle.hash_elements(H, e[4:9])
+    assert oracle.merge(H, a, b) == b3.blake3(a[:24] + b[:24]).digest()[:24] + bytes(8)
+    assert oracle.merge_many(H, a + b + a) == b3.blake3(a[:24] + b[:24] + a[:24]).digest()[:24] + bytes(8)
+    for v in (0, 12345, 2**64 - 1):
+        assert oracle.merge_with_int(H, a, v) == b3.blake3(a[:24] + v.to_bytes(8, "little")).digest()[:24] + bytes(8)
+    trace, res = oracle.build_fib_trace(2, 128)
+    for ext in (1, 3):
+        opts = oracle.make_opts(ext=ext, hash_id=H, grinding=3, folding=4, rem_max_deg=7)
+        proof = oracle.prove_fib(trace, res, opts)
+        assert oracle.verify_fib(proof, 2, res, H) == 0 and oracle.verify_fib(proof, 2, res, oracle.BLAKE3) != 0
+        assert len(proof) < len(oracle.prove_fib(trace, res, oracle.make_opts(ext=ext, hash_id=0, grinding=3, folding=4, rem_max_deg=7)))
+        t = bytearray(proof)
+        t[len(t) // 2] ^= 1
+        assert oracle.verify_fib(bytes(t), 2, res, H) != 0
+
+
 # ---- Merkle: crypto/src/merkle/tests.rs:14-84 ----
 LEAVES4 = [
     [166, 168, 47, 140, 153, 86, 156, 86, 226, 229, 149, 76, 70, 132, 209, 109, 166, 193, 113, 197, 42, 116, 170, 144, 74, 104, 29, 110, 220, 49, 224, 123],

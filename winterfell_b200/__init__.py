@@ -17,6 +17,7 @@ P = 0xFFFFFFFF00000001
 HASH_BLAKE3_256 = 0
 HASH_RP64_256 = 1
 HASH_RPJIVE64_256 = 2
+HASH_BLAKE3_192 = 3
 
 WF_OK = 0
 

@@ -94,6 +94,31 @@ GL_HD void b3_hash64(const u32 m[16], u32 out[8], u32 one = 1) {
     b3_iv(out);
     b3_compress(out, m, 0, 64, B3_CHUNK_START | B3_CHUNK_END | B3_ROOT, one);
 }
+// merge of two digests of DW 32-bit words each (8: Blake3_256, blake/mod.rs:33; 6: Blake3_192, :85-88 — the 48 digest bytes
+// back to back), result truncated to DW words, the rest of the slot zero
+template <int DW>
+GL_HD void b3_merge_words(const u32 a[8], const u32 b[8], u32 out[8], u32 one = 1) {
+    u32 m[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) m[k] = k < DW ? a[k] : (k < 2 * DW ? b[k - DW] : 0);
+    b3_iv(out);
+    b3_compress(out, m, 0, 8 * DW, B3_CHUNK_START | B3_CHUNK_END | B3_ROOT, one);
+#pragma unroll
+    for (int k = DW; k < 8; k++) out[k] = 0;
+}
+// merge_with_int (blake/mod.rs:41-46, :95-102): seed digest bytes then the u64 little-endian
+template <int DW>
+GL_HD void b3_merge_with_int_words(const u32 seed[8], u64 value, u32 out[8], u32 one = 1) {
+    u32 m[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) m[k] = k < DW ? seed[k] : 0;
+    m[DW] = (u32)value;
+    m[DW + 1] = (u32)(value >> 32);
+    b3_iv(out);
+    b3_compress(out, m, 0, 4 * DW + 8, B3_CHUNK_START | B3_CHUNK_END | B3_ROOT, one);
+#pragma unroll
+    for (int k = DW; k < 8; k++) out[k] = 0;
+}
 // runtime 1 for the device kernels (see B3_G)
 #ifdef __CUDACC__
 __device__ __forceinline__ u32 b3_runtime_one() { return blockDim.y; }

@@ -940,7 +940,7 @@ void wf_open_finish(const OpenPlan& pl, const uint8_t* got, uint8_t* leaves_out,
     proof.usize(pl.vec_slots.size());
     for (auto& v : pl.vec_slots) {
         proof.usize(v.size());
-        for (size_t s : v) proof.bytes(got + s * 32, 32);
+        for (size_t s : v) proof.bytes(got + s * 32, pl.digest_bytes);   // 32-byte slots, ByteDigest<N> writes N bytes
     }
 }
 
@@ -963,6 +963,7 @@ int GatherBatch::add_opening(wf_ctx* ctx, const wf_tree* t, const std::vector<u6
     digs.emplace_back();
     digs.back().t = t;
     CKI(wf_open_plan(ctx, t->nleaves, pos.data(), pos.size(), digs.back().plan));
+    digs.back().plan.digest_bytes = WF_DIGEST_BYTES(t->hash_id);
     digs.back().idx = digs.back().plan.want;
     *id = digs.size() - 1;
     return WF_OK;
@@ -973,6 +974,7 @@ int GatherBatch::add_opening_sharded(wf_ctx* ctx, const wf_tree* t, size_t n_glo
     DigJob& j = digs.back();
     j.t = t;
     CKI(wf_open_plan(ctx, n_global, pos.data(), pos.size(), j.plan));
+    if (t) j.plan.digest_bytes = WF_DIGEST_BYTES(t->hash_id);   // (the host-only planning export passes no tree)
     const size_t n_local = n_global / (size_t)world;
     u32 log_w = 0;
     while ((1 << log_w) < world) log_w++;

@@ -80,7 +80,7 @@ __device__ void blake3_row(const RowSrc& m, size_t row, u32 out[8], u32 first = 
 
 // fast path: one 8-column segment row == exactly one 64-byte BLAKE3 block
 __global__ void __launch_bounds__(256) hash_rows_blake3_w8c8_kernel(const u64* __restrict__ base, size_t nrows,
-                                                                    uint4* __restrict__ digests) {
+                                                                    uint4* __restrict__ digests, u32 dw /*digest words kept: 8 | 6*/) {
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nrows) return;
     const uint4* src = reinterpret_cast<const uint4*>(base + row * 8);
@@ -92,15 +92,17 @@ __global__ void __launch_bounds__(256) hash_rows_blake3_w8c8_kernel(const u64* _
     }
     u32 cv[8];
     b3_hash64(msg, cv, b3_runtime_one());
+    if (dw == 6) { cv[6] = 0; cv[7] = 0; }   // Blake3_192: ByteDigest<24>
     digests[2 * row] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
     digests[2 * row + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
 
-__global__ void __launch_bounds__(256) hash_rows_blake3_kernel(RowSrc m, size_t nrows, uint4* __restrict__ digests) {
+__global__ void __launch_bounds__(256) hash_rows_blake3_kernel(RowSrc m, size_t nrows, uint4* __restrict__ digests, u32 dw) {
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nrows) return;
     u32 cv[8];
     blake3_row(m, row, cv);
+    if (dw == 6) { cv[6] = 0; cv[7] = 0; }
     digests[2 * row] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
     digests[2 * row + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
@@ -146,24 +148,26 @@ __global__ void __launch_bounds__(128) hash_rows_partitioned_kernel(int hash_id,
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nrows) return;
     const u32 np = (m.cols + psize - 1) / psize;  // <= 16
-    if (hash_id == WF_HASH_BLAKE3_256) {
+    if (WF_HASH_IS_BLAKE3(hash_id)) {
+        const u32 dw = WF_DIGEST_WORDS32(hash_id);
         u32 parts[16][8];
         for (u32 j = 0; j < np; j++) blake3_row(m, row, parts[j], j * psize, psize);
-        // BLAKE3 of np*32 bytes (<= 512: one chunk)
+        // merge_many = BLAKE3 of the np digests back to back, dw words each (<= 512 bytes: one chunk)
         u32 cv[8];
         b3_iv(cv);
-        const u32 nblk = (np + 1) / 2;
+        const u32 total = np * dw, nblk = (total + 15) / 16;
         for (u32 b = 0; b < nblk; b++) {
             u32 msg[16];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                msg[k] = parts[2 * b][k];
-                msg[8 + k] = (2 * b + 1 < np) ? parts[2 * b + 1][k] : 0;
+            for (int k = 0; k < 16; k++) {
+                const u32 t = b * 16 + k;
+                msg[k] = t < total ? parts[t / dw][t % dw] : 0;
             }
-            u32 bl = (2 * b + 1 < np) ? 64 : 32;
+            u32 bl = min(64u, (total - b * 16) * 4);
             u32 fl = (b == 0 ? B3_CHUNK_START : 0) | (b == nblk - 1 ? (B3_CHUNK_END | B3_ROOT) : 0);
             b3_compress(cv, msg, 0, bl, fl, b3_runtime_one());
         }
+        if (dw == 6) { cv[6] = 0; cv[7] = 0; }
 #pragma unroll
         for (int k = 0; k < 4; k++) digests[row * 4 + k] = (u64)cv[2 * k] | ((u64)cv[2 * k + 1] << 32);
     } else if (hash_id == WF_HASH_RP64_256) {
@@ -174,18 +178,20 @@ __global__ void __launch_bounds__(128) hash_rows_partitioned_kernel(int hash_id,
 }
 
 // ---- Merkle levels ----------------------------------------------------------------------------
+template <int DW>
 __global__ void __launch_bounds__(256) merkle_level_blake3_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
                                                                   size_t count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    u32 msg[16];
+    u32 w[16];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         uint4 v = __ldg(in + 4 * i + k);
-        msg[4 * k] = v.x; msg[4 * k + 1] = v.y; msg[4 * k + 2] = v.z; msg[4 * k + 3] = v.w;
+        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
     }
     u32 cv[8];
-    b3_hash64(msg, cv, b3_runtime_one());
+    if (DW == 8) b3_hash64(w, cv, b3_runtime_one());
+    else b3_merge_words<DW>(w, w + 8, cv, b3_runtime_one());
     out[2 * i] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
     out[2 * i + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
@@ -207,11 +213,12 @@ __global__ void __launch_bounds__(128) merkle_level_alg_kernel(const u64* __rest
 // the first level computed (children = `src`, 2m digests); levels stop at `m_stop` (inclusive).
 template <int HASH>
 __device__ __forceinline__ void merge_digests(const u64* a /*8 words: two digests*/, u64* out /*4 words*/) {
-    if (HASH == WF_HASH_BLAKE3_256) {
+    if (WF_HASH_IS_BLAKE3(HASH)) {
         u32 msg[16], cv[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) { msg[2 * k] = (u32)a[k]; msg[2 * k + 1] = (u32)(a[k] >> 32); }
-        b3_hash64(msg, cv, b3_runtime_one());
+        if (HASH == WF_HASH_BLAKE3_256) b3_hash64(msg, cv, b3_runtime_one());
+        else b3_merge_words<6>(msg, msg + 8, cv, b3_runtime_one());
 #pragma unroll
         for (int k = 0; k < 4; k++) out[k] = (u64)cv[2 * k] | ((u64)cv[2 * k + 1] << 32);
     } else {
@@ -265,12 +272,13 @@ cudaError_t commit_hash_rows(int hash_id, const SegMatrix& m, u64* digests, cuda
         hash_rows_partitioned_kernel<<<(unsigned)((m.rows + 127) / 128), 128, 0, st>>>(hash_id, src, m.rows, partition_size, digests);
         return cudaGetLastError();
     }
-    if (hash_id == WF_HASH_BLAKE3_256) {
+    if (WF_HASH_IS_BLAKE3(hash_id)) {
         unsigned blocks = (unsigned)((m.rows + 255) / 256);
+        const u32 dw = WF_DIGEST_WORDS32(hash_id);
         if (m.W == 8 && m.cols == 8)
-            hash_rows_blake3_w8c8_kernel<<<blocks, 256, 0, st>>>(m.base, m.rows, reinterpret_cast<uint4*>(digests));
+            hash_rows_blake3_w8c8_kernel<<<blocks, 256, 0, st>>>(m.base, m.rows, reinterpret_cast<uint4*>(digests), dw);
         else
-            hash_rows_blake3_kernel<<<blocks, 256, 0, st>>>(src, m.rows, reinterpret_cast<uint4*>(digests));
+            hash_rows_blake3_kernel<<<blocks, 256, 0, st>>>(src, m.rows, reinterpret_cast<uint4*>(digests), dw);
     } else {
         unsigned blocks = (unsigned)((m.rows + 127) / 128);
         if (hash_id == WF_HASH_RP64_256) hash_rows_alg_kernel<WF_HASH_RP64_256><<<blocks, 128, 0, st>>>(src, m.rows, digests);
@@ -289,8 +297,11 @@ cudaError_t commit_merkle_nodes(int hash_id, const u64* leaves, size_t nleaves, 
     while (m > (1u << 13)) {
         u64* dst = nodes + m * 4;
         if (hash_id == WF_HASH_BLAKE3_256)
-            merkle_level_blake3_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src),
-                                                                                   reinterpret_cast<uint4*>(dst), m);
+            merkle_level_blake3_kernel<8><<<(unsigned)((m + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src),
+                                                                                      reinterpret_cast<uint4*>(dst), m);
+        else if (hash_id == WF_HASH_BLAKE3_192)
+            merkle_level_blake3_kernel<6><<<(unsigned)((m + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src),
+                                                                                      reinterpret_cast<uint4*>(dst), m);
         else if (hash_id == WF_HASH_RP64_256)
             merkle_level_alg_kernel<WF_HASH_RP64_256><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(src, dst, m);
         else
@@ -301,6 +312,7 @@ cudaError_t commit_merkle_nodes(int hash_id, const u64* leaves, size_t nleaves, 
     for (;;) {
         unsigned blocks = (unsigned)((m + 255) / 256);
         if (hash_id == WF_HASH_BLAKE3_256) merkle_subtree_kernel<WF_HASH_BLAKE3_256><<<blocks, 256, 0, st>>>(src, nodes, m);
+        else if (hash_id == WF_HASH_BLAKE3_192) merkle_subtree_kernel<WF_HASH_BLAKE3_192><<<blocks, 256, 0, st>>>(src, nodes, m);
         else if (hash_id == WF_HASH_RP64_256) merkle_subtree_kernel<WF_HASH_RP64_256><<<blocks, 256, 0, st>>>(src, nodes, m);
         else merkle_subtree_kernel<WF_HASH_RPJIVE64_256><<<blocks, 256, 0, st>>>(src, nodes, m);
         if (m <= 256) break;           // this launch reached the root

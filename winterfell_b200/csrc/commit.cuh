@@ -9,7 +9,13 @@
 #define WF_HASH_BLAKE3_256 0
 #define WF_HASH_RP64_256 1
 #define WF_HASH_RPJIVE64_256 2
-#define WF_HASH_IS_KNOWN(h) ((h) == WF_HASH_BLAKE3_256 || (h) == WF_HASH_RP64_256 || (h) == WF_HASH_RPJIVE64_256)
+#define WF_HASH_BLAKE3_192 3
+#define WF_HASH_IS_KNOWN(h) ((h) >= 0 && (h) <= 3)
+#define WF_HASH_IS_BLAKE3(h) ((h) == WF_HASH_BLAKE3_256 || (h) == WF_HASH_BLAKE3_192)
+// digests occupy 32-byte slots everywhere; Blake3_192 (crypto/src/hash/blake/mod.rs:73-123) keeps and serializes the first 24
+// bytes (the rest of the slot is zero, as ByteDigest::as_bytes pads it)
+#define WF_DIGEST_BYTES(h) ((h) == WF_HASH_BLAKE3_192 ? 24 : 32)
+#define WF_DIGEST_WORDS32(h) ((h) == WF_HASH_BLAKE3_192 ? 6 : 8)
 
 // rows x cols base-field matrix in segment layout (see ntt.cuh):
 // elem(row, col) = base[(col / W) * seg_stride + row * W + col % W]

@@ -168,33 +168,71 @@ __device__ __forceinline__ void generic_constraints_row(const GenEvalParams& p) 
     u64 ex = 1;
     for (u32 k = 0; k < p.num_exempt; k++) ex = gl_mul(ex, gl_sub(x, p.exempt[k]));
     GlExt<D> acc = ext_mul_base(T, gl_mul(p.zt[i & (((size_t)1 << p.log_ce_blowup) - 1)], ex));
-    for (u32 g = 0; g < p.num_groups; g++) {
-        GlExt<D> B = ext_zero<D>();
-        for (u32 e = p.g_off[g]; e < p.g_off[g + 1]; e++) {
-            u64 val = p.e_val[e];
-            if (const u64* tab = p.e_tab[e]) val = tab[(size_t)((u32)(i - p.e_shift[e]) & cemask) * p.e_tstride[e]];
-            B = ext_add(B, ext_mul_base(ld_ext<D>(p.e_cc + (size_t)e * D), gl_sub(WF_MAIN_CUR(p.e_col[e]), val)));
+    // boundary groups, WF_BGRP at a time sharing ONE field inversion (math::batch_inversion, math/src/utils/mod.rs:169; the
+    // divisors are never zero on the coset 7 <w_ce>): an inversion is a 72-multiplication chain, the first version spent more
+    // time in one gl_inv per group and row than in the transition program of a Rescue-sized AIR
+    constexpr u32 WF_BGRP = 4;
+    for (u32 g0 = 0; g0 < p.num_groups; g0 += WF_BGRP) {
+        GlExt<D> Bs[WF_BGRP];
+        u64 den[WF_BGRP], pre[WF_BGRP], run = 1;
+#pragma unroll
+        for (u32 t = 0; t < WF_BGRP; t++) {
+            const u32 g = g0 + t;
+            Bs[t] = ext_zero<D>();
+            den[t] = 1;
+            if (g < p.num_groups) {
+                for (u32 e = p.g_off[g]; e < p.g_off[g + 1]; e++) {
+                    u64 val = p.e_val[e];
+                    if (const u64* tab = p.e_tab[e]) val = tab[(size_t)((u32)(i - p.e_shift[e]) & cemask) * p.e_tstride[e]];
+                    Bs[t] = ext_add(Bs[t], ext_mul_base(ld_ext<D>(p.e_cc + (size_t)e * D), gl_sub(WF_MAIN_CUR(p.e_col[e]), val)));
+                }
+                // x^a = 7^a * w_ce^(i*a mod ce)
+                u32 ia = (u32)(((u64)i * p.g_a[g]) & cemask);
+                u64 wa = p.tw_ce[ia & (half - 1)];
+                if (ia & half) wa = gl_neg(wa);
+                den[t] = gl_sub(gl_mul(wa, p.g_oa[g]), p.g_b[g]);
+            }
+            pre[t] = run;
+            run = gl_mul(run, den[t]);
         }
-        // x^a = 7^a * w_ce^(i*a mod ce)
-        u32 ia = (u32)(((u64)i * p.g_a[g]) & cemask);
-        u64 wa = p.tw_ce[ia & (half - 1)];
-        if (ia & half) wa = gl_neg(wa);
-        u64 den = gl_sub(gl_mul(wa, p.g_oa[g]), p.g_b[g]);
-        acc = ext_add(acc, ext_mul_base(B, gl_inv(den)));
+        run = gl_inv(run);
+#pragma unroll
+        for (int t = WF_BGRP - 1; t >= 0; t--) {
+            const u64 inv = gl_mul(run, pre[t]);
+            run = gl_mul(run, den[t]);
+            acc = ext_add(acc, ext_mul_base(Bs[t], inv));
+        }
     }
     if constexpr (AUX) {  // evaluator/boundary.rs: aux_single_value constraints, values and columns in E
-        for (u32 g = 0; g < p.num_agroups; g++) {
-            GlExt<D> B = ext_zero<D>();
-            for (u32 e = p.ag_off[g]; e < p.ag_off[g + 1]; e++) {
-                GlExt<D> val = ld_ext<D>(p.ae_val + (size_t)e * D);
-                if (const u64* tab = p.ae_tab[e]) val = ld_ext<D>(tab + (size_t)((u32)(i - p.ae_shift[e]) & cemask) * p.ae_tstride[e]);
-                B = ext_add(B, ext_mul(ext_sub(WF_AUX_CUR(p.ae_col[e]), val), ld_ext<D>(p.ae_cc + (size_t)e * D)));
+        for (u32 g0 = 0; g0 < p.num_agroups; g0 += WF_BGRP) {
+            GlExt<D> Bs[WF_BGRP];
+            u64 den[WF_BGRP], pre[WF_BGRP], run = 1;
+#pragma unroll
+            for (u32 t = 0; t < WF_BGRP; t++) {
+                const u32 g = g0 + t;
+                Bs[t] = ext_zero<D>();
+                den[t] = 1;
+                if (g < p.num_agroups) {
+                    for (u32 e = p.ag_off[g]; e < p.ag_off[g + 1]; e++) {
+                        GlExt<D> val = ld_ext<D>(p.ae_val + (size_t)e * D);
+                        if (const u64* tab = p.ae_tab[e]) val = ld_ext<D>(tab + (size_t)((u32)(i - p.ae_shift[e]) & cemask) * p.ae_tstride[e]);
+                        Bs[t] = ext_add(Bs[t], ext_mul(ext_sub(WF_AUX_CUR(p.ae_col[e]), val), ld_ext<D>(p.ae_cc + (size_t)e * D)));
+                    }
+                    u32 ia = (u32)(((u64)i * p.ag_a[g]) & cemask);
+                    u64 wa = p.tw_ce[ia & (half - 1)];
+                    if (ia & half) wa = gl_neg(wa);
+                    den[t] = gl_sub(gl_mul(wa, p.ag_oa[g]), p.ag_b[g]);
+                }
+                pre[t] = run;
+                run = gl_mul(run, den[t]);
             }
-            u32 ia = (u32)(((u64)i * p.ag_a[g]) & cemask);
-            u64 wa = p.tw_ce[ia & (half - 1)];
-            if (ia & half) wa = gl_neg(wa);
-            u64 den = gl_sub(gl_mul(wa, p.ag_oa[g]), p.ag_b[g]);
-            acc = ext_add(acc, ext_mul_base(B, gl_inv(den)));
+            run = gl_inv(run);
+#pragma unroll
+            for (int t = WF_BGRP - 1; t >= 0; t--) {
+                const u64 inv = gl_mul(run, pre[t]);
+                run = gl_mul(run, den[t]);
+                acc = ext_add(acc, ext_mul_base(Bs[t], inv));
+            }
         }
     }
     u64* o = p.out.base + i * p.out.W;

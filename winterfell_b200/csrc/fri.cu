@@ -8,7 +8,7 @@
 #include "alg_hash.cuh"
 
 __global__ void __launch_bounds__(256) fri_hash_blake3_kernel(const u64* __restrict__ ev, size_t m, int d, int ld, int nf,
-                                                              uint4* __restrict__ digests) {
+                                                              uint4* __restrict__ digests, u32 dw) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const u32 ne = (u32)(nf * d);       // <= 48 elements: a single chunk
@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) fri_hash_blake3_kernel(const u64* __restr
         u32 fl = (b == 0 ? B3_CHUNK_START : 0) | (b == nblk - 1 ? (B3_CHUNK_END | B3_ROOT) : 0);
         b3_compress(cv, msg, 0, bl, fl, b3_runtime_one());
     }
+    if (dw == 6) { cv[6] = 0; cv[7] = 0; }
     digests[2 * i] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
     digests[2 * i + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
@@ -109,9 +110,9 @@ __global__ void __launch_bounds__(256) fri_fold_kernel(const u64* __restrict__ e
 cudaError_t fri_hash_layer(int hash_id, const u64* evals, size_t len, int d, int ld, int nf, u64* digests,
                            cudaStream_t st) {
     size_t m = len / nf;
-    if (hash_id == WF_HASH_BLAKE3_256)
+    if (WF_HASH_IS_BLAKE3(hash_id))
         fri_hash_blake3_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(evals, m, d, ld, nf,
-                                                                            reinterpret_cast<uint4*>(digests));
+                                                                            reinterpret_cast<uint4*>(digests), WF_DIGEST_WORDS32(hash_id));
     else if (hash_id == WF_HASH_RP64_256)
         fri_hash_alg_kernel<WF_HASH_RP64_256><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(evals, m, d, ld, nf, digests);
     else
@@ -157,12 +158,11 @@ cudaError_t fri_fold_layer(const u64* evals, size_t len, int d, int ld, int nf, 
 // its own coin afterwards and checks that it drew the same alphas.
 template <int HASH>
 __device__ __forceinline__ void coin_merge(const u64 a[4], const u64 b[4], u64 out[4]) {
-    if (HASH == WF_HASH_BLAKE3_256) {
-        u32 m[16], cv[8];
+    if (WF_HASH_IS_BLAKE3(HASH)) {
+        u32 wa[8], wb[8], cv[8];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { m[2 * i] = (u32)a[i]; m[2 * i + 1] = (u32)(a[i] >> 32); m[8 + 2 * i] = (u32)b[i]; m[9 + 2 * i] = (u32)(b[i] >> 32); }
-        b3_iv(cv);
-        b3_compress(cv, m, 0, 64, B3_CHUNK_START | B3_CHUNK_END | B3_ROOT);
+        for (int i = 0; i < 4; i++) { wa[2 * i] = (u32)a[i]; wa[2 * i + 1] = (u32)(a[i] >> 32); wb[2 * i] = (u32)b[i]; wb[2 * i + 1] = (u32)(b[i] >> 32); }
+        b3_merge_words<WF_DIGEST_WORDS32(HASH)>(wa, wb, cv);
 #pragma unroll
         for (int i = 0; i < 4; i++) out[i] = (u64)cv[2 * i] | ((u64)cv[2 * i + 1] << 32);
     } else {
@@ -174,15 +174,11 @@ __device__ __forceinline__ void coin_merge(const u64 a[4], const u64 b[4], u64 o
 }
 template <int HASH>
 __device__ __forceinline__ void coin_merge_with_int(const u64 seed[4], u64 value, u64 out[4]) {
-    if (HASH == WF_HASH_BLAKE3_256) {  // blake/mod.rs:41-46
-        u32 m[16], cv[8];
+    if (WF_HASH_IS_BLAKE3(HASH)) {  // blake/mod.rs:41-46, :95-102
+        u32 ws[8], cv[8];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { m[2 * i] = (u32)seed[i]; m[2 * i + 1] = (u32)(seed[i] >> 32); }
-        m[8] = (u32)value; m[9] = (u32)(value >> 32);
-#pragma unroll
-        for (int i = 10; i < 16; i++) m[i] = 0;
-        b3_iv(cv);
-        b3_compress(cv, m, 0, 40, B3_CHUNK_START | B3_CHUNK_END | B3_ROOT);
+        for (int i = 0; i < 4; i++) { ws[2 * i] = (u32)seed[i]; ws[2 * i + 1] = (u32)(seed[i] >> 32); }
+        b3_merge_with_int_words<WF_DIGEST_WORDS32(HASH)>(ws, value, cv);
 #pragma unroll
         for (int i = 0; i < 4; i++) out[i] = (u64)cv[2 * i] | ((u64)cv[2 * i + 1] << 32);
     } else {  // rp64_256/mod.rs:198-218, rp64_256_jive/mod.rs:206-229
@@ -211,6 +207,7 @@ __global__ void fri_coin_kernel(u64* state, const u64* root, int d, u64* alpha_o
 }
 cudaError_t fri_coin_step(int hash_id, u64* state, const u64* root, int d, u64* alpha_out, u64* log_entry, cudaStream_t st) {
     if (hash_id == WF_HASH_BLAKE3_256) fri_coin_kernel<WF_HASH_BLAKE3_256><<<1, 32, 0, st>>>(state, root, d, alpha_out, log_entry);
+    else if (hash_id == WF_HASH_BLAKE3_192) fri_coin_kernel<WF_HASH_BLAKE3_192><<<1, 32, 0, st>>>(state, root, d, alpha_out, log_entry);
     else if (hash_id == WF_HASH_RP64_256) fri_coin_kernel<WF_HASH_RP64_256><<<1, 32, 0, st>>>(state, root, d, alpha_out, log_entry);
     else fri_coin_kernel<WF_HASH_RPJIVE64_256><<<1, 32, 0, st>>>(state, root, d, alpha_out, log_entry);
     return cudaGetLastError();

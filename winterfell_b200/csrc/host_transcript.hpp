@@ -19,10 +19,12 @@ struct Digest {
     u8 b[32];
 };
 
+// (digests live in 32-byte slots; Blake3_192 keeps the first 24 bytes, the rest of the slot is zero — commit.cuh)
 static inline Digest hh_hash_elements(int hash_id, const u64* e, size_t n) {
     Digest d;
-    if (hash_id == WF_HASH_BLAKE3_256) {
+    if (WF_HASH_IS_BLAKE3(hash_id)) {
         b3_host_hash(reinterpret_cast<const u8*>(e), n * 8, d.b);  // canonical LE bytes (x86 host is LE)
+        if (hash_id == WF_HASH_BLAKE3_192) memset(d.b + 24, 0, 8);
     } else {
         u64 o[4];
         if (hash_id == WF_HASH_RP64_256) rp64_host_hash_elements(e, n, o);
@@ -33,11 +35,13 @@ static inline Digest hh_hash_elements(int hash_id, const u64* e, size_t n) {
 }
 static inline Digest hh_merge(int hash_id, const Digest& a, const Digest& b) {
     Digest d;
-    if (hash_id == WF_HASH_BLAKE3_256) {
+    if (WF_HASH_IS_BLAKE3(hash_id)) {
+        const size_t dl = WF_DIGEST_BYTES(hash_id);   // blake/mod.rs:33, :85-88: the digests' bytes back to back
         u8 two[64];
-        memcpy(two, a.b, 32);
-        memcpy(two + 32, b.b, 32);
-        b3_host_hash(two, 64, d.b);
+        memcpy(two, a.b, dl);
+        memcpy(two + dl, b.b, dl);
+        b3_host_hash(two, 2 * dl, d.b);
+        if (dl == 24) memset(d.b + 24, 0, 8);
     } else {
         u64 in[8], o[4];
         memcpy(in, a.b, 32);
@@ -50,11 +54,13 @@ static inline Digest hh_merge(int hash_id, const Digest& a, const Digest& b) {
 }
 static inline Digest hh_merge_with_int(int hash_id, const Digest& seed, u64 value) {
     Digest d;
-    if (hash_id == WF_HASH_BLAKE3_256) {
+    if (WF_HASH_IS_BLAKE3(hash_id)) {
+        const size_t dl = WF_DIGEST_BYTES(hash_id);   // blake/mod.rs:41-46, :95-102
         u8 data[40];
-        memcpy(data, seed.b, 32);
-        memcpy(data + 32, &value, 8);
-        b3_host_hash(data, 40, d.b);
+        memcpy(data, seed.b, dl);
+        memcpy(data + dl, &value, 8);
+        b3_host_hash(data, dl + 8, d.b);
+        if (dl == 24) memset(d.b + 24, 0, 8);
     } else {
         u64 s[4], o[4];
         memcpy(s, seed.b, 32);

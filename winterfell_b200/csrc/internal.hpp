@@ -137,6 +137,7 @@ struct wf_tree;
 int wf_fri_layer_tree(wf_ctx* ctx, int hash_id, const u64* vals, size_t len, int d, int ld, int nf, wf_tree** out);
 struct OpenPlan {
     u32 depth;
+    u32 digest_bytes = 32;                       // bytes a digest serializes to (24 for Blake3_192), set from the tree's hasher
     std::vector<u64> want;                       // < n: nodes[want]; >= n: leaves[want - n]
     std::vector<std::vector<size_t>> vec_slots;  // per proof vector: slots into `want`
     std::vector<size_t> leaf_slot;               // per queried position: slot of its leaf digest

@@ -417,15 +417,12 @@ __global__ void __launch_bounds__(256) grind_kernel(int hash_id, const u64* seed
     if (idx >= count) return;
     u64 nonce = start + idx;
     u64 head;
-    if (hash_id == WF_HASH_BLAKE3_256) {
-        u32 m[16], cv[8];
+    if (WF_HASH_IS_BLAKE3(hash_id)) {
+        u32 ws[8], cv[8];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { m[2 * i] = (u32)seed[i]; m[2 * i + 1] = (u32)(seed[i] >> 32); }
-        m[8] = (u32)nonce; m[9] = (u32)(nonce >> 32);
-#pragma unroll
-        for (int i = 10; i < 16; i++) m[i] = 0;
-        b3_iv(cv);
-        b3_compress(cv, m, 0, 40, B3_CHUNK_START | B3_CHUNK_END | B3_ROOT, b3_runtime_one());  // blake/mod.rs:41-46
+        for (int i = 0; i < 4; i++) { ws[2 * i] = (u32)seed[i]; ws[2 * i + 1] = (u32)(seed[i] >> 32); }
+        if (hash_id == WF_HASH_BLAKE3_256) b3_merge_with_int_words<8>(ws, nonce, cv, b3_runtime_one());  // blake/mod.rs:41-46
+        else b3_merge_with_int_words<6>(ws, nonce, cv, b3_runtime_one());                                 // :95-102
         head = (u64)cv[0] | ((u64)cv[1] << 32);
     } else {
         u64 sd[4], o[4];
@@ -449,7 +446,7 @@ static int grind_on_device(wf_ctx* ctx, int hash_id, const Digest& seed, u32 gri
     CKI(wf_dev_alloc(ctx, 8, &d_res));
     CK(cudaMemcpyAsync(d_seed, seed.b, 32, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemsetAsync(d_res, 0xff, 8, ctx->st));
-    const u64 batch = hash_id == WF_HASH_BLAKE3_256 ? (1ULL << 20) : (1ULL << 16);
+    const u64 batch = WF_HASH_IS_BLAKE3(hash_id) ? (1ULL << 20) : (1ULL << 16);
     u64 start = 1, found = ~0ULL;
     while (found == ~0ULL) {
         grind_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, ctx->st>>>(hash_id, (const u64*)d_seed, start, batch, grinding,
@@ -654,7 +651,7 @@ struct Channel {  // ProverChannel (prover/src/channel.rs)
     ByteVec commitments;
     Channel(int h, const std::vector<u64>& seed) : coin(h, seed.data(), seed.size()) {}
     void commit(const u8 root[32]) {  // commit_trace / commit_constraints / commit_fri_layer
-        commitments.bytes(root, 32);
+        commitments.bytes(root, WF_DIGEST_BYTES(coin.hash_id));   // ByteDigest<N>::write_into: N bytes
         Digest d;
         memcpy(d.b, root, 32);
         coin.reseed(d);
@@ -1284,7 +1281,7 @@ int prove_air(wf_ctx* ctx, const AirHost& air_in, const uint64_t* const* trace_c
     {   // transcript replicated on the device: one synchronisation for the whole commit phase (capi.cu)
         std::vector<Digest> fri_roots;
         CKI(wf_fri_build_layers_coin(ctx, h, deep, D, o.folding, o.rem_max_deg, o.blowup, ch.coin, fri_roots, &fri));
-        for (auto& r : fri_roots) ch.commitments.bytes(r.b, 32);
+        for (auto& r : fri_roots) ch.commitments.bytes(r.b, WF_DIGEST_BYTES(h));
     }
     scope.drop(deep);
     wf_mark(ctx, "fri_layers");
@@ -1817,7 +1814,7 @@ int prove_fib_sharded(wf_ctx* ctx, const wf_comm* cm, const uint64_t* const* loc
     {
         std::vector<Digest> fri_roots;
         CKI(wf_fri_build_layers_coin(ctx, h, fri_in, D, o.folding, o.rem_max_deg, o.blowup, ch.coin, fri_roots, &fri));
-        for (auto& rt : fri_roots) ch.commitments.bytes(rt.b, 32);
+        for (auto& rt : fri_roots) ch.commitments.bytes(rt.b, WF_DIGEST_BYTES(h));
     }
     scope.drop(fri_in);
     wf_mark(ctx, "fri_layers");
