@@ -44,6 +44,7 @@ extern "C" {
 #define WF_HASH_BLAKE3_256 0 /* crypto/src/hash/blake/mod.rs:21 */
 #define WF_HASH_RP64_256 1   /* crypto/src/hash/rescue/rp64_256/mod.rs:118 */
 #define WF_HASH_RPJIVE64_256 2 /* crypto/src/hash/rescue/rp64_256_jive/mod.rs:112 (Jive compression for merges) */
+#define WF_HASH_SHA3_256 4     /* crypto/src/hash/sha/mod.rs:19 */
 #define WF_HASH_BLAKE3_192 3   /* crypto/src/hash/blake/mod.rs:73: 24-byte digests. Digests cross this ABI in 32-byte slots (the last
                                 * 8 bytes zero, as ByteDigest::as_bytes pads them); proofs carry 24 bytes per digest */
 

@@ -17,6 +17,7 @@ BLAKE3 = 0
 RP64 = 1
 RPJIVE = 2
 BLAKE3_192 = 3
+SHA3 = 4
 
 
 def build(force=False):

@@ -600,6 +600,44 @@ static void rpj_merge_with_int(const u8 seed[32], u64 value, u8 out[32]) {  // m
 // =================================================================================================
 // HASHER DISPATCH  (crypto/src/hash/mod.rs:31-64)
 // =================================================================================================
+// =================================================================================================
+// SHA3-256  (third-party crate `sha3 = "0.10"`, crypto/Cargo.toml; FIPS 202 restated, byte-oriented)
+// =================================================================================================
+static void keccak_f(u64 st[25]) {
+    static const u64 RC[24] = {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL,
+                               0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL,
+                               0x0000000080008009ULL, 0x000000008000000aULL, 0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL,
+                               0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+                               0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    static const int ROT[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
+    static const int PIL[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+    for (int r = 0; r < 24; r++) {
+        u64 bc[5];
+        for (int i = 0; i < 5; i++) bc[i] = st[i] ^ st[i + 5] ^ st[i + 10] ^ st[i + 15] ^ st[i + 20];
+        for (int i = 0; i < 5; i++) {
+            u64 t = bc[(i + 4) % 5] ^ ((bc[(i + 1) % 5] << 1) | (bc[(i + 1) % 5] >> 63));
+            for (int j = 0; j < 25; j += 5) st[j + i] ^= t;
+        }
+        u64 t = st[1];
+        for (int i = 0; i < 24; i++) { int j = PIL[i]; u64 b = st[j]; st[j] = (t << ROT[i]) | (t >> (64 - ROT[i])); t = b; }
+        for (int j = 0; j < 25; j += 5) {
+            for (int i = 0; i < 5; i++) bc[i] = st[j + i];
+            for (int i = 0; i < 5; i++) st[j + i] ^= (~bc[(i + 1) % 5]) & bc[(i + 2) % 5];
+        }
+        st[0] ^= RC[r];
+    }
+}
+static void sha3_256(const u8* data, size_t len, u8 out[32]) {
+    u64 st[25] = {0};
+    u8* sb = (u8*)st;  // little-endian host
+    size_t i = 0;
+    for (size_t k = 0; k < len; k++) { sb[i++] ^= data[k]; if (i == 136) { keccak_f(st); i = 0; } }
+    sb[i] ^= 0x06;
+    sb[135] ^= 0x80;
+    keccak_f(st);
+    memcpy(out, st, 32);
+}
+
 // Digests live in 32-byte slots everywhere in this file; Blake3_192 (blake/mod.rs:73-123) keeps the first 24 bytes of the BLAKE3
 // output (ByteDigest<24>; the slot's last 8 bytes are zero, as ByteDigest::as_bytes pads them) and hashes / serializes 24
 // bytes per digest.
@@ -608,6 +646,7 @@ static void b3_192(const u8* data, size_t len, u8 out[32]) { blake3_hash(data, l
 static void hash_elements(int h, const u64* e, size_t n, u8 out[32]) {
     if (h == WFO_HASH_BLAKE3_256) blake3_hash((const u8*)e, n * 8, out);  // blake/mod.rs:52-65: canonical LE bytes
     else if (h == WFO_HASH_BLAKE3_192) b3_192((const u8*)e, n * 8, out);  // :108-115
+    else if (h == WFO_HASH_SHA3_256) sha3_256((const u8*)e, n * 8, out);  // sha/mod.rs:49-55
     else if (h == WFO_HASH_RP64_256) rp_hash_elements(e, n, out);
     else rpj_hash_elements(e, n, out);
 }
@@ -615,6 +654,7 @@ static void merge_many(int h, const u8* dg, size_t n, u8 out[32]);
 static void merge(int h, const u8 two[64], u8 out[32]) {
     if (h == WFO_HASH_BLAKE3_256) blake3_hash(two, 64, out);  // blake/mod.rs:33
     else if (h == WFO_HASH_BLAKE3_192) merge_many(h, two, 2, out);  // :85-88: BLAKE3 of the 48 digest bytes
+    else if (h == WFO_HASH_SHA3_256) sha3_256(two, 64, out);         // sha/mod.rs:30-32
     else if (h == WFO_HASH_RP64_256) rp_merge(two, out);
     else rpj_merge(two, out);
 }
@@ -625,6 +665,7 @@ static void merge_many(int h, const u8* dg, size_t n, u8 out[32]) {
         for (size_t i = 0; i < n; i++) memcpy(cat.data() + 24 * i, dg + 32 * i, 24);
         b3_192(cat.data(), cat.size(), out);
     }
+    else if (h == WFO_HASH_SHA3_256) sha3_256(dg, n * 32, out);                     // sha/mod.rs:34-36
     else if (h == WFO_HASH_RP64_256) rp_hash_elements((const u64*)dg, n * 4, out);  // rp64_256/mod.rs:194
     else rpj_hash_elements((const u64*)dg, n * 4, out);                             // rp64_256_jive/mod.rs:198-200
 }
@@ -639,6 +680,11 @@ static void merge_with_int(int h, const u8 seed[32], u64 value, u8 out[32]) {
         memcpy(data, seed, 24);
         memcpy(data + 24, &value, 8);
         b3_192(data, 32, out);
+    } else if (h == WFO_HASH_SHA3_256) {  // sha/mod.rs:38-43
+        u8 data[40];
+        memcpy(data, seed, 32);
+        memcpy(data + 32, &value, 8);
+        sha3_256(data, 40, out);
     } else if (h == WFO_HASH_RP64_256) rp_merge_with_int(seed, value, out);
     else rpj_merge_with_int(seed, value, out);
 }

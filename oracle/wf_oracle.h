@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-enum { WFO_HASH_BLAKE3_256 = 0, WFO_HASH_RP64_256 = 1, WFO_HASH_RPJIVE64_256 = 2, WFO_HASH_BLAKE3_192 = 3 };
+enum { WFO_HASH_BLAKE3_256 = 0, WFO_HASH_RP64_256 = 1, WFO_HASH_RPJIVE64_256 = 2, WFO_HASH_BLAKE3_192 = 3, WFO_HASH_SHA3_256 = 4 };
 
 void wfo_set_threads(int n);  // number of OpenMP threads for the `concurrent`-style loops
 int wfo_get_threads(void);

@@ -95,7 +95,7 @@ def test_interpolate_with_offset(ctx, oracle):
         assert (got[c] == oracle.interpolate_poly_with_offset(ev[c], 7)).all()
 
 
-@pytest.mark.parametrize("h", [wf.HASH_BLAKE3_256, wf.HASH_RP64_256, wf.HASH_RPJIVE64_256, wf.HASH_BLAKE3_192])
+@pytest.mark.parametrize("h", [wf.HASH_BLAKE3_256, wf.HASH_RP64_256, wf.HASH_RPJIVE64_256, wf.HASH_BLAKE3_192, wf.HASH_SHA3_256])
 @pytest.mark.parametrize("cols", [1, 2, 3, 4, 7, 8, 9, 16, 24, 64, 130])
 def test_row_hash_and_merkle_vs_oracle(ctx, oracle, h, cols):
     rows = 1024 if h in (wf.HASH_BLAKE3_256, wf.HASH_BLAKE3_192) else 256
@@ -136,7 +136,7 @@ def test_merkle_reference_fixture(ctx):
     assert ctx.tree_from_leaves(wf.HASH_BLAKE3_256, l8).root() == root
 
 
-@pytest.mark.parametrize("h", [wf.HASH_BLAKE3_256, wf.HASH_RP64_256, wf.HASH_RPJIVE64_256, wf.HASH_BLAKE3_192])
+@pytest.mark.parametrize("h", [wf.HASH_BLAKE3_256, wf.HASH_RP64_256, wf.HASH_RPJIVE64_256, wf.HASH_BLAKE3_192, wf.HASH_SHA3_256])
 @pytest.mark.parametrize("d,nf,log_len", [(1, 4, 12), (1, 2, 10), (1, 8, 12), (1, 16, 12), (2, 4, 10), (3, 4, 12), (3, 8, 9)])
 def test_fri_layers_vs_oracle(ctx, oracle, h, d, nf, log_len):
     # fri/src/prover/tests.rs round trip shape: commit phase roots and remainder
@@ -191,7 +191,7 @@ def test_plain_dev_kernels(ctx, oracle):
     assert (nd.cpu().numpy().reshape(n, 32) == oracle.merkle_nodes(oracle.BLAKE3, want)).all()
 
 
-@pytest.mark.parametrize("h", [wf.HASH_BLAKE3_256, wf.HASH_RP64_256, wf.HASH_RPJIVE64_256, wf.HASH_BLAKE3_192])
+@pytest.mark.parametrize("h", [wf.HASH_BLAKE3_256, wf.HASH_RP64_256, wf.HASH_RPJIVE64_256, wf.HASH_BLAKE3_192, wf.HASH_SHA3_256])
 @pytest.mark.parametrize("cols,psize", [(64, 8), (64, 16), (20, 8), (9, 4), (130, 9), (16, 1)])
 def test_partitioned_row_hash_vs_oracle(ctx, oracle, h, cols, psize):
     # RowMatrix::commit_to_rows with PartitionOptions (row_matrix.rs:204-223): merge_many of chunk digests

@@ -35,6 +35,9 @@ CASES = [
     (1, 7, 1, wf.HASH_BLAKE3_192, 4, 7, 0, 0, 8, 28),    # 24-byte digests (crypto/src/hash/blake/mod.rs:73-123)
     (4, 10, 3, wf.HASH_BLAKE3_192, 4, 31, 1, 6, 8, 32),
     (32, 9, 2, wf.HASH_BLAKE3_192, 8, 7, 2, 0, 8, 20),
+    (1, 7, 1, wf.HASH_SHA3_256, 4, 7, 0, 0, 8, 28),      # Sha3_256 (crypto/src/hash/sha/mod.rs:19)
+    (4, 10, 3, wf.HASH_SHA3_256, 4, 31, 1, 5, 8, 32),
+    (16, 9, 2, wf.HASH_SHA3_256, 8, 7, 2, 0, 8, 20),     # 32 columns: rows longer than one 136-byte rate block
 ]
 
 
@@ -66,7 +69,7 @@ def test_montgomery_trace_input(ctx, oracle):
     assert ctx.prove_fib(tm, results, opts, mont=True) == oracle.prove_fib(trace, results, opts)
 
 
-@pytest.mark.parametrize("h,g", [(wf.HASH_BLAKE3_256, 16), (wf.HASH_BLAKE3_256, 21), (wf.HASH_RP64_256, 10), (wf.HASH_RPJIVE64_256, 9), (wf.HASH_BLAKE3_192, 14)])
+@pytest.mark.parametrize("h,g", [(wf.HASH_BLAKE3_256, 16), (wf.HASH_BLAKE3_256, 21), (wf.HASH_RP64_256, 10), (wf.HASH_RPJIVE64_256, 9), (wf.HASH_BLAKE3_192, 14), (wf.HASH_SHA3_256, 11)])
 def test_grinding_smallest_nonce(ctx, oracle, h, g):
     # prover/src/channel.rs:173-175 (serial branch): smallest nonce
     coin = oracle.RandomCoin(h, [1, 2, 3, g])
@@ -249,7 +252,7 @@ def test_overlapping_assertions_are_refused(ctx, oracle):
 # still merge_many); (16, 1) is the maximum partition count.
 @pytest.mark.parametrize("k,log_n,ext,h,parts,rate", [
     (4, 10, 1, wf.HASH_BLAKE3_256, 2, 8), (4, 10, 3, wf.HASH_BLAKE3_256, 4, 8), (32, 9, 3, wf.HASH_BLAKE3_256, 8, 8),
-    (8, 9, 2, wf.HASH_RP64_256, 2, 8), (4, 9, 1, wf.HASH_RP64_256, 8, 8), (4, 8, 3, wf.HASH_RPJIVE64_256, 4, 4), (8, 9, 3, wf.HASH_BLAKE3_192, 4, 8), (1, 9, 3, wf.HASH_BLAKE3_256, 4, 64),
+    (8, 9, 2, wf.HASH_RP64_256, 2, 8), (4, 9, 1, wf.HASH_RP64_256, 8, 8), (4, 8, 3, wf.HASH_RPJIVE64_256, 4, 4), (8, 9, 3, wf.HASH_BLAKE3_192, 4, 8), (16, 9, 1, wf.HASH_SHA3_256, 2, 8), (1, 9, 3, wf.HASH_BLAKE3_256, 4, 64),
     (16, 9, 1, wf.HASH_BLAKE3_256, 16, 1)])
 def test_partitioned_commitments_match_oracle(ctx, oracle, k, log_n, ext, h, parts, rate):
     trace, results = oracle.build_fib_trace(k, 1 << log_n)

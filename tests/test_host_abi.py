@@ -43,7 +43,7 @@ def test_host_field_helpers(oracle):
         assert L.wf_host_mul(a, b) == a * b % P
 
 
-@pytest.mark.parametrize("h", [wf.HASH_BLAKE3_256, wf.HASH_RP64_256, wf.HASH_RPJIVE64_256, wf.HASH_BLAKE3_192])
+@pytest.mark.parametrize("h", [wf.HASH_BLAKE3_256, wf.HASH_RP64_256, wf.HASH_RPJIVE64_256, wf.HASH_BLAKE3_192, wf.HASH_SHA3_256])
 def test_host_hashers_match_oracle(oracle, h):
     for n in (0, 1, 4, 7, 8, 9, 16, 100, 128, 129, 300, 1000):
         e = oracle.rand_elems(n, 100 + n)
@@ -71,7 +71,7 @@ def test_host_usize_encoding_matches_reference_test():
         assert (int.from_bytes(b[1:9], "little") if length == 9 else int.from_bytes(b, "little") >> length) == v
 
 
-@pytest.mark.parametrize("h", [0, 1, 2, 3])
+@pytest.mark.parametrize("h", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("d", [1, 2, 3])
 def test_host_coin_matches_oracle(oracle, h, d):
     # the product's DefaultRandomCoin (host_transcript.hpp) against the oracle's (crypto/src/random/default.rs)
@@ -89,7 +89,7 @@ def test_host_coin_matches_oracle(oracle, h, d):
         assert (coin.draw(d) == out[i]).all()
 
 
-@pytest.mark.parametrize("h,d", [(0, 1), (1, 3), (0, 2), (2, 2), (3, 3)])
+@pytest.mark.parametrize("h,d", [(0, 1), (1, 3), (0, 2), (2, 2), (3, 3), (4, 1)])
 def test_cpp_mirror_host_logic(oracle, tmp_path, h, d):
     # include/winterfell_b200.hpp builds with plain g++ on a machine without a GPU, and its transcript pieces
     # (AIR description parsing, Context::to_elements, vint64 writer, coin, coefficient batching) agree with the oracle

@@ -288,6 +288,24 @@ def test_blake3_192_against_the_spec(oracle):
         assert oracle.verify_fib(bytes(t), 2, res, H) != 0
 
 
+def test_sha3_256_against_the_spec(oracle):
+    # Sha3_256 (crypto/src/hash/sha/mod.rs:19-60) pinned to FIPS 202 through hashlib; includes messages that end exactly on
+    # the 136-byte rate (17 elements) and a complete proof
+    import hashlib
+    H = oracle.SHA3
+    for n in (1, 4, 16, 17, 18, 34, 40):
+        e = oracle.rand_elems(n, 70 + n)
+        assert oracle.hash_elements(H, e) == hashlib.sha3_256(e.tobytes()).digest()
+    a, b = oracle.hash_elements(H, oracle.rand_elems(3, 1)), oracle.hash_elements(H, oracle.rand_elems(5, 2))
+    assert oracle.merge(H, a, b) == hashlib.sha3_256(a + b).digest()
+    assert oracle.merge_many(H, a + b + a) == hashlib.sha3_256(a + b + a).digest()
+    assert oracle.merge_with_int(H, a, 2**64 - 3) == hashlib.sha3_256(a + (2**64 - 3).to_bytes(8, "little")).digest()
+    trace, res = oracle.build_fib_trace(2, 128)
+    opts = oracle.make_opts(ext=3, hash_id=H, grinding=3, folding=4, rem_max_deg=7)
+    proof = oracle.prove_fib(trace, res, opts)
+    assert oracle.verify_fib(proof, 2, res, H) == 0 and oracle.verify_fib(proof, 2, res, oracle.BLAKE3) != 0
+
+
 # ---- Merkle: crypto/src/merkle/tests.rs:14-84 ----
 LEAVES4 = [
     [166, 168, 47, 140, 153, 86, 156, 86, 226, 229, 149, 76, 70, 132, 209, 109, 166, 193, 113, 197, 42, 116, 170, 144, 74, 104, 29, 110, 220, 49, 224, 123],

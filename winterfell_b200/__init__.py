@@ -18,6 +18,7 @@ HASH_BLAKE3_256 = 0
 HASH_RP64_256 = 1
 HASH_RPJIVE64_256 = 2
 HASH_BLAKE3_192 = 3
+HASH_SHA3_256 = 4
 
 WF_OK = 0
 

@@ -172,6 +172,8 @@ __global__ void __launch_bounds__(128) hash_rows_partitioned_kernel(int hash_id,
         for (int k = 0; k < 4; k++) digests[row * 4 + k] = (u64)cv[2 * k] | ((u64)cv[2 * k + 1] << 32);
     } else if (hash_id == WF_HASH_RP64_256) {
         partitioned_alg_row<WF_HASH_RP64_256>(m, row, psize, np, digests);
+    } else if (hash_id == WF_HASH_SHA3_256) {
+        partitioned_alg_row<WF_HASH_SHA3_256>(m, row, psize, np, digests);
     } else {
         partitioned_alg_row<WF_HASH_RPJIVE64_256>(m, row, psize, np, digests);
     }
@@ -282,6 +284,7 @@ cudaError_t commit_hash_rows(int hash_id, const SegMatrix& m, u64* digests, cuda
     } else {
         unsigned blocks = (unsigned)((m.rows + 127) / 128);
         if (hash_id == WF_HASH_RP64_256) hash_rows_alg_kernel<WF_HASH_RP64_256><<<blocks, 128, 0, st>>>(src, m.rows, digests);
+        else if (hash_id == WF_HASH_SHA3_256) hash_rows_alg_kernel<WF_HASH_SHA3_256><<<blocks, 128, 0, st>>>(src, m.rows, digests);
         else hash_rows_alg_kernel<WF_HASH_RPJIVE64_256><<<blocks, 128, 0, st>>>(src, m.rows, digests);
     }
     return cudaGetLastError();
@@ -304,6 +307,8 @@ cudaError_t commit_merkle_nodes(int hash_id, const u64* leaves, size_t nleaves, 
                                                                                       reinterpret_cast<uint4*>(dst), m);
         else if (hash_id == WF_HASH_RP64_256)
             merkle_level_alg_kernel<WF_HASH_RP64_256><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(src, dst, m);
+        else if (hash_id == WF_HASH_SHA3_256)
+            merkle_level_alg_kernel<WF_HASH_SHA3_256><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(src, dst, m);
         else
             merkle_level_alg_kernel<WF_HASH_RPJIVE64_256><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(src, dst, m);
         src = dst;
@@ -314,6 +319,7 @@ cudaError_t commit_merkle_nodes(int hash_id, const u64* leaves, size_t nleaves, 
         if (hash_id == WF_HASH_BLAKE3_256) merkle_subtree_kernel<WF_HASH_BLAKE3_256><<<blocks, 256, 0, st>>>(src, nodes, m);
         else if (hash_id == WF_HASH_BLAKE3_192) merkle_subtree_kernel<WF_HASH_BLAKE3_192><<<blocks, 256, 0, st>>>(src, nodes, m);
         else if (hash_id == WF_HASH_RP64_256) merkle_subtree_kernel<WF_HASH_RP64_256><<<blocks, 256, 0, st>>>(src, nodes, m);
+        else if (hash_id == WF_HASH_SHA3_256) merkle_subtree_kernel<WF_HASH_SHA3_256><<<blocks, 256, 0, st>>>(src, nodes, m);
         else merkle_subtree_kernel<WF_HASH_RPJIVE64_256><<<blocks, 256, 0, st>>>(src, nodes, m);
         if (m <= 256) break;           // this launch reached the root
         // the launch produced levels m, m/2, ..., m/256 (one node per block); continue above them

@@ -10,7 +10,8 @@
 #define WF_HASH_RP64_256 1
 #define WF_HASH_RPJIVE64_256 2
 #define WF_HASH_BLAKE3_192 3
-#define WF_HASH_IS_KNOWN(h) ((h) >= 0 && (h) <= 3)
+#define WF_HASH_SHA3_256 4
+#define WF_HASH_IS_KNOWN(h) ((h) >= 0 && (h) <= 4)
 #define WF_HASH_IS_BLAKE3(h) ((h) == WF_HASH_BLAKE3_256 || (h) == WF_HASH_BLAKE3_192)
 // digests occupy 32-byte slots everywhere; Blake3_192 (crypto/src/hash/blake/mod.rs:73-123) keeps and serializes the first 24
 // bytes (the rest of the slot is zero, as ByteDigest::as_bytes pads it)

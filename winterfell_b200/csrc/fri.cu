@@ -115,6 +115,8 @@ cudaError_t fri_hash_layer(int hash_id, const u64* evals, size_t len, int d, int
                                                                             reinterpret_cast<uint4*>(digests), WF_DIGEST_WORDS32(hash_id));
     else if (hash_id == WF_HASH_RP64_256)
         fri_hash_alg_kernel<WF_HASH_RP64_256><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(evals, m, d, ld, nf, digests);
+    else if (hash_id == WF_HASH_SHA3_256)
+        fri_hash_alg_kernel<WF_HASH_SHA3_256><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(evals, m, d, ld, nf, digests);
     else
         fri_hash_alg_kernel<WF_HASH_RPJIVE64_256><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(evals, m, d, ld, nf, digests);
     return cudaGetLastError();
@@ -209,6 +211,7 @@ cudaError_t fri_coin_step(int hash_id, u64* state, const u64* root, int d, u64* 
     if (hash_id == WF_HASH_BLAKE3_256) fri_coin_kernel<WF_HASH_BLAKE3_256><<<1, 32, 0, st>>>(state, root, d, alpha_out, log_entry);
     else if (hash_id == WF_HASH_BLAKE3_192) fri_coin_kernel<WF_HASH_BLAKE3_192><<<1, 32, 0, st>>>(state, root, d, alpha_out, log_entry);
     else if (hash_id == WF_HASH_RP64_256) fri_coin_kernel<WF_HASH_RP64_256><<<1, 32, 0, st>>>(state, root, d, alpha_out, log_entry);
+    else if (hash_id == WF_HASH_SHA3_256) fri_coin_kernel<WF_HASH_SHA3_256><<<1, 32, 0, st>>>(state, root, d, alpha_out, log_entry);
     else fri_coin_kernel<WF_HASH_RPJIVE64_256><<<1, 32, 0, st>>>(state, root, d, alpha_out, log_entry);
     return cudaGetLastError();
 }

@@ -14,6 +14,7 @@
 #include "commit.cuh"
 #include "rp64.cuh"
 #include "rpjive.cuh"
+#include "sha3.cuh"
 
 struct Digest {
     u8 b[32];
@@ -28,6 +29,7 @@ static inline Digest hh_hash_elements(int hash_id, const u64* e, size_t n) {
     } else {
         u64 o[4];
         if (hash_id == WF_HASH_RP64_256) rp64_host_hash_elements(e, n, o);
+        else if (hash_id == WF_HASH_SHA3_256) sha3_host_words(e, n, o);   // sha/mod.rs:49-55: the canonical LE element bytes
         else rpj_host_hash_elements(e, n, o);
         memcpy(d.b, o, 32);
     }
@@ -47,6 +49,7 @@ static inline Digest hh_merge(int hash_id, const Digest& a, const Digest& b) {
         memcpy(in, a.b, 32);
         memcpy(in + 4, b.b, 32);
         if (hash_id == WF_HASH_RP64_256) rp64_merge(in, o);
+        else if (hash_id == WF_HASH_SHA3_256) sha3_host_words(in, 8, o);
         else rpj_merge(in, o);
         memcpy(d.b, o, 32);
     }
@@ -65,6 +68,7 @@ static inline Digest hh_merge_with_int(int hash_id, const Digest& seed, u64 valu
         u64 s[4], o[4];
         memcpy(s, seed.b, 32);
         if (hash_id == WF_HASH_RP64_256) rp64_host_merge_with_int(s, value, o);
+        else if (hash_id == WF_HASH_SHA3_256) { u64 w5[5] = {s[0], s[1], s[2], s[3], value}; sha3_host_words(w5, 5, o); }
         else rpj_merge_with_int(s, value, o);
         memcpy(d.b, o, 32);
     }

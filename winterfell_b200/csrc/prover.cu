@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(256) grind_kernel(int hash_id, const u64* seed
 #pragma unroll
         for (int i = 0; i < 4; i++) sd[i] = seed[i];
         if (hash_id == WF_HASH_RP64_256) alg_merge_with_int<WF_HASH_RP64_256>(sd, nonce, o);       // rp64_256/mod.rs:198-218
+        else if (hash_id == WF_HASH_SHA3_256) alg_merge_with_int<WF_HASH_SHA3_256>(sd, nonce, o);  // sha/mod.rs:38-43
         else alg_merge_with_int<WF_HASH_RPJIVE64_256>(sd, nonce, o);                                // rp64_256_jive/mod.rs:206-229
         head = o[0];
     }
