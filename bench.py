@@ -17,7 +17,7 @@ byte-identical to the single-GPU proof. A short cfg2 (2^20 x 8, base field) reco
 
 `--impl reference` times the CPU arm: the oracle (C++ restatement of the reference's `concurrent` prover — the
 reference is Rust and cannot be built in this image) at the FULL configuration, for as many steps as fit the wall
-budget (WF_REF_BUDGET_S, default 240 s; at least one); the line reports the steps actually run, never a scaled sample.
+budget (WF_REF_BUDGET_S, default 170 s; at least one); the line reports the steps actually run, never a scaled sample.
 """
 import argparse
 import json
@@ -171,7 +171,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     pairs, log_n, ext = CONFIGS[args.config]
-    budget = float(os.environ.get("WF_REF_BUDGET_S", "240"))
+    budget = float(os.environ.get("WF_REF_BUDGET_S", "170"))
     ms, steps_run, warm_run, cores = cpu_prove(pairs, log_n, ext, args.steps, min(args.warmup, 1), budget)
     sample = (ORACLE_DESC.format(cores=cores) + f"; FULL configuration (2^{log_n} rows x {2 * pairs} columns), {steps_run} timed proof(s) "
               f"actually run inside a {budget:.0f} s wall budget ({args.steps} requested), no scaling")

@@ -461,6 +461,7 @@ GL_HD GlExt<3> ext_mul(const GlExt<3>& a, const GlExt<3>& b) {  // f64/mod.rs:44
     r.v[2] = gl_sub(s02, m);
     return r;
 }
+GL_HD GlExt<1> ext_frobenius(const GlExt<1>& x) { return x; }
 GL_HD GlExt<2> ext_frobenius(const GlExt<2>& x) {  // f64/mod.rs:431
     GlExt<2> r;
     r.v[0] = gl_add(x.v[0], x.v[1]);

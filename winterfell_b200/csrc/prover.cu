@@ -352,58 +352,111 @@ __global__ void __launch_bounds__(DEEP_SUM_THREADS) deep_sum_kernel(DeepParams p
 
 // rows per thread sharing one batch inversion
 #ifndef DEEP_ROWS1
-#define DEEP_ROWS1 16
+#define DEEP_ROWS1 8
 #endif
 #ifndef DEEP_ROWS2
 #define DEEP_ROWS2 8
 #endif
 #ifndef DEEP_ROWS3
-#define DEEP_ROWS3 4
+#define DEEP_ROWS3 8
 #endif
 #ifndef DEEP_DIV_MINB
-#define DEEP_DIV_MINB 2  // <= 128 registers: measured 0.55 -> 0.44 ms on cfg2, 1.20 -> 0.98 ms on 2^18 x 64 cubic
+#define DEEP_DIV_MINB 2
 #endif
 #define DEEP_ROWS (D == 1 ? DEEP_ROWS1 : (D == 2 ? DEEP_ROWS2 : DEEP_ROWS3))
+// 1 / (x - z) for x in the BASE field and z in the extension, without an extension-field inversion: with m_z the minimal
+// polynomial of z over the base field (degree D, base-field coefficients) and Q_z(X) = m_z(X) / (X - z) (degree D - 1, extension
+// coefficients, monic),   1 / (x - z) = Q_z(x) / m_z(x),   m_z(x) = N(x - z) in the base field.
+// So the per-row inversion is a BASE-field one (3 multiplications per denominator in a batch inversion instead of 3
+// extension products = 18 for the cubic extension) and Q_z(x) costs D - 1 base-by-extension products. The host supplies
+//   D = 3: m = X^3 - t X^2 + s X - n (t = trace, n = norm), Q = X^2 - q1 X + q0, q1 = z' + z'', q0 = z' z'' (Frobenius conjugates)
+//   D = 2: m = X^2 - t X + n,                                Q = X - q0,          q0 = z'
+//   D = 1: m = X - z,                                        Q = 1.
 template <int D>
-__global__ void __launch_bounds__(256, DEEP_DIV_MINB) deep_div_kernel(DeepParams p, GlExt<D> z, GlExt<D> zg, GlExt<D> Sz, GlExt<D> Szg) {
+struct DeepPoint {
+    u64 t, s, n;        // base-field coefficients of m_z
+    GlExt<D> q1, q0;    // extension coefficients of Q_z
+};
+template <int D>
+__device__ __forceinline__ u64 deep_m(const DeepPoint<D>& pt, u64 x, u64 x2) {
+    if (D == 1) return gl_sub(x, pt.n);                                          // x - z
+    if (D == 2) return gl_add(gl_sub(x2, gl_mul(pt.t, x)), pt.n);               // x^2 - t x + n
+    return gl_sub(gl_add(gl_mul(x2, gl_sub(x, pt.t)), gl_mul(pt.s, x)), pt.n);  // x^2 (x - t) + s x - n
+}
+template <int D>
+__device__ __forceinline__ GlExt<D> deep_q(const DeepPoint<D>& pt, u64 x, u64 x2) {
+    GlExt<D> q;
+    if (D == 1) { q.v[0] = 1; return q; }
+    if (D == 2) { q = ext_sub(ext_from_base<D>(x), pt.q0); return q; }
+    q = ext_sub(pt.q0, ext_mul_base(pt.q1, x));
+    q.v[0] = gl_add(q.v[0], x2);
+    return q;
+}
+template <int D>
+__global__ void __launch_bounds__(256, DEEP_DIV_MINB) deep_div_kernel(DeepParams p, DeepPoint<D> pz, DeepPoint<D> pzg, GlExt<D> Sz, GlExt<D> Szg) {
     const size_t N = p.nrows ? p.nrows : ((size_t)1 << p.log_N);   // rows of this launch
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     constexpr int ROWS = DEEP_ROWS;
-    GlExt<D> den[2 * ROWS];
+    u64 xs[D == 1 ? 1 : ROWS], den[2 * ROWS];   // x is only needed again by Q_z for D > 1
     const u32 half = (u32)(((size_t)1 << p.log_N) >> 1);
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
         size_t row = tid + r * stride;
-        den[2 * r] = ext_from_base<D>(1);
-        den[2 * r + 1] = ext_from_base<D>(1);
+        if (D > 1) xs[r] = 0;
+        den[2 * r] = 1; den[2 * r + 1] = 1;
         if (row >= N) continue;
         const size_t grow = row + p.row0;   // row of the LDE domain
         u64 w = p.tw_N[grow & (half - 1)];
         if (grow & half) w = gl_neg(w);
-        GlExt<D> x = ext_from_base<D>(gl_mul(w, GL_GENERATOR));
-        den[2 * r] = ext_sub(x, z);
-        den[2 * r + 1] = ext_sub(x, zg);
+        const u64 x = gl_mul(w, GL_GENERATOR), x2 = gl_sqr(x);
+        if (D > 1) xs[r] = x;
+        den[2 * r] = deep_m<D>(pz, x, x2);
+        den[2 * r + 1] = deep_m<D>(pzg, x, x2);
     }
-    // batch inversion; denominators are never zero (z is outside the base-field LDE domain with
-    // overwhelming probability; a zero would also break the reference's synthetic division)
-    GlExt<D> pre[2 * ROWS];
-    GlExt<D> run = ext_from_base<D>(1);
+    // batch inversion in the base field; the norms are never zero (z is outside the base-field LDE domain with overwhelming
+    // probability; a zero would also break the reference's synthetic division)
+    u64 pre[2 * ROWS], run = 1;
 #pragma unroll
-    for (int q = 0; q < 2 * ROWS; q++) { pre[q] = run; run = ext_mul(run, den[q]); }
-    run = ext_inv(run);
+    for (int q = 0; q < 2 * ROWS; q++) { pre[q] = run; run = gl_mul(run, den[q]); }
+    run = gl_inv(run);
 #pragma unroll
-    for (int q = 2 * ROWS - 1; q >= 0; q--) { GlExt<D> inv = ext_mul(run, pre[q]); run = ext_mul(run, den[q]); den[q] = inv; }
+    for (int q = 2 * ROWS - 1; q >= 0; q--) { const u64 inv = gl_mul(run, pre[q]); run = gl_mul(run, den[q]); den[q] = inv; }
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
         size_t row = tid + r * stride;
         if (row >= N) continue;
         u64* o = p.out.base + row * p.out.W;
-        GlExt<D> S = ld_ext<D>(o);
-        GlExt<D> v = ext_add(ext_mul(ext_sub(S, Sz), den[2 * r]), ext_mul(ext_sub(S, Szg), den[2 * r + 1]));
+        const GlExt<D> S = ld_ext<D>(o);
+        const u64 x = D > 1 ? xs[r] : 0, x2 = D > 1 ? gl_sqr(x) : 0;
+        const GlExt<D> a = ext_mul_base(ext_mul(ext_sub(S, Sz), deep_q<D>(pz, x, x2)), den[2 * r]);
+        const GlExt<D> b = ext_mul_base(ext_mul(ext_sub(S, Szg), deep_q<D>(pzg, x, x2)), den[2 * r + 1]);
+        const GlExt<D> v = ext_add(a, b);
 #pragma unroll
         for (int q = 0; q < D; q++) o[q] = v.v[q];
     }
+}
+// host side of DeepPoint: the conjugates of z under the Frobenius map (math/src/field/f64/mod.rs:431, :490-498)
+template <int D>
+static bool deep_point(const GlExt<D>& z, DeepPoint<D>& pt) {
+    pt.t = pt.s = pt.n = 0;
+    pt.q1 = ext_zero<D>(); pt.q0 = ext_zero<D>();
+    if (D == 1) { pt.n = z.v[0]; return true; }
+    const GlExt<D> z1 = ext_frobenius(z);
+    if (D == 2) {
+        const GlExt<D> tr = ext_add(z, z1), nm = ext_mul(z, z1);
+        pt.t = tr.v[0]; pt.n = nm.v[0]; pt.q0 = z1;
+        return tr.v[1] == 0 && nm.v[1] == 0;
+    }
+    const GlExt<D> z2 = ext_frobenius(z1);
+    const GlExt<D> tr = ext_add(z, ext_add(z1, z2));
+    const GlExt<D> z12 = ext_mul(z1, z2);
+    const GlExt<D> sm = ext_add(ext_mul(z, ext_add(z1, z2)), z12), nm = ext_mul(z, z12);
+    pt.t = tr.v[0]; pt.s = sm.v[0]; pt.n = nm.v[0];
+    pt.q1 = ext_add(z1, z2); pt.q0 = z12;
+    bool ok = true;
+    for (int k = 1; k < D; k++) ok = ok && tr.v[k] == 0 && sm.v[k] == 0 && nm.v[k] == 0;
+    return ok;
 }
 
 // Proof-of-work grinding (K13; prover/src/channel.rs:169-184, crypto/src/random/default.rs:141-146):
@@ -1089,7 +1142,9 @@ int deep_compose(wf_ctx* ctx, const wf_mat* lde, const wf_mat* alde, const wf_ma
     deep_sum_kernel<D><<<(unsigned)((N + DEEP_SUM_THREADS - 1) / DEEP_SUM_THREADS), DEEP_SUM_THREADS, coef_bytes, ctx->st>>>(p);
     const size_t rows_per_thread = DEEP_ROWS;
     size_t threads = (N + rows_per_thread - 1) / rows_per_thread;
-    deep_div_kernel<D><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->st>>>(p, z, zg, Sz, Szg);
+    DeepPoint<D> pz, pzg;
+    if (!deep_point<D>(z, pz) || !deep_point<D>(zg, pzg)) return wf_fail(ctx, WF_ERR_STATE, "conjugates of the out-of-domain point are inconsistent");
+    deep_div_kernel<D><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->st>>>(p, pz, pzg, Sz, Szg);
     ctx->launches += 2;
     CK(cudaGetLastError());
     // the coefficient buffers are pool allocations on the same stream: safe to release after the launch
