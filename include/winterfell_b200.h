@@ -58,6 +58,8 @@ typedef struct wf_fri wf_fri;   /* FRI prover state (fri/src/prover/mod.rs:100-1
 int wf_ctx_create(wf_ctx** out, int device, void* stream);
 void wf_ctx_destroy(wf_ctx* ctx);
 const char* wf_last_error(const wf_ctx* ctx);
+/* One wf_ctx belongs to one device and one calling thread at a time; the library makes ctx's device current on the calling thread
+ * wherever work for it starts (allocation, transform launch, gather, sync), so a process may hold contexts for several GPUs. */
 int wf_ctx_sync(wf_ctx* ctx);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 uint64_t wf_ctx_launch_count(const wf_ctx* ctx);
@@ -70,7 +72,9 @@ int wf_ctx_stage_times(wf_ctx* ctx, char* names, size_t names_cap, float* ms, si
 
 /* ---- matrices --------------------------------------------------------------------------------- */
 /* ColMatrix<E> (prover/src/matrix/col_matrix.rs:33): `ncols` host columns of `nrows` elements of
- * extension degree `ext_degree`; becomes ncols*ext_degree base columns on the device. */
+ * extension degree `ext_degree`; becomes ncols*ext_degree base columns on the device. The copies are enqueued on the ctx
+ * stream: with PINNED host memory they are asynchronous, and the columns must stay valid and unmodified until the next call that
+ * synchronises the context (wf_ctx_sync, any wf_*_root / *_to_host / wf_prove_*); pageable memory is staged before return. */
 int wf_mat_from_host_columns(wf_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, size_t nrows,
                              int ext_degree, int mont, wf_mat** out);
 /* same, from a DEVICE buffer laid out column-major [ncols][nrows] (base columns, canonical) */

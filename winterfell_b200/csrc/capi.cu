@@ -30,7 +30,14 @@ int wf_fail(wf_ctx* ctx, int code, const char* fmt, ...) {
     if (ctx) ctx->err = buf;
     return code;
 }
+// The context's device is made current on the calling thread wherever work for it starts (allocation, pass launch, gather,
+// stage mark, sync): a process may hold contexts for several GPUs, or call from a thread whose current device is another one.
+static inline void wf_use_device(wf_ctx* ctx) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != ctx->device) cudaSetDevice(ctx->device);
+}
 int wf_dev_alloc(wf_ctx* ctx, size_t bytes, void** out) {
+    wf_use_device(ctx);
     bytes = (bytes + 255) & ~(size_t)255;
     if (bytes == 0) bytes = 256;
     auto it = ctx->pool.find(bytes);
@@ -137,6 +144,7 @@ static int get_round_tw(wf_ctx* ctx, u32 logS, const u64** out) {
 // One pass: fills in the twiddle tables the kernel family of this sub-transform size reads, then launches.
 // p.logS, p.logM, p.has_post, p.W and the geometry must be set; sub_tw / master / tw_hi / tw_lo are set here.
 static int launch_pass(wf_ctx* ctx, int mode, NttPassParams& p, u32 n_segments, u32 n_batch) {
+    wf_use_device(ctx);
     if (p.logS >= NTT2_MIN_LOGS) {
         CKI(get_round_tw(ctx, (u32)p.logS, &p.sub_tw));
         if (p.has_post) {
@@ -491,7 +499,7 @@ int wf_ctx_stage_times(wf_ctx* ctx, char* names, size_t names_cap, float* ms, si
     return WF_OK;
 }
 const char* wf_last_error(const wf_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (is a CUDA device present?)"; }
-int wf_ctx_sync(wf_ctx* ctx) { CK(cudaStreamSynchronize(ctx->st)); return WF_OK; }
+int wf_ctx_sync(wf_ctx* ctx) { wf_use_device(ctx); CK(cudaStreamSynchronize(ctx->st)); return WF_OK; }
 uint64_t wf_ctx_launch_count(const wf_ctx* ctx) { return ctx->launches; }
 
 // ---- matrices -----------------------------------------------------------------------------------
@@ -997,6 +1005,7 @@ int GatherBatch::add_opening_sharded(wf_ctx* ctx, const wf_tree* t, size_t n_glo
     return WF_OK;
 }
 int GatherBatch::run(wf_ctx* ctx) {
+    wf_use_device(ctx);
     size_t idx_words = 0, out_words = 0;
     for (auto& j : rows) { j.idx_off = idx_words; j.out_off = out_words; idx_words += j.pos.size(); out_words += j.pos.size() * j.m.cols; }
     for (auto& j : digs) { j.idx_off = idx_words; j.out_off = out_words; idx_words += j.plan.want.size(); out_words += j.plan.want.size() * 4; }
