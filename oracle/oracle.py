@@ -252,14 +252,15 @@ def merkle_nodes(h, leaves):
     return o
 
 
-def merkle_prove_batch(leaves, nodes, indexes):
+def merkle_prove_batch(leaves, nodes, indexes, hash_id=BLAKE3):
+    """hash_id only matters for the digest length in the serialized proof (24 bytes for Blake3_192)."""
     l_, lp = _u8(leaves); n_, np_ = _u8(nodes); i_, ip = _u64(indexes)
     k = i_.size
     lo = np.zeros((k, 32), dtype=np.uint8)
     cap = 16 + k * (int(l_.shape[0]).bit_length() + 2) * 33
     out = np.zeros(cap, dtype=np.uint8)
-    r = lib().wfo_merkle_prove_batch(lp, np_, C.c_size_t(l_.shape[0]), ip, C.c_size_t(k),
-                                     lo.ctypes.data_as(u8p), out.ctypes.data_as(u8p), C.c_size_t(cap))
+    r = lib().wfo_merkle_prove_batch_h(C.c_int(hash_id), lp, np_, C.c_size_t(l_.shape[0]), ip, C.c_size_t(k),
+                                       lo.ctypes.data_as(u8p), out.ctypes.data_as(u8p), C.c_size_t(cap))
     if r < 0:
         raise ValueError("prove_batch failed")
     return lo, out[:r].tobytes()

@@ -915,6 +915,11 @@ long wfo_merkle_prove_batch(const uint8_t* leaves, const uint8_t* nodes, size_t 
                             uint8_t* leaves_out, uint8_t* out, size_t cap) {
     return merkle_prove_batch(leaves, nodes, nleaves, idx, k, leaves_out, out, cap);
 }
+// same for a hasher whose digests serialize to fewer than 32 bytes (Blake3_192: 24)
+long wfo_merkle_prove_batch_h(int hash_id, const uint8_t* leaves, const uint8_t* nodes, size_t nleaves, const uint64_t* idx, size_t k,
+                              uint8_t* leaves_out, uint8_t* out, size_t cap) {
+    return merkle_prove_batch(leaves, nodes, nleaves, idx, k, leaves_out, out, cap, digest_len(hash_id));
+}
 
 void wfo_transpose_slice(const uint64_t* src, size_t len, int d, size_t nf, uint64_t* dst) { transpose_slice(src, len, d, nf, dst); }
 void wfo_apply_drp(const uint64_t* tv, size_t rows, int d, size_t nf, uint64_t off, const uint64_t* alpha, uint64_t* out) {

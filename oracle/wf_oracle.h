@@ -73,6 +73,8 @@ void wfo_merkle_nodes(int hash_id, const uint8_t* leaves, size_t nleaves, uint8_
 long wfo_merkle_prove_batch(const uint8_t* leaves, const uint8_t* nodes, size_t nleaves,
                             const uint64_t* indexes, size_t k, uint8_t* leaves_out,
                             uint8_t* out, size_t out_cap);
+long wfo_merkle_prove_batch_h(int hash_id, const uint8_t* leaves, const uint8_t* nodes, size_t nleaves, const uint64_t* idx, size_t k,
+                              uint8_t* leaves_out, uint8_t* out, size_t cap);
 
 // ---- FRI (fri/src) ----
 void wfo_transpose_slice(const uint64_t* src, size_t len, int d, size_t folding, uint64_t* dst);

@@ -111,7 +111,7 @@ def test_row_hash_and_merkle_vs_oracle(ctx, oracle, h, cols):
     # batch openings (crypto/src/merkle/mod.rs:217-272)
     for pos in ([1], [1, 2], [1, 6], [3, 4, 5], [0, 7, 100, 101, rows - 1], list(range(8))):
         glv, gpr = t.open_many(pos)
-        wlv, wpr = oracle.merkle_prove_batch(want_lv, want_nd, pos)
+        wlv, wpr = oracle.merkle_prove_batch(want_lv, want_nd, pos, h)
         assert (glv == wlv).all() and gpr == wpr
     m.free(); t.free()
 
