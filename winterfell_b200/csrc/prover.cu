@@ -36,6 +36,9 @@
 // =================================================================================================
 #include "constraints_generic.cuh"  // ld_ext / seg_at, GenEvalParams, generic_constraints_kernel (also the source NVRTC compiles per AIR)
 
+#ifndef FIB_ROWS_D3
+#define FIB_ROWS_D3 2   // CE rows per thread sharing one inversion, cubic extension (register budget)
+#endif
 struct FibEvalParams {
     SegMatrix lde;      // N x 2k trace LDE
     SegMatrix out;      // ce x D combined constraint evaluations
@@ -60,7 +63,7 @@ struct FibEvalParams {
 template <int D>
 __global__ void __launch_bounds__(256) fib_constraints_kernel(FibEvalParams p) {
     extern __shared__ __align__(16) u64 fsm[];
-    constexpr int ROWS = D == 3 ? 2 : 4;
+    constexpr int ROWS = D == 3 ? FIB_ROWS_D3 : 4;
     for (u32 i = threadIdx.x; i < p.k * 5 * D; i += blockDim.x) fsm[i] = p.coef[i];
     __syncthreads();
     const size_t ce_all = (size_t)1 << (p.log_n + p.log_ce_blowup);
@@ -931,7 +934,7 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
         if (log_ceb > 3) return wf_fail(ctx, WF_ERR_STATE, "FibSmall has degree-1 constraints");  // FibEvalParams::zt[8]
         for (u32 i = 0; i < (1u << log_ceb); i++) p.zt[i] = zt[i];
         p.row0 = row0; p.ce_rows = ce_rows;
-        const size_t rows_per_thread = D == 3 ? 2 : 4;
+        const size_t rows_per_thread = D == 3 ? FIB_ROWS_D3 : 4;
         size_t threads = ((ce_rows ? ce_rows : ce) + rows_per_thread - 1) / rows_per_thread;
         fib_constraints_kernel<D><<<(unsigned)((threads + 255) / 256), 256, cf.size() * 8, ctx->st>>>(p);
         ctx->launches++;
