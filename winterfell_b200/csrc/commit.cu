@@ -97,6 +97,38 @@ __global__ void __launch_bounds__(256) hash_rows_blake3_w8c8_kernel(const u64* _
     digests[2 * row + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
 
+// rows of whole 8-column segments, at most one BLAKE3 chunk (<= 128 columns): segment g of the row IS message block g (64 bytes,
+// four 16-byte loads), chained through the chaining value; the next block's loads are issued before the current compression
+__global__ void __launch_bounds__(256) hash_rows_blake3_w8_kernel(const u64* __restrict__ base, size_t seg_stride, u32 nseg, size_t nrows,
+                                                                  uint4* __restrict__ digests, u32 dw) {
+    size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    const u32 one = b3_runtime_one();
+    u32 cv[8];
+    b3_iv(cv);
+    uint4 nx[4];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(base + row * 8);
+#pragma unroll
+        for (int k = 0; k < 4; k++) nx[k] = __ldg(src + k);
+    }
+    for (u32 g = 0; g < nseg; g++) {
+        u32 msg[16];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { msg[4 * k] = nx[k].x; msg[4 * k + 1] = nx[k].y; msg[4 * k + 2] = nx[k].z; msg[4 * k + 3] = nx[k].w; }
+        if (g + 1 < nseg) {
+            const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)(g + 1) * seg_stride + row * 8);
+#pragma unroll
+            for (int k = 0; k < 4; k++) nx[k] = __ldg(src + k);
+        }
+        const u32 fl = (g == 0 ? B3_CHUNK_START : 0) | (g == nseg - 1 ? (B3_CHUNK_END | B3_ROOT) : 0);
+        b3_compress(cv, msg, 0, 64, fl, one);
+    }
+    if (dw == 6) { cv[6] = 0; cv[7] = 0; }
+    digests[2 * row] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    digests[2 * row + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+
 __global__ void __launch_bounds__(256) hash_rows_blake3_kernel(RowSrc m, size_t nrows, uint4* __restrict__ digests, u32 dw) {
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nrows) return;
@@ -279,6 +311,8 @@ cudaError_t commit_hash_rows(int hash_id, const SegMatrix& m, u64* digests, cuda
         const u32 dw = WF_DIGEST_WORDS32(hash_id);
         if (m.W == 8 && m.cols == 8)
             hash_rows_blake3_w8c8_kernel<<<blocks, 256, 0, st>>>(m.base, m.rows, reinterpret_cast<uint4*>(digests), dw);
+        else if (m.W == 8 && m.cols % 8 == 0 && m.cols <= 128)
+            hash_rows_blake3_w8_kernel<<<blocks, 256, 0, st>>>(m.base, m.seg_stride, m.cols / 8, m.rows, reinterpret_cast<uint4*>(digests), dw);
         else
             hash_rows_blake3_kernel<<<blocks, 256, 0, st>>>(src, m.rows, reinterpret_cast<uint4*>(digests), dw);
     } else {

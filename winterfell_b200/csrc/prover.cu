@@ -279,7 +279,9 @@ struct DeepParams {
 //     thread sharing one batch inversion (math/src/utils/mod.rs:169).
 // (Tried and dropped: chains of rows i, i + b, ... that reuse 1 / (x_{i-b} - z) = g / (x_i - z g) to halve
 // the inversions — the strided row pattern cost more than the arithmetic saved.)
+#ifndef DEEP_SUM_THREADS
 #define DEEP_SUM_THREADS 256
+#endif
 template <int D>
 __global__ void __launch_bounds__(DEEP_SUM_THREADS) deep_sum_kernel(DeepParams p) {
     extern __shared__ __align__(16) u64 dsm[];
