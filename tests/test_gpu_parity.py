@@ -96,7 +96,7 @@ def test_interpolate_with_offset(ctx, oracle):
 
 
 @pytest.mark.parametrize("h", [wf.HASH_BLAKE3_256, wf.HASH_RP64_256, wf.HASH_RPJIVE64_256, wf.HASH_BLAKE3_192, wf.HASH_SHA3_256])
-@pytest.mark.parametrize("cols", [1, 2, 3, 4, 7, 8, 9, 16, 24, 64, 130])
+@pytest.mark.parametrize("cols", [1, 2, 3, 4, 7, 8, 9, 16, 24, 64, 128, 130])
 def test_row_hash_and_merkle_vs_oracle(ctx, oracle, h, cols):
     rows = 1024 if h in (wf.HASH_BLAKE3_256, wf.HASH_BLAKE3_192) else 256
     x = oracle.rand_elems((cols, rows), 31 * cols + h)

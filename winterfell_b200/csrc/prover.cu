@@ -1557,11 +1557,11 @@ int prove_fib_sharded(wf_ctx* ctx, const wf_comm* cm, const uint64_t* const* loc
     Channel<D> ch(h, seed);  // every rank replays the whole transcript
 
     wf_mat *trace = nullptr, *polys = nullptr, *lde = nullptr, *shard = nullptr, *comp_l = nullptr, *comp = nullptr, *cpolys = nullptr,
-           *clde = nullptr, *deep = nullptr, *fri_in = nullptr;
+           *clde = nullptr, *deep = nullptr, *fri_in = nullptr, *tstage = nullptr;
     ShardTree ttree, ctree;
     wf_fri* fri = nullptr;
-    ProofScope scope(ctx);
-    scope.own({&trace, &polys, &lde, &shard, &comp_l, &comp, &cpolys, &clde, &deep, &fri_in});
+    ProofScope scope(ctx);   // holds the ADDRESSES of these pointers: every owned pointer lives as long as the scope
+    scope.own({&trace, &polys, &lde, &shard, &comp_l, &comp, &cpolys, &clde, &deep, &fri_in, &tstage});
     scope.own({&ttree.local, &ctree.local});
     scope.fri = &fri;
     struct SLayer { u64* vals; size_t m_l, m_g; ShardTree tree; };
@@ -1605,8 +1605,7 @@ int prove_fib_sharded(wf_ctx* ctx, const wf_comm* cm, const uint64_t* const* loc
         sc.bytes_overlapped += (double)(G - 1) * nsl * (double)rows_per * 64;
         push = true;
     } else {
-    wf_mat* stage = nullptr;           // what arrives: [global segment][coset][nj][8]
-    scope.own({&stage});
+    wf_mat*& stage = tstage;           // what arrives: [global segment][coset][nj][8]
     CKI(wf_mat_alloc_w(ctx, N, cl, 8, &lde));          // mine, coset-major: [local segment][coset][n][8]
     CKI(wf_mat_alloc_w(ctx, rows_per, c, 8, &stage));
     // Preferred transport: every rank maps the others' `stage` buffers (CUDA IPC) and PUSHES its blocks there with peer copies
