@@ -373,6 +373,15 @@ def main():
         return {"ms": ms_step, "e2e_ms": e2e_step, "launches": launches, "breakdown": breakdown, "proof": p_e2e, "h2d": int(host_np.nbytes),
                 "wall_ms": wall_ms / steps, "clocks": sampler.summary() if sampler else None}
 
+    def fri_compressions(L):
+        """BLAKE3 compressions of the FRI commit phase on an L-point base-field codeword (folding 4): every layer of n points
+        hashes n/4 leaves of 32 bytes (one compression each) and n/4 - 1 tree nodes; layers until the remainder's domain."""
+        tot, n = 0, L
+        while n > (REM_MAX_DEG + 1) << LOG_BLOWUP:
+            tot += n // FOLDING + n // FOLDING - 1
+            n //= FOLDING
+        return tot
+
     def fri_sweep():
         """BASELINE.json configs[4]: FRI commit phase alone (fold + leaf hash + Merkle tree of every layer, device-side coin) on
         2^20 .. 2^26-point base-field codewords (LDE, blowup 8, of random polynomials), folding 4, remainder max degree 31,
@@ -497,8 +506,13 @@ def main():
                                  "points": [{"log2_len": ll, "ms": round(ms, 4),
                                              "GBps_per_gpu": round(fri_algorithmic_bytes(1 << ll, 1) / (ms * 1e-3) / 1e9, 1),
                                              "frac_of_hbm": round(fri_algorithmic_bytes(1 << ll, 1) / (ms * 1e-3) / 1e9 / hbm, 4),
-                                             "aggregate_GBps": round(world * fri_algorithmic_bytes(1 << ll, 1) / (ms * 1e-3) / 1e9, 1)}
-                                            for ll, ms in sweep]}
+                                             "aggregate_GBps": round(world * fri_algorithmic_bytes(1 << ll, 1) / (ms * 1e-3) / 1e9, 1),
+                                             # the layers' leaf hashes and trees are BLAKE3 compressions on the INT32 pipes: the bound that
+                                             # applies before HBM does (one per 32-byte leaf of 4 evaluations + one per tree node)
+                                             "blake3_compressions": fri_compressions(1 << ll),
+                                             "frac_of_compress_ceiling": round(fri_compressions(1 << ll) / (ms * 1e-3) / 1e9 / compress_gps, 4)}
+                                            for ll, ms in sweep],
+                                 "compress_ceiling_G_per_s": compress_gps}
         if not args.no_cpu_baseline:
             # bounded sample of the same workload in a fresh process (torch has already initialised libgomp here with the
             # spinning wait policy): the same AIR / columns / extension on 1/16 of the rows; the value is the SAMPLE's own
