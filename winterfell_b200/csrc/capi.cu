@@ -1081,6 +1081,18 @@ int wf_fri_free(wf_ctx* ctx, wf_fri* f) {
     return WF_OK;
 }
 
+}  // extern "C"
+// What a commit phase under construction owns: the wf_fri with its finished layers, the tree of the layer in flight and the
+// scratch buffers — all of it returns to the pool on every early error return.
+struct FriBuild {
+    wf_ctx* ctx;
+    wf_fri* f;
+    wf_tree* t = nullptr;
+    DevScratch tmp;
+    FriBuild(wf_ctx* c, wf_fri* fr) : ctx(c), f(fr), tmp(c) {}
+    ~FriBuild() { if (t) wf_tree_free(ctx, t); if (f) wf_fri_free(ctx, f); }
+};
+extern "C" {
 int wf_fri_build_layers(wf_ctx* ctx, int hash_id, const wf_mat* evals, int d, uint32_t folding, uint32_t rem_max_deg,
                         uint32_t blowup, wf_fri_commit_fn commit, wf_fri_draw_fn draw_alpha, void* user, wf_fri** out) {
     if (!ctx || !evals || !commit || !draw_alpha || !out) return wf_fail(ctx, WF_ERR_INVALID, "bad arguments");
@@ -1090,19 +1102,20 @@ int wf_fri_build_layers(wf_ctx* ctx, int hash_id, const wf_mat* evals, int d, ui
     u32 logL;
     if (log2_exact(len, &logL)) return wf_fail(ctx, WF_ERR_INVALID, "domain size must be a power of two");
     wf_fri* f = new wf_fri();
+    FriBuild g(ctx, f);
     f->hash_id = hash_id; f->d = d; f->folding = folding; f->blowup = blowup;
     f->ld = evals->m.W;  // d base columns live in one segment of width W >= d
     const int ld = f->ld;
     // layer 0 evaluations: copy of the segment (the prover keeps its own copy, fri/src/prover/mod.rs:217-221)
     void* cur;
-    CKI(wf_dev_alloc(ctx, len * ld * 8, &cur));
+    CKI(g.tmp.alloc(len * ld * 8, &cur));
     CK(cudaMemcpyAsync(cur, evals->m.base, len * ld * 8, cudaMemcpyDeviceToDevice, ctx->st));
     size_t max_rem = (size_t)(rem_max_deg + 1) * blowup;  // fri/src/options.rs:85-93
     while (len > max_rem) {
         size_t m = len / folding;
         wf_tree* t;
-        int r = tree_alloc(ctx, hash_id, m, &t);
-        if (r != WF_OK) { wf_dev_free(ctx, cur); wf_fri_free(ctx, f); return r; }
+        CKI(tree_alloc(ctx, hash_id, m, &t));
+        g.t = t;
         CK(fri_hash_layer(hash_id, (u64*)cur, len, d, ld, (int)folding, t->leaves, ctx->st));
         CK(commit_merkle_nodes(hash_id, t->leaves, m, t->nodes, ctx->st));
         ctx->launches += 1 + merkle_launches(m);
@@ -1117,11 +1130,12 @@ int wf_fri_build_layers(wf_ctx* ctx, int hash_id, const wf_mat* evals, int d, ui
         while (((size_t)1 << ll) < len) ll++;
         CKI(wf_get_twiddles(ctx, ll, &master));
         void* nxt;
-        CKI(wf_dev_alloc(ctx, m * ld * 8, &nxt));
+        CKI(g.tmp.alloc(m * ld * 8, &nxt));
         if (ld > d) CK(cudaMemsetAsync(nxt, 0, m * ld * 8, ctx->st));
         CK(fri_fold_layer((u64*)cur, len, d, ld, (int)folding, alpha, master, (u64*)nxt, ld, ctx->st));
         ctx->launches++;
-        f->layers.push_back(FriLayer{(u64*)cur, len, t});
+        f->layers.push_back(FriLayer{(u64*)g.tmp.keep(cur), len, t});   // the wf_fri owns layer and tree from here
+        g.t = nullptr;
         cur = nxt;
         len = m;
     }
@@ -1129,7 +1143,7 @@ int wf_fri_build_layers(wf_ctx* ctx, int hash_id, const wf_mat* evals, int d, ui
     std::vector<u64> raw(len * ld), v(len * d);
     CK(cudaMemcpyAsync(raw.data(), cur, len * ld * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    wf_dev_free(ctx, cur);
+    g.tmp.free(cur);
     for (size_t i = 0; i < len; i++)
         for (int c = 0; c < d; c++) v[i * d + c] = raw[i * ld + c];
     wf_host_dft(v, len, d, true, GL_GENERATOR);
@@ -1139,6 +1153,7 @@ int wf_fri_build_layers(wf_ctx* ctx, int hash_id, const wf_mat* evals, int d, ui
         for (int c = 0; c < d; c++) f->remainder[i * d + c] = v[(rsize - 1 - i) * d + c];
     Digest rc = hh_hash_elements(hash_id, f->remainder.data(), f->remainder.size());
     commit(user, rc.b);
+    g.f = nullptr;   // the caller's now
     *out = f;
     return WF_OK;
 }
@@ -1158,6 +1173,7 @@ int wf_fri_build_layers_coin(wf_ctx* ctx, int hash_id, const wf_mat* evals, int 
     u32 logL;
     if (log2_exact(len, &logL)) return wf_fail(ctx, WF_ERR_INVALID, "domain size must be a power of two");
     wf_fri* f = new wf_fri();
+    FriBuild g(ctx, f);
     f->hash_id = hash_id; f->d = d; f->folding = folding; f->blowup = blowup;
     f->ld = evals->m.W;
     const int ld = f->ld;
@@ -1165,11 +1181,11 @@ int wf_fri_build_layers_coin(wf_ctx* ctx, int hash_id, const wf_mat* evals, int 
     size_t nlayers = 0;
     for (size_t l = len; l > max_rem; l /= folding) nlayers++;
     void *cur, *dstate, *dalpha, *dlog;
-    CKI(wf_dev_alloc(ctx, len * ld * 8, &cur));
+    CKI(g.tmp.alloc(len * ld * 8, &cur));
     CK(cudaMemcpyAsync(cur, evals->m.base, len * ld * 8, cudaMemcpyDeviceToDevice, ctx->st));
-    CKI(wf_dev_alloc(ctx, 8 * 8, &dstate));
-    CKI(wf_dev_alloc(ctx, 8 * 8, &dalpha));
-    CKI(wf_dev_alloc(ctx, std::max<size_t>(nlayers, 1) * 8 * 8, &dlog));
+    CKI(g.tmp.alloc(8 * 8, &dstate));
+    CKI(g.tmp.alloc(8 * 8, &dalpha));
+    CKI(g.tmp.alloc(std::max<size_t>(nlayers, 1) * 8 * 8, &dlog));
     u64 seed_words[4];
     memcpy(seed_words, coin.seed.b, 32);
     CK(cudaMemcpyAsync(dstate, seed_words, 32, cudaMemcpyHostToDevice, ctx->st));
@@ -1177,8 +1193,8 @@ int wf_fri_build_layers_coin(wf_ctx* ctx, int hash_id, const wf_mat* evals, int 
     while (len > max_rem) {
         size_t m = len / folding;
         wf_tree* t;
-        int r = tree_alloc(ctx, hash_id, m, &t);
-        if (r != WF_OK) { wf_dev_free(ctx, cur); wf_fri_free(ctx, f); return r; }
+        CKI(tree_alloc(ctx, hash_id, m, &t));
+        g.t = t;
         CK(fri_hash_layer(hash_id, (u64*)cur, len, d, ld, (int)folding, t->leaves, ctx->st));
         CK(commit_merkle_nodes(hash_id, t->leaves, m, t->nodes, ctx->st));
         CK(fri_coin_step(hash_id, (u64*)dstate, t->nodes + 4, d, (u64*)dalpha, (u64*)dlog + 8 * layer, ctx->st));
@@ -1188,11 +1204,12 @@ int wf_fri_build_layers_coin(wf_ctx* ctx, int hash_id, const wf_mat* evals, int 
         while (((size_t)1 << ll) < len) ll++;
         CKI(wf_get_twiddles(ctx, ll, &master));
         void* nxt;
-        CKI(wf_dev_alloc(ctx, m * ld * 8, &nxt));
+        CKI(g.tmp.alloc(m * ld * 8, &nxt));
         if (ld > d) CK(cudaMemsetAsync(nxt, 0, m * ld * 8, ctx->st));
         CK(fri_fold_layer((u64*)cur, len, d, ld, (int)folding, nullptr, master, (u64*)nxt, ld, ctx->st, (const u64*)dalpha));
         ctx->launches++;
-        f->layers.push_back(FriLayer{(u64*)cur, len, t});
+        f->layers.push_back(FriLayer{(u64*)g.tmp.keep(cur), len, t});   // the wf_fri owns layer and tree from here
+        g.t = nullptr;
         cur = nxt;
         len = m;
         layer++;
@@ -1201,8 +1218,8 @@ int wf_fri_build_layers_coin(wf_ctx* ctx, int hash_id, const wf_mat* evals, int 
     CK(cudaMemcpyAsync(raw.data(), cur, len * ld * 8, cudaMemcpyDeviceToHost, ctx->st));
     if (nlayers) CK(cudaMemcpyAsync(log.data(), dlog, nlayers * 8 * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    wf_dev_free(ctx, cur);
-    wf_dev_free(ctx, dstate); wf_dev_free(ctx, dalpha); wf_dev_free(ctx, dlog);
+    g.tmp.free(cur);
+    g.tmp.free(dstate); g.tmp.free(dalpha); g.tmp.free(dlog);
     // replay on the host coin: commit_fri_layer, draw_fri_alpha (prover/src/channel.rs:215-234)
     for (size_t l = 0; l < nlayers; l++) {
         Digest root;
@@ -1212,7 +1229,7 @@ int wf_fri_build_layers_coin(wf_ctx* ctx, int hash_id, const wf_mat* evals, int 
         u64 alpha[3] = {0, 0, 0};
         bool ok = coin.draw(d, alpha) && log[8 * l + 7] == 1;
         for (int k = 0; k < d; k++) ok = ok && alpha[k] == log[8 * l + 4 + k];
-        if (!ok) { wf_fri_free(ctx, f); return wf_fail(ctx, WF_ERR_STATE, "device and host FRI transcripts diverged at layer %zu", l); }
+        if (!ok) return wf_fail(ctx, WF_ERR_STATE, "device and host FRI transcripts diverged at layer %zu", l);
     }
     // remainder (fri/src/prover/mod.rs:230-239)
     for (size_t i = 0; i < len; i++)
@@ -1225,6 +1242,7 @@ int wf_fri_build_layers_coin(wf_ctx* ctx, int hash_id, const wf_mat* evals, int 
     Digest rc = hh_hash_elements(hash_id, f->remainder.data(), f->remainder.size());
     commitments.push_back(rc);
     coin.reseed(rc);
+    g.f = nullptr;   // the caller's now
     *out = f;
     return WF_OK;
 }

@@ -113,6 +113,24 @@ int wf_jit_compile(const std::string& src, std::vector<char>& cubin, std::string
 int wf_jit_get_kernel(wf_ctx* ctx, const std::string& src, cudaKernel_t* kernel);
 int wf_dev_alloc(wf_ctx* ctx, size_t bytes, void** out);
 void wf_dev_free(wf_ctx* ctx, void* p);
+// Scratch buffers of one call: whatever is still registered when the scope ends (every early error return included) goes back
+// to the context's pool. free() hands one back early, keep() passes ownership on (the buffer outlives the call).
+struct DevScratch {
+    wf_ctx* ctx;
+    std::vector<void*> bufs;
+    explicit DevScratch(wf_ctx* c) : ctx(c) {}
+    DevScratch(const DevScratch&) = delete;
+    DevScratch& operator=(const DevScratch&) = delete;
+    ~DevScratch() { for (void* p : bufs) if (p) wf_dev_free(ctx, p); }
+    int alloc(size_t bytes, void** out) {
+        int r = wf_dev_alloc(ctx, bytes, out);
+        if (r == WF_OK) bufs.push_back(*out);
+        return r;
+    }
+    void forget(void* p) { for (void*& q : bufs) if (q == p) { q = nullptr; return; } }
+    void free(void* p) { if (!p) return; forget(p); wf_dev_free(ctx, p); }
+    void* keep(void* p) { forget(p); return p; }
+};
 int wf_mat_alloc(wf_ctx* ctx, size_t rows, u32 cols, wf_mat** out);
 int wf_mat_alloc_w(wf_ctx* ctx, size_t rows, u32 cols, int W, wf_mat** out);
 // LDE output scattered into the row shards of the ranks of a sharded proof (NttPassParams::sc_*, ntt.cuh)

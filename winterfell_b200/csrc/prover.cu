@@ -749,20 +749,21 @@ template <int D>
 int ood_eval(wf_ctx* ctx, const std::vector<const wf_mat*>& mats, const GlExt<D>& z0, const GlExt<D>& z1,
              std::vector<std::vector<GlExt<D>>>& out) {
     const int nm = (int)mats.size();
+    DevScratch tmp(ctx);               // every buffer below returns to the pool on any exit
     std::vector<void*> part(nm);
     void* res;
     size_t total_cols = 0;
     for (auto* m : mats) total_cols += m->m.cols;
     out.assign(2 * nm, {});
-    CKI(wf_dev_alloc(ctx, total_cols * 2 * D * 8, &res));
+    CKI(tmp.alloc(total_cols * 2 * D * 8, &res));
     size_t off = 0;
     std::vector<void*> zbs(nm, nullptr);
     for (int m = 0; m < nm; m++) {
         const size_t n = mats[m]->m.rows;
         const u32 chunks = (u32)((n + OOD_ROWS_PER_BLOCK - 1) / OOD_ROWS_PER_BLOCK);
         const u32 cols = mats[m]->m.cols;
-        CKI(wf_dev_alloc(ctx, (size_t)cols * chunks * 2 * D * 8, &part[m]));
-        CKI(wf_dev_alloc(ctx, (size_t)2 * chunks * D * 8, &zbs[m]));
+        CKI(tmp.alloc((size_t)cols * chunks * 2 * D * 8, &part[m]));
+        CKI(tmp.alloc((size_t)2 * chunks * D * 8, &zbs[m]));
         ood_pow_kernel<D><<<(2 * chunks + 127) / 128, 128, 0, ctx->st>>>(z0, z1, chunks, (u64*)zbs[m]);
         ood_partial_kernel<D><<<dim3(chunks, mats[m]->m.nseg()), 256, 0, ctx->st>>>(mats[m]->m, z0, z1, (const u64*)zbs[m], (u64*)part[m], chunks);
         ood_reduce_kernel<D><<<(2 * cols * 32 + 255) / 256, 256, 0, ctx->st>>>((const u64*)part[m], cols, chunks, (u64*)res + off);
@@ -773,9 +774,6 @@ int ood_eval(wf_ctx* ctx, const std::vector<const wf_mat*>& mats, const GlExt<D>
     std::vector<u64> host(total_cols * 2 * D);
     CK(cudaMemcpyAsync(host.data(), res, host.size() * 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    for (void* pp : part) wf_dev_free(ctx, pp);
-    for (void* pp : zbs) wf_dev_free(ctx, pp);
-    wf_dev_free(ctx, res);
     off = 0;
     for (int m = 0; m < nm; m++) {
         const u32 cols = mats[m]->m.cols;
@@ -893,13 +891,19 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
         u64 o_n = gl_pow(GL_GENERATOR, n), w_ceb = gl_root_of_unity(log_ceb);
         for (u32 i = 0; i < (1u << log_ceb); i++) zt[i] = gl_inv(gl_sub(gl_mul(o_n, gl_pow(w_ceb, i)), 1));
     }
-    std::vector<void*> scratch;  // device buffers of this stage
+    // device buffers of this stage; `comp` too until it is handed to the caller (returned to the pool on every error path)
+    struct StageBufs {
+        DevScratch dev;
+        wf_mat* comp;
+        std::vector<wf_mat*> mats;
+        StageBufs(wf_ctx* c, wf_mat* m) : dev(c), comp(m) {}
+        ~StageBufs() { if (comp) wf_mat_free(dev.ctx, comp); for (wf_mat* t : mats) wf_mat_free(dev.ctx, t); }
+    } stage(ctx, comp);
     auto upload = [&](const void* src, size_t bytes, void** out) -> int {
         void* p;
-        CKI(wf_dev_alloc(ctx, std::max(bytes, (size_t)8), &p));
+        CKI(stage.dev.alloc(std::max(bytes, (size_t)8), &p));
         // stream-ordered copy; the (pageable) source vectors stay alive until the synchronisation below
         if (bytes) CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->st));
-        scratch.push_back(p);
         *out = p;
         return WF_OK;
     };
@@ -974,7 +978,7 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
         std::vector<u32> goff = {0}, ecol, etstride, eshift;
         std::vector<u64> ga, gb, goa, eval, ecc;
         std::vector<const u64*> etab;
-        std::vector<wf_mat*> seq_tables;  // freed after the kernel
+        std::vector<wf_mat*>& seq_tables = stage.mats;  // returned to the pool when the stage ends (stream-ordered: after the kernel)
         for (auto& kv : groups) {
             u64 a = kv.first.first == 0 ? 1 : n / kv.first.first;
             ga.push_back(a);
@@ -1065,10 +1069,9 @@ int eval_constraints(wf_ctx* ctx, const AirHost& air, const wf_mat* lde, const w
         }
         ctx->launches++;
         CK(cudaGetLastError());
-        for (wf_mat* t : seq_tables) wf_mat_free(ctx, t);  // stream-ordered pool: reuse is ordered after the kernel
     }
     CK(cudaStreamSynchronize(ctx->st));
-    for (void* sp : scratch) wf_dev_free(ctx, sp);
+    stage.comp = nullptr;   // the caller's now
     *out = comp;
     return WF_OK;
 }
@@ -1266,10 +1269,11 @@ int prove_air(wf_ctx* ctx, const AirHost& air_in, const uint64_t* const* trace_c
         // E column j -> D base columns j*D + q (rows of the LDE then serialise exactly like [E] rows)
         std::vector<const u64*> cols(aw);
         for (u32 j = 0; j < aw; j++) cols[j] = &aux_host[(size_t)j * n * D];
-        wf_mat* atrace;
+        wf_mat* atrace = nullptr;
         CKI(wf_mat_from_host_columns(ctx, cols.data(), aw, n, D, mont, &atrace));
-        CKI(wf_mat_interpolate(ctx, atrace, &apolys));
+        int ir = wf_mat_interpolate(ctx, atrace, &apolys);
         wf_mat_free(ctx, atrace);
+        if (ir != WF_OK) return ir;
         CKI(wf_mat_lde(ctx, apolys, log_b, &alde));
         CKI(wf_commit_rows_partitioned(ctx, h, alde, o.part_words(aw, D), &atree));
         CKI(wf_tree_root(ctx, atree, root));
