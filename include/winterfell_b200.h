@@ -63,6 +63,10 @@ const char* wf_last_error(const wf_ctx* ctx);
 int wf_ctx_sync(wf_ctx* ctx);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 uint64_t wf_ctx_launch_count(const wf_ctx* ctx);
+/* device memory this ctx holds: buffers handed out and not yet freed (count and bytes: the matrices, trees, FRI layers the
+ * caller still owns) and bytes parked in the ctx's pool for reuse. After every handle is freed, live_buffers is 0 — also
+ * after a call that returned an error. Any of the pointers may be NULL. */
+int wf_ctx_mem_stats(const wf_ctx* ctx, uint64_t* live_buffers, uint64_t* live_bytes, uint64_t* pooled_bytes);
 const char* wf_version(void);
 /* stage tracing (the reference's `tracing` spans, prover/src/lib.rs:312-466): when on, the proving
  * entry points record a CUDA event at every stage boundary; wf_ctx_stage_times returns the stage

@@ -336,3 +336,31 @@ def test_compiled_constraint_kernel_aux_segment(ctx, oracle):
     ctx.set_jit(False)
     assert ctx.prove_air_aux(desc, trace, opts, builder, airs.PERM_RAP_AUX_WIDTH, 2) == want
     ctx.set_jit(True)
+
+
+def test_no_device_buffers_left_behind(oracle):
+    # every proof entry point — succeeding or refusing its input — hands all of its device buffers back to the context's
+    # pool (wf_ctx_mem_stats: nothing live once the caller holds no handle)
+    c = wf.Context(0)
+    try:
+        trace, results = oracle.build_fib_trace(4, 1 << 10)
+        opts = oracle.make_opts(ext=3, grinding=2, folding=4, rem_max_deg=7)
+        c.prove_fib(trace, results, opts)
+        desc, tr = airs.sequence_mix(1 << 8)
+        c.prove_air(desc, tr, oracle.make_opts(num_queries=8, blowup=8, ext=2))
+        with pytest.raises(wf.WfError):
+            c.prove_air(desc, tr[:, :128].copy(), oracle.make_opts(num_queries=8, blowup=8))
+        d2, t2, builder = airs.perm_rap(128)
+        c.prove_air_aux(d2, t2, oracle.make_opts(num_queries=16, blowup=8, ext=2, folding=4, rem_max_deg=7), builder, airs.PERM_RAP_AUX_WIDTH, 2)
+        with pytest.raises(wf.WfError):
+            c.prove_fib(trace, results, oracle.make_opts(num_partitions=17, hash_rate=8))
+        m = c.mat_from_host_columns(oracle.rand_elems((1, 1 << 12), 5))
+        cw = m.lde(3)
+        assert c.mem_stats()[0] == 2           # the two matrices the test holds
+        f, _ = c.fri_build_layers_default(wf.HASH_BLAKE3_256, cw, 1, 4, 7, 8)
+        assert c.mem_stats()[0] > 2            # + the FRI layers and their trees
+        f.free(); m.free(); cw.free()
+        live, live_bytes, pooled = c.mem_stats()
+        assert live == 0 and live_bytes == 0 and pooled > 0
+    finally:
+        c.close()

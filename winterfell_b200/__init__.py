@@ -39,6 +39,7 @@ _SIGS = [
     ("wf_last_error", C.c_char_p, [vp]),
     ("wf_ctx_sync", C.c_int, [vp]),
     ("wf_ctx_launch_count", C.c_uint64, [vp]),
+    ("wf_ctx_mem_stats", C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("wf_version", C.c_char_p, []),
     ("wf_ctx_set_profiling", C.c_int, [vp, C.c_int]),
     ("wf_ctx_stage_times", C.c_int, [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_size_t)]),
@@ -178,6 +179,12 @@ class Context:
     @property
     def launches(self):
         return self.L.wf_ctx_launch_count(self.h)
+
+    def mem_stats(self):
+        """(live_buffers, live_bytes, pooled_bytes): device buffers handed out and not yet freed, and bytes parked for reuse."""
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self.check(self.L.wf_ctx_mem_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     # ---- matrices ----
     def mat_from_host_columns(self, cols, ext_degree=1, mont=False):

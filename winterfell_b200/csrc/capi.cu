@@ -501,6 +501,16 @@ int wf_ctx_stage_times(wf_ctx* ctx, char* names, size_t names_cap, float* ms, si
 const char* wf_last_error(const wf_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (is a CUDA device present?)"; }
 int wf_ctx_sync(wf_ctx* ctx) { wf_use_device(ctx); CK(cudaStreamSynchronize(ctx->st)); return WF_OK; }
 uint64_t wf_ctx_launch_count(const wf_ctx* ctx) { return ctx->launches; }
+int wf_ctx_mem_stats(const wf_ctx* ctx, uint64_t* live_buffers, uint64_t* live_bytes, uint64_t* pooled_bytes) {
+    if (!ctx) return WF_ERR_INVALID;
+    uint64_t lb = 0, pb = 0;
+    for (auto& kv : ctx->live) lb += kv.second;
+    for (auto& kv : ctx->pool) pb += kv.first;
+    if (live_buffers) *live_buffers = ctx->live.size();
+    if (live_bytes) *live_bytes = lb;
+    if (pooled_bytes) *pooled_bytes = pb;
+    return WF_OK;
+}
 
 // ---- matrices -----------------------------------------------------------------------------------
 int wf_mat_from_device_columns(wf_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, size_t nrows, wf_mat** out) {
