@@ -26,38 +26,60 @@ namespace rp64_host {
 #define RP64_TAB(name) rp64_host::name
 #endif
 
+// The S-box arithmetic runs on words that are only reduced below 2^64 (gl_mul_weak): every chain ends in the MDS product,
+// which takes any 64-bit words and returns canonical ones.
 GL_HD u64 rp64_exp7(u64 x) {  // f64/mod.rs:96
-    u64 x2 = gl_sqr(x), x4 = gl_sqr(x2), x3 = gl_mul(x2, x);
-    return gl_mul(x3, x4);
+    u64 x2 = gl_mul_weak(x, x), x4 = gl_mul_weak(x2, x2), x3 = gl_mul_weak(x2, x);
+    return gl_mul_weak(x3, x4);
 }
 
-// x^(1/7) = x^10540996611094048183, addition chain of apply_inv_sbox (:351-385), per element
-GL_HD u64 rp64_inv7(u64 x) {
-    u64 t1 = gl_sqr(x);            // x^(0b10)
-    u64 t2 = gl_sqr(t1);           // x^(0b100)
-    u64 t3 = t2;                   // exp_acc<3>(t2, t2)
+// x^(1/7) = x^10540996611094048183 for G state elements at once, the addition chain of apply_inv_sbox (:351-385):
+//   t1 = x^2, t2 = t1^2, t3 = t2^(2^3) t2, t4 = t3^(2^6) t3, t5 = t4^(2^12) t4, t6 = t5^(2^6) t3, t7 = t6^(2^31) t6,
+//   result = ((t7^2 t6)^2)^2 * (t1 t2 x).
+// The G chains are independent: the element loops are unrolled inside the (rolled) squaring loops, so G multiplications are in
+// flight per thread (the first version walked one element's 72 dependent squarings at a time and ran at 0.4 instructions per
+// clock and scheduler). Live values: four per element (the t1 t2 x product, t3, the saved factor, the running power).
+#ifndef RP64_GROUP
+#define RP64_GROUP 6
+#endif
+template <int G>
+GL_HD void rp64_inv7_group(u64* s) {
+    u64 b[G], t3[G], p[G], acc[G];
 #pragma unroll
-    for (int i = 0; i < 3; i++) t3 = gl_sqr(t3);
-    t3 = gl_mul(t3, t2);
-    u64 t4 = t3;                   // exp_acc<6>(t3, t3)
+    for (int e = 0; e < G; e++) {
+        const u64 x = s[e];
+        const u64 t1 = gl_mul_weak(x, x);
+        const u64 t2 = gl_mul_weak(t1, t1);
+        b[e] = gl_mul_weak(gl_mul_weak(t1, t2), x);
+        p[e] = t2;
+        acc[e] = t2;
+    }
+#define RP64_SQ(n)                                              \
+    _Pragma("unroll 1") for (int i = 0; i < (n); i++) {         \
+        _Pragma("unroll") for (int e = 0; e < G; e++) acc[e] = gl_mul_weak(acc[e], acc[e]); \
+    }
+    RP64_SQ(3)
 #pragma unroll
-    for (int i = 0; i < 6; i++) t4 = gl_sqr(t4);
-    t4 = gl_mul(t4, t3);
-    u64 t5 = t4;                   // exp_acc<12>(t4, t4)
+    for (int e = 0; e < G; e++) { acc[e] = gl_mul_weak(acc[e], p[e]); t3[e] = acc[e]; }             // t3
+    RP64_SQ(6)
 #pragma unroll
-    for (int i = 0; i < 12; i++) t5 = gl_sqr(t5);
-    t5 = gl_mul(t5, t4);
-    u64 t6 = t5;                   // exp_acc<6>(t5, t3)
+    for (int e = 0; e < G; e++) { acc[e] = gl_mul_weak(acc[e], t3[e]); p[e] = acc[e]; }             // t4
+    RP64_SQ(12)
 #pragma unroll
-    for (int i = 0; i < 6; i++) t6 = gl_sqr(t6);
-    t6 = gl_mul(t6, t3);
-    u64 t7 = t6;                   // exp_acc<31>(t6, t6)
-#pragma unroll 1
-    for (int i = 0; i < 31; i++) t7 = gl_sqr(t7);
-    t7 = gl_mul(t7, t6);
-    u64 a = gl_sqr(gl_sqr(gl_mul(gl_sqr(t7), t6)));
-    u64 b = gl_mul(gl_mul(t1, t2), x);
-    return gl_mul(a, b);
+    for (int e = 0; e < G; e++) acc[e] = gl_mul_weak(acc[e], p[e]);                                 // t5
+    RP64_SQ(6)
+#pragma unroll
+    for (int e = 0; e < G; e++) { acc[e] = gl_mul_weak(acc[e], t3[e]); p[e] = acc[e]; }             // t6
+    RP64_SQ(31)
+#pragma unroll
+    for (int e = 0; e < G; e++) {
+        u64 a = gl_mul_weak(acc[e], p[e]);                                                          // t7
+        a = gl_mul_weak(gl_mul_weak(a, a), p[e]);
+        a = gl_mul_weak(a, a);
+        a = gl_mul_weak(a, a);
+        s[e] = gl_mul_weak(a, b[e]);
+    }
+#undef RP64_SQ
 }
 
 GL_HD void rp64_mds(u64 s[12]) {
@@ -89,7 +111,7 @@ GL_HD void rp64_permute(u64 s[12]) {
 #pragma unroll
         for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], RP64_TAB(RP64_ARK1)[r][i]);
 #pragma unroll 1
-        for (int i = 0; i < 12; i++) s[i] = rp64_inv7(s[i]);
+        for (int g = 0; g < 12; g += RP64_GROUP) rp64_inv7_group<RP64_GROUP>(s + g);
         rp64_mds(s);
 #pragma unroll
         for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], RP64_TAB(RP64_ARK2)[r][i]);

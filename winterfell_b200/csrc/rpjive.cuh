@@ -8,7 +8,7 @@
 // The MDS is the circulant with first row [23, 8, 13, 10, 7, 6, 21, 8] (:417; the reference multiplies through a real FFT,
 // mds_f64_8x8.rs) — entries < 32, so the product is accumulated from 32-bit halves without reduction, as in rp64.cuh.
 #pragma once
-#include "rp64.cuh"  // rp64_exp7 / rp64_inv7: the S-boxes are the same maps x^7 and x^(1/7) (mod.rs:366-412)
+#include "rp64.cuh"  // rp64_exp7 / rp64_inv7_group: the S-boxes are the same maps x^7 and x^(1/7) (mod.rs:366-412)
 
 #ifdef __CUDACC__
 #define RPJ_CONST_QUAL static __device__ __constant__ const
@@ -55,7 +55,7 @@ GL_HD void rpj_permute(u64 s[8]) {
 #pragma unroll
         for (int i = 0; i < 8; i++) s[i] = gl_add(s[i], RPJ_TAB(RPJ_ARK1)[r][i]);
 #pragma unroll 1
-        for (int i = 0; i < 8; i++) s[i] = rp64_inv7(s[i]);
+        for (int g = 0; g < 8; g += 4) rp64_inv7_group<4>(s + g);
         rpj_mds(s);
 #pragma unroll
         for (int i = 0; i < 8; i++) s[i] = gl_add(s[i], RPJ_TAB(RPJ_ARK2)[r][i]);

@@ -318,8 +318,10 @@ def bench_sharded(ctx, stream, cfg, steps, warmup, configs, proof_opts, flush, c
         dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, k):
-        total = 0.0
+    step_log = {}
+
+    def timed(fn, k, name):
+        total, per = 0.0, []
         for _ in range(k):
             flush.zero_()
             barrier()                                                    # ranks start a proof together
@@ -328,7 +330,9 @@ def bench_sharded(ctx, stream, cfg, steps, warmup, configs, proof_opts, flush, c
             fn()
             b.record(stream)
             b.synchronize()
-            total += a.elapsed_time(b)
+            per.append(a.elapsed_time(b))
+            total += per[-1]
+        step_log[name] = per
         return total / k
 
     with torch.cuda.stream(stream):
@@ -346,11 +350,11 @@ def bench_sharded(ctx, stream, cfg, steps, warmup, configs, proof_opts, flush, c
         sampler.start()
         l0 = ctx.launches
         t0 = time.perf_counter()
-        ms = timed(step_resident, steps)
+        ms = timed(step_resident, steps, "resident")
         wall = (time.perf_counter() - t0) * 1e3 / steps
         launches = int(ctx.launches - l0) // max(steps, 1)
         res_stats = dict(stats)
-        e2e = timed(step_e2e, steps)
+        e2e = timed(step_e2e, steps, "e2e")
         sampler.stop_flag = True
         sampler.join(timeout=2)
         flush.zero_()
@@ -359,6 +363,12 @@ def bench_sharded(ctx, stream, cfg, steps, warmup, configs, proof_opts, flush, c
         step_resident()
         breakdown = {k: round(v, 4) for k, v in ctx.stage_times()}
         ctx.set_profiling(False)
+    # every rank's device time of every timed step (ms): the reported value is the max over ranks of the per-rank means
+    per_rank = torch.tensor([step_log["resident"], step_log["e2e"]], device="cuda", dtype=torch.float64)
+    gathered = [torch.empty_like(per_rank) for _ in range(world)]
+    dist.all_gather(gathered, per_rank)
+    step_ms_by_rank = {"resident": [[round(float(x), 3) for x in g[0]] for g in gathered],
+                       "e2e": [[round(float(x), 3) for x in g[1]] for g in gathered]}
     gbps = res_stats["bytes_sent"] / max(res_stats["exchange_ms"], 1e-9) / 1e6
     bd_ex = breakdown.get("trace_exchange", 0.0)
     return {"ms": ms, "e2e_ms": e2e, "launches": launches, "breakdown": breakdown, "proof": proof, "h2d": int(host_np.nbytes) * world,
@@ -380,4 +390,4 @@ def bench_sharded(ctx, stream, cfg, steps, warmup, configs, proof_opts, flush, c
                      "blocking_bytes_sent_per_rank": int(res_stats["bytes_sent"]), "blocking_exchange_ms_rank0": round(res_stats["exchange_ms"], 3),
                      "blocking_exchange_GBps_per_rank": round(gbps, 1), "collectives_per_proof": int(res_stats["collectives"]),
                      "host_collective_ms": round(res_stats["small_collective_ms"], 3), "sharded_fri_layers": int(res_stats["sharded_fri_layers"]),
-                     "byte_identical_to_single_gpu": identical}}
+                     "byte_identical_to_single_gpu": identical, "step_ms_by_rank": step_ms_by_rank}}
