@@ -18,6 +18,8 @@ prover/src/trace/trace_lde/default/mod.rs:63, :245-282):
 This module contains no arithmetic: local compute goes through a backend (the CUDA context in the
 product; the tests substitute a CPU backend), collectives through torch.distributed.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -171,8 +173,10 @@ class TorchComm:
         self.side = torch.cuda.Stream(device=self.device) if self.nccl else None   # exchanges overlapped with compute (fork / join)
         self._forked = False
         # gloo (host-staged test double): no overlap, the callbacks stay NULL and every exchange is ordered on the ctx stream
-        fork = _FORK_FN(self._fork) if self.nccl else _FORK_FN()
-        join = _FORK_FN(self._join) if self.nccl else _FORK_FN()
+        # WF_COMM_NO_FORK=1: NCCL exchanges stay on the context stream (blocking in stream order; the measured alternative)
+        overlap = self.nccl and os.environ.get("WF_COMM_NO_FORK", "0") in ("", "0")
+        fork = _FORK_FN(self._fork) if overlap else _FORK_FN()
+        join = _FORK_FN(self._join) if overlap else _FORK_FN()
         self._keep = (_EXCHANGE_FN(self._exchange), _GATHER_FN(self._gather), _REDUCE_FN(self._reduce), fork, join)
         self.struct = WfComm(None, self.rank, self.world, *self._keep)
 
