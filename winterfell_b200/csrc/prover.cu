@@ -1114,11 +1114,14 @@ int composition_polys(wf_ctx* ctx, const wf_mat* comp, u32 log_n, int D, u32 kc,
 }
 int composition_commit(wf_ctx* ctx, int h, const wf_mat* comp, u32 log_n, u32 log_b, int D, u32 kc, wf_mat** polys_out,
                        wf_mat** lde_out, wf_tree** tree_out, u32 partition_words = 0) {
-    wf_mat *cpolys, *clde;
+    wf_mat *cpolys = nullptr, *clde = nullptr;
     CKI(composition_polys(ctx, comp, log_n, D, kc, &cpolys));
-    CKI(wf_mat_lde(ctx, cpolys, log_b, &clde));
-    wf_mark(ctx, "composition_lde");
-    if (tree_out) CKI(wf_commit_rows_partitioned(ctx, h, clde, partition_words, tree_out));  // sharded proofs commit their own row range
+    int r = wf_mat_lde(ctx, cpolys, log_b, &clde);
+    if (r == WF_OK) {
+        wf_mark(ctx, "composition_lde");
+        if (tree_out) r = wf_commit_rows_partitioned(ctx, h, clde, partition_words, tree_out);  // sharded proofs commit their own row range
+    }
+    if (r != WF_OK) { wf_mat_free(ctx, cpolys); wf_mat_free(ctx, clde); return r; }
     *polys_out = cpolys;
     *lde_out = clde;
     return WF_OK;
