@@ -1,7 +1,7 @@
 """Row hashing + Merkle tree throughput of every hasher (Merkle leaves/s; for the algebraic hashers
 permutations/s against the integer-pipe ceiling of their S-box arithmetic). CUDA events on the context stream, L2 flushed
 between repetitions.
-   python tools/bench_hash.py [log_rows] [cols]"""
+   python tools/bench_hash.py [log_rows] [cols] [hasher name, e.g. Rp64_256: only that one] [repetitions]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -9,6 +9,8 @@ import winterfell_b200 as wf
 
 log_rows = int(sys.argv[1]) if len(sys.argv) > 1 else 21
 cols = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+only = sys.argv[3] if len(sys.argv) > 3 else None
+reps = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 rows = 1 << log_rows
 stream = torch.cuda.Stream()
 ctx = wf.Context(0, stream.cuda_stream)
@@ -28,8 +30,10 @@ with torch.cuda.stream(stream):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     m = ctx.mat_from_host_columns(rng.integers(0, wf.P, size=(cols, rows), dtype=np.uint64))
     for h in (wf.HASH_BLAKE3_256, wf.HASH_BLAKE3_192, wf.HASH_SHA3_256, wf.HASH_RP64_256, wf.HASH_RPJIVE64_256):
+        if only and NAMES[h] != only:
+            continue
         times = []
-        for rep in range(4):
+        for rep in range(reps):
             flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
@@ -39,7 +43,7 @@ with torch.cuda.stream(stream):
             times.append(a.elapsed_time(b))
             root = bytes(t.root())
             t.free()
-        ms = min(times[1:])
+        ms = min(times[1:]) if len(times) > 1 else times[0]
         per_row, per_node = calls(h, cols)
         n_calls = rows * per_row + (rows - 1) * per_node
         print(json.dumps({"hasher": NAMES[h], "rows": rows, "cols": cols, "commit_ms": round(ms, 4),
