@@ -266,6 +266,46 @@ __device__ __forceinline__ u64 gl_mul_weak(u64 a, u64 b) {
         : "l"(a), "l"(b) GL_EPS_OPERAND);
     return r;
 }
+// a * a for any 64-bit word, weakly reduced like gl_mul_weak. Written with mul.wide so that the three partial products are
+// three IMAD.WIDE: from the mul.lo / mul.hi form ptxas builds a square out of IMAD + IMAD.HI pairs, and IMAD.HI occupies the
+// FMA-heavy pipe more than twice as long as IMAD.WIDE — ncu on the Rescue kernels (profiles/r2_rp64_kernels_summary.txt):
+// that pipe 87.5 % busy, math-pipe throttle the top stall. The cross product is doubled on the ALU pipe (46 % busy there).
+// Measured (Rp64 tree of 2^21 rows): 30.4 ms against 29.3 ms with the mul.lo / mul.hi form — the bound just moves to the ALU
+// pipe — so this form is an option (RP64_SQR_WIDE), not the default.
+__device__ __forceinline__ u64 gl_sqr_weak(u64 a) {
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 a0, a1, c0, c1, c2, c3, o0, o1, o2, k, m;\n\t"
+        ".reg .u64 w;\n\t"
+        "mov.b64 {a0, a1}, %1;\n\t"
+        "mul.wide.u32 w, a0, a0;\n\t"
+        "mov.b64 {c0, c1}, w;\n\t"
+        "mul.wide.u32 w, a1, a1;\n\t"
+        "mov.b64 {c2, c3}, w;\n\t"
+        "mul.wide.u32 w, a0, a1;\n\t"
+        "mov.b64 {o0, o1}, w;\n\t"
+        "add.cc.u32 o0, o0, o0;\n\t"          // 2 a0 a1 < 2^65
+        "addc.cc.u32 o1, o1, o1;\n\t"
+        "addc.u32 o2, 0, 0;\n\t"
+        "add.cc.u32 c1, c1, o0;\n\t"
+        "addc.cc.u32 c2, c2, o1;\n\t"
+        "addc.u32 c3, c3, o2;\n\t"
+        "sub.cc.u32 c0, c0, c3;\n\t"
+        "subc.cc.u32 c1, c1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 c0, c0, m;\n\t"
+        "subc.u32 c1, c1, 0;\n\t"
+        "mad.lo.cc.u32 c0, c2, " GL_EPSM(2) ", c0;\n\t"
+        "madc.hi.cc.u32 c1, c2, " GL_EPSM(2) ", c1;\n\t"
+        "addc.u32 k, 0, 0;\n\t"
+        "mad.lo.cc.u32 c0, k, " GL_EPSM(2) ", c0;\n\t"
+        "madc.hi.u32 c1, k, " GL_EPSM(2) ", c1;\n\t"
+        "mov.b64 %0, {c0, c1};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(a) GL_EPS_OPERAND);
+    return r;
+}
 // x * 2^K for a compile-time K < 96 and canonical x, written on the three words y = x << (K mod 32) (y2 < 2^(K mod 32)):
 //   K < 32      : (y1:y0) + (2^32 - 1) y2                      -> carry * 2^64 + r < 2p, folded as in gl_reduce128 (11 instr.)
 //   32 <= K < 64: 2^32 y0 + (2^32 - 1) y1 - y2 = ((y0:0) - y2, a borrow repaid with -(2^32 - 1)) + (2^32 - 1) y1 -> fold
@@ -332,6 +372,7 @@ GL_HD u64 gl_mul(u64 a, u64 b) {
     return gl_reduce128((u64)x, (u64)(x >> 64));
 }
 GL_HD u64 gl_mul_weak(u64 a, u64 b) { return gl_mul(a, b); }   // the host form is canonical anyway
+GL_HD u64 gl_sqr_weak(u64 a) { return gl_mul(a, a); }
 static inline void gl_butterfly(u64& a, u64& b) {
     u64 s = gl_add(a, b);
     b = gl_sub(a, b);

@@ -28,8 +28,18 @@ namespace rp64_host {
 
 // The S-box arithmetic runs on words that are only reduced below 2^64 (gl_mul_weak): every chain ends in the MDS product,
 // which takes any 64-bit words and returns canonical ones.
+#ifndef RP64_SQR_WIDE
+#define RP64_SQR_WIDE 0
+#endif
+GL_HD u64 rp64_sqr(u64 x) {
+#if RP64_SQR_WIDE
+    return gl_sqr_weak(x);
+#else
+    return gl_mul_weak(x, x);
+#endif
+}
 GL_HD u64 rp64_exp7(u64 x) {  // f64/mod.rs:96
-    u64 x2 = gl_mul_weak(x, x), x4 = gl_mul_weak(x2, x2), x3 = gl_mul_weak(x2, x);
+    u64 x2 = rp64_sqr(x), x4 = rp64_sqr(x2), x3 = gl_mul_weak(x2, x);
     return gl_mul_weak(x3, x4);
 }
 
@@ -48,15 +58,15 @@ GL_HD void rp64_inv7_group(u64* s) {
 #pragma unroll
     for (int e = 0; e < G; e++) {
         const u64 x = s[e];
-        const u64 t1 = gl_mul_weak(x, x);
-        const u64 t2 = gl_mul_weak(t1, t1);
+        const u64 t1 = rp64_sqr(x);
+        const u64 t2 = rp64_sqr(t1);
         b[e] = gl_mul_weak(gl_mul_weak(t1, t2), x);
         p[e] = t2;
         acc[e] = t2;
     }
 #define RP64_SQ(n)                                              \
     _Pragma("unroll 1") for (int i = 0; i < (n); i++) {         \
-        _Pragma("unroll") for (int e = 0; e < G; e++) acc[e] = gl_mul_weak(acc[e], acc[e]); \
+        _Pragma("unroll") for (int e = 0; e < G; e++) acc[e] = rp64_sqr(acc[e]); \
     }
     RP64_SQ(3)
 #pragma unroll
@@ -74,9 +84,9 @@ GL_HD void rp64_inv7_group(u64* s) {
 #pragma unroll
     for (int e = 0; e < G; e++) {
         u64 a = gl_mul_weak(acc[e], p[e]);                                                          // t7
-        a = gl_mul_weak(gl_mul_weak(a, a), p[e]);
-        a = gl_mul_weak(a, a);
-        a = gl_mul_weak(a, a);
+        a = gl_mul_weak(rp64_sqr(a), p[e]);
+        a = rp64_sqr(a);
+        a = rp64_sqr(a);
         s[e] = gl_mul_weak(a, b[e]);
     }
 #undef RP64_SQ
