@@ -321,6 +321,11 @@ int wf_prove_fib_sharded(wf_ctx* ctx, const wf_comm* comm, const uint64_t* const
 int wf_ctx_set_jit(wf_ctx* ctx, int on);
 int wf_ctx_jit_stats(wf_ctx* ctx, uint64_t* compiled, uint64_t* cache_hits, uint64_t* fallbacks);
 int wf_jit_compile_air(const uint64_t* air_desc, size_t air_desc_len, uint32_t ext, size_t* cubin_bytes, char* log, size_t log_cap);
+/* Everything wf_prove_air / wf_eval_constraints check about a description before they touch the device, without a device:
+ * structure, degrees against the blowup factor, periodic columns, assertion validity and overlaps (the conditions
+ * Air::new, BoundaryConstraints::new and prepare_assertions panic on, air/src/air/boundary/mod.rs:190-215). WF_OK, or
+ * WF_ERR_INVALID with the reason in msg. */
+int wf_air_check(const uint64_t* air_desc, size_t air_desc_len, uint32_t log_n, uint32_t blowup, char* msg, size_t msg_cap);
 
 /* ---- plain kernels on caller-owned DEVICE buffers (unit parity + bench legs) ------------------- */
 /* in-place NTT (inverse=0) / iNTT (inverse=1) of `cols` columns, column-major [cols][n], n = 1 << log_n */

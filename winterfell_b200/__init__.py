@@ -96,6 +96,7 @@ _SIGS = [
     ("wf_ctx_set_jit", C.c_int, [vp, C.c_int]),
     ("wf_ctx_jit_stats", C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("wf_jit_compile_air", C.c_int, [u64p, C.c_size_t, C.c_uint32, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]),
+    ("wf_air_check", C.c_int, [u64p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t]),
     ("wf_host_hash_elements", C.c_int, [C.c_int, u64p, C.c_size_t, u8p]),
     ("wf_host_merge", C.c_int, [C.c_int, u8p, u8p]),
     ("wf_host_merge_with_int", C.c_int, [C.c_int, u8p, C.c_uint64, u8p]),
@@ -598,6 +599,14 @@ def host_merge_with_int(hash_id, seed, value):
     o = np.zeros(32, dtype=np.uint8)
     lib().wf_host_merge_with_int(hash_id, tp, value, o.ctypes.data_as(u8p))
     return o.tobytes()
+
+
+def air_check(desc, log_n, blowup):
+    """The checks the proving entry points run on an AIR description, without a device. Returns (status, reason)."""
+    d_, dp = _u64(desc)
+    msg = C.create_string_buffer(512)
+    rc = lib().wf_air_check(dp, d_.size, log_n, blowup, msg, 512)
+    return rc, msg.value.decode(errors="replace")
 
 
 def jit_compile_air(desc, ext):

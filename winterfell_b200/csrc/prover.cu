@@ -2097,6 +2097,29 @@ extern "C" int wf_jit_compile_air(const uint64_t* air_desc, size_t air_desc_len,
     return rc == 0 ? WF_OK : WF_ERR_UNSUPPORTED;
 }
 
+// The checks wf_prove_air / wf_eval_constraints run on an AIR description before touching the device, without a device:
+// structure of the description, degrees against the blowup factor, periodic columns, assertion validity and overlaps
+// (the panics of Air::new / BoundaryConstraints::new / prepare_assertions in the reference, returned as a status).
+extern "C" int wf_air_check(const uint64_t* air_desc, size_t air_desc_len, uint32_t log_n, uint32_t blowup, char* msg, size_t msg_cap) {
+    auto say = [&](const char* t) { if (msg && msg_cap) { strncpy(msg, t, msg_cap - 1); msg[msg_cap - 1] = 0; } };
+    say("");
+    if (!air_desc || log_n < 3 || log_n > 32 || blowup < 2 || blowup > 128 || (blowup & (blowup - 1))) { say("bad arguments"); return WF_ERR_INVALID; }
+    AirHost air;
+    if (!parse_air_host(air_desc, air_desc_len, air)) { say("malformed AIR description"); return WF_ERR_INVALID; }
+    wf_ctx note{};   // carries the message of the shared validators, nothing else
+    u32 log_b = 0;
+    while ((1u << log_b) < blowup) log_b++;
+    const size_t n = (size_t)1 << log_n;
+    int r = WF_OK;
+    if (air.log_ce_blowup() > log_b) r = wf_fail(&note, WF_ERR_INVALID, "blowup factor too small for the constraint degrees");
+    for (auto& col : air.periodic) if (r == WF_OK && col.size() > n) r = wf_fail(&note, WF_ERR_INVALID, "periodic column longer than the trace");
+    if (r == WF_OK) r = validate_degrees(&note, air.all_degrees(), n);
+    if (r == WF_OK) r = validate_assertions(&note, air.aux_asserts, n, 3, "aux assertion");
+    if (r == WF_OK) r = validate_assertions(&note, air.asserts, n, 1, "assertion");
+    say(note.err.c_str());
+    return r;
+}
+
 // ---- stepwise exports: the seams of prover/src/lib.rs:125-223 (ConstraintEvaluator, ConstraintCommitment)
 //      and the concrete steps between them, for a host that keeps the transcript itself ----------------
 template <int D>
