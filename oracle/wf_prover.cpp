@@ -911,6 +911,20 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
     o.rem_max_deg = r.u8_(); o.batch_c = r.u8_(); o.batch_d = r.u8_(); o.num_partitions = r.u8_(); o.hash_rate = r.u8_();
     u64 ncons = r.usize();
     if (!r.ok) return V_MALFORMED;
+    // what deserialisation refuses in the reference: ProofOptions::new / with_partitions assert these ranges
+    // (air/src/options.rs:143-172, :410-417), FieldExtension / BatchingMethod::read_from accept 1..=3 / 0..=2,
+    // TraceInfo::read_from needs 2^logn >= 8 (trace_info.rs MIN_TRACE_LENGTH) and the LDE domain must fit the field's
+    // two-adicity (2^32 for f64, get_root_of_unity)
+    auto pow2 = [](u64 v) { return v && !(v & (v - 1)); };
+    if (o.num_queries == 0 || !pow2(o.blowup) || o.blowup < 2 || o.blowup > 128 || o.grinding > 32 || !pow2(o.folding) || o.folding < 2 ||
+        o.folding > 16 || !pow2((u64)o.rem_max_deg + 1) || o.batch_c > 2 || o.batch_d > 2 || o.num_partitions < 1 || o.num_partitions > 16 ||
+        o.hash_rate < 1)
+        return V_MALFORMED;
+    {
+        u32 lb = 0;
+        while ((1u << lb) < o.blowup) lb++;
+        if (logn < 3 || logn + lb > 32) return V_MALFORMED;
+    }
     air.o = o;
     air.n = (size_t)1 << logn;
     if (air.asserts.empty() && air.w > 0) {  // FibSmall x k entry point: assertions reference step n - 1
@@ -960,7 +974,7 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
         u64 pl = r.le(4); const u8* p2 = r.take(pl); if (!r.ok) return V_MALFORMED; fp[i].assign(p2, p2 + pl);
     }
     u64 reml = r.le(2); const u8* rem = r.take(reml);
-    r.u8_();
+    const u8 fri_log_parts = r.u8_();   // FriProof::num_partitions, stored as a power of two (fri/src/proof.rs:36,101-103)
     u64 nonce = r.le(8);
     if (!r.ok || r.pos != len || reml % (8 * d)) return V_MALFORMED;
 
@@ -1086,6 +1100,15 @@ static int verify_fib(const u8* proof, size_t len, FibAir air /* options + resul
         for (size_t depth = 0; depth < nlayers; depth++) {
             std::vector<u64> fpos(positions.size());
             fpos.resize(fold_positions(positions.data(), positions.size(), dom, nf, fpos.data()));
+            // map_positions_to_indexes (fri/src/utils.rs:9-33): with P = 2^fri_log_parts > 1 partitions the verifier looks the
+            // folded positions up at index (p mod P) (target / P) + (p - p mod P) / P of the layer commitment. The prover this
+            // oracle restates commits every layer in domain order (P = 1): any other index set cannot open that commitment.
+            if (fri_log_parts) {
+                if (fri_log_parts >= 32) return V_MALFORMED;
+                const u64 P_ = (u64)1 << fri_log_parts, target = dom / nf, psize = target / P_;
+                for (u64 p : fpos)
+                    if ((p % P_) * psize + (p - p % P_) / P_ != p) return V_FRI_LAYER;
+            }
             const std::vector<u8>& vals = fv[depth];
             if (vals.size() != fpos.size() * nf * d * 8) return V_FRI_LAYER;
             std::vector<std::array<u8, 32>> lv(fpos.size());
