@@ -22,6 +22,16 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in L.wf_version()
 
 
+def test_library_exports_nothing_but_the_c_abi():
+    # winterfell_b200/exports.map: kernels' host stubs, C++ helpers and template instantiations stay local to the library
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", wf.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    names = [l.split()[-1] for l in out.splitlines() if l.strip()]
+    hdr = open(os.path.join(ROOT, "include", "winterfell_b200.h")).read()
+    declared = set(re.findall(r"\b(wf_[a-z0-9_]+)\s*\(", hdr)) - {"wf_fri_commit_fn", "wf_fri_draw_fn"}
+    assert names and set(names) == declared, sorted(set(names) ^ declared)
+
+
 def test_no_gpu_means_error_not_fallback():
     import torch
     if torch.cuda.is_available():

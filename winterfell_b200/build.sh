@@ -25,7 +25,7 @@ for f in ntt ntt2 commit fri layout capi prover jit ${EXTRA_SRCS}; do
 done
 for p in "${pids[@]}"; do wait $p; done
 # linked beside its final place and renamed: a reader (or a snapshot of the tree) never sees a half-written library
-$NVCC -Wno-deprecated-gpu-targets -shared -o _build/libwinterfell_b200.so.new _build/*.o -lcudart -ldl -ccbin /usr/bin/g++
+$NVCC -Wno-deprecated-gpu-targets -shared -Xlinker --version-script=exports.map -o _build/libwinterfell_b200.so.new _build/*.o -lcudart -ldl -ccbin /usr/bin/g++
 mv -f _build/libwinterfell_b200.so.new libwinterfell_b200.so
 echo "built $(pwd)/libwinterfell_b200.so"
 # the C++ mirror of the reference's plugin interface (include/winterfell_b200.hpp) + its driver: plain
