@@ -814,7 +814,7 @@ struct BatchProof { u8 depth; std::vector<std::vector<std::array<u8, 32>>> nodes
 static bool read_batch_proof(Reader& r, BatchProof& bp, size_t dlen = 32) {
     bp.depth = r.u8_();
     u64 nv = r.usize();
-    if (!r.ok || nv > 100000) return false;
+    if (!r.ok || nv > 100000 || bp.depth < 1 || bp.depth > 40) return false;   // a tree of 2^depth leaves; callers shift by it
     bp.nodes.resize(nv);
     for (auto& v : bp.nodes) {
         u64 ln = r.usize();
