@@ -217,6 +217,40 @@ def fri_algorithmic_bytes(N, d):
     return total
 
 
+def sharded_records(bd, log_n, pairs, world, hbm, peak_src, sm_mhz=None):
+    """Roofline and throughput keys of an N > 1 line (one proof sharded over `world` GPUs) from rank 0's stage times. The
+    `trace_lde` stage covers this rank's column block: layout, interpolation, extension of every coset (the copy-engine
+    pushes of the finished cosets run under it). Per-GPU algorithmic bytes 8n(2+b) x cols / world; the aggregate is what
+    BASELINE's "NTT Gelem/s at 1/2/4/8 GPUs" asks for."""
+    n_, cols_ = 1 << log_n, 2 * pairs
+    N = n_ << LOG_BLOWUP
+    alg = 8.0 * n_ * (2 + (1 << LOG_BLOWUP)) * cols_ / world
+    t = bd["trace_lde"] * 1e-3
+    ach = alg / t / 1e9
+    alu = None
+    try:  # the ALU-pipe roofline of the instruction mix (profiles/ntt_alu_model.json), per GPU
+        m = json.load(open(os.path.join(ROOT, "profiles", "ntt_alu_model.json")))
+        per = m["alu_instr_per_element_pass"]
+        mean_instr = (per["contiguous_2p11"] + per["strided_2p11"]) / 2.0
+        ceil_passes = m["sms"] * m["alu_lanes_per_clk_per_sm"] * (sm_mhz or 1965) * 1e6 / mean_instr
+        passes = 2.0 * (n_ + N) * cols_ / world / t
+        alu = {"bound": "alu_pipe", "achieved": round(passes / 1e9, 2), "peak": round(ceil_passes / 1e9, 2), "unit": "G element-passes/s per GPU",
+               "frac": round(passes / ceil_passes, 4), "alu_instr_per_element_pass": mean_instr, "sm_mhz": sm_mhz or 1965}
+    except Exception:
+        pass
+    out = {"roofline": {"bound": "hbm", "kernel": "ntt_pass (per GPU: layout + interpolate + LDE of this rank's column block, the exchange of the "
+                                                  "finished cosets running under it on the copy engines)",
+                        "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s", "alu_pipe": alu, "frac": round(ach / hbm, 4), "traffic": None,
+                        "peak_source": peak_src, "algorithmic_bytes": int(alg), "kernel_ms": round(bd["trace_lde"], 4),
+                        "aggregate_GBps": round(ach * world, 1),
+                        "note": "rank 0's stage time; includes the segment layout kernel; integer-ALU-bound (DESIGN.md 4)"},
+           "ntt_gelem_per_s": round(N * cols_ / t / 1e9, 3),
+           "merkle_leaves_per_s": round(N / (bd["trace_commit"] * 1e-3), 1) if bd.get("trace_commit") else None,
+           "lde_commit_fri_ms": round(sum(bd.get(k, 0.0) for k in ("trace_lde", "trace_exchange", "trace_commit", "composition_lde",
+                                                                     "composition_commit", "fri_layers")), 4)}
+    return out
+
+
 def rooflines(breakdown, cfg, hbm, peak_src, compress_gps, sm_mhz=None):
     pairs, log_n, ext = CONFIGS[cfg]
     n, cols = 1 << log_n, 2 * pairs
@@ -476,23 +510,7 @@ def main():
             line["ntt_gelem_per_s"] = round(rl[0]["elements_per_s"] / 1e9, 3)
             line["merkle_leaves_per_s"] = rl[1]["leaves_per_s"]
         elif "trace_lde" in bd and world > 1:
-            # sharded proof: the stage covers this rank's column block (layout, interpolate, extend; the last pass stores the rows
-            # into their owners' shards). Per-GPU algorithmic bytes 8n(2+b) x cols / N; the aggregate is what BASELINE's
-            # "NTT Gelem/s at 1/2/4/8 GPUs" asks for (max over ranks is not taken for stage times: rank 0's events)
-            n_, cols_ = 1 << log_n, 2 * pairs
-            alg = 8.0 * n_ * (2 + (1 << LOG_BLOWUP)) * cols_ / world
-            t = bd["trace_lde"] * 1e-3
-            ach = alg / t / 1e9
-            line["roofline"] = {"bound": "hbm", "kernel": "ntt_pass (per GPU: layout + interpolate + LDE of this rank's column block; the last pass stores "
-                                                          "each row into its owner's shard over NVLink)",
-                                "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": None,
-                                "peak_source": peak_src, "algorithmic_bytes": int(alg), "kernel_ms": round(bd["trace_lde"], 4),
-                                "aggregate_GBps": round(ach * world, 1),
-                                "note": "rank 0's stage time; includes the segment layout kernel; integer-ALU-bound (DESIGN.md 4)"}
-            line["ntt_gelem_per_s"] = round(N * cols_ / t / 1e9, 3)
-            line["merkle_leaves_per_s"] = round(N / (bd["trace_commit"] * 1e-3), 1) if bd.get("trace_commit") else None
-            line["lde_commit_fri_ms"] = round(sum(bd.get(k, 0.0) for k in ("trace_lde", "trace_exchange", "trace_commit", "composition_lde",
-                                                                                "composition_commit", "fri_layers")), 4)
+            line.update(sharded_records(bd, log_n, pairs, world, hbm, peak_src, (main_rec.get("clocks") or {}).get("sm_mhz")))
         for k in ("comm", "roofline", "ntt_gelem_per_s", "merkle_leaves_per_s", "lde_commit_fri_ms"):
             if k in main_rec:
                 line[k] = main_rec[k]

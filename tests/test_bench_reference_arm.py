@@ -51,3 +51,18 @@ def test_reference_arm_under_torchrun_only_rank0_works():
     assert r.returncode == 0, r.stderr[-2000:]
     d = _line(r.stdout)                                                   # exactly one line: rank 1 printed nothing
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["scaling"] == "strong" and d["steps"] == 1
+
+
+def test_sharded_line_helper_reproduces_the_recorded_8gpu_keys():
+    # bench.sharded_records builds the roofline / throughput keys of an N > 1 line from rank 0's stage times: fed with the
+    # stage times of the committed 8-GPU line it must give that line's own numbers (and the ALU-pipe roofline beside them)
+    sys.path.insert(0, ROOT)
+    import bench
+    d = json.loads([l for l in open(os.path.join(ROOT, "profiles", "r2_bench_line_8gpu.json")) if l.startswith("{")][0])
+    r = bench.sharded_records(d["stage_ms"], 22, 32, 8, d["roofline"]["peak"], d["roofline"]["peak_source"], d["clocks"]["sm_mhz"])
+    assert r["ntt_gelem_per_s"] == d["ntt_gelem_per_s"] and r["lde_commit_fri_ms"] == d["lde_commit_fri_ms"]
+    assert r["merkle_leaves_per_s"] == d["merkle_leaves_per_s"]
+    for k in ("achieved", "frac", "algorithmic_bytes", "kernel_ms", "aggregate_GBps"):
+        assert r["roofline"][k] == d["roofline"][k], k
+    alu = r["roofline"]["alu_pipe"]
+    assert alu["bound"] == "alu_pipe" and 0.3 < alu["frac"] < 1.0
